@@ -1,0 +1,337 @@
+/*
+ * fake_gpu.c — a deterministic, GPU-less stand-in for libcuda.so.1 AND libnvidia-ml.so.1.
+ *
+ * TEST INFRASTRUCTURE ONLY (oracle/): lets the *reference binary* lib/nvidia/libvgpu.so and the
+ * new libvgpu.so run their accounting/limit logic on a CPU-only box, on the same driver-API
+ * trace, so their shared-region counters and return codes can be compared word for word
+ * (SURVEY.md §8c "CPU-only execution", Appendix D = the entry points the reference calls).
+ * Nothing under k8s-device-plugin_b200/ links or loads this file.
+ *
+ * One ELF object provides both libraries; oracle/Makefile installs it as
+ * oracle/_ref/fake/libcuda.so.1 plus a symlink libnvidia-ml.so.1 -> libcuda.so.1, so glibc
+ * loads ONE instance (same inode) and the cu* and nvml* halves share state (NVML's process
+ * list reflects the fake primary context — needed by the reference's set_task_pid,
+ * libvgpu.so@0x16a7f).
+ *
+ * Behaviour knobs (env): FAKE_GPU_COUNT (1), FAKE_GPU_TOTAL_MIB (183359 = B200),
+ * FAKE_GPU_CTX_MIB (512: bytes NVML reports for a process with a primary context),
+ * FAKE_GPU_SM_UTIL (0: smUtil returned by nvmlDeviceGetProcessUtilization),
+ * FAKE_GPU_LOG (unset: silent).
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/time.h>
+#include <unistd.h>
+
+typedef int CUresult;
+typedef int CUdevice;
+typedef unsigned long long CUdeviceptr;
+typedef void *CUcontext;
+typedef void *CUstream;
+typedef void *CUfunction;
+typedef void *CUmodule;
+typedef void *CUevent;
+typedef struct { unsigned char bytes[16]; } CUuuid;
+
+#define CUDA_SUCCESS 0
+#define CUDA_ERROR_INVALID_VALUE 1
+#define CUDA_ERROR_OUT_OF_MEMORY 2
+#define CUDA_ERROR_NOT_INITIALIZED 3
+#define CUDA_ERROR_INVALID_DEVICE 101
+#define CUDA_ERROR_INVALID_CONTEXT 201
+#define CUDA_ERROR_NOT_FOUND 500
+#define CUDA_ERROR_NOT_SUPPORTED 801
+
+#define MAXDEV 16
+#define EXPORT __attribute__((visibility("default")))
+
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static int g_inited, g_ndev = 1, g_log;
+static uint64_t g_total = 183359ull << 20, g_ctx_bytes = 512ull << 20;
+static unsigned g_sm_util;
+static uint64_t g_used[MAXDEV];
+static int g_ctx_refs[MAXDEV];
+static int g_ctx_obj[MAXDEV]; /* address of g_ctx_obj[d] is the CUcontext of device d */
+static __thread CUcontext t_cur;
+static uint64_t g_next_va = 0x7f4000000000ull;
+static uint64_t g_launches;
+
+/* live allocations: open-addressing table keyed by base address */
+#define HCAP (1u << 20)
+static struct { uint64_t base, size; int dev; int live; } *g_h;
+
+static void fake_init(void) {
+    if (g_inited) return;
+    const char *e;
+    if ((e = getenv("FAKE_GPU_COUNT"))) g_ndev = atoi(e);
+    if (g_ndev < 1) g_ndev = 1;
+    if (g_ndev > MAXDEV) g_ndev = MAXDEV;
+    if ((e = getenv("FAKE_GPU_TOTAL_MIB"))) g_total = strtoull(e, 0, 0) << 20;
+    if ((e = getenv("FAKE_GPU_CTX_MIB"))) g_ctx_bytes = strtoull(e, 0, 0) << 20;
+    if ((e = getenv("FAKE_GPU_SM_UTIL"))) g_sm_util = (unsigned)atoi(e);
+    g_log = getenv("FAKE_GPU_LOG") != NULL;
+    g_h = calloc(HCAP, sizeof(*g_h));
+    g_inited = 1;
+}
+#define LOGF(...) do { if (g_log) { fprintf(stderr, "[fake_gpu] " __VA_ARGS__); fputc('\n', stderr); } } while (0)
+
+static int cur_dev(void) {
+    if (!t_cur) return -1;
+    return (int)((int *)t_cur - g_ctx_obj);
+}
+
+static unsigned hslot(uint64_t base) { return (unsigned)((base >> 9) * 0x9E3779B97F4A7C15ull >> 44) & (HCAP - 1); }
+
+static CUresult do_alloc(CUdeviceptr *dptr, size_t size) {
+    fake_init();
+    int d = cur_dev();
+    if (d < 0) return CUDA_ERROR_INVALID_CONTEXT;
+    if (!dptr || size == 0) return CUDA_ERROR_INVALID_VALUE;
+    pthread_mutex_lock(&g_mu);
+    if (g_used[d] + size > g_total) { pthread_mutex_unlock(&g_mu); return CUDA_ERROR_OUT_OF_MEMORY; }
+    uint64_t base = g_next_va;
+    g_next_va += (size + 511) & ~511ull;
+    unsigned s = hslot(base);
+    while (g_h[s].live) s = (s + 1) & (HCAP - 1);
+    g_h[s].base = base; g_h[s].size = size; g_h[s].dev = d; g_h[s].live = 1;
+    g_used[d] += size;
+    pthread_mutex_unlock(&g_mu);
+    *dptr = base;
+    return CUDA_SUCCESS;
+}
+
+static CUresult do_free(CUdeviceptr p) {
+    fake_init();
+    if (!p) return CUDA_SUCCESS;
+    pthread_mutex_lock(&g_mu);
+    unsigned s = hslot(p);
+    for (unsigned n = 0; n < HCAP; n++, s = (s + 1) & (HCAP - 1)) {
+        if (!g_h[s].live && g_h[s].base == 0) break;
+        if (g_h[s].live && g_h[s].base == p) {
+            g_h[s].live = 0; /* tombstone keeps base != 0 so probing continues */
+            g_used[g_h[s].dev] -= g_h[s].size;
+            pthread_mutex_unlock(&g_mu);
+            return CUDA_SUCCESS;
+        }
+    }
+    pthread_mutex_unlock(&g_mu);
+    return CUDA_ERROR_INVALID_VALUE;
+}
+
+/* ------------------------------------------------------------------ CUDA driver half */
+EXPORT CUresult cuInit(unsigned flags) { (void)flags; fake_init(); LOGF("cuInit"); return CUDA_SUCCESS; }
+EXPORT CUresult cuDriverGetVersion(int *v) { *v = 12090; return CUDA_SUCCESS; }
+EXPORT CUresult cuDeviceGetCount(int *c) { fake_init(); *c = g_ndev; return CUDA_SUCCESS; }
+EXPORT CUresult cuDeviceGet(CUdevice *d, int ord) { fake_init(); if (ord < 0 || ord >= g_ndev) return CUDA_ERROR_INVALID_DEVICE; *d = ord; return CUDA_SUCCESS; }
+EXPORT CUresult cuDeviceGetName(char *name, int len, CUdevice d) { (void)d; snprintf(name, (size_t)len, "NVIDIA B200 (fake)"); return CUDA_SUCCESS; }
+EXPORT CUresult cuDeviceGetAttribute(int *pi, int attrib, CUdevice d) {
+    (void)d;
+    switch (attrib) {
+    case 16: *pi = 148; break;          /* MULTIPROCESSOR_COUNT */
+    case 39: *pi = 2048; break;         /* MAX_THREADS_PER_MULTIPROCESSOR */
+    case 75: *pi = 10; break;           /* COMPUTE_CAPABILITY_MAJOR */
+    case 76: *pi = 0; break;            /* COMPUTE_CAPABILITY_MINOR */
+    case 33: *pi = 0x1b + d; break;     /* PCI_BUS_ID */
+    case 34: *pi = 0; break;            /* PCI_DEVICE_ID */
+    case 50: *pi = 0; break;            /* PCI_DOMAIN_ID */
+    case 1: *pi = 1024; break;          /* MAX_THREADS_PER_BLOCK */
+    default: *pi = 0; break;
+    }
+    return CUDA_SUCCESS;
+}
+static void fill_uuid(unsigned char *b, int d) { for (int i = 0; i < 16; i++) b[i] = (unsigned char)(0xB2 ^ (i * 17) ^ d); b[15] = (unsigned char)d; }
+EXPORT CUresult cuDeviceGetUuid(CUuuid *u, CUdevice d) { fill_uuid(u->bytes, d); return CUDA_SUCCESS; }
+EXPORT CUresult cuDeviceGetUuid_v2(CUuuid *u, CUdevice d) { fill_uuid(u->bytes, d); return CUDA_SUCCESS; }
+EXPORT CUresult cuDeviceGetPCIBusId(char *s, int len, CUdevice d) { snprintf(s, (size_t)len, "00000000:%02X:00.0", 0x1b + d); return CUDA_SUCCESS; }
+EXPORT CUresult cuDeviceGetByPCIBusId(CUdevice *d, const char *s) { unsigned dom, bus; if (sscanf(s, "%x:%x", &dom, &bus) == 2) { *d = (int)bus - 0x1b; return CUDA_SUCCESS; } return CUDA_ERROR_INVALID_VALUE; }
+EXPORT CUresult cuDeviceTotalMem_v2(size_t *bytes, CUdevice d) { (void)d; fake_init(); *bytes = g_total; return CUDA_SUCCESS; }
+EXPORT CUresult cuDeviceTotalMem(size_t *bytes, CUdevice d) { return cuDeviceTotalMem_v2(bytes, d); }
+EXPORT CUresult cuDeviceComputeCapability(int *maj, int *min, CUdevice d) { (void)d; *maj = 10; *min = 0; return CUDA_SUCCESS; }
+
+EXPORT CUresult cuDevicePrimaryCtxRetain(CUcontext *ctx, CUdevice d) {
+    fake_init();
+    if (d < 0 || d >= g_ndev) return CUDA_ERROR_INVALID_DEVICE;
+    pthread_mutex_lock(&g_mu); g_ctx_refs[d]++; pthread_mutex_unlock(&g_mu);
+    *ctx = &g_ctx_obj[d];
+    LOGF("primary ctx retain dev %d", d);
+    return CUDA_SUCCESS;
+}
+EXPORT CUresult cuDevicePrimaryCtxRelease_v2(CUdevice d) { pthread_mutex_lock(&g_mu); if (g_ctx_refs[d] > 0) g_ctx_refs[d]--; pthread_mutex_unlock(&g_mu); return CUDA_SUCCESS; }
+EXPORT CUresult cuDevicePrimaryCtxRelease(CUdevice d) { return cuDevicePrimaryCtxRelease_v2(d); }
+EXPORT CUresult cuDevicePrimaryCtxGetState(CUdevice d, unsigned *flags, int *active) { if (flags) *flags = 0; if (active) *active = g_ctx_refs[d] > 0; return CUDA_SUCCESS; }
+EXPORT CUresult cuDevicePrimaryCtxSetFlags_v2(CUdevice d, unsigned f) { (void)d; (void)f; return CUDA_SUCCESS; }
+EXPORT CUresult cuDevicePrimaryCtxReset_v2(CUdevice d) { (void)d; return CUDA_SUCCESS; }
+EXPORT CUresult cuCtxCreate_v2(CUcontext *ctx, unsigned flags, CUdevice d) { (void)flags; CUresult r = cuDevicePrimaryCtxRetain(ctx, d); if (!r) t_cur = *ctx; return r; }
+EXPORT CUresult cuCtxDestroy_v2(CUcontext ctx) { (void)ctx; return CUDA_SUCCESS; }
+EXPORT CUresult cuCtxSetCurrent(CUcontext ctx) { t_cur = ctx; return CUDA_SUCCESS; }
+EXPORT CUresult cuCtxGetCurrent(CUcontext *ctx) { *ctx = t_cur; return CUDA_SUCCESS; }
+EXPORT CUresult cuCtxPushCurrent_v2(CUcontext ctx) { t_cur = ctx; return CUDA_SUCCESS; }
+EXPORT CUresult cuCtxPopCurrent_v2(CUcontext *ctx) { if (ctx) *ctx = t_cur; return CUDA_SUCCESS; }
+EXPORT CUresult cuCtxGetDevice(CUdevice *d) { int c = cur_dev(); if (c < 0) return CUDA_ERROR_INVALID_CONTEXT; *d = c; return CUDA_SUCCESS; }
+EXPORT CUresult cuCtxSynchronize(void) { return CUDA_SUCCESS; }
+EXPORT CUresult cuCtxGetApiVersion(CUcontext c, unsigned *v) { (void)c; *v = 12090; return CUDA_SUCCESS; }
+
+EXPORT CUresult cuMemAlloc_v2(CUdeviceptr *p, size_t n) { return do_alloc(p, n); }
+EXPORT CUresult cuMemAllocManaged(CUdeviceptr *p, size_t n, unsigned flags) { (void)flags; return do_alloc(p, n); }
+EXPORT CUresult cuMemAllocPitch_v2(CUdeviceptr *p, size_t *pitch, size_t w, size_t h, unsigned elem) {
+    (void)elem; size_t pt = (w + 511) & ~(size_t)511; if (pitch) *pitch = pt; return do_alloc(p, pt * h);
+}
+EXPORT CUresult cuMemFree_v2(CUdeviceptr p) { return do_free(p); }
+EXPORT CUresult cuMemGetInfo_v2(size_t *fr, size_t *tot) {
+    fake_init(); int d = cur_dev(); if (d < 0) return CUDA_ERROR_INVALID_CONTEXT;
+    *tot = g_total; *fr = g_total - g_used[d]; return CUDA_SUCCESS;
+}
+EXPORT CUresult cuMemHostAlloc(void **pp, size_t n, unsigned f) { (void)f; *pp = malloc(n); return *pp ? 0 : CUDA_ERROR_OUT_OF_MEMORY; }
+EXPORT CUresult cuMemAllocHost_v2(void **pp, size_t n) { *pp = malloc(n); return *pp ? 0 : CUDA_ERROR_OUT_OF_MEMORY; }
+EXPORT CUresult cuMemFreeHost(void *p) { free(p); return CUDA_SUCCESS; }
+EXPORT CUresult cuMemGetAddressRange_v2(CUdeviceptr *base, size_t *size, CUdeviceptr p) {
+    CUresult r = CUDA_ERROR_INVALID_VALUE;
+    pthread_mutex_lock(&g_mu);
+    for (unsigned s = 0; s < HCAP; s++) if (g_h && g_h[s].live && p >= g_h[s].base && p < g_h[s].base + g_h[s].size) {
+        if (base) *base = g_h[s].base;
+        if (size) *size = g_h[s].size;
+        r = CUDA_SUCCESS; break; }
+    pthread_mutex_unlock(&g_mu);
+    return r;
+}
+
+EXPORT CUresult cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
+                               unsigned smem, CUstream st, void **params, void **extra) {
+    (void)f; (void)gx; (void)gy; (void)gz; (void)bx; (void)by; (void)bz; (void)smem; (void)st; (void)params; (void)extra;
+    __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
+    return CUDA_SUCCESS;
+}
+static int g_mod_obj, g_fn_obj;
+EXPORT CUresult cuModuleLoadData(CUmodule *m, const void *img) { (void)img; *m = &g_mod_obj; return CUDA_SUCCESS; }
+EXPORT CUresult cuModuleLoadDataEx(CUmodule *m, const void *img, unsigned n, void *o, void **v) { (void)img; (void)n; (void)o; (void)v; *m = &g_mod_obj; return CUDA_SUCCESS; }
+EXPORT CUresult cuModuleGetFunction(CUfunction *f, CUmodule m, const char *name) { (void)m; (void)name; *f = &g_fn_obj; return CUDA_SUCCESS; }
+EXPORT CUresult cuModuleUnload(CUmodule m) { (void)m; return CUDA_SUCCESS; }
+EXPORT CUresult cuStreamCreate(CUstream *s, unsigned f) { (void)f; *s = &g_mod_obj; return CUDA_SUCCESS; }
+EXPORT CUresult cuStreamDestroy_v2(CUstream s) { (void)s; return CUDA_SUCCESS; }
+EXPORT CUresult cuStreamSynchronize(CUstream s) { (void)s; return CUDA_SUCCESS; }
+EXPORT CUresult cuGetErrorString(CUresult e, const char **s) { (void)e; *s = "fake"; return CUDA_SUCCESS; }
+EXPORT CUresult cuGetErrorName(CUresult e, const char **s) { (void)e; *s = "FAKE"; return CUDA_SUCCESS; }
+/* The reference patches slots 2 and 6 of the cudart-interface export table in place (libvgpu.so@0x3f858-0x3f8fd)
+ * and copies slots 0..2 of a second one (@0x3f8ff): hand back writable tables of inert entries. */
+static CUresult export_stub(void) { return CUDA_ERROR_NOT_SUPPORTED; }
+static void *g_export_tbl[4][16] __attribute__((aligned(4096)));
+EXPORT CUresult cuGetExportTable(const void **tbl, const CUuuid *id) {
+    if (!tbl || !id) return CUDA_ERROR_INVALID_VALUE;
+    unsigned k = id->bytes[0] & 3u;
+    g_export_tbl[k][0] = (void *)(uintptr_t)(16 * sizeof(void *));
+    for (int i = 1; i < 16; i++) if (!g_export_tbl[k][i]) g_export_tbl[k][i] = (void *)export_stub;
+    *tbl = g_export_tbl[k];
+    return CUDA_SUCCESS;
+}
+EXPORT CUresult cuArray3DGetDescriptor_v2(void *d, void *a) { (void)d; (void)a; return CUDA_ERROR_NOT_SUPPORTED; }
+EXPORT CUresult cuMemAddressFree(CUdeviceptr p, size_t n) { (void)p; (void)n; return CUDA_SUCCESS; }
+EXPORT CUresult cuMemRelease(unsigned long long h) { (void)h; return CUDA_SUCCESS; }
+EXPORT CUresult cuMemSetAccess(CUdeviceptr p, size_t n, const void *d, size_t c) { (void)p; (void)n; (void)d; (void)c; return CUDA_SUCCESS; }
+EXPORT CUresult cuMemUnmap(CUdeviceptr p, size_t n) { (void)p; (void)n; return CUDA_SUCCESS; }
+
+/* test hook: number of kernel launches that reached the "hardware" */
+EXPORT uint64_t fake_gpu_launch_count(void) { return g_launches; }
+EXPORT uint64_t fake_gpu_used_bytes(int d) { return g_used[d]; }
+
+static void *self_sym(const char *name) {
+    static void *self;
+    if (!self) { Dl_info di; if (dladdr((void *)&cuInit, &di)) self = dlopen(di.dli_fname, RTLD_NOW | RTLD_NOLOAD); }
+    return self ? dlsym(self, name) : NULL;
+}
+static CUresult proc_addr(const char *sym, void **pfn) {
+    char buf[160];
+    void *p = NULL;
+    snprintf(buf, sizeof buf, "%s_v3", sym); p = self_sym(buf);
+    if (!p) { snprintf(buf, sizeof buf, "%s_v2", sym); p = self_sym(buf); }
+    if (!p) p = self_sym(sym);
+    *pfn = p;
+    return p ? CUDA_SUCCESS : CUDA_ERROR_NOT_FOUND;
+}
+EXPORT CUresult cuGetProcAddress(const char *sym, void **pfn, int ver, uint64_t flags) { (void)ver; (void)flags; return proc_addr(sym, pfn); }
+EXPORT CUresult cuGetProcAddress_v2(const char *sym, void **pfn, int ver, uint64_t flags, int *status) {
+    (void)ver; (void)flags; CUresult r = proc_addr(sym, pfn); if (status) *status = r ? 1 : 0; return CUDA_SUCCESS;
+}
+
+/* ------------------------------------------------------------------ NVML half */
+typedef int nvmlReturn_t;
+typedef void *nvmlDevice_t;
+#define NVML_SUCCESS 0
+#define NVML_ERROR_INVALID_ARGUMENT 2
+#define NVML_ERROR_INSUFFICIENT_SIZE 7
+#define NVML_ERROR_NOT_FOUND 6
+static int g_nvdev_obj[MAXDEV];
+static int nv_index(nvmlDevice_t h) { return (int)((int *)h - g_nvdev_obj); }
+
+typedef struct { unsigned pid; unsigned long long usedGpuMemory; unsigned gi, ci; } fake_procinfo_v2;
+typedef struct { unsigned pid; unsigned long long usedGpuMemory; } fake_procinfo_v1;
+typedef struct { unsigned pid; unsigned long long timeStamp; unsigned smUtil, memUtil, encUtil, decUtil; } fake_procutil;
+typedef struct { unsigned long long total, free, used; } fake_meminfo;
+typedef struct { unsigned version; unsigned long long total, reserved, free, used; } fake_meminfo_v2;
+typedef struct { char busIdLegacy[16]; unsigned domain, bus, device, pciDeviceId, pciSubSystemId; char busId[32]; } fake_pciinfo;
+
+EXPORT nvmlReturn_t nvmlInit_v2(void) { fake_init(); return NVML_SUCCESS; }
+EXPORT nvmlReturn_t nvmlInit(void) { fake_init(); return NVML_SUCCESS; }
+EXPORT nvmlReturn_t nvmlInitWithFlags(unsigned f) { (void)f; fake_init(); return NVML_SUCCESS; }
+EXPORT nvmlReturn_t nvmlShutdown(void) { return NVML_SUCCESS; }
+EXPORT const char *nvmlErrorString(nvmlReturn_t r) { (void)r; return "fake nvml"; }
+EXPORT nvmlReturn_t nvmlDeviceGetCount_v2(unsigned *c) { fake_init(); *c = (unsigned)g_ndev; return NVML_SUCCESS; }
+EXPORT nvmlReturn_t nvmlDeviceGetCount(unsigned *c) { return nvmlDeviceGetCount_v2(c); }
+EXPORT nvmlReturn_t nvmlDeviceGetHandleByIndex_v2(unsigned i, nvmlDevice_t *h) { fake_init(); if ((int)i >= g_ndev) return NVML_ERROR_INVALID_ARGUMENT; *h = &g_nvdev_obj[i]; return NVML_SUCCESS; }
+EXPORT nvmlReturn_t nvmlDeviceGetHandleByIndex(unsigned i, nvmlDevice_t *h) { return nvmlDeviceGetHandleByIndex_v2(i, h); }
+EXPORT nvmlReturn_t nvmlDeviceGetIndex(nvmlDevice_t h, unsigned *i) { *i = (unsigned)nv_index(h); return NVML_SUCCESS; }
+EXPORT nvmlReturn_t nvmlDeviceGetUUID(nvmlDevice_t h, char *uuid, unsigned len) {
+    unsigned char b[16]; fill_uuid(b, nv_index(h));
+    snprintf(uuid, len, "GPU-%02x%02x%02x%02x-%02x%02x-%02x%02x-%02x%02x-%02x%02x%02x%02x%02x%02x",
+             b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], b[8], b[9], b[10], b[11], b[12], b[13], b[14], b[15]);
+    return NVML_SUCCESS;
+}
+EXPORT nvmlReturn_t nvmlDeviceGetHandleByUUID(const char *uuid, nvmlDevice_t *h) {
+    char buf[96];
+    for (int i = 0; i < g_ndev; i++) { nvmlDeviceGetUUID(&g_nvdev_obj[i], buf, sizeof buf); if (!strcmp(buf, uuid)) { *h = &g_nvdev_obj[i]; return NVML_SUCCESS; } }
+    return NVML_ERROR_NOT_FOUND;
+}
+EXPORT nvmlReturn_t nvmlDeviceGetName(nvmlDevice_t h, char *name, unsigned len) { (void)h; snprintf(name, len, "NVIDIA B200 (fake)"); return NVML_SUCCESS; }
+static void fill_pci(fake_pciinfo *p, int d) {
+    memset(p, 0, sizeof *p); p->bus = 0x1b + (unsigned)d;
+    snprintf(p->busIdLegacy, sizeof p->busIdLegacy, "0000:%02X:00.0", p->bus);
+    snprintf(p->busId, sizeof p->busId, "00000000:%02X:00.0", p->bus);
+}
+EXPORT nvmlReturn_t nvmlDeviceGetPciInfo_v3(nvmlDevice_t h, fake_pciinfo *p) { fill_pci(p, nv_index(h)); return NVML_SUCCESS; }
+EXPORT nvmlReturn_t nvmlDeviceGetPciInfo_v2(nvmlDevice_t h, fake_pciinfo *p) { fill_pci(p, nv_index(h)); return NVML_SUCCESS; }
+EXPORT nvmlReturn_t nvmlDeviceGetPciInfo(nvmlDevice_t h, fake_pciinfo *p) { fill_pci(p, nv_index(h)); return NVML_SUCCESS; }
+EXPORT nvmlReturn_t nvmlDeviceGetHandleByPciBusId_v2(const char *s, nvmlDevice_t *h) { unsigned dom, bus; if (sscanf(s, "%x:%x", &dom, &bus) == 2 && (int)bus - 0x1b < g_ndev) { *h = &g_nvdev_obj[bus - 0x1b]; return NVML_SUCCESS; } return NVML_ERROR_NOT_FOUND; }
+
+static unsigned long long proc_bytes(int d) { return g_ctx_refs[d] > 0 ? g_ctx_bytes + g_used[d] : 0; }
+EXPORT nvmlReturn_t nvmlDeviceGetComputeRunningProcesses_v3(nvmlDevice_t h, unsigned *cnt, fake_procinfo_v2 *infos) {
+    int d = nv_index(h); unsigned have = g_ctx_refs[d] > 0 ? 1u : 0u;
+    if (!cnt) return NVML_ERROR_INVALID_ARGUMENT;
+    if (*cnt < have) { *cnt = have; return NVML_ERROR_INSUFFICIENT_SIZE; }
+    if (have && infos) { infos[0].pid = (unsigned)getpid(); infos[0].usedGpuMemory = proc_bytes(d); infos[0].gi = infos[0].ci = 0xFFFFFFFFu; }
+    *cnt = have; return NVML_SUCCESS;
+}
+EXPORT nvmlReturn_t nvmlDeviceGetComputeRunningProcesses_v2(nvmlDevice_t h, unsigned *cnt, fake_procinfo_v2 *infos) { return nvmlDeviceGetComputeRunningProcesses_v3(h, cnt, infos); }
+EXPORT nvmlReturn_t nvmlDeviceGetComputeRunningProcesses(nvmlDevice_t h, unsigned *cnt, fake_procinfo_v1 *infos) {
+    int d = nv_index(h); unsigned have = g_ctx_refs[d] > 0 ? 1u : 0u;
+    if (!cnt) return NVML_ERROR_INVALID_ARGUMENT;
+    if (*cnt < have) { *cnt = have; return NVML_ERROR_INSUFFICIENT_SIZE; }
+    if (have && infos) { infos[0].pid = (unsigned)getpid(); infos[0].usedGpuMemory = proc_bytes(d); }
+    *cnt = have; return NVML_SUCCESS;
+}
+EXPORT nvmlReturn_t nvmlDeviceGetGraphicsRunningProcesses_v3(nvmlDevice_t h, unsigned *cnt, void *infos) { (void)h; (void)infos; *cnt = 0; return NVML_SUCCESS; }
+EXPORT nvmlReturn_t nvmlDeviceGetProcessUtilization(nvmlDevice_t h, fake_procutil *u, unsigned *cnt, unsigned long long since) {
+    (void)since; int d = nv_index(h); unsigned have = g_ctx_refs[d] > 0 ? 1u : 0u;
+    if (!cnt) return NVML_ERROR_INVALID_ARGUMENT;
+    if (!u || *cnt < have) { *cnt = have; return NVML_ERROR_INSUFFICIENT_SIZE; }
+    if (have) { struct timeval tv; gettimeofday(&tv, 0); memset(u, 0, sizeof *u); u[0].pid = (unsigned)getpid();
+        u[0].timeStamp = (unsigned long long)tv.tv_sec * 1000000ull + (unsigned long long)tv.tv_usec; u[0].smUtil = g_sm_util; }
+    *cnt = have; return NVML_SUCCESS;
+}
+EXPORT nvmlReturn_t nvmlDeviceGetMemoryInfo(nvmlDevice_t h, fake_meminfo *m) { int d = nv_index(h); m->total = g_total; m->used = proc_bytes(d); m->free = g_total - m->used; return NVML_SUCCESS; }
+EXPORT nvmlReturn_t nvmlDeviceGetMemoryInfo_v2(nvmlDevice_t h, fake_meminfo_v2 *m) { int d = nv_index(h); m->total = g_total; m->reserved = 0; m->used = proc_bytes(d); m->free = g_total - m->used; return NVML_SUCCESS; }
+EXPORT nvmlReturn_t nvmlSystemGetDriverVersion(char *v, unsigned len) { snprintf(v, len, "580.159"); return NVML_SUCCESS; }
+EXPORT nvmlReturn_t nvmlSystemGetCudaDriverVersion(int *v) { *v = 12090; return NVML_SUCCESS; }

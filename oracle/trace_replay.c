@@ -1,0 +1,147 @@
+/*
+ * trace_replay.c — TEST INFRASTRUCTURE (oracle/). A pure CUDA-driver-API program (no cudart, so the
+ * reference's cuGetExportTable hooks stay out of the picture — SURVEY.md §7 hard part (d)) that
+ * replays an allocation trace and, after every op, prints the return code plus the accounting words
+ * of the container's shared region (Go mirror cmd/vGPUmonitor/cudevshr.go:18-58).
+ *
+ * Run it three ways and diff the output streams:
+ *   LD_PRELOAD=dlsym_shim.so:_ref/libvgpu.so   (the reference binary — the real oracle)
+ *   LD_PRELOAD=<new>/libvgpu.so                (the product)
+ *   no preload, mode "model"                   (oracle/vgpu_oracle.c, the CPU restatement)
+ * with LD_LIBRARY_PATH pointing at oracle/_ref/fake (CPU box) or the real driver (GPU box).
+ *
+ * Trace grammar, one op per line (ids index a pointer table):
+ *   A id size | M id size (managed) | P id width height (pitch, elem 4) | F id | X hexaddr (free raw)
+ *   I (cuMemGetInfo_v2) | T (cuDeviceTotalMem_v2) | L gx gy gz (cuLaunchKernel of an empty kernel)
+ * Output line: "<op#> <opcode> rc=<int> ctx=<u64> mod=<u64> buf=<u64> off=<u64> tot=<u64> [free=.. total=..]"
+ * where the five counters are SUMMED over every process slot of device 0 (== own slot for one process).
+ */
+#define _GNU_SOURCE
+#include <fcntl.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+typedef int CUresult;
+typedef int CUdevice;
+typedef unsigned long long CUdeviceptr;
+typedef void *CUcontext;
+typedef void *CUfunction;
+typedef void *CUmodule;
+typedef void *CUstream;
+
+extern CUresult cuInit(unsigned);
+extern CUresult cuDeviceGet(CUdevice *, int);
+extern CUresult cuDevicePrimaryCtxRetain(CUcontext *, CUdevice);
+extern CUresult cuCtxSetCurrent(CUcontext);
+extern CUresult cuMemAlloc_v2(CUdeviceptr *, size_t);
+extern CUresult cuMemAllocManaged(CUdeviceptr *, size_t, unsigned);
+extern CUresult cuMemAllocPitch_v2(CUdeviceptr *, size_t *, size_t, size_t, unsigned);
+extern CUresult cuMemFree_v2(CUdeviceptr);
+extern CUresult cuMemGetInfo_v2(size_t *, size_t *);
+extern CUresult cuDeviceTotalMem_v2(size_t *, CUdevice);
+extern CUresult cuLaunchKernel(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **);
+extern CUresult cuModuleLoadData(CUmodule *, const void *) __attribute__((weak));
+extern CUresult cuModuleGetFunction(CUfunction *, CUmodule, const char *) __attribute__((weak));
+extern CUresult cuCtxSynchronize(void);
+
+/* Appendix A offsets */
+#define REGION_SIZE 0xC4748
+#define OFF_PROCS 0x738
+#define SLOT_STRIDE 0x310
+#define OFF_USED 0x8
+#define USED_STRIDE 40
+#define OFF_PROCNUM 0xC4738
+#define MAXPROC 1024
+
+static const unsigned char *g_region;
+
+static void map_region(void) {
+    const char *path = getenv("CUDA_DEVICE_MEMORY_SHARED_CACHE");
+    if (!path) path = "/tmp/cudevshr.cache";
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return;
+    struct stat st;
+    if (fstat(fd, &st) == 0 && st.st_size >= REGION_SIZE)
+        g_region = mmap(NULL, REGION_SIZE, PROT_READ, MAP_SHARED, fd, 0);
+    if (g_region == MAP_FAILED) g_region = NULL;
+    close(fd);
+}
+
+static void counters(int dev, uint64_t out[5]) {
+    memset(out, 0, 5 * sizeof(uint64_t));
+    if (!g_region) return;
+    for (int s = 0; s < MAXPROC; s++) {
+        const unsigned char *slot = g_region + OFF_PROCS + (size_t)s * SLOT_STRIDE;
+        int32_t pid; memcpy(&pid, slot, 4);
+        if (pid == 0) continue;
+        const unsigned char *u = slot + OFF_USED + (size_t)dev * USED_STRIDE;
+        for (int k = 0; k < 5; k++) { uint64_t v; memcpy(&v, u + 8 * k, 8); out[k] += v; }
+    }
+}
+
+static const char *k_ptx =
+    ".version 7.0\n.target sm_52\n.address_size 64\n.visible .entry vgpu_empty()\n{\n ret;\n}\n";
+
+int main(int argc, char **argv) {
+    if (argc < 2) { fprintf(stderr, "usage: %s trace.txt [nptr]\n", argv[0]); return 2; }
+    FILE *tf = fopen(argv[1], "r");
+    if (!tf) { perror("trace"); return 2; }
+    size_t nptr = argc > 2 ? strtoull(argv[2], 0, 0) : (1u << 20);
+    CUdeviceptr *ptrs = calloc(nptr, sizeof *ptrs);
+
+    CUdevice dev; CUcontext ctx;
+    CUresult r;
+    if ((r = cuInit(0))) { printf("cuInit rc=%d\n", r); return 1; }
+    if ((r = cuDeviceGet(&dev, 0))) { printf("cuDeviceGet rc=%d\n", r); return 1; }
+    if ((r = cuDevicePrimaryCtxRetain(&ctx, dev))) { printf("retain rc=%d\n", r); return 1; }
+    if ((r = cuCtxSetCurrent(ctx))) { printf("setcurrent rc=%d\n", r); return 1; }
+    map_region();
+
+    CUfunction fn = NULL;
+    if (!getenv("TRACE_NO_MODULE") && cuModuleLoadData && cuModuleGetFunction) {
+        CUmodule mod;
+        if (cuModuleLoadData(&mod, k_ptx) == 0) cuModuleGetFunction(&fn, mod, "vgpu_empty");
+    }
+
+    uint64_t c[5];
+    counters(0, c);
+    printf("init rc=0 ctx=%lu mod=%lu buf=%lu off=%lu tot=%lu region=%d\n", c[0], c[1], c[2], c[3], c[4], g_region != NULL);
+
+    char line[256];
+    unsigned long opn = 0;
+    while (fgets(line, sizeof line, tf)) {
+        char op; unsigned long long a = 0, b = 0, d = 0;
+        if (line[0] == '#' || line[0] == '\n') continue;
+        int n = sscanf(line, " %c %lli %lli %lli", &op, (long long *)&a, (long long *)&b, (long long *)&d);
+        if (n < 1) continue;
+        size_t fr = 0, tot = 0; int has_info = 0;
+        switch (op) {
+        case 'A': ptrs[a] = 0; r = cuMemAlloc_v2(&ptrs[a], (size_t)b); if (r) ptrs[a] = 0; break;
+        case 'M': ptrs[a] = 0; r = cuMemAllocManaged(&ptrs[a], (size_t)b, 1); if (r) ptrs[a] = 0; break;
+        case 'P': { size_t pitch = 0; ptrs[a] = 0; r = cuMemAllocPitch_v2(&ptrs[a], &pitch, (size_t)b, (size_t)d, 4); if (r) ptrs[a] = 0; break; }
+        case 'F': r = cuMemFree_v2(ptrs[a]); if (!r) ptrs[a] = 0; break;
+        case 'X': r = cuMemFree_v2((CUdeviceptr)a); break;
+        case 'I': r = cuMemGetInfo_v2(&fr, &tot); has_info = 1; break;
+        case 'T': r = cuDeviceTotalMem_v2(&tot, dev); fr = 0; has_info = 1; break;
+        case 'L': r = cuLaunchKernel(fn, (unsigned)a, (unsigned)b, (unsigned)d, 1, 1, 1, 0, NULL, NULL, NULL); break;
+        default: continue;
+        }
+        counters(0, c);
+        printf("%lu %c rc=%d ctx=%lu mod=%lu buf=%lu off=%lu tot=%lu", opn, op, r, c[0], c[1], c[2], c[3], c[4]);
+        if (has_info) {
+            /* free/total only compared when the hook owns them (limit set): the reference reports the
+             * real driver's view in the unlimited case */
+            printf(" free=%zu total=%zu", fr, tot);
+        }
+        putchar('\n');
+        opn++;
+    }
+    cuCtxSynchronize();
+    fflush(stdout);
+    return 0;
+}
