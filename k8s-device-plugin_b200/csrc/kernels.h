@@ -1,0 +1,52 @@
+// kernels.h — parameter/record layouts shared by kernels.cu and the host-side launch code.
+#pragma once
+#include <stdint.h>
+
+#define VGPU_PACK_STAGES 6                 /* shared-memory ring depth of vgpu_pack_tma */
+#define VGPU_PACK_TILE_BYTES (32u * 1024u) /* one TMA bulk copy; 6 x 32 KiB + barriers = 192.1 KiB of the 227 KiB */
+#define VGPU_PACK_MAX_SEG 96               /* segments per launch; keeps the kernel parameter block < 4 KiB */
+#define VGPU_SCAN_DIGIT_BITS 11
+#define VGPU_SCAN_BINS (1 << VGPU_SCAN_DIGIT_BITS)
+
+/* allocation-table row states (device-resident table; oracle/vgpu_oracle.h mirrors these for the CPU checker) */
+#define VGPU_ST_FREE 0u
+#define VGPU_ST_RESIDENT 1u
+#define VGPU_ST_PAGED_OUT 2u
+#define VGPU_ST_PINNED 4u                  /* flag OR-ed onto RESIDENT: in use by an admission in progress, not evictable */
+
+typedef struct VgpuEntry {                 /* 32 bytes, 32-byte aligned rows */
+    uint64_t base;                         /* device VA (stable across page-out/page-in) */
+    uint64_t size;                         /* requested bytes */
+    uint64_t last_touch;                   /* logical launch tick of the last kernel/memcpy that referenced the buffer */
+    uint32_t state;
+    uint32_t host_slot;                    /* page index into the pinned pool while paged out */
+} VgpuEntry;
+
+typedef struct VgpuPackSeg {
+    uint64_t src;                          /* device address */
+    uint64_t dst;                          /* device address */
+    uint64_t bytes;
+    uint64_t tile_begin;                   /* index of this segment's first tile within the launch */
+} VgpuPackSeg;
+
+typedef struct VgpuPackParams {
+    uint32_t nseg;
+    uint32_t tile_bytes;
+    uint64_t total_tiles;
+    VgpuPackSeg seg[VGPU_PACK_MAX_SEG];
+} VgpuPackParams;
+
+typedef struct VgpuScanState {
+    uint64_t prefix;                       /* selected high digits of K* so far */
+    uint64_t need_left;
+    uint64_t need;
+    uint64_t cand_bytes;                   /* total candidate bytes (valid when insufficient) */
+    uint64_t out_freed;                    /* size sum of the emitted victims */
+    uint32_t done_ctas;
+    uint32_t insufficient;
+    uint32_t out_count;
+    uint32_t chain_flag;
+    uint32_t chain_offset;
+    uint32_t _pad;
+    uint64_t hist[VGPU_SCAN_BINS];
+} VgpuScanState;

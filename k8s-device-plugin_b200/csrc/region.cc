@@ -1,0 +1,325 @@
+// region.cc — see region.h.
+#include "region.h"
+
+#include <fcntl.h>
+#include <semaphore.h>
+#include <sys/file.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+
+#include "log.h"
+
+namespace vgpu {
+
+uint64_t parse_limit(const char *v) {
+    // get_limit_from_env@0x40d00 (multiprocess_memory_limit.c:L101-111): unit from the LAST character, number by
+    // strtoul(base 0), zero product or overflowing product -> 0 (= unlimited)
+    if (!v) return 0;
+    size_t len = std::strlen(v);
+    if (!len) return 0;
+    uint64_t scalar = 1;
+    switch (v[len - 1]) {
+        case 'G': case 'g': scalar = 1ull << 30; break;
+        case 'M': case 'm': scalar = 1ull << 20; break;
+        case 'K': case 'k': scalar = 1ull << 10; break;
+        default: break;
+    }
+    uint64_t n = std::strtoul(v, nullptr, 0);
+    uint64_t prod = n * scalar;
+    if (prod == 0 || prod / scalar != n) return 0;
+    return prod;
+}
+
+uint64_t limit_from_env(const char *base, int dev) {
+    char name[96];
+    std::snprintf(name, sizeof name, "%s_%d", base, dev);
+    uint64_t v = parse_limit(std::getenv(name));
+    if (v) return v;
+    return parse_limit(std::getenv(base));
+}
+
+static sem_t *sem_of(vgpu_shared_region_t *r) { return reinterpret_cast<sem_t *>(r->sem); }
+static_assert(sizeof(sem_t) <= 32, "sem_t must fit the 32-byte lane of the region");
+
+static bool pid_alive(int32_t pid) {
+    // proc_alive@0x40aac parses /proc/<pid>/stat; existence of the directory is the same predicate
+    if (pid <= 0) return false;
+    char p[64];
+    std::snprintf(p, sizeof p, "/proc/%d/stat", pid);
+    FILE *f = std::fopen(p, "r");
+    if (!f) return false;
+    char state = '?';
+    int rd = std::fscanf(f, "%*d %*[^)]%*c %c", &state);
+    std::fclose(f);
+    return rd != 1 || (state != 'Z' && state != 'X');
+}
+
+Region *Region::open(const char *path, bool create, const uint64_t *mem_limits, const uint64_t *sm_limits, int priority,
+                     const char (*uuids)[VGPU_UUID_LEN], int ndev, std::string *err) {
+    mode_t old = umask(0);  // file must be usable by every uid of the container and by the monitor (0666, @0x4429e)
+    int fd = ::open(path, create ? (O_RDWR | O_CREAT) : O_RDWR, 0666);
+    umask(old);
+    if (fd < 0) {
+        if (err) *err = std::string("open ") + path + ": " + std::strerror(errno);
+        return nullptr;
+    }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || static_cast<uint64_t>(st.st_size) < VGPU_REGION_SIZE) {
+        if (!create || ftruncate(fd, VGPU_REGION_SIZE) != 0) {
+            if (err) *err = "region file too small";
+            ::close(fd);
+            return nullptr;
+        }
+    }
+    void *m = mmap(nullptr, VGPU_REGION_SIZE, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    if (m == MAP_FAILED) {
+        if (err) *err = std::string("mmap: ") + std::strerror(errno);
+        ::close(fd);
+        return nullptr;
+    }
+    Region *R = new Region();
+    R->r_ = static_cast<vgpu_shared_region_t *>(m);
+    R->fd_ = fd;
+    R->path_ = path;
+    vgpu_shared_region_t *r = R->r_;
+
+    // creation race: whole-file advisory lock while the magic is examined/written (lockf @0x4458c)
+    if (lockf(fd, F_LOCK, VGPU_REGION_SIZE) != 0) LOG_WARN("lockf(%s): %s", path, std::strerror(errno));
+    if (r->initialized_flag != VGPU_REGION_MAGIC) {
+        if (!create) {
+            if (lockf(fd, F_ULOCK, VGPU_REGION_SIZE) != 0) {}
+            if (err) *err = "region not initialised";
+            delete R;
+            return nullptr;
+        }
+        for (int d = 0; d < VGPU_MAX_DEVICES; d++) {
+            r->limit[d] = mem_limits ? mem_limits[d] : 0;
+            r->sm_limit[d] = sm_limits ? sm_limits[d] : 100;
+        }
+        if (sem_init(sem_of(r), 1, 1) != 0) LOG_ERROR("sem_init: %s", std::strerror(errno));
+        r->owner_pid = 0;
+        r->sm_init_flag = 0;
+        r->utilization_switch = 1;
+        r->recent_kernel = 2;
+        r->priority = priority;
+        r->proc_num = 0;
+        if (uuids && ndev > 0) {
+            r->device_num = static_cast<uint64_t>(ndev);
+            for (int d = 0; d < ndev && d < VGPU_MAX_DEVICES; d++) std::memcpy(r->uuids[d], uuids[d], VGPU_UUID_LEN);
+        }
+        __atomic_thread_fence(__ATOMIC_SEQ_CST);
+        r->initialized_flag = VGPU_REGION_MAGIC;
+    } else if (mem_limits) {
+        for (int d = 0; d < VGPU_MAX_DEVICES; d++) {
+            if (mem_limits[d] != r->limit[d])
+                LOG_ERROR("Limit inconsistency detected for %dth device, %lu expected, get %lu", d,
+                          (unsigned long)r->limit[d], (unsigned long)mem_limits[d]);
+            if (sm_limits && sm_limits[d] != r->sm_limit[d])
+                LOG_INFO("SM limit inconsistency for device %d: %lu stored, %lu in env", d, (unsigned long)r->sm_limit[d],
+                         (unsigned long)sm_limits[d]);
+        }
+    }
+    if (lockf(fd, F_ULOCK, VGPU_REGION_SIZE) != 0) {}
+    return R;
+}
+
+Region::~Region() {
+    if (r_) munmap(r_, VGPU_REGION_SIZE);
+    if (fd_ >= 0) ::close(fd_);
+}
+
+void Region::lock() {
+    // lock_shrreg@0x437d3 (multiprocess_memory_limit.c:L518-542): sem_timedwait(10 s); on timeout take the lock
+    // over when its recorded owner is this process or a dead one (fix_lock_shrreg@0x4317c, under lockf), or after
+    // 30 timeouts with no recorded owner.
+    int trials = 0;
+    for (;;) {
+        struct timespec ts;
+        clock_gettime(CLOCK_REALTIME, &ts);
+        ts.tv_sec += 10;
+        if (sem_timedwait(sem_of(r_), &ts) == 0) {
+            r_->owner_pid = static_cast<uint64_t>(getpid());
+            __atomic_thread_fence(__ATOMIC_SEQ_CST);
+            return;
+        }
+        if (errno == EINTR) continue;
+        if (errno != ETIMEDOUT) {
+            LOG_ERROR("region lock: %s", std::strerror(errno));
+            continue;
+        }
+        int32_t owner = static_cast<int32_t>(r_->owner_pid);
+        bool takeover = false;
+        if (owner == getpid() || (owner != 0 && !pid_alive(owner))) takeover = true;
+        else if (owner == 0 && ++trials >= 30) takeover = true;
+        else ++trials;
+        if (takeover) {
+            if (lockf(fd_, F_LOCK, VGPU_REGION_SIZE) == 0) {
+                int32_t now = static_cast<int32_t>(r_->owner_pid);
+                bool still = (now == owner);
+                if (still) r_->owner_pid = static_cast<uint64_t>(getpid());
+                if (lockf(fd_, F_ULOCK, VGPU_REGION_SIZE) != 0) {}
+                if (still) {
+                    LOG_WARN("region lock taken over from dead owner %d", owner);
+                    return;  // lock held WITHOUT a sem_wait: the dead owner's count is ours now
+                }
+            }
+        }
+    }
+}
+
+void Region::unlock() {
+    __atomic_thread_fence(__ATOMIC_SEQ_CST);
+    r_->owner_pid = 0;
+    sem_post(sem_of(r_));
+}
+
+int Region::find_slot_locked(int32_t pid) {
+    int n = r_->proc_num;
+    if (cached_slot_ >= 0 && cached_slot_ < n && r_->procs[cached_slot_].pid == pid) return cached_slot_;
+    for (int i = 0; i < n; i++)
+        if (r_->procs[i].pid == pid) return cached_slot_ = i;
+    return -1;
+}
+
+int Region::claim_slot(int32_t pid) {
+    lock();
+    int s = find_slot_locked(pid);
+    if (s < 0) {
+        if (r_->proc_num >= VGPU_MAX_PROCS) reap_dead_locked();
+        if (r_->proc_num < VGPU_MAX_PROCS) {
+            s = r_->proc_num;
+            std::memset(&r_->procs[s], 0, sizeof(vgpu_proc_slot_t));
+            r_->procs[s].pid = pid;
+            r_->procs[s].hostpid = 0;
+            r_->procs[s].status = VGPU_STATUS_RUNNING;
+            __atomic_thread_fence(__ATOMIC_RELEASE);
+            r_->proc_num = s + 1;
+            cached_slot_ = s;
+        }
+    } else {
+        r_->procs[s].status = VGPU_STATUS_RUNNING;
+    }
+    unlock();
+    return s;
+}
+
+void Region::release_slot(int32_t pid) {
+    lock();
+    int s = find_slot_locked(pid);
+    if (s >= 0) {
+        int last = r_->proc_num - 1;
+        std::memset(&r_->procs[s], 0, sizeof(vgpu_proc_slot_t));
+        r_->proc_num = last;
+        if (s != last) {
+            std::memcpy(&r_->procs[s], &r_->procs[last], sizeof(vgpu_proc_slot_t));
+            std::memset(&r_->procs[last], 0, sizeof(vgpu_proc_slot_t));
+        }
+        cached_slot_ = -1;
+    }
+    unlock();
+}
+
+void Region::set_hostpid(int32_t pid, int32_t hostpid) {
+    lock();
+    int s = find_slot_locked(pid);
+    if (s >= 0) r_->procs[s].hostpid = hostpid;
+    unlock();
+}
+
+uint64_t Region::usage_locked(int dev) const {
+    uint64_t sum = 0;
+    int n = r_->proc_num;
+    for (int i = 0; i < n; i++) sum += r_->procs[i].used[dev].total;
+    return sum;  // reference adds initial_offset (a process-local constant 0 in the shipped binary)
+}
+
+uint64_t Region::usage(int dev) {
+    lock();
+    uint64_t u = usage_locked(dev);
+    unlock();
+    return u;
+}
+
+int Region::reap_dead_locked() {
+    // rm_quitted_process@0x41a8e runs `ps ax` through popen on every quota breach; /proc/<pid> answers the same
+    // question without forking a shell from inside a CUDA allocation call.
+    int reaped = 0;
+    int32_t self = getpid();
+    for (int i = 0; i < r_->proc_num;) {
+        int32_t p = r_->procs[i].pid;
+        if (p != self && !pid_alive(p)) {
+            int last = r_->proc_num - 1;
+            if (i != last) std::memcpy(&r_->procs[i], &r_->procs[last], sizeof(vgpu_proc_slot_t));
+            std::memset(&r_->procs[last], 0, sizeof(vgpu_proc_slot_t));
+            r_->proc_num = last;
+            cached_slot_ = -1;
+            reaped++;
+        } else {
+            i++;
+        }
+    }
+    return reaped;
+}
+
+static uint64_t *lane(vgpu_device_memory_t &m, int type) {
+    switch (type) {
+        case VGPU_MEM_CONTEXT: return &m.context_size;
+        case VGPU_MEM_MODULE: return &m.module_size;
+        case VGPU_MEM_BUFFER: return &m.buffer_size;
+        default: return nullptr;
+    }
+}
+
+bool Region::try_add(int32_t pid, int dev, uint64_t bytes, int type, bool enforce, bool check_only) {
+    lock();
+    if (enforce) {
+        uint64_t lim = r_->limit[dev];
+        if (lim != 0) {
+            uint64_t u = usage_locked(dev);
+            if (u + bytes > lim) {  // strict: usage+size == limit is admitted (ja @0x3fb88)
+                bool ok = false;
+                if (reap_dead_locked() > 0) {
+                    u = usage_locked(dev);
+                    ok = !(u + bytes > lim);
+                }
+                if (!ok) {
+                    unlock();
+                    LOG_ERROR("Device %d OOM %lu / %lu", dev, (unsigned long)(u + bytes), (unsigned long)lim);
+                    return false;
+                }
+            }
+        }
+    }
+    if (!check_only) {
+        int s = find_slot_locked(pid);
+        if (s >= 0) {
+            vgpu_device_memory_t &m = r_->procs[s].used[dev];
+            m.total += bytes;
+            if (uint64_t *l = lane(m, type)) *l += bytes;
+        } else {
+            LOG_WARN("add: no slot for pid %d", pid);
+        }
+    }
+    unlock();
+    return true;
+}
+
+void Region::sub(int32_t pid, int dev, uint64_t bytes, int type) {
+    lock();
+    int s = find_slot_locked(pid);
+    if (s >= 0) {
+        vgpu_device_memory_t &m = r_->procs[s].used[dev];
+        m.total -= bytes;  // wrapping u64, like the reference
+        if (uint64_t *l = lane(m, type)) *l -= bytes;
+    }
+    unlock();
+}
+
+}  // namespace vgpu

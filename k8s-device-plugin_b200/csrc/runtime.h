@@ -1,0 +1,118 @@
+// runtime.h — process-wide enforcement state behind the exported hooks: configuration from the plugin's env
+// contract, the shared region, the process-local allocation table and the semantic implementation of every
+// intercepted driver call. hook.cc only adapts exported symbol names onto these methods; cabi.cc exposes the
+// same objects to host tools.
+//
+// Reference counterparts: libvgpu.c (cuInit@0x15f5a, preInit@0x15c14, postInit@0x15d63), allocator.c
+// (add_chunk@0x40007, remove_chunk@0x40871, check_memory_type@0x407f2), memory.c (cuMemAlloc_v2@0x3180a ...
+// cuLaunchKernel@0x370bf), utils.c (set_task_pid@0x16a7f, try_lock_unified_lock@0x1612c).
+#pragma once
+#include <cuda.h>
+
+#include <atomic>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+
+#include "region.h"
+
+namespace vgpu {
+
+class SwapEngine;
+class Limiter;
+
+constexpr size_t kIpcSize = 2u << 20;  // IPCSIZE .data@0x610a8: allocations above this take the swap switch
+
+enum class AllocKind : uint8_t { Device, Managed, Pitch, Swap };
+
+struct Alloc {
+    size_t size;       // bytes charged to the quota (requested bytes, no rounding — Appendix E)
+    int dev;           // CUDA ordinal it was charged to
+    AllocKind kind;
+};
+
+struct Config {
+    bool oversubscribe = false;   // CUDA_OVERSUBSCRIBE=true  (server.go:356-358)
+    int util_policy = 0;          // GPU_CORE_UTILIZATION_POLICY: 0 default, 1 force, 2 disable (get_utilization_switch@0x45307)
+    bool active_oom_killer = false;
+    int priority = 1;             // CUDA_TASK_PRIORITY
+    std::string region_path;      // CUDA_DEVICE_MEMORY_SHARED_CACHE, default /tmp/cudevshr.cache
+    uint64_t mem_limit[VGPU_MAX_DEVICES] = {};
+    uint64_t sm_limit[VGPU_MAX_DEVICES] = {};
+    uint64_t virtual_limit[VGPU_MAX_DEVICES] = {};  // swap mode only: CUDA_DEVICE_MEMORY_VIRTUAL_LIMIT[_i]; 0 = host pool bound
+    static Config from_env();
+};
+
+class Runtime {
+   public:
+    static Runtime &get();
+
+    // region + slot; safe before cuInit and in non-CUDA processes (nothing GPU-side is touched)
+    bool ensure_initialized();
+    bool initialized() const { return inited_.load(std::memory_order_acquire); }
+
+    // ---- intercepted calls (semantics + reference return codes; see hook.cc for the symbol mapping)
+    CUresult init(unsigned flags);                                        // cuInit
+    CUresult mem_alloc(CUdeviceptr *dptr, size_t bytes);                  // cuMemAlloc_v2
+    CUresult mem_alloc_managed(CUdeviceptr *dptr, size_t bytes, unsigned flags);
+    CUresult mem_alloc_pitch(CUdeviceptr *dptr, size_t *pitch, size_t width, size_t height, unsigned elem);
+    CUresult mem_free(CUdeviceptr dptr);                                  // cuMemFree_v2
+    CUresult mem_get_info(size_t *free_b, size_t *total_b);               // cuMemGetInfo_v2
+    CUresult device_total_mem(size_t *bytes, CUdevice dev);               // cuDeviceTotalMem_v2
+    CUresult primary_ctx_retain(CUcontext *ctx, CUdevice dev);            // cuDevicePrimaryCtxRetain
+    CUresult ctx_create(CUcontext *ctx, unsigned flags, CUdevice dev);    // cuCtxCreate_v2
+    CUresult launch_kernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
+                           unsigned smem, CUstream st, void **params, void **extra);
+    CUresult launch_kernel_ex(const CUlaunchConfig *cfg, CUfunction f, void **params, void **extra);
+    CUresult launch_cooperative(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by,
+                                unsigned bz, unsigned smem, CUstream st, void **params);
+    // check_oom() of the reference (oom_check(dev, 0)): used by host-alloc style hooks
+    bool check_oom();
+    // memcpy/memset family: make the touched device ranges resident before the real call (swap mode only)
+    void touch_range(CUdeviceptr p, size_t bytes, CUstream st);
+    void touch_range2(CUdeviceptr a, size_t abytes, CUdeviceptr b, size_t bbytes, CUstream st);
+
+    // NVML view: nvmlDeviceGetMemoryInfo under the quota (nvml/hook.c:L327-334)
+    bool nvml_memory_view(int nvml_index, unsigned long long *total, unsigned long long *free_b, unsigned long long *used);
+
+    // ---- introspection (C-ABI, tests)
+    Region *region() { return region_.get(); }
+    const Config &config() const { return cfg_; }
+    int check_memory_type(CUdeviceptr p);   // 2 = tracked device memory, 1 = not (check_memory_type@0x407f2)
+    size_t table_size();
+    uint64_t context_size() const { return context_size_; }
+    SwapEngine *swap(int dev);
+    Limiter *limiter() { return limiter_.get(); }
+    void on_fork_child();
+    void on_exit();
+
+   private:
+    Runtime() = default;
+    int current_device();
+    void post_init();                       // postInit@0x15d63
+    void measure_context_size();            // set_task_pid@0x16a7f
+    void wait_running();                    // wait_status_self(1) loop of every wrapper
+    bool track(CUdeviceptr base, size_t size, int dev, AllocKind kind);
+    CUresult admit_launch(CUfunction f, void **params, void **extra, CUstream st, unsigned grids);
+    CUresult swap_alloc(CUdeviceptr *dptr, size_t bytes, int dev);
+
+    std::atomic<bool> inited_{false};
+    std::atomic<bool> post_inited_{false};
+    std::mutex init_mu_;
+    Config cfg_;
+    std::unique_ptr<Region> region_;
+    int32_t pid_ = 0;
+    uint64_t context_size_ = 0;
+    bool pid_found_ = false;
+    bool ctx_charged_[VGPU_MAX_DEVICES] = {};
+
+    std::mutex table_mu_;                   // the reference's single allocator mutex (mutex@0x61180)
+    std::map<CUdeviceptr, Alloc> table_;    // base -> alloc; ordered for range classification
+
+    std::mutex swap_mu_;
+    std::unique_ptr<SwapEngine> swap_[VGPU_MAX_DEVICES];
+    std::unique_ptr<Limiter> limiter_;
+};
+
+}  // namespace vgpu
