@@ -1,0 +1,247 @@
+// hook.cc — the LD_PRELOAD surface of libvgpu.so: every symbol an application (or libcudart, through dlsym /
+// cuGetProcAddress) can reach and that carries vGPU semantics.
+//
+// Reference boundary: lib/nvidia/libvgpu.so is injected into every process of the container via
+// /etc/ld.so.preload (pkg/device-plugin/nvidiadevice/nvinternal/plugin/server.go:386-391, lib/nvidia/ld.so.preload:1)
+// and re-routes symbol resolution three ways — its own exported cu*/nvml* symbols, a dlsym override
+// (libvgpu.so@0x11b36 -> __dlsym_hook_section@0x11e8e / _nvml@0x13ab8) and cuGetProcAddress{,_v2}
+// (@0x2e4ad / @0x2e9c8 via find_symbols_in_table@0x2e172). The same three routes exist here. The reference wraps
+// 205 cu* + 246 nvml* names, nearly all of them pure log-and-forward; only names with semantics are wrapped here,
+// everything else resolves straight to the real library (nothing to forward, nothing to log on the hot path).
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvml.h>
+#undef cuGetProcAddress   // cuda.h maps the unsuffixed name onto _v2; both entry points are exported here
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "driver.h"
+#include "log.h"
+#include "runtime.h"
+
+using vgpu::drv;
+using vgpu::Runtime;
+
+#define VGPU_EXPORT extern "C" __attribute__((visibility("default")))
+
+// ------------------------------------------------------------------------------------------------ hooked driver API
+VGPU_EXPORT CUresult cuInit(unsigned int flags) { return Runtime::get().init(flags); }
+
+VGPU_EXPORT CUresult cuMemAlloc_v2(CUdeviceptr *dptr, size_t bytesize) { return Runtime::get().mem_alloc(dptr, bytesize); }
+VGPU_EXPORT CUresult cuMemAllocManaged(CUdeviceptr *dptr, size_t bytesize, unsigned int flags) {
+    return Runtime::get().mem_alloc_managed(dptr, bytesize, flags);
+}
+VGPU_EXPORT CUresult cuMemAllocPitch_v2(CUdeviceptr *dptr, size_t *pPitch, size_t WidthInBytes, size_t Height,
+                                        unsigned int ElementSizeBytes) {
+    return Runtime::get().mem_alloc_pitch(dptr, pPitch, WidthInBytes, Height, ElementSizeBytes);
+}
+VGPU_EXPORT CUresult cuMemFree_v2(CUdeviceptr dptr) { return Runtime::get().mem_free(dptr); }
+VGPU_EXPORT CUresult cuMemGetInfo_v2(size_t *free_b, size_t *total) { return Runtime::get().mem_get_info(free_b, total); }
+VGPU_EXPORT CUresult cuDeviceTotalMem_v2(size_t *bytes, CUdevice dev) { return Runtime::get().device_total_mem(bytes, dev); }
+VGPU_EXPORT CUresult cuDevicePrimaryCtxRetain(CUcontext *pctx, CUdevice dev) { return Runtime::get().primary_ctx_retain(pctx, dev); }
+VGPU_EXPORT CUresult cuCtxCreate_v2(CUcontext *pctx, unsigned int flags, CUdevice dev) { return Runtime::get().ctx_create(pctx, flags, dev); }
+
+// host allocations only run the quota check (reference: cuMemHostAlloc@0x32577 / cuMemAllocHost_v2@0x319f8 /
+// cuMemHostRegister_v2@0x32842: real call, then check_oom(); on breach undo and return CUDA_ERROR_OUT_OF_MEMORY)
+VGPU_EXPORT CUresult cuMemHostAlloc(void **pp, size_t bytesize, unsigned int flags) {
+    Runtime &rt = Runtime::get();
+    rt.ensure_initialized();
+    CUresult r = drv().cuMemHostAlloc(pp, bytesize, flags);
+    if (r == CUDA_SUCCESS && rt.check_oom()) { drv().cuMemFreeHost(*pp); *pp = nullptr; return CUDA_ERROR_OUT_OF_MEMORY; }
+    return r;
+}
+VGPU_EXPORT CUresult cuMemAllocHost_v2(void **pp, size_t bytesize) {
+    Runtime &rt = Runtime::get();
+    rt.ensure_initialized();
+    CUresult r = drv().cuMemAllocHost_v2(pp, bytesize);
+    if (r == CUDA_SUCCESS && rt.check_oom()) { drv().cuMemFreeHost(*pp); return CUDA_ERROR_OUT_OF_MEMORY; }
+    return r;
+}
+
+VGPU_EXPORT CUresult cuLaunchKernel(CUfunction f, unsigned int gridDimX, unsigned int gridDimY, unsigned int gridDimZ,
+                                    unsigned int blockDimX, unsigned int blockDimY, unsigned int blockDimZ,
+                                    unsigned int sharedMemBytes, CUstream hStream, void **kernelParams, void **extra) {
+    return Runtime::get().launch_kernel(f, gridDimX, gridDimY, gridDimZ, blockDimX, blockDimY, blockDimZ, sharedMemBytes,
+                                        hStream, kernelParams, extra);
+}
+VGPU_EXPORT CUresult cuLaunchKernelEx(const CUlaunchConfig *config, CUfunction f, void **kernelParams, void **extra) {
+    return Runtime::get().launch_kernel_ex(config, f, kernelParams, extra);
+}
+VGPU_EXPORT CUresult cuLaunchCooperativeKernel(CUfunction f, unsigned int gridDimX, unsigned int gridDimY,
+                                               unsigned int gridDimZ, unsigned int blockDimX, unsigned int blockDimY,
+                                               unsigned int blockDimZ, unsigned int sharedMemBytes, CUstream hStream,
+                                               void **kernelParams) {
+    return Runtime::get().launch_cooperative(f, gridDimX, gridDimY, gridDimZ, blockDimX, blockDimY, blockDimZ,
+                                             sharedMemBytes, hStream, kernelParams);
+}
+
+// memcpy / memset: pass-through, except that in swap mode the device ranges they touch are paged in first (a DMA
+// engine cannot fault on an unmapped VMM range the way UVM-managed memory does in the reference)
+#define TOUCH1(p, n, st) Runtime::get().touch_range((p), (n), (st))
+#define TOUCH2(a, an, b, bn, st) Runtime::get().touch_range2((a), (an), (b), (bn), (st))
+#define TOUCH_DONE(st) Runtime::get().touch_done(st)
+VGPU_EXPORT CUresult cuMemcpyHtoD_v2(CUdeviceptr dst, const void *src, size_t n) {
+    TOUCH1(dst, n, nullptr); CUresult r = drv().cuMemcpyHtoD_v2(dst, src, n); TOUCH_DONE(nullptr); return r;
+}
+VGPU_EXPORT CUresult cuMemcpyDtoH_v2(void *dst, CUdeviceptr src, size_t n) {
+    TOUCH1(src, n, nullptr); CUresult r = drv().cuMemcpyDtoH_v2(dst, src, n); TOUCH_DONE(nullptr); return r;
+}
+VGPU_EXPORT CUresult cuMemcpyDtoD_v2(CUdeviceptr dst, CUdeviceptr src, size_t n) {
+    TOUCH2(dst, n, src, n, nullptr); CUresult r = drv().cuMemcpyDtoD_v2(dst, src, n); TOUCH_DONE(nullptr); return r;
+}
+VGPU_EXPORT CUresult cuMemcpyHtoDAsync_v2(CUdeviceptr dst, const void *src, size_t n, CUstream st) {
+    TOUCH1(dst, n, st); CUresult r = drv().cuMemcpyHtoDAsync_v2(dst, src, n, st); TOUCH_DONE(st); return r;
+}
+VGPU_EXPORT CUresult cuMemcpyDtoHAsync_v2(void *dst, CUdeviceptr src, size_t n, CUstream st) {
+    TOUCH1(src, n, st); CUresult r = drv().cuMemcpyDtoHAsync_v2(dst, src, n, st); TOUCH_DONE(st); return r;
+}
+VGPU_EXPORT CUresult cuMemcpyDtoDAsync_v2(CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream st) {
+    TOUCH2(dst, n, src, n, st); CUresult r = drv().cuMemcpyDtoDAsync_v2(dst, src, n, st); TOUCH_DONE(st); return r;
+}
+VGPU_EXPORT CUresult cuMemcpy(CUdeviceptr dst, CUdeviceptr src, size_t n) {
+    TOUCH2(dst, n, src, n, nullptr); CUresult r = drv().cuMemcpy(dst, src, n); TOUCH_DONE(nullptr); return r;
+}
+VGPU_EXPORT CUresult cuMemcpyAsync(CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream st) {
+    TOUCH2(dst, n, src, n, st); CUresult r = drv().cuMemcpyAsync(dst, src, n, st); TOUCH_DONE(st); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD8_v2(CUdeviceptr dst, unsigned char v, size_t n) {
+    TOUCH1(dst, n, nullptr); CUresult r = drv().cuMemsetD8_v2(dst, v, n); TOUCH_DONE(nullptr); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD16_v2(CUdeviceptr dst, unsigned short v, size_t n) {
+    TOUCH1(dst, n * 2, nullptr); CUresult r = drv().cuMemsetD16_v2(dst, v, n); TOUCH_DONE(nullptr); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD32_v2(CUdeviceptr dst, unsigned int v, size_t n) {
+    TOUCH1(dst, n * 4, nullptr); CUresult r = drv().cuMemsetD32_v2(dst, v, n); TOUCH_DONE(nullptr); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD8Async(CUdeviceptr dst, unsigned char v, size_t n, CUstream st) {
+    TOUCH1(dst, n, st); CUresult r = drv().cuMemsetD8Async(dst, v, n, st); TOUCH_DONE(st); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD16Async(CUdeviceptr dst, unsigned short v, size_t n, CUstream st) {
+    TOUCH1(dst, n * 2, st); CUresult r = drv().cuMemsetD16Async(dst, v, n, st); TOUCH_DONE(st); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD32Async(CUdeviceptr dst, unsigned int v, size_t n, CUstream st) {
+    TOUCH1(dst, n * 4, st); CUresult r = drv().cuMemsetD32Async(dst, v, n, st); TOUCH_DONE(st); return r;
+}
+
+// extras the reference exports for its own tooling
+VGPU_EXPORT CUresult cuMemoryAllocate(CUdeviceptr *dptr, size_t bytesize, size_t *bytesallocated, void *data) {
+    (void)data;                                   // cuMemoryAllocate@0x315da: the allocmode switch
+    if (bytesallocated) *bytesallocated = bytesize;
+    return Runtime::get().mem_alloc(dptr, bytesize);
+}
+VGPU_EXPORT CUresult cuMemoryFree(CUdeviceptr dptr) { return Runtime::get().mem_free(dptr); }   // cuMemoryFree@0x3792f
+VGPU_EXPORT int cuVGPUViewAllocator(void) {       // view_vgpu_allocator@0x3fc34
+    Runtime &rt = Runtime::get();
+    std::fprintf(stderr, "[vgpu-b200] allocation table: %zu entries, context_size=%lu\n", rt.table_size(),
+                 (unsigned long)rt.context_size());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ hooked NVML
+VGPU_EXPORT nvmlReturn_t nvmlDeviceGetMemoryInfo(nvmlDevice_t device, nvmlMemory_t *memory) {
+    // nvmlDeviceGetMemoryInfo@0x24069 (nvml/hook.c:L327-334): under a quota, nvidia-smi inside the container sees
+    // total = limit, used = container usage
+    const vgpu::NvmlTable &n = vgpu::nvml();
+    if (!n.nvmlDeviceGetMemoryInfo) return NVML_ERROR_FUNCTION_NOT_FOUND;
+    nvmlReturn_t r = n.nvmlDeviceGetMemoryInfo(device, memory);
+    if (r != NVML_SUCCESS || !memory) return r;
+    unsigned idx = 0;
+    if (n.nvmlDeviceGetIndex && n.nvmlDeviceGetIndex(device, &idx) == NVML_SUCCESS) {
+        unsigned long long t, f, u;
+        if (Runtime::get().nvml_memory_view((int)idx, &t, &f, &u)) { memory->total = t; memory->free = f; memory->used = u; }
+    }
+    return r;
+}
+VGPU_EXPORT nvmlReturn_t nvmlDeviceGetMemoryInfo_v2(nvmlDevice_t device, nvmlMemory_v2_t *memory) {
+    const vgpu::NvmlTable &n = vgpu::nvml();
+    if (!n.nvmlDeviceGetMemoryInfo_v2) return NVML_ERROR_FUNCTION_NOT_FOUND;
+    nvmlReturn_t r = n.nvmlDeviceGetMemoryInfo_v2(device, memory);
+    if (r != NVML_SUCCESS || !memory) return r;
+    unsigned idx = 0;
+    if (n.nvmlDeviceGetIndex && n.nvmlDeviceGetIndex(device, &idx) == NVML_SUCCESS) {
+        unsigned long long t, f, u;
+        if (Runtime::get().nvml_memory_view((int)idx, &t, &f, &u)) { memory->total = t; memory->free = f; memory->used = u; memory->reserved = 0; }
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------ symbol routing
+VGPU_EXPORT CUresult cuGetProcAddress_v2(const char *symbol, void **pfn, int cudaVersion, cuuint64_t flags,
+                                         CUdriverProcAddressQueryResult *symbolStatus);
+VGPU_EXPORT CUresult cuGetProcAddress(const char *symbol, void **pfn, int cudaVersion, cuuint64_t flags);
+
+namespace {
+struct HookEntry { const char *name; void *fn; };
+#define H(sym) {#sym, reinterpret_cast<void *>(&sym)}
+const HookEntry kHooks[] = {
+    H(cuInit), H(cuGetProcAddress), H(cuGetProcAddress_v2),
+    H(cuMemAlloc_v2), H(cuMemAllocManaged), H(cuMemAllocPitch_v2), H(cuMemFree_v2), H(cuMemGetInfo_v2),
+    H(cuDeviceTotalMem_v2), H(cuDevicePrimaryCtxRetain), H(cuCtxCreate_v2), H(cuMemHostAlloc), H(cuMemAllocHost_v2),
+    H(cuLaunchKernel), H(cuLaunchKernelEx), H(cuLaunchCooperativeKernel),
+    H(cuMemcpyHtoD_v2), H(cuMemcpyDtoH_v2), H(cuMemcpyDtoD_v2), H(cuMemcpyHtoDAsync_v2), H(cuMemcpyDtoHAsync_v2),
+    H(cuMemcpyDtoDAsync_v2), H(cuMemcpy), H(cuMemcpyAsync),
+    H(cuMemsetD8_v2), H(cuMemsetD16_v2), H(cuMemsetD32_v2), H(cuMemsetD8Async), H(cuMemsetD16Async), H(cuMemsetD32Async),
+    H(cuMemoryAllocate), H(cuMemoryFree), H(cuVGPUViewAllocator),
+    H(nvmlDeviceGetMemoryInfo), H(nvmlDeviceGetMemoryInfo_v2),
+};
+#undef H
+
+void *find_hook_exact(const char *name) {
+    for (const HookEntry &e : kHooks)
+        if (!std::strcmp(e.name, name)) return e.fn;
+    return nullptr;
+}
+// find_symbols_in_table@0x2e172: try name_v3, name_v2, name (cudaVersion and flags are ignored, as in the reference:
+// per-thread-default-stream requests collapse onto the legacy-stream wrapper)
+void *find_hook_versioned(const char *name) {
+    char buf[128];
+    if (std::strlen(name) > 100) return nullptr;
+    std::snprintf(buf, sizeof buf, "%s_v3", name);
+    if (void *p = find_hook_exact(buf)) return p;
+    std::snprintf(buf, sizeof buf, "%s_v2", name);
+    if (void *p = find_hook_exact(buf)) return p;
+    return find_hook_exact(name);
+}
+bool control_disabled() {
+    static bool off = std::getenv("CUDA_DISABLE_CONTROL") != nullptr;   // container opt-out (server.go:380-385)
+    return off;
+}
+}  // namespace
+
+VGPU_EXPORT CUresult cuGetProcAddress_v2(const char *symbol, void **pfn, int cudaVersion, cuuint64_t flags,
+                                         CUdriverProcAddressQueryResult *symbolStatus) {
+    if (symbol && pfn && !control_disabled()) {
+        if (void *h = find_hook_versioned(symbol)) {
+            *pfn = h;
+            if (symbolStatus) *symbolStatus = CU_GET_PROC_ADDRESS_SUCCESS;
+            return CUDA_SUCCESS;
+        }
+    }
+    if (drv().cuGetProcAddress_v2) return drv().cuGetProcAddress_v2(symbol, pfn, cudaVersion, flags, symbolStatus);
+    if (drv().cuGetProcAddress_v1) {
+        CUresult r = drv().cuGetProcAddress_v1(symbol, pfn, cudaVersion, flags);
+        if (symbolStatus) *symbolStatus = r == CUDA_SUCCESS ? CU_GET_PROC_ADDRESS_SUCCESS : CU_GET_PROC_ADDRESS_SYMBOL_NOT_FOUND;
+        return r;
+    }
+    return CUDA_ERROR_NOT_INITIALIZED;
+}
+
+VGPU_EXPORT CUresult cuGetProcAddress(const char *symbol, void **pfn, int cudaVersion, cuuint64_t flags) {
+    if (symbol && pfn && !control_disabled()) {
+        if (void *h = find_hook_versioned(symbol)) { *pfn = h; return CUDA_SUCCESS; }
+    }
+    if (drv().cuGetProcAddress_v1) return drv().cuGetProcAddress_v1(symbol, pfn, cudaVersion, flags);
+    if (drv().cuGetProcAddress_v2) return drv().cuGetProcAddress_v2(symbol, pfn, cudaVersion, flags, nullptr);
+    return CUDA_ERROR_NOT_INITIALIZED;
+}
+
+// dlsym override (libvgpu.so@0x11b36): libcudart and frameworks resolve the driver with dlopen("libcuda.so.1") +
+// dlsym(handle, "cu..."), which never consults LD_PRELOAD order — so the lookup itself is intercepted.
+VGPU_EXPORT void *dlsym(void *handle, const char *symbol) {
+    if (symbol && !control_disabled() && ((symbol[0] == 'c' && symbol[1] == 'u') || !std::strncmp(symbol, "nvml", 4))) {
+        if (void *h = find_hook_exact(symbol)) return h;
+    }
+    return vgpu::real_dlsym(handle, symbol);
+}

@@ -1,0 +1,187 @@
+// kmod.cc — see kmod.h.
+#include "kmod.h"
+
+#include <cstring>
+#include <map>
+#include <mutex>
+
+#include "driver.h"
+#include "log.h"
+
+extern "C" {
+extern const unsigned char vgpu_kernels_cubin[];      // generated: bin2c of kernels.cu's sm_100a cubin
+extern const unsigned long long vgpu_kernels_cubin_size;
+}
+
+namespace vgpu {
+
+static std::mutex g_mu;
+static std::map<CUcontext, Kernels *> g_by_ctx;
+
+const Kernels *kernels_for_current_ctx() {
+    const DriverTable &d = drv();
+    if (!d.loaded) { LOG_ERROR("CUDA driver not loaded: kernels unavailable"); return nullptr; }
+    CUcontext ctx = nullptr;
+    if (d.cuCtxGetCurrent(&ctx) != CUDA_SUCCESS || !ctx) { LOG_ERROR("no current CUDA context: kernels unavailable"); return nullptr; }
+    std::lock_guard<std::mutex> g(g_mu);
+    auto it = g_by_ctx.find(ctx);
+    if (it != g_by_ctx.end()) return it->second;
+    Kernels *k = new Kernels();
+    CUresult r = d.cuModuleLoadData(&k->mod, vgpu_kernels_cubin);
+    if (r != CUDA_SUCCESS) {
+        LOG_ERROR("cuModuleLoadData(sm_100a cubin, %llu bytes) failed: %d %s — this library requires a B200 (sm_100a) device",
+                  vgpu_kernels_cubin_size, (int)r, cu_err(r));
+        delete k;
+        g_by_ctx[ctx] = nullptr;
+        return nullptr;
+    }
+    struct { const char *name; CUfunction *fn; } tab[] = {
+        {"vgpu_pack_tma", &k->pack_tma}, {"vgpu_pack_generic", &k->pack_generic},
+        {"vgpu_victim_init", &k->victim_init}, {"vgpu_victim_hist", &k->victim_hist}, {"vgpu_victim_emit", &k->victim_emit},
+        {"vgpu_stamp", &k->stamp}, {"vgpu_wl_fill", &k->wl_fill}, {"vgpu_wl_touch", &k->wl_touch},
+        {"vgpu_wl_verify", &k->wl_verify}, {"vgpu_wl_empty", &k->wl_empty},
+    };
+    for (auto &t : tab) {
+        r = d.cuModuleGetFunction(t.fn, k->mod, t.name);
+        if (r != CUDA_SUCCESS) { LOG_ERROR("kernel %s missing from cubin: %d", t.name, (int)r); delete k; g_by_ctx[ctx] = nullptr; return nullptr; }
+    }
+    CUdevice dev = 0;
+    d.cuCtxGetDevice(&dev);
+    d.cuDeviceGetAttribute(&k->sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev);
+    if (k->sm_count <= 0) k->sm_count = 148;
+    const int smem = 128 + VGPU_PACK_STAGES * (int)VGPU_PACK_TILE_BYTES;
+    r = d.cuFuncSetAttribute(k->pack_tma, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem);
+    if (r != CUDA_SUCCESS) LOG_ERROR("cuFuncSetAttribute(max dynamic smem %d) failed: %d", smem, (int)r);
+    g_by_ctx[ctx] = k;
+    return k;
+}
+
+static CUresult launch_pack_set(const Kernels *k, CUfunction fn, bool tma, const PackSegment *segs, const uint32_t *which,
+                                size_t n, CUstream stream, int *launches) {
+    const DriverTable &d = drv();
+    size_t i = 0;
+    while (i < n) {
+        VgpuPackParams p;
+        p.tile_bytes = VGPU_PACK_TILE_BYTES;
+        p.nseg = 0;
+        uint64_t tiles = 0;
+        while (i < n && p.nseg < VGPU_PACK_MAX_SEG) {
+            const PackSegment &s = segs[which[i]];
+            VgpuPackSeg &o = p.seg[p.nseg++];
+            o.src = s.src; o.dst = s.dst; o.bytes = s.bytes; o.tile_begin = tiles;
+            tiles += (s.bytes + VGPU_PACK_TILE_BYTES - 1) / VGPU_PACK_TILE_BYTES;
+            i++;
+        }
+        p.total_tiles = tiles;
+        if (tiles == 0) continue;
+        void *args[] = {&p};
+        CUresult r;
+        if (tma) {
+            // persistent: one CTA per SM (a multiple of the SM count would only add barrier-ring copies)
+            unsigned grid = (unsigned)(tiles < (uint64_t)k->sm_count ? tiles : (uint64_t)k->sm_count);
+            r = d.cuLaunchKernel(fn, grid, 1, 1, 32, 1, 1, 128 + VGPU_PACK_STAGES * VGPU_PACK_TILE_BYTES, stream, args, nullptr);
+        } else {
+            uint64_t want = tiles < (uint64_t)k->sm_count * 8 ? tiles : (uint64_t)k->sm_count * 8;
+            r = d.cuLaunchKernel(fn, (unsigned)want, 1, 1, 256, 1, 1, 0, stream, args, nullptr);
+        }
+        if (r != CUDA_SUCCESS) { LOG_ERROR("pack launch failed: %d %s", (int)r, cu_err(r)); return r; }
+        if (launches) (*launches)++;
+    }
+    return CUDA_SUCCESS;
+}
+
+CUresult launch_pack(const Kernels *k, const PackSegment *segs, size_t nseg, CUstream stream, int *launches_out) {
+    if (!k) return CUDA_ERROR_NOT_INITIALIZED;
+    std::vector<uint32_t> al, un;
+    for (size_t i = 0; i < nseg; i++) {
+        if (segs[i].bytes == 0) continue;
+        bool aligned = ((segs[i].src | segs[i].dst | segs[i].bytes) & 15u) == 0;
+        (aligned ? al : un).push_back((uint32_t)i);
+    }
+    CUresult r = CUDA_SUCCESS;
+    if (!al.empty()) r = launch_pack_set(k, k->pack_tma, true, segs, al.data(), al.size(), stream, launches_out);
+    if (r == CUDA_SUCCESS && !un.empty()) r = launch_pack_set(k, k->pack_generic, false, segs, un.data(), un.size(), stream, launches_out);
+    return r;
+}
+
+VictimScanner::~VictimScanner() {
+    const DriverTable &d = drv();
+    if (d_state_) d.cuMemFree_v2(d_state_);
+    if (d_out_) d.cuMemFree_v2(d_out_);
+    if (h_state_) d.cuMemFreeHost(h_state_);
+    if (h_out_) d.cuMemFreeHost(h_out_);
+}
+
+CUresult VictimScanner::init(const Kernels *k, uint32_t max_rows) {
+    const DriverTable &d = drv();
+    k_ = k;
+    cap_ = max_rows;
+    CUresult r;
+    if ((r = d.cuMemAlloc_v2(&d_state_, sizeof(VgpuScanState))) != CUDA_SUCCESS) return r;
+    if ((r = d.cuMemAlloc_v2(&d_out_, (size_t)cap_ * 4)) != CUDA_SUCCESS) return r;
+    if ((r = d.cuMemHostAlloc(&h_state_, 64, 0)) != CUDA_SUCCESS) return r;
+    if ((r = d.cuMemHostAlloc((void **)&h_out_, (size_t)cap_ * 4, 0)) != CUDA_SUCCESS) return r;
+    return CUDA_SUCCESS;
+}
+
+static uint32_t bit_length(uint64_t v) { uint32_t b = 0; while (v) { b++; v >>= 1; } return b; }
+
+CUresult VictimScanner::scan(CUdeviceptr d_tbl, uint32_t n, uint64_t need, uint64_t max_touch, CUstream stream,
+                             std::vector<uint32_t> *victims, uint64_t *freed, bool *insufficient, int *launches_out) {
+    const DriverTable &d = drv();
+    victims->clear();
+    if (freed) *freed = 0;
+    if (insufficient) *insufficient = false;
+    if (n == 0 || need == 0) return CUDA_SUCCESS;
+    if (n > cap_) return CUDA_ERROR_INVALID_VALUE;
+    uint32_t idx_bits = bit_length(n - 1);
+    if (idx_bits == 0) idx_bits = 1;
+    uint32_t touch_bits = bit_length(max_touch);
+    if (touch_bits == 0) touch_bits = 1;
+    if (idx_bits + touch_bits > 64) return CUDA_ERROR_INVALID_VALUE;
+    uint32_t key_bits = idx_bits + touch_bits;
+    int launches = 0;
+    CUresult r;
+    {
+        void *a[] = {&d_state_, &need};
+        if ((r = d.cuLaunchKernel(k_->victim_init, 1, 1, 1, 256, 1, 1, 0, stream, a, nullptr)) != CUDA_SUCCESS) return r;
+        launches++;
+    }
+    // grid sized so that every CTA is co-resident (the emit kernel's chained scan relies on in-order progress)
+    uint32_t rows_per_cta = 256 * 8;
+    uint32_t grid = (n + rows_per_cta - 1) / rows_per_cta;
+    uint32_t max_grid = (uint32_t)k_->sm_count * 4;
+    if (grid > max_grid) grid = max_grid;
+    if (grid == 0) grid = 1;
+    for (int hi = (int)key_bits; hi > 0; hi -= VGPU_SCAN_DIGIT_BITS) {
+        uint32_t shift = hi > VGPU_SCAN_DIGIT_BITS ? (uint32_t)(hi - VGPU_SCAN_DIGIT_BITS) : 0u;
+        uint32_t width = (uint32_t)hi - shift;
+        void *a[] = {&d_tbl, &n, &d_state_, &idx_bits, &shift, &width};
+        if ((r = d.cuLaunchKernel(k_->victim_hist, grid, 1, 1, 256, 1, 1, 0, stream, a, nullptr)) != CUDA_SUCCESS) return r;
+        launches++;
+    }
+    uint32_t chunk = (n + grid - 1) / grid;
+    {
+        void *a[] = {&d_tbl, &n, &d_state_, &idx_bits, &chunk, &d_out_, &cap_};
+        if ((r = d.cuLaunchKernel(k_->victim_emit, grid, 1, 1, 256, 1, 1, 0, stream, a, nullptr)) != CUDA_SUCCESS) return r;
+        launches++;
+    }
+    if (launches_out) *launches_out += launches;
+    if ((r = d.cuMemcpyDtoHAsync_v2(h_state_, d_state_, 64, stream)) != CUDA_SUCCESS) return r;
+    // optimistic first page of indices; the rest (rare) after the count is known
+    uint32_t first = cap_ < 1024 ? cap_ : 1024;
+    if ((r = d.cuMemcpyDtoHAsync_v2(h_out_, d_out_, (size_t)first * 4, stream)) != CUDA_SUCCESS) return r;
+    if ((r = d.cuStreamSynchronize(stream)) != CUDA_SUCCESS) return r;
+    const VgpuScanState *hs = static_cast<const VgpuScanState *>(h_state_);
+    uint32_t cnt = hs->out_count;
+    if (cnt > first) {
+        if ((r = d.cuMemcpyDtoHAsync_v2(h_out_ + first, d_out_ + (size_t)first * 4, (size_t)(cnt - first) * 4, stream)) != CUDA_SUCCESS) return r;
+        if ((r = d.cuStreamSynchronize(stream)) != CUDA_SUCCESS) return r;
+    }
+    victims->assign(h_out_, h_out_ + cnt);
+    if (freed) *freed = hs->out_freed;
+    if (insufficient) *insufficient = hs->insufficient != 0;
+    return CUDA_SUCCESS;
+}
+
+}  // namespace vgpu

@@ -1,0 +1,534 @@
+// runtime.cc — see runtime.h.
+#include "runtime.h"
+
+#include <fcntl.h>
+#include <pthread.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <set>
+#include <unordered_map>
+#include <vector>
+
+#include "driver.h"
+#include "limiter.h"
+#include "log.h"
+#include "swap.h"
+
+namespace vgpu {
+
+static bool env_true(const char *name) {
+    const char *e = std::getenv(name);
+    return e && (!strcasecmp(e, "true") || !std::strcmp(e, "1"));
+}
+// Return codes on a quota breach / unknown pointer follow the reference bit for bit by default ((CUresult)-1 from
+// add_chunk@0x4005d and remove_chunk@0x409f0); VGPU_STRICT_CUDA_ERRORS=1 switches to CUDA-conformant codes.
+static bool strict_errors() {
+    static bool v = env_true("VGPU_STRICT_CUDA_ERRORS");
+    return v;
+}
+static const CUresult kQuotaBreachAlloc = static_cast<CUresult>(-1);
+
+Config Config::from_env() {
+    Config c;
+    c.oversubscribe = env_true("CUDA_OVERSUBSCRIBE");
+    if (const char *p = std::getenv("GPU_CORE_UTILIZATION_POLICY")) {
+        if (!strcasecmp(p, "force")) c.util_policy = 1;
+        else if (!strcasecmp(p, "disable")) c.util_policy = 2;
+    }
+    c.active_oom_killer = env_true("ACTIVE_OOM_KILLER");
+    if (const char *p = std::getenv("CUDA_TASK_PRIORITY")) c.priority = std::atoi(p);
+    const char *rp = std::getenv("CUDA_DEVICE_MEMORY_SHARED_CACHE");
+    c.region_path = rp && *rp ? rp : "/tmp/cudevshr.cache";
+    for (int d = 0; d < VGPU_MAX_DEVICES; d++) {
+        c.mem_limit[d] = limit_from_env("CUDA_DEVICE_MEMORY_LIMIT", d);
+        uint64_t sm = limit_from_env("CUDA_DEVICE_SM_LIMIT", d);
+        c.sm_limit[d] = sm ? sm : 100;  // do_init_device_sm_limits@0x41946: default 100
+        c.virtual_limit[d] = limit_from_env("CUDA_DEVICE_MEMORY_VIRTUAL_LIMIT", d);
+    }
+    return c;
+}
+
+Runtime &Runtime::get() {
+    static Runtime *r = new Runtime();  // intentionally leaked: hooks may run during process teardown
+    return *r;
+}
+
+static void atexit_trampoline() { Runtime::get().on_exit(); }
+static void atfork_child_trampoline() { Runtime::get().on_fork_child(); }
+
+bool Runtime::ensure_initialized() {
+    if (inited_.load(std::memory_order_acquire)) return region_ != nullptr;
+    std::lock_guard<std::mutex> g(init_mu_);
+    if (inited_.load(std::memory_order_relaxed)) return region_ != nullptr;
+    cfg_ = Config::from_env();
+    pid_ = getpid();
+    char uuids[VGPU_MAX_DEVICES][VGPU_UUID_LEN];
+    std::memset(uuids, 0, sizeof uuids);
+    int ndev = 0;
+    if (nvml_ready()) {  // put_device_info (multiprocess_memory_limit.c:L150)
+        unsigned cnt = 0;
+        if (nvml().nvmlDeviceGetCount_v2(&cnt) == NVML_SUCCESS) {
+            for (unsigned i = 0; i < cnt && i < VGPU_MAX_DEVICES; i++) {
+                nvmlDevice_t h;
+                if (nvml().nvmlDeviceGetHandleByIndex_v2(i, &h) == NVML_SUCCESS) nvml().nvmlDeviceGetUUID(h, uuids[i], VGPU_UUID_LEN);
+            }
+            ndev = (int)(cnt < VGPU_MAX_DEVICES ? cnt : VGPU_MAX_DEVICES);
+        }
+    }
+    std::string err;
+    Region *R = Region::open(cfg_.region_path.c_str(), true, cfg_.mem_limit, cfg_.sm_limit, cfg_.priority, uuids, ndev, &err);
+    if (!R) {
+        LOG_ERROR("shared region %s unavailable (%s): limits are NOT enforced in this process", cfg_.region_path.c_str(), err.c_str());
+    } else {
+        region_.reset(R);
+        if (region_->claim_slot(pid_) < 0) LOG_ERROR("no free process slot in %s", cfg_.region_path.c_str());
+        std::atexit(atexit_trampoline);
+        pthread_atfork(nullptr, nullptr, atfork_child_trampoline);
+    }
+    inited_.store(true, std::memory_order_release);
+    return region_ != nullptr;
+}
+
+void Runtime::on_exit() {
+    if (region_) region_->release_slot(pid_);
+}
+
+void Runtime::on_fork_child() {
+    // child_reinit_flag@0x43f54: the child is a new pid with no CUDA state; give it its own slot
+    pid_ = getpid();
+    {
+        std::lock_guard<std::mutex> g(table_mu_);
+        table_.clear();
+    }
+    for (auto &c : ctx_charged_) c = false;
+    if (region_) region_->claim_slot(pid_);
+}
+
+int Runtime::current_device() {
+    CUdevice d = -1;
+    if (drv().cuCtxGetDevice(&d) != CUDA_SUCCESS) return -1;
+    return (int)d;
+}
+
+// ------------------------------------------------------------------------------------------------ init
+static bool unified_lock() {
+    // try_lock_unified_lock@0x1612c: the lock IS the existence of /tmp/vgpulock/lock (open O_CREAT|O_EXCL, remove to
+    // unlock); the directory is bind-mounted from the host so every container on the node serialises here.
+    const char *path = "/tmp/vgpulock/lock";
+    for (int i = 0; i < 200; i++) {
+        int fd = ::open(path, O_CREAT | O_EXCL, 0700);
+        if (fd >= 0) { ::close(fd); return true; }
+        if (errno == ENOENT) return false;  // directory not mounted: nothing to serialise against
+        usleep(100 * 1000);
+    }
+    LOG_MSG("unified lock stale for 20 s, removing");
+    ::remove(path);
+    int fd = ::open(path, O_CREAT | O_EXCL, 0700);
+    if (fd >= 0) ::close(fd);
+    return fd >= 0;
+}
+static void unified_unlock() { ::remove("/tmp/vgpulock/lock"); }
+
+void Runtime::measure_context_size() {
+    // set_task_pid@0x16a7f (utils.c:L135-202): NVML's compute-process list before and after creating the primary
+    // context; the new entry is this process as the HOST sees it (pid namespace) and its usedGpuMemory is what a
+    // bare context costs on this GPU/driver.
+    if (std::getenv("VGPU_SKIP_CONTEXT_MEASURE") || !nvml_ready()) { LOG_WARN("SET_TASK_PID FAILED."); return; }
+    const NvmlTable &n = nvml();
+    const DriverTable &d = drv();
+    nvmlDevice_t h;
+    if (n.nvmlDeviceGetHandleByIndex_v2(0, &h) != NVML_SUCCESS) { LOG_WARN("SET_TASK_PID FAILED."); return; }
+    bool locked = unified_lock();
+    std::vector<nvmlProcessInfo_t> before(1024), after(1024);
+    unsigned nb = (unsigned)before.size(), na = (unsigned)after.size();
+    nvmlReturn_t r1 = n.nvmlDeviceGetComputeRunningProcesses_v3(h, &nb, before.data());
+    if (r1 != NVML_SUCCESS) nb = 0;
+    CUcontext ctx = nullptr;
+    if (d.cuDevicePrimaryCtxRetain(&ctx, 0) == CUDA_SUCCESS) {
+        nvmlReturn_t r2 = n.nvmlDeviceGetComputeRunningProcesses_v3(h, &na, after.data());
+        if (r2 != NVML_SUCCESS) na = 0;
+        std::set<unsigned> old;
+        for (unsigned i = 0; i < nb; i++) old.insert(before[i].pid);
+        int pick = -1;
+        for (unsigned i = 0; i < na; i++) if (after[i].pid == (unsigned)pid_) pick = (int)i;         // same pid namespace
+        if (pick < 0) for (unsigned i = 0; i < na; i++) if (!old.count(after[i].pid)) { pick = (int)i; break; }
+        if (pick >= 0) {
+            context_size_ = after[pick].usedGpuMemory;
+            pid_found_ = true;
+            if (region_) region_->set_hostpid(pid_, (int32_t)after[pick].pid);
+            LOG_INFO("hostPid=%u Primary Context Size==%lu", after[pick].pid, (unsigned long)context_size_);
+        } else {
+            LOG_WARN("host pid is error!");
+        }
+        d.cuDevicePrimaryCtxRelease_v2(0);
+    }
+    if (locked) unified_unlock();
+    if (!pid_found_) LOG_WARN("SET_TASK_PID FAILED.");
+}
+
+void Runtime::post_init() {
+    bool expected = false;
+    if (!post_inited_.compare_exchange_strong(expected, true)) return;
+    measure_context_size();
+    int pct = (int)(region_ ? region_->sm_limit(0) : cfg_.sm_limit[0]);
+    limiter_.reset(new Limiter(pct, region_ ? region_->raw() : nullptr, cfg_.util_policy));
+    LOG_MSG("Initialized: oversubscribe=%d mem_limit0=%lu sm_limit0=%d", (int)cfg_.oversubscribe,
+            (unsigned long)(region_ ? region_->limit(0) : 0), pct);
+}
+
+CUresult Runtime::init(unsigned flags) {
+    ensure_initialized();
+    if (!drv().loaded) return CUDA_ERROR_NOT_INITIALIZED;
+    CUresult r = drv().cuInit(flags);
+    if (r == CUDA_SUCCESS) post_init();
+    return r;
+}
+
+void Runtime::wait_running() {
+    // wait_status_self(1)@0x4555e guards every reference wrapper; the status word only ever leaves RUNNING through
+    // the reference's dormant SIGUSR2 suspend protocol (nothing calls suspend_all), so there is nothing to wait for.
+}
+
+// ------------------------------------------------------------------------------------------------ allocation table
+bool Runtime::track(CUdeviceptr base, size_t size, int dev, AllocKind kind) {
+    table_[base] = Alloc{size, dev, kind};
+    return true;
+}
+
+int Runtime::check_memory_type(CUdeviceptr p) {
+    std::lock_guard<std::mutex> g(table_mu_);
+    auto it = table_.upper_bound(p);
+    if (it == table_.begin()) return 1;
+    --it;
+    return (p >= it->first && p <= it->first + it->second.size) ? 2 : 1;  // inclusive end, like check_memory_type@0x407f2
+}
+
+size_t Runtime::table_size() {
+    std::lock_guard<std::mutex> g(table_mu_);
+    return table_.size();
+}
+
+SwapEngine *Runtime::swap(int dev) {
+    if (dev < 0 || dev >= VGPU_MAX_DEVICES) return nullptr;
+    return swap_[dev].get();
+}
+
+CUresult Runtime::swap_alloc(CUdeviceptr *dptr, size_t bytes, int dev) {
+    SwapEngine *e;
+    {
+        std::lock_guard<std::mutex> g(swap_mu_);
+        if (!swap_[dev]) {
+            uint64_t lim = region_ ? region_->limit(dev) : 0;
+            uint64_t fixed = region_ ? region_->usage(dev) : 0;
+            uint64_t cap = lim > fixed ? lim - fixed : 0;
+            if (lim && cap < (64ull << 20)) { LOG_ERROR("gpumem quota %lu leaves no room for swappable memory", (unsigned long)lim); return CUDA_ERROR_OUT_OF_MEMORY; }
+            SwapConfig sc = SwapConfig::from_env(lim ? cap : 0, cfg_.virtual_limit[dev]);
+            swap_[dev].reset(SwapEngine::create(dev, sc));
+            if (!swap_[dev]) { LOG_ERROR("swap engine unavailable on device %d", dev); return CUDA_ERROR_NOT_SUPPORTED; }
+        }
+        e = swap_[dev].get();
+    }
+    CUresult r = e->alloc(dptr, bytes);
+    if (r != CUDA_SUCCESS) return r;
+    if (region_) region_->add(pid_, dev, bytes, VGPU_MEM_BUFFER);
+    track(*dptr, bytes, dev, AllocKind::Swap);
+    return CUDA_SUCCESS;
+}
+
+CUresult Runtime::mem_alloc(CUdeviceptr *dptr, size_t bytes) {
+    ensure_initialized();
+    const DriverTable &d = drv();
+    if (!region_) return d.cuMemAlloc_v2(dptr, bytes);
+    int dev = current_device();
+    if (dev < 0) return d.cuMemAlloc_v2(dptr, bytes);  // no context: let the driver report it
+    std::lock_guard<std::mutex> g(table_mu_);          // allocate_raw@0x40a10 holds the allocator mutex across add_chunk
+    if (cfg_.oversubscribe && bytes > kIpcSize) {
+        // the reference's swap switch: cuMemoryAllocate@0x315da allocmode 0 (there: cuMemAllocManaged + UVM)
+        CUresult r = swap_alloc(dptr, bytes, dev);
+        if (r == CUDA_ERROR_OUT_OF_MEMORY && !strict_errors()) return kQuotaBreachAlloc;
+        return r;
+    }
+    if (cfg_.oversubscribe) {
+        // small allocations stay resident for their whole life: they may use the quota but cannot exceed it
+        if (!region_->try_add(pid_, dev, bytes, VGPU_MEM_BUFFER, true)) return strict_errors() ? CUDA_ERROR_OUT_OF_MEMORY : kQuotaBreachAlloc;
+    } else if (!region_->try_add(pid_, dev, bytes, VGPU_MEM_BUFFER, true)) {
+        return strict_errors() ? CUDA_ERROR_OUT_OF_MEMORY : kQuotaBreachAlloc;   // add_chunk@0x4005d returns -1
+    }
+    CUresult r = d.cuMemAlloc_v2(dptr, bytes);
+    if (r != CUDA_SUCCESS) {
+        region_->sub(pid_, dev, bytes, VGPU_MEM_BUFFER);
+        LOG_ERROR("cuMemoryAllocate failed res=%d", (int)r);
+        return r;
+    }
+    track(*dptr, bytes, dev, AllocKind::Device);
+    return CUDA_SUCCESS;
+}
+
+CUresult Runtime::mem_alloc_managed(CUdeviceptr *dptr, size_t bytes, unsigned flags) {
+    ensure_initialized();
+    const DriverTable &d = drv();
+    if (!region_) return d.cuMemAllocManaged(dptr, bytes, flags);
+    int dev = current_device();
+    if (dev < 0) return d.cuMemAllocManaged(dptr, bytes, flags);
+    if (!region_->try_add(pid_, dev, bytes, VGPU_MEM_BUFFER, true)) return CUDA_ERROR_OUT_OF_MEMORY;  // @0x31eab
+    CUresult r = d.cuMemAllocManaged(dptr, bytes, flags);
+    if (r != CUDA_SUCCESS) { region_->sub(pid_, dev, bytes, VGPU_MEM_BUFFER); return r; }
+    std::lock_guard<std::mutex> g(table_mu_);   // add_chunk_only@0x404a5
+    track(*dptr, bytes, dev, AllocKind::Managed);
+    return CUDA_SUCCESS;
+}
+
+CUresult Runtime::mem_alloc_pitch(CUdeviceptr *dptr, size_t *pitch, size_t width, size_t height, unsigned elem) {
+    ensure_initialized();
+    const DriverTable &d = drv();
+    if (!region_ || elem == 0) return d.cuMemAllocPitch_v2(dptr, pitch, width, height, elem);
+    int dev = current_device();
+    if (dev < 0) return d.cuMemAllocPitch_v2(dptr, pitch, width, height, elem);
+    // cuMemAllocPitch_v2@0x3206b: guess_pitch = ((W-1)/elem + 1) * elem ; bytesize = guess_pitch * H — the GUESS is
+    // what gets charged, not the pitch the driver picks
+    size_t guess = ((width - 1) / elem + 1) * (size_t)elem;
+    size_t bytes = guess * height;
+    if (!region_->try_add(pid_, dev, bytes, VGPU_MEM_BUFFER, true)) return CUDA_ERROR_OUT_OF_MEMORY;  // @0x321ef
+    CUresult r = d.cuMemAllocPitch_v2(dptr, pitch, width, height, elem);
+    if (r != CUDA_SUCCESS) { region_->sub(pid_, dev, bytes, VGPU_MEM_BUFFER); return r; }
+    std::lock_guard<std::mutex> g(table_mu_);
+    track(*dptr, bytes, dev, AllocKind::Pitch);
+    return CUDA_SUCCESS;
+}
+
+CUresult Runtime::mem_free(CUdeviceptr dptr) {
+    if (!dptr) return CUDA_SUCCESS;                 // cuMemFree_v2@0x32383
+    ensure_initialized();
+    const DriverTable &d = drv();
+    if (!region_) return d.cuMemFree_v2(dptr);
+    std::lock_guard<std::mutex> g(table_mu_);
+    auto it = table_.find(dptr);
+    if (it == table_.end()) {
+        // remove_chunk@0x409f0 answers -1 for anything it did not hand out (including pointers from unhooked
+        // allocators); strict mode lets the driver decide instead
+        return strict_errors() ? d.cuMemFree_v2(dptr) : static_cast<CUresult>(-1);
+    }
+    Alloc a = it->second;
+    CUresult r;
+    if (a.kind == AllocKind::Swap) {
+        SwapEngine *e = swap(a.dev);
+        r = e ? e->free(dptr) : CUDA_ERROR_INVALID_VALUE;
+    } else {
+        r = d.cuMemFree_v2(dptr);
+    }
+    // remove_chunk unlinks and un-accounts whatever the real free returned
+    table_.erase(it);
+    region_->sub(pid_, a.dev, a.size, VGPU_MEM_BUFFER);
+    return r == CUDA_SUCCESS ? CUDA_SUCCESS : r;
+}
+
+bool Runtime::check_oom() {
+    if (!ensure_initialized()) return false;
+    int dev = current_device();
+    if (dev < 0) return false;
+    return !region_->try_add(pid_, dev, 0, VGPU_MEM_BUFFER, true, true);
+}
+
+CUresult Runtime::mem_get_info(size_t *free_b, size_t *total_b) {
+    ensure_initialized();
+    const DriverTable &d = drv();
+    if (!region_) return d.cuMemGetInfo_v2(free_b, total_b);
+    int dev = current_device();
+    if (dev < 0) return d.cuMemGetInfo_v2(free_b, total_b);
+    // cuMemGetInfo_v2@0x367dc (memory.c:L549-566)
+    uint64_t usage = region_->usage(dev);
+    uint64_t limit = region_->limit(dev);
+    size_t rf = 0, rt = 0;
+    if (limit == 0) {
+        CUresult r = d.cuMemGetInfo_v2(&rf, &rt);
+        if (r != CUDA_SUCCESS) return r;
+        if (total_b) *total_b = rt;
+        if (free_b) *free_b = rt - usage;
+        return CUDA_SUCCESS;
+    }
+    if (cfg_.oversubscribe) {
+        // swap mode: the quota bounds residency, not live bytes (DESIGN.md "quota semantics"); report the virtual
+        // capacity and never the reference's CUDA_ERROR_INVALID_VALUE for usage > limit (@0x36b3a)
+        uint64_t vcap = cfg_.virtual_limit[dev];
+        if (!vcap) {
+            SwapEngine *e = swap(dev);
+            uint64_t pool = e ? e->config().host_pool_cap : 0;
+            CUresult r = d.cuMemGetInfo_v2(&rf, &rt);
+            if (r != CUDA_SUCCESS) return r;
+            vcap = pool ? limit + pool : (uint64_t)rt + limit;   // unbounded pool: advertise one device's worth beyond the quota
+        }
+        if (total_b) *total_b = vcap;
+        if (free_b) *free_b = vcap > usage ? vcap - usage : 0;
+        return CUDA_SUCCESS;
+    }
+    if (limit < usage) return CUDA_ERROR_INVALID_VALUE;
+    CUresult r = d.cuMemGetInfo_v2(&rf, &rt);
+    if (r != CUDA_SUCCESS) return r;
+    if (free_b) *free_b = limit - usage;
+    if (total_b) *total_b = limit;
+    return CUDA_SUCCESS;
+}
+
+CUresult Runtime::device_total_mem(size_t *bytes, CUdevice dev) {
+    ensure_initialized();
+    uint64_t limit = (region_ && dev >= 0 && dev < VGPU_MAX_DEVICES) ? region_->limit(dev) : 0;
+    // cuDeviceTotalMem_v2@0x2d3f8 stores the limit unconditionally — 0 bytes for an unlimited container. That is
+    // a defect, not a contract: unlimited containers get the driver's answer here (DESIGN.md "deviations").
+    if (limit == 0) return drv().cuDeviceTotalMem_v2(bytes, dev);
+    if (bytes) *bytes = limit;
+    return CUDA_SUCCESS;
+}
+
+CUresult Runtime::primary_ctx_retain(CUcontext *ctx, CUdevice dev) {
+    ensure_initialized();
+    CUresult r = drv().cuDevicePrimaryCtxRetain(ctx, dev);
+    if (r == CUDA_SUCCESS && region_ && dev >= 0 && dev < VGPU_MAX_DEVICES && !ctx_charged_[dev]) {
+        // cuDevicePrimaryCtxRetain (context.c:L72-86): add_gpu_device_memory_usage(pid, dev, context_size, 0)
+        ctx_charged_[dev] = true;
+        if (context_size_) region_->add(pid_, dev, context_size_, VGPU_MEM_CONTEXT);
+    }
+    return r;
+}
+
+CUresult Runtime::ctx_create(CUcontext *ctx, unsigned flags, CUdevice dev) {
+    ensure_initialized();
+    CUresult r = drv().cuCtxCreate_v2(ctx, flags, dev);
+    if (r == CUDA_SUCCESS && region_ && dev >= 0 && dev < VGPU_MAX_DEVICES && context_size_)
+        region_->add(pid_, dev, context_size_, VGPU_MEM_CONTEXT);   // cuCtxCreate_v2@0x29c75: once per created context
+    return r;
+}
+
+bool Runtime::nvml_memory_view(int idx, unsigned long long *total, unsigned long long *free_b, unsigned long long *used) {
+    if (!ensure_initialized() || idx < 0 || idx >= VGPU_MAX_DEVICES) return false;
+    uint64_t limit = region_->limit(idx);
+    if (limit == 0) return false;
+    uint64_t usage = region_->usage(idx);
+    *total = limit;
+    *used = usage;
+    *free_b = limit > usage ? limit - usage : 0;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ launches
+namespace {
+struct ParamLayout { std::vector<std::pair<size_t, size_t>> p; bool known = false; };
+std::mutex g_layout_mu;
+std::unordered_map<CUfunction, ParamLayout> g_layouts;
+
+const ParamLayout &layout_of(CUfunction f) {
+    std::lock_guard<std::mutex> g(g_layout_mu);
+    auto it = g_layouts.find(f);
+    if (it != g_layouts.end()) return it->second;
+    ParamLayout L;
+    const DriverTable &d = drv();
+    if (d.cuFuncGetParamInfo) {
+        L.known = true;
+        for (size_t i = 0; i < 1024; i++) {
+            size_t off = 0, sz = 0;
+            if (d.cuFuncGetParamInfo(f, i, &off, &sz) != CUDA_SUCCESS) break;
+            L.p.emplace_back(off, sz);
+        }
+    }
+    return g_layouts.emplace(f, std::move(L)).first->second;
+}
+}  // namespace
+
+// Collects the swap-table rows referenced by a launch's arguments (pointers falling inside the swap arena).
+static void collect_launch_rows(SwapEngine *e, CUfunction f, void **params, void **extra, std::vector<int> *rows) {
+    const ParamLayout &L = layout_of(f);
+    if (params && L.known) {
+        for (size_t i = 0; i < L.p.size(); i++)
+            if (L.p[i].second >= 8 && params[i]) e->collect_rows(params[i], L.p[i].second, rows);
+    } else if (extra) {
+        // CU_LAUNCH_PARAM_BUFFER_POINTER / _SIZE pairs
+        void *buf = nullptr; size_t size = 0;
+        for (int i = 0; i < 16 && extra[i] != CU_LAUNCH_PARAM_END; i += 2) {
+            if (extra[i] == CU_LAUNCH_PARAM_BUFFER_POINTER) buf = extra[i + 1];
+            else if (extra[i] == CU_LAUNCH_PARAM_BUFFER_SIZE) size = *static_cast<size_t *>(extra[i + 1]);
+        }
+        if (buf && size) e->collect_rows(buf, size, rows);
+    } else if (params && !L.known) {
+        static bool warned = false;
+        if (!warned) { warned = true; LOG_ERROR("driver lacks cuFuncGetParamInfo: kernel arguments cannot be scanned, swapped-out buffers may fault"); }
+    }
+}
+
+// Shared shape of every launch intercept: limiter gate -> swap admission -> real launch -> bookkeeping.
+template <typename RealLaunch>
+static CUresult guarded_launch(Runtime &rt, const Config &cfg, Limiter *lim, CUfunction f, void **params, void **extra,
+                               CUstream st, RealLaunch real) {
+    if (lim) lim->before_launch(st);     // rate_limiter@0x4591a position: before the real launch
+    SwapEngine *e = nullptr;
+    thread_local std::vector<int> rows;
+    rows.clear();
+    if (cfg.oversubscribe) {
+        CUdevice dev = -1;
+        if (drv().cuCtxGetDevice(&dev) == CUDA_SUCCESS) e = rt.swap((int)dev);
+        if (e) {
+            collect_launch_rows(e, f, params, extra, &rows);
+            if (!rows.empty()) {
+                CUresult r = e->ensure_resident(rows.data(), (int)rows.size(), st);
+                if (r != CUDA_SUCCESS) return r;
+            }
+        }
+    }
+    CUresult r = real();
+    if (e && !rows.empty()) e->note_use(rows.data(), (int)rows.size(), st);
+    if (lim) lim->after_launch(st);
+    return r;
+}
+
+CUresult Runtime::launch_kernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
+                                unsigned smem, CUstream st, void **params, void **extra) {
+    if (!initialized()) ensure_initialized();
+    return guarded_launch(*this, cfg_, limiter_.get(), f, params, extra, st,
+                          [&] { return drv().cuLaunchKernel(f, gx, gy, gz, bx, by, bz, smem, st, params, extra); });
+}
+
+CUresult Runtime::launch_kernel_ex(const CUlaunchConfig *cfg, CUfunction f, void **params, void **extra) {
+    if (!cfg || !drv().cuLaunchKernelEx) return CUDA_ERROR_NOT_SUPPORTED;
+    if (!initialized()) ensure_initialized();
+    return guarded_launch(*this, cfg_, limiter_.get(), f, params, extra, cfg->hStream,
+                          [&] { return drv().cuLaunchKernelEx(cfg, f, params, extra); });
+}
+
+CUresult Runtime::launch_cooperative(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by,
+                                     unsigned bz, unsigned smem, CUstream st, void **params) {
+    // the reference lets cooperative launches bypass rate_limiter (Appendix E); here they are limited and admitted
+    // like any other launch
+    if (!initialized()) ensure_initialized();
+    return guarded_launch(*this, cfg_, limiter_.get(), f, params, nullptr, st,
+                          [&] { return drv().cuLaunchCooperativeKernel(f, gx, gy, gz, bx, by, bz, smem, st, params); });
+}
+
+static thread_local std::vector<int> t_touch_rows;   // rows pinned between touch_range*() and touch_done()
+
+void Runtime::touch_range(CUdeviceptr p, size_t bytes, CUstream st) { touch_range2(p, bytes, 0, 0, st); }
+
+void Runtime::touch_range2(CUdeviceptr a, size_t abytes, CUdeviceptr b, size_t bbytes, CUstream st) {
+    if (!cfg_.oversubscribe) return;
+    int dev = current_device();
+    SwapEngine *e = swap(dev);
+    if (!e) return;
+    int rows[2]; int n = 0;
+    (void)abytes; (void)bbytes;
+    int ra = a ? e->lookup(a) : -1, rb = b ? e->lookup(b) : -1;
+    if (ra >= 0) rows[n++] = ra;
+    if (rb >= 0 && rb != ra) rows[n++] = rb;
+    if (!n) return;
+    if (e->ensure_resident(rows, n, st) != CUDA_SUCCESS) { LOG_ERROR("memcpy/memset target could not be made resident"); return; }
+    // the copy itself is enqueued by the caller right after this returns; note_use after it keeps the rows pinned
+    t_touch_rows.assign(rows, rows + n);
+}
+
+void Runtime::touch_done(CUstream st) {
+    if (t_touch_rows.empty()) return;
+    int dev = current_device();
+    if (SwapEngine *e = swap(dev)) e->note_use(t_touch_rows.data(), (int)t_touch_rows.size(), st);
+    t_touch_rows.clear();
+}
+
+}  // namespace vgpu

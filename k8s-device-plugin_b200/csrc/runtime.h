@@ -72,6 +72,7 @@ class Runtime {
     // memcpy/memset family: make the touched device ranges resident before the real call (swap mode only)
     void touch_range(CUdeviceptr p, size_t bytes, CUstream st);
     void touch_range2(CUdeviceptr a, size_t abytes, CUdeviceptr b, size_t bbytes, CUstream st);
+    void touch_done(CUstream st);   // after the real copy has been enqueued: unpins + records the use
 
     // NVML view: nvmlDeviceGetMemoryInfo under the quota (nvml/hook.c:L327-334)
     bool nvml_memory_view(int nvml_index, unsigned long long *total, unsigned long long *free_b, unsigned long long *used);
@@ -94,7 +95,6 @@ class Runtime {
     void measure_context_size();            // set_task_pid@0x16a7f
     void wait_running();                    // wait_status_self(1) loop of every wrapper
     bool track(CUdeviceptr base, size_t size, int dev, AllocKind kind);
-    CUresult admit_launch(CUfunction f, void **params, void **extra, CUstream st, unsigned grids);
     CUresult swap_alloc(CUdeviceptr *dptr, size_t bytes, int dev);
 
     std::atomic<bool> inited_{false};

@@ -1,0 +1,687 @@
+// swap.cc — see swap.h.
+#include "swap.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "driver.h"
+#include "log.h"
+
+namespace vgpu {
+
+#define CU_TRY(expr)                                                                     \
+    do {                                                                                 \
+        CUresult _r = (expr);                                                            \
+        if (_r != CUDA_SUCCESS) {                                                        \
+            LOG_ERROR("%s failed: %d %s", #expr, (int)_r, cu_err(_r));                   \
+            return _r;                                                                   \
+        }                                                                                \
+    } while (0)
+
+static uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+static uint64_t env_u64(const char *name, uint64_t dflt) {
+    const char *e = std::getenv(name);
+    return e && *e ? std::strtoull(e, nullptr, 0) : dflt;
+}
+
+SwapConfig SwapConfig::from_env(uint64_t resident_cap, uint64_t virtual_cap) {
+    SwapConfig c;
+    c.resident_cap = resident_cap;
+    c.virtual_cap = virtual_cap;
+    c.host_pool_cap = env_u64("VGPU_SWAP_HOST_POOL_MB", 0) << 20;
+    c.chunk_bytes = (size_t)env_u64("VGPU_SWAP_CHUNK_MB", 32) << 20;
+    c.ring_slots = (int)env_u64("VGPU_SWAP_RING", 4);
+    c.slab_bytes = (size_t)env_u64("VGPU_SWAP_SLAB_MB", 1024) << 20;
+    c.arena_bytes = env_u64("VGPU_SWAP_ARENA_GB", 1024) << 30;
+    c.profile = env_u64("VGPU_SWAP_PROFILE", 0) != 0;
+    if (c.ring_slots < 2) c.ring_slots = 2;
+    if (c.chunk_bytes < (1u << 20)) c.chunk_bytes = 1u << 20;
+    return c;
+}
+
+SwapEngine *SwapEngine::create(int dev, const SwapConfig &cfg) {
+    SwapEngine *e = new SwapEngine();
+    if (!e->init(dev, cfg)) {
+        delete e;
+        return nullptr;
+    }
+    return e;
+}
+
+bool SwapEngine::init(int dev, const SwapConfig &cfg) {
+    const DriverTable &d = drv();
+    dev_ = dev;
+    cfg_ = cfg;
+    k_ = kernels_for_current_ctx();
+    if (!k_) return false;
+    CUmemAllocationProp prop = {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = dev_;
+    if (!d.cuMemGetAllocationGranularity || d.cuMemGetAllocationGranularity(&gran_, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS) {
+        LOG_ERROR("VMM unavailable (cuMemGetAllocationGranularity)");
+        return false;
+    }
+    cfg_.chunk_bytes = round_up(cfg_.chunk_bytes, gran_);
+    if (cfg_.resident_cap == 0) {
+        size_t fr = 0, tot = 0;
+        d.cuMemGetInfo_v2(&fr, &tot);
+        uint64_t overhead = 2ull * cfg_.ring_slots * cfg_.chunk_bytes + (512ull << 20);
+        cfg_.resident_cap = fr > overhead ? fr - overhead : fr / 2;
+    }
+    uint64_t want = round_up(cfg_.arena_bytes, gran_);
+    CUresult r = CUDA_ERROR_UNKNOWN;
+    while (want >= (8ull << 30)) {
+        r = d.cuMemAddressReserve(&arena_, want, 0, 0, 0);
+        if (r == CUDA_SUCCESS) break;
+        want >>= 1;
+    }
+    if (r != CUDA_SUCCESS) { LOG_ERROR("cuMemAddressReserve failed: %d %s", (int)r, cu_err(r)); return false; }
+    cfg_.arena_bytes = want;
+    va_free_[0] = want;
+    owner_.assign(want / gran_, -1);
+
+    if (d.cuStreamCreate(&s_kern_, CU_STREAM_NON_BLOCKING) || d.cuStreamCreate(&s_out_, CU_STREAM_NON_BLOCKING) ||
+        d.cuStreamCreate(&s_in_, CU_STREAM_NON_BLOCKING)) { LOG_ERROR("side stream creation failed"); return false; }
+    auto mkring = [&](std::vector<Slot> &ring) {
+        ring.resize(cfg_.ring_slots);
+        for (auto &s : ring) {
+            if (d.cuMemAlloc_v2(&s.buf, cfg_.chunk_bytes) != CUDA_SUCCESS) return false;
+            if (d.cuEventCreate(&s.busy, CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) return false;
+        }
+        return true;
+    };
+    if (!mkring(ring_out_) || !mkring(ring_in_)) { LOG_ERROR("staging ring allocation failed (%d x %zu MiB x 2)", cfg_.ring_slots, cfg_.chunk_bytes >> 20); return false; }
+
+    tbl_cap_ = 4096;
+    if (d.cuMemAlloc_v2(&d_tbl_, (size_t)tbl_cap_ * sizeof(VgpuEntry)) != CUDA_SUCCESS) return false;
+    if (d.cuMemHostAlloc((void **)&h_tbl_stage_, (size_t)tbl_cap_ * sizeof(VgpuEntry), 0) != CUDA_SUCCESS) return false;
+    scanner_.reset(new VictimScanner());
+    if (scanner_->init(k_, tbl_cap_) != CUDA_SUCCESS) return false;
+    use_ring_.resize(1024);
+    for (auto &e : use_ring_) if (d.cuEventCreate(&e, CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) return false;
+    LOG_INFO("swap engine dev %d: resident cap %lu MiB, virtual cap %lu MiB, chunk %zu MiB x %d, arena %lu GiB, gran %zu",
+             dev_, (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(cfg_.virtual_cap >> 20), cfg_.chunk_bytes >> 20,
+             cfg_.ring_slots, (unsigned long)(cfg_.arena_bytes >> 30), gran_);
+    return true;
+}
+
+SwapEngine::~SwapEngine() {
+    const DriverTable &d = drv();
+    if (!d.loaded) return;
+    drain();
+    for (size_t i = 0; i < rows_.size(); i++) {
+        if (rows_[i].state == VGPU_ST_FREE) continue;
+        if (rows_[i].state & VGPU_ST_RESIDENT) { d.cuMemUnmap(rows_[i].base, side_[i].mapped); if (side_[i].has_handle) d.cuMemRelease(side_[i].handle); }
+    }
+    for (auto &p : phys_pool_) d.cuMemRelease(p.second);
+    for (auto &s : ring_out_) { if (s.buf) d.cuMemFree_v2(s.buf); if (s.busy) d.cuEventDestroy_v2(s.busy); }
+    for (auto &s : ring_in_) { if (s.buf) d.cuMemFree_v2(s.buf); if (s.busy) d.cuEventDestroy_v2(s.busy); }
+    for (auto &sl : slabs_) if (sl.host) d.cuMemFreeHost(sl.host);
+    for (auto &e : use_ring_) if (e) d.cuEventDestroy_v2(e);
+    for (auto &e : ready_free_) d.cuEventDestroy_v2(e);
+    if (d_tbl_) d.cuMemFree_v2(d_tbl_);
+    if (h_tbl_stage_) d.cuMemFreeHost(h_tbl_stage_);
+    if (arena_) d.cuMemAddressFree(arena_, cfg_.arena_bytes);
+    if (s_kern_) d.cuStreamDestroy_v2(s_kern_);
+    if (s_out_) d.cuStreamDestroy_v2(s_out_);
+    if (s_in_) d.cuStreamDestroy_v2(s_in_);
+}
+
+// ---------------------------------------------------------------------------------------------- small allocators
+static bool map_alloc(std::map<uint64_t, uint64_t> &fl, uint64_t bytes, uint64_t *off) {
+    for (auto it = fl.begin(); it != fl.end(); ++it) {
+        if (it->second >= bytes) {
+            *off = it->first;
+            uint64_t rest = it->second - bytes, at = it->first + bytes;
+            fl.erase(it);
+            if (rest) fl[at] = rest;
+            return true;
+        }
+    }
+    return false;
+}
+static void map_free(std::map<uint64_t, uint64_t> &fl, uint64_t off, uint64_t bytes) {
+    auto nx = fl.lower_bound(off);
+    if (nx != fl.begin()) {
+        auto pv = std::prev(nx);
+        if (pv->first + pv->second == off) { off = pv->first; bytes += pv->second; fl.erase(pv); }
+    }
+    if (nx != fl.end() && off + bytes == nx->first) { bytes += nx->second; fl.erase(nx); }
+    fl[off] = bytes;
+}
+
+bool SwapEngine::va_alloc(size_t bytes, uint64_t *off) { return map_alloc(va_free_, bytes, off); }
+void SwapEngine::va_free(uint64_t off, size_t bytes) { map_free(va_free_, off, bytes); }
+
+// pinned pool: global offset = slab_index << 44 | offset-in-slab
+bool SwapEngine::host_alloc(size_t bytes, uint64_t *off) {
+    const DriverTable &d = drv();
+    bytes = round_up(bytes, 256);
+    for (size_t i = 0; i < slabs_.size(); i++) {
+        uint64_t o;
+        if (map_alloc(slabs_[i].free, bytes, &o)) {
+            *off = ((uint64_t)i << 44) | o;
+            host_used_ += bytes;
+            return true;
+        }
+    }
+    size_t sb = std::max<size_t>(cfg_.slab_bytes, bytes);
+    uint64_t have = 0;
+    for (auto &s : slabs_) have += s.bytes;
+    if (cfg_.host_pool_cap && have + sb > cfg_.host_pool_cap) {
+        if (have + bytes > cfg_.host_pool_cap) return false;
+        sb = bytes;
+    }
+    Slab s;
+    CUresult r = d.cuMemHostAlloc((void **)&s.host, sb, CU_MEMHOSTALLOC_PORTABLE);
+    if (r != CUDA_SUCCESS) { LOG_ERROR("pinned slab of %zu MiB failed: %d %s", sb >> 20, (int)r, cu_err(r)); return false; }
+    s.bytes = sb;
+    if (sb > bytes) s.free[bytes] = sb - bytes;
+    slabs_.push_back(std::move(s));
+    *off = ((uint64_t)(slabs_.size() - 1) << 44);
+    host_used_ += bytes;
+    return true;
+}
+unsigned char *SwapEngine::host_ptr(uint64_t off) { return slabs_[off >> 44].host + (off & ((1ull << 44) - 1)); }
+
+// ---------------------------------------------------------------------------------------------- table
+int SwapEngine::new_row() {
+    if (!free_rows_.empty()) { int r = free_rows_.back(); free_rows_.pop_back(); return r; }
+    rows_.push_back(VgpuEntry{});
+    side_.push_back(Side{});
+    return (int)rows_.size() - 1;
+}
+void SwapEngine::mark_dirty(int row) {
+    dirty_lo_ = std::min<uint32_t>(dirty_lo_, (uint32_t)row);
+    dirty_hi_ = std::max<uint32_t>(dirty_hi_, (uint32_t)row + 1);
+}
+CUresult SwapEngine::sync_table(CUstream s) {
+    const DriverTable &d = drv();
+    uint32_t n = (uint32_t)rows_.size();
+    if (n > tbl_cap_) {
+        uint32_t nc = tbl_cap_;
+        while (nc < n) nc *= 2;
+        CU_TRY(d.cuStreamSynchronize(s));
+        d.cuMemFree_v2(d_tbl_);
+        d.cuMemFreeHost(h_tbl_stage_);
+        CU_TRY(d.cuMemAlloc_v2(&d_tbl_, (size_t)nc * sizeof(VgpuEntry)));
+        CU_TRY(d.cuMemHostAlloc((void **)&h_tbl_stage_, (size_t)nc * sizeof(VgpuEntry), 0));
+        scanner_.reset(new VictimScanner());
+        CU_TRY(scanner_->init(k_, nc));
+        tbl_cap_ = nc;
+        dirty_lo_ = 0; dirty_hi_ = n;
+    }
+    if (dirty_lo_ >= dirty_hi_) return CUDA_SUCCESS;
+    uint32_t lo = dirty_lo_, hi = std::min(dirty_hi_, n);
+    // the pinned staging copy must not be overwritten while a previous upload is in flight
+    CU_TRY(d.cuStreamSynchronize(s));
+    std::memcpy(h_tbl_stage_ + lo, rows_.data() + lo, (size_t)(hi - lo) * sizeof(VgpuEntry));
+    CU_TRY(d.cuMemcpyHtoDAsync_v2(d_tbl_ + (size_t)lo * sizeof(VgpuEntry), h_tbl_stage_ + lo, (size_t)(hi - lo) * sizeof(VgpuEntry), s));
+    dirty_lo_ = UINT32_MAX; dirty_hi_ = 0;
+    return CUDA_SUCCESS;
+}
+
+int SwapEngine::lookup(CUdeviceptr p) const {
+    if (!owns(p)) return -1;
+    std::lock_guard<std::mutex> g(mu_);
+    int r = owner_[(p - arena_) / gran_];
+    if (r < 0) return -1;
+    if (p >= rows_[r].base + side_[r].mapped) return -1;
+    return r;
+}
+
+void SwapEngine::collect_rows(const void *param, size_t bytes, std::vector<int> *rows) const {
+    if (bytes < 8) return;
+    const unsigned char *b = static_cast<const unsigned char *>(param);
+    std::lock_guard<std::mutex> g(mu_);
+    for (size_t o = 0; o + 8 <= bytes; o += 8) {
+        uint64_t v;
+        std::memcpy(&v, b + o, 8);
+        if (v < arena_ || v >= arena_ + cfg_.arena_bytes) continue;
+        int r = owner_[(v - arena_) / gran_];
+        if (r < 0) continue;
+        if (std::find(rows->begin(), rows->end(), r) == rows->end()) rows->push_back(r);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- physical memory
+void SwapEngine::trim_phys_pool(uint64_t need) {
+    const DriverTable &d = drv();
+    while (!phys_pool_.empty() && resident_mapped_ + phys_pool_bytes_ + need > cfg_.resident_cap) {
+        auto it = std::prev(phys_pool_.end());
+        d.cuMemRelease(it->second);
+        phys_pool_bytes_ -= it->first;
+        phys_pool_.erase(it);
+    }
+}
+CUresult SwapEngine::get_phys(size_t mapped, CUmemGenericAllocationHandle *h) {
+    const DriverTable &d = drv();
+    auto it = phys_pool_.find(mapped);
+    if (it != phys_pool_.end()) {
+        *h = it->second;
+        phys_pool_bytes_ -= mapped;
+        phys_pool_.erase(it);
+        st_.phys_reuses++;
+        return CUDA_SUCCESS;
+    }
+    trim_phys_pool(mapped);
+    CUmemAllocationProp prop = {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = dev_;
+    CUresult r = d.cuMemCreate(h, mapped, &prop, 0);
+    if (r == CUDA_ERROR_OUT_OF_MEMORY && !phys_pool_.empty()) {
+        for (auto &p : phys_pool_) d.cuMemRelease(p.second);
+        phys_pool_.clear();
+        phys_pool_bytes_ = 0;
+        r = d.cuMemCreate(h, mapped, &prop, 0);
+    }
+    if (r == CUDA_SUCCESS) st_.phys_creates++;
+    return r;
+}
+CUresult SwapEngine::map_row(int row) {
+    const DriverTable &d = drv();
+    Side &s = side_[row];
+    CUmemGenericAllocationHandle h;
+    CUresult r = get_phys(s.mapped, &h);
+    if (r != CUDA_SUCCESS) return r;
+    r = d.cuMemMap(rows_[row].base, s.mapped, 0, h, 0);
+    if (r != CUDA_SUCCESS) { d.cuMemRelease(h); LOG_ERROR("cuMemMap failed: %d %s", (int)r, cu_err(r)); return r; }
+    CUmemAccessDesc acc = {};
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = dev_;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    r = d.cuMemSetAccess(rows_[row].base, s.mapped, &acc, 1);
+    if (r != CUDA_SUCCESS) { d.cuMemUnmap(rows_[row].base, s.mapped); d.cuMemRelease(h); LOG_ERROR("cuMemSetAccess failed: %d %s", (int)r, cu_err(r)); return r; }
+    s.handle = h;
+    s.has_handle = true;
+    resident_mapped_ += s.mapped;
+    return CUDA_SUCCESS;
+}
+void SwapEngine::unmap_row(int row) {
+    const DriverTable &d = drv();
+    Side &s = side_[row];
+    d.cuMemUnmap(rows_[row].base, s.mapped);
+    phys_pool_.emplace(s.mapped, s.handle);
+    phys_pool_bytes_ += s.mapped;
+    s.has_handle = false;
+    resident_mapped_ -= s.mapped;
+}
+
+// ---------------------------------------------------------------------------------------------- events / rings
+CUevent SwapEngine::use_event(uint64_t seq) {
+    if (seq == 0) return nullptr;
+    if (seq + use_ring_.size() <= use_seq_) return nullptr;  // slot was recycled: that use is known complete (note_use)
+    return use_ring_[seq % use_ring_.size()];
+}
+SwapEngine::Slot &SwapEngine::acquire_slot(std::vector<Slot> &ring, int *cursor) {
+    Slot &s = ring[*cursor];
+    *cursor = (*cursor + 1) % (int)ring.size();
+    if (s.used) drv().cuEventSynchronize(s.busy);  // back-pressure: the only place the host waits for the link
+    s.used = true;
+    s.seq++;
+    return s;
+}
+void SwapEngine::prof_begin(CUstream s, CUevent *a) {
+    *a = nullptr;
+    if (!cfg_.profile) return;
+    const DriverTable &d = drv();
+    if (d.cuEventCreate(a, CU_EVENT_DEFAULT) != CUDA_SUCCESS) { *a = nullptr; return; }
+    d.cuEventRecord(*a, s);
+}
+void SwapEngine::prof_end(CUstream s, CUevent a, bool unpack, uint64_t bytes) {
+    if (!a) return;
+    const DriverTable &d = drv();
+    CUevent b;
+    if (d.cuEventCreate(&b, CU_EVENT_DEFAULT) != CUDA_SUCCESS) { d.cuEventDestroy_v2(a); return; }
+    d.cuEventRecord(b, s);
+    prof_.push_back(Prof{a, b, unpack, bytes});
+    if (prof_.size() > 4096) harvest_prof(false);
+}
+void SwapEngine::harvest_prof(bool wait) {
+    const DriverTable &d = drv();
+    size_t keep = 0;
+    for (size_t i = 0; i < prof_.size(); i++) {
+        Prof &p = prof_[i];
+        if (wait) d.cuEventSynchronize(p.b);
+        if (d.cuEventQuery(p.b) == CUDA_SUCCESS) {
+            float ms = 0;
+            if (d.cuEventElapsedTime(&ms, p.a, p.b) == CUDA_SUCCESS) {
+                if (p.unpack) { st_.unpack_ms += ms; st_.unpack_bytes += p.bytes; }
+                else { st_.pack_ms += ms; st_.pack_bytes += p.bytes; }
+            }
+            d.cuEventDestroy_v2(p.a);
+            d.cuEventDestroy_v2(p.b);
+        } else {
+            prof_[keep++] = p;
+        }
+    }
+    prof_.resize(keep);
+}
+
+// ---------------------------------------------------------------------------------------------- page-out / page-in
+CUresult SwapEngine::page_out(const std::vector<uint32_t> &victims) {
+    const DriverTable &d = drv();
+    if (victims.empty()) return CUDA_SUCCESS;
+    // one contiguous pinned block for the whole batch so the staging layout equals the host layout (one DMA per
+    // chunk even when the victims are many small buffers); fall back to one block per victim when fragmented
+    std::vector<uint64_t> len(victims.size());
+    uint64_t total = 0;
+    for (size_t i = 0; i < victims.size(); i++) { len[i] = round_up(rows_[victims[i]].size, 256); total += len[i]; }
+    uint64_t block = 0;
+    bool contiguous = host_alloc(total, &block);
+    if (contiguous) {
+        uint64_t o = 0;
+        for (size_t i = 0; i < victims.size(); i++) { side_[victims[i]].host_off = block + o; o += len[i]; }
+    } else {
+        if (victims.size() == 1) { LOG_ERROR("pinned host pool exhausted (%lu MiB in use)", (unsigned long)(host_used_ >> 20)); return CUDA_ERROR_OUT_OF_MEMORY; }
+        for (uint32_t v : victims) { CUresult r = page_out(std::vector<uint32_t>{v}); if (r != CUDA_SUCCESS) return r; }
+        return CUDA_SUCCESS;
+    }
+    // order the pack behind the victims' last users
+    for (uint32_t v : victims)
+        if (CUevent e = use_event(side_[v].use_seq)) d.cuStreamWaitEvent(s_kern_, e, 0);
+
+    std::vector<PackSegment> segs;
+    Slot *slot = nullptr;
+    uint64_t pos = 0, host_pos = 0, slot_host_start = 0;
+    auto flush = [&]() -> CUresult {
+        if (!slot || segs.empty()) return CUDA_SUCCESS;
+        int launches = 0;
+        CUevent pa;
+        prof_begin(s_kern_, &pa);
+        CUresult r = launch_pack(k_, segs.data(), segs.size(), s_kern_, &launches);
+        if (r != CUDA_SUCCESS) return r;
+        prof_end(s_kern_, pa, false, pos);
+        st_.pack_launches += launches;
+        // slot.busy doubles as "packed" marker for the copy stream, then is re-recorded as "drained"
+        CU_TRY(d.cuEventRecord(slot->busy, s_kern_));
+        CU_TRY(d.cuStreamWaitEvent(s_out_, slot->busy, 0));
+        CU_TRY(d.cuMemcpyDtoHAsync_v2(host_ptr(block) + slot_host_start, slot->buf, pos, s_out_));
+        CU_TRY(d.cuEventRecord(slot->busy, s_out_));
+        st_.page_out_bytes += pos;
+        segs.clear();
+        slot = nullptr;
+        return CUDA_SUCCESS;
+    };
+    for (size_t i = 0; i < victims.size(); i++) {
+        uint64_t off = 0;
+        while (off < len[i]) {
+            if (!slot) { slot = &acquire_slot(ring_out_, &cur_out_); pos = 0; slot_host_start = host_pos; }
+            uint64_t piece = std::min<uint64_t>(len[i] - off, cfg_.chunk_bytes - pos);
+            segs.push_back(PackSegment{rows_[victims[i]].base + off, slot->buf + pos, piece});
+            side_[victims[i]].out_slot = (int)(slot - ring_out_.data());
+            side_[victims[i]].out_seq = slot->seq;
+            off += piece; pos += piece; host_pos += piece;
+            if (pos == cfg_.chunk_bytes || segs.size() == VGPU_PACK_MAX_SEG) { CUresult r = flush(); if (r != CUDA_SUCCESS) return r; }
+        }
+    }
+    { CUresult r = flush(); if (r != CUDA_SUCCESS) return r; }
+    // the victims' physical pages may be recycled as soon as the LAST PACK has read them — not when the DMA is done
+    CUevent packed = nullptr;
+    if (!ready_free_.empty()) { packed = ready_free_.back(); ready_free_.pop_back(); }
+    else CU_TRY(d.cuEventCreate(&packed, CU_EVENT_DISABLE_TIMING));
+    CU_TRY(d.cuEventRecord(packed, s_kern_));
+    CU_TRY(d.cuEventSynchronize(packed));
+    ready_free_.push_back(packed);
+    for (size_t i = 0; i < victims.size(); i++) {
+        uint32_t v = victims[i];
+        unmap_row((int)v);
+        side_[v].has_host = true;
+        rows_[v].state = VGPU_ST_PAGED_OUT;
+        rows_[v].host_slot = (uint32_t)(side_[v].host_off >> 12);
+        if (side_[v].ready) { ready_free_.push_back(side_[v].ready); side_[v].ready = nullptr; }
+        mark_dirty((int)v);
+        st_.evictions++;
+    }
+    return CUDA_SUCCESS;
+}
+
+CUresult SwapEngine::page_in(const std::vector<int> &rows) {
+    const DriverTable &d = drv();
+    for (int r : rows) {
+        CUresult rc = map_row(r);
+        if (rc != CUDA_SUCCESS) return rc;
+        // a row that was paged out moments ago: its D2H may still be in flight -> order the H2D behind that chunk
+        // only (not behind the whole page-out queue, which would serialise the two link directions)
+        Side &s = side_[r];
+        if (s.out_slot >= 0 && ring_out_[s.out_slot].seq == s.out_seq) CU_TRY(d.cuStreamWaitEvent(s_in_, ring_out_[s.out_slot].busy, 0));
+        s.out_slot = -1;
+    }
+    std::vector<PackSegment> segs;
+    Slot *slot = nullptr;
+    uint64_t pos = 0;
+    // pending host->staging copy run (merged while both sides stay contiguous)
+    unsigned char *run_src = nullptr; uint64_t run_dst = 0, run_len = 0;
+    auto flush_run = [&]() -> CUresult {
+        if (!run_len) return CUDA_SUCCESS;
+        CU_TRY(d.cuMemcpyHtoDAsync_v2(slot->buf + run_dst, run_src, run_len, s_in_));
+        st_.page_in_bytes += run_len;
+        run_len = 0;
+        return CUDA_SUCCESS;
+    };
+    auto flush = [&]() -> CUresult {
+        if (!slot || segs.empty()) return CUDA_SUCCESS;
+        CUresult r = flush_run();
+        if (r != CUDA_SUCCESS) return r;
+        CU_TRY(d.cuEventRecord(slot->busy, s_in_));
+        CU_TRY(d.cuStreamWaitEvent(s_kern_, slot->busy, 0));
+        int launches = 0;
+        CUevent pa;
+        prof_begin(s_kern_, &pa);
+        r = launch_pack(k_, segs.data(), segs.size(), s_kern_, &launches);
+        if (r != CUDA_SUCCESS) return r;
+        prof_end(s_kern_, pa, true, pos);
+        st_.unpack_launches += launches;
+        CU_TRY(d.cuEventRecord(slot->busy, s_kern_));
+        segs.clear();
+        slot = nullptr;
+        return CUDA_SUCCESS;
+    };
+    for (int r : rows) {
+        uint64_t len = round_up(rows_[r].size, 256), off = 0;
+        while (off < len) {
+            if (!slot) { slot = &acquire_slot(ring_in_, &cur_in_); pos = 0; }
+            uint64_t piece = std::min<uint64_t>(len - off, cfg_.chunk_bytes - pos);
+            unsigned char *src = host_ptr(side_[r].host_off) + off;
+            if (run_len && run_src + run_len == src && run_dst + run_len == pos) run_len += piece;
+            else { CUresult rc = flush_run(); if (rc != CUDA_SUCCESS) return rc; run_src = src; run_dst = pos; run_len = piece; }
+            segs.push_back(PackSegment{slot->buf + pos, rows_[r].base + off, piece});
+            off += piece; pos += piece;
+            if (pos == cfg_.chunk_bytes || segs.size() == VGPU_PACK_MAX_SEG) { CUresult rc = flush(); if (rc != CUDA_SUCCESS) return rc; }
+        }
+        // completion marker for this row: everything enqueued on s_kern_ so far includes its last unpack once flushed
+        CUresult rc = flush();
+        if (rc != CUDA_SUCCESS) return rc;
+        CUevent ev = nullptr;
+        if (!ready_free_.empty()) { ev = ready_free_.back(); ready_free_.pop_back(); }
+        else CU_TRY(d.cuEventCreate(&ev, CU_EVENT_DISABLE_TIMING));
+        CU_TRY(d.cuEventRecord(ev, s_kern_));
+        side_[r].ready = ev;
+        // the pinned range is reusable once the H2D copies have read it: s_out_ (the only writer of the pool) is
+        // ordered behind this point of s_in_ before the range is handed out again
+        pending_host_.push_back(PendingHost{side_[r].host_off, round_up(rows_[r].size, 256)});
+        side_[r].has_host = false;
+        rows_[r].state = VGPU_ST_RESIDENT;
+        mark_dirty(r);
+    }
+    if (!pending_host_.empty()) {
+        // one event orders every later D2H behind the H2D reads issued above, then the ranges return to the pool
+        CUevent ev = nullptr;
+        if (!ready_free_.empty()) { ev = ready_free_.back(); ready_free_.pop_back(); }
+        else CU_TRY(d.cuEventCreate(&ev, CU_EVENT_DISABLE_TIMING));
+        CU_TRY(d.cuEventRecord(ev, s_in_));
+        CU_TRY(d.cuStreamWaitEvent(s_out_, ev, 0));
+        ready_free_.push_back(ev);
+        for (auto &p : pending_host_) release_host_range(p.off, p.len);
+        pending_host_.clear();
+    }
+    return CUDA_SUCCESS;
+}
+
+void SwapEngine::release_host_range(uint64_t off, uint64_t len) {
+    // page_out carves one block per batch; every victim gives back exactly its own 256-byte-granular sub-range
+    map_free(slabs_[off >> 44].free, off & ((1ull << 44) - 1), len);
+    host_used_ = host_used_ > len ? host_used_ - len : 0;
+}
+
+CUresult SwapEngine::make_room(uint64_t need_mapped) {
+    if (need_mapped > cfg_.resident_cap) return CUDA_ERROR_OUT_OF_MEMORY;
+    if (resident_mapped_ + need_mapped <= cfg_.resident_cap) { trim_phys_pool(need_mapped); return CUDA_SUCCESS; }
+    uint64_t deficit = resident_mapped_ + need_mapped - cfg_.resident_cap;
+    CUresult r = sync_table(s_kern_);
+    if (r != CUDA_SUCCESS) return r;
+    std::vector<uint32_t> victims;
+    uint64_t freed = 0;
+    bool insufficient = false;
+    int launches = 0;
+    r = scanner_->scan(d_tbl_, (uint32_t)rows_.size(), deficit, tick_, s_kern_, &victims, &freed, &insufficient, &launches);
+    st_.scan_launches += launches;
+    st_.scans++;
+    if (r != CUDA_SUCCESS) { LOG_ERROR("victim scan failed: %d %s", (int)r, cu_err(r)); return r; }
+    if (insufficient) {
+        LOG_ERROR("resident quota %lu MiB cannot hold the working set of this launch (need %lu MiB more, evictable %lu MiB)",
+                  (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(deficit >> 20), (unsigned long)(freed >> 20));
+        return CUDA_ERROR_OUT_OF_MEMORY;
+    }
+    r = page_out(victims);
+    if (r != CUDA_SUCCESS) return r;
+    trim_phys_pool(need_mapped);
+    return CUDA_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------------------------- public operations
+CUresult SwapEngine::alloc(CUdeviceptr *dptr, size_t bytes) {
+    if (!dptr || bytes == 0) return CUDA_ERROR_INVALID_VALUE;
+    std::lock_guard<std::mutex> g(mu_);
+    if (cfg_.virtual_cap && live_bytes_ + bytes > cfg_.virtual_cap) return CUDA_ERROR_OUT_OF_MEMORY;
+    uint64_t mapped = round_up(bytes, gran_);
+    uint64_t off;
+    if (!va_alloc(mapped, &off)) { LOG_ERROR("swap arena exhausted"); return CUDA_ERROR_OUT_OF_MEMORY; }
+    CUresult r = make_room(mapped);
+    if (r != CUDA_SUCCESS) { va_free(off, mapped); return r; }
+    int row = new_row();
+    rows_[row] = VgpuEntry{arena_ + off, bytes, ++tick_, VGPU_ST_RESIDENT, 0};
+    side_[row] = Side{};
+    side_[row].mapped = mapped;
+    side_[row].va_off = off;
+    r = map_row(row);
+    if (r != CUDA_SUCCESS) {
+        rows_[row].state = VGPU_ST_FREE;
+        free_rows_.push_back(row);
+        va_free(off, mapped);
+        return r;
+    }
+    for (uint64_t gidx = off / gran_; gidx < (off + mapped) / gran_; gidx++) owner_[gidx] = row;
+    mark_dirty(row);
+    live_bytes_ += bytes;
+    *dptr = arena_ + off;
+    return CUDA_SUCCESS;
+}
+
+CUresult SwapEngine::free(CUdeviceptr dptr) {
+    const DriverTable &d = drv();
+    if (!owns(dptr)) return CUDA_ERROR_INVALID_VALUE;
+    std::lock_guard<std::mutex> g(mu_);
+    int row = owner_[(dptr - arena_) / gran_];
+    if (row < 0 || rows_[row].base != dptr) return CUDA_ERROR_INVALID_VALUE;
+    Side &s = side_[row];
+    if (CUevent e = use_event(s.use_seq)) d.cuEventSynchronize(e);
+    if (s.ready) { d.cuEventSynchronize(s.ready); ready_free_.push_back(s.ready); s.ready = nullptr; }
+    if (rows_[row].state & VGPU_ST_RESIDENT) unmap_row(row);
+    else if (s.has_host) release_host_range(s.host_off, round_up(rows_[row].size, 256));
+    for (uint64_t gidx = s.va_off / gran_; gidx < (s.va_off + s.mapped) / gran_; gidx++) owner_[gidx] = -1;
+    va_free(s.va_off, s.mapped);
+    live_bytes_ -= rows_[row].size;
+    rows_[row].state = VGPU_ST_FREE;
+    rows_[row].size = 0;
+    mark_dirty(row);
+    free_rows_.push_back(row);
+    return CUDA_SUCCESS;
+}
+
+CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
+    const DriverTable &d = drv();
+    std::lock_guard<std::mutex> g(mu_);
+    st_.admissions++;
+    tick_++;
+    std::vector<int> missing;
+    uint64_t need = 0;
+    for (int i = 0; i < n; i++) {
+        int r = rows[i];
+        rows_[r].last_touch = tick_;
+        side_[r].pins++;
+        if (rows_[r].state & VGPU_ST_RESIDENT) rows_[r].state = VGPU_ST_RESIDENT | VGPU_ST_PINNED;
+        else { missing.push_back(r); need += side_[r].mapped; }
+        mark_dirty(r);
+    }
+    if (!missing.empty()) {
+        st_.faults += missing.size();
+        CUresult r = make_room(need);
+        if (r == CUDA_SUCCESS) r = page_in(missing);
+        if (r != CUDA_SUCCESS) {
+            for (int i = 0; i < n; i++) {
+                Side &s = side_[rows[i]];
+                if (--s.pins == 0 && (rows_[rows[i]].state & VGPU_ST_RESIDENT)) rows_[rows[i]].state = VGPU_ST_RESIDENT;
+            }
+            return r;
+        }
+        for (int r2 : missing) rows_[r2].state = VGPU_ST_RESIDENT | VGPU_ST_PINNED;
+    }
+    for (int i = 0; i < n; i++) {
+        Side &s = side_[rows[i]];
+        if (!s.ready) continue;
+        if (d.cuEventQuery(s.ready) == CUDA_SUCCESS) { ready_free_.push_back(s.ready); s.ready = nullptr; }
+        else d.cuStreamWaitEvent(stream, s.ready, 0);
+    }
+    return CUDA_SUCCESS;
+}
+
+void SwapEngine::note_use(const int *rows, int n, CUstream stream) {
+    const DriverTable &d = drv();
+    std::lock_guard<std::mutex> g(mu_);
+    uint64_t seq = ++use_seq_;
+    CUevent ev = use_ring_[seq % use_ring_.size()];
+    // the slot's previous owner (seq - ring size) is only forgotten once it is known complete, see use_event()
+    if (seq > use_ring_.size()) d.cuEventSynchronize(ev);
+    d.cuEventRecord(ev, stream);
+    for (int i = 0; i < n; i++) {
+        Side &s = side_[rows[i]];
+        s.use_seq = seq;
+        if (s.pins > 0 && --s.pins == 0 && (rows_[rows[i]].state & VGPU_ST_RESIDENT)) {
+            rows_[rows[i]].state = VGPU_ST_RESIDENT;
+            mark_dirty(rows[i]);
+        }
+    }
+}
+
+CUresult SwapEngine::drain() {
+    const DriverTable &d = drv();
+    std::lock_guard<std::mutex> g(mu_);
+    CUresult r = CUDA_SUCCESS, t;
+    if (s_kern_ && (t = d.cuStreamSynchronize(s_kern_)) != CUDA_SUCCESS) r = t;
+    if (s_out_ && (t = d.cuStreamSynchronize(s_out_)) != CUDA_SUCCESS) r = t;
+    if (s_in_ && (t = d.cuStreamSynchronize(s_in_)) != CUDA_SUCCESS) r = t;
+    harvest_prof(true);
+    return r;
+}
+
+SwapStats SwapEngine::stats() {
+    std::lock_guard<std::mutex> g(mu_);
+    harvest_prof(false);
+    SwapStats s = st_;
+    s.resident_bytes = resident_mapped_;
+    s.live_bytes = live_bytes_;
+    s.host_bytes = host_used_;
+    s.entries = rows_.size() - free_rows_.size();
+    return s;
+}
+
+std::vector<VgpuEntry> SwapEngine::snapshot_table() {
+    std::lock_guard<std::mutex> g(mu_);
+    return rows_;
+}
+
+}  // namespace vgpu

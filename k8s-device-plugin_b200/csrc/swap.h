@@ -1,0 +1,156 @@
+// swap.h — the virtual-device-memory swap engine (one per device/context).
+//
+// Behind the same switch as the reference's oversubscription (CUDA_OVERSUBSCRIBE=true -> allocmode 0,
+// postInit libvgpu.so@0x15d63; large allocations then go through cuMemoryAllocate@0x315da), but where the
+// reference hands the problem to CUDA UVM (cuMemAllocManaged; victim choice and page traffic inside the NVIDIA
+// kernel driver on host cores), this engine keeps explicit control:
+//   * every swappable allocation is a stable virtual range (cuMemAddressReserve arena) backed by VMM physical
+//     handles that are mapped only while the buffer is resident;
+//   * a device-resident allocation table (32-byte rows) records residency and a logical LRU clock;
+//   * when an admission (kernel launch / memcpy / new allocation) needs more physical memory than the container's
+//     resident quota allows, a GPU victim scan picks exact-LRU victims, a TMA pack kernel compacts them into a
+//     staging ring in HBM, and a copy stream drains the ring to pinned host memory while the next chunk is packed;
+//     page-in is the mirror image (pinned host -> staging ring -> unpack kernel into the re-mapped range);
+//   * nothing on the host ever waits for a PCIe transfer except for ring back-pressure: the application stream is
+//     ordered behind the page-in with events.
+#pragma once
+#include <cuda.h>
+
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "kernels.h"
+#include "kmod.h"
+
+namespace vgpu {
+
+struct SwapConfig {
+    uint64_t resident_cap = 0;            // bytes of physical backing the container may hold (its gpumem quota); 0 = device free memory
+    uint64_t virtual_cap = 0;             // live swappable bytes allowed; 0 = bounded by host pool only
+    uint64_t host_pool_cap = 0;           // pinned bytes allowed; 0 = unbounded
+    size_t chunk_bytes = 32u << 20;       // staging slot size (one DMA)
+    int ring_slots = 4;                   // staging slots per direction
+    size_t slab_bytes = 1ull << 30;       // pinned pool growth unit
+    uint64_t arena_bytes = 1ull << 40;    // virtual address arena
+    bool profile = false;                 // bracket pack/unpack launches with events (bench roofline)
+    static SwapConfig from_env(uint64_t resident_cap, uint64_t virtual_cap);
+};
+
+struct SwapStats {
+    uint64_t page_out_bytes = 0, page_in_bytes = 0;
+    uint64_t evictions = 0, faults = 0, admissions = 0;
+    uint64_t pack_launches = 0, unpack_launches = 0, scan_launches = 0, scans = 0;
+    uint64_t resident_bytes = 0, live_bytes = 0, host_bytes = 0, entries = 0;
+    uint64_t phys_creates = 0, phys_reuses = 0;
+    double pack_ms = 0, unpack_ms = 0;     // device time, only when profiling
+    uint64_t pack_bytes = 0, unpack_bytes = 0;
+};
+
+class SwapEngine {
+   public:
+    // Must be called with the target context current. Returns nullptr (and logs) on failure.
+    static SwapEngine *create(int dev, const SwapConfig &cfg);
+    ~SwapEngine();
+
+    CUresult alloc(CUdeviceptr *dptr, size_t bytes);
+    CUresult free(CUdeviceptr dptr);            // CUDA_ERROR_INVALID_VALUE when not one of ours
+    bool owns(CUdeviceptr p) const { return p >= arena_ && p < arena_ + cfg_.arena_bytes; }
+    int lookup(CUdeviceptr p) const;            // row index of the allocation containing p, or -1
+
+    // Makes every listed row resident and orders `stream` after the page-ins. Rows stay pinned (not evictable)
+    // until note_use() is called with the same list after the real launch has been enqueued.
+    CUresult ensure_resident(const int *rows, int n, CUstream stream);
+    void note_use(const int *rows, int n, CUstream stream);
+    // Scans kernel parameter bytes for pointers into the arena; appends distinct row indices.
+    void collect_rows(const void *param, size_t bytes, std::vector<int> *rows) const;
+
+    SwapStats stats();
+    void set_profile(bool on) { cfg_.profile = on; }
+    CUresult drain();                          // wait for all side-stream work (tests / shutdown)
+    const SwapConfig &config() const { return cfg_; }
+    uint64_t live_bytes() const { return live_bytes_; }
+
+    // test hook: copy of the host mirror of the table
+    std::vector<VgpuEntry> snapshot_table();
+
+   private:
+    struct Side {                // host-only companion of a table row
+        size_t mapped = 0;
+        CUmemGenericAllocationHandle handle = 0;
+        bool has_handle = false;
+        uint64_t host_off = 0;   // pinned pool location while paged out
+        bool has_host = false;
+        CUevent ready = nullptr; // pending page-in completion (owned by ready_pool_)
+        uint64_t use_seq = 0;    // sequence number of the last-use event
+        int pins = 0;
+        uint64_t va_off = 0;
+        int out_slot = -1;       // staging slot of the last page-out chunk of this row ...
+        uint64_t out_seq = 0;    // ... and that slot's use counter at the time (stale => the D2H is known complete)
+    };
+    struct Slab { unsigned char *host = nullptr; size_t bytes = 0; std::map<uint64_t, uint64_t> free; };
+    struct Slot { CUdeviceptr buf = 0; CUevent busy = nullptr; bool used = false; uint64_t seq = 0; };
+    struct PendingHost { uint64_t off, len; };
+
+    SwapEngine() = default;
+    bool init(int dev, const SwapConfig &cfg);
+    int new_row();
+    void mark_dirty(int row);
+    CUresult sync_table(CUstream s);
+    CUresult make_room(uint64_t need_mapped);
+    CUresult page_out(const std::vector<uint32_t> &victims);
+    CUresult page_in(const std::vector<int> &rows);
+    CUresult map_row(int row);
+    void unmap_row(int row);
+    CUresult get_phys(size_t mapped, CUmemGenericAllocationHandle *h);
+    void trim_phys_pool(uint64_t need);
+    bool host_alloc(size_t bytes, uint64_t *off);
+    void release_host_range(uint64_t off, uint64_t len);
+    unsigned char *host_ptr(uint64_t off);
+    bool va_alloc(size_t bytes, uint64_t *off);
+    void va_free(uint64_t off, size_t bytes);
+    CUevent use_event(uint64_t seq);
+    Slot &acquire_slot(std::vector<Slot> &ring, int *cursor);
+    void prof_begin(CUstream s, CUevent *a);
+    void prof_end(CUstream s, CUevent a, bool unpack, uint64_t bytes);
+    void harvest_prof(bool wait);
+
+    mutable std::mutex mu_;
+    int dev_ = 0;
+    SwapConfig cfg_;
+    const Kernels *k_ = nullptr;
+    size_t gran_ = 2u << 20;
+    CUdeviceptr arena_ = 0;
+    std::map<uint64_t, uint64_t> va_free_;          // offset -> len
+    std::vector<int32_t> owner_;                    // granule -> row (or -1)
+
+    std::vector<VgpuEntry> rows_;                   // host mirror (authoritative)
+    std::vector<Side> side_;
+    std::vector<int> free_rows_;
+    CUdeviceptr d_tbl_ = 0;
+    uint32_t tbl_cap_ = 0;
+    uint32_t dirty_lo_ = UINT32_MAX, dirty_hi_ = 0;
+    VgpuEntry *h_tbl_stage_ = nullptr;              // pinned upload buffer
+    uint64_t tick_ = 0;
+
+    uint64_t resident_mapped_ = 0, live_bytes_ = 0, host_used_ = 0;
+    std::multimap<size_t, CUmemGenericAllocationHandle> phys_pool_;
+    uint64_t phys_pool_bytes_ = 0;
+    std::vector<Slab> slabs_;
+
+    CUstream s_kern_ = nullptr, s_out_ = nullptr, s_in_ = nullptr;
+    std::vector<Slot> ring_out_, ring_in_;
+    int cur_out_ = 0, cur_in_ = 0;
+    std::vector<CUevent> use_ring_;                 // last-use events, indexed by seq % size
+    uint64_t use_seq_ = 0;
+    std::vector<CUevent> ready_free_;
+    std::unique_ptr<VictimScanner> scanner_;
+    std::vector<PendingHost> pending_host_;
+    SwapStats st_;
+    struct Prof { CUevent a, b; bool unpack; uint64_t bytes; };
+    std::vector<Prof> prof_;
+};
+
+}  // namespace vgpu
