@@ -208,6 +208,7 @@ EXPORT CUresult cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned 
 }
 static int g_mod_obj, g_fn_obj;
 EXPORT CUresult cuModuleLoadData(CUmodule *m, const void *img) { (void)img; *m = &g_mod_obj; return CUDA_SUCCESS; }
+EXPORT CUresult cuModuleLoad(CUmodule *m, const char *path) { (void)path; *m = &g_mod_obj; return CUDA_SUCCESS; }
 EXPORT CUresult cuModuleLoadDataEx(CUmodule *m, const void *img, unsigned n, void *o, void **v) { (void)img; (void)n; (void)o; (void)v; *m = &g_mod_obj; return CUDA_SUCCESS; }
 EXPORT CUresult cuModuleGetFunction(CUfunction *f, CUmodule m, const char *name) { (void)m; (void)name; *f = &g_fn_obj; return CUDA_SUCCESS; }
 EXPORT CUresult cuModuleUnload(CUmodule m) { (void)m; return CUDA_SUCCESS; }

@@ -1,0 +1,131 @@
+"""The PRODUCT's accounting (libvgpu.so, LD_PRELOADed into a driver-API trace replayer running on the fake driver)
+against the reference: golden streams recorded from the reference binary, the CPU restatement, and the reference
+binary live when present. Bit-exact: return codes and every counter word of the shared region after every op
+(SURVEY.md §8d cfg 2). No GPU involved — this is host logic."""
+import gzip
+import hashlib
+import json
+import os
+import subprocess
+
+import pytest
+from conftest import FAKE, GOLDEN, HOOK_SO, LIBDIR, OREF, have_reference, run_replay
+from trace_gen import gen_trace
+
+
+def _write(tmp_path, text):
+    p = tmp_path / "trace.txt"
+    p.write_text(text)
+    return str(p)
+
+
+def _env(tmp_path, limit="8192m", **kw):
+    e = {"CUDA_DEVICE_MEMORY_SHARED_CACHE": str(tmp_path / "new.cache")}
+    if limit is not None:
+        e["CUDA_DEVICE_MEMORY_LIMIT_0"] = limit
+    e.update(kw)
+    return e
+
+
+@pytest.mark.parametrize("name,n,seed,kinds", [("ref_trace_2k.out.gz", 2000, 0xB200, "A"), ("ref_trace_mixed.out.gz", 1500, 7, "AAMP")])
+def test_new_hook_stream_equals_golden_reference_stream(tmp_path, name, n, seed, kinds):
+    want = gzip.open(os.path.join(GOLDEN, name), "rt").read()
+    got = run_replay(_write(tmp_path, gen_trace(n, seed=seed, kinds=kinds)), "new", _env(tmp_path))
+    assert got == want
+
+
+def test_new_hook_cfg2_100k_ops_bit_exact(tmp_path):
+    """BASELINE.json configs[1] at full size: 100 000 ops, 8 GiB cap."""
+    h = json.load(open(os.path.join(GOLDEN, "ref_hashes.json")))
+    big = _write(tmp_path, gen_trace(100000, seed=0xB200))
+    got = run_replay(big, "new", _env(tmp_path))
+    assert hashlib.sha256(got.encode()).hexdigest() == h["cfg2_100k_limit8192m"]
+    mixed = _write(tmp_path, gen_trace(20000, seed=7, kinds="AAMP"))
+    got = run_replay(mixed, "new", _env(tmp_path))
+    assert hashlib.sha256(got.encode()).hexdigest() == h["mixed_20k_limit8192m"]
+
+
+def test_new_hook_equals_oracle_on_other_limits(tmp_path):
+    for lim, ctx in (("1g", "100"), ("300m", "64"), ("64g", "512")):
+        t = _write(tmp_path, gen_trace(4000, seed=hash(lim) & 0xFFFF, kinds="AAMP", max_size=256 << 20))
+        env = _env(tmp_path, lim, FAKE_GPU_CTX_MIB=ctx)
+        assert run_replay(t, "new", env) == run_replay(t, "oracle", env), lim
+        os.remove(env["CUDA_DEVICE_MEMORY_SHARED_CACHE"])
+
+
+def test_oom_boundary_is_strict(tmp_path):
+    # usage + size == limit is admitted, one byte more is refused with the reference's (CUresult)-1
+    t = _write(tmp_path, "A 0 1048576\nA 1 %d\nA 2 1\nF 1\nM 3 %d\nM 4 1\nI\n" % ((64 << 20) - (1 << 20) - (16 << 20), (64 << 20) - (1 << 20) - (16 << 20)))
+    env = _env(tmp_path, "64m", FAKE_GPU_CTX_MIB="16")
+    out = run_replay(t, "new", env).splitlines()
+    assert " rc=0 " in out[1] and " rc=0 " in out[2]
+    assert " rc=-1 " in out[3]          # cuMemAlloc_v2 breach: add_chunk@0x4005d
+    assert " rc=0 " in out[5] and " rc=2 " in out[6]   # cuMemAllocManaged breach: CUDA_ERROR_OUT_OF_MEMORY @0x31eab
+    assert out[7].endswith("free=0 total=67108864")
+    assert out == run_replay(t, "oracle", env).splitlines()
+
+
+def test_unlimited_container_deviation_total_mem(tmp_path):
+    """Documented deviation: the reference answers cuDeviceTotalMem_v2 with the limit even when it is 0
+    (cuDeviceTotalMem_v2@0x2d3f8); the product returns the real total for an unlimited container."""
+    t = _write(tmp_path, "A 0 4096\nT\n")
+    env = _env(tmp_path, None)
+    new = run_replay(t, "new", env).splitlines()
+    ora = run_replay(t, "oracle", env).splitlines()
+    assert new[:2] == ora[:2]
+    assert ora[2].endswith("total=0") and new[2].endswith("total=%d" % (183359 << 20))
+
+
+def test_strict_error_mode(tmp_path):
+    t = _write(tmp_path, "A 0 %d\nX 0x1234000\n" % (128 << 20))
+    out = run_replay(t, "new", _env(tmp_path, "64m", VGPU_STRICT_CUDA_ERRORS="1")).splitlines()
+    assert " rc=2 " in out[1]       # CUDA_ERROR_OUT_OF_MEMORY instead of -1
+    assert " rc=1 " in out[2]       # the driver's own CUDA_ERROR_INVALID_VALUE for a pointer it never handed out
+
+
+def test_control_can_be_disabled_per_container(tmp_path):
+    t = _write(tmp_path, "A 0 %d\n" % (128 << 20))
+    out = run_replay(t, "new", _env(tmp_path, "64m", CUDA_DISABLE_CONTROL="1")).splitlines()
+    # exported symbols still interpose a directly linked program; what the opt-out guarantees (server.go:380-385) is
+    # that the library is not preloaded at all — checked in the plugin tests. Here: the hook stays consistent.
+    assert " rc=-1 " in out[1]
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
+def test_new_hook_equals_reference_binary_live(tmp_path):
+    t = _write(tmp_path, gen_trace(3000, seed=99, kinds="AAAMP"))
+    env_new = _env(tmp_path, "2g", FAKE_GPU_CTX_MIB="200")
+    env_ref = dict(env_new, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "ref.cache"))
+    assert run_replay(t, "new", env_new) == run_replay(t, "reference", env_ref)
+
+
+def test_multi_process_container_shares_the_quota(tmp_path):
+    """Two processes of one container (same cache file): the second sees the first one's bytes in its quota."""
+    cache = str(tmp_path / "shared.cache")
+    env = dict(os.environ, LD_LIBRARY_PATH=FAKE, LD_PRELOAD=HOOK_SO, LIBCUDA_LOG_LEVEL="0",
+               CUDA_DEVICE_MEMORY_LIMIT_0="256m", CUDA_DEVICE_MEMORY_SHARED_CACHE=cache, FAKE_GPU_CTX_MIB="16")
+    holder = tmp_path / "hold.txt"
+    holder.write_text("A 0 %d\n" % (150 << 20) + "I\n" * 400000)   # keeps ~150 MiB for a while
+    p1 = subprocess.Popen([os.path.join(OREF, "trace_replay"), str(holder)], env=env, stdout=subprocess.DEVNULL)
+    try:
+        import time
+        import k8s_device_plugin_b200 as v
+        for _ in range(200):
+            time.sleep(0.05)
+            if os.path.exists(cache) and os.path.getsize(cache) >= v.REGION_SIZE:
+                with v.Region(cache) as r:
+                    if r.usage(0) >= (150 << 20):
+                        break
+        t = tmp_path / "second.txt"
+        t.write_text("A 0 %d\nA 1 %d\n" % (100 << 20, 50 << 20))
+        out = subprocess.run([os.path.join(OREF, "trace_replay"), str(t)], env=env, stdout=subprocess.PIPE, text=True).stdout.splitlines()
+        assert " rc=-1 " in out[1], out     # 16+150 (proc 1) + 16 (own ctx) + 100 > 256
+        assert " rc=0 " in out[2], out      # 50 MiB still fits
+    finally:
+        p1.kill()
+        p1.wait()
+    # the killed process never ran its exit handler: its slot is reclaimed on the next quota breach (rm_quitted_process)
+    t2 = tmp_path / "third.txt"
+    t2.write_text("A 0 %d\n" % (200 << 20))
+    out = subprocess.run([os.path.join(OREF, "trace_replay"), str(t2)], env=env, stdout=subprocess.PIPE, text=True).stdout.splitlines()
+    assert " rc=0 " in out[1], out

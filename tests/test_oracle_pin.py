@@ -1,0 +1,73 @@
+"""Pins the CPU restatement (oracle/vgpu_oracle.c) to the reference: against golden fixtures produced by EXECUTING the
+reference's shipped hook binary (tests/golden/make_golden.py), and — where the binary is present (build container) —
+against the binary live. The reference's own tests hold no vectors for this path."""
+import ctypes as C
+import gzip
+import hashlib
+import json
+import os
+
+import pytest
+from conftest import GOLDEN, OREF, have_reference, run_replay
+from trace_gen import gen_trace
+
+ORA = C.CDLL(os.path.join(OREF, "libvgpu_oracle.so"))
+ORA.vo_parse_limit.restype = C.c_uint64
+ORA.vo_parse_limit.argtypes = [C.c_char_p]
+ORA.vo_delta.restype = C.c_int32
+ORA.vo_delta.argtypes = [C.c_int32] * 6
+ORA.vo_total_cuda_cores.restype = C.c_int32
+ORA.vo_total_cuda_cores.argtypes = [C.c_int32, C.c_int32]
+
+
+def _write(tmp_path, text):
+    p = tmp_path / "trace.txt"
+    p.write_text(text)
+    return str(p)
+
+
+def test_kat_limit_parse_matches_reference_binary():
+    kat = json.load(open(os.path.join(GOLDEN, "ref_kat.json")))
+    for text, want in kat["limit"]:
+        assert ORA.vo_parse_limit(text.encode()) == want, text
+    # SURVEY.md Appendix E vectors, now confirmed by the binary
+    assert ORA.vo_parse_limit(b"8192m") == 8589934592
+    assert ORA.vo_parse_limit(b"1000k") == 1024000
+    assert ORA.vo_parse_limit(None) == 0
+
+
+def test_kat_delta_matches_reference_binary():
+    kat = json.load(open(os.path.join(GOLDEN, "ref_kat.json")))
+    assert ORA.vo_total_cuda_cores(148, 2048) == kat["total_cores"] == 9699328
+    for up, cur, share, want in kat["delta"]:
+        assert ORA.vo_delta(148, 2048, 9699328, up, cur, share) == want, (up, cur, share)
+    for up, cur, share, want in kat["delta_v100"]:
+        assert ORA.vo_delta(80, 2048, 80 * 2048 * 32, up, cur, share) == want, (up, cur, share)
+    # the int32 overflow on B200 that makes the share RISE while over quota (Appendix E)
+    assert ORA.vo_delta(148, 2048, 9699328, 30, 100, 5000000) == 7037212
+
+
+@pytest.mark.parametrize("name,n,seed,kinds", [("ref_trace_2k.out.gz", 2000, 0xB200, "A"), ("ref_trace_mixed.out.gz", 1500, 7, "AAMP")])
+def test_oracle_stream_equals_golden_reference_stream(tmp_path, name, n, seed, kinds):
+    want = gzip.open(os.path.join(GOLDEN, name), "rt").read()
+    got = run_replay(_write(tmp_path, gen_trace(n, seed=seed, kinds=kinds)), "oracle", {"CUDA_DEVICE_MEMORY_LIMIT_0": "8192m"})
+    assert got == want
+    assert "rc=-1" in want and ("rc=2" in want or kinds == "A")  # the fixtures do exercise quota breaches
+
+
+def test_oracle_100k_trace_hashes_equal_reference(tmp_path):
+    h = json.load(open(os.path.join(GOLDEN, "ref_hashes.json")))
+    big = _write(tmp_path, gen_trace(100000, seed=0xB200))
+    got = run_replay(big, "oracle", {"CUDA_DEVICE_MEMORY_LIMIT_0": "8192m"})
+    assert hashlib.sha256(got.encode()).hexdigest() == h["cfg2_100k_limit8192m"]
+    env = dict(os.environ)
+    env.pop("CUDA_DEVICE_MEMORY_LIMIT_0", None)
+    got = run_replay(big, "oracle", {"CUDA_DEVICE_MEMORY_LIMIT_0": ""})
+    assert hashlib.sha256(got.encode()).hexdigest() == h["cfg2_100k_unlimited"]
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
+def test_oracle_equals_reference_binary_live(tmp_path):
+    t = _write(tmp_path, gen_trace(3000, seed=1234, kinds="AAAMP"))
+    env = {"CUDA_DEVICE_MEMORY_LIMIT_0": "4g", "CUDA_DEVICE_MEMORY_SHARED_CACHE": str(tmp_path / "ref.cache"), "FAKE_GPU_CTX_MIB": "300"}
+    assert run_replay(t, "reference", env) == run_replay(t, "oracle", env)
