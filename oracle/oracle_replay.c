@@ -10,6 +10,7 @@ int main(int argc, char **argv) {
     const char *e;
     uint64_t limit = vo_parse_limit(getenv("CUDA_DEVICE_MEMORY_LIMIT_0") ? getenv("CUDA_DEVICE_MEMORY_LIMIT_0") : getenv("CUDA_DEVICE_MEMORY_LIMIT"));
     uint64_t ctx = ((e = getenv("FAKE_GPU_CTX_MIB")) ? strtoull(e, 0, 0) : 512ull) << 20;
+    if ((e = getenv("ORACLE_CTX_BYTES"))) ctx = strtoull(e, 0, 0);   /* exact context size measured on a real box */
     uint64_t tot = ((e = getenv("FAKE_GPU_TOTAL_MIB")) ? strtoull(e, 0, 0) : 183359ull) << 20;
     vo_state_t *s = vo_create(limit, ctx, tot);
     uint64_t c[5]; vo_counters(s, c);

@@ -1,0 +1,134 @@
+"""Swap engine on a real B200 through the C ABI: data integrity across page-out/page-in (the reference's contract for
+swap is exactly that — bytes read back equal bytes written), LRU behaviour, quota enforcement."""
+import ctypes as C
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+import k8s_device_plugin_b200 as v  # noqa: E402
+
+MiB = 1 << 20
+
+
+@pytest.fixture(scope="module", autouse=True)
+def ctx():
+    assert torch.cuda.is_available()
+    torch.zeros(1, device="cuda:0")
+    v.lib()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _fill(sw, p, nbytes, idx):
+    sw.acquire([p], _stream())
+    assert v.lib().vgpu_wl_fill(p, nbytes // 8, idx, C.c_void_p(_stream())) == 0
+    sw.release([p], _stream())
+
+
+def _touch(sw, p, nbytes):
+    sw.acquire([p], _stream())
+    assert v.lib().vgpu_wl_touch(p, nbytes // 8, C.c_void_p(_stream())) == 0
+    sw.release([p], _stream())
+
+
+def _verify(sw, bufs, sizes, touches):
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for i, p in enumerate(bufs):
+        sw.acquire([p], _stream())
+        assert v.lib().vgpu_wl_verify(p, sizes[i] // 8, i, touches[i], cnt.data_ptr(), C.c_void_p(_stream())) == 0
+        sw.release([p], _stream())
+    torch.cuda.synchronize()
+    return int(cnt.item())
+
+
+def test_cyclic_oversubscription_keeps_every_word():
+    sw = v.Swap(resident_cap=256 * MiB, chunk_bytes=16 * MiB, ring_slots=3)
+    n, nbytes = 12, 64 * MiB                       # 768 MiB live under a 256 MiB quota
+    bufs = [sw.alloc(nbytes) for _ in range(n)]
+    for i, p in enumerate(bufs):
+        _fill(sw, p, nbytes, i)
+    touches = [0] * n
+    for t in range(3 * n):                         # 3 sweeps, cyclic = every touch misses
+        _touch(sw, bufs[t % n], nbytes)
+        touches[t % n] += 1
+    assert _verify(sw, bufs, [nbytes] * n, touches) == 0
+    s = sw.stats()
+    assert s["resident_bytes"] <= 256 * MiB
+    assert s["faults"] >= 3 * n - 4 and s["evictions"] >= s["faults"] - 4
+    assert s["page_in_bytes"] == s["faults"] * nbytes
+    assert s["phys_reuses"] > 0                    # steady state recycles physical handles instead of create/release
+    for p in bufs:
+        sw.free(p)
+    assert sw.stats()["live_bytes"] == 0
+    sw.close()
+
+
+def test_ragged_sizes_and_multi_buffer_admission():
+    sw = v.Swap(resident_cap=128 * MiB, chunk_bytes=8 * MiB, ring_slots=2)
+    sizes = [3 * MiB + 8, 17 * MiB + 4096, 2 * MiB + 16, 40 * MiB, 5 * MiB + 1000 * 8, 33 * MiB, 9 * MiB + 8, 26 * MiB]
+    bufs = [sw.alloc(s) for s in sizes]
+    for i, p in enumerate(bufs):
+        _fill(sw, p, sizes[i] // 8 * 8, i)
+    touches = [0] * len(bufs)
+    import random
+    rng = random.Random(5)
+    for _ in range(60):
+        grp = rng.sample(range(len(bufs)), 2)
+        ptrs = [bufs[g] for g in grp]
+        sw.acquire(ptrs, _stream())                # a launch that references two buffers at once
+        for g in grp:
+            assert v.lib().vgpu_wl_touch(bufs[g], sizes[g] // 8, C.c_void_p(_stream())) == 0
+            touches[g] += 1
+        sw.release(ptrs, _stream())
+    assert _verify(sw, bufs, [s // 8 * 8 for s in sizes], touches) == 0
+    sw.close()
+
+
+def test_lru_order_is_respected():
+    sw = v.Swap(resident_cap=64 * MiB, chunk_bytes=8 * MiB, ring_slots=2)
+    nbytes = 16 * MiB
+    bufs = [sw.alloc(nbytes) for _ in range(4)]    # exactly fills the quota
+    for i, p in enumerate(bufs):
+        _fill(sw, p, nbytes, i)
+    _touch(sw, bufs[0], nbytes)                    # 0 becomes most recent; LRU order is now 1,2,3,0
+    extra = sw.alloc(nbytes)                       # must evict buffer 1
+    tbl = {e.base: e for e in sw.table()}
+    assert tbl[bufs[1]].state == v.ENTRY_PAGED_OUT
+    assert all(tbl[bufs[i]].state == v.ENTRY_RESIDENT for i in (0, 2, 3))
+    extra2 = sw.alloc(2 * nbytes)                  # needs 32 MiB more: evicts 2 and 3, never 0
+    tbl = {e.base: e for e in sw.table()}
+    assert tbl[bufs[2]].state == v.ENTRY_PAGED_OUT and tbl[bufs[3]].state == v.ENTRY_PAGED_OUT
+    assert tbl[bufs[0]].state == v.ENTRY_RESIDENT
+    assert _verify(sw, bufs, [nbytes] * 4, [1, 0, 0, 0]) == 0
+    sw.free(extra)
+    sw.free(extra2)
+    sw.close()
+
+
+def test_working_set_larger_than_quota_is_refused_not_corrupted():
+    sw = v.Swap(resident_cap=32 * MiB, chunk_bytes=8 * MiB, ring_slots=2)
+    a, b = sw.alloc(24 * MiB), sw.alloc(24 * MiB)
+    with pytest.raises(v.VgpuError) as ei:
+        sw.acquire([a, b], _stream())              # 48 MiB cannot be resident under 32 MiB
+    assert ei.value.code == 2                      # CUDA_ERROR_OUT_OF_MEMORY
+    with pytest.raises(v.VgpuError):
+        sw.alloc(64 * MiB)
+    sw.acquire([a], _stream()); sw.release([a], _stream())
+    sw.acquire([b], _stream()); sw.release([b], _stream())
+    sw.close()
+
+
+def test_virtual_cap_and_free_of_paged_out_buffer():
+    sw = v.Swap(resident_cap=32 * MiB, virtual_cap=96 * MiB, chunk_bytes=8 * MiB, ring_slots=2)
+    bufs = [sw.alloc(32 * MiB) for _ in range(3)]
+    with pytest.raises(v.VgpuError):
+        sw.alloc(4 * MiB)                          # live bytes would exceed the virtual cap
+    sw.free(bufs[0])                               # paged out long ago: only host space to give back
+    again = sw.alloc(32 * MiB)
+    assert again
+    with pytest.raises(v.VgpuError):
+        sw.free(0x1234000)
+    sw.close()
