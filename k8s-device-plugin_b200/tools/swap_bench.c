@@ -31,7 +31,7 @@ static uint64_t rng(void) { uint64_t x = (rng_state += 0x9E3779B97F4A7C15ull); x
 
 int main(int argc, char **argv) {
     const char *cubin = NULL, *order = "cyclic";
-    long nbuf = 64, mib = 64, steps = 64, warmup = 8, managed = 0, ballast_mib = 0, verify = 1, profile = 0, seed = 0x5EED;
+    long nbuf = 64, mib = 64, steps = 64, warmup = 8, managed = 0, ballast_mib = 0, verify = 1, profile = 0, seed = 0x5EED, wait_stdin = 0;
     double zipf_s = 1.1;
     for (int i = 1; i + 1 < argc; i += 2) {
         const char *k = argv[i], *v = argv[i + 1];
@@ -47,6 +47,7 @@ int main(int argc, char **argv) {
         else if (!strcmp(k, "--profile")) profile = atol(v);
         else if (!strcmp(k, "--seed")) seed = strtol(v, 0, 0);
         else if (!strcmp(k, "--zipf")) zipf_s = atof(v);
+        else if (!strcmp(k, "--wait-stdin")) wait_stdin = atol(v);
         else { fprintf(stderr, "unknown option %s\n", k); return 2; }
     }
     if (!cubin) { fprintf(stderr, "--cubin required\n"); return 2; }
@@ -112,6 +113,11 @@ int main(int argc, char **argv) {
         touches[seq[t]]++;
     }
     CK(cuCtxSynchronize());
+    if (wait_stdin) {   /* multi-GPU runs: the launcher releases every rank's timed region together */
+        char line[16];
+        fprintf(stderr, "READY\n"); fflush(stderr);
+        if (!fgets(line, sizeof line, stdin)) return 5;
+    }
     if (get_stats) get_stats(0, &s0);
     double w0 = now_ms();
     CK(cuEventRecord(e0, 0));
