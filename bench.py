@@ -265,6 +265,39 @@ def reference_arm(args):
     print(json.dumps(line))
 
 
+def aggregate(dist, device, ms, nbytes):
+    """Whole-job throughput of N replicas: units all ranks processed / max-over-ranks time (GB/s)."""
+    import torch
+    if dist is None:
+        return ms, nbytes, nbytes / (ms / 1e3) / 1e9
+    t = torch.tensor([float(ms)], dtype=torch.float64, device=device)
+    b = torch.tensor([float(nbytes)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(b, op=dist.ReduceOp.SUM)
+    return float(t.item()), float(b.item()), float(b.item()) / (float(t.item()) / 1e3) / 1e9
+
+
+def dry_run_cpu(args):
+    """No GPU: gloo backend, synthetic per-rank measurements (rank r: 100+r ms, (r+1) GB) through the same
+    barrier / max-time / sum-bytes path the GPU run uses."""
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    d = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo")
+        dist.barrier()
+        d = dist
+    t_max, total, value = aggregate(d, "cpu", 100.0 + rank, (rank + 1) * 1e9)
+    if d:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps({"metric": "vmem_swap_GBps", "value": round(value, 6), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": t_max / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "data": "dry-run", "total_bytes": total, "t_max_ms": t_max}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -272,11 +305,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="graft")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--dry-run-cpu", action="store_true", help="exercise the multi-rank plumbing with gloo and synthetic per-rank numbers (tests)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
     if args.impl == "reference":
         return reference_arm(args)
+    if args.dry_run_cpu:
+        return dry_run_cpu(args)
 
     import torch
     import k8s_device_plugin_b200 as v
@@ -312,9 +348,7 @@ def main():
     # ---- arm 1: engine through the C ABI
     ms, d, bad = run_engine_arm(torch, v, nbuf, args.steps, args.warmup, barrier)
     page_bytes = d["page_in_bytes"] + d["page_out_bytes"]
-    t_max = reduce(ms, "MAX")
-    total_bytes = reduce(page_bytes, "SUM")
-    value = total_bytes / (t_max / 1e3) / 1e9
+    t_max, total_bytes, value = aggregate(dist, "cuda", ms, page_bytes)
     kern_ms = d["pack_ms"] + d["unpack_ms"]
     kern_bytes = 2 * (d["pack_bytes"] + d["unpack_bytes"])      # algorithmic: read + write of every byte moved
     kern_launches = d["pack_launches"] + d["unpack_launches"]
@@ -324,10 +358,8 @@ def main():
     # ---- arm 2: unmodified app under LD_PRELOAD (reference-facing boundary)
     p = spawn_app(local, nbuf, args.steps, args.warmup, "new", True)
     e2e = finish_app(p, True, barrier)
-    e2e_bytes = reduce(e2e["page_in_bytes"] + e2e["page_out_bytes"], "SUM")
-    e2e_ms = reduce(e2e["event_ms"], "MAX")
+    e2e_ms, e2e_bytes, e2e_value = aggregate(dist, "cuda", e2e["event_ms"], e2e["page_in_bytes"] + e2e["page_out_bytes"])
     e2e_bad = reduce(e2e["mismatches"], "SUM")
-    e2e_value = e2e_bytes / (e2e_ms / 1e3) / 1e9
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference's swap path on this box's host cores
     cpu = None

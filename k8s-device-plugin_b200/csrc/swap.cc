@@ -82,8 +82,8 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
     va_free_[0] = want;
     owner_.assign(want / gran_, -1);
 
-    if (d.cuStreamCreate(&s_kern_, CU_STREAM_NON_BLOCKING) || d.cuStreamCreate(&s_out_, CU_STREAM_NON_BLOCKING) ||
-        d.cuStreamCreate(&s_in_, CU_STREAM_NON_BLOCKING)) { LOG_ERROR("side stream creation failed"); return false; }
+    for (CUstream *s : {&s_scan_, &s_pack_, &s_unpack_, &s_out_, &s_in_})
+        if (d.cuStreamCreate(s, CU_STREAM_NON_BLOCKING) != CUDA_SUCCESS) { LOG_ERROR("side stream creation failed"); return false; }
     auto mkring = [&](std::vector<Slot> &ring) {
         ring.resize(cfg_.ring_slots);
         for (auto &s : ring) {
@@ -124,9 +124,7 @@ SwapEngine::~SwapEngine() {
     if (d_tbl_) d.cuMemFree_v2(d_tbl_);
     if (h_tbl_stage_) d.cuMemFreeHost(h_tbl_stage_);
     if (arena_) d.cuMemAddressFree(arena_, cfg_.arena_bytes);
-    if (s_kern_) d.cuStreamDestroy_v2(s_kern_);
-    if (s_out_) d.cuStreamDestroy_v2(s_out_);
-    if (s_in_) d.cuStreamDestroy_v2(s_in_);
+    for (CUstream s : {s_scan_, s_pack_, s_unpack_, s_out_, s_in_}) if (s) d.cuStreamDestroy_v2(s);
 }
 
 // ---------------------------------------------------------------------------------------------- small allocators
@@ -159,13 +157,17 @@ void SwapEngine::va_free(uint64_t off, size_t bytes) { map_free(va_free_, off, b
 bool SwapEngine::host_alloc(size_t bytes, uint64_t *off) {
     const DriverTable &d = drv();
     bytes = round_up(bytes, 256);
-    for (size_t i = 0; i < slabs_.size(); i++) {
-        uint64_t o;
-        if (map_alloc(slabs_[i].free, bytes, &o)) {
-            *off = ((uint64_t)i << 44) | o;
-            host_used_ += bytes;
-            return true;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        reap_pending_host(attempt == 1);   // second try: wait for parked ranges (<= ~1 ms) rather than pin a new slab (~100 ms)
+        for (size_t i = 0; i < slabs_.size(); i++) {
+            uint64_t o;
+            if (map_alloc(slabs_[i].free, bytes, &o)) {
+                *off = ((uint64_t)i << 44) | o;
+                host_used_ += bytes;
+                return true;
+            }
         }
+        if (pending_host_.empty()) break;
     }
     size_t sb = std::max<size_t>(cfg_.slab_bytes, bytes);
     uint64_t have = 0;
@@ -381,8 +383,10 @@ CUresult SwapEngine::page_out(const std::vector<uint32_t> &victims) {
         return CUDA_SUCCESS;
     }
     // order the pack behind the victims' last users
-    for (uint32_t v : victims)
-        if (CUevent e = use_event(side_[v].use_seq)) d.cuStreamWaitEvent(s_kern_, e, 0);
+    for (uint32_t v : victims) {
+        if (CUevent e = use_event(side_[v].use_seq)) d.cuStreamWaitEvent(s_pack_, e, 0);
+        if (side_[v].ready) d.cuStreamWaitEvent(s_pack_, side_[v].ready, 0);   // its own page-in may still be in flight
+    }
 
     std::vector<PackSegment> segs;
     Slot *slot = nullptr;
@@ -391,13 +395,13 @@ CUresult SwapEngine::page_out(const std::vector<uint32_t> &victims) {
         if (!slot || segs.empty()) return CUDA_SUCCESS;
         int launches = 0;
         CUevent pa;
-        prof_begin(s_kern_, &pa);
-        CUresult r = launch_pack(k_, segs.data(), segs.size(), s_kern_, &launches);
+        prof_begin(s_pack_, &pa);
+        CUresult r = launch_pack(k_, segs.data(), segs.size(), s_pack_, &launches);
         if (r != CUDA_SUCCESS) return r;
-        prof_end(s_kern_, pa, false, pos);
+        prof_end(s_pack_, pa, false, pos);
         st_.pack_launches += launches;
         // slot.busy doubles as "packed" marker for the copy stream, then is re-recorded as "drained"
-        CU_TRY(d.cuEventRecord(slot->busy, s_kern_));
+        CU_TRY(d.cuEventRecord(slot->busy, s_pack_));
         CU_TRY(d.cuStreamWaitEvent(s_out_, slot->busy, 0));
         CU_TRY(d.cuMemcpyDtoHAsync_v2(host_ptr(block) + slot_host_start, slot->buf, pos, s_out_));
         CU_TRY(d.cuEventRecord(slot->busy, s_out_));
@@ -420,10 +424,9 @@ CUresult SwapEngine::page_out(const std::vector<uint32_t> &victims) {
     }
     { CUresult r = flush(); if (r != CUDA_SUCCESS) return r; }
     // the victims' physical pages may be recycled as soon as the LAST PACK has read them — not when the DMA is done
-    CUevent packed = nullptr;
-    if (!ready_free_.empty()) { packed = ready_free_.back(); ready_free_.pop_back(); }
-    else CU_TRY(d.cuEventCreate(&packed, CU_EVENT_DISABLE_TIMING));
-    CU_TRY(d.cuEventRecord(packed, s_kern_));
+    CUevent packed = get_event();
+    if (!packed) return CUDA_ERROR_OUT_OF_MEMORY;
+    CU_TRY(d.cuEventRecord(packed, s_pack_));
     CU_TRY(d.cuEventSynchronize(packed));
     ready_free_.push_back(packed);
     for (size_t i = 0; i < victims.size(); i++) {
@@ -451,6 +454,7 @@ CUresult SwapEngine::page_in(const std::vector<int> &rows) {
         s.out_slot = -1;
     }
     std::vector<PackSegment> segs;
+    std::vector<PendingHost> fresh;
     Slot *slot = nullptr;
     uint64_t pos = 0;
     // pending host->staging copy run (merged while both sides stay contiguous)
@@ -467,15 +471,15 @@ CUresult SwapEngine::page_in(const std::vector<int> &rows) {
         CUresult r = flush_run();
         if (r != CUDA_SUCCESS) return r;
         CU_TRY(d.cuEventRecord(slot->busy, s_in_));
-        CU_TRY(d.cuStreamWaitEvent(s_kern_, slot->busy, 0));
+        CU_TRY(d.cuStreamWaitEvent(s_unpack_, slot->busy, 0));
         int launches = 0;
         CUevent pa;
-        prof_begin(s_kern_, &pa);
-        r = launch_pack(k_, segs.data(), segs.size(), s_kern_, &launches);
+        prof_begin(s_unpack_, &pa);
+        r = launch_pack(k_, segs.data(), segs.size(), s_unpack_, &launches);
         if (r != CUDA_SUCCESS) return r;
-        prof_end(s_kern_, pa, true, pos);
+        prof_end(s_unpack_, pa, true, pos);
         st_.unpack_launches += launches;
-        CU_TRY(d.cuEventRecord(slot->busy, s_kern_));
+        CU_TRY(d.cuEventRecord(slot->busy, s_unpack_));
         segs.clear();
         slot = nullptr;
         return CUDA_SUCCESS;
@@ -492,33 +496,51 @@ CUresult SwapEngine::page_in(const std::vector<int> &rows) {
             off += piece; pos += piece;
             if (pos == cfg_.chunk_bytes || segs.size() == VGPU_PACK_MAX_SEG) { CUresult rc = flush(); if (rc != CUDA_SUCCESS) return rc; }
         }
-        // completion marker for this row: everything enqueued on s_kern_ so far includes its last unpack once flushed
+        // completion marker for this row: everything enqueued on s_unpack_ so far includes its last unpack once flushed
         CUresult rc = flush();
         if (rc != CUDA_SUCCESS) return rc;
-        CUevent ev = nullptr;
-        if (!ready_free_.empty()) { ev = ready_free_.back(); ready_free_.pop_back(); }
-        else CU_TRY(d.cuEventCreate(&ev, CU_EVENT_DISABLE_TIMING));
-        CU_TRY(d.cuEventRecord(ev, s_kern_));
+        CUevent ev = get_event();
+        if (!ev) return CUDA_ERROR_OUT_OF_MEMORY;
+        CU_TRY(d.cuEventRecord(ev, s_unpack_));
         side_[r].ready = ev;
-        // the pinned range is reusable once the H2D copies have read it: s_out_ (the only writer of the pool) is
-        // ordered behind this point of s_in_ before the range is handed out again
-        pending_host_.push_back(PendingHost{side_[r].host_off, round_up(rows_[r].size, 256)});
+        fresh.push_back(PendingHost{side_[r].host_off, round_up(rows_[r].size, 256), nullptr});
         side_[r].has_host = false;
         rows_[r].state = VGPU_ST_RESIDENT;
         mark_dirty(r);
     }
-    if (!pending_host_.empty()) {
-        // one event orders every later D2H behind the H2D reads issued above, then the ranges return to the pool
-        CUevent ev = nullptr;
-        if (!ready_free_.empty()) { ev = ready_free_.back(); ready_free_.pop_back(); }
-        else CU_TRY(d.cuEventCreate(&ev, CU_EVENT_DISABLE_TIMING));
+    if (!fresh.empty()) {
+        // the pinned ranges go back to the pool only after the H2D copies above have READ them (a later page-out
+        // would otherwise overwrite them): parked with one event, reaped by host_alloc() once it has fired
+        CUevent ev = get_event();
+        if (!ev) return CUDA_ERROR_OUT_OF_MEMORY;
         CU_TRY(d.cuEventRecord(ev, s_in_));
-        CU_TRY(d.cuStreamWaitEvent(s_out_, ev, 0));
-        ready_free_.push_back(ev);
-        for (auto &p : pending_host_) release_host_range(p.off, p.len);
-        pending_host_.clear();
+        for (size_t i = 0; i < fresh.size(); i++) { fresh[i].done = (i + 1 == fresh.size()) ? ev : nullptr; pending_host_.push_back(fresh[i]); }
     }
     return CUDA_SUCCESS;
+}
+
+CUevent SwapEngine::get_event() {
+    if (!ready_free_.empty()) { CUevent e = ready_free_.back(); ready_free_.pop_back(); return e; }
+    CUevent e = nullptr;
+    if (drv().cuEventCreate(&e, CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) return nullptr;
+    return e;
+}
+
+void SwapEngine::reap_pending_host(bool wait) {
+    const DriverTable &d = drv();
+    // entries are in issue order; an entry without its own event completes with the next one that has one
+    size_t done_upto = 0;
+    for (size_t i = 0; i < pending_host_.size(); i++) {
+        if (!pending_host_[i].done) continue;
+        if (wait) d.cuEventSynchronize(pending_host_[i].done);
+        if (d.cuEventQuery(pending_host_[i].done) != CUDA_SUCCESS) break;
+        done_upto = i + 1;
+    }
+    for (size_t i = 0; i < done_upto; i++) {
+        release_host_range(pending_host_[i].off, pending_host_[i].len);
+        if (pending_host_[i].done) ready_free_.push_back(pending_host_[i].done);
+    }
+    pending_host_.erase(pending_host_.begin(), pending_host_.begin() + done_upto);
 }
 
 void SwapEngine::release_host_range(uint64_t off, uint64_t len) {
@@ -531,13 +553,13 @@ CUresult SwapEngine::make_room(uint64_t need_mapped) {
     if (need_mapped > cfg_.resident_cap) return CUDA_ERROR_OUT_OF_MEMORY;
     if (resident_mapped_ + need_mapped <= cfg_.resident_cap) { trim_phys_pool(need_mapped); return CUDA_SUCCESS; }
     uint64_t deficit = resident_mapped_ + need_mapped - cfg_.resident_cap;
-    CUresult r = sync_table(s_kern_);
+    CUresult r = sync_table(s_scan_);
     if (r != CUDA_SUCCESS) return r;
     std::vector<uint32_t> victims;
     uint64_t freed = 0;
     bool insufficient = false;
     int launches = 0;
-    r = scanner_->scan(d_tbl_, (uint32_t)rows_.size(), deficit, tick_, s_kern_, &victims, &freed, &insufficient, &launches);
+    r = scanner_->scan(d_tbl_, (uint32_t)rows_.size(), deficit, tick_, s_scan_, &victims, &freed, &insufficient, &launches);
     st_.scan_launches += launches;
     st_.scans++;
     if (r != CUDA_SUCCESS) { LOG_ERROR("victim scan failed: %d %s", (int)r, cu_err(r)); return r; }
@@ -661,9 +683,9 @@ CUresult SwapEngine::drain() {
     const DriverTable &d = drv();
     std::lock_guard<std::mutex> g(mu_);
     CUresult r = CUDA_SUCCESS, t;
-    if (s_kern_ && (t = d.cuStreamSynchronize(s_kern_)) != CUDA_SUCCESS) r = t;
-    if (s_out_ && (t = d.cuStreamSynchronize(s_out_)) != CUDA_SUCCESS) r = t;
-    if (s_in_ && (t = d.cuStreamSynchronize(s_in_)) != CUDA_SUCCESS) r = t;
+    for (CUstream s : {s_scan_, s_pack_, s_unpack_, s_out_, s_in_})
+        if (s && (t = d.cuStreamSynchronize(s)) != CUDA_SUCCESS) r = t;
+    reap_pending_host(true);
     harvest_prof(true);
     return r;
 }

@@ -11,6 +11,8 @@
 //     resident quota allows, a GPU victim scan picks exact-LRU victims, a TMA pack kernel compacts them into a
 //     staging ring in HBM, and a copy stream drains the ring to pinned host memory while the next chunk is packed;
 //     page-in is the mirror image (pinned host -> staging ring -> unpack kernel into the re-mapped range);
+//   * pack, unpack, scan, D2H and H2D each have their own stream, ordered only by the events that express real
+//     data dependencies, so the two link directions and the HBM compaction all overlap;
 //   * nothing on the host ever waits for a PCIe transfer except for ring back-pressure: the application stream is
 //     ordered behind the page-in with events.
 #pragma once
@@ -92,7 +94,7 @@ class SwapEngine {
     };
     struct Slab { unsigned char *host = nullptr; size_t bytes = 0; std::map<uint64_t, uint64_t> free; };
     struct Slot { CUdeviceptr buf = 0; CUevent busy = nullptr; bool used = false; uint64_t seq = 0; };
-    struct PendingHost { uint64_t off, len; };
+    struct PendingHost { uint64_t off, len; CUevent done; };
 
     SwapEngine() = default;
     bool init(int dev, const SwapConfig &cfg);
@@ -108,6 +110,8 @@ class SwapEngine {
     void trim_phys_pool(uint64_t need);
     bool host_alloc(size_t bytes, uint64_t *off);
     void release_host_range(uint64_t off, uint64_t len);
+    void reap_pending_host(bool wait);
+    CUevent get_event();
     unsigned char *host_ptr(uint64_t off);
     bool va_alloc(size_t bytes, uint64_t *off);
     void va_free(uint64_t off, size_t bytes);
@@ -140,7 +144,9 @@ class SwapEngine {
     uint64_t phys_pool_bytes_ = 0;
     std::vector<Slab> slabs_;
 
-    CUstream s_kern_ = nullptr, s_out_ = nullptr, s_in_ = nullptr;
+    // independent queues: a pack never waits behind an unpack that is itself waiting for its H2D, and a victim
+    // scan never waits behind either
+    CUstream s_scan_ = nullptr, s_pack_ = nullptr, s_unpack_ = nullptr, s_out_ = nullptr, s_in_ = nullptr;
     std::vector<Slot> ring_out_, ring_in_;
     int cur_out_ = 0, cur_in_ = 0;
     std::vector<CUevent> use_ring_;                 // last-use events, indexed by seq % size

@@ -87,3 +87,41 @@ def test_hard_cap_without_oversubscribe_refuses(tmp_path):
     r = subprocess.run([os.path.join(LIBDIR, "swap_bench"), "--cubin", CUBIN, "--buffers", "32", "--mib", "64", "--steps", "4"],
                        env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
     assert r.returncode == 3 and "rc=-1" in r.stdout        # cuMemAlloc_v2 -> (CUresult)-1 past the 1 GiB cap
+
+
+def _gemm_loop(env_extra, n=4096, seconds=6):
+    env = dict(os.environ)
+    env.pop("LD_PRELOAD", None)
+    env.update(env_extra)
+    r = subprocess.run([os.path.join(LIBDIR, "gemm_loop"), str(n), str(seconds)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:] + r.stdout[-300:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_sm_limit_holds_cublas_loop_to_its_quota(tmp_path):
+    """BASELINE.json configs[3]: gpucores=30 on a cuBLAS SGEMM loop (a cudart application: the driver is reached through
+    cuGetProcAddress, i.e. through the hook's symbol routing). Achieved duty cycle = device-busy / wall."""
+    bare = _gemm_loop({})
+    assert bare["duty"] > 0.9
+    hooked = dict(v.hook_env(sm_limit=30, cache_path=str(tmp_path / "lim.cache")), GPU_CORE_UTILIZATION_POLICY="force")
+    lim = _gemm_loop(hooked)
+    assert 0.22 <= lim["duty"] <= 0.38, lim
+    assert lim["gemms"] < bare["gemms"] * 0.5
+    free = dict(v.hook_env(sm_limit=100, cache_path=str(tmp_path / "nolim.cache")))
+    assert _gemm_loop(free)["duty"] > 0.9               # sm_limit >= 100: rate_limiter returns early (@0x4591a)
+    off = dict(v.hook_env(sm_limit=30, cache_path=str(tmp_path / "off.cache")), GPU_CORE_UTILIZATION_POLICY="disable")
+    assert _gemm_loop(off)["duty"] > 0.9                # plugin --disable-core-limit (server.go:359-361)
+
+
+def test_cudart_application_is_accounted_through_cugetprocaddress(tmp_path):
+    """cudaMalloc in gemm_loop (3 x 64 MiB + cuBLAS workspace) must show up in the region: proves the dlsym /
+    cuGetProcAddress routing catches a runtime-API program, not only directly linked driver-API calls."""
+    cache = str(tmp_path / "rt.cache")
+    env = dict(os.environ)
+    env.update(v.hook_env(limit_mib=100, cache_path=cache))
+    r = subprocess.run([os.path.join(LIBDIR, "gemm_loop"), "4096", "1"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode != 0, r.stdout      # 3 x 64 MiB does not fit a 100 MiB cap (cudart reports the hook's code as an error)
+    env["VGPU_STRICT_CUDA_ERRORS"] = "1"
+    r = subprocess.run([os.path.join(LIBDIR, "gemm_loop"), "4096", "1"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode != 0 and "out of memory" in (r.stdout + r.stderr).lower()
