@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "driver.h"
 #include "log.h"
@@ -173,36 +174,44 @@ VGPU_EXPORT CUresult cuGetProcAddress_v2(const char *symbol, void **pfn, int cud
 VGPU_EXPORT CUresult cuGetProcAddress(const char *symbol, void **pfn, int cudaVersion, cuuint64_t flags);
 
 namespace {
-struct HookEntry { const char *name; void *fn; };
-#define H(sym) {#sym, reinterpret_cast<void *>(&sym)}
-const HookEntry kHooks[] = {
-    H(cuInit), H(cuGetProcAddress), H(cuGetProcAddress_v2),
-    H(cuMemAlloc_v2), H(cuMemAllocManaged), H(cuMemAllocPitch_v2), H(cuMemFree_v2), H(cuMemGetInfo_v2),
-    H(cuDeviceTotalMem_v2), H(cuDevicePrimaryCtxRetain), H(cuCtxCreate_v2), H(cuMemHostAlloc), H(cuMemAllocHost_v2),
-    H(cuLaunchKernel), H(cuLaunchKernelEx), H(cuLaunchCooperativeKernel),
-    H(cuMemcpyHtoD_v2), H(cuMemcpyDtoH_v2), H(cuMemcpyDtoD_v2), H(cuMemcpyHtoDAsync_v2), H(cuMemcpyDtoHAsync_v2),
-    H(cuMemcpyDtoDAsync_v2), H(cuMemcpy), H(cuMemcpyAsync),
-    H(cuMemsetD8_v2), H(cuMemsetD16_v2), H(cuMemsetD32_v2), H(cuMemsetD8Async), H(cuMemsetD16Async), H(cuMemsetD32Async),
-    H(cuMemoryAllocate), H(cuMemoryFree), H(cuVGPUViewAllocator),
-    H(nvmlDeviceGetMemoryInfo), H(nvmlDeviceGetMemoryInfo_v2),
-};
+// name -> wrapper, plus the address of the REAL entry point the wrapper forwards to. cuGetProcAddress requests are
+// resolved by the real driver first and the wrapper is substituted only when the driver's answer IS that real entry
+// point: the ABI version the caller gets (cudaVersion / flags dependent: _v2 vs _v3, _ptsz ...) is then exactly
+// the one the wrapper implements. The reference substitutes by NAME (find_symbols_in_table@0x2e172 tries name_v3,
+// name_v2, name and ignores cudaVersion/flags), which hands e.g. a cuCtxCreate_v2-shaped wrapper to a caller that
+// asked for the 4-argument cuCtxCreate_v4 of CUDA 12.5+.
+struct HookEntry { const char *name; void *fn; void *const *real; };
+#define H(sym) {#sym, reinterpret_cast<void *>(&sym), reinterpret_cast<void *const *>(&drv().sym)}
+#define HN(sym) {#sym, reinterpret_cast<void *>(&sym), nullptr}
+const std::vector<HookEntry> &hooks() {
+    static const std::vector<HookEntry> *t = new std::vector<HookEntry>{
+        H(cuInit),
+        {"cuGetProcAddress", reinterpret_cast<void *>(&cuGetProcAddress), reinterpret_cast<void *const *>(&drv().cuGetProcAddress_v1)},
+        H(cuGetProcAddress_v2),
+        H(cuMemAlloc_v2), H(cuMemAllocManaged), H(cuMemAllocPitch_v2), H(cuMemFree_v2), H(cuMemGetInfo_v2),
+        H(cuDeviceTotalMem_v2), H(cuDevicePrimaryCtxRetain), H(cuCtxCreate_v2), H(cuMemHostAlloc), H(cuMemAllocHost_v2),
+        H(cuLaunchKernel), H(cuLaunchKernelEx), H(cuLaunchCooperativeKernel),
+        H(cuMemcpyHtoD_v2), H(cuMemcpyDtoH_v2), H(cuMemcpyDtoD_v2), H(cuMemcpyHtoDAsync_v2), H(cuMemcpyDtoHAsync_v2),
+        H(cuMemcpyDtoDAsync_v2), H(cuMemcpy), H(cuMemcpyAsync),
+        H(cuMemsetD8_v2), H(cuMemsetD16_v2), H(cuMemsetD32_v2), H(cuMemsetD8Async), H(cuMemsetD16Async), H(cuMemsetD32Async),
+        HN(cuMemoryAllocate), HN(cuMemoryFree), HN(cuVGPUViewAllocator),
+        HN(nvmlDeviceGetMemoryInfo), HN(nvmlDeviceGetMemoryInfo_v2),
+    };
+    return *t;
+}
 #undef H
+#undef HN
 
 void *find_hook_exact(const char *name) {
-    for (const HookEntry &e : kHooks)
+    for (const HookEntry &e : hooks())
         if (!std::strcmp(e.name, name)) return e.fn;
     return nullptr;
 }
-// find_symbols_in_table@0x2e172: try name_v3, name_v2, name (cudaVersion and flags are ignored, as in the reference:
-// per-thread-default-stream requests collapse onto the legacy-stream wrapper)
-void *find_hook_versioned(const char *name) {
-    char buf[128];
-    if (std::strlen(name) > 100) return nullptr;
-    std::snprintf(buf, sizeof buf, "%s_v3", name);
-    if (void *p = find_hook_exact(buf)) return p;
-    std::snprintf(buf, sizeof buf, "%s_v2", name);
-    if (void *p = find_hook_exact(buf)) return p;
-    return find_hook_exact(name);
+void *find_hook_for_real(void *real_fn) {
+    if (!real_fn) return nullptr;
+    for (const HookEntry &e : hooks())
+        if (e.real && *e.real == real_fn) return e.fn;
+    return nullptr;
 }
 bool control_disabled() {
     static bool off = std::getenv("CUDA_DISABLE_CONTROL") != nullptr;   // container opt-out (server.go:380-385)
@@ -212,29 +221,28 @@ bool control_disabled() {
 
 VGPU_EXPORT CUresult cuGetProcAddress_v2(const char *symbol, void **pfn, int cudaVersion, cuuint64_t flags,
                                          CUdriverProcAddressQueryResult *symbolStatus) {
-    if (symbol && pfn && !control_disabled()) {
-        if (void *h = find_hook_versioned(symbol)) {
-            *pfn = h;
-            if (symbolStatus) *symbolStatus = CU_GET_PROC_ADDRESS_SUCCESS;
-            return CUDA_SUCCESS;
-        }
-    }
-    if (drv().cuGetProcAddress_v2) return drv().cuGetProcAddress_v2(symbol, pfn, cudaVersion, flags, symbolStatus);
-    if (drv().cuGetProcAddress_v1) {
-        CUresult r = drv().cuGetProcAddress_v1(symbol, pfn, cudaVersion, flags);
+    CUresult r;
+    if (drv().cuGetProcAddress_v2) {
+        r = drv().cuGetProcAddress_v2(symbol, pfn, cudaVersion, flags, symbolStatus);
+    } else if (drv().cuGetProcAddress_v1) {
+        r = drv().cuGetProcAddress_v1(symbol, pfn, cudaVersion, flags);
         if (symbolStatus) *symbolStatus = r == CUDA_SUCCESS ? CU_GET_PROC_ADDRESS_SUCCESS : CU_GET_PROC_ADDRESS_SYMBOL_NOT_FOUND;
-        return r;
+    } else {
+        return CUDA_ERROR_NOT_INITIALIZED;
     }
-    return CUDA_ERROR_NOT_INITIALIZED;
+    if (r == CUDA_SUCCESS && pfn && !control_disabled())
+        if (void *h = find_hook_for_real(*pfn)) *pfn = h;
+    return r;
 }
 
 VGPU_EXPORT CUresult cuGetProcAddress(const char *symbol, void **pfn, int cudaVersion, cuuint64_t flags) {
-    if (symbol && pfn && !control_disabled()) {
-        if (void *h = find_hook_versioned(symbol)) { *pfn = h; return CUDA_SUCCESS; }
-    }
-    if (drv().cuGetProcAddress_v1) return drv().cuGetProcAddress_v1(symbol, pfn, cudaVersion, flags);
-    if (drv().cuGetProcAddress_v2) return drv().cuGetProcAddress_v2(symbol, pfn, cudaVersion, flags, nullptr);
-    return CUDA_ERROR_NOT_INITIALIZED;
+    CUresult r;
+    if (drv().cuGetProcAddress_v1) r = drv().cuGetProcAddress_v1(symbol, pfn, cudaVersion, flags);
+    else if (drv().cuGetProcAddress_v2) r = drv().cuGetProcAddress_v2(symbol, pfn, cudaVersion, flags, nullptr);
+    else return CUDA_ERROR_NOT_INITIALIZED;
+    if (r == CUDA_SUCCESS && pfn && !control_disabled())
+        if (void *h = find_hook_for_real(*pfn)) *pfn = h;
+    return r;
 }
 
 // dlsym override (libvgpu.so@0x11b36): libcudart and frameworks resolve the driver with dlopen("libcuda.so.1") +

@@ -216,6 +216,34 @@ SwapEngine *Runtime::swap(int dev) {
     return swap_[dev].get();
 }
 
+bool Runtime::charge(int dev, size_t bytes) {
+    if (!cfg_.oversubscribe) return region_->try_add(pid_, dev, bytes, VGPU_MEM_BUFFER, true);   // oom_check + add, reference semantics
+    // swap mode: the quota bounds RESIDENT bytes. Non-swappable allocations are resident for life, so they are checked
+    // against the quota net of what the swap engine can page out, and they shrink the engine's resident budget.
+    uint64_t lim = region_->limit(dev);
+    SwapEngine *e = swap(dev);
+    if (lim) {
+        uint64_t u = region_->usage(dev), live = e ? e->live_bytes() : 0;
+        uint64_t fixed = u > live ? u - live : 0;
+        if (fixed + bytes > lim) { LOG_ERROR("Device %d OOM %lu / %lu (non-swappable)", dev, (unsigned long)(fixed + bytes), (unsigned long)lim); return false; }
+        if (e) e->set_resident_cap(lim - fixed - bytes);
+    }
+    region_->add(pid_, dev, bytes, VGPU_MEM_BUFFER);
+    return true;
+}
+
+void Runtime::uncharge(int dev, size_t bytes) {
+    region_->sub(pid_, dev, bytes, VGPU_MEM_BUFFER);
+    if (!cfg_.oversubscribe) return;
+    uint64_t lim = region_->limit(dev);
+    SwapEngine *e = swap(dev);
+    if (lim && e) {
+        uint64_t u = region_->usage(dev), live = e->live_bytes();
+        uint64_t fixed = u > live ? u - live : 0;
+        e->set_resident_cap(lim > fixed ? lim - fixed : 0);
+    }
+}
+
 CUresult Runtime::swap_alloc(CUdeviceptr *dptr, size_t bytes, int dev) {
     SwapEngine *e;
     {
@@ -251,15 +279,10 @@ CUresult Runtime::mem_alloc(CUdeviceptr *dptr, size_t bytes) {
         if (r == CUDA_ERROR_OUT_OF_MEMORY && !strict_errors()) return kQuotaBreachAlloc;
         return r;
     }
-    if (cfg_.oversubscribe) {
-        // small allocations stay resident for their whole life: they may use the quota but cannot exceed it
-        if (!region_->try_add(pid_, dev, bytes, VGPU_MEM_BUFFER, true)) return strict_errors() ? CUDA_ERROR_OUT_OF_MEMORY : kQuotaBreachAlloc;
-    } else if (!region_->try_add(pid_, dev, bytes, VGPU_MEM_BUFFER, true)) {
-        return strict_errors() ? CUDA_ERROR_OUT_OF_MEMORY : kQuotaBreachAlloc;   // add_chunk@0x4005d returns -1
-    }
+    if (!charge(dev, bytes)) return strict_errors() ? CUDA_ERROR_OUT_OF_MEMORY : kQuotaBreachAlloc;   // add_chunk@0x4005d returns -1
     CUresult r = d.cuMemAlloc_v2(dptr, bytes);
     if (r != CUDA_SUCCESS) {
-        region_->sub(pid_, dev, bytes, VGPU_MEM_BUFFER);
+        uncharge(dev, bytes);
         LOG_ERROR("cuMemoryAllocate failed res=%d", (int)r);
         return r;
     }
@@ -273,9 +296,9 @@ CUresult Runtime::mem_alloc_managed(CUdeviceptr *dptr, size_t bytes, unsigned fl
     if (!region_) return d.cuMemAllocManaged(dptr, bytes, flags);
     int dev = current_device();
     if (dev < 0) return d.cuMemAllocManaged(dptr, bytes, flags);
-    if (!region_->try_add(pid_, dev, bytes, VGPU_MEM_BUFFER, true)) return CUDA_ERROR_OUT_OF_MEMORY;  // @0x31eab
+    if (!charge(dev, bytes)) return CUDA_ERROR_OUT_OF_MEMORY;  // @0x31eab
     CUresult r = d.cuMemAllocManaged(dptr, bytes, flags);
-    if (r != CUDA_SUCCESS) { region_->sub(pid_, dev, bytes, VGPU_MEM_BUFFER); return r; }
+    if (r != CUDA_SUCCESS) { uncharge(dev, bytes); return r; }
     std::lock_guard<std::mutex> g(table_mu_);   // add_chunk_only@0x404a5
     track(*dptr, bytes, dev, AllocKind::Managed);
     return CUDA_SUCCESS;
@@ -291,9 +314,9 @@ CUresult Runtime::mem_alloc_pitch(CUdeviceptr *dptr, size_t *pitch, size_t width
     // what gets charged, not the pitch the driver picks
     size_t guess = ((width - 1) / elem + 1) * (size_t)elem;
     size_t bytes = guess * height;
-    if (!region_->try_add(pid_, dev, bytes, VGPU_MEM_BUFFER, true)) return CUDA_ERROR_OUT_OF_MEMORY;  // @0x321ef
+    if (!charge(dev, bytes)) return CUDA_ERROR_OUT_OF_MEMORY;  // @0x321ef
     CUresult r = d.cuMemAllocPitch_v2(dptr, pitch, width, height, elem);
-    if (r != CUDA_SUCCESS) { region_->sub(pid_, dev, bytes, VGPU_MEM_BUFFER); return r; }
+    if (r != CUDA_SUCCESS) { uncharge(dev, bytes); return r; }
     std::lock_guard<std::mutex> g(table_mu_);
     track(*dptr, bytes, dev, AllocKind::Pitch);
     return CUDA_SUCCESS;
@@ -321,7 +344,8 @@ CUresult Runtime::mem_free(CUdeviceptr dptr) {
     }
     // remove_chunk unlinks and un-accounts whatever the real free returned
     table_.erase(it);
-    region_->sub(pid_, a.dev, a.size, VGPU_MEM_BUFFER);
+    if (a.kind == AllocKind::Swap) region_->sub(pid_, a.dev, a.size, VGPU_MEM_BUFFER);
+    else uncharge(a.dev, a.size);
     return r == CUDA_SUCCESS ? CUDA_SUCCESS : r;
 }
 

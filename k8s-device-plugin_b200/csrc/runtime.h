@@ -96,6 +96,8 @@ class Runtime {
     void wait_running();                    // wait_status_self(1) loop of every wrapper
     bool track(CUdeviceptr base, size_t size, int dev, AllocKind kind);
     CUresult swap_alloc(CUdeviceptr *dptr, size_t bytes, int dev);
+    bool charge(int dev, size_t bytes);     // quota check + accounting of a NON-swappable allocation (both modes)
+    void uncharge(int dev, size_t bytes);
 
     std::atomic<bool> inited_{false};
     std::atomic<bool> post_inited_{false};

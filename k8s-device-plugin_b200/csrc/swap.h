@@ -71,6 +71,8 @@ class SwapEngine {
 
     SwapStats stats();
     void set_profile(bool on) { cfg_.profile = on; }
+    // the quota left for swappable memory shrinks/grows with the container's non-swappable bytes (context, small buffers)
+    void set_resident_cap(uint64_t cap) { std::lock_guard<std::mutex> g(mu_); cfg_.resident_cap = cap; }
     CUresult drain();                          // wait for all side-stream work (tests / shutdown)
     const SwapConfig &config() const { return cfg_; }
     uint64_t live_bytes() const { return live_bytes_; }
