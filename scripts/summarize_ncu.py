@@ -1,0 +1,72 @@
+"""Turns gpurun_out/launches.csv (ncu --metrics gpu__time_duration.sum) and prof_*.ncu-rep into the tracked summaries
+under profiles/. Usage: python scripts/summarize_ncu.py <round tag>"""
+import collections
+import csv
+import io
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+
+
+def launches():
+    p = os.path.join(OUT, "launches.csv")
+    if not os.path.exists(p):
+        return None
+    text = open(p).read()
+    start = text.find('"ID"')
+    rows = list(csv.DictReader(io.StringIO(text[start:])))
+    agg = collections.OrderedDict()
+    for r in rows:
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        k = r["Kernel Name"].split("(")[0]
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r.get("Metric Unit", "ns")
+        ns = v * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}.get(unit, 1)
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += ns
+    total = sum(a[1] for a in agg.values()) or 1
+    lines = [f"# ncu launch list ({tag}) — scripts/ncu_target.py (engine-only swap loop, 32x64 MiB under 1 GiB)", "",
+             "cold-cache, serialised per-launch times: compare SHARES, not absolutes", "",
+             "| kernel | launches | total us | avg us | share |", "|---|---:|---:|---:|---:|"]
+    for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        lines.append(f"| {k} | {n} | {ns / 1e3:.1f} | {ns / 1e3 / n:.2f} | {ns / total:.1%} |")
+    return "\n".join(lines) + "\n"
+
+
+def full(rep, kernel):
+    p = os.path.join(OUT, rep)
+    if not os.path.exists(p):
+        return None
+    r = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    rows = list(csv.reader(io.StringIO(r.stdout)))
+    if len(rows) < 3:
+        return f"could not read {rep}: {r.stderr[:300]}\n"
+    hdr, units = rows[0], rows[1]
+    want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+            "dram__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread",
+            "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "lts__t_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum", "smsp__cycles_active.avg"]
+    idx = {h: i for i, h in enumerate(hdr)}
+    lines = [f"# ncu --set full: {kernel} ({tag})", "", "| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(rows) - 2)) + " |",
+             "|---|---|" + "---:|" * (len(rows) - 2)]
+    for m in want:
+        if m in idx:
+            lines.append(f"| {m} | {units[idx[m]]} | " + " | ".join(row[idx[m]] for row in rows[2:]) + " |")
+    return "\n".join(lines) + "\n"
+
+
+a = launches()
+if a:
+    open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w").write(a)
+    print(a)
+b = full("prof_pack.ncu-rep", "vgpu_pack_tma")
+if b:
+    open(os.path.join(ROOT, "profiles", f"{tag}_pack_tma_full.md"), "w").write(b)
+    print(b)

@@ -8,6 +8,7 @@ Fixtures:
   ref_kat.json            delta() and get_limit_from_env() called INSIDE the reference binary (oracle/ref_kat.c)
   ref_trace_2k.out.gz     full replay stream of gen_trace(2000, seed=0xB200), limit 8192m
   ref_trace_mixed.out.gz  full stream of gen_trace(1500, seed=7, kinds="AAMP"), limit 8192m (managed + pitch paths)
+  ref_exported_symbols.txt  the cu*/nvml* names the reference hook exports (nm -D), the drop-in symbol surface
   ref_hashes.json         sha256 of the replay streams of the 100 000-op cfg-2 trace (limit 8192m and unlimited) and
                           of a 20 000-op mixed trace
 """
@@ -55,6 +56,10 @@ def main():
     hashes["mixed_20k_limit8192m"] = hashlib.sha256(ref_stream(gen_trace(20000, seed=7, kinds="AAMP"), "8192m").encode()).hexdigest()
     hashes["_sha256_of_reference_binary"] = hashlib.sha256(open(REF_SO, "rb").read()).hexdigest()
     json.dump(hashes, open(os.path.join(HERE, "ref_hashes.json"), "w"), indent=1)
+    syms = subprocess.run(["nm", "-D", "--defined-only", REF_SO], stdout=subprocess.PIPE, text=True, check=True).stdout
+    import re
+    names = sorted({l.split()[2] for l in syms.splitlines() if len(l.split()) == 3 and l.split()[1] == "T" and re.match(r"^(cu[A-Z]|nvml[A-Z])", l.split()[2])})
+    open(os.path.join(HERE, "ref_exported_symbols.txt"), "w").write("\n".join(names) + "\n")
     print("golden fixtures written:", sorted(os.listdir(HERE)))
 
 

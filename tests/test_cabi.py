@@ -38,6 +38,38 @@ def test_hook_library_exports_the_interposed_driver_surface():
     assert "soname: [libvgpu.so]" in soname        # DT_SONAME the chart/ld.so.preload contract expects
 
 
+def test_hook_exports_every_symbol_the_reference_hook_exports():
+    """203 cu* + 243 nvml* exported names (nm -D lib/nvidia/libvgpu.so, committed as a golden list)."""
+    import subprocess
+    from conftest import GOLDEN
+    want = open(os.path.join(GOLDEN, "ref_exported_symbols.txt")).read().split()
+    assert len(want) == 446
+    have = set(l.split()[2] for l in subprocess.run(["nm", "-D", "--defined-only", HOOK_SO], stdout=subprocess.PIPE, text=True).stdout.splitlines()
+               if len(l.split()) == 3)
+    missing = [n for n in want if n not in have]
+    assert not missing, missing[:10]
+
+
+def test_passthrough_trampolines_forward_with_arguments_intact(tmp_path):
+    """A directly linked program calling names that only forward (cuDriverGetVersion, nvmlDeviceGetCount_v2 ...)."""
+    import subprocess
+    from conftest import FAKE
+    src = tmp_path / "pt.c"
+    src.write_text("""#include <stdio.h>
+extern int cuInit(unsigned); extern int cuDriverGetVersion(int*); extern int cuDeviceGetCount(int*);
+extern int cuDeviceGetAttribute(int*, int, int); extern int nvmlInit_v2(void); extern int nvmlDeviceGetCount_v2(unsigned*);
+extern int cuDeviceGetName(char*, int, int);
+int main(){ int v=0,c=0,a=0; unsigned n=0; char nm[64]; cuInit(0); cuDriverGetVersion(&v); cuDeviceGetCount(&c);
+ cuDeviceGetAttribute(&a, 16, 0); nvmlInit_v2(); nvmlDeviceGetCount_v2(&n); cuDeviceGetName(nm, 64, 0);
+ printf("%d %d %d %u %s\\n", v, c, a, n, nm); return 0; }
+""")
+    exe = tmp_path / "pt"
+    subprocess.run(["gcc", "-o", str(exe), str(src), "-L", FAKE, "-l:libcuda.so.1", "-Wl,--allow-shlib-undefined"], check=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=FAKE, LD_PRELOAD=HOOK_SO, LIBCUDA_LOG_LEVEL="0", CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "pt.cache"))
+    out = subprocess.run([str(exe)], env=env, stdout=subprocess.PIPE, text=True, check=True).stdout.strip()
+    assert out == "12090 1 148 1 NVIDIA B200 (fake)"
+
+
 def test_region_layout_matches_appendix_a(tmp_path):
     path = str(tmp_path / "r.cache")
     lim = [0] * 16
