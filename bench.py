@@ -207,7 +207,7 @@ def spawn_app(gpu, nbuf, steps, warmup, mode, wait_stdin, extra_args=(), ballast
     return subprocess.Popen(args, env=env, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
 
 
-def finish_app(p, wait_stdin, barrier):
+def finish_app(p, wait_stdin, barrier, timeout=3600):
     if wait_stdin:
         for line in p.stderr:              # wait for the populate + warm-up phases of this rank
             if line.startswith("READY"):
@@ -217,7 +217,12 @@ def finish_app(p, wait_stdin, barrier):
             p.stdin.write("go\n"); p.stdin.flush()
         except Exception:
             pass
-    out, err = p.communicate(timeout=3600)
+    try:
+        out, err = p.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        p.kill()
+        p.communicate()
+        raise RuntimeError(f"swap_bench did not finish within {timeout} s")
     if p.returncode != 0:
         raise RuntimeError(f"swap_bench failed rc={p.returncode}: {err[-2000:]} {out[-500:]}")
     return json.loads(out.strip().splitlines()[-1])
@@ -240,7 +245,7 @@ def reference_arm(args):
     if os.path.exists(os.path.join(OREF, "libvgpu.so")):
         try:
             p = spawn_app(0, nbuf, steps, warmup, "refhook", False, ballast_mib=ballast_mib)
-            res = finish_app(p, False, lambda: None)
+            res = finish_app(p, False, lambda: None, timeout=90)
             note = "lib/nvidia/libvgpu.so binary preloaded (CUDA_OVERSUBSCRIBE=true -> cuMemAllocManaged)"
         except Exception as e:
             note = f"reference binary did not run on this driver ({str(e)[:120]}); "
