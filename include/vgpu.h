@@ -108,6 +108,7 @@ typedef struct vgpu_swap_stats {
     uint64_t resident_bytes, live_bytes, host_bytes, entries, phys_creates, phys_reuses;
     uint64_t pack_bytes, unpack_bytes;
     double pack_ms, unpack_ms;
+    uint64_t scan_cache_hits;   /* evictions served from the previous scan's surplus (no new scan) */
 } vgpu_swap_stats_t;
 int vgpu_swap_create(int dev, const vgpu_swap_config_t *cfg, vgpu_swap_t **out);
 void vgpu_swap_destroy(vgpu_swap_t *s);

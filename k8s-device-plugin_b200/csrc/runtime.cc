@@ -6,6 +6,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <set>
@@ -93,6 +94,23 @@ bool Runtime::ensure_initialized() {
 }
 
 void Runtime::on_exit() {
+    if (std::getenv("VGPU_PRINT_STATS")) {
+        if (limiter_) {
+            LimiterStats s = limiter_->stats();
+            std::fprintf(stderr, "[vgpu-b200 stats] limiter: limit=%d%% active=%d launches=%lu stamps=%lu groups=%lu busy_ms=%.1f throttle_ms=%.1f wall_ms=%.1f\n",
+                         s.limit_percent, (int)limiter_->active(), (unsigned long)s.launches, (unsigned long)s.stamps, (unsigned long)s.groups,
+                         s.busy_ns / 1e6, s.throttle_ns / 1e6, s.wall_ns / 1e6);
+        } else {
+            std::fprintf(stderr, "[vgpu-b200 stats] limiter: not created (cuInit was never intercepted)\n");
+        }
+        for (int d = 0; d < VGPU_MAX_DEVICES; d++)
+            if (swap_[d]) {
+                SwapStats s = swap_[d]->stats();
+                std::fprintf(stderr, "[vgpu-b200 stats] swap dev %d: in=%lu out=%lu faults=%lu evictions=%lu scans=%lu cache_hits=%lu creates=%lu reuses=%lu\n", d,
+                             (unsigned long)s.page_in_bytes, (unsigned long)s.page_out_bytes, (unsigned long)s.faults, (unsigned long)s.evictions,
+                             (unsigned long)s.scans, (unsigned long)s.scan_cache_hits, (unsigned long)s.phys_creates, (unsigned long)s.phys_reuses);
+            }
+    }
     if (region_) region_->release_slot(pid_);
 }
 

@@ -35,6 +35,7 @@ SwapConfig SwapConfig::from_env(uint64_t resident_cap, uint64_t virtual_cap) {
     c.slab_bytes = (size_t)env_u64("VGPU_SWAP_SLAB_MB", 1024) << 20;
     c.arena_bytes = env_u64("VGPU_SWAP_ARENA_GB", 1024) << 30;
     c.profile = env_u64("VGPU_SWAP_PROFILE", 0) != 0;
+    c.scan_lookahead = (uint32_t)env_u64("VGPU_SWAP_SCAN_LOOKAHEAD", 8);
     if (c.ring_slots < 2) c.ring_slots = 2;
     if (c.chunk_bytes < (1u << 20)) c.chunk_bytes = 1u << 20;
     return c;
@@ -53,6 +54,7 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
     const DriverTable &d = drv();
     dev_ = dev;
     cfg_ = cfg;
+    scan_lookahead_ = cfg.scan_lookahead;
     k_ = kernels_for_current_ctx();
     if (!k_) return false;
     CUmemAllocationProp prop = {};
@@ -551,27 +553,58 @@ void SwapEngine::release_host_range(uint64_t off, uint64_t len) {
 
 CUresult SwapEngine::make_room(uint64_t need_mapped) {
     if (need_mapped > cfg_.resident_cap) return CUDA_ERROR_OUT_OF_MEMORY;
-    if (resident_mapped_ + need_mapped <= cfg_.resident_cap) { trim_phys_pool(need_mapped); return CUDA_SUCCESS; }
-    uint64_t deficit = resident_mapped_ + need_mapped - cfg_.resident_cap;
-    CUresult r = sync_table(s_scan_);
-    if (r != CUDA_SUCCESS) return r;
+    if (resident_mapped_ + need_mapped <= cfg_.resident_cap) return CUDA_SUCCESS;
+    const uint64_t deficit = resident_mapped_ + need_mapped - cfg_.resident_cap;
     std::vector<uint32_t> victims;
     uint64_t freed = 0;
-    bool insufficient = false;
-    int launches = 0;
-    r = scanner_->scan(d_tbl_, (uint32_t)rows_.size(), deficit, tick_, s_scan_, &victims, &freed, &insufficient, &launches);
-    st_.scan_launches += launches;
-    st_.scans++;
-    if (r != CUDA_SUCCESS) { LOG_ERROR("victim scan failed: %d %s", (int)r, cu_err(r)); return r; }
-    if (insufficient) {
-        LOG_ERROR("resident quota %lu MiB cannot hold the working set of this launch (need %lu MiB more, evictable %lu MiB)",
-                  (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(deficit >> 20), (unsigned long)(freed >> 20));
-        return CUDA_ERROR_OUT_OF_MEMORY;
+    auto valid = [&](const Cand &c) {
+        return c.row < rows_.size() && rows_[c.row].state == VGPU_ST_RESIDENT && rows_[c.row].last_touch == c.touch && rows_[c.row].base == c.base;
+    };
+    // 1. leftovers of the previous scan (still the exact LRU prefix, see swap.h)
+    {
+        std::deque<Cand> keep = victim_cache_;
+        std::vector<uint32_t> got;
+        uint64_t f = 0;
+        while (f < deficit && !keep.empty()) {
+            Cand cnd = keep.front();
+            keep.pop_front();
+            if (!valid(cnd)) continue;
+            got.push_back(cnd.row);
+            f += rows_[cnd.row].size;
+        }
+        if (f >= deficit) { victims = got; freed = f; victim_cache_.swap(keep); st_.scan_cache_hits++; }
+        else victim_cache_.clear();   // not enough left: start over from a fresh scan (nothing was consumed)
     }
-    r = page_out(victims);
-    if (r != CUDA_SUCCESS) return r;
-    trim_phys_pool(need_mapped);
-    return CUDA_SUCCESS;
+    // 2. GPU scan, asking for `scan_lookahead_` times the deficit so the next evictions need no scan
+    if (victims.empty()) {
+        CUresult r = sync_table(s_scan_);
+        if (r != CUDA_SUCCESS) return r;
+        std::vector<uint32_t> found;
+        uint64_t found_bytes = 0;
+        bool insufficient = false;
+        int launches = 0;
+        uint64_t ask = deficit * (uint64_t)(scan_lookahead_ ? scan_lookahead_ : 1);
+        r = scanner_->scan(d_tbl_, (uint32_t)rows_.size(), ask, tick_, s_scan_, &found, &found_bytes, &insufficient, &launches);
+        st_.scan_launches += launches;
+        st_.scans++;
+        if (r != CUDA_SUCCESS) { LOG_ERROR("victim scan failed: %d %s", (int)r, cu_err(r)); return r; }
+        if (found_bytes < deficit) {
+            LOG_ERROR("resident quota %lu MiB cannot hold the working set of this launch (need %lu MiB more, evictable %lu MiB)",
+                      (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(deficit >> 20), (unsigned long)(found_bytes >> 20));
+            return CUDA_ERROR_OUT_OF_MEMORY;
+        }
+        // the kernel returns the prefix SET in index order; LRU order within it comes from the host mirror
+        std::sort(found.begin(), found.end(), [&](uint32_t a, uint32_t b) {
+            if (rows_[a].last_touch != rows_[b].last_touch) return rows_[a].last_touch < rows_[b].last_touch;
+            return a < b;
+        });
+        size_t k = 0;
+        while (k < found.size() && freed < deficit) { victims.push_back(found[k]); freed += rows_[found[k]].size; k++; }
+        for (; k < found.size(); k++) victim_cache_.push_back(Cand{found[k], rows_[found[k]].last_touch, rows_[found[k]].base});
+    }
+    // the victims' physical handles are now pooled; get_phys() re-maps a same-size one under the incoming buffer
+    // (no cuMemCreate/cuMemRelease in steady state) and only trims the pool when it has to create
+    return page_out(victims);
 }
 
 // ---------------------------------------------------------------------------------------------- public operations
@@ -647,6 +680,7 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
             for (int i = 0; i < n; i++) {
                 Side &s = side_[rows[i]];
                 if (--s.pins == 0 && (rows_[rows[i]].state & VGPU_ST_RESIDENT)) rows_[rows[i]].state = VGPU_ST_RESIDENT;
+                mark_dirty(rows[i]);
             }
             return r;
         }

@@ -19,6 +19,7 @@
 #include <cuda.h>
 
 #include <cstdint>
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -38,13 +39,14 @@ struct SwapConfig {
     size_t slab_bytes = 1ull << 30;       // pinned pool growth unit
     uint64_t arena_bytes = 1ull << 40;    // virtual address arena
     bool profile = false;                 // bracket pack/unpack launches with events (bench roofline)
+    uint32_t scan_lookahead = 8;          // a scan selects this many times the bytes needed; the surplus is consumed by later evictions
     static SwapConfig from_env(uint64_t resident_cap, uint64_t virtual_cap);
 };
 
 struct SwapStats {
     uint64_t page_out_bytes = 0, page_in_bytes = 0;
     uint64_t evictions = 0, faults = 0, admissions = 0;
-    uint64_t pack_launches = 0, unpack_launches = 0, scan_launches = 0, scans = 0;
+    uint64_t pack_launches = 0, unpack_launches = 0, scan_launches = 0, scans = 0, scan_cache_hits = 0;
     uint64_t resident_bytes = 0, live_bytes = 0, host_bytes = 0, entries = 0;
     uint64_t phys_creates = 0, phys_reuses = 0;
     double pack_ms = 0, unpack_ms = 0;     // device time, only when profiling
@@ -156,6 +158,12 @@ class SwapEngine {
     std::vector<CUevent> ready_free_;
     std::unique_ptr<VictimScanner> scanner_;
     std::vector<PendingHost> pending_host_;
+    // victims selected by the last scan beyond what was needed then, in LRU order. They stay the exact LRU prefix for
+    // as long as they are untouched (anything touched or created since carries a larger tick), so consuming them
+    // is equivalent to re-scanning; an entry whose row changed is simply skipped.
+    struct Cand { uint32_t row; uint64_t touch, base; };
+    std::deque<Cand> victim_cache_;
+    uint32_t scan_lookahead_ = 8;
     SwapStats st_;
     struct Prof { CUevent a, b; bool unpack; uint64_t bytes; };
     std::vector<Prof> prof_;

@@ -10,6 +10,7 @@
 #include <string.h>
 #include <time.h>
 #define CK(x) do { CUresult _r = (x); if (_r != CUDA_SUCCESS) { fprintf(stderr, "linkbench: %s -> %d (line %d)\n", #x, (int)_r, __LINE__); exit(3); } } while (0)
+static void *h2p_buf(void *p) { return p; }
 static double now_us(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec / 1e3; }
 
 int main(int argc, char **argv) {
@@ -17,9 +18,9 @@ int main(int argc, char **argv) {
     size_t bytes = mib << 20;
     CUdevice dev; CUcontext ctx;
     CK(cuInit(0)); CK(cuDeviceGet(&dev, 0)); CK(cuDevicePrimaryCtxRetain(&ctx, dev)); CK(cuCtxSetCurrent(ctx));
-    void *h1, *h2; CUdeviceptr d1, d2; CUstream s1, s2; CUevent a, b, c, d;
+    void *h1, *h2; void *h2_host; CUdeviceptr d1, d2; CUstream s1, s2; CUevent a, b, c, d;
     CK(cuMemHostAlloc(&h1, bytes, CU_MEMHOSTALLOC_PORTABLE)); CK(cuMemHostAlloc(&h2, bytes, CU_MEMHOSTALLOC_PORTABLE));
-    memset(h1, 1, bytes); memset(h2, 2, bytes);
+    memset(h1, 1, bytes); memset(h2, 2, bytes); h2_host = h2;
     CK(cuMemAlloc(&d1, bytes)); CK(cuMemAlloc(&d2, bytes));
     CK(cuStreamCreate(&s1, CU_STREAM_NON_BLOCKING)); CK(cuStreamCreate(&s2, CU_STREAM_NON_BLOCKING));
     CK(cuEventCreate(&a, 0)); CK(cuEventCreate(&b, 0)); CK(cuEventCreate(&c, 0)); CK(cuEventCreate(&d, 0));
@@ -75,6 +76,31 @@ int main(int argc, char **argv) {
         printf("%s\"%zuMiB\": {\"create\": %.1f, \"map\": %.1f, \"setaccess\": %.1f, \"unmap\": %.1f, \"release\": %.1f, \"remap_cycle\": %.1f}",
                k ? ", " : "", sz >> 20, tc / reps, tm / reps, ta / reps, tu / reps, tr / reps, remap);
     }
-    printf("}}\n");
+    printf("}");
+    /* the same VMM calls while a long DMA is in flight on another stream: a call that takes about as long as the
+     * copy is implicitly synchronising the device, which would serialise the swap pipeline */
+    {
+        size_t sz = 64u << 20; CUdeviceptr va; CUmemGenericAllocationHandle h, h2;
+        CK(cuMemAddressReserve(&va, sz, 0, 0, 0));
+        CK(cuMemCreate(&h2, sz, &prop, 0));
+        double t[6] = {0, 0, 0, 0, 0, 0}; int reps = 5;
+        for (int i = 0; i < reps; i++) {
+            double a0, a1;
+            #define UNDER_LOAD(idx, stmt) CK(cuCtxSynchronize()); CK(cuMemcpyDtoHAsync(h1, d1, bytes, s1)); CK(cuMemcpyHtoDAsync(d2, h2p, bytes, s2)); a0 = now_us(); stmt; a1 = now_us(); t[idx] += a1 - a0;
+            void *h2p = h2p_buf(h2_host);
+            (void)h2p;
+            UNDER_LOAD(0, CK(cuMemCreate(&h, sz, &prop, 0)))
+            UNDER_LOAD(1, CK(cuMemMap(va, sz, 0, h, 0)))
+            UNDER_LOAD(2, CK(cuMemSetAccess(va, sz, &acc, 1)))
+            UNDER_LOAD(3, CK(cuMemUnmap(va, sz)))
+            UNDER_LOAD(4, CK(cuMemRelease(h)))
+            CK(cuCtxSynchronize()); CK(cuMemcpyDtoHAsync(h1, d1, bytes, s1)); a0 = now_us(); CK(cuStreamSynchronize(s1)); a1 = now_us(); t[5] += a1 - a0;
+        }
+        CK(cuCtxSynchronize());
+        printf(", \"vmm_us_under_dma_load\": {\"create\": %.1f, \"map\": %.1f, \"setaccess\": %.1f, \"unmap\": %.1f, \"release\": %.1f, \"dma_itself\": %.1f}",
+               t[0] / reps, t[1] / reps, t[2] / reps, t[3] / reps, t[4] / reps, t[5] / reps);
+        CK(cuMemRelease(h2)); CK(cuMemAddressFree(va, sz));
+    }
+    printf("}\n");
     return 0;
 }
