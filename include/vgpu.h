@@ -72,6 +72,8 @@ void *vgpu_region_raw(vgpu_region_handle_t *h);                                 
 typedef struct vgpu_seg { uint64_t src, dst, bytes; } vgpu_seg_t;
 /* pack / unpack: copy every segment src->dst on `stream` (TMA path for 16-byte-aligned segments). */
 int vgpu_pack(const vgpu_seg_t *segs, size_t nseg, void *stream);
+/* launch geometry of the TMA pack kernel (0 = keep): tile bytes (multiple of 16), ring stages (2..8), CTAs per SM */
+int vgpu_pack_config(uint32_t tile_bytes, uint32_t stages, uint32_t ctas_per_sm);
 
 typedef struct vgpu_entry {   /* one row of the allocation table; identical to VgpuEntry in csrc/kernels.h */
     uint64_t base, size, last_touch;

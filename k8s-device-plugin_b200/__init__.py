@@ -88,6 +88,7 @@ ABI = {
     "vgpu_region_set_hostpid": (_INT, [_P, _I32, _I32]),
     "vgpu_region_raw": (_P, [_P]),
     "vgpu_pack": (_INT, [C.POINTER(Seg), C.c_size_t, _P]),
+    "vgpu_pack_config": (_INT, [_U32, _U32, _U32]),
     "vgpu_victim_scan": (_INT, [_U64, _U32, _U64, _U64, _P, C.POINTER(_U32), _U32, C.POINTER(_U32), C.POINTER(_U64),
                                 C.POINTER(_INT)]),
     "vgpu_wl_fill": (_INT, [_U64, _U64, _U64, _P]),

@@ -97,6 +97,14 @@ VGPU_API int vgpu_pack(const vgpu_seg_t *segs, size_t nseg, void *stream) {
     return launch_pack(k, reinterpret_cast<const PackSegment *>(segs), nseg, static_cast<CUstream>(stream));
 }
 
+VGPU_API int vgpu_pack_config(uint32_t tile_bytes, uint32_t stages, uint32_t ctas_per_sm) {
+    PackConfig &c = pack_config();
+    if (tile_bytes) c.tile_bytes = tile_bytes;
+    if (stages) c.stages = stages;
+    if (ctas_per_sm) c.ctas_per_sm = ctas_per_sm;
+    return CUDA_SUCCESS;
+}
+
 VGPU_API int vgpu_victim_scan(uint64_t d_table, uint32_t n, uint64_t need, uint64_t max_touch, void *stream, uint32_t *out_idx,
                               uint32_t out_cap, uint32_t *out_count, uint64_t *freed, int *insufficient) {
     const Kernels *k = kernels_for_current_ctx();

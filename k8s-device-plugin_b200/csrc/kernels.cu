@@ -82,9 +82,9 @@ __device__ __forceinline__ int find_seg(const VgpuPackParams &p, uint64_t tile) 
 // No thread ever touches the payload: both directions run on the TMA unit, the SM only issues descriptors.
 extern "C" __global__ void __launch_bounds__(32, 1) vgpu_pack_tma(const __grid_constant__ VgpuPackParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int ST = VGPU_PACK_STAGES;
+    const int ST = static_cast<int>(p.stages);
     const uint32_t tile_bytes = p.tile_bytes;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem);              // ST barriers
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);              // up to VGPU_PACK_MAX_STAGES barriers
     unsigned char *buf = smem + 128;                                   // ST tiles
     if (threadIdx.x != 0) return;
 

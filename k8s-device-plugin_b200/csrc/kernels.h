@@ -2,8 +2,11 @@
 #pragma once
 #include <stdint.h>
 
-#define VGPU_PACK_STAGES 6                 /* shared-memory ring depth of vgpu_pack_tma */
-#define VGPU_PACK_TILE_BYTES (32u * 1024u) /* one TMA bulk copy; 6 x 32 KiB + barriers = 192.1 KiB of the 227 KiB */
+#define VGPU_PACK_MAX_STAGES 8             /* upper bound of the shared-memory ring depth of vgpu_pack_tma */
+#define VGPU_PACK_STAGES 4                 /* default ring depth ... */
+#define VGPU_PACK_TILE_BYTES (16u * 1024u) /* ... x default tile (one TMA bulk copy) = 64 KiB per CTA: three CTAs fit an SM, so a pack, an
+                                              unpack and an application kernel can share the SMs instead of queueing for shared memory */
+#define VGPU_PACK_CTAS_PER_SM 2            /* persistent CTAs per SM (each drives its own ring from one elected thread) */
 #define VGPU_PACK_MAX_SEG 96               /* segments per launch; keeps the kernel parameter block < 4 KiB */
 #define VGPU_SCAN_DIGIT_BITS 11
 #define VGPU_SCAN_BINS (1 << VGPU_SCAN_DIGIT_BITS)
@@ -33,6 +36,8 @@ typedef struct VgpuPackParams {
     uint32_t nseg;
     uint32_t tile_bytes;
     uint64_t total_tiles;
+    uint32_t stages;                       /* ring depth used by this launch (<= VGPU_PACK_MAX_STAGES) */
+    uint32_t _pad;
     VgpuPackSeg seg[VGPU_PACK_MAX_SEG];
 } VgpuPackParams;
 

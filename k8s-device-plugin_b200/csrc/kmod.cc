@@ -1,6 +1,7 @@
 // kmod.cc — see kmod.h.
 #include "kmod.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -14,6 +15,17 @@ extern const unsigned long long vgpu_kernels_cubin_size;
 }
 
 namespace vgpu {
+
+PackConfig &pack_config() {
+    static PackConfig c = [] {
+        PackConfig d;
+        if (const char *e = std::getenv("VGPU_PACK_TILE_KB")) d.tile_bytes = (uint32_t)std::atoi(e) * 1024u;
+        if (const char *e = std::getenv("VGPU_PACK_STAGES")) d.stages = (uint32_t)std::atoi(e);
+        if (const char *e = std::getenv("VGPU_PACK_CTAS_PER_SM")) d.ctas_per_sm = (uint32_t)std::atoi(e);
+        return d;
+    }();
+    return c;
+}
 
 static std::mutex g_mu;
 static std::map<CUcontext, Kernels *> g_by_ctx;
@@ -49,7 +61,7 @@ const Kernels *kernels_for_current_ctx() {
     d.cuCtxGetDevice(&dev);
     d.cuDeviceGetAttribute(&k->sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev);
     if (k->sm_count <= 0) k->sm_count = 148;
-    const int smem = 128 + VGPU_PACK_STAGES * (int)VGPU_PACK_TILE_BYTES;
+    const int smem = 227 * 1024;   // opt in to the maximum; each launch requests 128 + stages * tile bytes
     r = d.cuFuncSetAttribute(k->pack_tma, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem);
     if (r != CUDA_SUCCESS) LOG_ERROR("cuFuncSetAttribute(max dynamic smem %d) failed: %d", smem, (int)r);
     g_by_ctx[ctx] = k;
@@ -60,16 +72,25 @@ static CUresult launch_pack_set(const Kernels *k, CUfunction fn, bool tma, const
                                 size_t n, CUstream stream, int *launches) {
     const DriverTable &d = drv();
     size_t i = 0;
+    PackConfig cfg = pack_config();
+    if (cfg.stages < 2) cfg.stages = 2;
+    if (cfg.stages > VGPU_PACK_MAX_STAGES) cfg.stages = VGPU_PACK_MAX_STAGES;
+    if (cfg.tile_bytes < 1024 || (cfg.tile_bytes & 15u)) cfg.tile_bytes = VGPU_PACK_TILE_BYTES;
+    while (128u + cfg.stages * cfg.tile_bytes > 227u * 1024u) cfg.stages--;
+    if (cfg.ctas_per_sm < 1) cfg.ctas_per_sm = 1;
+    const uint32_t tile = tma ? cfg.tile_bytes : 32u * 1024u;
     while (i < n) {
         VgpuPackParams p;
-        p.tile_bytes = VGPU_PACK_TILE_BYTES;
+        p.tile_bytes = tile;
+        p.stages = cfg.stages;
+        p._pad = 0;
         p.nseg = 0;
         uint64_t tiles = 0;
         while (i < n && p.nseg < VGPU_PACK_MAX_SEG) {
             const PackSegment &s = segs[which[i]];
             VgpuPackSeg &o = p.seg[p.nseg++];
             o.src = s.src; o.dst = s.dst; o.bytes = s.bytes; o.tile_begin = tiles;
-            tiles += (s.bytes + VGPU_PACK_TILE_BYTES - 1) / VGPU_PACK_TILE_BYTES;
+            tiles += (s.bytes + tile - 1) / tile;
             i++;
         }
         p.total_tiles = tiles;
@@ -77,9 +98,10 @@ static CUresult launch_pack_set(const Kernels *k, CUfunction fn, bool tma, const
         void *args[] = {&p};
         CUresult r;
         if (tma) {
-            // persistent: one CTA per SM (a multiple of the SM count would only add barrier-ring copies)
-            unsigned grid = (unsigned)(tiles < (uint64_t)k->sm_count ? tiles : (uint64_t)k->sm_count);
-            r = d.cuLaunchKernel(fn, grid, 1, 1, 32, 1, 1, 128 + VGPU_PACK_STAGES * VGPU_PACK_TILE_BYTES, stream, args, nullptr);
+            // persistent grid: a multiple of the SM count, every CTA loops over tiles t = blockIdx, blockIdx + grid, ...
+            uint64_t want = (uint64_t)k->sm_count * cfg.ctas_per_sm;
+            unsigned grid = (unsigned)(tiles < want ? tiles : want);
+            r = d.cuLaunchKernel(fn, grid, 1, 1, 32, 1, 1, 128 + cfg.stages * cfg.tile_bytes, stream, args, nullptr);
         } else {
             uint64_t want = tiles < (uint64_t)k->sm_count * 8 ? tiles : (uint64_t)k->sm_count * 8;
             r = d.cuLaunchKernel(fn, (unsigned)want, 1, 1, 256, 1, 1, 0, stream, args, nullptr);

@@ -26,6 +26,10 @@ const Kernels *kernels_for_current_ctx();
 
 struct PackSegment { CUdeviceptr src, dst; uint64_t bytes; };
 
+// launch geometry of vgpu_pack_tma (process-wide; tuned by scripts/pack_sweep.py, overridable for experiments)
+struct PackConfig { uint32_t tile_bytes = VGPU_PACK_TILE_BYTES; uint32_t stages = VGPU_PACK_STAGES; uint32_t ctas_per_sm = VGPU_PACK_CTAS_PER_SM; };
+PackConfig &pack_config();
+
 // Enqueues the copies described by segs on `stream` (src -> dst for every segment). 16-byte-aligned segments go
 // through vgpu_pack_tma, the rest through vgpu_pack_generic. launches_out (optional) += number of kernel launches.
 CUresult launch_pack(const Kernels *k, const PackSegment *segs, size_t nseg, CUstream stream, int *launches_out = nullptr);
