@@ -76,6 +76,25 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+def bind_to_gpu_numa(torch, local):
+    """Run this rank (and the app it spawns) on the CPUs of the GPU's NUMA node, so the pinned page pool is allocated
+    next to the PCIe root the GPU hangs off (first-touch). Returns the node or None when sysfs does not say."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def host_budget_bytes(n_ranks):
     """Pinned host memory each rank may use for its page pool (the GPU box's RAM is shared by all ranks)."""
     avail = 0
@@ -345,6 +364,7 @@ def main():
         dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
         return float(t.item())
 
+    numa = bind_to_gpu_numa(torch, local)
     nbuf, over = choose_workload(world)
     link = measure_link(torch)
     sampler = ClockSampler(local)
@@ -384,7 +404,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": round(t_max / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"{nbuf}x{BUF_MIB}MiB alloc+touch loop, {QUOTA_MIB}MiB gpumem quota, {over >> 30} GiB oversubscribed, cyclic RMW touch, step={TOUCHES_PER_STEP} touches",
-                       "inputs": "larger than L2 (each step streams 1 GiB in + 1 GiB out)", "parallelism": f"replicas x{world}"},
+                       "inputs": "larger than L2 (each step streams 1 GiB in + 1 GiB out)", "parallelism": f"replicas x{world}", "numa_node": numa},
             "e2e": {"value": round(e2e_value, 3), "unit": "GB/s",
                     "h2d_bytes_per_step": int(e2e["page_in_bytes"] // args.steps), "d2h_bytes_per_step": int(e2e["page_out_bytes"] // args.steps),
                     "via": "LD_PRELOAD=libvgpu.so on an unmodified driver-API app (cuMemAlloc_v2/cuLaunchKernel intercept)",

@@ -187,10 +187,14 @@ void Runtime::measure_context_size() {
     if (!pid_found_) LOG_WARN("SET_TASK_PID FAILED.");
 }
 
-void Runtime::post_init() {
+void Runtime::post_init(bool late) {
     bool expected = false;
     if (!post_inited_.compare_exchange_strong(expected, true)) return;
-    measure_context_size();
+    // late = first intercepted call arrived without this library ever seeing cuInit (a runtime that resolved cuInit
+    // through a route that is not interposed): the driver is initialised and a context may already hold
+    // allocations, so the bare-context measurement would be wrong — skip it, keep everything else.
+    if (!late) measure_context_size();
+    else LOG_WARN("cuInit was not intercepted; initialising on first use (context size not measured)");
     int pct = (int)(region_ ? region_->sm_limit(0) : cfg_.sm_limit[0]);
     limiter_.reset(new Limiter(pct, region_ ? region_->raw() : nullptr, cfg_.util_policy));
     LOG_MSG("Initialized: oversubscribe=%d mem_limit0=%lu sm_limit0=%d", (int)cfg_.oversubscribe,
@@ -201,7 +205,7 @@ CUresult Runtime::init(unsigned flags) {
     ensure_initialized();
     if (!drv().loaded) return CUDA_ERROR_NOT_INITIALIZED;
     CUresult r = drv().cuInit(flags);
-    if (r == CUDA_SUCCESS) post_init();
+    if (r == CUDA_SUCCESS) post_init(false);
     return r;
 }
 
@@ -526,6 +530,7 @@ static CUresult guarded_launch(Runtime &rt, const Config &cfg, Limiter *lim, CUf
 CUresult Runtime::launch_kernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
                                 unsigned smem, CUstream st, void **params, void **extra) {
     if (!initialized()) ensure_initialized();
+    if (!post_inited_.load(std::memory_order_acquire)) post_init(true);
     return guarded_launch(*this, cfg_, limiter_.get(), f, params, extra, st,
                           [&] { return drv().cuLaunchKernel(f, gx, gy, gz, bx, by, bz, smem, st, params, extra); });
 }
@@ -533,6 +538,7 @@ CUresult Runtime::launch_kernel(CUfunction f, unsigned gx, unsigned gy, unsigned
 CUresult Runtime::launch_kernel_ex(const CUlaunchConfig *cfg, CUfunction f, void **params, void **extra) {
     if (!cfg || !drv().cuLaunchKernelEx) return CUDA_ERROR_NOT_SUPPORTED;
     if (!initialized()) ensure_initialized();
+    if (!post_inited_.load(std::memory_order_acquire)) post_init(true);
     return guarded_launch(*this, cfg_, limiter_.get(), f, params, extra, cfg->hStream,
                           [&] { return drv().cuLaunchKernelEx(cfg, f, params, extra); });
 }
@@ -542,6 +548,7 @@ CUresult Runtime::launch_cooperative(CUfunction f, unsigned gx, unsigned gy, uns
     // the reference lets cooperative launches bypass rate_limiter (Appendix E); here they are limited and admitted
     // like any other launch
     if (!initialized()) ensure_initialized();
+    if (!post_inited_.load(std::memory_order_acquire)) post_init(true);
     return guarded_launch(*this, cfg_, limiter_.get(), f, params, nullptr, st,
                           [&] { return drv().cuLaunchCooperativeKernel(f, gx, gy, gz, bx, by, bz, smem, st, params); });
 }

@@ -91,7 +91,7 @@ class Runtime {
    private:
     Runtime() = default;
     int current_device();
-    void post_init();                       // postInit@0x15d63
+    void post_init(bool late);              // postInit@0x15d63
     void measure_context_size();            // set_task_pid@0x16a7f
     void wait_running();                    // wait_status_self(1) loop of every wrapper
     bool track(CUdeviceptr base, size_t size, int dev, AllocKind kind);
