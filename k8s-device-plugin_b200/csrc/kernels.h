@@ -3,10 +3,13 @@
 #include <stdint.h>
 
 #define VGPU_PACK_MAX_STAGES 8             /* upper bound of the shared-memory ring depth of vgpu_pack_tma */
-#define VGPU_PACK_STAGES 4                 /* default ring depth ... */
-#define VGPU_PACK_TILE_BYTES (16u * 1024u) /* ... x default tile (one TMA bulk copy) = 64 KiB per CTA: three CTAs fit an SM, so a pack, an
-                                              unpack and an application kernel can share the SMs instead of queueing for shared memory */
-#define VGPU_PACK_CTAS_PER_SM 2            /* persistent CTAs per SM (each drives its own ring from one elected thread) */
+/* Default geometry from scripts/pack_sweep.py on B200 (profiles/r01_pack_sweep.json): 8 KiB tiles x 3 stages x 3 CTAs/SM
+ * reaches 6543 GB/s = 0.996 of the measured HBM copy peak with only 24 KiB of shared memory per CTA (72 KiB per SM),
+ * so a pack, an unpack and an application kernel co-reside on every SM instead of queueing for shared memory
+ * (the 6 x 32 KiB single-CTA ring first tried took 192 KiB and measured 0.914; 32 KiB x 2 x 2 is the top at 1.008). */
+#define VGPU_PACK_STAGES 3
+#define VGPU_PACK_TILE_BYTES (8u * 1024u)
+#define VGPU_PACK_CTAS_PER_SM 3            /* persistent CTAs per SM (each drives its own ring from one elected thread) */
 #define VGPU_PACK_MAX_SEG 96               /* segments per launch; keeps the kernel parameter block < 4 KiB */
 #define VGPU_SCAN_DIGIT_BITS 11
 #define VGPU_SCAN_BINS (1 << VGPU_SCAN_DIGIT_BITS)

@@ -1,7 +1,11 @@
 // swap.cc — see swap.h.
 #include "swap.h"
 
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -41,6 +45,34 @@ SwapConfig SwapConfig::from_env(uint64_t resident_cap, uint64_t virtual_cap) {
     return c;
 }
 
+// NUMA node of the GPU's PCIe root (sysfs), or -1. On HGX B200 boxes (2 sockets) page traffic that lands in the far
+// socket's DRAM crosses the inter-socket link and loses more than half of the host-link bandwidth (profiles/README.md),
+// so pinned slabs are allocated with a memory policy preferring the GPU's own node, wherever the caller's thread runs.
+static int gpu_numa_node(int dev) {
+    char bus[32] = {0};
+    CUdevice d = dev;
+    auto getbus = reinterpret_cast<CUresult (*)(char *, int, CUdevice)>(real_cuda_symbol("cuDeviceGetPCIBusId"));
+    if (!getbus || getbus(bus, sizeof bus, d) != CUDA_SUCCESS) return -1;
+    for (char *p = bus; *p; p++) if (*p >= 'A' && *p <= 'F') *p = (char)(*p - 'A' + 'a');
+    char path[128];
+    const char *bdf = bus;
+    if (std::strlen(bus) > 12) bdf = bus + (std::strlen(bus) - 12);   // "00000000:9c:00.0" -> "0000:9c:00.0"
+    std::snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bdf);
+    FILE *f = std::fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (std::fscanf(f, "%d", &node) != 1) node = -1;
+    std::fclose(f);
+    return node;
+}
+// set_mempolicy without libnuma: MPOL_PREFERRED = 1, MPOL_DEFAULT = 0
+static void prefer_node(int node) {
+    if (node < 0 || node >= 64) return;
+    unsigned long mask = 1ul << node;
+    syscall(SYS_set_mempolicy, 1, &mask, sizeof(mask) * 8);
+}
+static void default_policy() { syscall(SYS_set_mempolicy, 0, nullptr, 0); }
+
 SwapEngine *SwapEngine::create(int dev, const SwapConfig &cfg) {
     SwapEngine *e = new SwapEngine();
     if (!e->init(dev, cfg)) {
@@ -57,6 +89,7 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
     scan_lookahead_ = cfg.scan_lookahead;
     k_ = kernels_for_current_ctx();
     if (!k_) return false;
+    numa_node_ = std::getenv("VGPU_SWAP_NO_NUMA") ? -1 : gpu_numa_node(dev);
     CUmemAllocationProp prop = {};
     prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
     prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
@@ -103,8 +136,8 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
     if (scanner_->init(k_, tbl_cap_) != CUDA_SUCCESS) return false;
     use_ring_.resize(1024);
     for (auto &e : use_ring_) if (d.cuEventCreate(&e, CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) return false;
-    LOG_INFO("swap engine dev %d: resident cap %lu MiB, virtual cap %lu MiB, chunk %zu MiB x %d, arena %lu GiB, gran %zu",
-             dev_, (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(cfg_.virtual_cap >> 20), cfg_.chunk_bytes >> 20,
+    LOG_INFO("swap engine dev %d (numa %d): resident cap %lu MiB, virtual cap %lu MiB, chunk %zu MiB x %d, arena %lu GiB, gran %zu",
+             dev_, numa_node_, (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(cfg_.virtual_cap >> 20), cfg_.chunk_bytes >> 20,
              cfg_.ring_slots, (unsigned long)(cfg_.arena_bytes >> 30), gran_);
     return true;
 }
@@ -179,7 +212,9 @@ bool SwapEngine::host_alloc(size_t bytes, uint64_t *off) {
         sb = bytes;
     }
     Slab s;
+    if (numa_node_ >= 0) prefer_node(numa_node_);
     CUresult r = d.cuMemHostAlloc((void **)&s.host, sb, CU_MEMHOSTALLOC_PORTABLE);
+    if (numa_node_ >= 0) default_policy();
     if (r != CUDA_SUCCESS) { LOG_ERROR("pinned slab of %zu MiB failed: %d %s", sb >> 20, (int)r, cu_err(r)); return false; }
     s.bytes = sb;
     if (sb > bytes) s.free[bytes] = sb - bytes;

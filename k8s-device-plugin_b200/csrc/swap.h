@@ -127,6 +127,7 @@ class SwapEngine {
 
     mutable std::mutex mu_;
     int dev_ = 0;
+    int numa_node_ = -1;                            // NUMA node of the GPU (pinned slabs are allocated there)
     SwapConfig cfg_;
     const Kernels *k_ = nullptr;
     size_t gran_ = 2u << 20;

@@ -34,11 +34,31 @@ def _run(percent, nbytes, seconds=3.0):
     return n, wall, s.as_dict()
 
 
+def _kernel_ms(nbytes):
+    """device time of one touch kernel, by CUDA events, no limiter involved"""
+    buf = torch.zeros(nbytes // 8, dtype=torch.int64, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for _ in range(3):
+        v.lib().vgpu_wl_touch(buf.data_ptr(), nbytes // 8, st)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(10):
+        v.lib().vgpu_wl_touch(buf.data_ptr(), nbytes // 8, st)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / 10
+
+
 def test_long_kernels_are_held_to_30_percent():
-    n, wall, s = _run(30, 4 << 30)          # ~1.5 ms per touch of 4 GiB
+    t_kernel = _kernel_ms(4 << 30)          # ~1.5 ms per touch of 4 GiB
+    n, wall, s = _run(30, 4 << 30)
     duty = s["busy_ns"] / 1e9 / wall
     assert 0.24 <= duty <= 0.36, (duty, n, s)
     assert s["throttle_ns"] > 0.4 * wall * 1e9
+    # the %globaltimer stamps must agree with CUDA events on what a kernel costs (independent calibration) ...
+    assert abs(s["busy_ns"] / 1e6 / n - t_kernel) < 0.25 * t_kernel, (s["busy_ns"] / 1e6 / n, t_kernel)
+    # ... and so must the launch count: n kernels of t_kernel each inside `wall` seconds
+    assert 0.22 <= n * t_kernel / 1e3 / wall <= 0.38, (n, t_kernel, wall)
 
 
 def test_short_kernels_are_held_to_50_percent_with_amortised_stamps():
