@@ -117,8 +117,15 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
     va_free_[0] = want;
     owner_.assign(want / gran_, -1);
 
-    for (CUstream *s : {&s_scan_, &s_pack_, &s_unpack_, &s_out_, &s_in_})
-        if (d.cuStreamCreate(s, CU_STREAM_NON_BLOCKING) != CUDA_SUCCESS) { LOG_ERROR("side stream creation failed"); return false; }
+    // highest priority: when the application saturates the SMs, the block scheduler hands freed slots to the swap
+    // kernels first (they are short and the link is waiting on them)
+    int prio_lo = 0, prio_hi = 0;
+    if (d.cuCtxGetStreamPriorityRange) d.cuCtxGetStreamPriorityRange(&prio_lo, &prio_hi);
+    for (CUstream *s : {&s_scan_, &s_pack_, &s_unpack_, &s_out_, &s_in_}) {
+        CUresult sr = d.cuStreamCreateWithPriority ? d.cuStreamCreateWithPriority(s, CU_STREAM_NON_BLOCKING, prio_hi)
+                                                   : d.cuStreamCreate(s, CU_STREAM_NON_BLOCKING);
+        if (sr != CUDA_SUCCESS) { LOG_ERROR("side stream creation failed"); return false; }
+    }
     auto mkring = [&](std::vector<Slot> &ring) {
         ring.resize(cfg_.ring_slots);
         for (auto &s : ring) {

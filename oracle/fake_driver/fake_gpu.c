@@ -213,6 +213,8 @@ EXPORT CUresult cuModuleLoadDataEx(CUmodule *m, const void *img, unsigned n, voi
 EXPORT CUresult cuModuleGetFunction(CUfunction *f, CUmodule m, const char *name) { (void)m; (void)name; *f = &g_fn_obj; return CUDA_SUCCESS; }
 EXPORT CUresult cuModuleUnload(CUmodule m) { (void)m; return CUDA_SUCCESS; }
 EXPORT CUresult cuStreamCreate(CUstream *s, unsigned f) { (void)f; *s = &g_mod_obj; return CUDA_SUCCESS; }
+EXPORT CUresult cuStreamCreateWithPriority(CUstream *s, unsigned f, int p) { (void)f; (void)p; *s = &g_mod_obj; return CUDA_SUCCESS; }
+EXPORT CUresult cuCtxGetStreamPriorityRange(int *lo, int *hi) { if (lo) *lo = 0; if (hi) *hi = -5; return CUDA_SUCCESS; }
 EXPORT CUresult cuStreamDestroy_v2(CUstream s) { (void)s; return CUDA_SUCCESS; }
 EXPORT CUresult cuStreamSynchronize(CUstream s) { (void)s; return CUDA_SUCCESS; }
 EXPORT CUresult cuGetErrorString(CUresult e, const char **s) { (void)e; *s = "fake"; return CUDA_SUCCESS; }
