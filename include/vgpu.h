@@ -111,6 +111,8 @@ typedef struct vgpu_swap_stats {
     uint64_t pack_bytes, unpack_bytes;
     double pack_ms, unpack_ms;
     uint64_t scan_cache_hits;   /* evictions served from the previous scan's surplus (no new scan) */
+    /* calling-thread time inside admissions (ns): total, victim scan, wait for last pack, VMM calls, ring back-pressure */
+    uint64_t host_admit_ns, host_scan_ns, host_packsync_ns, host_vmm_ns, host_ring_ns;
 } vgpu_swap_stats_t;
 int vgpu_swap_create(int dev, const vgpu_swap_config_t *cfg, vgpu_swap_t **out);
 void vgpu_swap_destroy(vgpu_swap_t *s);

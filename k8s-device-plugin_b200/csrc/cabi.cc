@@ -159,6 +159,8 @@ static void fill_stats(const SwapStats &s, vgpu_swap_stats_t *o) {
     o->entries = s.entries; o->phys_creates = s.phys_creates; o->phys_reuses = s.phys_reuses;
     o->pack_bytes = s.pack_bytes; o->unpack_bytes = s.unpack_bytes; o->pack_ms = s.pack_ms; o->unpack_ms = s.unpack_ms;
     o->scan_cache_hits = s.scan_cache_hits;
+    o->host_admit_ns = s.host_admit_ns; o->host_scan_ns = s.host_scan_ns; o->host_packsync_ns = s.host_packsync_ns;
+    o->host_vmm_ns = s.host_vmm_ns; o->host_ring_ns = s.host_ring_ns;
 }
 VGPU_API int vgpu_swap_create(int dev, const vgpu_swap_config_t *cfg, vgpu_swap_t **out) {
     if (!out) return CUDA_ERROR_INVALID_VALUE;

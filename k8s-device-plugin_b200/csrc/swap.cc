@@ -1,7 +1,9 @@
 // swap.cc — see swap.h.
 #include "swap.h"
 
+#include <sched.h>
 #include <sys/syscall.h>
+#include <time.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -24,6 +26,8 @@ namespace vgpu {
     } while (0)
 
 static uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+static uint64_t mono_ns() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec; }
+struct ScopedNs { uint64_t *acc; uint64_t t0; explicit ScopedNs(uint64_t *a) : acc(a), t0(mono_ns()) {} ~ScopedNs() { *acc += mono_ns() - t0; } };
 static uint64_t env_u64(const char *name, uint64_t dflt) {
     const char *e = std::getenv(name);
     return e && *e ? std::strtoull(e, nullptr, 0) : dflt;
@@ -72,6 +76,36 @@ static void prefer_node(int node) {
     syscall(SYS_set_mempolicy, 1, &mask, sizeof(mask) * 8);
 }
 static void default_policy() { syscall(SYS_set_mempolicy, 0, nullptr, 0); }
+// The driver pins pages where the CALLING CPU sits (measured: with only a memory policy the pool still landed on
+// the far socket, 35-50 GB/s instead of 88), so the thread is moved onto the GPU's node for the duration of the slab
+// allocation and then put back. Fails harmlessly inside a cpuset that excludes those CPUs.
+struct NodeAffinity {
+    cpu_set_t saved;
+    bool moved = false;
+    explicit NodeAffinity(int node) {
+        if (node < 0) return;
+        char path[96];
+        std::snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+        FILE *f = std::fopen(path, "r");
+        if (!f) return;
+        char buf[1024] = {0};
+        if (!std::fgets(buf, sizeof buf, f)) { std::fclose(f); return; }
+        std::fclose(f);
+        cpu_set_t want;
+        CPU_ZERO(&want);
+        for (char *tok = std::strtok(buf, ",\n"); tok; tok = std::strtok(nullptr, ",\n")) {
+            int a = 0, b = 0;
+            if (std::sscanf(tok, "%d-%d", &a, &b) == 2) { for (int c = a; c <= b && c < CPU_SETSIZE; c++) CPU_SET(c, &want); }
+            else if (std::sscanf(tok, "%d", &a) == 1 && a < CPU_SETSIZE) CPU_SET(a, &want);
+        }
+        if (sched_getaffinity(0, sizeof saved, &saved) != 0) return;
+        cpu_set_t both;
+        CPU_AND(&both, &want, &saved);                 // stay inside whatever cpuset the container was given
+        if (CPU_COUNT(&both) == 0) return;
+        moved = sched_setaffinity(0, sizeof both, &both) == 0;
+    }
+    ~NodeAffinity() { if (moved) sched_setaffinity(0, sizeof saved, &saved); }
+};
 
 SwapEngine *SwapEngine::create(int dev, const SwapConfig &cfg) {
     SwapEngine *e = new SwapEngine();
@@ -219,9 +253,13 @@ bool SwapEngine::host_alloc(size_t bytes, uint64_t *off) {
         sb = bytes;
     }
     Slab s;
-    if (numa_node_ >= 0) prefer_node(numa_node_);
-    CUresult r = d.cuMemHostAlloc((void **)&s.host, sb, CU_MEMHOSTALLOC_PORTABLE);
-    if (numa_node_ >= 0) default_policy();
+    CUresult r;
+    {
+        NodeAffinity on_node(numa_node_);
+        if (numa_node_ >= 0) prefer_node(numa_node_);
+        r = d.cuMemHostAlloc((void **)&s.host, sb, CU_MEMHOSTALLOC_PORTABLE);
+        if (numa_node_ >= 0) default_policy();
+    }
     if (r != CUDA_SUCCESS) { LOG_ERROR("pinned slab of %zu MiB failed: %d %s", sb >> 20, (int)r, cu_err(r)); return false; }
     s.bytes = sb;
     if (sb > bytes) s.free[bytes] = sb - bytes;
@@ -329,6 +367,7 @@ CUresult SwapEngine::get_phys(size_t mapped, CUmemGenericAllocationHandle *h) {
 }
 CUresult SwapEngine::map_row(int row) {
     const DriverTable &d = drv();
+    ScopedNs t(&st_.host_vmm_ns);
     Side &s = side_[row];
     CUmemGenericAllocationHandle h;
     CUresult r = get_phys(s.mapped, &h);
@@ -348,6 +387,7 @@ CUresult SwapEngine::map_row(int row) {
 }
 void SwapEngine::unmap_row(int row) {
     const DriverTable &d = drv();
+    ScopedNs t(&st_.host_vmm_ns);
     Side &s = side_[row];
     d.cuMemUnmap(rows_[row].base, s.mapped);
     phys_pool_.emplace(s.mapped, s.handle);
@@ -365,7 +405,7 @@ CUevent SwapEngine::use_event(uint64_t seq) {
 SwapEngine::Slot &SwapEngine::acquire_slot(std::vector<Slot> &ring, int *cursor) {
     Slot &s = ring[*cursor];
     *cursor = (*cursor + 1) % (int)ring.size();
-    if (s.used) drv().cuEventSynchronize(s.busy);  // back-pressure: the only place the host waits for the link
+    if (s.used) { ScopedNs t(&st_.host_ring_ns); drv().cuEventSynchronize(s.busy); }  // back-pressure: the only place the host waits for the link
     s.used = true;
     s.seq++;
     return s;
@@ -471,7 +511,7 @@ CUresult SwapEngine::page_out(const std::vector<uint32_t> &victims) {
     CUevent packed = get_event();
     if (!packed) return CUDA_ERROR_OUT_OF_MEMORY;
     CU_TRY(d.cuEventRecord(packed, s_pack_));
-    CU_TRY(d.cuEventSynchronize(packed));
+    { ScopedNs t(&st_.host_packsync_ns); CU_TRY(d.cuEventSynchronize(packed)); }
     ready_free_.push_back(packed);
     for (size_t i = 0; i < victims.size(); i++) {
         uint32_t v = victims[i];
@@ -619,6 +659,7 @@ CUresult SwapEngine::make_room(uint64_t need_mapped) {
     }
     // 2. GPU scan, asking for `scan_lookahead_` times the deficit so the next evictions need no scan
     if (victims.empty()) {
+        ScopedNs t(&st_.host_scan_ns);
         CUresult r = sync_table(s_scan_);
         if (r != CUDA_SUCCESS) return r;
         std::vector<uint32_t> found;
@@ -702,6 +743,7 @@ CUresult SwapEngine::free(CUdeviceptr dptr) {
 CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
     const DriverTable &d = drv();
     std::lock_guard<std::mutex> g(mu_);
+    ScopedNs t_admit(&st_.host_admit_ns);
     st_.admissions++;
     tick_++;
     std::vector<int> missing;

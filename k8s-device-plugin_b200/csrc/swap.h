@@ -50,6 +50,9 @@ struct SwapStats {
     uint64_t resident_bytes = 0, live_bytes = 0, host_bytes = 0, entries = 0;
     uint64_t phys_creates = 0, phys_reuses = 0;
     double pack_ms = 0, unpack_ms = 0;     // device time, only when profiling
+    // where the calling thread's time goes inside ensure_resident/alloc (ns): victim scan incl. its sync, waiting for
+    // the last pack of a batch, VMM calls (unmap/map/setaccess/create), staging-ring back-pressure, whole admissions
+    uint64_t host_scan_ns = 0, host_packsync_ns = 0, host_vmm_ns = 0, host_ring_ns = 0, host_admit_ns = 0;
     uint64_t pack_bytes = 0, unpack_bytes = 0;
 };
 
