@@ -375,6 +375,7 @@ def main():
     page_bytes = d["page_in_bytes"] + d["page_out_bytes"]
     t_max, total_bytes, value = aggregate(dist, "cuda", ms, page_bytes)
     kern_ms = d["pack_ms"] + d["unpack_ms"]
+    span_ms = d.get("pack_span_ms", 0.0) + d.get("unpack_span_ms", 0.0)
     kern_bytes = 2 * (d["pack_bytes"] + d["unpack_bytes"])      # algorithmic: read + write of every byte moved
     kern_launches = d["pack_launches"] + d["unpack_launches"]
     launches = kern_launches + d["scan_launches"] + args.steps * TOUCHES_PER_STEP
@@ -415,7 +416,14 @@ def main():
                          "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4) if achieved else None, "peak_source": how, "traffic": None,
                          "launches": int(kern_launches), "avg_launch_us": round(kern_ms * 1e3 / max(kern_launches, 1), 2),
-                         "bytes_per_launch": int(kern_bytes // max(kern_launches, 1))},
+                         "bytes_per_launch": int(kern_bytes // max(kern_launches, 1)),
+                         "note": "achieved = CUDA-event brackets on the engine's kernel streams inside the timed region; they include the host's "
+                                 "event->launch gap (the streams are idle between chunks) and SM sharing with the application's touch kernel. "
+                                 "device_span = the same launches timed by in-kernel %globaltimer stamps (min CTA start .. max CTA end); "
+                                 "isolated figures and ncu captures: profiles/",
+                         "device_span": {"achieved": round(kern_bytes / (span_ms / 1e3) / 1e9, 1) if span_ms > 0 else None,
+                                         "frac": round(kern_bytes / (span_ms / 1e3) / 1e9 / peak, 4) if span_ms > 0 else None,
+                                         "avg_launch_us": round(span_ms * 1e3 / max(kern_launches, 1), 2)}},
             "link_roofline": {"bound": "host-link", "achieved": round(value / world, 3), "peak": round(link["bidir"], 2), "unit": "GB/s",
                               "frac": round(value / world / link["bidir"], 4) if link["bidir"] else None,
                               "h2d_peak": round(link["h2d"], 2), "d2h_peak": round(link["d2h"], 2),

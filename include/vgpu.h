@@ -113,6 +113,7 @@ typedef struct vgpu_swap_stats {
     uint64_t scan_cache_hits;   /* evictions served from the previous scan's surplus (no new scan) */
     /* calling-thread time inside admissions (ns): total, victim scan, wait for last pack, VMM calls, ring back-pressure */
     uint64_t host_admit_ns, host_scan_ns, host_packsync_ns, host_vmm_ns, host_ring_ns;
+    double pack_span_ms, unpack_span_ms;   /* exact in-kernel %globaltimer execution spans (profiling), valid after vgpu_swap_drain */
 } vgpu_swap_stats_t;
 int vgpu_swap_create(int dev, const vgpu_swap_config_t *cfg, vgpu_swap_t **out);
 void vgpu_swap_destroy(vgpu_swap_t *s);

@@ -56,7 +56,8 @@ class SwapStats(C.Structure):
         "page_out_bytes", "page_in_bytes", "evictions", "faults", "admissions", "pack_launches", "unpack_launches",
         "scan_launches", "scans", "resident_bytes", "live_bytes", "host_bytes", "entries", "phys_creates",
         "phys_reuses", "pack_bytes", "unpack_bytes")] + [("pack_ms", C.c_double), ("unpack_ms", C.c_double)] + [(n, C.c_uint64) for n in (
-        "scan_cache_hits", "host_admit_ns", "host_scan_ns", "host_packsync_ns", "host_vmm_ns", "host_ring_ns")]
+        "scan_cache_hits", "host_admit_ns", "host_scan_ns", "host_packsync_ns", "host_vmm_ns", "host_ring_ns")] + [
+        ("pack_span_ms", C.c_double), ("unpack_span_ms", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -161,6 +161,7 @@ static void fill_stats(const SwapStats &s, vgpu_swap_stats_t *o) {
     o->scan_cache_hits = s.scan_cache_hits;
     o->host_admit_ns = s.host_admit_ns; o->host_scan_ns = s.host_scan_ns; o->host_packsync_ns = s.host_packsync_ns;
     o->host_vmm_ns = s.host_vmm_ns; o->host_ring_ns = s.host_ring_ns;
+    o->pack_span_ms = s.pack_span_ms; o->unpack_span_ms = s.unpack_span_ms;
 }
 VGPU_API int vgpu_swap_create(int dev, const vgpu_swap_config_t *cfg, vgpu_swap_t **out) {
     if (!out) return CUDA_ERROR_INVALID_VALUE;

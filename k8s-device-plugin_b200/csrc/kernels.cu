@@ -87,6 +87,7 @@ extern "C" __global__ void __launch_bounds__(32, 1) vgpu_pack_tma(const __grid_c
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);              // up to VGPU_PACK_MAX_STAGES barriers
     unsigned char *buf = smem + 128;                                   // ST tiles
     if (threadIdx.x != 0) return;
+    const uint64_t t_start = p.span ? globaltimer() : 0;
 
     for (int s = 0; s < ST; s++) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -97,6 +98,7 @@ extern "C" __global__ void __launch_bounds__(32, 1) vgpu_pack_tma(const __grid_c
     const uint64_t first = blockIdx.x;
     if (first >= total) return;
     const uint64_t my_tiles = (total - first + stride - 1) / stride;
+    unsigned long long *span = reinterpret_cast<unsigned long long *>(p.span);
 
     auto tile_desc = [&](uint64_t k, const unsigned char *&src, unsigned char *&dst, uint32_t &len) {
         uint64_t t = first + k * stride;
@@ -133,6 +135,10 @@ extern "C" __global__ void __launch_bounds__(32, 1) vgpu_pack_tma(const __grid_c
         }
     }
     bulk_wait_all();
+    if (span) {   // exact execution span of this launch under whatever else shares the GPU: min start / max end over CTAs
+        atomicMin(&span[0], static_cast<unsigned long long>(t_start));
+        atomicMax(&span[1], static_cast<unsigned long long>(globaltimer()));
+    }
 }
 
 // Any-alignment fallback: all threads of the CTA copy one tile at a time through registers. Used for segments whose

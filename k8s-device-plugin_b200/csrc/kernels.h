@@ -41,6 +41,7 @@ typedef struct VgpuPackParams {
     uint64_t total_tiles;
     uint32_t stages;                       /* ring depth used by this launch (<= VGPU_PACK_MAX_STAGES) */
     uint32_t _pad;
+    uint64_t span;                         /* optional device address of {min start, max end} %globaltimer words (0 = off) */
     VgpuPackSeg seg[VGPU_PACK_MAX_SEG];
 } VgpuPackParams;
 

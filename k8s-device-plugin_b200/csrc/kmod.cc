@@ -69,7 +69,7 @@ const Kernels *kernels_for_current_ctx() {
 }
 
 static CUresult launch_pack_set(const Kernels *k, CUfunction fn, bool tma, const PackSegment *segs, const uint32_t *which,
-                                size_t n, CUstream stream, int *launches) {
+                                size_t n, CUstream stream, int *launches, CUdeviceptr span) {
     const DriverTable &d = drv();
     size_t i = 0;
     PackConfig cfg = pack_config();
@@ -84,6 +84,7 @@ static CUresult launch_pack_set(const Kernels *k, CUfunction fn, bool tma, const
         p.tile_bytes = tile;
         p.stages = cfg.stages;
         p._pad = 0;
+        p.span = span;
         p.nseg = 0;
         uint64_t tiles = 0;
         while (i < n && p.nseg < VGPU_PACK_MAX_SEG) {
@@ -112,7 +113,7 @@ static CUresult launch_pack_set(const Kernels *k, CUfunction fn, bool tma, const
     return CUDA_SUCCESS;
 }
 
-CUresult launch_pack(const Kernels *k, const PackSegment *segs, size_t nseg, CUstream stream, int *launches_out) {
+CUresult launch_pack(const Kernels *k, const PackSegment *segs, size_t nseg, CUstream stream, int *launches_out, CUdeviceptr span) {
     if (!k) return CUDA_ERROR_NOT_INITIALIZED;
     std::vector<uint32_t> al, un;
     for (size_t i = 0; i < nseg; i++) {
@@ -121,8 +122,8 @@ CUresult launch_pack(const Kernels *k, const PackSegment *segs, size_t nseg, CUs
         (aligned ? al : un).push_back((uint32_t)i);
     }
     CUresult r = CUDA_SUCCESS;
-    if (!al.empty()) r = launch_pack_set(k, k->pack_tma, true, segs, al.data(), al.size(), stream, launches_out);
-    if (r == CUDA_SUCCESS && !un.empty()) r = launch_pack_set(k, k->pack_generic, false, segs, un.data(), un.size(), stream, launches_out);
+    if (!al.empty()) r = launch_pack_set(k, k->pack_tma, true, segs, al.data(), al.size(), stream, launches_out, span);
+    if (r == CUDA_SUCCESS && !un.empty()) r = launch_pack_set(k, k->pack_generic, false, segs, un.data(), un.size(), stream, launches_out, 0);
     return r;
 }
 

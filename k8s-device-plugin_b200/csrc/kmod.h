@@ -32,7 +32,8 @@ PackConfig &pack_config();
 
 // Enqueues the copies described by segs on `stream` (src -> dst for every segment). 16-byte-aligned segments go
 // through vgpu_pack_tma, the rest through vgpu_pack_generic. launches_out (optional) += number of kernel launches.
-CUresult launch_pack(const Kernels *k, const PackSegment *segs, size_t nseg, CUstream stream, int *launches_out = nullptr);
+CUresult launch_pack(const Kernels *k, const PackSegment *segs, size_t nseg, CUstream stream, int *launches_out = nullptr,
+                     CUdeviceptr span = 0);   // span: optional {min start, max end} %globaltimer slot, pre-set to {~0, 0}
 
 // Exact-LRU victim selection on the GPU (see kernels.cu). Owns its device/pinned scratch.
 class VictimScanner {

@@ -410,6 +410,34 @@ SwapEngine::Slot &SwapEngine::acquire_slot(std::vector<Slot> &ring, int *cursor)
     s.seq++;
     return s;
 }
+CUdeviceptr SwapEngine::next_span(bool unpack) {
+    if (!cfg_.profile) return 0;
+    const DriverTable &d = drv();
+    if (!d_span_) {
+        span_cap_ = 1u << 16;
+        if (d.cuMemAlloc_v2(&d_span_, (size_t)span_cap_ * 16) != CUDA_SUCCESS) { d_span_ = 0; return 0; }
+        std::vector<uint64_t> init((size_t)span_cap_ * 2);
+        for (uint32_t i = 0; i < span_cap_; i++) { init[2 * i] = ~0ull; init[2 * i + 1] = 0; }
+        d.cuMemcpyHtoD_v2(d_span_, init.data(), init.size() * 8);
+        span_unpack_.assign(span_cap_, 0);
+    }
+    if (span_next_ >= span_cap_) return 0;   // enough samples
+    span_unpack_[span_next_] = unpack;
+    return d_span_ + (size_t)(span_next_++) * 16;
+}
+void SwapEngine::harvest_spans() {
+    if (!d_span_ || span_read_ >= span_next_) return;
+    const DriverTable &d = drv();
+    std::vector<uint64_t> v((size_t)(span_next_ - span_read_) * 2);
+    if (d.cuMemcpyDtoH_v2(v.data(), d_span_ + (size_t)span_read_ * 16, v.size() * 8) != CUDA_SUCCESS) return;
+    for (uint32_t i = 0; i < span_next_ - span_read_; i++) {
+        uint64_t a = v[2 * i], b = v[2 * i + 1];
+        if (a == ~0ull || b <= a) continue;
+        (span_unpack_[span_read_ + i] ? st_.unpack_span_ms : st_.pack_span_ms) += (double)(b - a) / 1e6;
+    }
+    span_read_ = span_next_;
+}
+
 void SwapEngine::prof_begin(CUstream s, CUevent *a) {
     *a = nullptr;
     if (!cfg_.profile) return;
@@ -480,7 +508,7 @@ CUresult SwapEngine::page_out(const std::vector<uint32_t> &victims) {
         int launches = 0;
         CUevent pa;
         prof_begin(s_pack_, &pa);
-        CUresult r = launch_pack(k_, segs.data(), segs.size(), s_pack_, &launches);
+        CUresult r = launch_pack(k_, segs.data(), segs.size(), s_pack_, &launches, next_span(false));
         if (r != CUDA_SUCCESS) return r;
         prof_end(s_pack_, pa, false, pos);
         st_.pack_launches += launches;
@@ -559,7 +587,7 @@ CUresult SwapEngine::page_in(const std::vector<int> &rows) {
         int launches = 0;
         CUevent pa;
         prof_begin(s_unpack_, &pa);
-        r = launch_pack(k_, segs.data(), segs.size(), s_unpack_, &launches);
+        r = launch_pack(k_, segs.data(), segs.size(), s_unpack_, &launches, next_span(true));
         if (r != CUDA_SUCCESS) return r;
         prof_end(s_unpack_, pa, true, pos);
         st_.unpack_launches += launches;
@@ -804,6 +832,7 @@ CUresult SwapEngine::drain() {
     for (CUstream s : {s_scan_, s_pack_, s_unpack_, s_out_, s_in_})
         if (s && (t = d.cuStreamSynchronize(s)) != CUDA_SUCCESS) r = t;
     reap_pending_host(true);
+    harvest_spans();
     harvest_prof(true);
     return r;
 }
@@ -811,6 +840,7 @@ CUresult SwapEngine::drain() {
 SwapStats SwapEngine::stats() {
     std::lock_guard<std::mutex> g(mu_);
     harvest_prof(false);
+    harvest_spans();
     SwapStats s = st_;
     s.resident_bytes = resident_mapped_;
     s.live_bytes = live_bytes_;

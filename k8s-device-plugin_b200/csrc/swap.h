@@ -49,7 +49,9 @@ struct SwapStats {
     uint64_t pack_launches = 0, unpack_launches = 0, scan_launches = 0, scans = 0, scan_cache_hits = 0;
     uint64_t resident_bytes = 0, live_bytes = 0, host_bytes = 0, entries = 0;
     uint64_t phys_creates = 0, phys_reuses = 0;
-    double pack_ms = 0, unpack_ms = 0;     // device time, only when profiling
+    double pack_ms = 0, unpack_ms = 0;     // CUDA-event brackets around each launch, only when profiling (include the
+                                           // host's event->launch gap when the stream is idle)
+    double pack_span_ms = 0, unpack_span_ms = 0;   // exact execution spans from in-kernel %globaltimer stamps (profiling)
     // where the calling thread's time goes inside ensure_resident/alloc (ns): victim scan incl. its sync, waiting for
     // the last pack of a batch, VMM calls (unmap/map/setaccess/create), staging-ring back-pressure, whole admissions
     uint64_t host_scan_ns = 0, host_packsync_ns = 0, host_vmm_ns = 0, host_ring_ns = 0, host_admit_ns = 0;
@@ -170,6 +172,11 @@ class SwapEngine {
     uint32_t scan_lookahead_ = 8;
     SwapStats st_;
     struct Prof { CUevent a, b; bool unpack; uint64_t bytes; };
+    CUdeviceptr d_span_ = 0;                        // profiling: {min start, max end} per launch, pre-set to {~0, 0}
+    uint32_t span_cap_ = 0, span_next_ = 0, span_read_ = 0;
+    std::vector<uint8_t> span_unpack_;
+    CUdeviceptr next_span(bool unpack);
+    void harvest_spans();
     std::vector<Prof> prof_;
 };
 

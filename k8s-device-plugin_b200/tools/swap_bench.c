@@ -21,7 +21,7 @@
 #define CK(x) do { CUresult _r = (x); if (_r != CUDA_SUCCESS) { const char *s = 0; cuGetErrorName(_r, &s); \
     fprintf(stderr, "swap_bench: %s -> %d %s (line %d)\n", #x, (int)_r, s ? s : "?", __LINE__); printf("{\"error\": \"%s rc=%d\"}\n", #x, (int)_r); exit(3); } } while (0)
 
-typedef struct { uint64_t v[17]; double pack_ms, unpack_ms; uint64_t scan_cache_hits, host_admit_ns, host_scan_ns, host_packsync_ns, host_vmm_ns, host_ring_ns; } swap_stats_t; /* mirrors vgpu_swap_stats_t */
+typedef struct { uint64_t v[17]; double pack_ms, unpack_ms; uint64_t scan_cache_hits, host_admit_ns, host_scan_ns, host_packsync_ns, host_vmm_ns, host_ring_ns; double pack_span_ms, unpack_span_ms; } swap_stats_t; /* mirrors vgpu_swap_stats_t */
 typedef int (*stats_fn)(int, swap_stats_t *);
 typedef int (*prof_fn)(int, int);
 
@@ -155,7 +155,8 @@ int main(int argc, char **argv) {
            "\"pack_ms\": %.3f, \"unpack_ms\": %.3f, \"pack_bytes\": %llu, \"unpack_bytes\": %llu, "
            "\"pack_launches\": %llu, \"unpack_launches\": %llu, \"scan_launches\": %llu, \"faults\": %llu, \"evictions\": %llu, "
            "\"phys_creates\": %llu, \"phys_reuses\": %llu, \"scans\": %llu, \"scan_cache_hits\": %llu, "
-           "\"host_ms\": {\"admit\": %.1f, \"scan\": %.1f, \"packsync\": %.1f, \"vmm\": %.1f, \"ringwait\": %.1f}}\n",
+           "\"host_ms\": {\"admit\": %.1f, \"scan\": %.1f, \"packsync\": %.1f, \"vmm\": %.1f, \"ringwait\": %.1f}, "
+           "\"pack_span_ms\": %.3f, \"unpack_span_ms\": %.3f}\n",
            nbuf, mib, steps, warmup, order, managed, ballast_mib, ev_ms, w1 - w0, w_enq - w0, t_alloc1 - t_alloc0, t_ver1 - t_ver0,
            get_stats ? "true" : "false", (unsigned long long)pin, (unsigned long long)pout,
            (unsigned long long)steps * bytes, mism, verify,
@@ -166,7 +167,8 @@ int main(int argc, char **argv) {
            (unsigned long long)(s1.v[13] - s0.v[13]), (unsigned long long)(s1.v[14] - s0.v[14]),
            (unsigned long long)(s1.v[8] - s0.v[8]), (unsigned long long)(s1.scan_cache_hits - s0.scan_cache_hits),
            (s1.host_admit_ns - s0.host_admit_ns) / 1e6, (s1.host_scan_ns - s0.host_scan_ns) / 1e6, (s1.host_packsync_ns - s0.host_packsync_ns) / 1e6,
-           (s1.host_vmm_ns - s0.host_vmm_ns) / 1e6, (s1.host_ring_ns - s0.host_ring_ns) / 1e6);
+           (s1.host_vmm_ns - s0.host_vmm_ns) / 1e6, (s1.host_ring_ns - s0.host_ring_ns) / 1e6,
+           s1.pack_span_ms - s0.pack_span_ms, s1.unpack_span_ms - s0.unpack_span_ms);
     fflush(stdout);
     return mism ? 4 : 0;
 }
