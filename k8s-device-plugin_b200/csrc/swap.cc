@@ -476,7 +476,7 @@ void SwapEngine::harvest_prof(bool wait) {
 }
 
 // ---------------------------------------------------------------------------------------------- page-out / page-in
-CUresult SwapEngine::page_out(const std::vector<uint32_t> &victims) {
+CUresult SwapEngine::page_out(const std::vector<uint32_t> &victims, bool finish) {
     const DriverTable &d = drv();
     if (victims.empty()) return CUDA_SUCCESS;
     // one contiguous pinned block for the whole batch so the staging layout equals the host layout (one DMA per
@@ -491,8 +491,8 @@ CUresult SwapEngine::page_out(const std::vector<uint32_t> &victims) {
         for (size_t i = 0; i < victims.size(); i++) { side_[victims[i]].host_off = block + o; o += len[i]; }
     } else {
         if (victims.size() == 1) { LOG_ERROR("pinned host pool exhausted (%lu MiB in use)", (unsigned long)(host_used_ >> 20)); return CUDA_ERROR_OUT_OF_MEMORY; }
-        for (uint32_t v : victims) { CUresult r = page_out(std::vector<uint32_t>{v}); if (r != CUDA_SUCCESS) return r; }
-        return CUDA_SUCCESS;
+        for (uint32_t v : victims) { CUresult r = page_out(std::vector<uint32_t>{v}, false); if (r != CUDA_SUCCESS) return r; }
+        return finish ? page_out_finish() : CUDA_SUCCESS;
     }
     // order the pack behind the victims' last users
     for (uint32_t v : victims) {
@@ -535,14 +535,22 @@ CUresult SwapEngine::page_out(const std::vector<uint32_t> &victims) {
         }
     }
     { CUresult r = flush(); if (r != CUDA_SUCCESS) return r; }
-    // the victims' physical pages may be recycled as soon as the LAST PACK has read them — not when the DMA is done
+    // the victims' physical pages may be recycled as soon as the LAST PACK has read them — not when the DMA is done.
+    // The wait for that pack is deferred to page_out_finish() so the caller can put the page-in's H2D copies on
+    // the wire first (they only need staging slots, not the physical memory being freed here).
+    for (uint32_t v : victims) out_pending_.push_back(v);
+    return finish ? page_out_finish() : CUDA_SUCCESS;
+}
+
+CUresult SwapEngine::page_out_finish() {
+    const DriverTable &d = drv();
+    if (out_pending_.empty()) return CUDA_SUCCESS;
     CUevent packed = get_event();
     if (!packed) return CUDA_ERROR_OUT_OF_MEMORY;
     CU_TRY(d.cuEventRecord(packed, s_pack_));
     { ScopedNs t(&st_.host_packsync_ns); CU_TRY(d.cuEventSynchronize(packed)); }
     ready_free_.push_back(packed);
-    for (size_t i = 0; i < victims.size(); i++) {
-        uint32_t v = victims[i];
+    for (uint32_t v : out_pending_) {
         unmap_row((int)v);
         side_[v].has_host = true;
         rows_[v].state = VGPU_ST_PAGED_OUT;
@@ -551,75 +559,103 @@ CUresult SwapEngine::page_out(const std::vector<uint32_t> &victims) {
         mark_dirty((int)v);
         st_.evictions++;
     }
+    out_pending_.clear();
     return CUDA_SUCCESS;
 }
 
-CUresult SwapEngine::page_in(const std::vector<int> &rows) {
+// Page-in is planned first (which pieces of which rows travel in which staging-slot job), then runs in two phases:
+//   stage  : host -> staging H2D copies for as many jobs as there are free staging slots, WITHOUT blocking. Needs
+//            neither the rows' physical memory nor their mappings, so it is issued before the victims are unmapped
+//            and overlaps the VMM calls (0.3-0.8 ms per remap on B200, profiles/README.md) with the transfer;
+//   finish : map the rows, then for every job (staged or not) launch the unpack kernel behind its H2D.
+CUresult SwapEngine::page_in_plan(const std::vector<int> &rows) {
+    in_jobs_.clear();
+    InJob cur;
+    uint64_t pos = 0;
+    auto close = [&]() { if (!cur.segs.empty()) { cur.bytes = pos; in_jobs_.push_back(std::move(cur)); cur = InJob(); pos = 0; } };
+    for (int r : rows) {
+        uint64_t len = round_up(rows_[r].size, 256), off = 0;
+        while (off < len) {
+            uint64_t piece = std::min<uint64_t>(len - off, cfg_.chunk_bytes - pos);
+            unsigned char *src = host_ptr(side_[r].host_off) + off;
+            if (!cur.runs.empty() && cur.runs.back().src + cur.runs.back().len == src && cur.runs.back().pos + cur.runs.back().len == pos) cur.runs.back().len += piece;
+            else cur.runs.push_back(InRun{src, pos, piece});
+            cur.segs.push_back(PackSegment{pos, rows_[r].base + off, piece});   // src = offset inside the slot, fixed up at issue time
+            off += piece; pos += piece;
+            if (off == len) cur.done_rows.push_back(r);
+            if (pos == cfg_.chunk_bytes || cur.segs.size() == VGPU_PACK_MAX_SEG) close();
+        }
+    }
+    close();
+    return CUDA_SUCCESS;
+}
+
+CUresult SwapEngine::in_issue_copies(InJob &j) {
+    const DriverTable &d = drv();
+    for (const InRun &r : j.runs) {
+        CU_TRY(d.cuMemcpyHtoDAsync_v2(j.slot->buf + r.pos, r.src, r.len, s_in_));
+        st_.page_in_bytes += r.len;
+    }
+    CU_TRY(d.cuEventRecord(j.slot->busy, s_in_));     // "loaded"; re-recorded as "unpacked" in finish
+    return CUDA_SUCCESS;
+}
+
+CUresult SwapEngine::page_in_stage(const std::vector<int> &rows) {
     const DriverTable &d = drv();
     for (int r : rows) {
-        CUresult rc = map_row(r);
-        if (rc != CUDA_SUCCESS) return rc;
         // a row that was paged out moments ago: its D2H may still be in flight -> order the H2D behind that chunk
         // only (not behind the whole page-out queue, which would serialise the two link directions)
         Side &s = side_[r];
         if (s.out_slot >= 0 && ring_out_[s.out_slot].seq == s.out_seq) CU_TRY(d.cuStreamWaitEvent(s_in_, ring_out_[s.out_slot].busy, 0));
         s.out_slot = -1;
     }
-    std::vector<PackSegment> segs;
+    CU_TRY(page_in_plan(rows));
+    for (InJob &j : in_jobs_) {
+        Slot &s = ring_in_[cur_in_];
+        if (s.used && d.cuEventQuery(s.busy) != CUDA_SUCCESS) break;   // never block here
+        cur_in_ = (cur_in_ + 1) % (int)ring_in_.size();
+        s.used = true;
+        s.seq++;
+        j.slot = &s;
+        CU_TRY(in_issue_copies(j));
+    }
+    return CUDA_SUCCESS;
+}
+
+CUresult SwapEngine::page_in_finish(const std::vector<int> &rows) {
+    const DriverTable &d = drv();
+    for (int r : rows) {
+        CUresult rc = map_row(r);
+        if (rc != CUDA_SUCCESS) return rc;
+    }
     std::vector<PendingHost> fresh;
-    Slot *slot = nullptr;
-    uint64_t pos = 0;
-    // pending host->staging copy run (merged while both sides stay contiguous)
-    unsigned char *run_src = nullptr; uint64_t run_dst = 0, run_len = 0;
-    auto flush_run = [&]() -> CUresult {
-        if (!run_len) return CUDA_SUCCESS;
-        CU_TRY(d.cuMemcpyHtoDAsync_v2(slot->buf + run_dst, run_src, run_len, s_in_));
-        st_.page_in_bytes += run_len;
-        run_len = 0;
-        return CUDA_SUCCESS;
-    };
-    auto flush = [&]() -> CUresult {
-        if (!slot || segs.empty()) return CUDA_SUCCESS;
-        CUresult r = flush_run();
-        if (r != CUDA_SUCCESS) return r;
-        CU_TRY(d.cuEventRecord(slot->busy, s_in_));
-        CU_TRY(d.cuStreamWaitEvent(s_unpack_, slot->busy, 0));
+    for (InJob &j : in_jobs_) {
+        if (!j.slot) {
+            j.slot = &acquire_slot(ring_in_, &cur_in_);
+            CU_TRY(in_issue_copies(j));
+        }
+        for (PackSegment &sg : j.segs) sg.src += j.slot->buf;
+        CU_TRY(d.cuStreamWaitEvent(s_unpack_, j.slot->busy, 0));
         int launches = 0;
         CUevent pa;
         prof_begin(s_unpack_, &pa);
-        r = launch_pack(k_, segs.data(), segs.size(), s_unpack_, &launches, next_span(true));
+        CUresult r = launch_pack(k_, j.segs.data(), j.segs.size(), s_unpack_, &launches, next_span(true));
         if (r != CUDA_SUCCESS) return r;
-        prof_end(s_unpack_, pa, true, pos);
+        prof_end(s_unpack_, pa, true, j.bytes);
         st_.unpack_launches += launches;
-        CU_TRY(d.cuEventRecord(slot->busy, s_unpack_));
-        segs.clear();
-        slot = nullptr;
-        return CUDA_SUCCESS;
-    };
-    for (int r : rows) {
-        uint64_t len = round_up(rows_[r].size, 256), off = 0;
-        while (off < len) {
-            if (!slot) { slot = &acquire_slot(ring_in_, &cur_in_); pos = 0; }
-            uint64_t piece = std::min<uint64_t>(len - off, cfg_.chunk_bytes - pos);
-            unsigned char *src = host_ptr(side_[r].host_off) + off;
-            if (run_len && run_src + run_len == src && run_dst + run_len == pos) run_len += piece;
-            else { CUresult rc = flush_run(); if (rc != CUDA_SUCCESS) return rc; run_src = src; run_dst = pos; run_len = piece; }
-            segs.push_back(PackSegment{slot->buf + pos, rows_[r].base + off, piece});
-            off += piece; pos += piece;
-            if (pos == cfg_.chunk_bytes || segs.size() == VGPU_PACK_MAX_SEG) { CUresult rc = flush(); if (rc != CUDA_SUCCESS) return rc; }
+        CU_TRY(d.cuEventRecord(j.slot->busy, s_unpack_));
+        for (int row : j.done_rows) {
+            CUevent ev = get_event();
+            if (!ev) return CUDA_ERROR_OUT_OF_MEMORY;
+            CU_TRY(d.cuEventRecord(ev, s_unpack_));
+            side_[row].ready = ev;
+            fresh.push_back(PendingHost{side_[row].host_off, round_up(rows_[row].size, 256), nullptr});
+            side_[row].has_host = false;
+            rows_[row].state = VGPU_ST_RESIDENT;
+            mark_dirty(row);
         }
-        // completion marker for this row: everything enqueued on s_unpack_ so far includes its last unpack once flushed
-        CUresult rc = flush();
-        if (rc != CUDA_SUCCESS) return rc;
-        CUevent ev = get_event();
-        if (!ev) return CUDA_ERROR_OUT_OF_MEMORY;
-        CU_TRY(d.cuEventRecord(ev, s_unpack_));
-        side_[r].ready = ev;
-        fresh.push_back(PendingHost{side_[r].host_off, round_up(rows_[r].size, 256), nullptr});
-        side_[r].has_host = false;
-        rows_[r].state = VGPU_ST_RESIDENT;
-        mark_dirty(r);
     }
+    in_jobs_.clear();
     if (!fresh.empty()) {
         // the pinned ranges go back to the pool only after the H2D copies above have READ them (a later page-out
         // would otherwise overwrite them): parked with one event, reaped by host_alloc() once it has fired
@@ -661,7 +697,7 @@ void SwapEngine::release_host_range(uint64_t off, uint64_t len) {
     host_used_ = host_used_ > len ? host_used_ - len : 0;
 }
 
-CUresult SwapEngine::make_room(uint64_t need_mapped) {
+CUresult SwapEngine::make_room(uint64_t need_mapped, bool finish) {
     if (need_mapped > cfg_.resident_cap) return CUDA_ERROR_OUT_OF_MEMORY;
     if (resident_mapped_ + need_mapped <= cfg_.resident_cap) return CUDA_SUCCESS;
     const uint64_t deficit = resident_mapped_ + need_mapped - cfg_.resident_cap;
@@ -715,7 +751,7 @@ CUresult SwapEngine::make_room(uint64_t need_mapped) {
     }
     // the victims' physical handles are now pooled; get_phys() re-maps a same-size one under the incoming buffer
     // (no cuMemCreate/cuMemRelease in steady state) and only trims the pool when it has to create
-    return page_out(victims);
+    return page_out(victims, finish);
 }
 
 // ---------------------------------------------------------------------------------------------- public operations
@@ -786,8 +822,13 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
     }
     if (!missing.empty()) {
         st_.faults += missing.size();
-        CUresult r = make_room(need);
-        if (r == CUDA_SUCCESS) r = page_in(missing);
+        // order matters for overlap: packs of the victims first (short), then the H2D copies of the incoming rows
+        // into staging, THEN the host-side wait for the packs and the VMM remaps, and finally the unpacks
+        CUresult r = make_room(need, false);
+        if (r == CUDA_SUCCESS) r = page_in_stage(missing);
+        if (r == CUDA_SUCCESS) r = page_out_finish();
+        if (r == CUDA_SUCCESS) r = page_in_finish(missing);
+        if (r != CUDA_SUCCESS) { page_out_finish(); in_jobs_.clear(); }
         if (r != CUDA_SUCCESS) {
             for (int i = 0; i < n; i++) {
                 Side &s = side_[rows[i]];

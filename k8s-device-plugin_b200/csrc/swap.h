@@ -110,9 +110,15 @@ class SwapEngine {
     int new_row();
     void mark_dirty(int row);
     CUresult sync_table(CUstream s);
-    CUresult make_room(uint64_t need_mapped);
-    CUresult page_out(const std::vector<uint32_t> &victims);
-    CUresult page_in(const std::vector<int> &rows);
+    CUresult make_room(uint64_t need_mapped, bool finish = true);
+    CUresult page_out(const std::vector<uint32_t> &victims, bool finish = true);
+    CUresult page_out_finish();
+    struct InRun { unsigned char *src; uint64_t pos, len; };
+    struct InJob { Slot *slot = nullptr; std::vector<PackSegment> segs; std::vector<InRun> runs; std::vector<int> done_rows; uint64_t bytes = 0; };
+    CUresult page_in_plan(const std::vector<int> &rows);
+    CUresult page_in_stage(const std::vector<int> &rows);
+    CUresult page_in_finish(const std::vector<int> &rows);
+    CUresult in_issue_copies(InJob &j);
     CUresult map_row(int row);
     void unmap_row(int row);
     CUresult get_phys(size_t mapped, CUmemGenericAllocationHandle *h);
@@ -164,6 +170,8 @@ class SwapEngine {
     std::vector<CUevent> ready_free_;
     std::unique_ptr<VictimScanner> scanner_;
     std::vector<PendingHost> pending_host_;
+    std::vector<uint32_t> out_pending_;             // victims packed but not yet unmapped (page_out_finish)
+    std::vector<InJob> in_jobs_;                    // page-in plan of the admission in progress
     // victims selected by the last scan beyond what was needed then, in LRU order. They stay the exact LRU prefix for
     // as long as they are untouched (anything touched or created since carries a larger tick), so consuming them
     // is equivalent to re-scanning; an entry whose row changed is simply skipped.

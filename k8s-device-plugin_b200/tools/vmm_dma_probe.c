@@ -1,0 +1,67 @@
+/*
+ * vmm_dma_probe.c — do VMM remaps (cuMemUnmap / cuMemMap / cuMemSetAccess) of an unrelated range slow down, or get
+ * slowed down by, pinned DMA running in both directions? The swap engine issues exactly that mix once per paged
+ * buffer; this isolates the interaction. Output: one JSON object.
+ */
+#include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#define CK(x) do { CUresult _r = (x); if (_r != CUDA_SUCCESS) { fprintf(stderr, "probe: %s -> %d (line %d)\n", #x, (int)_r, __LINE__); exit(3); } } while (0)
+static double now_us(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec / 1e3; }
+
+static double run(int with_vmm, int with_dma, size_t chunk, int nchunks, double *vmm_us_avg, int *vmm_ops, size_t remap_bytes) {
+    static void *h_in, *h_out; static CUdeviceptr d_in, d_out, va; static CUstream s_in, s_out; static CUevent a, b, c, d;
+    static CUmemGenericAllocationHandle hnd[2]; static int init;
+    CUmemAllocationProp prop; memset(&prop, 0, sizeof prop);
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED; prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE; prop.location.id = 0;
+    CUmemAccessDesc acc; memset(&acc, 0, sizeof acc); acc.location = prop.location; acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (!init) {
+        CK(cuMemHostAlloc(&h_in, chunk, CU_MEMHOSTALLOC_PORTABLE)); CK(cuMemHostAlloc(&h_out, chunk, CU_MEMHOSTALLOC_PORTABLE));
+        memset(h_in, 1, chunk); memset(h_out, 2, chunk);
+        CK(cuMemAlloc(&d_in, chunk)); CK(cuMemAlloc(&d_out, chunk));
+        CK(cuStreamCreate(&s_in, CU_STREAM_NON_BLOCKING)); CK(cuStreamCreate(&s_out, CU_STREAM_NON_BLOCKING));
+        CK(cuEventCreate(&a, 0)); CK(cuEventCreate(&b, 0)); CK(cuEventCreate(&c, 0)); CK(cuEventCreate(&d, 0));
+        CK(cuMemAddressReserve(&va, remap_bytes, 0, 0, 0));
+        CK(cuMemCreate(&hnd[0], remap_bytes, &prop, 0)); CK(cuMemCreate(&hnd[1], remap_bytes, &prop, 0));
+        CK(cuMemMap(va, remap_bytes, 0, hnd[0], 0)); CK(cuMemSetAccess(va, remap_bytes, &acc, 1));
+        init = 1;
+    }
+    CK(cuCtxSynchronize());
+    double t0 = now_us();
+    if (with_dma) {
+        CK(cuEventRecord(a, s_in)); CK(cuEventRecord(c, s_out));
+        for (int i = 0; i < nchunks; i++) { CK(cuMemcpyHtoDAsync(d_in, h_in, chunk, s_in)); CK(cuMemcpyDtoHAsync(h_out, d_out, chunk, s_out)); }
+        CK(cuEventRecord(b, s_in)); CK(cuEventRecord(d, s_out));
+    }
+    int ops = 0; double vmm_total = 0; int cur = 0;
+    if (with_vmm) {
+        double limit = with_dma ? 1e18 : 400e3;   /* without DMA: spin for 0.4 s */
+        while (1) {
+            if (with_dma && cuEventQuery(b) == CUDA_SUCCESS && cuEventQuery(d) == CUDA_SUCCESS) break;
+            if (!with_dma && now_us() - t0 > limit) break;
+            double v0 = now_us();
+            CK(cuMemUnmap(va, remap_bytes)); cur ^= 1;
+            CK(cuMemMap(va, remap_bytes, 0, hnd[cur], 0)); CK(cuMemSetAccess(va, remap_bytes, &acc, 1));
+            vmm_total += now_us() - v0; ops++;
+        }
+    }
+    CK(cuCtxSynchronize());
+    double gbs = 0;
+    if (with_dma) { float m1, m2; CK(cuEventElapsedTime(&m1, a, b)); CK(cuEventElapsedTime(&m2, c, d)); double ms = m1 > m2 ? m1 : m2; gbs = 2.0 * chunk * nchunks / ms / 1e6; }
+    *vmm_us_avg = ops ? vmm_total / ops : 0; *vmm_ops = ops;
+    return gbs;
+}
+
+int main(void) {
+    CUdevice dev; CUcontext ctx;
+    CK(cuInit(0)); CK(cuDeviceGet(&dev, 0)); CK(cuDevicePrimaryCtxRetain(&ctx, dev)); CK(cuCtxSetCurrent(ctx));
+    size_t chunk = 32u << 20; int n = 1200; double v; int ops;
+    double base = run(0, 1, chunk, n, &v, &ops, 64u << 20);
+    double v_idle; int ops_idle; run(1, 0, chunk, n, &v_idle, &ops_idle, 64u << 20);
+    double v_load; int ops_load; double loaded = run(1, 1, chunk, n, &v_load, &ops_load, 64u << 20);
+    printf("{\"dma_bidir_gbs_alone\": %.1f, \"dma_bidir_gbs_with_vmm_remaps\": %.1f, \"remap_us_idle\": %.1f, \"remap_us_under_dma\": %.1f, "
+           "\"remaps_during_dma\": %d, \"chunk_mib\": %zu, \"remap_mib\": 64}\n", base, loaded, v_idle, v_load, ops_load, chunk >> 20);
+    return 0;
+}
