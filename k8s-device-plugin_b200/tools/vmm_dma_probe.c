@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <pthread.h>
 #include <time.h>
 #define CK(x) do { CUresult _r = (x); if (_r != CUDA_SUCCESS) { fprintf(stderr, "probe: %s -> %d (line %d)\n", #x, (int)_r, __LINE__); exit(3); } } while (0)
 static double now_us(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec / 1e3; }
@@ -54,14 +55,49 @@ static double run(int with_vmm, int with_dma, size_t chunk, int nchunks, double 
     return gbs;
 }
 
+/* do VMM calls from several threads scale, or does the driver serialise them? each thread remaps its own range */
+static CUcontext g_ctx;
+struct targ { int reps; size_t bytes; double us_per_cycle; int split; };
+static void *remap_thread(void *p) {
+    struct targ *a = p;
+    CK(cuCtxSetCurrent(g_ctx));
+    CUmemAllocationProp prop; memset(&prop, 0, sizeof prop);
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED; prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE; prop.location.id = 0;
+    CUmemAccessDesc acc; memset(&acc, 0, sizeof acc); acc.location = prop.location; acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    CUdeviceptr va; CUmemGenericAllocationHandle h;
+    CK(cuMemAddressReserve(&va, a->bytes, 0, 0, 0)); CK(cuMemCreate(&h, a->bytes, &prop, 0));
+    CK(cuMemMap(va, a->bytes, 0, h, 0)); CK(cuMemSetAccess(va, a->bytes, &acc, 1));
+    double t0 = now_us();
+    for (int i = 0; i < a->reps; i++) {
+        if (a->split == 1) { CK(cuMemUnmap(va, a->bytes)); CK(cuMemMap(va, a->bytes, 0, h, 0)); }            /* unmap+map only */
+        else if (a->split == 2) { CK(cuMemSetAccess(va, a->bytes, &acc, 1)); }                                /* setaccess only */
+        else { CK(cuMemUnmap(va, a->bytes)); CK(cuMemMap(va, a->bytes, 0, h, 0)); CK(cuMemSetAccess(va, a->bytes, &acc, 1)); }
+    }
+    a->us_per_cycle = (now_us() - t0) / a->reps;
+    CK(cuMemUnmap(va, a->bytes)); CK(cuMemRelease(h)); CK(cuMemAddressFree(va, a->bytes));
+    return NULL;
+}
+static double threads_cycle_us(int nthreads, size_t bytes, int split) {
+    pthread_t th[8]; struct targ a[8]; double worst = 0;
+    for (int i = 0; i < nthreads; i++) { a[i].reps = 200; a[i].bytes = bytes; a[i].split = split; pthread_create(&th[i], NULL, remap_thread, &a[i]); }
+    for (int i = 0; i < nthreads; i++) { pthread_join(th[i], NULL); if (a[i].us_per_cycle > worst) worst = a[i].us_per_cycle; }
+    return worst;
+}
+
 int main(void) {
     CUdevice dev; CUcontext ctx;
     CK(cuInit(0)); CK(cuDeviceGet(&dev, 0)); CK(cuDevicePrimaryCtxRetain(&ctx, dev)); CK(cuCtxSetCurrent(ctx));
+    g_ctx = ctx;
+    double t1 = threads_cycle_us(1, 64u << 20, 0), t2 = threads_cycle_us(2, 64u << 20, 0), t4 = threads_cycle_us(4, 64u << 20, 0);
+    double um = threads_cycle_us(1, 64u << 20, 1), sa = threads_cycle_us(1, 64u << 20, 2);
+    double small = threads_cycle_us(1, 2u << 20, 0), big = threads_cycle_us(1, 1024u << 20, 0);
     size_t chunk = 32u << 20; int n = 1200; double v; int ops;
     double base = run(0, 1, chunk, n, &v, &ops, 64u << 20);
     double v_idle; int ops_idle; run(1, 0, chunk, n, &v_idle, &ops_idle, 64u << 20);
     double v_load; int ops_load; double loaded = run(1, 1, chunk, n, &v_load, &ops_load, 64u << 20);
     printf("{\"dma_bidir_gbs_alone\": %.1f, \"dma_bidir_gbs_with_vmm_remaps\": %.1f, \"remap_us_idle\": %.1f, \"remap_us_under_dma\": %.1f, "
-           "\"remaps_during_dma\": %d, \"chunk_mib\": %zu, \"remap_mib\": 64}\n", base, loaded, v_idle, v_load, ops_load, chunk >> 20);
+           "\"remaps_during_dma\": %d, \"chunk_mib\": %zu, \"remap_mib\": 64, "
+           "\"remap_cycle_us_1_2_4_threads\": [%.1f, %.1f, %.1f], \"unmap_map_us\": %.1f, \"setaccess_us\": %.1f, \"cycle_us_2MiB\": %.1f, \"cycle_us_1GiB\": %.1f}\n",
+           base, loaded, v_idle, v_load, ops_load, chunk >> 20, t1, t2, t4, um, sa, small, big);
     return 0;
 }
