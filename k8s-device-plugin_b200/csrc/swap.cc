@@ -141,8 +141,12 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
     }
     uint64_t want = round_up(cfg_.arena_bytes, gran_);
     CUresult r = CUDA_ERROR_UNKNOWN;
+    // base alignment: buffers sit at multiples of their own (power-of-two-ish) sizes from the arena base, so a base
+    // aligned to the upper page-directory span keeps a buffer from straddling page-table pages
+    uint64_t align = env_u64("VGPU_SWAP_ARENA_ALIGN_GB", 4) << 30;
     while (want >= (8ull << 30)) {
-        r = d.cuMemAddressReserve(&arena_, want, 0, 0, 0);
+        r = d.cuMemAddressReserve(&arena_, want, align, 0, 0);
+        if (r != CUDA_SUCCESS && align) r = d.cuMemAddressReserve(&arena_, want, 0, 0, 0);
         if (r == CUDA_SUCCESS) break;
         want >>= 1;
     }

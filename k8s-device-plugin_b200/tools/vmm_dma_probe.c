@@ -84,6 +84,43 @@ static double threads_cycle_us(int nthreads, size_t bytes, int split) {
     return worst;
 }
 
+/* what does a remap cycle cost as a function of where the range sits in the page-table hierarchy, and of whether the
+ * same or another physical handle comes back? */
+static void offset_study(void) {
+    CUmemAllocationProp prop; memset(&prop, 0, sizeof prop);
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED; prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE; prop.location.id = 0;
+    CUmemAccessDesc acc; memset(&acc, 0, sizeof acc); acc.location = prop.location; acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    size_t span = 4ull << 30, sz = 64u << 20; CUdeviceptr base; CUmemGenericAllocationHandle h[2];
+    CK(cuMemAddressReserve(&base, span, span, 0, 0));
+    CK(cuMemCreate(&h[0], sz, &prop, 0)); CK(cuMemCreate(&h[1], sz, &prop, 0));
+    size_t offs[] = {0, 2u << 20, 32u << 20, 480u << 20, (1024u - 32u) << 20, (2048u - 2u) << 20};
+    printf("\"offset_study_us\": {\"base_mod_4GiB\": %llu", (unsigned long long)(base & (span - 1)));
+    for (int alt = 0; alt < 2; alt++)
+        for (unsigned k = 0; k < sizeof offs / sizeof offs[0]; k++) {
+            CUdeviceptr va = base + offs[k]; int cur = 0;
+            CK(cuMemMap(va, sz, 0, h[0], 0)); CK(cuMemSetAccess(va, sz, &acc, 1));
+            for (int i = 0; i < 20; i++) { CK(cuMemUnmap(va, sz)); if (alt) cur ^= 1; CK(cuMemMap(va, sz, 0, h[cur], 0)); CK(cuMemSetAccess(va, sz, &acc, 1)); }
+            double t0 = now_us(); int reps = 100;
+            for (int i = 0; i < reps; i++) { CK(cuMemUnmap(va, sz)); if (alt) cur ^= 1; CK(cuMemMap(va, sz, 0, h[cur], 0)); CK(cuMemSetAccess(va, sz, &acc, 1)); }
+            printf(", \"%s@%zuMiB\": %.1f", alt ? "alt" : "same", offs[k] >> 20, (now_us() - t0) / reps);
+            CK(cuMemUnmap(va, sz));
+        }
+    /* two DIFFERENT ranges alternately (the engine's pattern: unmap victim range, map+setaccess incoming range) */
+    {
+        CUdeviceptr va1 = base + (256u << 20), va2 = base + (1280u << 20);
+        CK(cuMemMap(va1, sz, 0, h[0], 0)); CK(cuMemSetAccess(va1, sz, &acc, 1));
+        double t0 = now_us(); int reps = 100;
+        for (int i = 0; i < reps; i++) {
+            CK(cuMemUnmap(va1, sz)); CK(cuMemMap(va2, sz, 0, h[0], 0)); CK(cuMemSetAccess(va2, sz, &acc, 1));
+            CK(cuMemUnmap(va2, sz)); CK(cuMemMap(va1, sz, 0, h[0], 0)); CK(cuMemSetAccess(va1, sz, &acc, 1));
+        }
+        printf(", \"pingpong_two_ranges_per_remap\": %.1f", (now_us() - t0) / reps / 2);
+        CK(cuMemUnmap(va1, sz));
+    }
+    printf("}, ");
+    CK(cuMemRelease(h[0])); CK(cuMemRelease(h[1])); CK(cuMemAddressFree(base, span));
+}
+
 int main(void) {
     CUdevice dev; CUcontext ctx;
     CK(cuInit(0)); CK(cuDeviceGet(&dev, 0)); CK(cuDevicePrimaryCtxRetain(&ctx, dev)); CK(cuCtxSetCurrent(ctx));
@@ -91,11 +128,13 @@ int main(void) {
     double t1 = threads_cycle_us(1, 64u << 20, 0), t2 = threads_cycle_us(2, 64u << 20, 0), t4 = threads_cycle_us(4, 64u << 20, 0);
     double um = threads_cycle_us(1, 64u << 20, 1), sa = threads_cycle_us(1, 64u << 20, 2);
     double small = threads_cycle_us(1, 2u << 20, 0), big = threads_cycle_us(1, 1024u << 20, 0);
+    printf("{");
+    offset_study();
     size_t chunk = 32u << 20; int n = 1200; double v; int ops;
     double base = run(0, 1, chunk, n, &v, &ops, 64u << 20);
     double v_idle; int ops_idle; run(1, 0, chunk, n, &v_idle, &ops_idle, 64u << 20);
     double v_load; int ops_load; double loaded = run(1, 1, chunk, n, &v_load, &ops_load, 64u << 20);
-    printf("{\"dma_bidir_gbs_alone\": %.1f, \"dma_bidir_gbs_with_vmm_remaps\": %.1f, \"remap_us_idle\": %.1f, \"remap_us_under_dma\": %.1f, "
+    printf("\"dma_bidir_gbs_alone\": %.1f, \"dma_bidir_gbs_with_vmm_remaps\": %.1f, \"remap_us_idle\": %.1f, \"remap_us_under_dma\": %.1f, "
            "\"remaps_during_dma\": %d, \"chunk_mib\": %zu, \"remap_mib\": 64, "
            "\"remap_cycle_us_1_2_4_threads\": [%.1f, %.1f, %.1f], \"unmap_map_us\": %.1f, \"setaccess_us\": %.1f, \"cycle_us_2MiB\": %.1f, \"cycle_us_1GiB\": %.1f}\n",
            base, loaded, v_idle, v_load, ops_load, chunk >> 20, t1, t2, t4, um, sa, small, big);
