@@ -157,7 +157,8 @@ void Region::lock() {
         int32_t owner = static_cast<int32_t>(r_->owner_pid);
         bool takeover = false;
         if (owner == getpid() || (owner != 0 && !pid_alive(owner))) takeover = true;
-        else if (owner == 0 && ++trials >= 30) takeover = true;
+        else if (owner == 0 && ++trials >= 3) takeover = true;   // reference: 30 trials (5 min); a holder that never
+                                                                 // recorded itself died inside a microsecond window
         else ++trials;
         if (takeover) {
             if (lockf(fd_, F_LOCK, VGPU_REGION_SIZE) == 0) {

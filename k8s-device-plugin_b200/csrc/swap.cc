@@ -44,6 +44,8 @@ SwapConfig SwapConfig::from_env(uint64_t resident_cap, uint64_t virtual_cap) {
     c.arena_bytes = env_u64("VGPU_SWAP_ARENA_GB", 1024) << 30;
     c.profile = env_u64("VGPU_SWAP_PROFILE", 0) != 0;
     c.scan_lookahead = (uint32_t)env_u64("VGPU_SWAP_SCAN_LOOKAHEAD", 8);
+    c.async_unmap = env_u64("VGPU_SWAP_ASYNC_UNMAP", 1) != 0;
+    c.spare_bytes = env_u64("VGPU_SWAP_SPARE_MB", 128) << 20;
     if (c.ring_slots < 2) c.ring_slots = 2;
     if (c.chunk_bytes < (1u << 20)) c.chunk_bytes = 1u << 20;
     return c;
@@ -76,6 +78,12 @@ static void prefer_node(int node) {
     syscall(SYS_set_mempolicy, 1, &mask, sizeof(mask) * 8);
 }
 static void default_policy() { syscall(SYS_set_mempolicy, 0, nullptr, 0); }
+// which node did the kernel actually give us? (get_mempolicy MPOL_F_NODE|MPOL_F_ADDR = 3); -1 when unknown
+static int node_of(void *addr) {
+    int node = -1;
+    if (syscall(SYS_get_mempolicy, &node, nullptr, 0, addr, 3) != 0) return -1;
+    return node;
+}
 // The driver pins pages where the CALLING CPU sits (measured: with only a memory policy the pool still landed on
 // the far socket, 35-50 GB/s instead of 88), so the thread is moved onto the GPU's node for the duration of the slab
 // allocation and then put back. Fails harmlessly inside a cpuset that excludes those CPUs.
@@ -181,6 +189,8 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
     if (scanner_->init(k_, tbl_cap_) != CUDA_SUCCESS) return false;
     use_ring_.resize(1024);
     for (auto &e : use_ring_) if (d.cuEventCreate(&e, CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) return false;
+    d.cuCtxGetCurrent(&ctx_);
+    if (cfg_.async_unmap) reaper_ = std::thread([this] { reaper_main(); });
     LOG_INFO("swap engine dev %d (numa %d): resident cap %lu MiB, virtual cap %lu MiB, chunk %zu MiB x %d, arena %lu GiB, gran %zu",
              dev_, numa_node_, (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(cfg_.virtual_cap >> 20), cfg_.chunk_bytes >> 20,
              cfg_.ring_slots, (unsigned long)(cfg_.arena_bytes >> 30), gran_);
@@ -191,6 +201,11 @@ SwapEngine::~SwapEngine() {
     const DriverTable &d = drv();
     if (!d.loaded) return;
     drain();
+    if (reaper_.joinable()) {
+        { std::lock_guard<std::mutex> g(rq_mu_); reaper_stop_ = true; }
+        rq_cv_.notify_all();
+        reaper_.join();
+    }
     for (size_t i = 0; i < rows_.size(); i++) {
         if (rows_[i].state == VGPU_ST_FREE) continue;
         if (rows_[i].state & VGPU_ST_RESIDENT) { d.cuMemUnmap(rows_[i].base, side_[i].mapped); if (side_[i].has_handle) d.cuMemRelease(side_[i].handle); }
@@ -265,6 +280,12 @@ bool SwapEngine::host_alloc(size_t bytes, uint64_t *off) {
         if (numa_node_ >= 0) default_policy();
     }
     if (r != CUDA_SUCCESS) { LOG_ERROR("pinned slab of %zu MiB failed: %d %s", sb >> 20, (int)r, cu_err(r)); return false; }
+    st_.host_slabs++;
+    if (numa_node_ >= 0) {
+        int got = node_of(s.host + sb / 2);
+        if (got == numa_node_) st_.host_slabs_local++;
+        else LOG_WARN("pinned slab landed on NUMA node %d, GPU is on node %d: page traffic will cross the socket link", got, numa_node_);
+    }
     s.bytes = sb;
     if (sb > bytes) s.free[bytes] = sb - bytes;
     slabs_.push_back(std::move(s));
@@ -337,7 +358,8 @@ void SwapEngine::collect_rows(const void *param, size_t bytes, std::vector<int> 
 // ---------------------------------------------------------------------------------------------- physical memory
 void SwapEngine::trim_phys_pool(uint64_t need) {
     const DriverTable &d = drv();
-    while (!phys_pool_.empty() && resident_mapped_ + phys_pool_bytes_ + need > cfg_.resident_cap) {
+    const uint64_t allowed = cfg_.resident_cap + (cfg_.async_unmap ? cfg_.spare_bytes : 0);
+    while (!phys_pool_.empty() && resident_mapped_ + evicting_mapped_ + phys_pool_bytes_ + need > allowed) {
         auto it = std::prev(phys_pool_.end());
         d.cuMemRelease(it->second);
         phys_pool_bytes_ -= it->first;
@@ -346,15 +368,25 @@ void SwapEngine::trim_phys_pool(uint64_t need) {
 }
 CUresult SwapEngine::get_phys(size_t mapped, CUmemGenericAllocationHandle *h) {
     const DriverTable &d = drv();
-    auto it = phys_pool_.find(mapped);
-    if (it != phys_pool_.end()) {
-        *h = it->second;
-        phys_pool_bytes_ -= mapped;
-        phys_pool_.erase(it);
-        st_.phys_reuses++;
-        return CUDA_SUCCESS;
+    for (;;) {
+        auto it = phys_pool_.find(mapped);
+        if (it != phys_pool_.end()) {
+            *h = it->second;
+            phys_pool_bytes_ -= mapped;
+            phys_pool_.erase(it);
+            st_.phys_reuses++;
+            return CUDA_SUCCESS;
+        }
+        // physical memory held = resident + victims awaiting their unmap + pooled handles; it may exceed the quota
+        // by at most spare_bytes (a documented overhead like the staging rings) so that mapping the incoming row
+        // does not have to wait for the reaper
+        uint64_t held = resident_mapped_ + evicting_mapped_ + phys_pool_bytes_;
+        uint64_t allowed = cfg_.resident_cap + (cfg_.async_unmap ? cfg_.spare_bytes : 0);
+        if (held + mapped <= allowed) break;
+        if (!phys_pool_.empty()) { trim_phys_pool(mapped); held = resident_mapped_ + evicting_mapped_ + phys_pool_bytes_; if (held + mapped <= allowed) break; }
+        if (evicting_mapped_ == 0) break;            // nothing more will come back: create and let the driver decide
+        reap_cv_.wait(mu_);                          // a reaper batch will return handles
     }
-    trim_phys_pool(mapped);
     CUmemAllocationProp prop = {};
     prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
     prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
@@ -371,11 +403,12 @@ CUresult SwapEngine::get_phys(size_t mapped, CUmemGenericAllocationHandle *h) {
 }
 CUresult SwapEngine::map_row(int row) {
     const DriverTable &d = drv();
+    wait_not_evicting(row);                      // its own previous mapping may still be queued at the reaper
+    CUmemGenericAllocationHandle h;
+    CUresult r = get_phys(side_[row].mapped, &h);   // may wait for the reaper with mu_ released: take references after
+    if (r != CUDA_SUCCESS) return r;
     ScopedNs t(&st_.host_vmm_ns);
     Side &s = side_[row];
-    CUmemGenericAllocationHandle h;
-    CUresult r = get_phys(s.mapped, &h);
-    if (r != CUDA_SUCCESS) return r;
     r = d.cuMemMap(rows_[row].base, s.mapped, 0, h, 0);
     if (r != CUDA_SUCCESS) { d.cuMemRelease(h); LOG_ERROR("cuMemMap failed: %d %s", (int)r, cu_err(r)); return r; }
     CUmemAccessDesc acc = {};
@@ -546,12 +579,69 @@ CUresult SwapEngine::page_out(const std::vector<uint32_t> &victims, bool finish)
     return finish ? page_out_finish() : CUDA_SUCCESS;
 }
 
+void SwapEngine::reaper_main() {
+    const DriverTable &d = drv();
+    d.cuCtxSetCurrent(ctx_);
+    for (;;) {
+        ReapJob job;
+        {
+            std::unique_lock<std::mutex> lk(rq_mu_);
+            rq_cv_.wait(lk, [&] { return reaper_stop_ || !rq_.empty(); });
+            if (rq_.empty()) return;
+            job = std::move(rq_.front());
+            rq_.pop_front();
+            reaper_busy_ = true;
+        }
+        d.cuEventSynchronize(job.packed);                       // the last pack of the batch has read the victims
+        for (size_t i = 0; i < job.rows.size(); i++) d.cuMemUnmap(job.bases[i], job.mapped[i]);   // no engine lock held
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            for (size_t i = 0; i < job.rows.size(); i++) {
+                Side &s = side_[job.rows[i]];
+                phys_pool_.emplace(s.mapped, s.handle);
+                phys_pool_bytes_ += s.mapped;
+                s.has_handle = false;
+                s.evicting = false;
+                evicting_mapped_ -= s.mapped;
+            }
+            ready_free_.push_back(job.packed);
+        }
+        { std::lock_guard<std::mutex> lk(rq_mu_); reaper_busy_ = false; }
+        reap_cv_.notify_all();
+    }
+}
+
+void SwapEngine::wait_not_evicting(int row) {
+    while (side_[row].evicting) reap_cv_.wait(mu_);            // mu_ is held by the caller; released while waiting
+}
+
 CUresult SwapEngine::page_out_finish() {
     const DriverTable &d = drv();
     if (out_pending_.empty()) return CUDA_SUCCESS;
     CUevent packed = get_event();
     if (!packed) return CUDA_ERROR_OUT_OF_MEMORY;
     CU_TRY(d.cuEventRecord(packed, s_pack_));
+    if (cfg_.async_unmap) {
+        ReapJob job;
+        job.packed = packed;
+        for (uint32_t v : out_pending_) {
+            Side &sd = side_[v];
+            job.rows.push_back(v); job.bases.push_back(rows_[v].base); job.mapped.push_back(sd.mapped);
+            sd.evicting = true;
+            sd.has_host = true;
+            resident_mapped_ -= sd.mapped;
+            evicting_mapped_ += sd.mapped;
+            rows_[v].state = VGPU_ST_PAGED_OUT;
+            rows_[v].host_slot = (uint32_t)(sd.host_off >> 12);
+            if (sd.ready) { ready_free_.push_back(sd.ready); sd.ready = nullptr; }
+            mark_dirty((int)v);
+            st_.evictions++;
+        }
+        out_pending_.clear();
+        { std::lock_guard<std::mutex> lk(rq_mu_); rq_.push_back(std::move(job)); }
+        rq_cv_.notify_one();
+        return CUDA_SUCCESS;
+    }
     { ScopedNs t(&st_.host_packsync_ns); CU_TRY(d.cuEventSynchronize(packed)); }
     ready_free_.push_back(packed);
     for (uint32_t v : out_pending_) {
@@ -793,6 +883,7 @@ CUresult SwapEngine::free(CUdeviceptr dptr) {
     std::lock_guard<std::mutex> g(mu_);
     int row = owner_[(dptr - arena_) / gran_];
     if (row < 0 || rows_[row].base != dptr) return CUDA_ERROR_INVALID_VALUE;
+    wait_not_evicting(row);
     Side &s = side_[row];
     if (CUevent e = use_event(s.use_seq)) d.cuEventSynchronize(e);
     if (s.ready) { d.cuEventSynchronize(s.ready); ready_free_.push_back(s.ready); s.ready = nullptr; }
@@ -873,6 +964,7 @@ void SwapEngine::note_use(const int *rows, int n, CUstream stream) {
 CUresult SwapEngine::drain() {
     const DriverTable &d = drv();
     std::lock_guard<std::mutex> g(mu_);
+    while (evicting_mapped_ != 0) reap_cv_.wait(mu_);
     CUresult r = CUDA_SUCCESS, t;
     for (CUstream s : {s_scan_, s_pack_, s_unpack_, s_out_, s_in_})
         if (s && (t = d.cuStreamSynchronize(s)) != CUDA_SUCCESS) r = t;

@@ -19,10 +19,12 @@
 #include <cuda.h>
 
 #include <cstdint>
+#include <condition_variable>
 #include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "kernels.h"
@@ -40,6 +42,8 @@ struct SwapConfig {
     uint64_t arena_bytes = 1ull << 40;    // virtual address arena
     bool profile = false;                 // bracket pack/unpack launches with events (bench roofline)
     uint32_t scan_lookahead = 8;          // a scan selects this many times the bytes needed; the surplus is consumed by later evictions
+    bool async_unmap = true;              // victims are unmapped by a reaper thread, off the admitting thread's critical path
+    uint64_t spare_bytes = 128u << 20;    // physical memory the engine may hold beyond the quota while victims await their unmap
     static SwapConfig from_env(uint64_t resident_cap, uint64_t virtual_cap);
 };
 
@@ -49,6 +53,7 @@ struct SwapStats {
     uint64_t pack_launches = 0, unpack_launches = 0, scan_launches = 0, scans = 0, scan_cache_hits = 0;
     uint64_t resident_bytes = 0, live_bytes = 0, host_bytes = 0, entries = 0;
     uint64_t phys_creates = 0, phys_reuses = 0;
+    uint64_t host_slabs = 0, host_slabs_local = 0;   // pinned slabs allocated / of those on the GPU's NUMA node
     double pack_ms = 0, unpack_ms = 0;     // CUDA-event brackets around each launch, only when profiling (include the
                                            // host's event->launch gap when the stream is idle)
     double pack_span_ms = 0, unpack_span_ms = 0;   // exact execution spans from in-kernel %globaltimer stamps (profiling)
@@ -98,6 +103,7 @@ class SwapEngine {
         uint64_t use_seq = 0;    // sequence number of the last-use event
         int pins = 0;
         uint64_t va_off = 0;
+        bool evicting = false;   // packed and logically paged out, but its unmap is still queued at the reaper
         int out_slot = -1;       // staging slot of the last page-out chunk of this row ...
         uint64_t out_seq = 0;    // ... and that slot's use counter at the time (stale => the D2H is known complete)
     };
@@ -171,6 +177,19 @@ class SwapEngine {
     std::unique_ptr<VictimScanner> scanner_;
     std::vector<PendingHost> pending_host_;
     std::vector<uint32_t> out_pending_;             // victims packed but not yet unmapped (page_out_finish)
+    // reaper: waits for a batch's last pack, unmaps the victims (VMM calls cost 0.1-1 ms each under load on B200) and
+    // returns their physical handles to the pool while the admitting thread is already mapping the incoming rows
+    struct ReapJob { std::vector<uint32_t> rows; std::vector<CUdeviceptr> bases; std::vector<size_t> mapped; CUevent packed; };
+    std::thread reaper_;
+    std::mutex rq_mu_;
+    std::condition_variable rq_cv_;
+    std::condition_variable_any reap_cv_;          // waited on with mu_ held
+    std::deque<ReapJob> rq_;
+    bool reaper_stop_ = false, reaper_busy_ = false;
+    CUcontext ctx_ = nullptr;
+    uint64_t evicting_mapped_ = 0;
+    void reaper_main();
+    void wait_not_evicting(int row);
     std::vector<InJob> in_jobs_;                    // page-in plan of the admission in progress
     // victims selected by the last scan beyond what was needed then, in LRU order. They stay the exact LRU prefix for
     // as long as they are untouched (anything touched or created since carries a larger tick), so consuming them

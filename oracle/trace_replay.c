@@ -12,7 +12,7 @@
  *
  * Trace grammar, one op per line (ids index a pointer table):
  *   A id size | M id size (managed) | P id width height (pitch, elem 4) | F id | X hexaddr (free raw)
- *   I (cuMemGetInfo_v2) | T (cuDeviceTotalMem_v2) | L gx gy gz (cuLaunchKernel of an empty kernel)
+ *   I (cuMemGetInfo_v2) | T (cuDeviceTotalMem_v2) | L gx gy gz (cuLaunchKernel of an empty kernel) | S ms (sleep)
  * Output line: "<op#> <opcode> rc=<int> ctx=<u64> mod=<u64> buf=<u64> off=<u64> tot=<u64> [free=.. total=..]"
  * where the five counters are SUMMED over every process slot of device 0 (== own slot for one process).
  */
@@ -129,6 +129,7 @@ int main(int argc, char **argv) {
         case 'I': r = cuMemGetInfo_v2(&fr, &tot); has_info = 1; break;
         case 'T': r = cuDeviceTotalMem_v2(&tot, dev); fr = 0; has_info = 1; break;
         case 'L': r = cuLaunchKernel(fn, (unsigned)a, (unsigned)b, (unsigned)d, 1, 1, 1, 0, NULL, NULL, NULL); break;
+        case 'S': usleep((useconds_t)a * 1000); r = 0; break;   /* sleep a ms (multi-process tests) */
         default: continue;
         }
         counters(0, c);

@@ -105,7 +105,7 @@ def test_multi_process_container_shares_the_quota(tmp_path):
     env = dict(os.environ, LD_LIBRARY_PATH=FAKE, LD_PRELOAD=HOOK_SO, LIBCUDA_LOG_LEVEL="0",
                CUDA_DEVICE_MEMORY_LIMIT_0="256m", CUDA_DEVICE_MEMORY_SHARED_CACHE=cache, FAKE_GPU_CTX_MIB="16")
     holder = tmp_path / "hold.txt"
-    holder.write_text("A 0 %d\n" % (150 << 20) + "I\n" * 400000)   # keeps ~150 MiB for a while
+    holder.write_text("A 0 %d\nS 600000\n" % (150 << 20))   # keeps ~150 MiB, then sleeps (killed below, no exit handler)
     p1 = subprocess.Popen([os.path.join(OREF, "trace_replay"), str(holder)], env=env, stdout=subprocess.DEVNULL)
     try:
         import time
