@@ -44,7 +44,7 @@ SwapConfig SwapConfig::from_env(uint64_t resident_cap, uint64_t virtual_cap) {
     c.arena_bytes = env_u64("VGPU_SWAP_ARENA_GB", 1024) << 30;
     c.profile = env_u64("VGPU_SWAP_PROFILE", 0) != 0;
     c.scan_lookahead = (uint32_t)env_u64("VGPU_SWAP_SCAN_LOOKAHEAD", 8);
-    c.async_unmap = env_u64("VGPU_SWAP_ASYNC_UNMAP", 1) != 0;
+    c.async_unmap = env_u64("VGPU_SWAP_ASYNC_UNMAP", 0) != 0;
     c.spare_bytes = env_u64("VGPU_SWAP_SPARE_MB", 128) << 20;
     if (c.ring_slots < 2) c.ring_slots = 2;
     if (c.chunk_bytes < (1u << 20)) c.chunk_bytes = 1u << 20;

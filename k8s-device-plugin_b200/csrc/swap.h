@@ -42,7 +42,9 @@ struct SwapConfig {
     uint64_t arena_bytes = 1ull << 40;    // virtual address arena
     bool profile = false;                 // bracket pack/unpack launches with events (bench roofline)
     uint32_t scan_lookahead = 8;          // a scan selects this many times the bytes needed; the surplus is consumed by later evictions
-    bool async_unmap = true;              // victims are unmapped by a reaper thread, off the admitting thread's critical path
+    bool async_unmap = false;             // VGPU_SWAP_ASYNC_UNMAP=1: victims are unmapped by a reaper thread instead of the admitting
+                                          // thread. Measured neutral on B200/driver 580 (VMM calls from two threads serialise in the driver:
+                                          // 68 vs 70 GB/s, profiles/README.md), kept as the building block of the prefetch pipeline
     uint64_t spare_bytes = 128u << 20;    // physical memory the engine may hold beyond the quota while victims await their unmap
     static SwapConfig from_env(uint64_t resident_cap, uint64_t virtual_cap);
 };

@@ -74,6 +74,12 @@ def test_unmodified_app_under_hook_swaps_and_verifies(tmp_path):
     assert out["phys_reuses"] > 0
 
 
+def test_reaper_thread_variant_keeps_every_word(tmp_path):
+    out = _swap_bench(tmp_path, {"CUDA_OVERSUBSCRIBE": "true", "CUDA_DEVICE_MEMORY_LIMIT_0": "2048m", "VGPU_SWAP_ASYNC_UNMAP": "1"},
+                      ["--buffers", "48", "--mib", "64", "--steps", "144", "--warmup", "8", "--order", "cyclic"])
+    assert out["mismatches"] == 0 and out["page_in_bytes"] == 144 * (64 << 20)
+
+
 def test_zipf_order_hits_resident_set(tmp_path):
     out = _swap_bench(tmp_path, {"CUDA_OVERSUBSCRIBE": "true", "CUDA_DEVICE_MEMORY_LIMIT_0": "2048m"},
                       ["--buffers", "48", "--mib", "64", "--steps", "200", "--warmup", "50", "--order", "zipf"])
