@@ -106,6 +106,7 @@ void Runtime::on_exit() {
         for (int d = 0; d < VGPU_MAX_DEVICES; d++)
             if (swap_[d]) {
                 SwapStats s = swap_[d]->stats();
+                swap_[d]->dump_trace(stderr);
                 std::fprintf(stderr, "[vgpu-b200 stats] swap dev %d host ms: admit=%.1f scan=%.1f packsync=%.1f vmm=%.1f ringwait=%.1f slabs=%lu local=%lu\n", d, s.host_admit_ns / 1e6,
                              s.host_scan_ns / 1e6, s.host_packsync_ns / 1e6, s.host_vmm_ns / 1e6, s.host_ring_ns / 1e6, (unsigned long)s.host_slabs, (unsigned long)s.host_slabs_local);
                 std::fprintf(stderr, "[vgpu-b200 stats] swap dev %d: in=%lu out=%lu faults=%lu evictions=%lu scans=%lu cache_hits=%lu creates=%lu reuses=%lu\n", d,

@@ -45,6 +45,7 @@ SwapConfig SwapConfig::from_env(uint64_t resident_cap, uint64_t virtual_cap) {
     c.profile = env_u64("VGPU_SWAP_PROFILE", 0) != 0;
     c.scan_lookahead = (uint32_t)env_u64("VGPU_SWAP_SCAN_LOOKAHEAD", 8);
     c.async_unmap = env_u64("VGPU_SWAP_ASYNC_UNMAP", 0) != 0;
+    c.trace = (uint32_t)env_u64("VGPU_SWAP_TRACE", 0);
     c.spare_bytes = env_u64("VGPU_SWAP_SPARE_MB", 128) << 20;
     if (c.ring_slots < 2) c.ring_slots = 2;
     if (c.chunk_bytes < (1u << 20)) c.chunk_bytes = 1u << 20;
@@ -129,6 +130,8 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
     dev_ = dev;
     cfg_ = cfg;
     scan_lookahead_ = cfg.scan_lookahead;
+    trace_want_ = cfg.trace;
+    trace_skip_ = 300;   // let the pipeline reach steady state first
     k_ = kernels_for_current_ctx();
     if (!k_) return false;
     numa_node_ = std::getenv("VGPU_SWAP_NO_NUMA") ? -1 : gpu_numa_node(dev);
@@ -552,7 +555,9 @@ CUresult SwapEngine::page_out(const std::vector<uint32_t> &victims, bool finish)
         // slot.busy doubles as "packed" marker for the copy stream, then is re-recorded as "drained"
         CU_TRY(d.cuEventRecord(slot->busy, s_pack_));
         CU_TRY(d.cuStreamWaitEvent(s_out_, slot->busy, 0));
+        if (tr_) trace_mark(&tr_->d2h, s_out_);
         CU_TRY(d.cuMemcpyDtoHAsync_v2(host_ptr(block) + slot_host_start, slot->buf, pos, s_out_));
+        if (tr_) trace_mark(&tr_->d2h, s_out_);
         CU_TRY(d.cuEventRecord(slot->busy, s_out_));
         st_.page_out_bytes += pos;
         segs.clear();
@@ -686,10 +691,12 @@ CUresult SwapEngine::page_in_plan(const std::vector<int> &rows) {
 
 CUresult SwapEngine::in_issue_copies(InJob &j) {
     const DriverTable &d = drv();
+    if (tr_) trace_mark(&tr_->h2d, s_in_);
     for (const InRun &r : j.runs) {
         CU_TRY(d.cuMemcpyHtoDAsync_v2(j.slot->buf + r.pos, r.src, r.len, s_in_));
         st_.page_in_bytes += r.len;
     }
+    if (tr_) trace_mark(&tr_->h2d, s_in_);
     CU_TRY(d.cuEventRecord(j.slot->busy, s_in_));     // "loaded"; re-recorded as "unpacked" in finish
     return CUDA_SUCCESS;
 }
@@ -919,10 +926,24 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
         st_.faults += missing.size();
         // order matters for overlap: packs of the victims first (short), then the H2D copies of the incoming rows
         // into staging, THEN the host-side wait for the packs and the VMM remaps, and finally the unpacks
+        tr_ = nullptr;
+        if (trace_want_ && trace_.size() < trace_want_) {
+            if (trace_skip_) trace_skip_--;
+            else {
+                if (!trace_base_) { d.cuEventCreate(&trace_base_, CU_EVENT_DEFAULT); d.cuEventRecord(trace_base_, s_out_); d.cuEventSynchronize(trace_base_); trace_base_ns_ = mono_ns(); trace_.reserve(trace_want_); }
+                trace_.emplace_back();
+                tr_ = &trace_.back();
+                tr_->t_begin = mono_ns();
+            }
+        }
         CUresult r = make_room(need, false);
+        if (tr_) tr_->t_packs = mono_ns();
         if (r == CUDA_SUCCESS) r = page_in_stage(missing);
+        if (tr_) tr_->t_staged = mono_ns();
         if (r == CUDA_SUCCESS) r = page_out_finish();
+        if (tr_) tr_->t_unmapped = mono_ns();
         if (r == CUDA_SUCCESS) r = page_in_finish(missing);
+        if (tr_) { tr_->t_end = mono_ns(); tr_ = nullptr; }
         if (r != CUDA_SUCCESS) { page_out_finish(); in_jobs_.clear(); }
         if (r != CUDA_SUCCESS) {
             for (int i = 0; i < n; i++) {
@@ -984,6 +1005,38 @@ SwapStats SwapEngine::stats() {
     s.host_bytes = host_used_;
     s.entries = rows_.size() - free_rows_.size();
     return s;
+}
+
+void SwapEngine::trace_mark(std::vector<CUevent> *v, CUstream s) {
+    CUevent e = nullptr;
+    if (drv().cuEventCreate(&e, CU_EVENT_DEFAULT) != CUDA_SUCCESS) return;
+    drv().cuEventRecord(e, s);
+    v->push_back(e);
+}
+
+void SwapEngine::dump_trace(FILE *f) {
+    const DriverTable &d = drv();
+    std::lock_guard<std::mutex> g(mu_);
+    if (trace_.empty() || !trace_base_) return;
+    for (CUstream s : {s_out_, s_in_}) d.cuStreamSynchronize(s);
+    auto rel = [&](uint64_t ns) { return (double)(ns - trace_base_ns_) / 1e3; };
+    for (size_t i = 0; i < trace_.size(); i++) {
+        TraceRec &t = trace_[i];
+        std::fprintf(f, "[vgpu-b200 trace] {\"i\": %zu, \"host_us\": {\"begin\": %.0f, \"packs\": %.0f, \"staged\": %.0f, \"unmapped\": %.0f, \"end\": %.0f}",
+                     i, rel(t.t_begin), rel(t.t_packs), rel(t.t_staged), rel(t.t_unmapped), rel(t.t_end));
+        for (int dir = 0; dir < 2; dir++) {
+            std::vector<CUevent> &v = dir ? t.h2d : t.d2h;
+            std::fprintf(f, ", \"%s_us\": [", dir ? "h2d" : "d2h");
+            for (size_t k = 0; k + 1 < v.size(); k += 2) {
+                float a = 0, b = 0;
+                d.cuEventElapsedTime(&a, trace_base_, v[k]);
+                d.cuEventElapsedTime(&b, trace_base_, v[k + 1]);
+                std::fprintf(f, "%s[%.0f, %.0f]", k ? ", " : "", a * 1e3, b * 1e3);
+            }
+            std::fprintf(f, "]");
+        }
+        std::fprintf(f, "}\n");
+    }
 }
 
 std::vector<VgpuEntry> SwapEngine::snapshot_table() {

@@ -42,6 +42,7 @@ struct SwapConfig {
     uint64_t arena_bytes = 1ull << 40;    // virtual address arena
     bool profile = false;                 // bracket pack/unpack launches with events (bench roofline)
     uint32_t scan_lookahead = 8;          // a scan selects this many times the bytes needed; the surplus is consumed by later evictions
+    uint32_t trace = 0;                   // VGPU_SWAP_TRACE=n: timeline of n steady-state misses (diagnostics)
     bool async_unmap = false;             // VGPU_SWAP_ASYNC_UNMAP=1: victims are unmapped by a reaper thread instead of the admitting
                                           // thread. Measured neutral on B200/driver 580 (VMM calls from two threads serialise in the driver:
                                           // 68 vs 70 GB/s, profiles/README.md), kept as the building block of the prefetch pipeline
@@ -90,6 +91,10 @@ class SwapEngine {
     CUresult drain();                          // wait for all side-stream work (tests / shutdown)
     const SwapConfig &config() const { return cfg_; }
     uint64_t live_bytes() const { return live_bytes_; }
+
+    // diagnostics (VGPU_SWAP_TRACE=n): host timestamps and timed GPU events of the first n missing admissions after
+    // warm-up, printed as JSON lines by dump_trace() — where do the two DMA queues idle?
+    void dump_trace(FILE *f);
 
     // test hook: copy of the host mirror of the table
     std::vector<VgpuEntry> snapshot_table();
@@ -193,6 +198,13 @@ class SwapEngine {
     void reaper_main();
     void wait_not_evicting(int row);
     std::vector<InJob> in_jobs_;                    // page-in plan of the admission in progress
+    struct TraceRec { uint64_t t_begin = 0, t_packs = 0, t_staged = 0, t_unmapped = 0, t_mapped = 0, t_end = 0; std::vector<CUevent> d2h, h2d; };
+    std::vector<TraceRec> trace_;
+    uint32_t trace_want_ = 0, trace_skip_ = 0;
+    CUevent trace_base_ = nullptr;
+    uint64_t trace_base_ns_ = 0;
+    TraceRec *tr_ = nullptr;                        // record of the admission in progress (or null)
+    void trace_mark(std::vector<CUevent> *v, CUstream s);
     // victims selected by the last scan beyond what was needed then, in LRU order. They stay the exact LRU prefix for
     // as long as they are untouched (anything touched or created since carries a larger tick), so consuming them
     // is equivalent to re-scanning; an entry whose row changed is simply skipped.
