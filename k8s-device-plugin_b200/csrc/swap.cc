@@ -927,6 +927,13 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
         // order matters for overlap: packs of the victims first (short), then the H2D copies of the incoming rows
         // into staging, THEN the host-side wait for the packs and the VMM remaps, and finally the unpacks
         tr_ = nullptr;
+        if (trace_want_ && trace_.size() == trace_want_ && !trace_dumped_) {
+            // the driver is gone by the time atexit handlers run: print as soon as the window is full
+            trace_dumped_ = true;
+            mu_.unlock();
+            dump_trace(stderr);
+            mu_.lock();
+        }
         if (trace_want_ && trace_.size() < trace_want_) {
             if (trace_skip_) trace_skip_--;
             else {

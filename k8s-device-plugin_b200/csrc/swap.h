@@ -201,6 +201,7 @@ class SwapEngine {
     struct TraceRec { uint64_t t_begin = 0, t_packs = 0, t_staged = 0, t_unmapped = 0, t_mapped = 0, t_end = 0; std::vector<CUevent> d2h, h2d; };
     std::vector<TraceRec> trace_;
     uint32_t trace_want_ = 0, trace_skip_ = 0;
+    bool trace_dumped_ = false;
     CUevent trace_base_ = nullptr;
     uint64_t trace_base_ns_ = 0;
     TraceRec *tr_ = nullptr;                        // record of the admission in progress (or null)
