@@ -256,7 +256,14 @@ bool SwapEngine::host_alloc(size_t bytes, uint64_t *off) {
     const DriverTable &d = drv();
     bytes = round_up(bytes, 256);
     for (int attempt = 0; attempt < 2; attempt++) {
-        reap_pending_host(attempt == 1);   // second try: wait for parked ranges (<= ~1 ms) rather than pin a new slab (~100 ms)
+        // second try: wait for parked ranges (their H2D reads finish within ~1 ms) rather than pin a new slab (~100 ms) —
+        // but only when enough bytes are parked to make the wait worthwhile
+        if (attempt == 1) {
+            uint64_t parked = 0;
+            for (auto &p : pending_host_) parked += p.len;
+            if (parked < bytes) break;
+        }
+        reap_pending_host(attempt == 1);
         for (size_t i = 0; i < slabs_.size(); i++) {
             uint64_t o;
             if (map_alloc(slabs_[i].free, bytes, &o)) {
