@@ -247,6 +247,39 @@ def finish_app(p, wait_stdin, barrier, timeout=3600):
     return json.loads(out.strip().splitlines()[-1])
 
 
+def intercept_overhead(gpu):
+    """Second half of BASELINE.json's metric: ns per cuMemAlloc+cuMemFree(1 MiB) and per empty cuLaunchKernel, bare vs
+    under LD_PRELOAD=libvgpu.so (hard-cap mode, 8 GiB limit), best of 3 alternating runs each."""
+    import k8s_device_plugin_b200 as v
+    exe = os.path.join(LIBDIR, "intercept_bench")
+    best = {"bare": None, "hooked": None}
+    for _ in range(3):
+        for mode in ("bare", "hooked"):
+            env = dict(os.environ)
+            env.pop("LD_PRELOAD", None)
+            env["CUDA_VISIBLE_DEVICES"] = str(gpu)
+            if mode == "hooked":
+                cache = f"/tmp/vgpu_bench_{os.getpid()}_ib.cache"
+                if os.path.exists(cache):
+                    os.remove(cache)
+                env.update(v.hook_env(limit_mib=QUOTA_MIB, cache_path=cache))
+                env["LIBCUDA_LOG_LEVEL"] = "0"
+            try:
+                r = subprocess.run([exe, CUBIN, "3000", "100000"], env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=120)
+                j = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception:
+                continue
+            b = best[mode]
+            best[mode] = j if b is None else {k: min(b[k], j[k]) if isinstance(j[k], float) else j[k] for k in j}
+    if not best["bare"] or not best["hooked"]:
+        return None
+    out = {}
+    for k in ("alloc_free_1mib_ns", "launch_empty_ns"):
+        out[k] = {"bare": best["bare"][k], "hooked": best["hooked"][k],
+                  "overhead_pct": round(100.0 * (best["hooked"][k] - best["bare"][k]) / best["bare"][k], 2)}
+    return out
+
+
 def reference_arm(args):
     """The reference's swap path = CUDA UVM demand paging (cuMemAllocManaged, cuMemoryAllocate libvgpu.so@0x315da),
     executed by the NVIDIA UVM driver's fault-servicing threads on the host cores. A ballast allocation pins all but
@@ -397,6 +430,8 @@ def main():
         except Exception as e:  # reported, never silently replaced
             cpu = {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {str(e)[:200]}"}
 
+    overhead = intercept_overhead(local) if (rank == 0 and world == 1) else None
+
     if rank == 0:
         peak, how = hbm_peak()
         achieved = kern_bytes / (kern_ms / 1e3) / 1e9 if kern_ms > 0 else None
@@ -429,6 +464,7 @@ def main():
                               "h2d_peak": round(link["h2d"], 2), "d2h_peak": round(link["d2h"], 2),
                               "peak_source": "pinned 1 GiB cudaMemcpyAsync both directions at once, measured in this run"},
             "cpu_baseline": cpu,
+            "intercept_overhead": overhead,
             "mismatches": bad,
             "engine": {k: d[k] for k in ("faults", "evictions", "scans", "scan_launches", "phys_creates", "phys_reuses")},
         }
