@@ -218,7 +218,7 @@ def spawn_app(gpu, nbuf, steps, warmup, mode, wait_stdin, extra_args=(), ballast
     elif mode == "refhook":
         os.makedirs("/tmp/vgpulock", exist_ok=True)
         env["LD_PRELOAD"] = os.path.join(OREF, "dlsym_shim.so") + ":" + os.path.join(OREF, "libvgpu.so")
-        env.update({"CUDA_OVERSUBSCRIBE": "true", "CUDA_DEVICE_MEMORY_LIMIT_0": "170000m", "CUDA_DEVICE_MEMORY_SHARED_CACHE": cache,
+        env.update({"CUDA_OVERSUBSCRIBE": "true", "CUDA_DEVICE_MEMORY_LIMIT_0": "250000m", "CUDA_DEVICE_MEMORY_SHARED_CACHE": cache,
                     "LIBCUDA_LOG_LEVEL": "0"})
         args += ["--ballast-mib", str(ballast_mib)]
     else:

@@ -277,9 +277,12 @@ typedef struct { unsigned long long total, free, used; } fake_meminfo;
 typedef struct { unsigned version; unsigned long long total, reserved, free, used; } fake_meminfo_v2;
 typedef struct { char busIdLegacy[16]; unsigned domain, bus, device, pciDeviceId, pciSubSystemId; char busId[32]; } fake_pciinfo;
 
-EXPORT nvmlReturn_t nvmlInit_v2(void) { fake_init(); return NVML_SUCCESS; }
+/* driver 580's libnvidia-ml resolves symbols with dlsym() while it initialises; FAKE_NVML_DLSYM=1 mimics that, which is
+ * what deadlocks the reference hook there (its dlsym override re-enters pthread_once(preInit) from inside preInit) */
+static void nvml_init_side_effects(void) { if (getenv("FAKE_NVML_DLSYM")) (void)dlsym(RTLD_DEFAULT, "cuGetProcAddress"); }
+EXPORT nvmlReturn_t nvmlInit_v2(void) { fake_init(); nvml_init_side_effects(); return NVML_SUCCESS; }
 EXPORT nvmlReturn_t nvmlInit(void) { fake_init(); return NVML_SUCCESS; }
-EXPORT nvmlReturn_t nvmlInitWithFlags(unsigned f) { (void)f; fake_init(); return NVML_SUCCESS; }
+EXPORT nvmlReturn_t nvmlInitWithFlags(unsigned f) { (void)f; fake_init(); nvml_init_side_effects(); return NVML_SUCCESS; }
 EXPORT nvmlReturn_t nvmlShutdown(void) { return NVML_SUCCESS; }
 EXPORT const char *nvmlErrorString(nvmlReturn_t r) { (void)r; return "fake nvml"; }
 EXPORT nvmlReturn_t nvmlDeviceGetCount_v2(unsigned *c) { fake_init(); *c = (unsigned)g_ndev; return NVML_SUCCESS; }

@@ -71,3 +71,25 @@ def test_oracle_equals_reference_binary_live(tmp_path):
     t = _write(tmp_path, gen_trace(3000, seed=1234, kinds="AAAMP"))
     env = {"CUDA_DEVICE_MEMORY_LIMIT_0": "4g", "CUDA_DEVICE_MEMORY_SHARED_CACHE": str(tmp_path / "ref.cache"), "FAKE_GPU_CTX_MIB": "300"}
     assert run_replay(t, "reference", env) == run_replay(t, "oracle", env)
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
+def test_reference_deadlocks_without_the_shim_when_nvml_calls_dlsym(tmp_path):
+    """Why the reference hook cannot run on driver 580 without oracle/dlsym_shim.c: libnvidia-ml resolves cu* symbols
+    with dlsym() inside nvmlInit, the hook's dlsym override answers cu* names through pthread_once(preInit), and the
+    hook calls nvmlInit from inside preInit. Reproduced with the fake driver (FAKE_NVML_DLSYM=1)."""
+    import subprocess
+    from conftest import FAKE, REF_SO, SHIM_SO
+    t = _write(tmp_path, "A 0 4096\n")
+    base = dict(os.environ, LD_LIBRARY_PATH=FAKE, LIBCUDA_LOG_LEVEL="0", FAKE_NVML_DLSYM="1", CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "r.cache"))
+    os.makedirs("/tmp/vgpulock", exist_ok=True)
+    # a _dl_sym-only shim (what SURVEY.md §0.5 proposed): still deadlocks
+    mini = tmp_path / "mini.c"
+    mini.write_text('#define _GNU_SOURCE\n#include <dlfcn.h>\nvoid *_dl_sym(void *h, const char *n, void *w) { (void)w; return dlvsym(h, n, "GLIBC_2.2.5"); }\n')
+    subprocess.run(["gcc", "-shared", "-fPIC", "-o", str(tmp_path / "mini.so"), str(mini), "-ldl"], check=True)
+    with pytest.raises(subprocess.TimeoutExpired):
+        subprocess.run([os.path.join(OREF, "trace_replay"), t], env=dict(base, LD_PRELOAD=f"{tmp_path / 'mini.so'}:{REF_SO}"),
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=8)
+    r = subprocess.run([os.path.join(OREF, "trace_replay"), t], env=dict(base, LD_PRELOAD=f"{SHIM_SO}:{REF_SO}"),
+                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=60, text=True)
+    assert r.returncode == 0 and " rc=0 " in r.stdout.splitlines()[1]
