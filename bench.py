@@ -295,12 +295,32 @@ def reference_arm(args):
     steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
     kind, res, note = "reference", None, ""
     if os.path.exists(os.path.join(OREF, "libvgpu.so")):
+        holder = None
         try:
-            p = spawn_app(0, nbuf, steps, warmup, "refhook", False, ballast_mib=ballast_mib)
-            res = finish_app(p, False, lambda: None, timeout=90)
-            note = "lib/nvidia/libvgpu.so binary preloaded (CUDA_OVERSUBSCRIBE=true -> cuMemAllocManaged)"
+            # the ballast lives in an UNHOOKED helper process: inside the reference-hooked process every large cuMemAlloc
+            # becomes managed memory (cuMemoryAllocate allocmode 0) and would not pin anything
+            henv = dict(os.environ, CUDA_VISIBLE_DEVICES="0", SWAP_BENCH_HOLD_MIB=str(ballast_mib))
+            henv.pop("LD_PRELOAD", None)
+            holder = subprocess.Popen([os.path.join(LIBDIR, "swap_bench")], env=henv, stdin=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            for line in holder.stderr:
+                if line.startswith("READY"):
+                    break
+            p = spawn_app(0, nbuf, steps, warmup, "refhook", False, ballast_mib=0)
+            res = finish_app(p, False, lambda: None, timeout=240)
+            if res["event_ms"] / max(res["steps"], 1) < 0.5 * BUF_MIB * MiB / 60e6:   # faster than the link allows: nothing was paged
+                raise RuntimeError("no paging happened under the reference hook")
+            note = ("lib/nvidia/libvgpu.so binary preloaded (oracle/dlsym_shim.so first; CUDA_OVERSUBSCRIBE=true -> cuMemAllocManaged); "
+                    "ballast held by an unhooked helper process")
         except Exception as e:
-            note = f"reference binary did not run on this driver ({str(e)[:120]}); "
+            res = None
+            note = f"reference binary run unusable on this box ({str(e)[:120]}); "
+        finally:
+            if holder:
+                try:
+                    holder.stdin.close()
+                    holder.wait(timeout=30)
+                except Exception:
+                    holder.kill()
     if res is None:
         p = spawn_app(0, nbuf, steps, warmup, "managed", False, ballast_mib=ballast_mib)
         res = finish_app(p, False, lambda: None)

@@ -50,6 +50,18 @@ int main(int argc, char **argv) {
         else if (!strcmp(k, "--wait-stdin")) wait_stdin = atol(v);
         else { fprintf(stderr, "unknown option %s\n", k); return 2; }
     }
+    if (getenv("SWAP_BENCH_HOLD_MIB")) {
+        /* ballast holder: an UNHOOKED helper process that pins physical memory with plain cuMemAlloc so that the
+         * reference hook's UVM allocations in another process see the same physical budget as the quota (the reference
+         * turns every large cuMemAlloc of its own process into managed memory, so the ballast cannot live there) */
+        CUdevice hd; CUcontext hc; CUdeviceptr hp; char line[8];
+        CK(cuInit(0)); CK(cuDeviceGet(&hd, 0)); CK(cuDevicePrimaryCtxRetain(&hc, hd)); CK(cuCtxSetCurrent(hc));
+        CK(cuMemAlloc(&hp, (size_t)atol(getenv("SWAP_BENCH_HOLD_MIB")) << 20));
+        CK(cuMemsetD8(hp, 0, 1 << 20));
+        fprintf(stderr, "READY\n"); fflush(stderr);
+        if (!fgets(line, sizeof line, stdin)) return 0;
+        return 0;
+    }
     if (!cubin) { fprintf(stderr, "--cubin required\n"); return 2; }
     rng_state = (uint64_t)seed;
     const size_t bytes = (size_t)mib << 20;
