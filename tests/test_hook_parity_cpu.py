@@ -6,6 +6,7 @@ import gzip
 import hashlib
 import json
 import os
+import json
 import subprocess
 
 import pytest
@@ -129,3 +130,28 @@ def test_multi_process_container_shares_the_quota(tmp_path):
     t2.write_text("A 0 %d\n" % (200 << 20))
     out = subprocess.run([os.path.join(OREF, "trace_replay"), str(t2)], env=env, stdout=subprocess.PIPE, text=True).stdout.splitlines()
     assert " rc=0 " in out[1], out
+
+
+def _intercept(env_extra, n_alloc, n_launch):
+    env = dict(os.environ, LD_LIBRARY_PATH=FAKE, LIBCUDA_LOG_LEVEL="0")
+    env.pop("LD_PRELOAD", None)
+    env.update(env_extra)
+    r = subprocess.run([os.path.join(LIBDIR, "intercept_bench"), "unused.cubin", str(n_alloc), str(n_launch)], env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=300)
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
+def test_pure_intercept_overhead_is_below_the_reference_hooks(tmp_path):
+    """Against a zero-cost (fake) driver the numbers are the hooks' own cost per call: the reference pays several
+    getenv+atoi per wrapper and two semaphore round trips with linear slot scans per allocation."""
+    os.makedirs("/tmp/vgpulock", exist_ok=True)
+    bare = _intercept({}, 100000, 1000000)
+    new = _intercept(dict(LD_PRELOAD=HOOK_SO, CUDA_DEVICE_MEMORY_LIMIT_0="8192m", CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "n.cache")), 100000, 1000000)
+    ref = _intercept(dict(LD_PRELOAD=os.path.join(OREF, "dlsym_shim.so") + ":" + os.path.join(OREF, "libvgpu.so"),
+                          CUDA_DEVICE_MEMORY_LIMIT_0="8192m", CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "r.cache")), 20000, 200000)
+    new_launch, ref_launch = new["launch_empty_ns"] - bare["launch_empty_ns"], ref["launch_empty_ns"] - bare["launch_empty_ns"]
+    new_alloc, ref_alloc = new["alloc_free_1mib_ns"] - bare["alloc_free_1mib_ns"], ref["alloc_free_1mib_ns"] - bare["alloc_free_1mib_ns"]
+    print(f"launch +{new_launch:.0f} ns (reference +{ref_launch:.0f}); alloc+free +{new_alloc:.0f} ns (reference +{ref_alloc:.0f})")
+    assert new_launch < 150 and new_launch < ref_launch
+    assert new_alloc < 3000 and new_alloc < ref_alloc
