@@ -6,7 +6,6 @@ import gzip
 import hashlib
 import json
 import os
-import json
 import subprocess
 
 import pytest
