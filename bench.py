@@ -469,7 +469,11 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "vgpu_pack_tma (pack + unpack launches inside the timed region)",
                          "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4) if achieved else None, "peak_source": how, "traffic": None,
+                         "frac": round(achieved / peak, 4) if achieved else None, "peak_source": how,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same 32 MiB-chunk launch, ncu --set full
+                         # (profiles/r01b_pack_tma_full.md: 33.567 MB read + 0.456 MB written back so far; the 33.55 MB written
+                         # by the kernel are still dirty in the 126 MB L2 when it ends)
+                         "traffic": 34023936,
                          "launches": int(kern_launches), "avg_launch_us": round(kern_ms * 1e3 / max(kern_launches, 1), 2),
                          "bytes_per_launch": int(kern_bytes // max(kern_launches, 1)),
                          "note": "achieved = CUDA-event brackets on the engine's kernel streams inside the timed region; they include the host's "

@@ -78,6 +78,11 @@ VGPU_EXPORT CUresult cuLaunchCooperativeKernel(CUfunction f, unsigned int gridDi
                                              sharedMemBytes, hStream, kernelParams);
 }
 
+VGPU_EXPORT CUresult cuModuleUnload(CUmodule hmod) {
+    Runtime::get().forget_function_layouts();
+    return drv().cuModuleUnload(hmod);
+}
+
 // memcpy / memset: pass-through, except that in swap mode the device ranges they touch are paged in first (a DMA
 // engine cannot fault on an unmapped VMM range the way UVM-managed memory does in the reference)
 #define TOUCH1(p, n, st) Runtime::get().touch_range((p), (n), (st))
@@ -190,7 +195,7 @@ const std::vector<HookEntry> &hooks() {
         H(cuGetProcAddress_v2),
         H(cuMemAlloc_v2), H(cuMemAllocManaged), H(cuMemAllocPitch_v2), H(cuMemFree_v2), H(cuMemGetInfo_v2),
         H(cuDeviceTotalMem_v2), H(cuDevicePrimaryCtxRetain), H(cuCtxCreate_v2), H(cuMemHostAlloc), H(cuMemAllocHost_v2),
-        H(cuLaunchKernel), H(cuLaunchKernelEx), H(cuLaunchCooperativeKernel),
+        H(cuLaunchKernel), H(cuLaunchKernelEx), H(cuLaunchCooperativeKernel), H(cuModuleUnload),
         H(cuMemcpyHtoD_v2), H(cuMemcpyDtoH_v2), H(cuMemcpyDtoD_v2), H(cuMemcpyHtoDAsync_v2), H(cuMemcpyDtoHAsync_v2),
         H(cuMemcpyDtoDAsync_v2), H(cuMemcpy), H(cuMemcpyAsync),
         H(cuMemsetD8_v2), H(cuMemsetD16_v2), H(cuMemsetD32_v2), H(cuMemsetD8Async), H(cuMemsetD16Async), H(cuMemsetD32Async),

@@ -465,9 +465,10 @@ bool Runtime::nvml_memory_view(int idx, unsigned long long *total, unsigned long
 namespace {
 struct ParamLayout { std::vector<std::pair<size_t, size_t>> p; bool known = false; };
 std::mutex g_layout_mu;
-std::unordered_map<CUfunction, ParamLayout> g_layouts;
+std::unordered_map<CUfunction, std::shared_ptr<const ParamLayout>> g_layouts;
 
-const ParamLayout &layout_of(CUfunction f) {
+// shared_ptr: cuModuleUnload may clear the cache while another thread is still scanning with a layout
+std::shared_ptr<const ParamLayout> layout_of(CUfunction f) {
     std::lock_guard<std::mutex> g(g_layout_mu);
     auto it = g_layouts.find(f);
     if (it != g_layouts.end()) return it->second;
@@ -481,13 +482,21 @@ const ParamLayout &layout_of(CUfunction f) {
             L.p.emplace_back(off, sz);
         }
     }
-    return g_layouts.emplace(f, std::move(L)).first->second;
+    auto sp = std::make_shared<const ParamLayout>(std::move(L));
+    g_layouts.emplace(f, sp);
+    return sp;
 }
 }  // namespace
 
+void Runtime::forget_function_layouts() {
+    std::lock_guard<std::mutex> g(g_layout_mu);
+    g_layouts.clear();
+}
+
 // Collects the swap-table rows referenced by a launch's arguments (pointers falling inside the swap arena).
 static void collect_launch_rows(SwapEngine *e, CUfunction f, void **params, void **extra, std::vector<int> *rows) {
-    const ParamLayout &L = layout_of(f);
+    std::shared_ptr<const ParamLayout> Lp = layout_of(f);
+    const ParamLayout &L = *Lp;
     if (params && L.known) {
         for (size_t i = 0; i < L.p.size(); i++)
             if (L.p[i].second >= 8 && params[i]) e->collect_rows(params[i], L.p[i].second, rows);

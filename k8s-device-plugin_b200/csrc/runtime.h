@@ -68,6 +68,8 @@ class Runtime {
     CUresult launch_cooperative(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by,
                                 unsigned bz, unsigned smem, CUstream st, void **params);
     // check_oom() of the reference (oom_check(dev, 0)): used by host-alloc style hooks
+    // cuModuleUnload: CUfunction handles of the module die with it; forget their cached parameter layouts
+    void forget_function_layouts();
     bool check_oom();
     // memcpy/memset family: make the touched device ranges resident before the real call (swap mode only)
     void touch_range(CUdeviceptr p, size_t bytes, CUstream st);
