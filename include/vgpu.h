@@ -66,7 +66,16 @@ uint64_t vgpu_region_usage(vgpu_region_handle_t *h, int dev);
 /* monitor write-back (feedback.go:153-156,207-251); pass INT32_MIN to leave a field unchanged */
 int vgpu_region_set_feedback(vgpu_region_handle_t *h, int32_t recent_kernel, int32_t utilization_switch);
 int vgpu_region_set_hostpid(vgpu_region_handle_t *h, int32_t pid, int32_t hostpid);
+/* publish a device identity in lane `dev` (the hook does this itself from NVML: put_device_info, multiprocess_memory_limit.c:L150) */
+int vgpu_region_set_uuid(vgpu_region_handle_t *h, int dev, const char *uuid);
 void *vgpu_region_raw(vgpu_region_handle_t *h);                                          /* vgpu_shared_region_t* */
+
+/* ---- node monitor feedback (reference: Observe cmd/vGPUmonitor/feedback.go:197-255, CheckBlocking :165-179, CheckPriority
+ * :181-195). One pass over the regions of every container on the node: decrements recentKernel, counts active tasks per GPU
+ * UUID and priority, then blocks lower-priority containers (recentKernel = -1) while a higher-priority one is active and
+ * switches the core limiter on only where a GPU is actually contended (utilizationSwitch). Returns the number of regions
+ * whose words were changed. */
+int vgpu_monitor_observe(vgpu_region_handle_t **regions, int n);
 
 /* ---- sm_100a kernels, directly (a CUDA context must be current on the calling thread) */
 typedef struct vgpu_seg { uint64_t src, dst, bytes; } vgpu_seg_t;

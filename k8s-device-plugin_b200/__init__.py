@@ -88,7 +88,9 @@ ABI = {
     "vgpu_region_usage": (_U64, [_P, _INT]),
     "vgpu_region_set_feedback": (_INT, [_P, _I32, _I32]),
     "vgpu_region_set_hostpid": (_INT, [_P, _I32, _I32]),
+    "vgpu_region_set_uuid": (_INT, [_P, _INT, C.c_char_p]),
     "vgpu_region_raw": (_P, [_P]),
+    "vgpu_monitor_observe": (_INT, [C.POINTER(_P), _INT]),
     "vgpu_pack": (_INT, [C.POINTER(Seg), C.c_size_t, _P]),
     "vgpu_pack_config": (_INT, [_U32, _U32, _U32]),
     "vgpu_victim_scan": (_INT, [_U64, _U32, _U64, _U64, _P, C.POINTER(_U32), _U32, C.POINTER(_U32), C.POINTER(_U64),
@@ -193,6 +195,9 @@ class Region:
     def usage(self, dev):
         return lib().vgpu_region_usage(self._h, dev)
 
+    def set_uuid(self, dev, uuid):
+        lib().vgpu_region_set_uuid(self._h, dev, uuid.encode())
+
     def set_feedback(self, recent_kernel=None, utilization_switch=None):
         keep = -(2 ** 31)
         lib().vgpu_region_set_feedback(self._h, keep if recent_kernel is None else recent_kernel,
@@ -203,6 +208,12 @@ class Region:
 
     def __exit__(self, *a):
         self.close()
+
+
+def monitor_observe(regions):
+    """One feedback pass of the node monitor over Region objects (reference Observe, feedback.go:197-255)."""
+    arr = (_P * max(len(regions), 1))(*[r._h for r in regions])
+    return lib().vgpu_monitor_observe(arr, len(regions))
 
 
 def pack(segments, stream=0):

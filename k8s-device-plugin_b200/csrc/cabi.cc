@@ -1,8 +1,10 @@
 // cabi.cc — implementation of include/vgpu.h on top of the core classes. Plain pointers and sizes only.
 #include "vgpu.h"
 
+#include <array>
 #include <climits>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -87,7 +89,61 @@ VGPU_API int vgpu_region_set_hostpid(vgpu_region_handle_t *h, int32_t pid, int32
     h->r->set_hostpid(pid, hostpid);
     return 0;
 }
+VGPU_API int vgpu_region_set_uuid(vgpu_region_handle_t *h, int dev, const char *uuid) {
+    if (!h || !uuid || dev < 0 || dev >= VGPU_MAX_DEVICES) return 1;
+    vgpu_shared_region_t *r = h->r->raw();
+    std::memset(r->uuids[dev], 0, VGPU_UUID_LEN);
+    std::strncpy(r->uuids[dev], uuid, VGPU_UUID_LEN - 1);
+    if (r->device_num < (uint64_t)dev + 1) r->device_num = (uint64_t)dev + 1;
+    return 0;
+}
 VGPU_API void *vgpu_region_raw(vgpu_region_handle_t *h) { return h ? h->r->raw() : nullptr; }
+
+// ------------------------------------------------------------------------------------------------ monitor feedback
+VGPU_API int vgpu_monitor_observe(vgpu_region_handle_t **regions, int n) {
+    // utSwitchOn: GPU uuid -> active task count per priority (index 0 = high, 1 = low; feedback.go:214-217)
+    std::map<std::string, std::array<int, 2>> active;
+    auto key = [](const char *u) { return std::string(u, VGPU_UUID_LEN); };
+    auto prio = [](const vgpu_shared_region_t *r) { return r->priority < 0 ? 0 : (r->priority > 1 ? 1 : r->priority); };
+    for (int i = 0; i < n; i++) {
+        if (!regions[i]) continue;
+        vgpu_shared_region_t *r = regions[i]->r->raw();
+        if (r->recent_kernel > 0) {
+            r->recent_kernel--;
+            if (r->recent_kernel > 0)
+                for (int d = 0; d < VGPU_MAX_DEVICES; d++) {
+                    if (r->uuids[d][0] == 0) continue;          // "Null device condition"
+                    active[key(r->uuids[d])][prio(r)]++;
+                }
+        }
+    }
+    int changed = 0;
+    for (int i = 0; i < n; i++) {
+        if (!regions[i]) continue;
+        vgpu_shared_region_t *r = regions[i]->r->raw();
+        const int p = prio(r);
+        bool blocking = false, contended = false;
+        for (int d = 0; d < VGPU_MAX_DEVICES; d++) {            // CheckBlocking: decided by the FIRST uuid found in the map
+            auto it = active.find(key(r->uuids[d]));
+            if (it == active.end()) continue;
+            for (int q = 0; q < p; q++) if (it->second[q] > 0) blocking = true;
+            break;
+        }
+        for (int d = 0; d < VGPU_MAX_DEVICES && !contended; d++) {   // CheckPriority: any uuid
+            auto it = active.find(key(r->uuids[d]));
+            if (it == active.end()) continue;
+            for (int q = 0; q < p; q++) if (it->second[q] > 0) contended = true;
+            if (it->second[p] > 1) contended = true;
+        }
+        bool touched = false;
+        if (blocking) { if (r->recent_kernel >= 0) { r->recent_kernel = -1; touched = true; } }
+        else if (r->recent_kernel < 0) { r->recent_kernel = 0; touched = true; }
+        if (contended) { if (r->utilization_switch != 1) { r->utilization_switch = 1; touched = true; } }
+        else if (r->utilization_switch != 0) { r->utilization_switch = 0; touched = true; }
+        changed += touched;
+    }
+    return changed;
+}
 
 // ------------------------------------------------------------------------------------------------ kernels
 VGPU_API int vgpu_pack(const vgpu_seg_t *segs, size_t nseg, void *stream) {
