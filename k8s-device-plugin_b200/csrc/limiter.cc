@@ -86,6 +86,16 @@ void Limiter::harvest() {
         PerStream &ps = streams_[it->st];
         if (!it->has_begin && ps.last_end > b) b = ps.last_end;
         uint64_t busy = e > b ? e - b : 0;
+        if (it->idle_ns && busy > 0) {
+            // span = work + the host's pause: keep what preceded the pause, cap what followed it at the recent average
+            uint64_t est = (uint64_t)(avg_busy_per_launch_ns_ * (it->launches ? it->launches : 1));
+            uint64_t before_pause = busy > it->idle_ns ? busy - it->idle_ns : 0;
+            uint64_t capped = before_pause + (it->idle_ns < est ? it->idle_ns : est);
+            if (capped < busy) busy = capped;
+        } else if (it->launches) {
+            double per = (double)busy / it->launches;
+            avg_busy_per_launch_ns_ = avg_busy_per_launch_ns_ == 0 ? per : 0.8 * avg_busy_per_launch_ns_ + 0.2 * per;
+        }
         ps.last_end = e;
         bucket_ns_ -= (double)busy;
         st_.busy_ns += busy;
@@ -112,7 +122,17 @@ void Limiter::before_launch(CUstream st) {
     uint64_t t_in = now_ns();
     refill(t_in);
     harvest();
-    // throttle: wait until the bucket is positive and the in-flight measurement backlog is bounded
+    // throttle: wait until the bucket is positive and the in-flight measurement backlog is bounded. A group that is
+    // still open on this stream is closed FIRST: its end stamp then runs right behind the kernels already queued, so
+    // the time this thread is about to sleep is not billed as GPU time when the group is finally measured.
+    if (bucket_ns_ <= 0 || (int)pending_.size() >= max_inflight_) {
+        PerStream &cur = streams_[st];
+        if (cur.open && cur.since_end > 0) {
+            int e = stamp(st);
+            if (e >= 0) pending_.push_back(Group{st, cur.begin_idx, e, cur.last_end, cur.begin_idx >= 0, cur.since_end, 0});
+            cur.open = false;
+        }
+    }
     while (bucket_ns_ <= 0 || (int)pending_.size() >= max_inflight_) {
         if (!pending_.empty()) {
             sleep_ns(20000);
@@ -134,11 +154,12 @@ void Limiter::before_launch(CUstream st) {
         bool behind_pending = false;
         for (auto &gq : pending_) if (gq.st == st) behind_pending = true;
         ps.begin_idx = behind_pending ? -1 : stamp(st);
-    } else if (t_out - ps.last_launch_ns > 20000) {
-        // the host paused inside an open group: close it and start a fresh one, so that at most the pause up to
-        // this point (not the whole idle period that may follow) is billed as GPU time
+    } else if (t_out - ps.last_launch_ns > 200000) {
+        // the APPLICATION paused inside an open group (no end stamp was queued behind its last launch). Close the group
+        // now; its span then contains the pause, so harvest() replaces the part of the span that lies after the last
+        // launch by an estimate from the recent busy-per-launch average (idle_ns = how long the host was away).
         int e = stamp(st);
-        if (e >= 0) pending_.push_back(Group{st, ps.begin_idx, e, ps.last_end, ps.begin_idx >= 0});
+        if (e >= 0) pending_.push_back(Group{st, ps.begin_idx, e, ps.last_end, ps.begin_idx >= 0, ps.since_end, t_out - ps.last_launch_ns});
         ps.begin_idx = -1;
         ps.since_end = 0;
     }
@@ -153,7 +174,7 @@ void Limiter::after_launch(CUstream st) {
     ps.last_launch_ns = now_ns();
     if (++ps.since_end >= stride_) {
         int e = stamp(st);
-        if (e >= 0) pending_.push_back(Group{st, ps.begin_idx, e, ps.last_end, ps.begin_idx >= 0});
+        if (e >= 0) pending_.push_back(Group{st, ps.begin_idx, e, ps.last_end, ps.begin_idx >= 0, ps.since_end, 0});
         ps.open = false;
     }
 }

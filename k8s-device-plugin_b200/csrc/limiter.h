@@ -40,7 +40,7 @@ class Limiter {
     bool active() const { return active_; }
 
    private:
-    struct Group { CUstream st; int begin_idx; int end_idx; uint64_t prev_end; bool has_begin; };
+    struct Group { CUstream st; int begin_idx; int end_idx; uint64_t prev_end; bool has_begin; int launches; uint64_t idle_ns; };
     struct PerStream { uint64_t last_end = 0; int since_end = 0; uint64_t last_launch_ns = 0; bool open = false; int begin_idx = -1; };
     bool ensure_ring();
     int stamp(CUstream st);
@@ -61,6 +61,7 @@ class Limiter {
     double bucket_ns_ = 0, burst_ns_ = 5e6;
     uint64_t last_refill_ = 0, t0_ = 0;
     int stride_ = 1, max_inflight_ = 2;
+    double avg_busy_per_launch_ns_ = 0;   // from groups measured without a pause inside
     LimiterStats st_;
 };
 

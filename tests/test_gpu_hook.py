@@ -143,3 +143,23 @@ def test_cudart_application_is_accounted_through_cugetprocaddress(tmp_path):
     env["VGPU_STRICT_CUDA_ERRORS"] = "1"
     r = subprocess.run([os.path.join(LIBDIR, "gemm_loop"), "4096", "1"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
     assert r.returncode != 0 and "out of memory" in (r.stdout + r.stderr).lower()
+
+
+def _launch_loop(env_extra, mib, seconds=5):
+    env = dict(os.environ)
+    env.pop("LD_PRELOAD", None)
+    env.update(env_extra)
+    r = subprocess.run([os.path.join(LIBDIR, "launch_loop"), CUBIN, str(mib), str(seconds)], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=200)
+    assert r.returncode == 0, r.stderr[-1500:] + r.stdout[-300:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.parametrize("mib,quota,lo,hi", [(2048, 30, 0.24, 0.36), (2048, 60, 0.52, 0.68), (16, 30, 0.18, 0.40)])
+def test_sm_limit_on_a_driver_api_launch_loop(tmp_path, mib, quota, lo, hi):
+    """Duty cycle = launches x un-throttled kernel time / wall, for ~0.7 ms kernels and for ~17 us kernels (stamps amortised
+    over groups). The reference hook measured on the same loop: no limiting at all at 30 % (94 % utilisation) and a multi-second
+    stall at 60 % (profiles/r01_cfg4_limiter_comparison.txt) — its delta() overflows int32 on B200."""
+    env = dict(v.hook_env(sm_limit=quota, cache_path=str(tmp_path / "ll.cache")), GPU_CORE_UTILIZATION_POLICY="force")
+    out = _launch_loop(env, mib)
+    assert lo <= out["duty"] <= hi, out
