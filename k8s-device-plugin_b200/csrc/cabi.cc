@@ -7,6 +7,8 @@
 #include <map>
 #include <string>
 #include <vector>
+#include <mutex>
+#include <memory>
 
 #include "driver.h"
 #include "kmod.h"
@@ -165,9 +167,22 @@ VGPU_API int vgpu_victim_scan(uint64_t d_table, uint32_t n, uint64_t need, uint6
                               uint32_t out_cap, uint32_t *out_count, uint64_t *freed, int *insufficient) {
     const Kernels *k = kernels_for_current_ctx();
     if (!k) return CUDA_ERROR_NOT_INITIALIZED;
-    VictimScanner sc;
-    CUresult r = sc.init(k, n ? n : 1);
-    if (r != CUDA_SUCCESS) return r;
+    // One scanner per context, grown on demand: its scratch (state words, pinned readback) is sized by the row count and
+    // allocating it costs far more than the scan itself.
+    static std::mutex mu;
+    // (leaked on purpose: at static-destruction time the driver may already be torn down)
+    static auto *cache = new std::map<const Kernels *, std::pair<uint32_t, std::unique_ptr<VictimScanner>>>();
+    std::lock_guard<std::mutex> g(mu);
+    auto &slot = (*cache)[k];
+    uint32_t want = n ? n : 1;
+    CUresult r = CUDA_SUCCESS;
+    if (!slot.second || slot.first < want) {
+        slot.second.reset(new VictimScanner());
+        r = slot.second->init(k, want);
+        if (r != CUDA_SUCCESS) { slot.second.reset(); return r; }
+        slot.first = want;
+    }
+    VictimScanner &sc = *slot.second;
     std::vector<uint32_t> v;
     bool ins = false;
     uint64_t fr = 0;
