@@ -490,7 +490,10 @@ def main():
             "cpu_baseline": cpu,
             "intercept_overhead": overhead,
             "mismatches": bad,
-            "engine": {k: d[k] for k in ("faults", "evictions", "scans", "scan_launches", "phys_creates", "phys_reuses")},
+            "engine": dict({k: d[k] for k in ("faults", "evictions", "scans", "scan_launches", "phys_creates", "phys_reuses")},
+                           # rank 0's calling-thread time per step inside admissions: where the step goes when it is not DMA
+                           host_ms_per_step={k[5:-3]: round(d[k] / 1e6 / args.steps, 3) for k in
+                                             ("host_admit_ns", "host_scan_ns", "host_packsync_ns", "host_vmm_ns", "host_ring_ns") if k in d}),
         }
         print(json.dumps(line))
     if dist:

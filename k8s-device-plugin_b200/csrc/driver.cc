@@ -54,6 +54,9 @@ const DriverTable &drv() {
     if (!g_drv.name) LOG_DEBUG("driver lacks %s", #name);
         VGPU_DRV_FUNCS(X)
 #undef X
+#define X(name, sfx) g_drv.name##sfx = reinterpret_cast<decltype(g_drv.name##sfx)>(real_dlsym(h, #name #sfx));
+        VGPU_DRV_PT_FUNCS(X)
+#undef X
         g_drv.cuGetProcAddress_v1 =
             reinterpret_cast<decltype(g_drv.cuGetProcAddress_v1)>(real_dlsym(h, "cuGetProcAddress"));
         if (!g_drv.cuDeviceGetUuid_v2)  // pre-11.4 drivers

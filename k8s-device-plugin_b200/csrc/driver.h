@@ -30,7 +30,19 @@ namespace vgpu {
     X(cuEventDestroy_v2)                                                                                          \
     X(cuModuleLoadData) X(cuModuleGetFunction) X(cuModuleUnload) X(cuFuncSetAttribute) X(cuFuncGetParamInfo)      \
     X(cuLaunchKernel) X(cuLaunchKernelEx) X(cuLaunchCooperativeKernel) X(cuOccupancyMaxActiveBlocksPerMultiprocessor) \
+    X(cuMemAllocAsync) X(cuMemAllocFromPoolAsync) X(cuMemFreeAsync) X(cuGraphLaunch)                              \
     X(cuGetProcAddress_v2) X(cuGetErrorString) X(cuGetErrorName)
+
+// per-thread-default-stream twins (cuda.h hides their prototypes behind __CUDA_API_VERSION_INTERNAL; the signatures
+// are those of the base name). cudart built with --default-stream per-thread asks cuGetProcAddress for these.
+#define VGPU_DRV_PT_FUNCS(X)                                                                                      \
+    X(cuLaunchKernel, _ptsz) X(cuLaunchKernelEx, _ptsz) X(cuLaunchCooperativeKernel, _ptsz) X(cuGraphLaunch, _ptsz) \
+    X(cuMemAllocAsync, _ptsz) X(cuMemAllocFromPoolAsync, _ptsz) X(cuMemFreeAsync, _ptsz)                          \
+    X(cuMemcpyHtoD_v2, _ptds) X(cuMemcpyDtoH_v2, _ptds) X(cuMemcpyDtoD_v2, _ptds) X(cuMemcpy, _ptds)              \
+    X(cuMemcpyHtoDAsync_v2, _ptsz) X(cuMemcpyDtoHAsync_v2, _ptsz) X(cuMemcpyDtoDAsync_v2, _ptsz)                  \
+    X(cuMemcpyAsync, _ptsz)                                                                                       \
+    X(cuMemsetD8_v2, _ptds) X(cuMemsetD16_v2, _ptds) X(cuMemsetD32_v2, _ptds)                                     \
+    X(cuMemsetD8Async, _ptsz) X(cuMemsetD16Async, _ptsz) X(cuMemsetD32Async, _ptsz)
 
 #define VGPU_NVML_FUNCS(X)                                                                                        \
     X(nvmlInit_v2) X(nvmlShutdown) X(nvmlDeviceGetCount_v2) X(nvmlDeviceGetHandleByIndex_v2) X(nvmlDeviceGetUUID) \
@@ -40,6 +52,9 @@ namespace vgpu {
 struct DriverTable {
 #define X(name) decltype(&::name) name = nullptr;
     VGPU_DRV_FUNCS(X)
+#undef X
+#define X(name, sfx) decltype(&::name) name##sfx = nullptr;
+    VGPU_DRV_PT_FUNCS(X)
 #undef X
     // cuGetProcAddress (v1 signature, CUDA 11.3-11.8 entry point) has no prototype in cuda.h 12.x
     CUresult (*cuGetProcAddress_v1)(const char *, void **, int, cuuint64_t) = nullptr;

@@ -78,6 +78,42 @@ VGPU_EXPORT CUresult cuLaunchCooperativeKernel(CUfunction f, unsigned int gridDi
                                              sharedMemBytes, hStream, kernelParams);
 }
 
+// per-thread-default-stream twins: same semantics, the driver's _ptsz entry underneath
+VGPU_EXPORT CUresult cuLaunchKernel_ptsz(CUfunction f, unsigned int gx, unsigned int gy, unsigned int gz, unsigned int bx,
+                                         unsigned int by, unsigned int bz, unsigned int smem, CUstream st, void **params, void **extra) {
+    return Runtime::get().launch_kernel_ptsz(f, gx, gy, gz, bx, by, bz, smem, st, params, extra);
+}
+VGPU_EXPORT CUresult cuLaunchKernelEx_ptsz(const CUlaunchConfig *config, CUfunction f, void **params, void **extra) {
+    return Runtime::get().launch_kernel_ex_ptsz(config, f, params, extra);
+}
+VGPU_EXPORT CUresult cuLaunchCooperativeKernel_ptsz(CUfunction f, unsigned int gx, unsigned int gy, unsigned int gz, unsigned int bx,
+                                                    unsigned int by, unsigned int bz, unsigned int smem, CUstream st, void **params) {
+    return Runtime::get().launch_cooperative_ptsz(f, gx, gy, gz, bx, by, bz, smem, st, params);
+}
+
+// beyond the reference's coverage: graph launches are rate-limited, stream-ordered and VMM
+// allocations are charged to the quota
+VGPU_EXPORT CUresult cuGraphLaunch(CUgraphExec g, CUstream st) { return Runtime::get().graph_launch(g, st, false); }
+VGPU_EXPORT CUresult cuGraphLaunch_ptsz(CUgraphExec g, CUstream st) { return Runtime::get().graph_launch(g, st, true); }
+VGPU_EXPORT CUresult cuMemAllocAsync(CUdeviceptr *dptr, size_t bytesize, CUstream st) {
+    return Runtime::get().mem_alloc_async(dptr, bytesize, nullptr, false, st, false);
+}
+VGPU_EXPORT CUresult cuMemAllocAsync_ptsz(CUdeviceptr *dptr, size_t bytesize, CUstream st) {
+    return Runtime::get().mem_alloc_async(dptr, bytesize, nullptr, false, st, true);
+}
+VGPU_EXPORT CUresult cuMemAllocFromPoolAsync(CUdeviceptr *dptr, size_t bytesize, CUmemoryPool pool, CUstream st) {
+    return Runtime::get().mem_alloc_async(dptr, bytesize, pool, true, st, false);
+}
+VGPU_EXPORT CUresult cuMemAllocFromPoolAsync_ptsz(CUdeviceptr *dptr, size_t bytesize, CUmemoryPool pool, CUstream st) {
+    return Runtime::get().mem_alloc_async(dptr, bytesize, pool, true, st, true);
+}
+VGPU_EXPORT CUresult cuMemFreeAsync(CUdeviceptr dptr, CUstream st) { return Runtime::get().mem_free_async(dptr, st, false); }
+VGPU_EXPORT CUresult cuMemFreeAsync_ptsz(CUdeviceptr dptr, CUstream st) { return Runtime::get().mem_free_async(dptr, st, true); }
+VGPU_EXPORT CUresult cuMemCreate(CUmemGenericAllocationHandle *handle, size_t size, const CUmemAllocationProp *prop, unsigned long long flags) {
+    return Runtime::get().mem_create(handle, size, prop, flags);
+}
+VGPU_EXPORT CUresult cuMemRelease(CUmemGenericAllocationHandle handle) { return Runtime::get().mem_release(handle); }
+
 VGPU_EXPORT CUresult cuModuleUnload(CUmodule hmod) {
     Runtime::get().forget_function_layouts();
     return drv().cuModuleUnload(hmod);
@@ -130,6 +166,52 @@ VGPU_EXPORT CUresult cuMemsetD16Async(CUdeviceptr dst, unsigned short v, size_t 
 VGPU_EXPORT CUresult cuMemsetD32Async(CUdeviceptr dst, unsigned int v, size_t n, CUstream st) {
     TOUCH1(dst, n * 4, st); CUresult r = drv().cuMemsetD32Async(dst, v, n, st); TOUCH_DONE(st); return r;
 }
+
+// per-thread-default-stream twins of the copy / fill family (a null stream is the calling thread's own stream)
+#define PTS(st) ((st) ? (st) : CU_STREAM_PER_THREAD)
+VGPU_EXPORT CUresult cuMemcpyHtoD_v2_ptds(CUdeviceptr dst, const void *src, size_t n) {
+    TOUCH1(dst, n, CU_STREAM_PER_THREAD); CUresult r = drv().cuMemcpyHtoD_v2_ptds(dst, src, n); TOUCH_DONE(CU_STREAM_PER_THREAD); return r;
+}
+VGPU_EXPORT CUresult cuMemcpyDtoH_v2_ptds(void *dst, CUdeviceptr src, size_t n) {
+    TOUCH1(src, n, CU_STREAM_PER_THREAD); CUresult r = drv().cuMemcpyDtoH_v2_ptds(dst, src, n); TOUCH_DONE(CU_STREAM_PER_THREAD); return r;
+}
+VGPU_EXPORT CUresult cuMemcpyDtoD_v2_ptds(CUdeviceptr dst, CUdeviceptr src, size_t n) {
+    TOUCH2(dst, n, src, n, CU_STREAM_PER_THREAD); CUresult r = drv().cuMemcpyDtoD_v2_ptds(dst, src, n); TOUCH_DONE(CU_STREAM_PER_THREAD); return r;
+}
+VGPU_EXPORT CUresult cuMemcpy_ptds(CUdeviceptr dst, CUdeviceptr src, size_t n) {
+    TOUCH2(dst, n, src, n, CU_STREAM_PER_THREAD); CUresult r = drv().cuMemcpy_ptds(dst, src, n); TOUCH_DONE(CU_STREAM_PER_THREAD); return r;
+}
+VGPU_EXPORT CUresult cuMemcpyHtoDAsync_v2_ptsz(CUdeviceptr dst, const void *src, size_t n, CUstream st) {
+    TOUCH1(dst, n, PTS(st)); CUresult r = drv().cuMemcpyHtoDAsync_v2_ptsz(dst, src, n, st); TOUCH_DONE(PTS(st)); return r;
+}
+VGPU_EXPORT CUresult cuMemcpyDtoHAsync_v2_ptsz(void *dst, CUdeviceptr src, size_t n, CUstream st) {
+    TOUCH1(src, n, PTS(st)); CUresult r = drv().cuMemcpyDtoHAsync_v2_ptsz(dst, src, n, st); TOUCH_DONE(PTS(st)); return r;
+}
+VGPU_EXPORT CUresult cuMemcpyDtoDAsync_v2_ptsz(CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream st) {
+    TOUCH2(dst, n, src, n, PTS(st)); CUresult r = drv().cuMemcpyDtoDAsync_v2_ptsz(dst, src, n, st); TOUCH_DONE(PTS(st)); return r;
+}
+VGPU_EXPORT CUresult cuMemcpyAsync_ptsz(CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream st) {
+    TOUCH2(dst, n, src, n, PTS(st)); CUresult r = drv().cuMemcpyAsync_ptsz(dst, src, n, st); TOUCH_DONE(PTS(st)); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD8_v2_ptds(CUdeviceptr dst, unsigned char v, size_t n) {
+    TOUCH1(dst, n, CU_STREAM_PER_THREAD); CUresult r = drv().cuMemsetD8_v2_ptds(dst, v, n); TOUCH_DONE(CU_STREAM_PER_THREAD); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD16_v2_ptds(CUdeviceptr dst, unsigned short v, size_t n) {
+    TOUCH1(dst, n * 2, CU_STREAM_PER_THREAD); CUresult r = drv().cuMemsetD16_v2_ptds(dst, v, n); TOUCH_DONE(CU_STREAM_PER_THREAD); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD32_v2_ptds(CUdeviceptr dst, unsigned int v, size_t n) {
+    TOUCH1(dst, n * 4, CU_STREAM_PER_THREAD); CUresult r = drv().cuMemsetD32_v2_ptds(dst, v, n); TOUCH_DONE(CU_STREAM_PER_THREAD); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD8Async_ptsz(CUdeviceptr dst, unsigned char v, size_t n, CUstream st) {
+    TOUCH1(dst, n, PTS(st)); CUresult r = drv().cuMemsetD8Async_ptsz(dst, v, n, st); TOUCH_DONE(PTS(st)); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD16Async_ptsz(CUdeviceptr dst, unsigned short v, size_t n, CUstream st) {
+    TOUCH1(dst, n * 2, PTS(st)); CUresult r = drv().cuMemsetD16Async_ptsz(dst, v, n, st); TOUCH_DONE(PTS(st)); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD32Async_ptsz(CUdeviceptr dst, unsigned int v, size_t n, CUstream st) {
+    TOUCH1(dst, n * 4, PTS(st)); CUresult r = drv().cuMemsetD32Async_ptsz(dst, v, n, st); TOUCH_DONE(PTS(st)); return r;
+}
+#undef PTS
 
 // extras the reference exports for its own tooling
 VGPU_EXPORT CUresult cuMemoryAllocate(CUdeviceptr *dptr, size_t bytesize, size_t *bytesallocated, void *data) {
@@ -199,6 +281,12 @@ const std::vector<HookEntry> &hooks() {
         H(cuMemcpyHtoD_v2), H(cuMemcpyDtoH_v2), H(cuMemcpyDtoD_v2), H(cuMemcpyHtoDAsync_v2), H(cuMemcpyDtoHAsync_v2),
         H(cuMemcpyDtoDAsync_v2), H(cuMemcpy), H(cuMemcpyAsync),
         H(cuMemsetD8_v2), H(cuMemsetD16_v2), H(cuMemsetD32_v2), H(cuMemsetD8Async), H(cuMemsetD16Async), H(cuMemsetD32Async),
+        H(cuLaunchKernel_ptsz), H(cuLaunchKernelEx_ptsz), H(cuLaunchCooperativeKernel_ptsz), H(cuGraphLaunch), H(cuGraphLaunch_ptsz),
+        H(cuMemAllocAsync), H(cuMemAllocAsync_ptsz), H(cuMemAllocFromPoolAsync), H(cuMemAllocFromPoolAsync_ptsz), H(cuMemFreeAsync),
+        H(cuMemFreeAsync_ptsz), H(cuMemCreate), H(cuMemRelease),
+        H(cuMemcpyHtoD_v2_ptds), H(cuMemcpyDtoH_v2_ptds), H(cuMemcpyDtoD_v2_ptds), H(cuMemcpy_ptds), H(cuMemcpyHtoDAsync_v2_ptsz),
+        H(cuMemcpyDtoHAsync_v2_ptsz), H(cuMemcpyDtoDAsync_v2_ptsz), H(cuMemcpyAsync_ptsz), H(cuMemsetD8_v2_ptds), H(cuMemsetD16_v2_ptds),
+        H(cuMemsetD32_v2_ptds), H(cuMemsetD8Async_ptsz), H(cuMemsetD16Async_ptsz), H(cuMemsetD32Async_ptsz),
         HN(cuMemoryAllocate), HN(cuMemoryFree), HN(cuVGPUViewAllocator),
         HN(nvmlDeviceGetMemoryInfo), HN(nvmlDeviceGetMemoryInfo_v2),
     };

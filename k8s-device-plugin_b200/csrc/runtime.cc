@@ -26,6 +26,12 @@ static bool env_true(const char *name) {
 }
 // Return codes on a quota breach / unknown pointer follow the reference bit for bit by default ((CUresult)-1 from
 // add_chunk@0x4005d and remove_chunk@0x409f0); VGPU_STRICT_CUDA_ERRORS=1 switches to CUDA-conformant codes.
+// VGPU_REFERENCE_COVERAGE=1: intercept exactly what the reference intercepts (async/pool allocations, cuMemCreate and
+// graph launches forwarded untouched)
+static bool reference_coverage() {
+    static bool on = [] { const char *e = std::getenv("VGPU_REFERENCE_COVERAGE"); return e && *e && *e != '0'; }();
+    return on;
+}
 static bool strict_errors() {
     static bool v = env_true("VGPU_STRICT_CUDA_ERRORS");
     return v;
@@ -563,6 +569,139 @@ CUresult Runtime::launch_cooperative(CUfunction f, unsigned gx, unsigned gy, uns
     if (!post_inited_.load(std::memory_order_acquire)) post_init(true);
     return guarded_launch(*this, cfg_, limiter_.get(), f, params, nullptr, st,
                           [&] { return drv().cuLaunchCooperativeKernel(f, gx, gy, gz, bx, by, bz, smem, st, params); });
+}
+
+static inline CUstream pt(CUstream st) { return st ? st : CU_STREAM_PER_THREAD; }
+
+CUresult Runtime::launch_kernel_ptsz(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
+                                     unsigned smem, CUstream st, void **params, void **extra) {
+    if (!drv().cuLaunchKernel_ptsz) return CUDA_ERROR_NOT_SUPPORTED;
+    if (!initialized()) ensure_initialized();
+    if (!post_inited_.load(std::memory_order_acquire)) post_init(true);
+    return guarded_launch(*this, cfg_, limiter_.get(), f, params, extra, pt(st),
+                          [&] { return drv().cuLaunchKernel_ptsz(f, gx, gy, gz, bx, by, bz, smem, st, params, extra); });
+}
+
+CUresult Runtime::launch_kernel_ex_ptsz(const CUlaunchConfig *cfg, CUfunction f, void **params, void **extra) {
+    if (!cfg || !drv().cuLaunchKernelEx_ptsz) return CUDA_ERROR_NOT_SUPPORTED;
+    if (!initialized()) ensure_initialized();
+    if (!post_inited_.load(std::memory_order_acquire)) post_init(true);
+    return guarded_launch(*this, cfg_, limiter_.get(), f, params, extra, pt(cfg->hStream),
+                          [&] { return drv().cuLaunchKernelEx_ptsz(cfg, f, params, extra); });
+}
+
+CUresult Runtime::launch_cooperative_ptsz(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by,
+                                          unsigned bz, unsigned smem, CUstream st, void **params) {
+    if (!drv().cuLaunchCooperativeKernel_ptsz) return CUDA_ERROR_NOT_SUPPORTED;
+    if (!initialized()) ensure_initialized();
+    if (!post_inited_.load(std::memory_order_acquire)) post_init(true);
+    return guarded_launch(*this, cfg_, limiter_.get(), f, params, nullptr, pt(st),
+                          [&] { return drv().cuLaunchCooperativeKernel_ptsz(f, gx, gy, gz, bx, by, bz, smem, st, params); });
+}
+
+// A graph launch is one unit of GPU work for the core limiter: gated like a kernel launch and billed by the same
+// device-side stamps (the limiter measures busy time around whatever was enqueued, so a whole graph is covered). The
+// reference has no hook on graph launches at all — a captured decode loop runs unthrottled there.
+CUresult Runtime::graph_launch(CUgraphExec g, CUstream st, bool ptsz) {
+    auto real = ptsz ? drv().cuGraphLaunch_ptsz : drv().cuGraphLaunch;
+    if (!real) return CUDA_ERROR_NOT_SUPPORTED;
+    if (!initialized()) ensure_initialized();
+    if (!post_inited_.load(std::memory_order_acquire)) post_init(true);
+    Limiter *lim = reference_coverage() ? nullptr : limiter_.get();
+    CUstream eff = ptsz ? pt(st) : st;
+    if (lim) lim->before_launch(eff);
+    CUresult r = real(g, st);
+    if (lim) lim->after_launch(eff);
+    return r;
+}
+
+// Stream-ordered allocations come out of a driver memory pool: charged to the quota like cuMemAlloc (requested bytes),
+// tracked in the same table so cuMemFree_v2 / cuMemFreeAsync / check_memory_type see them. Never swappable.
+CUresult Runtime::mem_alloc_async(CUdeviceptr *dptr, size_t bytes, CUmemoryPool pool, bool from_pool, CUstream st, bool ptsz) {
+    ensure_initialized();
+    const DriverTable &d = drv();
+    auto real = [&]() -> CUresult {
+        if (from_pool) {
+            auto f = ptsz ? d.cuMemAllocFromPoolAsync_ptsz : d.cuMemAllocFromPoolAsync;
+            return f ? f(dptr, bytes, pool, st) : CUDA_ERROR_NOT_SUPPORTED;
+        }
+        auto f = ptsz ? d.cuMemAllocAsync_ptsz : d.cuMemAllocAsync;
+        return f ? f(dptr, bytes, st) : CUDA_ERROR_NOT_SUPPORTED;
+    };
+    if (!region_ || reference_coverage()) return real();
+    int dev = current_device();
+    if (dev < 0) return real();
+    if (!charge(dev, bytes)) return CUDA_ERROR_OUT_OF_MEMORY;
+    CUresult r = real();
+    if (r != CUDA_SUCCESS) { uncharge(dev, bytes); return r; }
+    std::lock_guard<std::mutex> g(table_mu_);
+    track(*dptr, bytes, dev, AllocKind::Async);
+    return CUDA_SUCCESS;
+}
+
+CUresult Runtime::mem_free_async(CUdeviceptr dptr, CUstream st, bool ptsz) {
+    ensure_initialized();
+    const DriverTable &d = drv();
+    auto real = ptsz ? d.cuMemFreeAsync_ptsz : d.cuMemFreeAsync;
+    if (!real) return CUDA_ERROR_NOT_SUPPORTED;
+    if (!dptr || !region_) return real(dptr, st);
+    Alloc a;
+    {
+        std::lock_guard<std::mutex> g(table_mu_);
+        auto it = table_.find(dptr);
+        if (it == table_.end()) return real(dptr, st);          // not ours (allocated before the hook, or coverage off)
+        a = it->second;
+        if (a.kind == AllocKind::Swap) {
+            // a swappable buffer has no driver allocation behind its address: order the free behind the stream, then
+            // let the engine release it
+            d.cuStreamSynchronize(ptsz ? pt(st) : st);
+            SwapEngine *e = swap(a.dev);
+            CUresult r = e ? e->free(dptr) : CUDA_ERROR_INVALID_VALUE;
+            table_.erase(it);
+            region_->sub(pid_, a.dev, a.size, VGPU_MEM_BUFFER);
+            return r;
+        }
+        table_.erase(it);
+    }
+    CUresult r = real(dptr, st);
+    uncharge(a.dev, a.size);
+    return r;
+}
+
+// VMM physical allocations (PyTorch expandable segments, NCCL user buffers): the handle is what occupies HBM, mapped
+// or not, so the handle is what gets charged. Host-located handles are not device memory.
+CUresult Runtime::mem_create(CUmemGenericAllocationHandle *h, size_t bytes, const CUmemAllocationProp *prop, unsigned long long flags) {
+    ensure_initialized();
+    const DriverTable &d = drv();
+    if (!d.cuMemCreate) return CUDA_ERROR_NOT_SUPPORTED;
+    if (!region_ || reference_coverage() || !prop || prop->location.type != CU_MEM_LOCATION_TYPE_DEVICE)
+        return d.cuMemCreate(h, bytes, prop, flags);
+    int dev = prop->location.id;
+    if (dev < 0 || dev >= VGPU_MAX_DEVICES) return d.cuMemCreate(h, bytes, prop, flags);
+    if (!charge(dev, bytes)) return CUDA_ERROR_OUT_OF_MEMORY;
+    CUresult r = d.cuMemCreate(h, bytes, prop, flags);
+    if (r != CUDA_SUCCESS) { uncharge(dev, bytes); return r; }
+    std::lock_guard<std::mutex> g(table_mu_);
+    phys_[*h] = Alloc{bytes, dev, AllocKind::Device};
+    return CUDA_SUCCESS;
+}
+
+CUresult Runtime::mem_release(CUmemGenericAllocationHandle h) {
+    ensure_initialized();
+    const DriverTable &d = drv();
+    if (!d.cuMemRelease) return CUDA_ERROR_NOT_SUPPORTED;
+    CUresult r = d.cuMemRelease(h);
+    if (!region_ || r != CUDA_SUCCESS) return r;
+    Alloc a;
+    {
+        std::lock_guard<std::mutex> g(table_mu_);
+        auto it = phys_.find(h);
+        if (it == phys_.end()) return r;                        // imported / retained handle, or coverage off
+        a = it->second;
+        phys_.erase(it);
+    }
+    uncharge(a.dev, a.size);
+    return r;
 }
 
 static thread_local std::vector<int> t_touch_rows;   // rows pinned between touch_range*() and touch_done()

@@ -24,7 +24,7 @@ class Limiter;
 
 constexpr size_t kIpcSize = 2u << 20;  // IPCSIZE .data@0x610a8: allocations above this take the swap switch
 
-enum class AllocKind : uint8_t { Device, Managed, Pitch, Swap };
+enum class AllocKind : uint8_t { Device, Managed, Pitch, Swap, Async };
 
 struct Alloc {
     size_t size;       // bytes charged to the quota (requested bytes, no rounding — Appendix E)
@@ -67,6 +67,19 @@ class Runtime {
     CUresult launch_kernel_ex(const CUlaunchConfig *cfg, CUfunction f, void **params, void **extra);
     CUresult launch_cooperative(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by,
                                 unsigned bz, unsigned smem, CUstream st, void **params);
+    // per-thread-default-stream twins of the three launches above (ptsz: a null stream means CU_STREAM_PER_THREAD)
+    CUresult launch_kernel_ptsz(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
+                                unsigned smem, CUstream st, void **params, void **extra);
+    CUresult launch_kernel_ex_ptsz(const CUlaunchConfig *cfg, CUfunction f, void **params, void **extra);
+    CUresult launch_cooperative_ptsz(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by,
+                                     unsigned bz, unsigned smem, CUstream st, void **params);
+    // ---- coverage beyond the reference: the reference forwards these unaccounted / unlimited
+    // (cuMemAllocAsync@0x37e52, cuMemCreate@0x37ba1, cuGraphLaunch); VGPU_REFERENCE_COVERAGE=1 restores that.
+    CUresult mem_alloc_async(CUdeviceptr *dptr, size_t bytes, CUmemoryPool pool, bool from_pool, CUstream st, bool ptsz);
+    CUresult mem_free_async(CUdeviceptr dptr, CUstream st, bool ptsz);
+    CUresult mem_create(CUmemGenericAllocationHandle *h, size_t bytes, const CUmemAllocationProp *prop, unsigned long long flags);
+    CUresult mem_release(CUmemGenericAllocationHandle h);
+    CUresult graph_launch(CUgraphExec g, CUstream st, bool ptsz);
     // check_oom() of the reference (oom_check(dev, 0)): used by host-alloc style hooks
     // cuModuleUnload: CUfunction handles of the module die with it; forget their cached parameter layouts
     void forget_function_layouts();
@@ -113,6 +126,7 @@ class Runtime {
 
     std::mutex table_mu_;                   // the reference's single allocator mutex (mutex@0x61180)
     std::map<CUdeviceptr, Alloc> table_;    // base -> alloc; ordered for range classification
+    std::map<CUmemGenericAllocationHandle, Alloc> phys_;   // cuMemCreate handles charged to the quota (same mutex)
 
     std::mutex swap_mu_;
     std::unique_ptr<SwapEngine> swap_[VGPU_MAX_DEVICES];

@@ -233,7 +233,15 @@ EXPORT CUresult cuGetExportTable(const void **tbl, const CUuuid *id) {
 }
 EXPORT CUresult cuArray3DGetDescriptor_v2(void *d, void *a) { (void)d; (void)a; return CUDA_ERROR_NOT_SUPPORTED; }
 EXPORT CUresult cuMemAddressFree(CUdeviceptr p, size_t n) { (void)p; (void)n; return CUDA_SUCCESS; }
-EXPORT CUresult cuMemRelease(unsigned long long h) { (void)h; return CUDA_SUCCESS; }
+/* VMM physical handles and stream-ordered allocations: same bookkeeping as cuMemAlloc (a handle is its fake address) */
+EXPORT CUresult cuMemCreate(unsigned long long *h, size_t n, const void *prop, unsigned long long flags) {
+    (void)prop; (void)flags; CUdeviceptr p = 0; CUresult r = do_alloc(&p, n); if (!r) *h = p; return r;
+}
+EXPORT CUresult cuMemRelease(unsigned long long h) { return do_free(h); }
+EXPORT CUresult cuMemAllocAsync(CUdeviceptr *p, size_t n, CUstream st) { (void)st; return do_alloc(p, n); }
+EXPORT CUresult cuMemAllocFromPoolAsync(CUdeviceptr *p, size_t n, void *pool, CUstream st) { (void)pool; (void)st; return do_alloc(p, n); }
+EXPORT CUresult cuMemFreeAsync(CUdeviceptr p, CUstream st) { (void)st; return do_free(p); }
+EXPORT CUresult cuGraphLaunch(void *g, CUstream st) { (void)g; (void)st; __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); return CUDA_SUCCESS; }
 EXPORT CUresult cuMemSetAccess(CUdeviceptr p, size_t n, const void *d, size_t c) { (void)p; (void)n; (void)d; (void)c; return CUDA_SUCCESS; }
 EXPORT CUresult cuMemUnmap(CUdeviceptr p, size_t n) { (void)p; (void)n; return CUDA_SUCCESS; }
 

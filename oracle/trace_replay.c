@@ -13,6 +13,8 @@
  * Trace grammar, one op per line (ids index a pointer table):
  *   A id size | M id size (managed) | P id width height (pitch, elem 4) | F id | X hexaddr (free raw)
  *   I (cuMemGetInfo_v2) | T (cuDeviceTotalMem_v2) | L gx gy gz (cuLaunchKernel of an empty kernel) | S ms (sleep)
+ *   Y id size (cuMemAllocAsync) | Z id (cuMemFreeAsync) | C id size (cuMemCreate on device 0) | R id (cuMemRelease)
+ *   G (cuGraphLaunch of a null graph — only meaningful on the fake driver)
  * Output line: "<op#> <opcode> rc=<int> ctx=<u64> mod=<u64> buf=<u64> off=<u64> tot=<u64> [free=.. total=..]"
  * where the five counters are SUMMED over every process slot of device 0 (== own slot for one process).
  */
@@ -48,6 +50,13 @@ extern CUresult cuLaunchKernel(CUfunction, unsigned, unsigned, unsigned, unsigne
 extern CUresult cuModuleLoadData(CUmodule *, const void *) __attribute__((weak));
 extern CUresult cuModuleGetFunction(CUfunction *, CUmodule, const char *) __attribute__((weak));
 extern CUresult cuCtxSynchronize(void);
+/* entry points the reference forwards untouched */
+extern CUresult cuMemAllocAsync(CUdeviceptr *, size_t, CUstream) __attribute__((weak));
+extern CUresult cuMemFreeAsync(CUdeviceptr, CUstream) __attribute__((weak));
+extern CUresult cuMemCreate(unsigned long long *, size_t, const void *, unsigned long long) __attribute__((weak));
+extern CUresult cuMemRelease(unsigned long long) __attribute__((weak));
+extern CUresult cuGraphLaunch(void *, CUstream) __attribute__((weak));
+struct mem_prop { int type; int requested_handle_types; struct { int type; int id; } location; void *win32; struct { unsigned char c, g; unsigned short u; unsigned char r[4]; } flags; };
 
 /* Appendix A offsets */
 #define REGION_SIZE 0xC4748
@@ -130,6 +139,12 @@ int main(int argc, char **argv) {
         case 'T': r = cuDeviceTotalMem_v2(&tot, dev); fr = 0; has_info = 1; break;
         case 'L': r = cuLaunchKernel(fn, (unsigned)a, (unsigned)b, (unsigned)d, 1, 1, 1, 0, NULL, NULL, NULL); break;
         case 'S': usleep((useconds_t)a * 1000); r = 0; break;   /* sleep a ms (multi-process tests) */
+        case 'Y': ptrs[a] = 0; r = cuMemAllocAsync ? cuMemAllocAsync(&ptrs[a], (size_t)b, NULL) : 801; if (r) ptrs[a] = 0; break;
+        case 'Z': r = cuMemFreeAsync ? cuMemFreeAsync(ptrs[a], NULL) : 801; if (!r) ptrs[a] = 0; break;
+        case 'C': { struct mem_prop pr; memset(&pr, 0, sizeof pr); pr.type = 1 /* PINNED */; pr.location.type = 1 /* DEVICE */; pr.location.id = 0;
+                    ptrs[a] = 0; r = cuMemCreate ? cuMemCreate(&ptrs[a], (size_t)b, &pr, 0) : 801; if (r) ptrs[a] = 0; break; }
+        case 'R': r = cuMemRelease ? cuMemRelease(ptrs[a]) : 801; if (!r) ptrs[a] = 0; break;
+        case 'G': r = cuGraphLaunch ? cuGraphLaunch(NULL, NULL) : 801; break;
         default: continue;
         }
         counters(0, c);

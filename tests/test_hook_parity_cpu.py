@@ -154,3 +154,38 @@ def test_pure_intercept_overhead_is_below_the_reference_hooks(tmp_path):
     print(f"launch +{new_launch:.0f} ns (reference +{ref_launch:.0f}); alloc+free +{new_alloc:.0f} ns (reference +{ref_alloc:.0f})")
     assert new_launch < 150 and new_launch < ref_launch
     assert new_alloc < 3000 and new_alloc < ref_alloc
+
+
+_WIDE_TRACE = ("A 0 %d\nY 1 %d\nC 2 %d\nI\nY 3 %d\nC 4 %d\nZ 1\nR 2\nI\nY 5 %d\nF 5\nZ 0\nG\nI\n" %
+               (8 << 20, 16 << 20, 16 << 20, 32 << 20, 32 << 20, 8 << 20))
+
+
+def test_stream_ordered_and_vmm_allocations_are_charged(tmp_path):
+    """cuMemAllocAsync / cuMemCreate are forwarded UNACCOUNTED by the reference (@0x37e52, @0x37ba1),
+    so a PyTorch process (caching allocator on cuMemCreate, cudaMallocAsync pools) escapes its gpumem quota. Here they are
+    charged like cuMemAlloc: requested bytes, CUDA_ERROR_OUT_OF_MEMORY on breach, released on free."""
+    t = _write(tmp_path, _WIDE_TRACE)
+    out = run_replay(t, "new", _env(tmp_path, "64m", FAKE_GPU_CTX_MIB="16")).splitlines()
+    M = 1 << 20
+    f = lambda line, key: int(line.split(key + "=")[1].split()[0])
+    assert [f(l, "rc") for l in out[1:4]] == [0, 0, 0] and f(out[3], "buf") == 40 * M           # A 8 + Y 16 + C 16
+    assert out[4].endswith("free=%d total=%d" % (8 * M, 64 * M))                               # 64 - 16 ctx - 40
+    assert f(out[5], "rc") == 2 and f(out[6], "rc") == 2 and f(out[6], "buf") == 40 * M         # both breach: refused, uncharged
+    assert f(out[7], "rc") == 0 and f(out[8], "rc") == 0 and f(out[8], "buf") == 8 * M          # Z, R give the bytes back
+    assert out[9].endswith("free=%d total=%d" % (40 * M, 64 * M))
+    assert f(out[10], "rc") == 0 and f(out[11], "rc") == 0 and f(out[11], "buf") == 8 * M       # async alloc freed by cuMemFree_v2
+    assert f(out[12], "rc") == 0 and f(out[12], "buf") == 0                                     # cuMemAlloc'd pointer freed by cuMemFreeAsync
+    assert f(out[13], "rc") == 0                                                                # graph launch forwarded
+    assert f(out[14], "tot") == 16 * M
+
+
+def test_reference_coverage_switch_restores_the_reference_blind_spots(tmp_path):
+    t = _write(tmp_path, _WIDE_TRACE)
+    env = _env(tmp_path, "64m", FAKE_GPU_CTX_MIB="16", VGPU_REFERENCE_COVERAGE="1")
+    out = run_replay(t, "new", env).splitlines()
+    f = lambda line, key: int(line.split(key + "=")[1].split()[0])
+    assert all(f(l, "rc") == 0 for l in out[1:10]) and f(out[8], "buf") == 8 << 20     # only the cuMemAlloc is ever counted
+    if have_reference():
+        ref = run_replay(t, "reference", dict(env, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "ref.cache"))).splitlines()
+        # identical up to the two frees that cross allocator families (the reference answers -1 for pointers it never tracked)
+        assert out[:11] == ref[:11], (out[:11], ref[:11])
