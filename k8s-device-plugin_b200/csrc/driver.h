@@ -25,7 +25,7 @@ namespace vgpu {
     X(cuMemcpyDtoDAsync_v2) X(cuMemcpy) X(cuMemcpyAsync)                                                          \
     X(cuMemsetD8_v2) X(cuMemsetD16_v2) X(cuMemsetD32_v2) X(cuMemsetD8Async) X(cuMemsetD16Async)                   \
     X(cuMemsetD32Async)                                                                                           \
-    X(cuStreamCreate) X(cuStreamCreateWithPriority) X(cuCtxGetStreamPriorityRange) X(cuStreamDestroy_v2) X(cuStreamSynchronize) X(cuStreamWaitEvent) X(cuStreamQuery)          \
+    X(cuStreamCreate) X(cuStreamCreateWithPriority) X(cuCtxGetStreamPriorityRange) X(cuStreamDestroy_v2) X(cuStreamSynchronize) X(cuStreamWaitEvent) X(cuStreamQuery) X(cuStreamIsCapturing)          \
     X(cuEventCreate) X(cuEventRecord) X(cuEventSynchronize) X(cuEventQuery) X(cuEventElapsedTime)                 \
     X(cuEventDestroy_v2)                                                                                          \
     X(cuModuleLoadData) X(cuModuleGetFunction) X(cuModuleUnload) X(cuFuncSetAttribute) X(cuFuncGetParamInfo)      \

@@ -520,14 +520,39 @@ static void collect_launch_rows(SwapEngine *e, CUfunction f, void **params, void
     }
 }
 
+static bool stream_is_capturing(CUstream st) {
+    if (!drv().cuStreamIsCapturing) return false;
+    CUstreamCaptureStatus cs = CU_STREAM_CAPTURE_STATUS_NONE;
+    if (drv().cuStreamIsCapturing(st, &cs) != CUDA_SUCCESS) return false;   // legacy stream during a global capture: the launch itself will fail
+    return cs != CU_STREAM_CAPTURE_STATUS_NONE;
+}
+
 // Shared shape of every launch intercept: limiter gate -> swap admission -> real launch -> bookkeeping.
 template <typename RealLaunch>
 static CUresult guarded_launch(Runtime &rt, const Config &cfg, Limiter *lim, CUfunction f, void **params, void **extra,
                                CUstream st, RealLaunch real) {
-    if (lim) lim->before_launch(st);     // rate_limiter@0x4591a position: before the real launch
     SwapEngine *e = nullptr;
     thread_local std::vector<int> rows;
     rows.clear();
+    if ((lim || cfg.oversubscribe) && stream_is_capturing(st)) {
+        // Stream capture: nothing executes now, and a capturing stream may neither carry the limiter's stamp kernels
+        // (they would be replayed with every graph launch) nor wait on the engine's page-in events (capture
+        // isolation). The launch is billed when the graph runs (graph_launch); its swappable operands are made
+        // resident on the host's time and stay pinned, since a replay cannot fault them back in.
+        if (cfg.oversubscribe) {
+            CUdevice dev = -1;
+            if (drv().cuCtxGetDevice(&dev) == CUDA_SUCCESS) e = rt.swap((int)dev);
+            if (e) {
+                collect_launch_rows(e, f, params, extra, &rows);
+                if (!rows.empty()) {
+                    CUresult r = e->ensure_resident(rows.data(), (int)rows.size(), SwapEngine::kHostWait);
+                    if (r != CUDA_SUCCESS) return r;
+                }
+            }
+        }
+        return real();
+    }
+    if (lim) lim->before_launch(st);     // rate_limiter@0x4591a position: before the real launch
     if (cfg.oversubscribe) {
         CUdevice dev = -1;
         if (drv().cuCtxGetDevice(&dev) == CUDA_SUCCESS) e = rt.swap((int)dev);
@@ -719,6 +744,10 @@ void Runtime::touch_range2(CUdeviceptr a, size_t abytes, CUdeviceptr b, size_t b
     if (ra >= 0) rows[n++] = ra;
     if (rb >= 0 && rb != ra) rows[n++] = rb;
     if (!n) return;
+    if (stream_is_capturing(st)) {   // captured copy node: operands pinned resident, nothing recorded into the capture
+        if (e->ensure_resident(rows, n, SwapEngine::kHostWait) != CUDA_SUCCESS) LOG_ERROR("captured memcpy/memset target could not be made resident");
+        return;
+    }
     if (e->ensure_resident(rows, n, st) != CUDA_SUCCESS) { LOG_ERROR("memcpy/memset target could not be made resident"); return; }
     // the copy itself is enqueued by the caller right after this returns; note_use after it keeps the rows pinned
     t_touch_rows.assign(rows, rows + n);

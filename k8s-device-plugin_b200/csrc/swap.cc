@@ -906,6 +906,7 @@ CUresult SwapEngine::free(CUdeviceptr dptr) {
     for (uint64_t gidx = s.va_off / gran_; gidx < (s.va_off + s.mapped) / gran_; gidx++) owner_[gidx] = -1;
     va_free(s.va_off, s.mapped);
     live_bytes_ -= rows_[row].size;
+    s.pins = 0;                       // rows pinned for a stream capture are never unpinned by note_use
     rows_[row].state = VGPU_ST_FREE;
     rows_[row].size = 0;
     mark_dirty(row);
@@ -972,6 +973,7 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
     for (int i = 0; i < n; i++) {
         Side &s = side_[rows[i]];
         if (!s.ready) continue;
+        if (stream == kHostWait) d.cuEventSynchronize(s.ready);
         if (d.cuEventQuery(s.ready) == CUDA_SUCCESS) { ready_free_.push_back(s.ready); s.ready = nullptr; }
         else d.cuStreamWaitEvent(stream, s.ready, 0);
     }

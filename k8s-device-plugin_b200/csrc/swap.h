@@ -79,6 +79,10 @@ class SwapEngine {
 
     // Makes every listed row resident and orders `stream` after the page-ins. Rows stay pinned (not evictable)
     // until note_use() is called with the same list after the real launch has been enqueued.
+    // stream == kHostWait: block the calling thread until the rows are usable instead of ordering a stream behind the
+    // page-ins (stream capture: a capturing stream may not wait on outside work). Rows acquired this way and never
+    // passed to note_use() stay pinned resident — what a captured kernel's operands need.
+    static inline CUstream kHostWait = reinterpret_cast<CUstream>(~uintptr_t(0));
     CUresult ensure_resident(const int *rows, int n, CUstream stream);
     void note_use(const int *rows, int n, CUstream stream);
     // Scans kernel parameter bytes for pointers into the arena; appends distinct row indices.

@@ -24,6 +24,17 @@ def test_every_declared_symbol_is_exported_by_both_libraries():
             assert hasattr(lib, n), f"{n} missing from {so}"
 
 
+def test_every_header_under_include_is_fully_exported():
+    import glob
+    for hdr in sorted(glob.glob(os.path.join(ROOT, "include", "*.h"))):
+        text = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)
+        names = sorted(set(re.findall(r"\b(vgpu_[a-z0-9_]+)\s*\(", text)))
+        for so in (CORE_SO, HOOK_SO):
+            lib = C.CDLL(so, mode=C.RTLD_LOCAL)
+            missing = [n for n in names if not hasattr(lib, n)]
+            assert not missing, f"{os.path.basename(hdr)}: {missing} missing from {so}"
+
+
 def test_hook_library_exports_the_interposed_driver_surface():
     import subprocess
     syms = subprocess.run(["nm", "-D", "--defined-only", HOOK_SO], stdout=subprocess.PIPE, text=True).stdout

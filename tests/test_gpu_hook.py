@@ -163,3 +163,49 @@ def test_sm_limit_on_a_driver_api_launch_loop(tmp_path, mib, quota):
     lim = _launch_loop(env, mib)
     ratio = (lim["launches"] / lim["wall_s"]) / (bare["launches"] / bare["wall_s"])
     assert 0.75 * quota / 100 <= ratio <= 1.25 * quota / 100, (ratio, bare, lim)
+
+
+def _wide_probe(env_extra, seconds=4):
+    env = dict(os.environ)
+    env.pop("LD_PRELOAD", None)
+    env.update(env_extra)
+    r = subprocess.run([os.path.join(LIBDIR, "wide_probe"), CUBIN, str(seconds)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, timeout=200)
+    assert r.returncode == 0, r.stderr[-1500:] + r.stdout[-300:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_async_pool_and_vmm_allocations_count_against_the_quota(tmp_path):
+    """SURVEY.md §8(f) #4 on the real driver: cuMemAllocAsync and cuMemCreate are charged and refused like cuMemAlloc
+    (the reference forwards both unaccounted, so a PyTorch caching allocator escapes its quota there)."""
+    M = 1 << 20
+    bare = _wide_probe({}, seconds=1)
+    assert bare["async"]["rc"] == 0 and bare["async"]["rc_big"] == 0 and bare["vmm"]["rc_big"] == 0 and bare["vmm"]["data_ok"] == 1
+    out = _wide_probe(v.hook_env(limit_mib=2048, cache_path=str(tmp_path / "w.cache")), seconds=1)
+    assert out["async"] == {"rc": 0, "rc_big": 2, "rc_free": 0, "charged": 512 * M, "returned": 512 * M}
+    assert out["vmm"]["rc"] == 0 and out["vmm"]["rc_big"] == 2 and out["vmm"]["data_ok"] == 1
+    assert out["vmm"]["charged"] == out["vmm"]["returned"] and 512 * M <= out["vmm"]["charged"] < 520 * M
+    assert out["graph"]["word0"] == out["graph"]["expect_word0"]
+    off = _wide_probe(dict(v.hook_env(limit_mib=2048, cache_path=str(tmp_path / "r.cache")), VGPU_REFERENCE_COVERAGE="1"), seconds=1)
+    assert off["async"]["rc_big"] == 0 and off["vmm"]["rc_big"] == 0 and off["async"]["charged"] == 0
+
+
+def test_sm_limit_holds_a_replayed_cuda_graph_to_its_quota(tmp_path):
+    """A captured decode-style loop: capture must survive the limiter (no stamp kernels inside the capture), and the
+    replays are billed — graph launch RATE under a 30 % quota vs the bare rate. The reference has no hook on
+    cuGraphLaunch at all."""
+    bare = _wide_probe({}, seconds=3)
+    env = dict(v.hook_env(sm_limit=30, cache_path=str(tmp_path / "g.cache")), GPU_CORE_UTILIZATION_POLICY="force")
+    lim = _wide_probe(env, seconds=5)
+    assert lim["graph"]["word0"] == lim["graph"]["expect_word0"]
+    ratio = (lim["graph"]["launches"] / lim["graph"]["wall_s"]) / (bare["graph"]["launches"] / bare["graph"]["wall_s"])
+    assert 0.22 <= ratio <= 0.38, (ratio, bare, lim)
+
+
+def test_captured_kernels_keep_their_swappable_operands_resident(tmp_path):
+    """Swap mode + stream capture: the captured kernels' buffer lives in the swap arena; capture pins it resident (a
+    replay cannot fault), so every replay sees mapped memory and the arithmetic is exact."""
+    env = v.hook_env(limit_mib=4096, oversubscribe=True, cache_path=str(tmp_path / "s.cache"))
+    out = _wide_probe(env, seconds=1)
+    assert out["graph"]["word0"] == out["graph"]["expect_word0"] and out["graph"]["launches"] > 0
+    assert out["async"]["rc"] == 0 and out["vmm"]["data_ok"] == 1
