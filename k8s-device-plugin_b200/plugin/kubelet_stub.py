@@ -15,10 +15,12 @@ class KubeletStub:
         self.socket = os.path.join(socket_dir, "kubelet.sock")
         self.registered = threading.Event()
         self.request = None
+        self.registrations = []           # every RegisterRequest seen, in order
         self.server = None
 
     def _register(self, request, context):
         self.request = request
+        self.registrations.append(request)
         self.registered.set()
         return api.Empty()
 
