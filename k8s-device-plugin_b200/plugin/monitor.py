@@ -105,7 +105,7 @@ class Monitor:
                                f'data="{tot["buffer_size"]}",offset="{tot["offset"]}"}} {float(tot["total"])}')
         return "\n".join(out) + "\n"
 
-    def serve(self, port=9394):                         # metrics.go:309
+    def serve(self, port=9394, host="127.0.0.1"):       # metrics.go:309
         mon = self
 
         class H(BaseHTTPRequestHandler):
@@ -120,6 +120,6 @@ class Monitor:
             def log_message(self, *a):
                 pass
 
-        srv = HTTPServer(("127.0.0.1", port), H)
+        srv = HTTPServer((host, port), H)
         threading.Thread(target=srv.serve_forever, daemon=True).start()
         return srv
