@@ -69,6 +69,9 @@ int vgpu_region_set_hostpid(vgpu_region_handle_t *h, int32_t pid, int32_t hostpi
 /* publish a device identity in lane `dev` (the hook does this itself from NVML: put_device_info, multiprocess_memory_limit.c:L150) */
 int vgpu_region_set_uuid(vgpu_region_handle_t *h, int dev, const char *uuid);
 void *vgpu_region_raw(vgpu_region_handle_t *h);                                          /* vgpu_shared_region_t* */
+/* swap counters of the container on device `dev`, summed over its processes (extension block, vgpu_region.h). Returns 0,
+ * or -1 when the file carries no extension block (created by the reference hook). out->pid = number of records summed. */
+int vgpu_region_swap_counters(vgpu_region_handle_t *h, int dev, vgpu_swap_record_t *out);
 
 /* ---- node monitor feedback (reference: Observe cmd/vGPUmonitor/feedback.go:197-255, CheckBlocking :165-179, CheckPriority
  * :181-195). One pass over the regions of every container on the node: decrements recentKernel, counts active tasks per GPU

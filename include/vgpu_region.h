@@ -88,6 +88,32 @@ VGPU_STATIC_ASSERT(offsetof(vgpu_shared_region_t, recent_kernel) == 0xC4740, "re
 VGPU_STATIC_ASSERT(offsetof(vgpu_shared_region_t, priority) == 0xC4744, "priority @0x44702");
 VGPU_STATIC_ASSERT(sizeof(vgpu_shared_region_t) == VGPU_REGION_SIZE, "region file size");
 
+/*
+ * Extension block (not in the reference): swap-engine counters of the container, for the node monitor (SURVEY.md §8(f) #2
+ * "extend with swap counters via the new C ABI"). It lives in the SAME file, page-aligned behind the reference's region,
+ * so the directory contract of the reference monitor (at most two entries, checkfiles pathmonitor.go:38-71) and every
+ * reference offset above stay untouched; consumers that map VGPU_REGION_SIZE bytes never see it. One record per
+ * (process, device) that runs a swap engine; the owning process overwrites its record with relaxed stores, readers sum
+ * the records of a device. Records of exited processes are cleared together with their process slot.
+ */
+#define VGPU_REGION_EXT_OFFSET 0xC5000u
+#define VGPU_REGION_EXT_MAGIC 0x30303242u      /* "B200" */
+#define VGPU_REGION_EXT_RECORDS 1024
+typedef struct vgpu_swap_record {
+    int32_t pid;                               /* 0 = free */
+    int32_t dev;
+    uint64_t page_out_bytes, page_in_bytes;    /* cumulative */
+    uint64_t evictions, faults;                /* cumulative */
+    uint64_t resident_bytes, live_bytes, host_bytes;   /* gauges */
+} vgpu_swap_record_t;
+typedef struct vgpu_region_ext {
+    uint32_t magic, version;
+    uint64_t reserved[7];
+    vgpu_swap_record_t swap[VGPU_REGION_EXT_RECORDS];
+} vgpu_region_ext_t;
+VGPU_STATIC_ASSERT(sizeof(vgpu_swap_record_t) == 64, "swap record");
+VGPU_STATIC_ASSERT(VGPU_REGION_EXT_OFFSET >= VGPU_REGION_SIZE && VGPU_REGION_EXT_OFFSET % 4096 == 0, "extension placement");
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,12 @@ class ProcUsage(C.Structure):
                 ("used", DeviceMemory * MAX_DEVICES)]
 
 
+class SwapRecord(C.Structure):          # vgpu_swap_record_t (include/vgpu_region.h)
+    _fields_ = [("pid", C.c_int32), ("dev", C.c_int32), ("page_out_bytes", C.c_uint64), ("page_in_bytes", C.c_uint64),
+                ("evictions", C.c_uint64), ("faults", C.c_uint64), ("resident_bytes", C.c_uint64), ("live_bytes", C.c_uint64),
+                ("host_bytes", C.c_uint64)]
+
+
 class RegionSnapshot(C.Structure):
     _fields_ = [("initialized", C.c_int32), ("proc_num", C.c_int32), ("utilization_switch", C.c_int32),
                 ("recent_kernel", C.c_int32), ("priority", C.c_int32), ("_pad", C.c_int32),
@@ -89,6 +95,7 @@ ABI = {
     "vgpu_region_set_feedback": (_INT, [_P, _I32, _I32]),
     "vgpu_region_set_hostpid": (_INT, [_P, _I32, _I32]),
     "vgpu_region_set_uuid": (_INT, [_P, _INT, C.c_char_p]),
+    "vgpu_region_swap_counters": (_INT, [_P, _INT, _P]),
     "vgpu_region_raw": (_P, [_P]),
     "vgpu_monitor_observe": (_INT, [C.POINTER(_P), _INT]),
     "vgpu_pack": (_INT, [C.POINTER(Seg), C.c_size_t, _P]),
@@ -197,6 +204,14 @@ class Region:
 
     def set_uuid(self, dev, uuid):
         lib().vgpu_region_set_uuid(self._h, dev, uuid.encode())
+
+    def swap_counters(self, dev):
+        """Swap-engine counters of the container on `dev` (extension block of the region file), or None when the file has
+        none (written by the reference hook)."""
+        rec = SwapRecord()
+        if lib().vgpu_region_swap_counters(self._h, dev, C.byref(rec)) != 0:
+            return None
+        return {k: getattr(rec, k) for k, _ in SwapRecord._fields_ if k not in ("pid", "dev")} | {"processes": rec.pid}
 
     def set_feedback(self, recent_kernel=None, utilization_switch=None):
         keep = -(2 ** 31)

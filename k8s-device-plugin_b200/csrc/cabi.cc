@@ -99,6 +99,10 @@ VGPU_API int vgpu_region_set_uuid(vgpu_region_handle_t *h, int dev, const char *
     if (r->device_num < (uint64_t)dev + 1) r->device_num = (uint64_t)dev + 1;
     return 0;
 }
+VGPU_API int vgpu_region_swap_counters(vgpu_region_handle_t *h, int dev, vgpu_swap_record_t *out) {
+    if (!h || !out || dev < 0 || dev >= VGPU_MAX_DEVICES) return -1;
+    return h->r->swap_counters(dev, out) ? 0 : -1;
+}
 VGPU_API void *vgpu_region_raw(vgpu_region_handle_t *h) { return h ? h->r->raw() : nullptr; }
 
 // ------------------------------------------------------------------------------------------------ monitor feedback

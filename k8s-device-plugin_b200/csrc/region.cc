@@ -126,11 +126,81 @@ Region *Region::open(const char *path, bool create, const uint64_t *mem_limits, 
                          (unsigned long)sm_limits[d]);
         }
     }
+    // extension block: grow the file when it ends before it (first creator, or a file made by the reference hook)
+    {
+        const off_t need = (off_t)VGPU_REGION_EXT_OFFSET + (off_t)sizeof(vgpu_region_ext_t);
+        struct stat st2;
+        bool ok = fstat(fd, &st2) == 0 && (st2.st_size >= need || (create && ftruncate(fd, need) == 0));
+        if (ok) {
+            void *em = mmap(nullptr, sizeof(vgpu_region_ext_t), PROT_READ | PROT_WRITE, MAP_SHARED, fd, VGPU_REGION_EXT_OFFSET);
+            if (em != MAP_FAILED) {
+                R->ext_ = static_cast<vgpu_region_ext_t *>(em);
+                if (R->ext_->magic != VGPU_REGION_EXT_MAGIC) {
+                    if (create) {
+                        std::memset(R->ext_, 0, sizeof(vgpu_region_ext_t));
+                        R->ext_->version = 1;
+                        __atomic_thread_fence(__ATOMIC_SEQ_CST);
+                        R->ext_->magic = VGPU_REGION_EXT_MAGIC;
+                    } else {
+                        munmap(em, sizeof(vgpu_region_ext_t));
+                        R->ext_ = nullptr;
+                    }
+                }
+            }
+        }
+    }
     if (lockf(fd, F_ULOCK, VGPU_REGION_SIZE) != 0) {}
     return R;
 }
 
+vgpu_swap_record_t *Region::swap_record(int32_t pid, int dev) {
+    if (!ext_) return nullptr;
+    lock();
+    vgpu_swap_record_t *hit = nullptr, *empty = nullptr;
+    for (int i = 0; i < VGPU_REGION_EXT_RECORDS; i++) {
+        vgpu_swap_record_t &rec = ext_->swap[i];
+        if (rec.pid == pid && rec.dev == dev) { hit = &rec; break; }
+        if (!empty && rec.pid == 0) empty = &rec;
+    }
+    if (!hit && !empty) {          // full: records of dead processes are reclaimed with their slots
+        reap_dead_locked();
+        for (int i = 0; i < VGPU_REGION_EXT_RECORDS && !empty; i++)
+            if (ext_->swap[i].pid == 0) empty = &ext_->swap[i];
+    }
+    if (!hit && empty) {
+        std::memset(empty, 0, sizeof *empty);
+        empty->dev = dev;
+        __atomic_thread_fence(__ATOMIC_RELEASE);
+        empty->pid = pid;
+        hit = empty;
+    }
+    unlock();
+    return hit;
+}
+
+bool Region::swap_counters(int dev, vgpu_swap_record_t *out) {
+    std::memset(out, 0, sizeof *out);
+    out->dev = dev;
+    if (!ext_) return false;
+    for (int i = 0; i < VGPU_REGION_EXT_RECORDS; i++) {
+        const vgpu_swap_record_t &rec = ext_->swap[i];
+        if (rec.pid == 0 || rec.dev != dev) continue;
+        out->pid++;
+        out->page_out_bytes += rec.page_out_bytes; out->page_in_bytes += rec.page_in_bytes;
+        out->evictions += rec.evictions; out->faults += rec.faults;
+        out->resident_bytes += rec.resident_bytes; out->live_bytes += rec.live_bytes; out->host_bytes += rec.host_bytes;
+    }
+    return true;
+}
+
+void Region::clear_swap_records_locked(int32_t pid) {
+    if (!ext_) return;
+    for (int i = 0; i < VGPU_REGION_EXT_RECORDS; i++)
+        if (ext_->swap[i].pid == pid) std::memset(&ext_->swap[i], 0, sizeof(vgpu_swap_record_t));
+}
+
 Region::~Region() {
+    if (ext_) munmap(ext_, sizeof(vgpu_region_ext_t));
     if (r_) munmap(r_, VGPU_REGION_SIZE);
     if (fd_ >= 0) ::close(fd_);
 }
@@ -224,6 +294,7 @@ void Region::release_slot(int32_t pid) {
         }
         cached_slot_ = -1;
     }
+    clear_swap_records_locked(pid);
     unlock();
 }
 
@@ -256,6 +327,7 @@ int Region::reap_dead_locked() {
     for (int i = 0; i < r_->proc_num;) {
         int32_t p = r_->procs[i].pid;
         if (p != self && !pid_alive(p)) {
+            clear_swap_records_locked(p);
             int last = r_->proc_num - 1;
             if (i != last) std::memcpy(&r_->procs[i], &r_->procs[last], sizeof(vgpu_proc_slot_t));
             std::memset(&r_->procs[last], 0, sizeof(vgpu_proc_slot_t));

@@ -55,12 +55,22 @@ class Region {
     // drop slots whose pid no longer exists; returns how many were reclaimed (lock must be held)
     int reap_dead_locked();
 
+    // extension block (vgpu_region.h): nullptr when the file has none and cannot be grown
+    vgpu_region_ext_t *ext() { return ext_; }
+    // the (pid, dev) record, claimed on first use; nullptr when there is no extension block or it is full
+    vgpu_swap_record_t *swap_record(int32_t pid, int dev);
+    // sum of the live records of `dev`; out->pid = records summed. false: no extension block
+    bool swap_counters(int dev, vgpu_swap_record_t *out);
+
    private:
     Region() = default;
     int find_slot_locked(int32_t pid);
     uint64_t usage_locked(int dev) const;
 
+    void clear_swap_records_locked(int32_t pid);
+
     vgpu_shared_region_t *r_ = nullptr;
+    vgpu_region_ext_t *ext_ = nullptr;
     int fd_ = -1;
     std::string path_;
     int cached_slot_ = -1;

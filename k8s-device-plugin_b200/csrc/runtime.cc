@@ -287,6 +287,7 @@ CUresult Runtime::swap_alloc(CUdeviceptr *dptr, size_t bytes, int dev) {
             SwapConfig sc = SwapConfig::from_env(lim ? cap : 0, cfg_.virtual_limit[dev]);
             swap_[dev].reset(SwapEngine::create(dev, sc));
             if (!swap_[dev]) { LOG_ERROR("swap engine unavailable on device %d", dev); return CUDA_ERROR_NOT_SUPPORTED; }
+            if (region_) swap_[dev]->set_shared_record(region_->swap_record(pid_, dev));   // counters for the node monitor
         }
         e = swap_[dev].get();
     }

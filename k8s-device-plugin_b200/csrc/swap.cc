@@ -888,6 +888,7 @@ CUresult SwapEngine::alloc(CUdeviceptr *dptr, size_t bytes) {
     mark_dirty(row);
     live_bytes_ += bytes;
     *dptr = arena_ + off;
+    publish_locked();
     return CUDA_SUCCESS;
 }
 
@@ -911,6 +912,7 @@ CUresult SwapEngine::free(CUdeviceptr dptr) {
     rows_[row].size = 0;
     mark_dirty(row);
     free_rows_.push_back(row);
+    publish_locked();
     return CUDA_SUCCESS;
 }
 
@@ -977,6 +979,7 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
         if (d.cuEventQuery(s.ready) == CUDA_SUCCESS) { ready_free_.push_back(s.ready); s.ready = nullptr; }
         else d.cuStreamWaitEvent(stream, s.ready, 0);
     }
+    if (!missing.empty()) publish_locked();
     return CUDA_SUCCESS;
 }
 
@@ -996,6 +999,18 @@ void SwapEngine::note_use(const int *rows, int n, CUstream stream) {
             mark_dirty(rows[i]);
         }
     }
+}
+
+void SwapEngine::publish_locked() {
+    vgpu_swap_record_t *r = shared_;
+    if (!r) return;
+    __atomic_store_n(&r->page_out_bytes, st_.page_out_bytes, __ATOMIC_RELAXED);
+    __atomic_store_n(&r->page_in_bytes, st_.page_in_bytes, __ATOMIC_RELAXED);
+    __atomic_store_n(&r->evictions, st_.evictions, __ATOMIC_RELAXED);
+    __atomic_store_n(&r->faults, st_.faults, __ATOMIC_RELAXED);
+    __atomic_store_n(&r->resident_bytes, (uint64_t)resident_mapped_, __ATOMIC_RELAXED);
+    __atomic_store_n(&r->live_bytes, (uint64_t)live_bytes_, __ATOMIC_RELAXED);
+    __atomic_store_n(&r->host_bytes, (uint64_t)host_used_, __ATOMIC_RELAXED);
 }
 
 CUresult SwapEngine::drain() {

@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "vgpu_region.h"
 #include "kmod.h"
 
 namespace vgpu {
@@ -92,6 +93,9 @@ class SwapEngine {
     void set_profile(bool on) { cfg_.profile = on; }
     // the quota left for swappable memory shrinks/grows with the container's non-swappable bytes (context, small buffers)
     void set_resident_cap(uint64_t cap) { std::lock_guard<std::mutex> g(mu_); cfg_.resident_cap = cap; }
+    // publish the counters into the container's shared region (vgpu_region.h extension block) after every call that
+    // changes them; nullptr = do not publish
+    void set_shared_record(vgpu_swap_record_t *rec) { std::lock_guard<std::mutex> g(mu_); shared_ = rec; publish_locked(); }
     CUresult drain();                          // wait for all side-stream work (tests / shutdown)
     const SwapConfig &config() const { return cfg_; }
     uint64_t live_bytes() const { return live_bytes_; }
@@ -217,6 +221,8 @@ class SwapEngine {
     std::deque<Cand> victim_cache_;
     uint32_t scan_lookahead_ = 8;
     SwapStats st_;
+    vgpu_swap_record_t *shared_ = nullptr;
+    void publish_locked();
     struct Prof { CUevent a, b; bool unpack; uint64_t bytes; };
     CUdeviceptr d_span_ = 0;                        // profiling: {min start, max end} per launch, pre-set to {~0, 0}
     uint32_t span_cap_ = 0, span_next_ = 0, span_read_ = 0;

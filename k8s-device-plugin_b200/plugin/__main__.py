@@ -113,7 +113,7 @@ def main(argv=None):
                               [c.get("name", "") for c in (p.get("spec") or {}).get("containers") or []])
                     for p in kube.list_pods(sel).get("items") or []]
 
-        mon = M.Monitor(args.containers_path, list_pods)
+        mon = M.Monitor(args.containers_path, list_pods, host_gpus=M.nvml_host_gpus)
         mon.serve(args.port, host="0.0.0.0")
         while not stop.is_set():          # watchAndFeedback (feedback.go:257-270): every 5 s
             try:

@@ -31,6 +31,21 @@ def check_files(dirpath):
     return None
 
 
+def nvml_host_gpus():
+    """HostGPUMemoryUsage / HostCoreUtilization inputs through NVML (metrics.go:152-195)."""
+    import pynvml as nv
+    nv.nvmlInit()
+    try:
+        out = []
+        for i in range(nv.nvmlDeviceGetCount()):
+            h = nv.nvmlDeviceGetHandleByIndex(i)
+            uuid = nv.nvmlDeviceGetUUID(h)
+            out.append((i, uuid.decode() if isinstance(uuid, bytes) else uuid, nv.nvmlDeviceGetMemoryInfo(h).used, nv.nvmlDeviceGetUtilizationRates(h).gpu))
+        return out
+    finally:
+        nv.nvmlShutdown()
+
+
 class PodInfo:
     def __init__(self, uid, namespace, name, containers):
         self.uid, self.namespace, self.name, self.containers = uid, namespace, name, list(containers)
@@ -42,9 +57,10 @@ class Monitor:
 
     GC_SECONDS = 300                                   # pathmonitor.go:96
 
-    def __init__(self, containers_path, list_pods):
+    def __init__(self, containers_path, list_pods, host_gpus=None):
         self.path = containers_path
         self.list_pods = list_pods
+        self.host_gpus = host_gpus                     # () -> [(index, uuid, used_bytes, sm_util_percent)]; nvml_host_gpus on a GPU node
         self.regions = {}                              # dir -> (idstr, Region)
         self.lock = threading.Lock()
 
@@ -85,6 +101,9 @@ class Monitor:
         out = ["# HELP vGPU_device_memory_usage_in_bytes vGPU device usage", "# TYPE vGPU_device_memory_usage_in_bytes gauge",
                "# HELP vGPU_device_memory_limit_in_bytes vGPU device limit", "# TYPE vGPU_device_memory_limit_in_bytes gauge",
                "# HELP Device_memory_desc_of_container Container device meory description", "# TYPE Device_memory_desc_of_container counter"]
+        for idx, uuid, used, util in (self.host_gpus() if self.host_gpus else []):     # metrics.go:152-195 (NVML walk)
+            out.append(f'HostGPUMemoryUsage{{deviceidx="{idx}",deviceuuid="{uuid}"}} {float(used)}')
+            out.append(f'HostCoreUtilization{{deviceidx="{idx}",deviceuuid="{uuid}"}} {float(util)}')
         with self.lock:
             for idstr, region in self.regions.values():
                 parts = idstr.split("_")                 # parseidstr (metrics.go:108-115)
@@ -103,6 +122,13 @@ class Monitor:
                     out.append(f"vGPU_device_memory_limit_in_bytes{{{base}}} {float(snap.limit[i])}")
                     out.append(f'Device_memory_desc_of_container{{{base},context="{tot["context_size"]}",module="{tot["module_size"]}",'
                                f'data="{tot["buffer_size"]}",offset="{tot["offset"]}"}} {float(tot["total"])}')
+                    sw = region.swap_counters(i)         # extension: swap engine counters
+                    if sw and sw["processes"]:
+                        for key, name in (("page_out_bytes", "vGPU_swap_page_out_bytes_total"), ("page_in_bytes", "vGPU_swap_page_in_bytes_total"),
+                                          ("faults", "vGPU_swap_faults_total"), ("evictions", "vGPU_swap_evictions_total"),
+                                          ("resident_bytes", "vGPU_swap_resident_bytes"), ("live_bytes", "vGPU_swap_live_bytes"),
+                                          ("host_bytes", "vGPU_swap_host_pool_bytes")):
+                            out.append(f"{name}{{{base}}} {float(sw[key])}")
         return "\n".join(out) + "\n"
 
     def serve(self, port=9394, host="127.0.0.1"):       # metrics.go:309

@@ -103,3 +103,49 @@ def test_stale_container_dirs_are_collected_after_300_seconds(tmp_path):
     import pytest
     with pytest.raises(ValueError):
         M.check_files(str(three))                       # "cache num not matched"
+
+
+def test_swap_counter_extension_block_layout_and_export(tmp_path):
+    """The extension block sits page-aligned BEHIND the reference's 0xC4748-byte region in the same file: reference
+    offsets, the file name and the directory contract are untouched; the monitor sums the records of a device."""
+    import mmap
+    import struct
+    uid, ctr = "pod-uid-7", "main"
+    cdir = tmp_path / "containers" / f"{uid}_{ctr}"
+    cdir.mkdir(parents=True)
+    path = str(cdir / "x.cache")
+    r = v.Region(path, create=True, mem_limits=[8 << 30] + [0] * 15, sm_limits=[100] * 16, priority=1)
+    assert os.path.getsize(path) == 0xC5000 + 64 + 1024 * 64
+    assert r.swap_counters(0) == {"page_out_bytes": 0, "page_in_bytes": 0, "evictions": 0, "faults": 0, "resident_bytes": 0,
+                                  "live_bytes": 0, "host_bytes": 0, "processes": 0}
+    slot = r.claim(os.getpid())
+    assert slot == 0
+    with open(path, "r+b") as f:                                    # what two hooked processes of the container would publish
+        m = mmap.mmap(f.fileno(), 0)
+        assert struct.unpack_from("<II", m, 0xC5000) == (0x30303242, 1)
+        m[0xC5000 + 64:0xC5000 + 128] = struct.pack("<iiQQQQQQQ", os.getpid(), 0, 100, 200, 3, 4, 50, 60, 10)
+        m[0xC5000 + 128:0xC5000 + 192] = struct.pack("<iiQQQQQQQ", 999999, 0, 1, 2, 1, 1, 5, 6, 1)
+        m[0xC5000 + 192:0xC5000 + 256] = struct.pack("<iiQQQQQQQ", os.getpid(), 1, 7, 7, 7, 7, 7, 7, 7)
+        m.flush(); m.close()
+    assert r.swap_counters(0) == {"page_out_bytes": 101, "page_in_bytes": 202, "evictions": 4, "faults": 5, "resident_bytes": 55,
+                                  "live_bytes": 66, "host_bytes": 11, "processes": 2}
+    assert r.swap_counters(1)["page_out_bytes"] == 7
+    r.set_uuid(0, "GPU-x")
+    mon = M.Monitor(str(tmp_path / "containers"), lambda: [M.PodInfo(uid, "default", "train", [ctr])],
+                    host_gpus=lambda: [(0, "GPU-x", 123456, 42)])
+    text = mon.collect()
+    base = 'podnamespace="default",podname="train",ctrname="main",vdeviceid="0",deviceuuid="GPU-x"'
+    assert f"vGPU_swap_page_out_bytes_total{{{base}}} 101.0" in text and f"vGPU_swap_resident_bytes{{{base}}} 55.0" in text
+    assert 'HostGPUMemoryUsage{deviceidx="0",deviceuuid="GPU-x"} 123456.0' in text
+    assert 'HostCoreUtilization{deviceidx="0",deviceuuid="GPU-x"} 42.0' in text
+    # a process that exits takes its records with it (exit_handler path)
+    r.release(os.getpid())
+    assert r.swap_counters(0)["processes"] == 1 and r.swap_counters(1)["processes"] == 0
+    r.close()
+    # a region file written by the reference hook has no extension block: the monitor reports none, nothing breaks
+    small = tmp_path / "small.cache"
+    with open(path, "rb") as f:
+        small.write_bytes(f.read(0xC4748))
+    r2 = v.Region(str(small))
+    assert r2.swap_counters(0) is None and r2.snapshot().initialized == 1
+    r2.close()
