@@ -209,3 +209,42 @@ def test_captured_kernels_keep_their_swappable_operands_resident(tmp_path):
     out = _wide_probe(env, seconds=1)
     assert out["graph"]["word0"] == out["graph"]["expect_word0"] and out["graph"]["launches"] > 0
     assert out["async"]["rc"] == 0 and out["vmm"]["data_ok"] == 1
+
+
+def test_node_monitor_sees_the_swap_counters_of_a_running_container(tmp_path):
+    """The hook publishes its swap engine's counters into the extension block of the region file while the application
+    runs; the host-side monitor (another process, C ABI only) reads residency and page traffic from there."""
+    import time
+    cache = str(tmp_path / "live.cache")
+    env = dict(os.environ)
+    env.update(v.hook_env(limit_mib=2048, oversubscribe=True, cache_path=cache))
+    p = subprocess.Popen([os.path.join(LIBDIR, "swap_bench"), "--cubin", CUBIN, "--buffers", "64", "--mib", "64", "--steps", "400", "--warmup", "8",
+                          "--order", "cyclic"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    seen, region = [], None
+    try:
+        deadline = time.time() + 120
+        while p.poll() is None and time.time() < deadline:
+            if region is None and os.path.exists(cache):
+                try:
+                    region = v.Region(cache)
+                except OSError:
+                    region = None
+            if region is not None:
+                c = region.swap_counters(0)
+                if c and c["processes"]:
+                    seen.append(c)
+            time.sleep(0.05)
+        out, err = p.communicate(timeout=120)
+    finally:
+        if p.poll() is None:
+            p.kill()
+    assert p.returncode == 0, err[-2000:]
+    final = json.loads(out.strip().splitlines()[-1])
+    assert final["mismatches"] == 0
+    assert len(seen) > 5
+    assert max(c["page_out_bytes"] for c in seen) > 10 * (64 << 20) and max(c["page_in_bytes"] for c in seen) > 10 * (64 << 20)
+    assert all(c["resident_bytes"] <= 2048 << 20 for c in seen)                  # the quota bounds residency ...
+    assert max(c["live_bytes"] for c in seen) == 64 * (64 << 20)                 # ... not live bytes
+    assert [c["page_out_bytes"] for c in seen] == sorted(c["page_out_bytes"] for c in seen)
+    assert region.swap_counters(0)["processes"] == 0                              # the exiting process took its record along
+    region.close()
