@@ -260,62 +260,102 @@ extern "C" __global__ void __launch_bounds__(256) vgpu_victim_hist(const VgpuEnt
     if (threadIdx.x == 0) st->done_ctas = 0;
 }
 
-// Ordered compaction of rows with key <= K* (all candidates when insufficient). CTA b owns rows
-// [b*chunk, (b+1)*chunk) and receives its output offset from CTA b-1 (chained scan), so indices come out ascending.
-extern "C" __global__ void __launch_bounds__(256) vgpu_victim_emit(const VgpuEntry *__restrict__ tbl, uint32_t n,
-                                                                   VgpuScanState *st, uint32_t idx_bits,
-                                                                   uint32_t chunk, uint32_t *__restrict__ out_idx,
-                                                                   uint32_t out_cap) {
-    __shared__ uint32_t warp_cnt[8];
-    __shared__ uint32_t base_off;
+// Ordered compaction of rows with key <= K* (all candidates when insufficient), ascending row index, in two launches
+// and without any inter-CTA spinning: CTA b owns rows [b*chunk, (b+1)*chunk).
+//   count: every CTA publishes how many of its rows qualify (and their bytes); the last CTA to finish (atomic ticket)
+//          turns the per-CTA counts into exclusive offsets and the totals.
+//   emit : every CTA recounts per thread, scans inside the block and writes behind its offset.
+__device__ __forceinline__ bool victim_row(const VgpuEntry &e, uint32_t i, uint32_t idx_bits, bool all, bool none, uint64_t kstar) {
+    if (e.state != VGPU_ST_RESIDENT || none) return false;
+    return all || row_key(e, i, idx_bits) <= kstar;
+}
+
+extern "C" __global__ void __launch_bounds__(256) vgpu_victim_count(const VgpuEntry *__restrict__ tbl, uint32_t n,
+                                                                    VgpuScanState *st, uint32_t idx_bits, uint32_t chunk) {
+    __shared__ uint32_t blk_cnt;
     __shared__ unsigned long long blk_bytes;
+    __shared__ bool last;
+    __shared__ uint32_t part[256];
     const bool all = st->insufficient != 0;
     const uint64_t kstar = st->prefix;
     const bool none = (st->need == 0);
     const uint32_t lo = blockIdx.x * chunk;
     const uint32_t hi = min(n, lo + chunk);
-    if (threadIdx.x == 0) blk_bytes = 0;
+    if (threadIdx.x == 0) { blk_cnt = 0; blk_bytes = 0; }
+    __syncthreads();
+    uint32_t cnt = 0;
+    unsigned long long bytes = 0;
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {       // counting needs no order: coalesced stride
+        VgpuEntry e = load_row(tbl, i);
+        if (victim_row(e, i, idx_bits, all, none, kstar)) { cnt++; bytes += e.size; }
+    }
+    for (int d = 16; d; d >>= 1) { cnt += __shfl_down_sync(0xffffffffu, cnt, d); bytes += __shfl_down_sync(0xffffffffu, bytes, d); }
+    if ((threadIdx.x & 31) == 0 && cnt) { atomicAdd(&blk_cnt, cnt); atomicAdd(&blk_bytes, bytes); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->cta_off[blockIdx.x] = blk_cnt;
+        st->cta_bytes[blockIdx.x] = blk_bytes;
+        __threadfence();
+        last = (atomicAdd(&st->done_ctas, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // last CTA: exclusive scan of gridDim.x (<= 1024) counts; thread t owns entries [t*per, (t+1)*per)
+    volatile uint32_t *off = st->cta_off;
+    volatile uint64_t *cb = st->cta_bytes;
+    const uint32_t g = gridDim.x;
+    const uint32_t per = (g + blockDim.x - 1) / blockDim.x;
+    const uint32_t a = min(g, threadIdx.x * per), b = min(g, a + per);
+    uint32_t mine = 0;
+    unsigned long long mybytes = 0;
+    for (uint32_t k = a; k < b; k++) { mine += off[k]; mybytes += cb[k]; }
+    part[threadIdx.x] = mine;
+    __syncthreads();
+    for (int d = 1; d < 256; d <<= 1) {                                    // Hillis-Steele over 256 partials
+        uint32_t v = threadIdx.x >= (uint32_t)d ? part[threadIdx.x - d] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[threadIdx.x] - mine;
+    for (uint32_t k = a; k < b; k++) { uint32_t c = off[k]; off[k] = run; run += c; }
+    if (mybytes) atomicAdd(reinterpret_cast<unsigned long long *>(&st->out_freed), mybytes);
+    if (threadIdx.x == blockDim.x - 1) st->out_count = part[threadIdx.x];
+    if (threadIdx.x == 0) st->done_ctas = 0;
+}
+
+extern "C" __global__ void __launch_bounds__(256) vgpu_victim_emit(const VgpuEntry *__restrict__ tbl, uint32_t n,
+                                                                   VgpuScanState *st, uint32_t idx_bits,
+                                                                   uint32_t chunk, uint32_t *__restrict__ out_idx,
+                                                                   uint32_t out_cap) {
+    __shared__ uint32_t warp_cnt[8];
+    const bool all = st->insufficient != 0;
+    const uint64_t kstar = st->prefix;
+    const bool none = (st->need == 0);
+    const uint32_t lo = blockIdx.x * chunk;
+    const uint32_t hi = min(n, lo + chunk);
     // each thread owns a contiguous run of rows so that thread order == index order
     const uint32_t per = (chunk + blockDim.x - 1) / blockDim.x;
     const uint32_t tlo = min(hi, lo + threadIdx.x * per);
     const uint32_t thi = min(hi, tlo + per);
     uint32_t cnt = 0;
-    unsigned long long bytes = 0;
     for (uint32_t i = tlo; i < thi; i++) {
         VgpuEntry e = load_row(tbl, i);
-        if (e.state != VGPU_ST_RESIDENT || none) continue;
-        if (all || row_key(e, i, idx_bits) <= kstar) { cnt++; bytes += e.size; }
+        if (victim_row(e, i, idx_bits, all, none, kstar)) cnt++;
     }
-    // block exclusive scan of cnt
     uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t incl = cnt;
     for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
     if (lane == 31) warp_cnt[wid] = incl;
     __syncthreads();
-    uint32_t woff = 0, btotal = 0;
-    for (uint32_t w = 0; w < blockDim.x / 32; w++) { if (w < wid) woff += warp_cnt[w]; btotal += warp_cnt[w]; }
-    if (bytes) atomicAdd(&blk_bytes, bytes);
-    if (threadIdx.x == 0) {
-        // wait for predecessor: chain_flag counts CTAs that have published
-        volatile uint32_t *flag = &st->chain_flag;
-        while (*flag != blockIdx.x) { __nanosleep(20); }
-        __threadfence();
-        base_off = st->chain_offset;
-    }
-    __syncthreads();
-    uint32_t o = base_off + woff + (incl - cnt);
+    uint32_t woff = 0;
+    for (uint32_t w = 0; w < wid; w++) woff += warp_cnt[w];
+    uint32_t o = st->cta_off[blockIdx.x] + woff + (incl - cnt);
+    if (!cnt) return;
     for (uint32_t i = tlo; i < thi; i++) {
         VgpuEntry e = load_row(tbl, i);
-        if (e.state != VGPU_ST_RESIDENT || none) continue;
-        if (all || row_key(e, i, idx_bits) <= kstar) { if (o < out_cap) out_idx[o] = i; o++; }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        st->chain_offset = base_off + btotal;
-        st->out_freed += blk_bytes;
-        if (blockIdx.x == gridDim.x - 1) st->out_count = base_off + btotal;
-        __threadfence();
-        st->chain_flag = blockIdx.x + 1;
+        if (victim_row(e, i, idx_bits, all, none, kstar)) { if (o < out_cap) out_idx[o] = i; o++; }
     }
 }
 

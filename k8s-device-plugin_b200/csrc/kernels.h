@@ -45,6 +45,7 @@ typedef struct VgpuPackParams {
     VgpuPackSeg seg[VGPU_PACK_MAX_SEG];
 } VgpuPackParams;
 
+#define VGPU_SCAN_MAX_CTAS 1024u       /* grid of the scan launches is capped at min(this, 4 x SMs) */
 typedef struct VgpuScanState {
     uint64_t prefix;                       /* selected high digits of K* so far */
     uint64_t need_left;
@@ -58,4 +59,7 @@ typedef struct VgpuScanState {
     uint32_t chain_offset;
     uint32_t _pad;
     uint64_t hist[VGPU_SCAN_BINS];
+    /* ordered emit: per-CTA victim counts, turned into exclusive offsets by the last CTA of the count launch */
+    uint32_t cta_off[VGPU_SCAN_MAX_CTAS];
+    uint64_t cta_bytes[VGPU_SCAN_MAX_CTAS];
 } VgpuScanState;

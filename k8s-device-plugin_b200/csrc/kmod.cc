@@ -49,7 +49,7 @@ const Kernels *kernels_for_current_ctx() {
     }
     struct { const char *name; CUfunction *fn; } tab[] = {
         {"vgpu_pack_tma", &k->pack_tma}, {"vgpu_pack_generic", &k->pack_generic},
-        {"vgpu_victim_init", &k->victim_init}, {"vgpu_victim_hist", &k->victim_hist}, {"vgpu_victim_emit", &k->victim_emit},
+        {"vgpu_victim_init", &k->victim_init}, {"vgpu_victim_hist", &k->victim_hist}, {"vgpu_victim_emit", &k->victim_emit}, {"vgpu_victim_count", &k->victim_count},
         {"vgpu_stamp", &k->stamp}, {"vgpu_wl_fill", &k->wl_fill}, {"vgpu_wl_touch", &k->wl_touch},
         {"vgpu_wl_verify", &k->wl_verify}, {"vgpu_wl_empty", &k->wl_empty},
     };
@@ -170,11 +170,12 @@ CUresult VictimScanner::scan(CUdeviceptr d_tbl, uint32_t n, uint64_t need, uint6
         if ((r = d.cuLaunchKernel(k_->victim_init, 1, 1, 1, 256, 1, 1, 0, stream, a, nullptr)) != CUDA_SUCCESS) return r;
         launches++;
     }
-    // grid sized so that every CTA is co-resident (the emit kernel's chained scan relies on in-order progress)
+    // one CTA per 2048 rows, capped at 4 CTAs per SM and at the per-CTA offset table of the ordered emit
     uint32_t rows_per_cta = 256 * 8;
     uint32_t grid = (n + rows_per_cta - 1) / rows_per_cta;
     uint32_t max_grid = (uint32_t)k_->sm_count * 4;
     if (grid > max_grid) grid = max_grid;
+    if (grid > VGPU_SCAN_MAX_CTAS) grid = VGPU_SCAN_MAX_CTAS;
     if (grid == 0) grid = 1;
     for (int hi = (int)key_bits; hi > 0; hi -= VGPU_SCAN_DIGIT_BITS) {
         uint32_t shift = hi > VGPU_SCAN_DIGIT_BITS ? (uint32_t)(hi - VGPU_SCAN_DIGIT_BITS) : 0u;
@@ -184,6 +185,11 @@ CUresult VictimScanner::scan(CUdeviceptr d_tbl, uint32_t n, uint64_t need, uint6
         launches++;
     }
     uint32_t chunk = (n + grid - 1) / grid;
+    {
+        void *a[] = {&d_tbl, &n, &d_state_, &idx_bits, &chunk};
+        if ((r = d.cuLaunchKernel(k_->victim_count, grid, 1, 1, 256, 1, 1, 0, stream, a, nullptr)) != CUDA_SUCCESS) return r;
+        launches++;
+    }
     {
         void *a[] = {&d_tbl, &n, &d_state_, &idx_bits, &chunk, &d_out_, &cap_};
         if ((r = d.cuLaunchKernel(k_->victim_emit, grid, 1, 1, 256, 1, 1, 0, stream, a, nullptr)) != CUDA_SUCCESS) return r;
