@@ -183,12 +183,14 @@ def run_engine_arm(torch, v, nbuf, steps, warmup, barrier):
     s0 = sw.stats()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.nvtx.range_push("timed")        # lets `ncu --nvtx --nvtx-include "timed/"` list exactly these launches
     e0.record()
     for _ in range(steps):
         step()
     e1.record()
     torch.cuda.synchronize()
     sw.drain()
+    torch.cuda.nvtx.range_pop()
     barrier()
     ms = e0.elapsed_time(e1)
     s1 = sw.stats()

@@ -210,13 +210,25 @@ extern "C" __global__ void __launch_bounds__(256) vgpu_victim_hist(const VgpuEnt
     const uint64_t prefix = st->prefix;
     const uint32_t hi = shift + width;
     const uint32_t mask = (1u << width) - 1u;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        VgpuEntry e = load_row(tbl, i);
-        if (e.state != VGPU_ST_RESIDENT) continue;
-        uint64_t key = row_key(e, i, idx_bits);
-        uint64_t top = hi >= 64 ? 0 : (key >> hi);
-        if (top != prefix) continue;
-        atomicAdd(&hist[static_cast<uint32_t>(key >> shift) & mask], static_cast<unsigned long long>(e.size));
+    // four independent row loads in flight per thread before any of them is consumed (memory-level parallelism: one
+    // 32-byte row per thread per trip leaves the SM far below the bytes in flight HBM3e needs)
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        VgpuEntry e[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            uint32_t i = i0 + u * stride;
+            if (i < n) e[u] = load_row(tbl, i); else e[u].state = VGPU_ST_FREE;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            uint32_t i = i0 + u * stride;
+            if (e[u].state != VGPU_ST_RESIDENT) continue;
+            uint64_t key = row_key(e[u], i, idx_bits);
+            uint64_t top = hi >= 64 ? 0 : (key >> hi);
+            if (top != prefix) continue;
+            atomicAdd(&hist[static_cast<uint32_t>(key >> shift) & mask], static_cast<unsigned long long>(e[u].size));
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < VGPU_SCAN_BINS; i += blockDim.x)
@@ -285,9 +297,16 @@ extern "C" __global__ void __launch_bounds__(256) vgpu_victim_count(const VgpuEn
     __syncthreads();
     uint32_t cnt = 0;
     unsigned long long bytes = 0;
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {       // counting needs no order: coalesced stride
-        VgpuEntry e = load_row(tbl, i);
-        if (victim_row(e, i, idx_bits, all, none, kstar)) { cnt++; bytes += e.size; }
+    for (uint32_t i0 = lo + threadIdx.x; i0 < hi; i0 += 4 * blockDim.x) {  // counting needs no order: coalesced stride, 4 loads in flight
+        VgpuEntry e[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            uint32_t i = i0 + u * blockDim.x;
+            if (i < hi) e[u] = load_row(tbl, i); else e[u].state = VGPU_ST_FREE;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (victim_row(e[u], i0 + u * blockDim.x, idx_bits, all, none, kstar)) { cnt++; bytes += e[u].size; }
     }
     for (int d = 16; d; d >>= 1) { cnt += __shfl_down_sync(0xffffffffu, cnt, d); bytes += __shfl_down_sync(0xffffffffu, bytes, d); }
     if ((threadIdx.x & 31) == 0 && cnt) { atomicAdd(&blk_cnt, cnt); atomicAdd(&blk_bytes, bytes); }

@@ -173,7 +173,7 @@ CUresult VictimScanner::scan(CUdeviceptr d_tbl, uint32_t n, uint64_t need, uint6
     // one CTA per 2048 rows, capped at 4 CTAs per SM and at the per-CTA offset table of the ordered emit
     uint32_t rows_per_cta = 256 * 8;
     uint32_t grid = (n + rows_per_cta - 1) / rows_per_cta;
-    uint32_t max_grid = (uint32_t)k_->sm_count * 4;
+    uint32_t max_grid = (uint32_t)k_->sm_count * 8;   // 8 x 256 threads fill an SM
     if (grid > max_grid) grid = max_grid;
     if (grid > VGPU_SCAN_MAX_CTAS) grid = VGPU_SCAN_MAX_CTAS;
     if (grid == 0) grid = 1;

@@ -129,8 +129,14 @@ void Runtime::on_fork_child() {
     {
         std::lock_guard<std::mutex> g(table_mu_);
         table_.clear();
+        phys_.clear();
     }
     for (auto &c : ctx_charged_) c = false;
+    // engines and the limiter own streams, events and threads of the PARENT's contexts: drop them without running
+    // destructors (CUDA state does not survive fork); the child builds its own on first use
+    for (auto &e : swap_) (void)e.release();
+    (void)limiter_.release();
+    post_inited_.store(false, std::memory_order_release);
     if (region_) region_->claim_slot(pid_);
 }
 
