@@ -27,7 +27,7 @@ def pytest_configure(config):
 
 def _build_once():
     # the driver runs build() before the tests; when a developer runs pytest directly make sure the natives exist
-    need = [HOOK_SO, CORE_SO, os.path.join(OREF, "oracle_replay"), os.path.join(OREF, "trace_replay"),
+    need = [HOOK_SO, CORE_SO, os.path.join(OREF, "oracle_replay"), os.path.join(OREF, "trace_replay"), os.path.join(OREF, "hook_stress"),
             os.path.join(FAKE, "libcuda.so.1"), os.path.join(OREF, "libvgpu_oracle.so")]
     if all(os.path.exists(p) for p in need):
         return
@@ -51,7 +51,7 @@ def run_replay(trace_path, mode, env_extra=None, fake=True, timeout=600):
     if mode == "oracle":
         cmd = [os.path.join(OREF, "oracle_replay"), trace_path]
     else:
-        cmd = [os.path.join(OREF, "trace_replay"), trace_path]
+        cmd = [os.path.join(OREF, "trace_replay"), os.path.join(OREF, "hook_stress"), trace_path]
         if mode == "reference":
             os.makedirs("/tmp/vgpulock", exist_ok=True)
             env["LD_PRELOAD"] = SHIM_SO + ":" + REF_SO
