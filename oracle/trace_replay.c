@@ -15,6 +15,7 @@
  *   I (cuMemGetInfo_v2) | T (cuDeviceTotalMem_v2) | L gx gy gz (cuLaunchKernel of an empty kernel) | S ms (sleep)
  *   Y id size (cuMemAllocAsync) | Z id (cuMemFreeAsync) | C id size (cuMemCreate on device 0) | R id (cuMemRelease)
  *   G (cuGraphLaunch of a null graph — only meaningful on the fake driver)
+ *   D n (make device n's primary context current; the counters printed from then on are device n's lane)
  * Output line: "<op#> <opcode> rc=<int> ctx=<u64> mod=<u64> buf=<u64> off=<u64> tot=<u64> [free=.. total=..]"
  * where the five counters are SUMMED over every process slot of device 0 (== own slot for one process).
  */
@@ -123,6 +124,8 @@ int main(int argc, char **argv) {
 
     char line[256];
     unsigned long opn = 0;
+    int cur = 0;                       /* device whose lane is reported */
+    CUcontext ctxs[16] = {ctx};
     while (fgets(line, sizeof line, tf)) {
         char op; unsigned long long a = 0, b = 0, d = 0;
         if (line[0] == '#' || line[0] == '\n') continue;
@@ -139,6 +142,11 @@ int main(int argc, char **argv) {
         case 'T': r = cuDeviceTotalMem_v2(&tot, dev); fr = 0; has_info = 1; break;
         case 'L': r = cuLaunchKernel(fn, (unsigned)a, (unsigned)b, (unsigned)d, 1, 1, 1, 0, NULL, NULL, NULL); break;
         case 'S': usleep((useconds_t)a * 1000); r = 0; break;   /* sleep a ms (multi-process tests) */
+        case 'D': { int n2 = (int)a & 15; CUdevice d2; r = cuDeviceGet(&d2, n2);
+                    if (!r && !ctxs[n2]) r = cuDevicePrimaryCtxRetain(&ctxs[n2], d2);
+                    if (!r) r = cuCtxSetCurrent(ctxs[n2]);
+                    if (!r) { cur = n2; dev = d2; }
+                    break; }
         case 'Y': ptrs[a] = 0; r = cuMemAllocAsync ? cuMemAllocAsync(&ptrs[a], (size_t)b, NULL) : 801; if (r) ptrs[a] = 0; break;
         case 'Z': r = cuMemFreeAsync ? cuMemFreeAsync(ptrs[a], NULL) : 801; if (!r) ptrs[a] = 0; break;
         case 'C': { struct mem_prop pr; memset(&pr, 0, sizeof pr); pr.type = 1 /* PINNED */; pr.location.type = 1 /* DEVICE */; pr.location.id = 0;
@@ -147,7 +155,7 @@ int main(int argc, char **argv) {
         case 'G': r = cuGraphLaunch ? cuGraphLaunch(NULL, NULL) : 801; break;
         default: continue;
         }
-        counters(0, c);
+        counters(cur, c);
         printf("%lu %c rc=%d ctx=%lu mod=%lu buf=%lu off=%lu tot=%lu", opn, op, r, c[0], c[1], c[2], c[3], c[4]);
         if (has_info) {
             /* free/total only compared when the hook owns them (limit set): the reference reports the

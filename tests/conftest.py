@@ -51,7 +51,7 @@ def run_replay(trace_path, mode, env_extra=None, fake=True, timeout=600):
     if mode == "oracle":
         cmd = [os.path.join(OREF, "oracle_replay"), trace_path]
     else:
-        cmd = [os.path.join(OREF, "trace_replay"), os.path.join(OREF, "hook_stress"), trace_path]
+        cmd = [os.path.join(OREF, "trace_replay"), trace_path]
         if mode == "reference":
             os.makedirs("/tmp/vgpulock", exist_ok=True)
             env["LD_PRELOAD"] = SHIM_SO + ":" + REF_SO

@@ -189,3 +189,20 @@ def test_reference_coverage_switch_restores_the_reference_blind_spots(tmp_path):
         ref = run_replay(t, "reference", dict(env, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "ref.cache"))).splitlines()
         # identical up to the two frees that cross allocator families (the reference answers -1 for pointers it never tracked)
         assert out[:11] == ref[:11], (out[:11], ref[:11])
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
+def test_two_device_container_lanes_match_the_reference_binary(tmp_path):
+    """A container holding two vGPUs: CUDA_DEVICE_MEMORY_LIMIT_0 / _1 (server.go:343-345), one usage lane per device in
+    the region. Allocations, breaches and cuMemGetInfo on either device — the stream equals the reference binary's."""
+    M = 1 << 20
+    t = _write(tmp_path, "\n".join([
+        "A 0 %d" % (8 * M), "I", "D 1", "I", "A 1 %d" % (8 * M), "A 2 %d" % (8 * M), "A 3 %d" % (8 * M), "I", "T",
+        "D 0", "A 4 %d" % (30 * M), "A 5 %d" % (30 * M), "I", "T", "F 0", "D 1", "F 1", "F 2", "I", "M 6 %d" % (20 * M), "M 7 %d" % (20 * M), "D 0", "I"]) + "\n")
+    env = _env(tmp_path, None, CUDA_DEVICE_MEMORY_LIMIT_0="64m", CUDA_DEVICE_MEMORY_LIMIT_1="32m", FAKE_GPU_COUNT="2", FAKE_GPU_CTX_MIB="16")
+    new = run_replay(t, "new", env).splitlines()
+    ref = run_replay(t, "reference", dict(env, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "ref.cache"))).splitlines()
+    assert new == ref, "\n".join(f"{a}   |   {b}" for a, b in zip(new, ref) if a != b)
+    f = lambda line, key: int(line.split(key + "=")[1].split()[0])
+    assert f(new[7], "rc") == -1 and new[8].endswith("free=0 total=%d" % (32 * M))      # device 1: 16 ctx + 8 + 8 fills 32m, the third 8 MiB is refused
+    assert f(new[12], "rc") == -1 and f(new[11], "rc") == 0                             # device 0: 16 + 8 + 30 fits 64m, another 30 does not
