@@ -378,6 +378,105 @@ extern "C" __global__ void __launch_bounds__(256) vgpu_victim_emit(const VgpuEnt
     }
 }
 
+// Whole scan in ONE launch for the tables a container really has (<= 8192 rows; SURVEY.md §8a6: 10^2-10^4 live
+// entries): one CTA of 1024 threads keeps its 8 rows per thread in registers (key + size), runs every radix digit
+// against a shared-memory histogram with __syncthreads between digits, then scans and emits in row order. Same
+// selection rule and outputs as the multi-launch path above; replaces 7 launches (init, 4 digits, count, emit) by one.
+extern "C" __global__ void __launch_bounds__(1024) vgpu_victim_small(const VgpuEntry *__restrict__ tbl, uint32_t n, VgpuScanState *st,
+                                                                     uint64_t need, uint32_t idx_bits, uint32_t key_bits,
+                                                                     uint32_t *__restrict__ out_idx, uint32_t out_cap) {
+    constexpr int R = VGPU_SCAN_SMALL_ROWS_PER_THREAD;
+    __shared__ unsigned long long hist[VGPU_SCAN_BINS];
+    __shared__ uint64_t s_prefix, s_need_left, s_cand;
+    __shared__ uint32_t s_insufficient;
+    __shared__ uint32_t warp_cnt[32];
+    __shared__ unsigned long long s_bytes;
+    uint64_t key[R], size[R];
+    uint32_t valid = 0;
+    const uint32_t base = threadIdx.x * R;
+#pragma unroll
+    for (int u = 0; u < R; u++) {
+        uint32_t i = base + u;
+        key[u] = 0; size[u] = 0;
+        if (i < n) {
+            VgpuEntry e = load_row(tbl, i);
+            if (e.state == VGPU_ST_RESIDENT) { valid |= 1u << u; key[u] = row_key(e, i, idx_bits); size[u] = e.size; }
+        }
+    }
+    if (threadIdx.x == 0) { s_prefix = 0; s_need_left = need; s_insufficient = 0; s_bytes = 0; s_cand = 0; }
+    __syncthreads();
+    for (int hi = (int)key_bits; hi > 0; hi -= VGPU_SCAN_DIGIT_BITS) {
+        const uint32_t shift = hi > VGPU_SCAN_DIGIT_BITS ? (uint32_t)(hi - VGPU_SCAN_DIGIT_BITS) : 0u;
+        const uint32_t width = (uint32_t)hi - shift;
+        const uint32_t mask = (1u << width) - 1u;
+        for (int i = threadIdx.x; i < VGPU_SCAN_BINS; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        const uint64_t prefix = s_prefix;
+#pragma unroll
+        for (int u = 0; u < R; u++) {
+            if (!(valid >> u & 1u)) continue;
+            uint64_t top = hi >= 64 ? 0 : (key[u] >> hi);
+            if (top != prefix) continue;
+            atomicAdd(&hist[static_cast<uint32_t>(key[u] >> shift) & mask], static_cast<unsigned long long>(size[u]));
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {       // warp 0 picks the digit: lane l owns bins [l*64, l*64+64)
+            constexpr int PER = VGPU_SCAN_BINS / 32;
+            volatile unsigned long long *gh = hist;
+            uint64_t mine = 0;
+            for (int j = 0; j < PER; j++) mine += gh[threadIdx.x * PER + j];
+            uint64_t incl = mine;
+            for (int d = 1; d < 32; d <<= 1) {
+                uint64_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (static_cast<int>(threadIdx.x) >= d) incl += o;
+            }
+            uint64_t excl = incl - mine;
+            uint64_t total = __shfl_sync(0xffffffffu, incl, 31);
+            uint64_t nl = s_need_left;
+            if (total < nl) {
+                if (threadIdx.x == 0) { s_insufficient = 1; s_cand = total; }
+            } else if (excl < nl && nl <= incl) {
+                uint64_t cum = excl;
+                int b = threadIdx.x * PER;
+                for (int j = 0; j < PER; j++, b++) {
+                    uint64_t h = gh[b];
+                    if (cum + h >= nl) break;
+                    cum += h;
+                }
+                s_prefix = (prefix << width) | static_cast<uint64_t>(b);
+                s_need_left = nl - cum;
+            }
+        }
+        __syncthreads();
+        if (s_insufficient) break;    // uniform: read after the barrier
+    }
+    const bool all = s_insufficient != 0;
+    const uint64_t kstar = s_prefix;
+    uint32_t cnt = 0;
+    unsigned long long bytes = 0;
+    uint32_t pick = 0;
+#pragma unroll
+    for (int u = 0; u < R; u++)
+        if ((valid >> u & 1u) && (all || key[u] <= kstar)) { pick |= 1u << u; cnt++; bytes += size[u]; }
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = cnt;
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+    for (int d = 16; d; d >>= 1) bytes += __shfl_down_sync(0xffffffffu, bytes, d);
+    if (lane == 31) warp_cnt[wid] = incl;
+    if (lane == 0 && bytes) atomicAdd(&s_bytes, bytes);
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+    for (uint32_t w = 0; w < blockDim.x / 32; w++) { if (w < wid) woff += warp_cnt[w]; total += warp_cnt[w]; }
+    uint32_t o = woff + (incl - cnt);
+#pragma unroll
+    for (int u = 0; u < R; u++)
+        if (pick >> u & 1u) { if (o < out_cap) out_idx[o] = base + u; o++; }
+    if (threadIdx.x == 0) {
+        st->prefix = kstar; st->need = need; st->need_left = s_need_left; st->cand_bytes = s_cand;
+        st->insufficient = s_insufficient; st->out_count = total; st->out_freed = s_bytes; st->done_ctas = 0;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ limiter stamp
 extern "C" __global__ void vgpu_stamp(uint64_t *slot) {
     uint64_t t = globaltimer();

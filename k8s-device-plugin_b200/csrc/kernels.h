@@ -45,6 +45,8 @@ typedef struct VgpuPackParams {
     VgpuPackSeg seg[VGPU_PACK_MAX_SEG];
 } VgpuPackParams;
 
+#define VGPU_SCAN_SMALL_ROWS_PER_THREAD 8u  /* single-CTA scan: 1024 threads x 8 rows held in registers */
+#define VGPU_SCAN_SMALL_MAX_ROWS 8192u
 #define VGPU_SCAN_MAX_CTAS 1024u       /* grid of the scan launches is capped at min(this, 4 x SMs) */
 typedef struct VgpuScanState {
     uint64_t prefix;                       /* selected high digits of K* so far */

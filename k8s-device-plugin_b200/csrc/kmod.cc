@@ -49,7 +49,7 @@ const Kernels *kernels_for_current_ctx() {
     }
     struct { const char *name; CUfunction *fn; } tab[] = {
         {"vgpu_pack_tma", &k->pack_tma}, {"vgpu_pack_generic", &k->pack_generic},
-        {"vgpu_victim_init", &k->victim_init}, {"vgpu_victim_hist", &k->victim_hist}, {"vgpu_victim_emit", &k->victim_emit}, {"vgpu_victim_count", &k->victim_count},
+        {"vgpu_victim_init", &k->victim_init}, {"vgpu_victim_hist", &k->victim_hist}, {"vgpu_victim_emit", &k->victim_emit}, {"vgpu_victim_count", &k->victim_count}, {"vgpu_victim_small", &k->victim_small},
         {"vgpu_stamp", &k->stamp}, {"vgpu_wl_fill", &k->wl_fill}, {"vgpu_wl_touch", &k->wl_touch},
         {"vgpu_wl_verify", &k->wl_verify}, {"vgpu_wl_empty", &k->wl_empty},
     };
@@ -165,6 +165,12 @@ CUresult VictimScanner::scan(CUdeviceptr d_tbl, uint32_t n, uint64_t need, uint6
     uint32_t key_bits = idx_bits + touch_bits;
     int launches = 0;
     CUresult r;
+    if (n <= VGPU_SCAN_SMALL_MAX_ROWS && k_->victim_small) {
+        // the whole scan in one launch: a single 1024-thread CTA with its rows in registers (kernels.cu)
+        void *a[] = {&d_tbl, &n, &d_state_, &need, &idx_bits, &key_bits, &d_out_, &cap_};
+        if ((r = d.cuLaunchKernel(k_->victim_small, 1, 1, 1, 1024, 1, 1, 0, stream, a, nullptr)) != CUDA_SUCCESS) return r;
+        launches++;
+    } else {
     {
         void *a[] = {&d_state_, &need};
         if ((r = d.cuLaunchKernel(k_->victim_init, 1, 1, 1, 256, 1, 1, 0, stream, a, nullptr)) != CUDA_SUCCESS) return r;
@@ -194,6 +200,7 @@ CUresult VictimScanner::scan(CUdeviceptr d_tbl, uint32_t n, uint64_t need, uint6
         void *a[] = {&d_tbl, &n, &d_state_, &idx_bits, &chunk, &d_out_, &cap_};
         if ((r = d.cuLaunchKernel(k_->victim_emit, grid, 1, 1, 256, 1, 1, 0, stream, a, nullptr)) != CUDA_SUCCESS) return r;
         launches++;
+    }
     }
     if (launches_out) *launches_out += launches;
     if ((r = d.cuMemcpyDtoHAsync_v2(h_state_, d_state_, 64, stream)) != CUDA_SUCCESS) return r;

@@ -13,7 +13,7 @@ namespace vgpu {
 struct Kernels {
     CUmodule mod = nullptr;
     CUfunction pack_tma = nullptr, pack_generic = nullptr;
-    CUfunction victim_init = nullptr, victim_hist = nullptr, victim_emit = nullptr, victim_count = nullptr;
+    CUfunction victim_init = nullptr, victim_hist = nullptr, victim_emit = nullptr, victim_count = nullptr, victim_small = nullptr;
     CUfunction stamp = nullptr;
     CUfunction wl_fill = nullptr, wl_touch = nullptr, wl_verify = nullptr, wl_empty = nullptr;
     int sm_count = 0;

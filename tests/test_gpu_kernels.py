@@ -143,6 +143,15 @@ def test_victim_scan_matches_oracle_small_tables(ora):
             _scan_case(ora, n, need, seed)
 
 
+def test_victim_scan_single_launch_path_and_its_boundary(ora):
+    # <= 8192 rows: one 1024-thread CTA does the whole scan (vgpu_victim_small); above: the multi-launch path
+    for n, need in ((1024, 8 << 30), (3000, 30 << 30), (8191, 100 << 30), (8192, 1 << 30), (8193, 100 << 30), (20000, 300 << 30)):
+        _scan_case(ora, n, need, seed=n)
+    _scan_case(ora, 8192, 1 << 62, seed=4)                       # insufficient on the single-launch path
+    _scan_case(ora, 8192, 90 << 30, seed=8, touch_max=(1 << 40) - 1)   # wide clock: 40 + 13 key bits, five digits
+    _scan_case(ora, 4096, 50 << 30, seed=9, touch_max=0)         # all ties: index order only
+
+
 def test_victim_scan_ties_broken_by_index(ora):
     # every candidate has the same last_touch: the order is purely by row index
     _scan_case(ora, 500, 1 << 30, seed=5, touch_max=0)
