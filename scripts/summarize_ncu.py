@@ -13,8 +13,8 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 
 
-def launches():
-    p = os.path.join(OUT, "launches.csv")
+def launches(name="launches.csv", title=None):
+    p = os.path.join(OUT, name)
     if not os.path.exists(p):
         return None
     text = open(p).read()
@@ -32,7 +32,7 @@ def launches():
         a[0] += 1
         a[1] += ns
     total = sum(a[1] for a in agg.values()) or 1
-    lines = [f"# ncu launch list ({tag}) — scripts/ncu_target.py (engine-only swap loop, 32x64 MiB under 1 GiB)", "",
+    lines = [title or f"# ncu launch list ({tag}) — scripts/ncu_target.py (engine-only swap loop, 32x64 MiB under 1 GiB)", "",
              "cold-cache, serialised per-launch times: compare SHARES, not absolutes", "",
              "| kernel | launches | total us | avg us | share |", "|---|---:|---:|---:|---:|"]
     for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -66,6 +66,11 @@ a = launches()
 if a:
     open(os.path.join(ROOT, "profiles", f"{tag}_launches.md"), "w").write(a)
     print(a)
+c = launches("launches_bench.csv", f"# ncu launch list ({tag}) — `python bench.py --steps 2 --warmup 3`, launches inside the NVTX range \"timed\" only "
+             "(`ncu --nvtx --nvtx-include \"timed/\" --metrics gpu__time_duration.sum --clock-control none`)")
+if c:
+    open(os.path.join(ROOT, "profiles", f"{tag}_launches_bench.md"), "w").write(c)
+    print(c)
 b = full("prof_pack.ncu-rep", "vgpu_pack_tma")
 if b:
     open(os.path.join(ROOT, "profiles", f"{tag}_pack_tma_full.md"), "w").write(b)
