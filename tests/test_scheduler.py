@@ -353,3 +353,63 @@ def test_http_routes_and_metrics():
             assert f"# TYPE {name} gauge" in text
     finally:
         srv.shutdown()
+
+
+def test_native_scoring_core_equals_the_python_restatement_on_random_clusters():
+    """Differential test: csrc/sched_core.cc against oracle/sched_oracle.py (an independent statement-level restatement
+    of score.go) on random nodes, usages, requests and annotations — same fit decision, same float32 score, same
+    devices in the same order, same charged usage."""
+    import random
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import sched_oracle as O
+    rng = random.Random(0xB200)
+    types = ["NVIDIA-NVIDIA B200", "NVIDIA-NVIDIA A100-SXM4-80GB", "NVIDIA-Tesla P4", "MLU-370"]
+    outcomes = {"fit": 0, "nofit": 0, "panic": 0}
+    for case in range(600):
+        ndev = rng.randint(1, 9)
+        devs = []
+        for i in range(ndev):
+            count = rng.choice([1, 2, 4, 10])
+            used = rng.randint(0, count)
+            totalmem = rng.choice([16384, 81920, 183359])
+            devs.append(dict(Id=f"GPU-{case}-{i}", Index=i, Used=used, Count=count, Usedmem=rng.randint(0, totalmem) if used else 0, Totalmem=totalmem,
+                             Totalcore=rng.choice([100, 100, 200, 0]), Usedcores=rng.choice([0, 10, 50, 100]) if used else 0, Numa=rng.randint(0, 1),
+                             Type=rng.choice(types), Health=True))
+        nctr = rng.choice([1, 1, 1, 2, 3])
+        reqs = []
+        for _ in range(nctr):
+            if rng.random() < 0.15:
+                reqs.append(None)
+                continue
+            mem = rng.choice([0, 0, 1024, 8192, 100000])
+            reqs.append(dict(Nums=rng.randint(1, 3), Type="NVIDIA", Memreq=mem, MemPercentagereq=101 if mem else rng.choice([101, 10, 50, 100]),
+                             Coresreq=rng.choice([0, 0, 10, 30, 100, 101])))
+        annos = {}
+        r = rng.random()
+        if r < 0.2:
+            annos[O.GPU_IN_USE] = rng.choice(["B200", "a100,b200", "P4", ""])
+        elif r < 0.4:
+            annos[O.GPU_NO_USE] = rng.choice(["B200", "a100,p4", "V100"])
+        if rng.random() < 0.3:
+            annos[O.NUMA_BIND] = rng.choice(["true", "false", "1", "yes"])
+
+        odevs = [dict(d) for d in devs]
+        want = O.score_node(odevs, reqs, annos)
+        usage = S.NodeUsage([S.DeviceUsage(d["Id"], d["Index"], d["Used"], d["Count"], d["Usedmem"], d["Totalmem"], d["Totalcore"], d["Usedcores"],
+                                           d["Numa"], d["Type"], d["Health"]) for d in devs])
+        creqs = [S.ContainerDeviceRequest() if q is None else S.ContainerDeviceRequest(q["Nums"], q["Type"], q["Memreq"], q["MemPercentagereq"], q["Coresreq"])
+                 for q in reqs]
+        outcomes[want[0]] += 1
+        if want[0] == "panic":
+            with pytest.raises(S.SchedulerPanic):
+                S.score_node(usage, creqs, annos, mode=0)
+            continue
+        fit, score, devices = S.score_node(usage, creqs, annos, mode=0)
+        assert fit == (want[0] == "fit"), (case, want)
+        if fit:
+            assert score == want[1], (case, score, want[1])
+            got = [[(d.UUID, d.Type, d.Usedmem, d.Usedcores) for d in ctr] for ctr in devices["NVIDIA"]]
+            exp = [[(d["UUID"], d["Type"], d["Usedmem"], d["Usedcores"]) for d in ctr if d] for ctr in want[2]]
+            assert got == exp, (case, got, exp)
+            assert [(d.Id, d.Used, d.Usedmem, d.Usedcores) for d in usage.Devices] == [(d["Id"], d["Used"], d["Usedmem"], d["Usedcores"]) for d in odevs], case
+    assert outcomes["fit"] > 50 and outcomes["nofit"] > 50 and outcomes["panic"] > 5, outcomes
