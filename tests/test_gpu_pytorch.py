@@ -1,0 +1,109 @@
+"""PyTorch as the application under the hook, on a real B200: the deployment the reference exists for. cudart resolves
+the driver through dlsym / cuGetProcAddress (the hook's symbol routing), the caching allocator uses cudaMalloc or —
+with expandable segments — cuMemCreate/cuMemMap, and CUDA graphs replay captured launches."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+import k8s_device_plugin_b200 as v
+
+pytestmark = pytest.mark.gpu
+
+
+def _torch_under_hook(tmp_path, code, env_extra, timeout=300):
+    env = dict(os.environ)
+    env.pop("LD_PRELOAD", None)
+    env.update(env_extra)
+    env.setdefault("LIBCUDA_LOG_LEVEL", "0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stderr[-3000:] + r.stdout[-500:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+_QUOTA = r"""
+import json, torch
+free, total = torch.cuda.mem_get_info()
+x = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+free2, _ = torch.cuda.mem_get_info()
+try:
+    y = torch.empty(8 << 30, dtype=torch.uint8, device="cuda")
+    refused = ""
+except RuntimeError as e:
+    refused = type(e).__name__
+a = torch.randn(2048, 2048, device="cuda"); b = torch.randn(2048, 2048, device="cuda")
+ok = bool(torch.allclose(a @ b, (a.double() @ b.double()).float(), rtol=1e-3, atol=1e-2))
+print(json.dumps({"total": total, "free_drop": free - free2, "refused": refused, "matmul_ok": ok}))
+"""
+
+
+@pytest.mark.parametrize("alloc_conf,strict", [("", False), ("", True), ("expandable_segments:True", False)])
+def test_pytorch_sees_and_obeys_the_gpumem_quota(tmp_path, alloc_conf, strict):
+    env = v.hook_env(limit_mib=4096, cache_path=str(tmp_path / "pt.cache"))
+    if alloc_conf:
+        env["PYTORCH_CUDA_ALLOC_CONF"] = alloc_conf          # caching allocator on cuMemCreate/cuMemMap: unaccounted in the reference
+    if strict:
+        env["VGPU_STRICT_CUDA_ERRORS"] = "1"
+    out = _torch_under_hook(tmp_path, _QUOTA, env)
+    assert out["total"] == 4096 << 20                        # cuMemGetInfo_v2 under the quota (memory.c:L549-566)
+    assert out["refused"] and out["matmul_ok"] is True       # refused, and the process keeps working afterwards
+    # cuMemAlloc_v2 answers the reference's (CUresult)-1 on a breach, which cudart reports as an unknown error; the strict
+    # switch and the cuMemCreate path answer CUDA_ERROR_OUT_OF_MEMORY, which PyTorch turns into OutOfMemoryError
+    if strict or alloc_conf:
+        assert out["refused"] == "OutOfMemoryError"
+    assert (1 << 30) <= out["free_drop"] <= (1 << 30) + (64 << 20)
+
+
+_GRAPH = r"""
+import json, time, torch
+x = torch.zeros(64 << 20, device="cuda")
+s = torch.cuda.Stream()
+with torch.cuda.stream(s):
+    for _ in range(3):
+        x.add_(1.0)
+    torch.cuda.current_stream().synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        for _ in range(16):
+            x.add_(1.0)
+torch.cuda.synchronize()
+t0 = time.time(); n = 0
+while time.time() - t0 < SECONDS:
+    g.replay(); n += 1
+    if n % 4 == 0:
+        torch.cuda.synchronize()
+torch.cuda.synchronize()
+wall = time.time() - t0
+print(json.dumps({"replays": n, "wall_s": wall, "value": float(x[0].item()), "expect": 3.0 + 16.0 * (n + 0)}))
+"""
+
+
+def test_pytorch_cuda_graph_replays_are_rate_limited_and_exact(tmp_path):
+    bare = _torch_under_hook(tmp_path, _GRAPH.replace("SECONDS", "3"), {})
+    env = dict(v.hook_env(sm_limit=30, cache_path=str(tmp_path / "g.cache")), GPU_CORE_UTILIZATION_POLICY="force")
+    lim = _torch_under_hook(tmp_path, _GRAPH.replace("SECONDS", "5"), env)
+    assert bare["value"] == bare["expect"] and lim["value"] == lim["expect"]
+    ratio = (lim["replays"] / lim["wall_s"]) / (bare["replays"] / bare["wall_s"])
+    assert 0.2 <= ratio <= 0.4, (ratio, bare, lim)
+
+
+_SWAP = r"""
+import json, torch
+bufs = [torch.full((1536 << 20,), i, dtype=torch.uint8, device="cuda") for i in range(4)]     # 6 GiB live under a 3 GiB quota
+for rnd in range(3):
+    for b in bufs:
+        b.add_(1)
+torch.cuda.synchronize()
+ok = all(int(b[0].item()) == i + 3 and int(b[-1].item()) == i + 3 and int(b.sum(dtype=torch.int64).item()) == (i + 3) * b.numel() for i, b in enumerate(bufs))
+free, total = torch.cuda.mem_get_info()
+print(json.dumps({"ok": ok, "total": total}))
+"""
+
+
+def test_pytorch_oversubscribes_through_the_swap_engine(tmp_path):
+    env = dict(v.hook_env(limit_mib=3072, oversubscribe=True, cache_path=str(tmp_path / "sw.cache")), VGPU_PRINT_STATS="1",
+               PYTORCH_NO_CUDA_MEMORY_CACHING="1")           # one cudaMalloc per tensor: the engine sees whole buffers
+    out = _torch_under_hook(tmp_path, _SWAP, env, timeout=600)
+    assert out["ok"] is True
