@@ -306,6 +306,11 @@ void *find_hook_for_real(void *real_fn) {
         if (e.real && *e.real == real_fn) return e.fn;
     return nullptr;
 }
+// VGPU_TRACE_GPA=1: log every cuGetProcAddress request and whether a wrapper was substituted (diagnostics)
+bool trace_gpa() {
+    static bool on = std::getenv("VGPU_TRACE_GPA") != nullptr;
+    return on;
+}
 bool control_disabled() {
     static bool off = std::getenv("CUDA_DISABLE_CONTROL") != nullptr;   // container opt-out (server.go:380-385)
     return off;
@@ -323,8 +328,11 @@ VGPU_EXPORT CUresult cuGetProcAddress_v2(const char *symbol, void **pfn, int cud
     } else {
         return CUDA_ERROR_NOT_INITIALIZED;
     }
-    if (r == CUDA_SUCCESS && pfn && !control_disabled())
-        if (void *h = find_hook_for_real(*pfn)) *pfn = h;
+    if (r == CUDA_SUCCESS && pfn && !control_disabled()) {
+        void *h = find_hook_for_real(*pfn);
+        if (trace_gpa()) std::fprintf(stderr, "[vgpu-b200 gpa] %s ver=%d flags=%llu -> %p %s\n", symbol, cudaVersion, (unsigned long long)flags, *pfn, h ? "HOOKED" : "");
+        if (h) *pfn = h;
+    }
     return r;
 }
 

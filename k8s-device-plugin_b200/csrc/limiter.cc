@@ -86,7 +86,8 @@ void Limiter::harvest() {
         PerStream &ps = streams_[it->st];
         if (!it->has_begin && ps.last_end > b) b = ps.last_end;
         uint64_t busy = e > b ? e - b : 0;
-        if (it->idle_ns && busy > 0) {
+        const bool estimated = it->idle_ns && busy > 0;
+        if (estimated) {
             // span = work + the host's pause: keep what preceded the pause, cap what followed it at the recent average
             uint64_t est = (uint64_t)(avg_busy_per_launch_ns_ * (it->launches ? it->launches : 1));
             uint64_t before_pause = busy > it->idle_ns ? busy - it->idle_ns : 0;
@@ -103,6 +104,7 @@ void Limiter::harvest() {
         // keep the measuring overhead proportional: long kernels -> stamp every launch and keep at most one group
         // in flight (tight duty cycle); short kernels -> stamp every `stride` launches
         if (busy > 1000000ull) { stride_ = 1; max_inflight_ = 1; }
+        else if (estimated) { /* not a measurement: no evidence for widening the stride */ }
         else if (busy < 100000ull * (uint64_t)stride_ && stride_ < 32) { stride_ *= 2; max_inflight_ = 4; }
         else if (busy > 400000ull && stride_ > 1) stride_ /= 2;
         it = pending_.erase(it);
@@ -162,17 +164,23 @@ void Limiter::before_launch(CUstream st) {
         if (e >= 0) pending_.push_back(Group{st, ps.begin_idx, e, ps.last_end, ps.begin_idx >= 0, ps.since_end, t_out - ps.last_launch_ns});
         ps.begin_idx = -1;
         ps.since_end = 0;
+        // An estimate was just substituted for a measurement. Measure the next launches one by one (begin/end stamps
+        // around each) so that the stride only grows back on evidence that they really are short — otherwise a pause
+        // inside a group of LONG launches (the host blocked in a synchronise while the GPU worked) under-bills the group,
+        // the low figure keeps the stride high, and the limiter never recovers.
+        stride_ = 1;
     }
 }
 
-void Limiter::after_launch(CUstream st) {
+void Limiter::after_launch(CUstream st, bool heavy) {
     if (!enabled_now()) return;
     std::lock_guard<std::mutex> g(mu_);
     if (!ring_) return;
     PerStream &ps = streams_[st];
     if (!ps.open) return;
     ps.last_launch_ns = now_ns();
-    if (++ps.since_end >= stride_) {
+    // heavy = one call that enqueues an unknown amount of work (a graph launch): always measured on its own
+    if (++ps.since_end >= stride_ || heavy) {
         int e = stamp(st);
         if (e >= 0) pending_.push_back(Group{st, ps.begin_idx, e, ps.last_end, ps.begin_idx >= 0, ps.since_end, 0});
         ps.open = false;

@@ -35,7 +35,7 @@ class Limiter {
     Limiter(int percent, vgpu_shared_region_t *region, int util_policy);
     ~Limiter();
     void before_launch(CUstream st);
-    void after_launch(CUstream st);
+    void after_launch(CUstream st, bool heavy = false);
     LimiterStats stats();
     bool active() const { return active_; }
 

@@ -643,7 +643,7 @@ CUresult Runtime::graph_launch(CUgraphExec g, CUstream st, bool ptsz) {
     CUstream eff = ptsz ? pt(st) : st;
     if (lim) lim->before_launch(eff);
     CUresult r = real(g, st);
-    if (lim) lim->after_launch(eff);
+    if (lim) lim->after_launch(eff, /*heavy=*/true);
     return r;
 }
 
