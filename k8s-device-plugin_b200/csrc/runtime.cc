@@ -391,6 +391,15 @@ bool Runtime::check_oom() {
     if (!ensure_initialized()) return false;
     int dev = current_device();
     if (dev < 0) return false;
+    if (cfg_.oversubscribe) {
+        // swap mode: the quota bounds resident bytes; live swappable bytes above it are the point of the mode, so only
+        // the non-swappable part is held against the limit (same rule as charge())
+        uint64_t lim = region_->limit(dev);
+        if (!lim) return false;
+        SwapEngine *e = swap(dev);
+        uint64_t u = region_->usage(dev), live = e ? e->live_bytes() : 0;
+        return (u > live ? u - live : 0) > lim;
+    }
     return !region_->try_add(pid_, dev, 0, VGPU_MEM_BUFFER, true, true);
 }
 
