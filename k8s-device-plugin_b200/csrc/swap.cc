@@ -866,8 +866,16 @@ CUresult SwapEngine::make_room(uint64_t need_mapped, bool finish) {
 CUresult SwapEngine::alloc(CUdeviceptr *dptr, size_t bytes) {
     if (!dptr || bytes == 0) return CUDA_ERROR_INVALID_VALUE;
     std::lock_guard<std::mutex> g(mu_);
-    if (cfg_.virtual_cap && live_bytes_ + bytes > cfg_.virtual_cap) return CUDA_ERROR_OUT_OF_MEMORY;
+    if (cfg_.virtual_cap && live_bytes_ + bytes > cfg_.virtual_cap) {
+        LOG_ERROR("Device %d OOM (virtual) %lu / %lu", dev_, (unsigned long)(live_bytes_ + bytes), (unsigned long)cfg_.virtual_cap);
+        return CUDA_ERROR_OUT_OF_MEMORY;
+    }
     uint64_t mapped = round_up(bytes, gran_);
+    if (cfg_.resident_cap && mapped > cfg_.resident_cap) {
+        // a buffer is resident as a whole while a kernel uses it: one that exceeds the resident cap can never be admitted
+        LOG_ERROR("Device %d OOM: a single %lu-byte buffer exceeds the resident cap of %lu bytes", dev_, (unsigned long)bytes, (unsigned long)cfg_.resident_cap);
+        return CUDA_ERROR_OUT_OF_MEMORY;
+    }
     uint64_t off;
     if (!va_alloc(mapped, &off)) { LOG_ERROR("swap arena exhausted"); return CUDA_ERROR_OUT_OF_MEMORY; }
     CUresult r = make_room(mapped);
