@@ -201,7 +201,8 @@ CUresult fx_launch(CUfunction f, void **params) {
     case K_VERIFY: { const uint64_t *b = ARG(const uint64_t *, 0); uint64_t n = ARG(uint64_t, 1), bi = ARG(uint64_t, 2), add = ARG(uint64_t, 3);
         unsigned long long *bad = ARG(unsigned long long *, 4); uint64_t m = 0;
         for (uint64_t j = 0; j < n; j++) if (b[j] != splitmix64((bi << 32) + j) + add) m++;
-        if (m) *bad += m; break; }
+        if (m) *bad += m;
+        break; }
     default: break;
     }
     return CUDA_SUCCESS;

@@ -16,7 +16,8 @@
  * Behaviour knobs (env): FAKE_GPU_COUNT (1), FAKE_GPU_TOTAL_MIB (183359 = B200),
  * FAKE_GPU_CTX_MIB (512: bytes NVML reports for a process with a primary context),
  * FAKE_GPU_SM_UTIL (0: smUtil returned by nvmlDeviceGetProcessUtilization),
- * FAKE_GPU_LOG (unset: silent).
+ * FAKE_GPU_LOG (unset: silent), FAKE_GPU_EXEC (unset: bookkeeping only; 1: device memory is real host memory and work
+ * executes — fake_exec.c).
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
@@ -28,30 +29,14 @@
 #include <sys/time.h>
 #include <unistd.h>
 
-typedef int CUresult;
-typedef int CUdevice;
-typedef unsigned long long CUdeviceptr;
-typedef void *CUcontext;
-typedef void *CUstream;
-typedef void *CUfunction;
-typedef void *CUmodule;
-typedef void *CUevent;
+#include "fake_internal.h"
 typedef struct { unsigned char bytes[16]; } CUuuid;
-
-#define CUDA_SUCCESS 0
-#define CUDA_ERROR_INVALID_VALUE 1
-#define CUDA_ERROR_OUT_OF_MEMORY 2
-#define CUDA_ERROR_NOT_INITIALIZED 3
-#define CUDA_ERROR_INVALID_DEVICE 101
-#define CUDA_ERROR_INVALID_CONTEXT 201
-#define CUDA_ERROR_NOT_FOUND 500
-#define CUDA_ERROR_NOT_SUPPORTED 801
 
 #define MAXDEV 16
 #define EXPORT __attribute__((visibility("default")))
 
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
-static int g_inited, g_ndev = 1, g_log;
+static int g_inited, g_ndev = 1, g_log, g_exec;
 static uint64_t g_total = 183359ull << 20, g_ctx_bytes = 512ull << 20;
 static unsigned g_sm_util;
 static uint64_t g_used[MAXDEV];
@@ -75,6 +60,7 @@ static void fake_init(void) {
     if ((e = getenv("FAKE_GPU_CTX_MIB"))) g_ctx_bytes = strtoull(e, 0, 0) << 20;
     if ((e = getenv("FAKE_GPU_SM_UTIL"))) g_sm_util = (unsigned)atoi(e);
     g_log = getenv("FAKE_GPU_LOG") != NULL;
+    g_exec = (e = getenv("FAKE_GPU_EXEC")) && *e && *e != '0';
     g_h = calloc(HCAP, sizeof(*g_h));
     g_inited = 1;
 }
@@ -87,27 +73,31 @@ static int cur_dev(void) {
 
 static unsigned hslot(uint64_t base) { return (unsigned)((base >> 9) * 0x9E3779B97F4A7C15ull >> 44) & (HCAP - 1); }
 
-static CUresult do_alloc(CUdeviceptr *dptr, size_t size) {
+int fake_exec_on(void) { fake_init(); return g_exec; }
+
+int fake_charge(int dev, int64_t delta) {
     fake_init();
-    int d = cur_dev();
-    if (d < 0) return CUDA_ERROR_INVALID_CONTEXT;
-    if (!dptr || size == 0) return CUDA_ERROR_INVALID_VALUE;
+    pthread_mutex_lock(&g_mu);
+    if (delta > 0 && g_used[dev] + (uint64_t)delta > g_total) { pthread_mutex_unlock(&g_mu); return 1; }
+    g_used[dev] = (uint64_t)((int64_t)g_used[dev] + delta);
+    pthread_mutex_unlock(&g_mu);
+    return 0;
+}
+
+CUresult fake_track(uint64_t base, uint64_t size, int d) {
+    fake_init();
     pthread_mutex_lock(&g_mu);
     if (g_used[d] + size > g_total) { pthread_mutex_unlock(&g_mu); return CUDA_ERROR_OUT_OF_MEMORY; }
-    uint64_t base = g_next_va;
-    g_next_va += (size + 511) & ~511ull;
     unsigned s = hslot(base);
     while (g_h[s].live) s = (s + 1) & (HCAP - 1);
     g_h[s].base = base; g_h[s].size = size; g_h[s].dev = d; g_h[s].live = 1;
     g_used[d] += size;
     pthread_mutex_unlock(&g_mu);
-    *dptr = base;
     return CUDA_SUCCESS;
 }
 
-static CUresult do_free(CUdeviceptr p) {
+CUresult fake_untrack(uint64_t p, uint64_t *size) {
     fake_init();
-    if (!p) return CUDA_SUCCESS;
     pthread_mutex_lock(&g_mu);
     unsigned s = hslot(p);
     for (unsigned n = 0; n < HCAP; n++, s = (s + 1) & (HCAP - 1)) {
@@ -115,12 +105,35 @@ static CUresult do_free(CUdeviceptr p) {
         if (g_h[s].live && g_h[s].base == p) {
             g_h[s].live = 0; /* tombstone keeps base != 0 so probing continues */
             g_used[g_h[s].dev] -= g_h[s].size;
+            if (size) *size = g_h[s].size;
             pthread_mutex_unlock(&g_mu);
             return CUDA_SUCCESS;
         }
     }
     pthread_mutex_unlock(&g_mu);
     return CUDA_ERROR_INVALID_VALUE;
+}
+
+static CUresult do_alloc(CUdeviceptr *dptr, size_t size) {
+    fake_init();
+    int d = cur_dev();
+    if (d < 0) return CUDA_ERROR_INVALID_CONTEXT;
+    if (!dptr || size == 0) return CUDA_ERROR_INVALID_VALUE;
+    if (g_exec) return fx_alloc(dptr, size, d);
+    pthread_mutex_lock(&g_mu);
+    uint64_t base = g_next_va;
+    g_next_va += (size + 511) & ~511ull;
+    pthread_mutex_unlock(&g_mu);
+    CUresult r = fake_track(base, size, d);
+    if (!r) *dptr = base;
+    return r;
+}
+
+static CUresult do_free(CUdeviceptr p) {
+    fake_init();
+    if (!p) return CUDA_SUCCESS;
+    if (g_exec) return fx_free(p);
+    return fake_untrack(p, NULL);
 }
 
 /* ------------------------------------------------------------------ CUDA driver half */
@@ -202,21 +215,72 @@ EXPORT CUresult cuMemGetAddressRange_v2(CUdeviceptr *base, size_t *size, CUdevic
 
 EXPORT CUresult cuLaunchKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
                                unsigned smem, CUstream st, void **params, void **extra) {
-    (void)f; (void)gx; (void)gy; (void)gz; (void)bx; (void)by; (void)bz; (void)smem; (void)st; (void)params; (void)extra;
+    (void)gx; (void)gy; (void)gz; (void)bx; (void)by; (void)bz; (void)smem; (void)st; (void)extra;
     __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
-    return CUDA_SUCCESS;
+    return fake_exec_on() ? fx_launch(f, params) : CUDA_SUCCESS;
+}
+EXPORT CUresult cuLaunchKernelEx(const void *cfg, CUfunction f, void **params, void **extra) {
+    (void)cfg; (void)extra; __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
+    return fake_exec_on() ? fx_launch(f, params) : CUDA_SUCCESS;
+}
+EXPORT CUresult cuLaunchCooperativeKernel(CUfunction f, unsigned gx, unsigned gy, unsigned gz, unsigned bx, unsigned by, unsigned bz,
+                                          unsigned smem, CUstream st, void **params) {
+    return cuLaunchKernel(f, gx, gy, gz, bx, by, bz, smem, st, params, NULL);
 }
 static int g_mod_obj, g_fn_obj;
 EXPORT CUresult cuModuleLoadData(CUmodule *m, const void *img) { (void)img; *m = &g_mod_obj; return CUDA_SUCCESS; }
 EXPORT CUresult cuModuleLoad(CUmodule *m, const char *path) { (void)path; *m = &g_mod_obj; return CUDA_SUCCESS; }
 EXPORT CUresult cuModuleLoadDataEx(CUmodule *m, const void *img, unsigned n, void *o, void **v) { (void)img; (void)n; (void)o; (void)v; *m = &g_mod_obj; return CUDA_SUCCESS; }
-EXPORT CUresult cuModuleGetFunction(CUfunction *f, CUmodule m, const char *name) { (void)m; (void)name; *f = &g_fn_obj; return CUDA_SUCCESS; }
+EXPORT CUresult cuModuleGetFunction(CUfunction *f, CUmodule m, const char *name) {
+    (void)m; if (fake_exec_on()) return fx_get_function(f, name); *f = &g_fn_obj; return CUDA_SUCCESS;
+}
+EXPORT CUresult cuFuncGetParamInfo(CUfunction f, size_t idx, size_t *off, size_t *size) {
+    return fake_exec_on() ? fx_param_info(f, idx, off, size) : CUDA_ERROR_INVALID_VALUE;
+}
+EXPORT CUresult cuFuncSetAttribute(CUfunction f, int attr, int v) { (void)f; (void)attr; (void)v; return CUDA_SUCCESS; }
+EXPORT CUresult cuOccupancyMaxActiveBlocksPerMultiprocessor(int *n, CUfunction f, int bs, size_t smem) { (void)f; (void)bs; (void)smem; *n = 4; return CUDA_SUCCESS; }
 EXPORT CUresult cuModuleUnload(CUmodule m) { (void)m; return CUDA_SUCCESS; }
 EXPORT CUresult cuStreamCreate(CUstream *s, unsigned f) { (void)f; *s = &g_mod_obj; return CUDA_SUCCESS; }
 EXPORT CUresult cuStreamCreateWithPriority(CUstream *s, unsigned f, int p) { (void)f; (void)p; *s = &g_mod_obj; return CUDA_SUCCESS; }
 EXPORT CUresult cuCtxGetStreamPriorityRange(int *lo, int *hi) { if (lo) *lo = 0; if (hi) *hi = -5; return CUDA_SUCCESS; }
 EXPORT CUresult cuStreamDestroy_v2(CUstream s) { (void)s; return CUDA_SUCCESS; }
 EXPORT CUresult cuStreamSynchronize(CUstream s) { (void)s; return CUDA_SUCCESS; }
+EXPORT CUresult cuStreamQuery(CUstream s) { (void)s; return CUDA_SUCCESS; }
+EXPORT CUresult cuStreamWaitEvent(CUstream s, CUevent e, unsigned f) { (void)s; (void)e; (void)f; return CUDA_SUCCESS; }
+EXPORT CUresult cuStreamIsCapturing(CUstream s, int *status) { (void)s; if (status) *status = 0; return CUDA_SUCCESS; }
+/* work completes at call time: an event is the clock at record time */
+EXPORT CUresult cuEventCreate(CUevent *e, unsigned f) { (void)f; return fx_event_create(e); }
+EXPORT CUresult cuEventRecord(CUevent e, CUstream s) { (void)s; return fx_event_record(e); }
+EXPORT CUresult cuEventSynchronize(CUevent e) { (void)e; return CUDA_SUCCESS; }
+EXPORT CUresult cuEventQuery(CUevent e) { (void)e; return CUDA_SUCCESS; }
+EXPORT CUresult cuEventElapsedTime(float *ms, CUevent a, CUevent b) { return fx_event_elapsed(ms, a, b); }
+EXPORT CUresult cuEventDestroy_v2(CUevent e) { return fx_event_destroy(e); }
+/* copies and fills act on real memory in exec mode; in bookkeeping mode device addresses are not backed */
+#define FX_ONLY(stmt) do { if (fake_exec_on()) { stmt; } return CUDA_SUCCESS; } while (0)
+EXPORT CUresult cuMemcpyHtoD_v2(CUdeviceptr d, const void *s, size_t n) { FX_ONLY(memmove((void *)(uintptr_t)d, s, n)); }
+EXPORT CUresult cuMemcpyDtoH_v2(void *d, CUdeviceptr s, size_t n) { FX_ONLY(memmove(d, (const void *)(uintptr_t)s, n)); }
+EXPORT CUresult cuMemcpyDtoD_v2(CUdeviceptr d, CUdeviceptr s, size_t n) { FX_ONLY(memmove((void *)(uintptr_t)d, (const void *)(uintptr_t)s, n)); }
+EXPORT CUresult cuMemcpyHtoDAsync_v2(CUdeviceptr d, const void *s, size_t n, CUstream st) { (void)st; FX_ONLY(memmove((void *)(uintptr_t)d, s, n)); }
+EXPORT CUresult cuMemcpyDtoHAsync_v2(void *d, CUdeviceptr s, size_t n, CUstream st) { (void)st; FX_ONLY(memmove(d, (const void *)(uintptr_t)s, n)); }
+EXPORT CUresult cuMemcpyDtoDAsync_v2(CUdeviceptr d, CUdeviceptr s, size_t n, CUstream st) { (void)st; FX_ONLY(memmove((void *)(uintptr_t)d, (const void *)(uintptr_t)s, n)); }
+EXPORT CUresult cuMemcpy(CUdeviceptr d, CUdeviceptr s, size_t n) { FX_ONLY(memmove((void *)(uintptr_t)d, (const void *)(uintptr_t)s, n)); }
+EXPORT CUresult cuMemcpyAsync(CUdeviceptr d, CUdeviceptr s, size_t n, CUstream st) { (void)st; FX_ONLY(memmove((void *)(uintptr_t)d, (const void *)(uintptr_t)s, n)); }
+EXPORT CUresult cuMemsetD8_v2(CUdeviceptr d, unsigned char v, size_t n) { FX_ONLY(memset((void *)(uintptr_t)d, v, n)); }
+EXPORT CUresult cuMemsetD8Async(CUdeviceptr d, unsigned char v, size_t n, CUstream st) { (void)st; FX_ONLY(memset((void *)(uintptr_t)d, v, n)); }
+EXPORT CUresult cuMemsetD16_v2(CUdeviceptr d, unsigned short v, size_t n) { FX_ONLY(for (size_t i = 0; i < n; i++) ((unsigned short *)(uintptr_t)d)[i] = v); }
+EXPORT CUresult cuMemsetD16Async(CUdeviceptr d, unsigned short v, size_t n, CUstream st) { (void)st; return cuMemsetD16_v2(d, v, n); }
+EXPORT CUresult cuMemsetD32_v2(CUdeviceptr d, unsigned v, size_t n) { FX_ONLY(for (size_t i = 0; i < n; i++) ((unsigned *)(uintptr_t)d)[i] = v); }
+EXPORT CUresult cuMemsetD32Async(CUdeviceptr d, unsigned v, size_t n, CUstream st) { (void)st; return cuMemsetD32_v2(d, v, n); }
+EXPORT CUresult cuMemHostGetDevicePointer_v2(CUdeviceptr *d, void *h, unsigned f) { (void)f; *d = (CUdeviceptr)(uintptr_t)h; return CUDA_SUCCESS; }
+EXPORT CUresult cuMemHostRegister_v2(void *p, size_t n, unsigned f) { (void)p; (void)n; (void)f; return CUDA_SUCCESS; }
+EXPORT CUresult cuMemGetAllocationGranularity(size_t *g, const void *prop, int opt) { (void)prop; (void)opt; *g = 2u << 20; return CUDA_SUCCESS; }
+EXPORT CUresult cuMemAddressReserve(CUdeviceptr *p, size_t n, size_t align, CUdeviceptr addr, unsigned long long fl) {
+    if (fake_exec_on()) return fx_address_reserve(p, n, align, addr, fl);
+    (void)align; (void)addr; (void)fl; *p = 0x600000000000ull; return CUDA_SUCCESS;
+}
+EXPORT CUresult cuMemMap(CUdeviceptr va, size_t n, size_t off, unsigned long long h, unsigned long long fl) {
+    return fake_exec_on() ? fx_mem_map(va, n, off, h, fl) : CUDA_SUCCESS;
+}
 EXPORT CUresult cuGetErrorString(CUresult e, const char **s) { (void)e; *s = "fake"; return CUDA_SUCCESS; }
 EXPORT CUresult cuGetErrorName(CUresult e, const char **s) { (void)e; *s = "FAKE"; return CUDA_SUCCESS; }
 /* The reference patches slots 2 and 6 of the cudart-interface export table in place (libvgpu.so@0x3f858-0x3f8fd)
@@ -232,18 +296,19 @@ EXPORT CUresult cuGetExportTable(const void **tbl, const CUuuid *id) {
     return CUDA_SUCCESS;
 }
 EXPORT CUresult cuArray3DGetDescriptor_v2(void *d, void *a) { (void)d; (void)a; return CUDA_ERROR_NOT_SUPPORTED; }
-EXPORT CUresult cuMemAddressFree(CUdeviceptr p, size_t n) { (void)p; (void)n; return CUDA_SUCCESS; }
+EXPORT CUresult cuMemAddressFree(CUdeviceptr p, size_t n) { if (fake_exec_on()) return fx_address_free(p, n); return CUDA_SUCCESS; }
 /* VMM physical handles and stream-ordered allocations: same bookkeeping as cuMemAlloc (a handle is its fake address) */
 EXPORT CUresult cuMemCreate(unsigned long long *h, size_t n, const void *prop, unsigned long long flags) {
+    if (fake_exec_on()) return fx_mem_create(h, n, prop, flags);
     (void)prop; (void)flags; CUdeviceptr p = 0; CUresult r = do_alloc(&p, n); if (!r) *h = p; return r;
 }
-EXPORT CUresult cuMemRelease(unsigned long long h) { return do_free(h); }
+EXPORT CUresult cuMemRelease(unsigned long long h) { if (fake_exec_on()) return fx_mem_release(h); return do_free(h); }
 EXPORT CUresult cuMemAllocAsync(CUdeviceptr *p, size_t n, CUstream st) { (void)st; return do_alloc(p, n); }
 EXPORT CUresult cuMemAllocFromPoolAsync(CUdeviceptr *p, size_t n, void *pool, CUstream st) { (void)pool; (void)st; return do_alloc(p, n); }
 EXPORT CUresult cuMemFreeAsync(CUdeviceptr p, CUstream st) { (void)st; return do_free(p); }
 EXPORT CUresult cuGraphLaunch(void *g, CUstream st) { (void)g; (void)st; __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); return CUDA_SUCCESS; }
-EXPORT CUresult cuMemSetAccess(CUdeviceptr p, size_t n, const void *d, size_t c) { (void)p; (void)n; (void)d; (void)c; return CUDA_SUCCESS; }
-EXPORT CUresult cuMemUnmap(CUdeviceptr p, size_t n) { (void)p; (void)n; return CUDA_SUCCESS; }
+EXPORT CUresult cuMemSetAccess(CUdeviceptr p, size_t n, const void *d, size_t c) { if (fake_exec_on()) return fx_mem_set_access(p, n, d, c); return CUDA_SUCCESS; }
+EXPORT CUresult cuMemUnmap(CUdeviceptr p, size_t n) { if (fake_exec_on()) return fx_mem_unmap(p, n); return CUDA_SUCCESS; }
 
 /* test hook: number of kernel launches that reached the "hardware" */
 EXPORT uint64_t fake_gpu_launch_count(void) { return g_launches; }

@@ -1,0 +1,127 @@
+"""The whole product on a CPU box: hook + swap engine + limiter running against the FUNCTIONAL fake driver
+(oracle/fake_driver/fake_exec.c, FAKE_GPU_EXEC=1: device memory is host memory, VMM is mmap/memfd, the product's kernels
+are emulated from their contracts, everything executes in program order). What this checks is the engine's logic and
+bookkeeping — victims, remaps, host pool, staging rings, counters, data integrity through page-out/page-in, the
+limiter's bucket arithmetic. The real kernels and stream overlap are checked by the -m gpu tests."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+import k8s_device_plugin_b200 as v
+from conftest import CUBIN, FAKE, HOOK_SO, LIBDIR, ROOT
+
+M = 1 << 20
+
+
+def _env(tmp_path, **kw):
+    env = dict(os.environ)
+    env.pop("LD_PRELOAD", None)
+    env.update({"FAKE_GPU_EXEC": "1", "FAKE_GPU_CTX_MIB": "16", "LIBCUDA_LOG_LEVEL": "0", "LD_LIBRARY_PATH": FAKE + ":" + env.get("LD_LIBRARY_PATH", ""),
+                "CUDA_DEVICE_MEMORY_SHARED_CACHE": str(tmp_path / "fx.cache"),
+                # engine geometry scaled to CPU-test sizes: 4 MiB staging slots, 8 GiB arena, 64 MiB host slabs
+                "VGPU_SWAP_CHUNK_MB": "4", "VGPU_SWAP_ARENA_GB": "8", "VGPU_SWAP_SLAB_MB": "64", "VGPU_SWAP_SPARE_MB": "16"})
+    env.update({k: str(val) for k, val in kw.items()})
+    return env
+
+
+def _swap_bench(tmp_path, args, **kw):
+    env = _env(tmp_path, LD_PRELOAD=HOOK_SO, CUDA_OVERSUBSCRIBE="true", **kw)
+    r = subprocess.run([os.path.join(LIBDIR, "swap_bench"), "--cubin", CUBIN] + args, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:] + r.stdout[-400:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_unmodified_app_swaps_and_verifies_on_the_functional_fake(tmp_path):
+    out = _swap_bench(tmp_path, ["--buffers", "32", "--mib", "16", "--steps", "96", "--warmup", "8", "--order", "cyclic"], CUDA_DEVICE_MEMORY_LIMIT_0="256m")
+    assert out["mismatches"] == 0 and out["verified"] == 1 and out["hooked_stats"] is True
+    assert out["page_in_bytes"] == 96 * 16 * M and out["page_out_bytes"] == 96 * 16 * M      # LRU worst case: every touch misses
+    assert out["faults"] == 96 and out["evictions"] == 96 and out["phys_reuses"] == 96 and out["phys_creates"] == 0
+    assert out["scan_cache_hits"] > 0                                                         # look-ahead serves most evictions
+
+
+def test_zipf_order_keeps_the_hot_set_resident(tmp_path):
+    out = _swap_bench(tmp_path, ["--buffers", "32", "--mib", "16", "--steps", "200", "--warmup", "50", "--order", "zipf"], CUDA_DEVICE_MEMORY_LIMIT_0="256m")
+    assert out["mismatches"] == 0
+    assert out["page_in_bytes"] < 200 * 16 * M * 0.8
+
+
+def test_reaper_thread_variant(tmp_path):
+    out = _swap_bench(tmp_path, ["--buffers", "24", "--mib", "16", "--steps", "72", "--warmup", "8", "--order", "cyclic"], CUDA_DEVICE_MEMORY_LIMIT_0="256m",
+                      VGPU_SWAP_ASYNC_UNMAP="1")
+    assert out["mismatches"] == 0 and out["page_in_bytes"] == 72 * 16 * M
+
+
+def test_hard_cap_without_oversubscribe(tmp_path):
+    env = _env(tmp_path, LD_PRELOAD=HOOK_SO, CUDA_DEVICE_MEMORY_LIMIT_0="128m")
+    r = subprocess.run([os.path.join(LIBDIR, "swap_bench"), "--cubin", CUBIN, "--buffers", "16", "--mib", "16", "--steps", "4"], env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode == 3 and "rc=-1" in r.stdout
+
+
+_ENGINE = r"""
+import ctypes as C, json, os, sys
+sys.path.insert(0, os.environ["VGPU_ROOT"])
+import k8s_device_plugin_b200 as v
+L = v.lib()
+drv = C.CDLL("libcuda.so.1")
+ctx = C.c_void_p(); dev = C.c_int(0)
+assert drv.cuInit(0) == 0 and drv.cuDeviceGet(C.byref(dev), 0) == 0 and drv.cuDevicePrimaryCtxRetain(C.byref(ctx), dev) == 0 and drv.cuCtxSetCurrent(ctx) == 0
+M = 1 << 20
+sw = v.Swap(dev=0, resident_cap=64 * M, chunk_bytes=4 * M)
+sizes = [2 * M, 6 * M, 16 * M, 4 * M, 10 * M, 2 * M, 12 * M, 8 * M, 14 * M, 6 * M, 16 * M, 2 * M]      # ragged: 98 MiB live over a 64 MiB cap
+bufs = []
+for i, n in enumerate(sizes):
+    p = sw.alloc(n); bufs.append(p)
+    sw.acquire([p], 0); L.vgpu_wl_fill(C.c_uint64(p), C.c_uint64(n // 8), C.c_uint64(i), None); sw.release([p], 0)
+touches = [0] * len(sizes)
+order = [0, 5, 2, 7, 1, 9, 3, 11, 4, 6, 8, 10, 2, 2, 0, 7, 7, 1, 10, 3]
+for t in order * 3:
+    sw.acquire([bufs[t]], 0); L.vgpu_wl_touch(C.c_uint64(bufs[t]), C.c_uint64(sizes[t] // 8), None); sw.release([bufs[t]], 0)
+    touches[t] += 1
+# two buffers in one admission (a kernel with two operands)
+sw.acquire([bufs[2], bufs[10]], 0); sw.release([bufs[2], bufs[10]], 0)
+table = sw.table()
+resident = sum((r.size + 2 * M - 1) // (2 * M) * (2 * M) for r in table if r.state & 1)
+bad = (C.c_uint64 * 1)(0)
+for i, p in enumerate(bufs):
+    sw.acquire([p], 0); L.vgpu_wl_verify(C.c_uint64(p), C.c_uint64(sizes[i] // 8), C.c_uint64(i), C.c_uint64(touches[i]), C.c_uint64(C.addressof(bad)), None); sw.release([p], 0)
+st = sw.stats()
+sw.free(bufs[3]); sw.free(bufs[0])
+st2 = sw.stats()
+print(json.dumps({"bad": int(bad[0]), "resident": resident, "faults": st["faults"], "evictions": st["evictions"], "page_in": st["page_in_bytes"], "page_out": st["page_out_bytes"],
+                  "live": st["live_bytes"], "live_after_free": st2["live_bytes"], "entries_after_free": st2["entries"], "host_bytes": st["host_bytes"]}))
+"""
+
+
+def test_engine_through_the_c_abi_with_ragged_sizes(tmp_path):
+    env = _env(tmp_path, VGPU_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-c", _ENGINE], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["bad"] == 0                                           # every word of every buffer survived its page-outs and page-ins
+    assert out["resident"] <= 64 * M                                 # the cap bounds mapped (granule-rounded) bytes at all times
+    assert out["live"] == sum([2, 6, 16, 4, 10, 2, 12, 8, 14, 6, 16, 2]) * M and out["live_after_free"] == out["live"] - 6 * M
+    assert out["entries_after_free"] == 10
+    assert out["faults"] > 10 and out["evictions"] >= out["faults"] - 1 and out["page_in"] > 0 and out["page_out"] >= out["page_in"]
+
+
+def _launch_loop(tmp_path, mib, seconds, **kw):
+    env = _env(tmp_path, **kw)
+    r = subprocess.run([os.path.join(LIBDIR, "launch_loop"), CUBIN, str(mib), str(seconds)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-1500:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+@pytest.mark.parametrize("quota", [30, 60])
+def test_limiter_bucket_arithmetic_on_the_functional_fake(tmp_path, quota):
+    """The emulated kernel occupies the calling thread for as long as it runs, so 'GPU busy' is wall time spent inside
+    cuLaunchKernel; the limiter's stamps see exactly that and must hold the launch RATE to the quota."""
+    bare = _launch_loop(tmp_path, 8, 2)
+    lim = _launch_loop(tmp_path, 8, 3, LD_PRELOAD=HOOK_SO, CUDA_DEVICE_SM_LIMIT=quota, GPU_CORE_UTILIZATION_POLICY="force")
+    ratio = (lim["launches"] / lim["wall_s"]) / (bare["launches"] / bare["wall_s"])
+    assert 0.75 * quota / 100 <= ratio <= 1.3 * quota / 100, (ratio, bare, lim)
