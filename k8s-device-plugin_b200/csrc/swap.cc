@@ -416,6 +416,28 @@ CUresult SwapEngine::map_row(int row) {
     wait_not_evicting(row);                      // its own previous mapping may still be queued at the reaper
     CUmemGenericAllocationHandle h;
     CUresult r = get_phys(side_[row].mapped, &h);   // may wait for the reaper with mu_ released: take references after
+    for (int attempt = 0; r == CUDA_ERROR_OUT_OF_MEMORY && attempt < 4; attempt++) {
+        // The device cannot give what the quota promises: on an overcommitted GPU other containers hold the rest (the
+        // reference leaves this case to UVM, which pages between processes). Live within what we have: lower the working
+        // cap to what is mapped now and make the room out of our own least recently used rows.
+        const uint64_t need = side_[row].mapped;
+        const uint64_t held = resident_mapped_ + evicting_mapped_;
+        if (held < need) break;                        // nothing of ours left to give up
+        if (!pressure_ || cfg_.resident_cap > held) {
+            if (!pressure_) {
+                quota_cap_ = std::max(quota_cap_, cfg_.resident_cap);
+                LOG_WARN("device %d: physical memory exhausted below the quota; resident cap %lu -> %lu MiB", dev_,
+                         (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(held >> 20));
+            } else {
+                LOG_INFO("device %d: upward probe failed; resident cap back to %lu MiB", dev_, (unsigned long)(held >> 20));
+            }
+            cfg_.resident_cap = held;
+            pressure_ = true;
+        }
+        pressure_events_++;
+        if (make_room(need, true) != CUDA_SUCCESS) break;
+        r = get_phys(need, &h);
+    }
     if (r != CUDA_SUCCESS) return r;
     ScopedNs t(&st_.host_vmm_ns);
     Side &s = side_[row];
@@ -960,6 +982,11 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
                 tr_ = &trace_.back();
                 tr_->t_begin = mono_ns();
             }
+        }
+        if (pressure_ && cfg_.resident_cap < quota_cap_ && (++pressure_probe_ & 31u) == 0) {
+            // probe upwards: the other tenants may have let go; a failed cuMemCreate simply lowers the cap again
+            cfg_.resident_cap = std::min(quota_cap_, cfg_.resident_cap + need);
+            if (cfg_.resident_cap == quota_cap_) pressure_ = false;
         }
         CUresult r = make_room(need, false);
         if (tr_) tr_->t_packs = mono_ns();

@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <condition_variable>
 #include <deque>
@@ -92,7 +93,12 @@ class SwapEngine {
     SwapStats stats();
     void set_profile(bool on) { cfg_.profile = on; }
     // the quota left for swappable memory shrinks/grows with the container's non-swappable bytes (context, small buffers)
-    void set_resident_cap(uint64_t cap) { std::lock_guard<std::mutex> g(mu_); cfg_.resident_cap = cap; }
+    void set_resident_cap(uint64_t cap) {
+        std::lock_guard<std::mutex> g(mu_);
+        quota_cap_ = cap;
+        // under physical pressure (see map_row) the working cap stays at what the device could actually give
+        cfg_.resident_cap = pressure_ ? std::min(cap, cfg_.resident_cap) : cap;
+    }
     // publish the counters into the container's shared region (vgpu_region.h extension block) after every call that
     // changes them; nullptr = do not publish
     void set_shared_record(vgpu_swap_record_t *rec) { std::lock_guard<std::mutex> g(mu_); shared_ = rec; publish_locked(); }
@@ -222,6 +228,13 @@ class SwapEngine {
     uint32_t scan_lookahead_ = 8;
     SwapStats st_;
     vgpu_swap_record_t *shared_ = nullptr;
+    // Physical pressure: the quota (quota_cap_) promises more than the device can give right now — other containers of an
+    // overcommitted GPU (DeviceMemoryScaling > 1, server.go:356) hold the rest. The working cap (cfg_.resident_cap) is
+    // lowered to what was obtainable and probed back up every few admissions.
+    uint64_t quota_cap_ = 0;
+    bool pressure_ = false;
+    uint32_t pressure_probe_ = 0;
+    uint64_t pressure_events_ = 0;
     void publish_locked();
     struct Prof { CUevent a, b; bool unpack; uint64_t bytes; };
     CUdeviceptr d_span_ = 0;                        // profiling: {min start, max end} per launch, pre-set to {~0, 0}

@@ -125,3 +125,14 @@ def test_limiter_bucket_arithmetic_on_the_functional_fake(tmp_path, quota):
     lim = _launch_loop(tmp_path, 8, 3, LD_PRELOAD=HOOK_SO, CUDA_DEVICE_SM_LIMIT=quota, GPU_CORE_UTILIZATION_POLICY="force")
     ratio = (lim["launches"] / lim["wall_s"]) / (bare["launches"] / bare["wall_s"])
     assert 0.75 * quota / 100 <= ratio <= 1.3 * quota / 100, (ratio, bare, lim)
+
+
+def test_engine_lives_within_the_physical_memory_an_overcommitted_gpu_can_give(tmp_path):
+    """DeviceMemoryScaling > 1 (server.go:356): quotas of the containers on a GPU add up to more than its HBM. The
+    reference leaves that to UVM, which pages between processes. Here the device hands out less than the quota promises
+    (fake device of 200 MiB, quota 384 MiB): the engine lowers its working cap to what it could get, evicts its own
+    rows instead of failing the application, and every word still verifies."""
+    out = _swap_bench(tmp_path, ["--buffers", "32", "--mib", "16", "--steps", "96", "--warmup", "8", "--order", "cyclic"],
+                      CUDA_DEVICE_MEMORY_LIMIT_0="384m", FAKE_GPU_TOTAL_MIB="200", LIBCUDA_LOG_LEVEL="2")
+    assert out["mismatches"] == 0 and out["verified"] == 1
+    assert out["page_in_bytes"] == 96 * 16 * M
