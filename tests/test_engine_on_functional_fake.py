@@ -136,3 +136,32 @@ def test_engine_lives_within_the_physical_memory_an_overcommitted_gpu_can_give(t
                       CUDA_DEVICE_MEMORY_LIMIT_0="384m", FAKE_GPU_TOTAL_MIB="200", LIBCUDA_LOG_LEVEL="2")
     assert out["mismatches"] == 0 and out["verified"] == 1
     assert out["page_in_bytes"] == 96 * 16 * M
+
+
+def test_swap_mode_accounting_matches_the_reference_binary_while_under_the_limit(tmp_path):
+    """CUDA_OVERSUBSCRIBE=true: the reference switches allocations above 2 MiB to cuMemAllocManaged (cuMemoryAllocate
+    @0x315da) and keeps charging the requested bytes; the new hook routes them to the swap engine and charges the same
+    bytes — return codes and every counter word agree after every op while live bytes stay under the limit. (Past the
+    limit the two differ by design: there the reference refuses, here the limit bounds RESIDENT bytes — DESIGN.md
+    'quota semantics'.)"""
+    from conftest import have_reference, run_replay
+    from trace_gen import gen_trace
+    if not have_reference():
+        pytest.skip("reference binary only exists in the build container")
+    import random
+    rng = random.Random(5)
+    lines, live = [], []
+    for i in range(300):
+        if live and (rng.random() < 0.45 or len(live) > 10):
+            lines.append(f"F {live.pop(rng.randrange(len(live)))}")
+        else:
+            lines.append(f"A {i} {rng.choice([1 << 20, 3 << 20, 4 << 20, 8 << 20, 16 << 20, (2 << 20) + 1])}")
+            live.append(i)
+    t = tmp_path / "t.txt"
+    t.write_text("\n".join(lines) + "\n")
+    env = {"FAKE_GPU_EXEC": "1", "FAKE_GPU_CTX_MIB": "16", "CUDA_OVERSUBSCRIBE": "true", "CUDA_DEVICE_MEMORY_LIMIT_0": "512m",
+           "VGPU_SWAP_CHUNK_MB": "4", "VGPU_SWAP_ARENA_GB": "8", "VGPU_SWAP_SLAB_MB": "64", "VGPU_SWAP_SPARE_MB": "16"}
+    new = run_replay(str(t), "new", dict(env, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "n.cache")))
+    ref = run_replay(str(t), "reference", dict(env, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "r.cache")))
+    assert new == ref
+    assert " rc=0 " in new.splitlines()[1] and "buf=" in new
