@@ -55,6 +55,9 @@ Config Config::from_env() {
         c.sm_limit[d] = sm ? sm : 100;  // do_init_device_sm_limits@0x41946: default 100
         c.virtual_limit[d] = limit_from_env("CUDA_DEVICE_MEMORY_VIRTUAL_LIMIT", d);
     }
+    if (const char *p = std::getenv("VGPU_SWAP_LIMIT_MODE")) c.limit_is_virtual = !strcasecmp(p, "virtual");
+    if (c.limit_is_virtual)
+        for (int d = 0; d < VGPU_MAX_DEVICES; d++) c.virtual_limit[d] = c.mem_limit[d];
     return c;
 }
 
@@ -255,6 +258,19 @@ SwapEngine *Runtime::swap(int dev) {
 
 bool Runtime::charge(int dev, size_t bytes) {
     if (!cfg_.oversubscribe) return region_->try_add(pid_, dev, bytes, VGPU_MEM_BUFFER, true);   // oom_check + add, reference semantics
+    if (cfg_.limit_is_virtual) {
+        // reference meaning of the limit (hard cap on live bytes), plus: what is not swappable is resident for life
+        if (!region_->try_add(pid_, dev, bytes, VGPU_MEM_BUFFER, true)) return false;
+        uint64_t lim = region_->limit(dev);
+        if (SwapEngine *e = swap(dev)) {
+            if (lim) {
+                uint64_t u = region_->usage(dev), live = e->live_bytes();
+                uint64_t fixed = u > live ? u - live : 0;
+                e->set_resident_cap(lim > fixed ? lim - fixed : 0);
+            }
+        }
+        return true;
+    }
     // swap mode: the quota bounds RESIDENT bytes. Non-swappable allocations are resident for life, so they are checked
     // against the quota net of what the swap engine can page out, and they shrink the engine's resident budget.
     uint64_t lim = region_->limit(dev);
@@ -290,12 +306,20 @@ CUresult Runtime::swap_alloc(CUdeviceptr *dptr, size_t bytes, int dev) {
             uint64_t fixed = region_ ? region_->usage(dev) : 0;
             uint64_t cap = lim > fixed ? lim - fixed : 0;
             if (lim && cap < (64ull << 20)) { LOG_ERROR("gpumem quota %lu leaves no room for swappable memory", (unsigned long)lim); return CUDA_ERROR_OUT_OF_MEMORY; }
-            SwapConfig sc = SwapConfig::from_env(lim ? cap : 0, cfg_.virtual_limit[dev]);
+            SwapConfig sc = SwapConfig::from_env(lim ? cap : 0, cfg_.limit_is_virtual ? 0 : cfg_.virtual_limit[dev]);   // virtual mode: the region check is the cap
             swap_[dev].reset(SwapEngine::create(dev, sc));
             if (!swap_[dev]) { LOG_ERROR("swap engine unavailable on device %d", dev); return CUDA_ERROR_NOT_SUPPORTED; }
             if (region_) swap_[dev]->set_shared_record(region_->swap_record(pid_, dev));   // counters for the node monitor
         }
         e = swap_[dev].get();
+    }
+    if (cfg_.limit_is_virtual && region_) {
+        // oom_check(dev, size) of the reference: usage + size > limit refuses, oversubscribed or not
+        if (!region_->try_add(pid_, dev, bytes, VGPU_MEM_BUFFER, true)) return CUDA_ERROR_OUT_OF_MEMORY;
+        CUresult r = e->alloc(dptr, bytes);
+        if (r != CUDA_SUCCESS) { region_->sub(pid_, dev, bytes, VGPU_MEM_BUFFER); return r; }
+        track(*dptr, bytes, dev, AllocKind::Swap);
+        return CUDA_SUCCESS;
     }
     CUresult r = e->alloc(dptr, bytes);
     if (r != CUDA_SUCCESS) return r;

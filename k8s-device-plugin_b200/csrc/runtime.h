@@ -41,6 +41,10 @@ struct Config {
     uint64_t mem_limit[VGPU_MAX_DEVICES] = {};
     uint64_t sm_limit[VGPU_MAX_DEVICES] = {};
     uint64_t virtual_limit[VGPU_MAX_DEVICES] = {};  // swap mode only: CUDA_DEVICE_MEMORY_VIRTUAL_LIMIT[_i]; 0 = host pool bound
+    // swap mode only. false (default): the gpumem limit bounds RESIDENT bytes, live bytes may exceed it (SURVEY.md §8d
+    // cfg 3). true (VGPU_SWAP_LIMIT_MODE=virtual): the reference's meaning — the limit is a hard cap on live bytes
+    // (oom_check still applies under CUDA_OVERSUBSCRIBE), and paging only starts when the DEVICE runs short
+    bool limit_is_virtual = false;
     static Config from_env();
 };
 

@@ -165,3 +165,50 @@ def test_swap_mode_accounting_matches_the_reference_binary_while_under_the_limit
     ref = run_replay(str(t), "reference", dict(env, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "r.cache")))
     assert new == ref
     assert " rc=0 " in new.splitlines()[1] and "buf=" in new
+
+
+def test_virtual_limit_mode_is_the_references_meaning_of_the_limit_past_the_limit_too(tmp_path):
+    """VGPU_SWAP_LIMIT_MODE=virtual: CUDA_DEVICE_MEMORY_LIMIT is a hard cap on LIVE bytes under CUDA_OVERSUBSCRIBE as well
+    (the reference's oom_check does not look at the switch), cuMemGetInfo reports limit - usage, and paging only starts
+    when the device itself runs short. The whole stream — breaches, frees, cuMemGetInfo — equals the reference binary's."""
+    from conftest import have_reference, run_replay
+    if not have_reference():
+        pytest.skip("reference binary only exists in the build container")
+    import random
+    rng = random.Random(11)
+    lines, live = [], []
+    for i in range(400):
+        r = rng.random()
+        if live and (r < 0.35 or len(live) > 14):
+            lines.append(f"F {live.pop(rng.randrange(len(live)))}")
+        elif r < 0.45:
+            lines.append("I")
+        else:
+            lines.append(f"A {i} {rng.choice([1 << 20, 3 << 20, 4 << 20, 8 << 20, 16 << 20, 32 << 20, (2 << 20) + 1, 4096])}")
+            live.append(i)
+    t = tmp_path / "t.txt"
+    t.write_text("\n".join(lines) + "\n")
+    env = {"FAKE_GPU_EXEC": "1", "FAKE_GPU_CTX_MIB": "16", "CUDA_OVERSUBSCRIBE": "true", "CUDA_DEVICE_MEMORY_LIMIT_0": "128m",
+           "VGPU_SWAP_LIMIT_MODE": "virtual", "VGPU_SWAP_CHUNK_MB": "4", "VGPU_SWAP_ARENA_GB": "8", "VGPU_SWAP_SLAB_MB": "64", "VGPU_SWAP_SPARE_MB": "16"}
+    new = run_replay(str(t), "new", dict(env, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "n.cache"))).splitlines()
+    ref = run_replay(str(t), "reference", dict(env, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "r.cache"))).splitlines()
+    # a failed allocation leaves the pointer table entry 0; the reference answers cuMemFree_v2(0) with 0 like the product
+    assert new == ref, "\n".join(f"{a}   |   {b}" for a, b in zip(new, ref) if a != b)
+    assert sum(" rc=-1 " in l for l in new) > 10                      # the limit was really crossed, many times
+
+
+def test_virtual_limit_mode_pages_only_under_physical_pressure(tmp_path):
+    # 320 MiB live under a 384 MiB limit on a device that can only give ~160 MiB: admitted by the limit, paged by the engine
+    out = _swap_bench(tmp_path, ["--buffers", "20", "--mib", "16", "--steps", "60", "--warmup", "4", "--order", "cyclic"],
+                      CUDA_DEVICE_MEMORY_LIMIT_0="384m", FAKE_GPU_TOTAL_MIB="200", VGPU_SWAP_LIMIT_MODE="virtual")
+    assert out["mismatches"] == 0 and out["page_in_bytes"] > 0
+    # the same application fits a device that has the memory: no paging at all
+    out = _swap_bench(tmp_path, ["--buffers", "20", "--mib", "16", "--steps", "60", "--warmup", "4", "--order", "cyclic"],
+                      CUDA_DEVICE_MEMORY_LIMIT_0="384m", VGPU_SWAP_LIMIT_MODE="virtual")
+    assert out["mismatches"] == 0 and out["page_in_bytes"] == 0 and out["faults"] == 0
+    # and one buffer more than the limit admits is refused, as in the reference
+    env = _env(tmp_path, LD_PRELOAD=HOOK_SO, CUDA_OVERSUBSCRIBE="true", CUDA_DEVICE_MEMORY_LIMIT_0="256m", VGPU_SWAP_LIMIT_MODE="virtual",
+               CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "other.cache"))      # a region keeps its creator's limit
+    r = subprocess.run([os.path.join(LIBDIR, "swap_bench"), "--cubin", CUBIN, "--buffers", "20", "--mib", "16", "--steps", "4"], env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode == 3 and "rc=-1" in r.stdout
