@@ -1,5 +1,7 @@
 // runtime.cc — see runtime.h.
 #include "runtime.h"
+#include <thread>
+#include <csignal>
 
 #include <fcntl.h>
 #include <pthread.h>
@@ -215,8 +217,73 @@ void Runtime::post_init(bool late) {
     else LOG_WARN("cuInit was not intercepted; initialising on first use (context size not measured)");
     int pct = (int)(region_ ? region_->sm_limit(0) : cfg_.sm_limit[0]);
     limiter_.reset(new Limiter(pct, region_ ? region_->raw() : nullptr, cfg_.util_policy));
+    start_memory_monitor(pct);
     LOG_MSG("Initialized: oversubscribe=%d mem_limit0=%lu sm_limit0=%d", (int)cfg_.oversubscribe,
             (unsigned long)(region_ ? region_->limit(0) : 0), pct);
+}
+
+// The reference's NVML-side safety net. Its utilization_watcher thread (only running when 0 < sm_limit < 100,
+// init_utilization_watcher@0x46937) calls get_used_gpu_utilization@0x46220 every 120 ms, which feeds every process NVML
+// lists on a device into set_gpu_device_memory_monitor@0x42301: the slot whose hostpid matches gets
+// monitorused[dev] = usedGpuMemory; under MEMORY_OVERRIDE=1 also offset = used - total, total = used; and when
+// (double)used > (double)limit * 1.1 (.rodata@0x56220) with the active OOM killer enabled (ACTIVE_OOM_KILLER, default on:
+// set_active_oom_killer@0x43ffa) every process of the container is killed (active_oom_killer@0x41e55). It catches what
+// the intercept cannot see. Same thread condition, period, arithmetic and log line here.
+static bool oom_killer_enabled() {
+    const char *e = std::getenv("ACTIVE_OOM_KILLER");
+    if (!e) return true;
+    if (!std::strcmp(e, "false") || !std::strcmp(e, "0")) return false;
+    return true;
+}
+
+void Runtime::start_memory_monitor(int sm_limit_percent) {
+    if (sm_limit_percent <= 0 || sm_limit_percent >= 100 || !region_ || !nvml_ready()) return;
+    if (cfg_.util_policy == 2) return;   // GPU_CORE_UTILIZATION_POLICY=disable: no watcher thread in the reference either
+    bool any = false;
+    for (int d = 0; d < VGPU_MAX_DEVICES; d++) any |= region_->limit(d) != 0;
+    if (!any) return;
+    const bool kill_enabled = oom_killer_enabled();
+    const bool memory_override = env_true("MEMORY_OVERRIDE") || (std::getenv("MEMORY_OVERRIDE") && std::atoi(std::getenv("MEMORY_OVERRIDE")) == 1);
+    std::thread([this, kill_enabled, memory_override] {
+        const NvmlTable &n = nvml();
+        if (!n.nvmlDeviceGetCount_v2 || !n.nvmlDeviceGetHandleByIndex_v2 || !n.nvmlDeviceGetComputeRunningProcesses_v3) return;
+        for (;;) {
+            struct timespec ts = {0, 120000000};   // g_wait .rodata@0x56240
+            nanosleep(&ts, nullptr);
+            unsigned cnt = 0;
+            if (n.nvmlDeviceGetCount_v2(&cnt) != NVML_SUCCESS) continue;
+            for (unsigned d = 0; d < cnt && d < VGPU_MAX_DEVICES; d++) {
+                uint64_t lim = region_->limit((int)d);
+                nvmlDevice_t h;
+                if (n.nvmlDeviceGetHandleByIndex_v2(d, &h) != NVML_SUCCESS) continue;
+                nvmlProcessInfo_t infos[64];
+                unsigned np = 64;
+                if (n.nvmlDeviceGetComputeRunningProcesses_v3(h, &np, infos) != NVML_SUCCESS) continue;
+                for (unsigned k = 0; k < np; k++) {
+                    uint64_t used = infos[k].usedGpuMemory;
+                    bool over = false;
+                    region_->lock();
+                    vgpu_shared_region_t *r = region_->raw();
+                    for (int i = 0; i < r->proc_num; i++) {
+                        if (r->procs[i].hostpid != (int32_t)infos[k].pid) continue;
+                        r->procs[i].monitorused[d] = used;
+                        if (memory_override) { r->procs[i].used[d].offset = used - r->procs[i].used[d].total; r->procs[i].used[d].total = used; }
+                        if (lim && (double)used > (double)lim * 1.1) over = true;
+                    }
+                    region_->unlock();
+                    if (over && kill_enabled) {
+                        LOG_ERROR("device OOM encountered: usage=%lu limit=%lu", (unsigned long)used, (unsigned long)lim);
+                        std::vector<int32_t> pids;
+                        region_->lock();
+                        for (int i = 0; i < r->proc_num; i++) pids.push_back(r->procs[i].pid);
+                        region_->unlock();
+                        for (int32_t p : pids) if (p > 0 && p != pid_) kill(p, SIGKILL);
+                        kill(pid_, SIGKILL);
+                    }
+                }
+            }
+        }
+    }).detach();
 }
 
 CUresult Runtime::init(unsigned flags) {
@@ -256,6 +323,13 @@ SwapEngine *Runtime::swap(int dev) {
     return swap_[dev].get();
 }
 
+// what the engine may keep resident: the quota minus everything that is resident for life (context, non-swappable
+// allocations) minus the engine's own staging rings
+static uint64_t room_for_engine(uint64_t lim, uint64_t fixed, const SwapEngine *e) {
+    uint64_t taken = fixed + (e ? e->device_overhead() : 0);
+    return lim > taken ? lim - taken : 0;
+}
+
 bool Runtime::charge(int dev, size_t bytes) {
     if (!cfg_.oversubscribe) return region_->try_add(pid_, dev, bytes, VGPU_MEM_BUFFER, true);   // oom_check + add, reference semantics
     if (cfg_.limit_is_virtual) {
@@ -266,7 +340,7 @@ bool Runtime::charge(int dev, size_t bytes) {
             if (lim) {
                 uint64_t u = region_->usage(dev), live = e->live_bytes();
                 uint64_t fixed = u > live ? u - live : 0;
-                e->set_resident_cap(lim > fixed ? lim - fixed : 0);
+                e->set_resident_cap(room_for_engine(lim, fixed, e));
             }
         }
         return true;
@@ -279,7 +353,7 @@ bool Runtime::charge(int dev, size_t bytes) {
         uint64_t u = region_->usage(dev), live = e ? e->live_bytes() : 0;
         uint64_t fixed = u > live ? u - live : 0;
         if (fixed + bytes > lim) { LOG_ERROR("Device %d OOM %lu / %lu (non-swappable)", dev, (unsigned long)(fixed + bytes), (unsigned long)lim); return false; }
-        if (e) e->set_resident_cap(lim - fixed - bytes);
+        if (e) e->set_resident_cap(room_for_engine(lim, fixed + bytes, e));
     }
     region_->add(pid_, dev, bytes, VGPU_MEM_BUFFER);
     return true;
@@ -293,7 +367,7 @@ void Runtime::uncharge(int dev, size_t bytes) {
     if (lim && e) {
         uint64_t u = region_->usage(dev), live = e->live_bytes();
         uint64_t fixed = u > live ? u - live : 0;
-        e->set_resident_cap(lim > fixed ? lim - fixed : 0);
+        e->set_resident_cap(room_for_engine(lim, fixed, e));
     }
 }
 
@@ -305,8 +379,12 @@ CUresult Runtime::swap_alloc(CUdeviceptr *dptr, size_t bytes, int dev) {
             uint64_t lim = region_ ? region_->limit(dev) : 0;
             uint64_t fixed = region_ ? region_->usage(dev) : 0;
             uint64_t cap = lim > fixed ? lim - fixed : 0;
-            if (lim && cap < (64ull << 20)) { LOG_ERROR("gpumem quota %lu leaves no room for swappable memory", (unsigned long)lim); return CUDA_ERROR_OUT_OF_MEMORY; }
             SwapConfig sc = SwapConfig::from_env(lim ? cap : 0, cfg_.limit_is_virtual ? 0 : cfg_.virtual_limit[dev]);   // virtual mode: the region check is the cap
+            if (lim) {
+                uint64_t overhead = 2ull * sc.ring_slots * sc.chunk_bytes;     // == SwapEngine::device_overhead()
+                sc.resident_cap = cap > overhead ? cap - overhead : 0;
+                if (sc.resident_cap < (32ull << 20)) { LOG_ERROR("gpumem quota %lu leaves no room for swappable memory", (unsigned long)lim); return CUDA_ERROR_OUT_OF_MEMORY; }
+            }
             swap_[dev].reset(SwapEngine::create(dev, sc));
             if (!swap_[dev]) { LOG_ERROR("swap engine unavailable on device %d", dev); return CUDA_ERROR_NOT_SUPPORTED; }
             if (region_) swap_[dev]->set_shared_record(region_->swap_record(pid_, dev));   // counters for the node monitor

@@ -112,6 +112,7 @@ class Runtime {
     int current_device();
     void post_init(bool late);              // postInit@0x15d63
     void measure_context_size();            // set_task_pid@0x16a7f
+    void start_memory_monitor(int sm_limit_percent);   // set_gpu_device_memory_monitor@0x42301 + active_oom_killer@0x41e55
     void wait_running();                    // wait_status_self(1) loop of every wrapper
     bool track(CUdeviceptr base, size_t size, int dev, AllocKind kind);
     CUresult swap_alloc(CUdeviceptr *dptr, size_t bytes, int dev);

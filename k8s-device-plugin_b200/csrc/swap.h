@@ -104,6 +104,10 @@ class SwapEngine {
     void set_shared_record(vgpu_swap_record_t *rec) { std::lock_guard<std::mutex> g(mu_); shared_ = rec; publish_locked(); }
     CUresult drain();                          // wait for all side-stream work (tests / shutdown)
     const SwapConfig &config() const { return cfg_; }
+    // device memory the engine itself holds next to the application's resident buffers: both staging rings (the table,
+    // scan scratch and span words are a few hundred KiB and not counted). The hook takes it out of the room it gives
+    // the engine, so that the container's PHYSICAL footprint stays within its gpumem quota.
+    uint64_t device_overhead() const { return 2ull * cfg_.ring_slots * cfg_.chunk_bytes; }
     uint64_t live_bytes() const { return live_bytes_; }
 
     // diagnostics (VGPU_SWAP_TRACE=n): host timestamps and timed GPU events of the first n missing admissions after

@@ -206,3 +206,43 @@ def test_two_device_container_lanes_match_the_reference_binary(tmp_path):
     f = lambda line, key: int(line.split(key + "=")[1].split()[0])
     assert f(new[7], "rc") == -1 and new[8].endswith("free=0 total=%d" % (32 * M))      # device 1: 16 ctx + 8 + 8 fills 32m, the third 8 MiB is refused
     assert f(new[12], "rc") == -1 and f(new[11], "rc") == 0                             # device 0: 16 + 8 + 30 fits 64m, another 30 does not
+
+
+def _replay_raw(trace, preload, env_extra):
+    import signal
+    from conftest import OREF as _OREF
+    env = dict(os.environ)
+    env.pop("LD_PRELOAD", None)
+    env.update({"LIBCUDA_LOG_LEVEL": "0", "LD_LIBRARY_PATH": FAKE + ":" + env.get("LD_LIBRARY_PATH", ""), "LD_PRELOAD": preload})
+    env.update(env_extra)
+    r = subprocess.run([os.path.join(_OREF, "trace_replay"), trace], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=60)
+    return r.returncode, r.stdout, signal.SIGKILL
+
+
+def test_active_oom_killer_matches_the_reference(tmp_path):
+    """The NVML-side safety net of the reference's watcher thread (set_gpu_device_memory_monitor@0x42301,
+    active_oom_killer@0x41e55): with a gpucores limit set, a process whose NVML-visible usage exceeds 1.1 x limit is
+    killed together with its container — on by default, off with ACTIVE_OOM_KILLER=false. Driven with an allocation the
+    intercept does not see (cuMemCreate under VGPU_REFERENCE_COVERAGE=1, i.e. the reference's blind spot)."""
+    from conftest import REF_SO, SHIM_SO
+    t = _write(tmp_path, "C 0 %d\nS 1200\nI\n" % (200 << 20))
+    base = {"CUDA_DEVICE_MEMORY_LIMIT_0": "128m", "CUDA_DEVICE_SM_LIMIT": "50", "FAKE_GPU_CTX_MIB": "16", "VGPU_REFERENCE_COVERAGE": "1"}
+    rc, out, KILL = _replay_raw(t, HOOK_SO, dict(base, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "n1.cache")))
+    assert rc == -KILL and "2 I" not in out
+    rc, out_off, _ = _replay_raw(t, HOOK_SO, dict(base, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "n2.cache"), ACTIVE_OOM_KILLER="false"))
+    assert rc == 0 and out_off.splitlines()[-1].endswith("free=117440512 total=134217728")
+    # without a gpucores limit there is no watcher thread and nothing is killed — in the reference as well
+    rc, _, _ = _replay_raw(t, HOOK_SO, dict({k: val for k, val in base.items() if k != "CUDA_DEVICE_SM_LIMIT"}, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "n3.cache")))
+    assert rc == 0
+    # with the product's own coverage the allocation is simply refused by the quota: nothing to kill
+    rc, out_cov, _ = _replay_raw(t, HOOK_SO, dict({k: val for k, val in base.items() if k != "VGPU_REFERENCE_COVERAGE"}, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "n4.cache")))
+    assert rc == 0 and " rc=2 " in out_cov.splitlines()[1]
+    if have_reference():
+        os.makedirs("/tmp/vgpulock", exist_ok=True)
+        pre = SHIM_SO + ":" + REF_SO
+        rc, out, _ = _replay_raw(t, pre, dict(base, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "r1.cache")))
+        assert rc == -KILL and "2 I" not in out
+        rc, out_ref_off, _ = _replay_raw(t, pre, dict(base, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "r2.cache"), ACTIVE_OOM_KILLER="false"))
+        assert rc == 0 and out_ref_off == out_off
+        rc, _, _ = _replay_raw(t, pre, dict({k: val for k, val in base.items() if k != "CUDA_DEVICE_SM_LIMIT"}, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "r3.cache")))
+        assert rc == 0
