@@ -40,6 +40,26 @@ static bool strict_errors() {
 }
 static const CUresult kQuotaBreachAlloc = static_cast<CUresult>(-1);
 
+// load_env_from_file@0x415a4 (called from nvml_preInit@0x24029 with "/overrideEnv"): every line KEY=VALUE of that file,
+// trailing newline stripped, split at the FIRST '=', is setenv'd over the process environment before anything is read
+// from it — the operator's way to change a running container's limits. (VGPU_OVERRIDE_ENV_FILE moves the path; tests.)
+static void load_env_from_file() {
+    const char *path = std::getenv("VGPU_OVERRIDE_ENV_FILE");
+    FILE *f = std::fopen(path && *path ? path : "/overrideEnv", "r");
+    if (!f) return;
+    char line[10000];
+    while (std::fgets(line, sizeof line, f)) {
+        size_t n = std::strlen(line);
+        if (n && line[n - 1] == '\n') line[n - 1] = 0;
+        char *eq = std::strchr(line, '=');
+        if (!eq) continue;
+        *eq = 0;
+        setenv(line, eq + 1, 1);
+        LOG_INFO("SET %s to %s", line, eq + 1);
+    }
+    std::fclose(f);
+}
+
 Config Config::from_env() {
     Config c;
     c.oversubscribe = env_true("CUDA_OVERSUBSCRIBE");
@@ -75,6 +95,7 @@ bool Runtime::ensure_initialized() {
     if (inited_.load(std::memory_order_acquire)) return region_ != nullptr;
     std::lock_guard<std::mutex> g(init_mu_);
     if (inited_.load(std::memory_order_relaxed)) return region_ != nullptr;
+    load_env_from_file();
     cfg_ = Config::from_env();
     pid_ = getpid();
     char uuids[VGPU_MAX_DEVICES][VGPU_UUID_LEN];

@@ -246,3 +246,14 @@ def test_active_oom_killer_matches_the_reference(tmp_path):
         assert rc == 0 and out_ref_off == out_off
         rc, _, _ = _replay_raw(t, pre, dict({k: val for k, val in base.items() if k != "CUDA_DEVICE_SM_LIMIT"}, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "r3.cache")))
         assert rc == 0
+
+
+def test_override_env_file_changes_the_limits(tmp_path):
+    """load_env_from_file@0x415a4: KEY=VALUE lines of /overrideEnv are set over the environment before the limits are read."""
+    ov = tmp_path / "overrideEnv"
+    ov.write_text("CUDA_DEVICE_MEMORY_LIMIT_0=64m\nnot a pair\nFOO=a=b\n")
+    t = _write(tmp_path, "A 0 %d\nI\n" % (100 << 20))
+    out = run_replay(t, "new", _env(tmp_path, "1g", VGPU_OVERRIDE_ENV_FILE=str(ov), FAKE_GPU_CTX_MIB="16")).splitlines()
+    assert " rc=-1 " in out[1] and out[2].endswith("total=67108864")         # the file's 64m won over the environment's 1g
+    out = run_replay(t, "new", dict(_env(tmp_path, "1g", FAKE_GPU_CTX_MIB="16"), CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "b.cache"))).splitlines()
+    assert " rc=0 " in out[1] and out[2].endswith("total=1073741824")
