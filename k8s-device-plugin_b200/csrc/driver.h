@@ -47,7 +47,7 @@ namespace vgpu {
 #define VGPU_NVML_FUNCS(X)                                                                                        \
     X(nvmlInit_v2) X(nvmlShutdown) X(nvmlDeviceGetCount_v2) X(nvmlDeviceGetHandleByIndex_v2) X(nvmlDeviceGetUUID) \
     X(nvmlDeviceGetMemoryInfo) X(nvmlDeviceGetMemoryInfo_v2) X(nvmlDeviceGetComputeRunningProcesses_v3)           \
-    X(nvmlDeviceGetProcessUtilization) X(nvmlDeviceGetIndex) X(nvmlErrorString)
+    X(nvmlDeviceGetProcessUtilization) X(nvmlDeviceGetIndex) X(nvmlErrorString) X(nvmlDeviceGetHandleByUUID)
 
 struct DriverTable {
 #define X(name) decltype(&::name) name = nullptr;

@@ -191,6 +191,22 @@ static bool unified_lock() {
 }
 static void unified_unlock() { ::remove("/tmp/vgpulock/lock"); }
 
+// CUDA ordinal -> NVML handle by UUID (the reference keeps cuda_to_nvml_map@0x62c80, built by
+// map_cuda_visible_devices@0x17e5a): CUDA_VISIBLE_DEVICES may reorder or hide devices, NVML enumerates all of them.
+static bool nvml_handle_for_cuda(int cuda_dev, nvmlDevice_t *h) {
+    const NvmlTable &n = nvml();
+    const DriverTable &d = drv();
+    CUuuid u;
+    if (n.nvmlDeviceGetHandleByUUID && d.cuDeviceGetUuid_v2 && d.cuDeviceGetUuid_v2(&u, cuda_dev) == CUDA_SUCCESS) {
+        const unsigned char *b = reinterpret_cast<const unsigned char *>(u.bytes);
+        char s[64];
+        std::snprintf(s, sizeof s, "GPU-%02x%02x%02x%02x-%02x%02x-%02x%02x-%02x%02x-%02x%02x%02x%02x%02x%02x", b[0], b[1], b[2], b[3], b[4], b[5],
+                      b[6], b[7], b[8], b[9], b[10], b[11], b[12], b[13], b[14], b[15]);
+        if (n.nvmlDeviceGetHandleByUUID(s, h) == NVML_SUCCESS) return true;
+    }
+    return n.nvmlDeviceGetHandleByIndex_v2 && n.nvmlDeviceGetHandleByIndex_v2((unsigned)cuda_dev, h) == NVML_SUCCESS;
+}
+
 void Runtime::measure_context_size() {
     // set_task_pid@0x16a7f (utils.c:L135-202): NVML's compute-process list before and after creating the primary
     // context; the new entry is this process as the HOST sees it (pid namespace) and its usedGpuMemory is what a
@@ -199,7 +215,7 @@ void Runtime::measure_context_size() {
     const NvmlTable &n = nvml();
     const DriverTable &d = drv();
     nvmlDevice_t h;
-    if (n.nvmlDeviceGetHandleByIndex_v2(0, &h) != NVML_SUCCESS) { LOG_WARN("SET_TASK_PID FAILED."); return; }
+    if (!nvml_handle_for_cuda(0, &h)) { LOG_WARN("SET_TASK_PID FAILED."); return; }
     bool locked = unified_lock();
     std::vector<nvmlProcessInfo_t> before(1024), after(1024);
     unsigned nb = (unsigned)before.size(), na = (unsigned)after.size();
@@ -271,12 +287,12 @@ void Runtime::start_memory_monitor(int sm_limit_percent) {
         for (;;) {
             struct timespec ts = {0, 120000000};   // g_wait .rodata@0x56240
             nanosleep(&ts, nullptr);
-            unsigned cnt = 0;
-            if (n.nvmlDeviceGetCount_v2(&cnt) != NVML_SUCCESS) continue;
-            for (unsigned d = 0; d < cnt && d < VGPU_MAX_DEVICES; d++) {
-                uint64_t lim = region_->limit((int)d);
+            int cnt = 0;
+            if (!drv().cuDeviceGetCount || drv().cuDeviceGetCount(&cnt) != CUDA_SUCCESS) continue;
+            for (int d = 0; d < cnt && d < VGPU_MAX_DEVICES; d++) {      // d = CUDA ordinal = region lane
+                uint64_t lim = region_->limit(d);
                 nvmlDevice_t h;
-                if (n.nvmlDeviceGetHandleByIndex_v2(d, &h) != NVML_SUCCESS) continue;
+                if (!nvml_handle_for_cuda(d, &h)) continue;
                 nvmlProcessInfo_t infos[64];
                 unsigned np = 64;
                 if (n.nvmlDeviceGetComputeRunningProcesses_v3(h, &np, infos) != NVML_SUCCESS) continue;
