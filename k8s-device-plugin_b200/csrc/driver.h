@@ -18,7 +18,7 @@ namespace vgpu {
     X(cuCtxGetDevice) X(cuCtxSynchronize)                                                                         \
     X(cuMemAlloc_v2) X(cuMemAllocManaged) X(cuMemAllocPitch_v2) X(cuMemFree_v2) X(cuMemGetInfo_v2)                \
     X(cuMemHostAlloc) X(cuMemFreeHost) X(cuMemHostGetDevicePointer_v2) X(cuMemHostRegister_v2)                    \
-    X(cuMemAllocHost_v2) X(cuMemGetAddressRange_v2)                                                               \
+    X(cuMemAllocHost_v2) X(cuMemGetAddressRange_v2) X(cuMemHostUnregister) X(cuMipmappedArrayCreate) X(cuMipmappedArrayDestroy) X(cuPointerGetAttribute) X(cuPointerGetAttributes)                                                               \
     X(cuMemAddressReserve) X(cuMemAddressFree) X(cuMemCreate) X(cuMemRelease) X(cuMemMap) X(cuMemUnmap)           \
     X(cuMemSetAccess) X(cuMemGetAllocationGranularity)                                                            \
     X(cuMemcpyHtoD_v2) X(cuMemcpyDtoH_v2) X(cuMemcpyDtoD_v2) X(cuMemcpyHtoDAsync_v2) X(cuMemcpyDtoHAsync_v2)      \

@@ -61,6 +61,23 @@ VGPU_EXPORT CUresult cuMemAllocHost_v2(void **pp, size_t bytesize) {
     return r;
 }
 
+VGPU_EXPORT CUresult cuMemHostRegister_v2(void *p, size_t bytesize, unsigned int flags) {   // cuMemHostRegister_v2@0x32842
+    Runtime &rt = Runtime::get();
+    rt.ensure_initialized();
+    if (!drv().cuMemHostRegister_v2) return CUDA_ERROR_NOT_SUPPORTED;
+    CUresult r = drv().cuMemHostRegister_v2(p, bytesize, flags);
+    if (r == CUDA_SUCCESS && rt.check_oom()) { if (drv().cuMemHostUnregister) drv().cuMemHostUnregister(p); return CUDA_ERROR_OUT_OF_MEMORY; }
+    return r;
+}
+VGPU_EXPORT CUresult cuMipmappedArrayCreate(CUmipmappedArray *h, const CUDA_ARRAY3D_DESCRIPTOR *desc, unsigned int levels) {   // @0x36d29
+    Runtime &rt = Runtime::get();
+    rt.ensure_initialized();
+    if (!drv().cuMipmappedArrayCreate) return CUDA_ERROR_NOT_SUPPORTED;
+    CUresult r = drv().cuMipmappedArrayCreate(h, desc, levels);
+    if (r == CUDA_SUCCESS && rt.check_oom()) { if (drv().cuMipmappedArrayDestroy) drv().cuMipmappedArrayDestroy(*h); return CUDA_ERROR_OUT_OF_MEMORY; }
+    return r;
+}
+
 VGPU_EXPORT CUresult cuLaunchKernel(CUfunction f, unsigned int gridDimX, unsigned int gridDimY, unsigned int gridDimZ,
                                     unsigned int blockDimX, unsigned int blockDimY, unsigned int blockDimZ,
                                     unsigned int sharedMemBytes, CUstream hStream, void **kernelParams, void **extra) {
@@ -213,6 +230,35 @@ VGPU_EXPORT CUresult cuMemsetD32Async_ptsz(CUdeviceptr dst, unsigned int v, size
 }
 #undef PTS
 
+// Pointer queries. The reference post-processes cuPointerGetAttributes@0x33187 because its swap switch turns every
+// large allocation into managed memory: MEMORY_TYPE := check_memory_type(ptr), IS_MANAGED := 0. Here swappable buffers
+// are VMM mappings — device memory to the driver — but a PAGED-OUT buffer has no mapping at all and the driver would
+// answer INVALID_VALUE, so the buffer is made resident first. The reference's overrides are applied to tracked pointers
+// only: its check_memory_type answers HOST for every pointer it did not hand out (VMM ranges mapped by the application,
+// IPC imports), which is wrong for those.
+static void fix_pointer_attribute(CUpointer_attribute a, void *data, CUdeviceptr ptr) {
+    if (!data || Runtime::get().check_memory_type(ptr) != 2) return;
+    if (a == CU_POINTER_ATTRIBUTE_MEMORY_TYPE) *static_cast<unsigned int *>(data) = CU_MEMORYTYPE_DEVICE;
+    else if (a == CU_POINTER_ATTRIBUTE_IS_MANAGED) *static_cast<unsigned int *>(data) = 0;
+}
+VGPU_EXPORT CUresult cuPointerGetAttribute(void *data, CUpointer_attribute attribute, CUdeviceptr ptr) {
+    if (!drv().cuPointerGetAttribute) return CUDA_ERROR_NOT_SUPPORTED;
+    TOUCH1(ptr, 1, nullptr);
+    CUresult r = drv().cuPointerGetAttribute(data, attribute, ptr);
+    TOUCH_DONE(nullptr);
+    if (r == CUDA_SUCCESS) fix_pointer_attribute(attribute, data, ptr);
+    return r;
+}
+VGPU_EXPORT CUresult cuPointerGetAttributes(unsigned int numAttributes, CUpointer_attribute *attributes, void **data, CUdeviceptr ptr) {
+    if (!drv().cuPointerGetAttributes) return CUDA_ERROR_NOT_SUPPORTED;
+    TOUCH1(ptr, 1, nullptr);
+    CUresult r = drv().cuPointerGetAttributes(numAttributes, attributes, data, ptr);
+    TOUCH_DONE(nullptr);
+    if (r == CUDA_SUCCESS && attributes && data)
+        for (unsigned int i = 0; i < numAttributes; i++) fix_pointer_attribute(attributes[i], data[i], ptr);
+    return r;
+}
+
 // extras the reference exports for its own tooling
 VGPU_EXPORT CUresult cuMemoryAllocate(CUdeviceptr *dptr, size_t bytesize, size_t *bytesallocated, void *data) {
     (void)data;                                   // cuMemoryAllocate@0x315da: the allocmode switch
@@ -277,6 +323,7 @@ const std::vector<HookEntry> &hooks() {
         H(cuGetProcAddress_v2),
         H(cuMemAlloc_v2), H(cuMemAllocManaged), H(cuMemAllocPitch_v2), H(cuMemFree_v2), H(cuMemGetInfo_v2),
         H(cuDeviceTotalMem_v2), H(cuDevicePrimaryCtxRetain), H(cuCtxCreate_v2), H(cuMemHostAlloc), H(cuMemAllocHost_v2),
+        H(cuMemHostRegister_v2), H(cuMipmappedArrayCreate), H(cuPointerGetAttribute), H(cuPointerGetAttributes),
         H(cuLaunchKernel), H(cuLaunchKernelEx), H(cuLaunchCooperativeKernel), H(cuModuleUnload),
         H(cuMemcpyHtoD_v2), H(cuMemcpyDtoH_v2), H(cuMemcpyDtoD_v2), H(cuMemcpyHtoDAsync_v2), H(cuMemcpyDtoHAsync_v2),
         H(cuMemcpyDtoDAsync_v2), H(cuMemcpy), H(cuMemcpyAsync),

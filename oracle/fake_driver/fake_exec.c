@@ -89,18 +89,36 @@ CUresult fx_mem_release(unsigned long long h) {
     free(x);
     return CUDA_SUCCESS;
 }
+/* currently mapped VMM ranges (pointer queries on an unmapped address fail, like on the real driver) */
+static struct { uint64_t va, n; } g_maps[65536];
+static int g_nmaps;
+static pthread_mutex_t g_maps_mu = PTHREAD_MUTEX_INITIALIZER;
+int fx_is_mapped(CUdeviceptr p) {
+    int hit = 0;
+    pthread_mutex_lock(&g_maps_mu);
+    for (int i = 0; i < g_nmaps && !hit; i++) hit = p >= g_maps[i].va && p < g_maps[i].va + g_maps[i].n;
+    pthread_mutex_unlock(&g_maps_mu);
+    return hit;
+}
 CUresult fx_mem_map(CUdeviceptr va, size_t n, size_t off, unsigned long long h, unsigned long long flags) {
     (void)flags;
     fx_handle *x = (fx_handle *)(uintptr_t)h;
     if (!x || off + n > x->size || (va % GRAN) || (n % GRAN)) return CUDA_ERROR_INVALID_VALUE;
     void *m = mmap((void *)(uintptr_t)va, n, PROT_NONE, MAP_SHARED | MAP_FIXED, x->fd, (off_t)off);   /* no access until cuMemSetAccess */
-    return m == MAP_FAILED ? CUDA_ERROR_INVALID_VALUE : CUDA_SUCCESS;
+    if (m == MAP_FAILED) return CUDA_ERROR_INVALID_VALUE;
+    pthread_mutex_lock(&g_maps_mu);
+    if (g_nmaps < 65536) { g_maps[g_nmaps].va = va; g_maps[g_nmaps].n = n; g_nmaps++; }
+    pthread_mutex_unlock(&g_maps_mu);
+    return CUDA_SUCCESS;
 }
 CUresult fx_mem_set_access(CUdeviceptr va, size_t n, const void *desc, size_t cnt) {
     (void)desc; (void)cnt;
     return mprotect((void *)(uintptr_t)va, n, PROT_READ | PROT_WRITE) ? CUDA_ERROR_INVALID_VALUE : CUDA_SUCCESS;
 }
 CUresult fx_mem_unmap(CUdeviceptr va, size_t n) {
+    pthread_mutex_lock(&g_maps_mu);
+    for (int i = 0; i < g_nmaps; i++) if (g_maps[i].va == va) { g_maps[i] = g_maps[--g_nmaps]; break; }
+    pthread_mutex_unlock(&g_maps_mu);
     void *m = mmap((void *)(uintptr_t)va, n, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE | MAP_FIXED, -1, 0);
     return m == MAP_FAILED ? CUDA_ERROR_INVALID_VALUE : CUDA_SUCCESS;
 }

@@ -114,6 +114,14 @@ CUresult fake_untrack(uint64_t p, uint64_t *size) {
     return CUDA_ERROR_INVALID_VALUE;
 }
 
+int fake_is_tracked(uint64_t p) {
+    int hit = 0;
+    pthread_mutex_lock(&g_mu);
+    for (unsigned s = 0; s < HCAP && !hit; s++) hit = g_h[s].live && p >= g_h[s].base && p < g_h[s].base + g_h[s].size;
+    pthread_mutex_unlock(&g_mu);
+    return hit;
+}
+
 static CUresult do_alloc(CUdeviceptr *dptr, size_t size) {
     fake_init();
     int d = cur_dev();
@@ -273,6 +281,26 @@ EXPORT CUresult cuMemsetD32_v2(CUdeviceptr d, unsigned v, size_t n) { FX_ONLY(fo
 EXPORT CUresult cuMemsetD32Async(CUdeviceptr d, unsigned v, size_t n, CUstream st) { (void)st; return cuMemsetD32_v2(d, v, n); }
 EXPORT CUresult cuMemHostGetDevicePointer_v2(CUdeviceptr *d, void *h, unsigned f) { (void)f; *d = (CUdeviceptr)(uintptr_t)h; return CUDA_SUCCESS; }
 EXPORT CUresult cuMemHostRegister_v2(void *p, size_t n, unsigned f) { (void)p; (void)n; (void)f; return CUDA_SUCCESS; }
+EXPORT CUresult cuMemHostUnregister(void *p) { (void)p; return CUDA_SUCCESS; }
+/* pointer queries: device memory when the address lies in a live allocation or a mapped VMM range, INVALID_VALUE otherwise */
+static CUresult pointer_attr(int attr, void *data, CUdeviceptr p) {
+    fake_init();
+    if (!(fake_is_tracked(p) || (fake_exec_on() && fx_is_mapped(p)))) return CUDA_ERROR_INVALID_VALUE;
+    if (!data) return CUDA_SUCCESS;
+    switch (attr) {
+    case 2: *(unsigned *)data = 2; break;                    /* MEMORY_TYPE = DEVICE */
+    case 3: *(CUdeviceptr *)data = p; break;                 /* DEVICE_POINTER */
+    case 8: *(unsigned *)data = 0; break;                    /* IS_MANAGED */
+    case 9: *(int *)data = cur_dev() < 0 ? 0 : cur_dev(); break;   /* DEVICE_ORDINAL */
+    default: memset(data, 0, 4); break;
+    }
+    return CUDA_SUCCESS;
+}
+EXPORT CUresult cuPointerGetAttribute(void *data, int attr, CUdeviceptr p) { return pointer_attr(attr, data, p); }
+EXPORT CUresult cuPointerGetAttributes(unsigned n, int *attrs, void **data, CUdeviceptr p) {
+    for (unsigned i = 0; i < n; i++) { CUresult r = pointer_attr(attrs[i], data ? data[i] : NULL, p); if (r) return r; }
+    return CUDA_SUCCESS;
+}
 EXPORT CUresult cuMemGetAllocationGranularity(size_t *g, const void *prop, int opt) { (void)prop; (void)opt; *g = 2u << 20; return CUDA_SUCCESS; }
 EXPORT CUresult cuMemAddressReserve(CUdeviceptr *p, size_t n, size_t align, CUdeviceptr addr, unsigned long long fl) {
     if (fake_exec_on()) return fx_address_reserve(p, n, align, addr, fl);

@@ -39,6 +39,8 @@ CUresult fx_mem_release(unsigned long long h);
 CUresult fx_mem_map(CUdeviceptr va, size_t n, size_t off, unsigned long long h, unsigned long long flags);
 CUresult fx_mem_set_access(CUdeviceptr va, size_t n, const void *desc, size_t cnt);
 CUresult fx_mem_unmap(CUdeviceptr va, size_t n);
+int fx_is_mapped(CUdeviceptr p);
+int fake_is_tracked(uint64_t p);                            /* inside a live plain allocation */
 CUresult fx_event_create(CUevent *e);
 CUresult fx_event_record(CUevent e);
 CUresult fx_event_elapsed(float *ms, CUevent a, CUevent b);

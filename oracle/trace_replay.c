@@ -16,6 +16,7 @@
  *   Y id size (cuMemAllocAsync) | Z id (cuMemFreeAsync) | C id size (cuMemCreate on device 0) | R id (cuMemRelease)
  *   G (cuGraphLaunch of a null graph — only meaningful on the fake driver)
  *   D n (make device n's primary context current; the counters printed from then on are device n's lane)
+ *   Q id (cuPointerGetAttributes {MEMORY_TYPE, IS_MANAGED} of pointer id; prints " type=<n> managed=<n>")
  * Output line: "<op#> <opcode> rc=<int> ctx=<u64> mod=<u64> buf=<u64> off=<u64> tot=<u64> [free=.. total=..]"
  * where the five counters are SUMMED over every process slot of device 0 (== own slot for one process).
  */
@@ -57,6 +58,7 @@ extern CUresult cuMemFreeAsync(CUdeviceptr, CUstream) __attribute__((weak));
 extern CUresult cuMemCreate(unsigned long long *, size_t, const void *, unsigned long long) __attribute__((weak));
 extern CUresult cuMemRelease(unsigned long long) __attribute__((weak));
 extern CUresult cuGraphLaunch(void *, CUstream) __attribute__((weak));
+extern CUresult cuPointerGetAttributes(unsigned, int *, void **, CUdeviceptr) __attribute__((weak));
 struct mem_prop { int type; int requested_handle_types; struct { int type; int id; } location; void *win32; struct { unsigned char c, g; unsigned short u; unsigned char r[4]; } flags; };
 
 /* Appendix A offsets */
@@ -131,7 +133,7 @@ int main(int argc, char **argv) {
         if (line[0] == '#' || line[0] == '\n') continue;
         int n = sscanf(line, " %c %lli %lli %lli", &op, (long long *)&a, (long long *)&b, (long long *)&d);
         if (n < 1) continue;
-        size_t fr = 0, tot = 0; int has_info = 0;
+        size_t fr = 0, tot = 0; int has_info = 0, has_q = 0, qtype = 0, qman = 0;
         switch (op) {
         case 'A': ptrs[a] = 0; r = cuMemAlloc_v2(&ptrs[a], (size_t)b); if (r) ptrs[a] = 0; break;
         case 'M': ptrs[a] = 0; r = cuMemAllocManaged(&ptrs[a], (size_t)b, 1); if (r) ptrs[a] = 0; break;
@@ -153,6 +155,8 @@ int main(int argc, char **argv) {
                     ptrs[a] = 0; r = cuMemCreate ? cuMemCreate(&ptrs[a], (size_t)b, &pr, 0) : 801; if (r) ptrs[a] = 0; break; }
         case 'R': r = cuMemRelease ? cuMemRelease(ptrs[a]) : 801; if (!r) ptrs[a] = 0; break;
         case 'G': r = cuGraphLaunch ? cuGraphLaunch(NULL, NULL) : 801; break;
+        case 'Q': { int attrs[2] = {2, 8}; unsigned ty = 0, mg = 0; void *data[2] = {&ty, &mg};
+                    r = cuPointerGetAttributes ? cuPointerGetAttributes(2, attrs, data, ptrs[a]) : 801; qtype = (int)ty; qman = (int)mg; has_q = 1; break; }
         default: continue;
         }
         counters(cur, c);
@@ -162,6 +166,7 @@ int main(int argc, char **argv) {
              * real driver's view in the unlimited case */
             printf(" free=%zu total=%zu", fr, tot);
         }
+        if (has_q) printf(" type=%d managed=%d", qtype, qman);
         putchar('\n');
         opn++;
     }

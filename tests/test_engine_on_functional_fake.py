@@ -212,3 +212,23 @@ def test_virtual_limit_mode_pages_only_under_physical_pressure(tmp_path):
     r = subprocess.run([os.path.join(LIBDIR, "swap_bench"), "--cubin", CUBIN, "--buffers", "20", "--mib", "16", "--steps", "4"], env=env,
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
     assert r.returncode == 3 and "rc=-1" in r.stdout
+
+
+def test_pointer_queries_on_a_paged_out_buffer(tmp_path):
+    """A paged-out swappable buffer has no mapping, and the driver answers pointer queries on it with INVALID_VALUE; the
+    hook pages it in first. Tracked pointers report device memory and not-managed, like the reference's post-processing
+    of cuPointerGetAttributes@0x33187."""
+    from conftest import run_replay
+    t = tmp_path / "t.txt"
+    t.write_text("A 0 %d\nA 1 %d\nA 2 %d\nQ 0\nQ 2\nA 3 4096\nQ 3\n" % (48 * M, 48 * M, 48 * M))
+    env = {"FAKE_GPU_EXEC": "1", "FAKE_GPU_CTX_MIB": "16", "CUDA_OVERSUBSCRIBE": "true", "CUDA_DEVICE_MEMORY_LIMIT_0": "128m",
+           "CUDA_DEVICE_MEMORY_SHARED_CACHE": str(tmp_path / "q.cache"),
+           "VGPU_SWAP_CHUNK_MB": "4", "VGPU_SWAP_ARENA_GB": "8", "VGPU_SWAP_SLAB_MB": "64", "VGPU_SWAP_SPARE_MB": "16"}
+    out = run_replay(str(t), "new", env).splitlines()
+    assert all(" rc=0 " in l for l in out[1:])                       # 144 MiB live under a 128 MiB quota: buffer 0 was evicted ...
+    assert out[4].endswith("type=2 managed=0") and out[5].endswith("type=2 managed=0") and out[7].endswith("type=2 managed=0")   # ... and is queried fine
+    # the same query straight at the driver (no hook) on a never-mapped address fails, which is what the hook prevents
+    t2 = tmp_path / "t2.txt"
+    t2.write_text("Q 5\n")
+    bare = run_replay(str(t2), "bare", {"FAKE_GPU_EXEC": "1"}).splitlines()
+    assert " rc=1 " in bare[1]
