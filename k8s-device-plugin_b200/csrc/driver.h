@@ -18,7 +18,10 @@ namespace vgpu {
     X(cuCtxGetDevice) X(cuCtxSynchronize)                                                                         \
     X(cuMemAlloc_v2) X(cuMemAllocManaged) X(cuMemAllocPitch_v2) X(cuMemFree_v2) X(cuMemGetInfo_v2)                \
     X(cuMemHostAlloc) X(cuMemFreeHost) X(cuMemHostGetDevicePointer_v2) X(cuMemHostRegister_v2)                    \
-    X(cuMemAllocHost_v2) X(cuMemGetAddressRange_v2) X(cuMemHostUnregister) X(cuMipmappedArrayCreate) X(cuMipmappedArrayDestroy) X(cuPointerGetAttribute) X(cuPointerGetAttributes)                                                               \
+    X(cuMemAllocHost_v2) X(cuMemGetAddressRange_v2) X(cuMemHostUnregister) X(cuMipmappedArrayCreate) X(cuMipmappedArrayDestroy) X(cuPointerGetAttribute) X(cuPointerGetAttributes)                                                            \
+    X(cuMemcpy2D_v2) X(cuMemcpy2DUnaligned_v2) X(cuMemcpy2DAsync_v2) X(cuMemcpy3D_v2) X(cuMemcpy3DAsync_v2)            \
+    X(cuMemsetD2D8_v2) X(cuMemsetD2D16_v2) X(cuMemsetD2D32_v2) X(cuMemsetD2D8Async) X(cuMemsetD2D16Async) X(cuMemsetD2D32Async) \
+    X(cuMemcpyPeer) X(cuMemcpyPeerAsync)                                                               \
     X(cuMemAddressReserve) X(cuMemAddressFree) X(cuMemCreate) X(cuMemRelease) X(cuMemMap) X(cuMemUnmap)           \
     X(cuMemSetAccess) X(cuMemGetAllocationGranularity)                                                            \
     X(cuMemcpyHtoD_v2) X(cuMemcpyDtoH_v2) X(cuMemcpyDtoD_v2) X(cuMemcpyHtoDAsync_v2) X(cuMemcpyDtoHAsync_v2)      \

@@ -230,6 +230,55 @@ VGPU_EXPORT CUresult cuMemsetD32Async_ptsz(CUdeviceptr dst, unsigned int v, size
 }
 #undef PTS
 
+// 2-D / 3-D / peer copies and 2-D fills: same rule as the linear family — device operands living in the swap arena are
+// paged in before the real call (the reference needs nothing here: UVM faults its managed memory in).
+#define DEVPTR_IF(type, ptr) ((type) == CU_MEMORYTYPE_DEVICE || (type) == CU_MEMORYTYPE_UNIFIED ? (ptr) : (CUdeviceptr)0)
+VGPU_EXPORT CUresult cuMemcpy2D_v2(const CUDA_MEMCPY2D *c) {
+    if (c) TOUCH2(DEVPTR_IF(c->dstMemoryType, c->dstDevice), 1, DEVPTR_IF(c->srcMemoryType, c->srcDevice), 1, nullptr);
+    CUresult r = drv().cuMemcpy2D_v2(c); TOUCH_DONE(nullptr); return r;
+}
+VGPU_EXPORT CUresult cuMemcpy2DUnaligned_v2(const CUDA_MEMCPY2D *c) {
+    if (c) TOUCH2(DEVPTR_IF(c->dstMemoryType, c->dstDevice), 1, DEVPTR_IF(c->srcMemoryType, c->srcDevice), 1, nullptr);
+    CUresult r = drv().cuMemcpy2DUnaligned_v2(c); TOUCH_DONE(nullptr); return r;
+}
+VGPU_EXPORT CUresult cuMemcpy2DAsync_v2(const CUDA_MEMCPY2D *c, CUstream st) {
+    if (c) TOUCH2(DEVPTR_IF(c->dstMemoryType, c->dstDevice), 1, DEVPTR_IF(c->srcMemoryType, c->srcDevice), 1, st);
+    CUresult r = drv().cuMemcpy2DAsync_v2(c, st); TOUCH_DONE(st); return r;
+}
+VGPU_EXPORT CUresult cuMemcpy3D_v2(const CUDA_MEMCPY3D *c) {
+    if (c) TOUCH2(DEVPTR_IF(c->dstMemoryType, c->dstDevice), 1, DEVPTR_IF(c->srcMemoryType, c->srcDevice), 1, nullptr);
+    CUresult r = drv().cuMemcpy3D_v2(c); TOUCH_DONE(nullptr); return r;
+}
+VGPU_EXPORT CUresult cuMemcpy3DAsync_v2(const CUDA_MEMCPY3D *c, CUstream st) {
+    if (c) TOUCH2(DEVPTR_IF(c->dstMemoryType, c->dstDevice), 1, DEVPTR_IF(c->srcMemoryType, c->srcDevice), 1, st);
+    CUresult r = drv().cuMemcpy3DAsync_v2(c, st); TOUCH_DONE(st); return r;
+}
+VGPU_EXPORT CUresult cuMemcpyPeer(CUdeviceptr dst, CUcontext dctx, CUdeviceptr src, CUcontext sctx, size_t n) {
+    TOUCH2(dst, n, src, n, nullptr); CUresult r = drv().cuMemcpyPeer(dst, dctx, src, sctx, n); TOUCH_DONE(nullptr); return r;
+}
+VGPU_EXPORT CUresult cuMemcpyPeerAsync(CUdeviceptr dst, CUcontext dctx, CUdeviceptr src, CUcontext sctx, size_t n, CUstream st) {
+    TOUCH2(dst, n, src, n, st); CUresult r = drv().cuMemcpyPeerAsync(dst, dctx, src, sctx, n, st); TOUCH_DONE(st); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD2D8_v2(CUdeviceptr dst, size_t pitch, unsigned char v, size_t w, size_t h) {
+    TOUCH1(dst, pitch * h, nullptr); CUresult r = drv().cuMemsetD2D8_v2(dst, pitch, v, w, h); TOUCH_DONE(nullptr); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD2D16_v2(CUdeviceptr dst, size_t pitch, unsigned short v, size_t w, size_t h) {
+    TOUCH1(dst, pitch * h, nullptr); CUresult r = drv().cuMemsetD2D16_v2(dst, pitch, v, w, h); TOUCH_DONE(nullptr); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD2D32_v2(CUdeviceptr dst, size_t pitch, unsigned int v, size_t w, size_t h) {
+    TOUCH1(dst, pitch * h, nullptr); CUresult r = drv().cuMemsetD2D32_v2(dst, pitch, v, w, h); TOUCH_DONE(nullptr); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD2D8Async(CUdeviceptr dst, size_t pitch, unsigned char v, size_t w, size_t h, CUstream st) {
+    TOUCH1(dst, pitch * h, st); CUresult r = drv().cuMemsetD2D8Async(dst, pitch, v, w, h, st); TOUCH_DONE(st); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD2D16Async(CUdeviceptr dst, size_t pitch, unsigned short v, size_t w, size_t h, CUstream st) {
+    TOUCH1(dst, pitch * h, st); CUresult r = drv().cuMemsetD2D16Async(dst, pitch, v, w, h, st); TOUCH_DONE(st); return r;
+}
+VGPU_EXPORT CUresult cuMemsetD2D32Async(CUdeviceptr dst, size_t pitch, unsigned int v, size_t w, size_t h, CUstream st) {
+    TOUCH1(dst, pitch * h, st); CUresult r = drv().cuMemsetD2D32Async(dst, pitch, v, w, h, st); TOUCH_DONE(st); return r;
+}
+#undef DEVPTR_IF
+
 // Pointer queries. The reference post-processes cuPointerGetAttributes@0x33187 because its swap switch turns every
 // large allocation into managed memory: MEMORY_TYPE := check_memory_type(ptr), IS_MANAGED := 0. Here swappable buffers
 // are VMM mappings — device memory to the driver — but a PAGED-OUT buffer has no mapping at all and the driver would
@@ -324,6 +373,8 @@ const std::vector<HookEntry> &hooks() {
         H(cuMemAlloc_v2), H(cuMemAllocManaged), H(cuMemAllocPitch_v2), H(cuMemFree_v2), H(cuMemGetInfo_v2),
         H(cuDeviceTotalMem_v2), H(cuDevicePrimaryCtxRetain), H(cuCtxCreate_v2), H(cuMemHostAlloc), H(cuMemAllocHost_v2),
         H(cuMemHostRegister_v2), H(cuMipmappedArrayCreate), H(cuPointerGetAttribute), H(cuPointerGetAttributes),
+        H(cuMemcpy2D_v2), H(cuMemcpy2DUnaligned_v2), H(cuMemcpy2DAsync_v2), H(cuMemcpy3D_v2), H(cuMemcpy3DAsync_v2), H(cuMemcpyPeer), H(cuMemcpyPeerAsync),
+        H(cuMemsetD2D8_v2), H(cuMemsetD2D16_v2), H(cuMemsetD2D32_v2), H(cuMemsetD2D8Async), H(cuMemsetD2D16Async), H(cuMemsetD2D32Async),
         H(cuLaunchKernel), H(cuLaunchKernelEx), H(cuLaunchCooperativeKernel), H(cuModuleUnload),
         H(cuMemcpyHtoD_v2), H(cuMemcpyDtoH_v2), H(cuMemcpyDtoD_v2), H(cuMemcpyHtoDAsync_v2), H(cuMemcpyDtoHAsync_v2),
         H(cuMemcpyDtoDAsync_v2), H(cuMemcpy), H(cuMemcpyAsync),
