@@ -332,8 +332,8 @@ VGPU_EXPORT nvmlReturn_t nvmlDeviceGetMemoryInfo(nvmlDevice_t device, nvmlMemory
     if (r != NVML_SUCCESS || !memory) return r;
     unsigned idx = 0;
     if (n.nvmlDeviceGetIndex && n.nvmlDeviceGetIndex(device, &idx) == NVML_SUCCESS) {
-        unsigned long long t, f, u;
-        if (Runtime::get().nvml_memory_view((int)idx, &t, &f, &u)) { memory->total = t; memory->free = f; memory->used = u; }
+        unsigned long long t = 0, f = 0, u = 0;
+        if (Runtime::get().nvml_memory_view((int)idx, &t, &f, &u)) { memory->used = u; if (t) { memory->total = t; memory->free = f; } }
     }
     return r;
 }
@@ -344,8 +344,8 @@ VGPU_EXPORT nvmlReturn_t nvmlDeviceGetMemoryInfo_v2(nvmlDevice_t device, nvmlMem
     if (r != NVML_SUCCESS || !memory) return r;
     unsigned idx = 0;
     if (n.nvmlDeviceGetIndex && n.nvmlDeviceGetIndex(device, &idx) == NVML_SUCCESS) {
-        unsigned long long t, f, u;
-        if (Runtime::get().nvml_memory_view((int)idx, &t, &f, &u)) { memory->total = t; memory->free = f; memory->used = u; memory->reserved = 0; }
+        unsigned long long t = 0, f = 0, u = 0;
+        if (Runtime::get().nvml_memory_view((int)idx, &t, &f, &u)) { memory->used = u; if (t) { memory->total = t; memory->free = f; memory->reserved = 0; } }
     }
     return r;
 }

@@ -612,12 +612,22 @@ CUresult Runtime::ctx_create(CUcontext *ctx, unsigned flags, CUdevice dev) {
 }
 
 bool Runtime::nvml_memory_view(int idx, unsigned long long *total, unsigned long long *free_b, unsigned long long *used) {
+    // nvmlDeviceGetMemoryInfo@0x24069 (nvml/hook.c:L327-334): usage = Σ used[d].total; under MEMORY_OVERRIDE=1 the
+    // NVML-monitored figure wins when it is larger; limit == 0 -> only `used` is replaced (by the container's usage),
+    // otherwise total = limit, free = limit - usage, used = usage.
     if (!ensure_initialized() || idx < 0 || idx >= VGPU_MAX_DEVICES) return false;
     uint64_t limit = region_->limit(idx);
-    if (limit == 0) return false;
     uint64_t usage = region_->usage(idx);
-    *total = limit;
+    static const bool override_on = [] { const char *e = std::getenv("MEMORY_OVERRIDE"); return e && std::atoi(e) == 1; }();
+    if (override_on) {
+        uint64_t monitor = 0;
+        vgpu_shared_region_t *r = region_->raw();
+        for (int i = 0; i < r->proc_num; i++) monitor += r->procs[i].monitorused[idx];
+        if (usage < monitor) usage = monitor;
+    }
     *used = usage;
+    if (limit == 0) return true;           // caller keeps the driver's total/free (signalled by *total == 0)
+    *total = limit;
     *free_b = limit > usage ? limit - usage : 0;
     return true;
 }

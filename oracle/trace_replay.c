@@ -16,11 +16,14 @@
  *   Y id size (cuMemAllocAsync) | Z id (cuMemFreeAsync) | C id size (cuMemCreate on device 0) | R id (cuMemRelease)
  *   G (cuGraphLaunch of a null graph — only meaningful on the fake driver)
  *   D n (make device n's primary context current; the counters printed from then on are device n's lane)
+ *   N (nvmlDeviceGetMemoryInfo of NVML device 0 — the hook's exported wrapper when one is preloaded; prints
+ *      " nv_total=.. nv_free=.. nv_used=..")
  *   Q id (cuPointerGetAttributes {MEMORY_TYPE, IS_MANAGED} of pointer id; prints " type=<n> managed=<n>")
  * Output line: "<op#> <opcode> rc=<int> ctx=<u64> mod=<u64> buf=<u64> off=<u64> tot=<u64> [free=.. total=..]"
  * where the five counters are SUMMED over every process slot of device 0 (== own slot for one process).
  */
 #define _GNU_SOURCE
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -59,6 +62,11 @@ extern CUresult cuMemCreate(unsigned long long *, size_t, const void *, unsigned
 extern CUresult cuMemRelease(unsigned long long) __attribute__((weak));
 extern CUresult cuGraphLaunch(void *, CUstream) __attribute__((weak));
 extern CUresult cuPointerGetAttributes(unsigned, int *, void **, CUdeviceptr) __attribute__((weak));
+/* NVML: bound to a preloaded hook's exported wrappers when there is one (the reference run preloads a dlsym shim that
+ * would hide its dlsym override, so symbol interposition is the route compared), else found with dlopen + dlsym */
+extern int nvmlInit_v2(void) __attribute__((weak));
+extern int nvmlDeviceGetHandleByIndex_v2(unsigned, void **) __attribute__((weak));
+extern int nvmlDeviceGetMemoryInfo(void *, void *) __attribute__((weak));
 struct mem_prop { int type; int requested_handle_types; struct { int type; int id; } location; void *win32; struct { unsigned char c, g; unsigned short u; unsigned char r[4]; } flags; };
 
 /* Appendix A offsets */
@@ -133,7 +141,8 @@ int main(int argc, char **argv) {
         if (line[0] == '#' || line[0] == '\n') continue;
         int n = sscanf(line, " %c %lli %lli %lli", &op, (long long *)&a, (long long *)&b, (long long *)&d);
         if (n < 1) continue;
-        size_t fr = 0, tot = 0; int has_info = 0, has_q = 0, qtype = 0, qman = 0;
+        size_t fr = 0, tot = 0; int has_info = 0, has_q = 0, qtype = 0, qman = 0, has_nv = 0;
+        unsigned long long nvmem[3] = {0, 0, 0};     /* nvmlMemory_t {total, free, used} */
         switch (op) {
         case 'A': ptrs[a] = 0; r = cuMemAlloc_v2(&ptrs[a], (size_t)b); if (r) ptrs[a] = 0; break;
         case 'M': ptrs[a] = 0; r = cuMemAllocManaged(&ptrs[a], (size_t)b, 1); if (r) ptrs[a] = 0; break;
@@ -155,6 +164,17 @@ int main(int argc, char **argv) {
                     ptrs[a] = 0; r = cuMemCreate ? cuMemCreate(&ptrs[a], (size_t)b, &pr, 0) : 801; if (r) ptrs[a] = 0; break; }
         case 'R': r = cuMemRelease ? cuMemRelease(ptrs[a]) : 801; if (!r) ptrs[a] = 0; break;
         case 'G': r = cuGraphLaunch ? cuGraphLaunch(NULL, NULL) : 801; break;
+        case 'N': { static void *nv; static int (*init)(void), (*byidx)(unsigned, void **), (*meminfo)(void *, void *);
+                    if (!init && nvmlInit_v2 && nvmlDeviceGetHandleByIndex_v2 && nvmlDeviceGetMemoryInfo) {
+                        init = nvmlInit_v2; byidx = nvmlDeviceGetHandleByIndex_v2; meminfo = nvmlDeviceGetMemoryInfo; init();
+                    } else if (!init && !nv && (nv = dlopen("libnvidia-ml.so.1", RTLD_NOW))) {
+                        init = (int (*)(void))dlsym(nv, "nvmlInit_v2"); byidx = (int (*)(unsigned, void **))dlsym(nv, "nvmlDeviceGetHandleByIndex_v2");
+                        meminfo = (int (*)(void *, void *))dlsym(nv, "nvmlDeviceGetMemoryInfo");
+                        if (init) init();
+                    }
+                    void *h = NULL; r = 801;
+                    if (byidx && meminfo && byidx(0, &h) == 0) { r = meminfo(h, nvmem); has_nv = 1; }
+                    break; }
         case 'Q': { int attrs[2] = {2, 8}; unsigned ty = 0, mg = 0; void *data[2] = {&ty, &mg};
                     r = cuPointerGetAttributes ? cuPointerGetAttributes(2, attrs, data, ptrs[a]) : 801; qtype = (int)ty; qman = (int)mg; has_q = 1; break; }
         default: continue;
@@ -167,6 +187,7 @@ int main(int argc, char **argv) {
             printf(" free=%zu total=%zu", fr, tot);
         }
         if (has_q) printf(" type=%d managed=%d", qtype, qman);
+        if (has_nv) printf(" nv_total=%llu nv_free=%llu nv_used=%llu", nvmem[0], nvmem[1], nvmem[2]);
         putchar('\n');
         opn++;
     }

@@ -257,3 +257,20 @@ def test_override_env_file_changes_the_limits(tmp_path):
     assert " rc=-1 " in out[1] and out[2].endswith("total=67108864")         # the file's 64m won over the environment's 1g
     out = run_replay(t, "new", dict(_env(tmp_path, "1g", FAKE_GPU_CTX_MIB="16"), CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "b.cache"))).splitlines()
     assert " rc=0 " in out[1] and out[2].endswith("total=1073741824")
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
+@pytest.mark.parametrize("limit", ["256m", None])
+def test_nvml_memory_view_matches_the_reference(tmp_path, limit):
+    """What nvidia-smi / pynvml see inside the container (nvmlDeviceGetMemoryInfo@0x24069, bound by symbol interposition):
+    under a quota total = limit, free = limit - usage, used = usage; without one only `used` is replaced by the
+    container's usage."""
+    t = _write(tmp_path, "N\nA 0 %d\nN\nA 1 %d\nN\nF 0\nN\n" % (10 << 20, 40 << 20))
+    env = _env(tmp_path, limit, FAKE_GPU_CTX_MIB="16")
+    new = run_replay(t, "new", env).splitlines()
+    ref = run_replay(t, "reference", dict(env, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "ref.cache"))).splitlines()
+    assert new == ref, "\n".join(f"{a}   |   {b}" for a, b in zip(new, ref) if a != b)
+    if limit:
+        assert new[3].endswith("nv_total=268435456 nv_free=%d nv_used=%d" % ((256 - 16 - 10) << 20, 26 << 20))
+    else:
+        assert new[3].endswith("nv_used=%d" % (26 << 20)) and "nv_total=%d" % (183359 << 20) in new[3]
