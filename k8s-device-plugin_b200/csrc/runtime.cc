@@ -519,10 +519,16 @@ CUresult Runtime::mem_free(CUdeviceptr dptr) {
     } else {
         r = d.cuMemFree_v2(dptr);
     }
-    // remove_chunk unlinks and un-accounts whatever the real free returned
+    // remove_chunk unlinks and un-accounts whatever the real free returned — and it credits the CURRENT device
+    // (remove_chunk@0x40871: cuCtxGetDevice(&dev); rm_gpu_device_memory_usage(getpid(), dev, size, 2)), not the one the
+    // buffer was charged to: freeing on device 0 what was allocated on device 1 leaves device 1 charged for ever and
+    // wraps device 0's lane downwards. Reproduced by default for bit-exact accounting; VGPU_STRICT_CUDA_ERRORS=1
+    // credits the owner.
     table_.erase(it);
-    if (a.kind == AllocKind::Swap) region_->sub(pid_, a.dev, a.size, VGPU_MEM_BUFFER);
-    else uncharge(a.dev, a.size);
+    int credit = a.dev;
+    if (!strict_errors()) { int cur = current_device(); if (cur >= 0 && cur < VGPU_MAX_DEVICES) credit = cur; }
+    if (a.kind == AllocKind::Swap) region_->sub(pid_, credit, a.size, VGPU_MEM_BUFFER);
+    else uncharge(credit, a.size);
     return r == CUDA_SUCCESS ? CUDA_SUCCESS : r;
 }
 
@@ -628,7 +634,7 @@ bool Runtime::nvml_memory_view(int idx, unsigned long long *total, unsigned long
     *used = usage;
     if (limit == 0) return true;           // caller keeps the driver's total/free (signalled by *total == 0)
     *total = limit;
-    *free_b = limit > usage ? limit - usage : 0;
+    *free_b = limit - usage;               // unsigned wrap when usage > limit, like the reference (@0x244b0-0x244b8)
     return true;
 }
 

@@ -274,3 +274,49 @@ def test_nvml_memory_view_matches_the_reference(tmp_path, limit):
         assert new[3].endswith("nv_total=268435456 nv_free=%d nv_used=%d" % ((256 - 16 - 10) << 20, 26 << 20))
     else:
         assert new[3].endswith("nv_used=%d" % (26 << 20)) and "nv_total=%d" % (183359 << 20) in new[3]
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_multi_device_traces_match_the_reference_binary(tmp_path, seed):
+    """Randomised differential test on a three-GPU container: device switches, the four allocation families, frees of
+    live / stale / foreign pointers, cuMemGetInfo, cuDeviceTotalMem, NVML memory queries, launches — under per-device
+    limits that are crossed many times. Every return code and every counter word after every op equals the reference."""
+    import random
+    rng = random.Random(seed)
+    lines, live, nid = [], {0: [], 1: [], 2: []}, 0
+    cur = 0
+    for _ in range(700):
+        r = rng.random()
+        if r < 0.08:
+            cur = rng.randrange(3); lines.append(f"D {cur}")
+        elif r < 0.50:
+            size = rng.choice([256, 4096, 1 << 20, (2 << 20) - 1, 2 << 20, (2 << 20) + 1, 5 << 20, 17 << 20, 33 << 20])
+            kind = rng.choice("AAAMP")
+            if kind == "P":
+                lines.append(f"P {nid} {rng.choice([100, 4096, 10000])} {rng.choice([1, 64, 500])}")
+            else:
+                lines.append(f"{kind} {nid} {size}")
+            live[cur].append(nid); nid += 1
+        elif r < 0.80 and live[cur]:
+            lines.append(f"F {live[cur].pop(rng.randrange(len(live[cur])))}")
+        elif r < 0.84:
+            lines.append(f"X {hex(0x7f0000000000 + rng.randrange(1 << 30))}")       # a pointer nobody handed out
+        elif r < 0.90:
+            lines.append("I")
+        elif r < 0.93:
+            lines.append("T")
+        elif r < 0.96:
+            lines.append("L 1 1 1")
+        else:
+            other = [d for d in (0, 1, 2) if d != cur and live[d]]
+            if other:                                                               # free on device A what device B allocated
+                d = rng.choice(other); lines.append(f"F {live[d].pop(rng.randrange(len(live[d])))}")
+    t = _write(tmp_path, "\n".join(lines) + "\n")
+    env = _env(tmp_path, None, CUDA_DEVICE_MEMORY_LIMIT_0="96m", CUDA_DEVICE_MEMORY_LIMIT_1="64m", CUDA_DEVICE_MEMORY_LIMIT_2="200m",
+               FAKE_GPU_COUNT="3", FAKE_GPU_CTX_MIB="16")
+    new = run_replay(t, "new", env).splitlines()
+    ref = run_replay(t, "reference", dict(env, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "ref.cache"))).splitlines()
+    diffs = [f"{a}   |   {b}" for a, b in zip(new, ref) if a != b]
+    assert not diffs and len(new) == len(ref), "\n".join(diffs[:10])
+    assert sum(" rc=-1 " in l for l in new) > 20 and sum(" rc=2 " in l for l in new) > 3
