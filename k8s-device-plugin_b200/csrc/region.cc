@@ -18,6 +18,37 @@
 
 namespace vgpu {
 
+// strtoul(text, NULL, 0) as the reference binary gets it: its call binds to the classic strtoul@GLIBC_2.2.5, while code
+// compiled today against glibc >= 2.38 is redirected to __isoc23_strtoul, which also accepts "0b"/"0B" binary literals
+// ("0B1k" would parse as 1 KiB here and as 0 there). Spelled out so the result does not depend on the C library's
+// vintage: leading white space, optional sign, 0x/0X hex, leading 0 octal, else decimal; overflow -> ULONG_MAX; a
+// negative number wraps like the library's.
+static uint64_t classic_strtoul_base0(const char *p) {
+    while (*p == ' ' || (*p >= '\t' && *p <= '\r')) p++;
+    bool neg = false;
+    if (*p == '+' || *p == '-') { neg = *p == '-'; p++; }
+    unsigned base = 10;
+    if (*p == '0') {
+        auto hex = [](char c) { return (c >= '0' && c <= '9') || (c >= 'a' && c <= 'f') || (c >= 'A' && c <= 'F'); };
+        if ((p[1] == 'x' || p[1] == 'X') && hex(p[2])) { base = 16; p += 2; }
+        else base = 8;
+    }
+    uint64_t acc = 0;
+    bool overflow = false;
+    for (;; p++) {
+        unsigned d;
+        if (*p >= '0' && *p <= '9') d = (unsigned)(*p - '0');
+        else if (*p >= 'a' && *p <= 'z') d = (unsigned)(*p - 'a') + 10;
+        else if (*p >= 'A' && *p <= 'Z') d = (unsigned)(*p - 'A') + 10;
+        else break;
+        if (d >= base) break;
+        if (acc > (UINT64_MAX - d) / base) overflow = true;
+        acc = acc * base + d;
+    }
+    if (overflow) return UINT64_MAX;
+    return neg ? (uint64_t)0 - acc : acc;
+}
+
 uint64_t parse_limit(const char *v) {
     // get_limit_from_env@0x40d00 (multiprocess_memory_limit.c:L101-111): unit from the LAST character, number by
     // strtoul(base 0), zero product or overflowing product -> 0 (= unlimited)
@@ -31,7 +62,7 @@ uint64_t parse_limit(const char *v) {
         case 'K': case 'k': scalar = 1ull << 10; break;
         default: break;
     }
-    uint64_t n = std::strtoul(v, nullptr, 0);
+    uint64_t n = classic_strtoul_base0(v);
     uint64_t prod = n * scalar;
     if (prod == 0 || prod / scalar != n) return 0;
     return prod;

@@ -11,6 +11,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 int main(int argc, char **argv) {
     if (argc < 2) return 2;
     void *h = dlopen(argv[1], RTLD_LAZY | RTLD_LOCAL);
@@ -21,6 +22,17 @@ int main(int argc, char **argv) {
     char *base = (char *)delta - 0x45c7b;
     int *g_sm_num = (int *)(base + 0x6113c), *g_thr = (int *)(base + 0x61140), *g_total = (int *)(base + 0x61148);
     *g_sm_num = 148; *g_thr = 2048; *g_total = 148 * 2048 * 32;
+    if (argc > 2 && !strcmp(argv[2], "--stdin")) {
+        /* bulk mode for differential fuzzing: "L <text>" -> get_limit_from_env, "D up cur share" -> delta (B200 geometry) */
+        char line[512];
+        while (fgets(line, sizeof line, stdin)) {
+            size_t n = strlen(line);
+            if (n && line[n - 1] == '\n') line[n - 1] = 0;
+            if (line[0] == 'L' && line[1] == ' ') { setenv("CUDA_DEVICE_MEMORY_LIMIT_9", line + 2, 1); printf("%lu\n", (unsigned long)getlim("CUDA_DEVICE_MEMORY_LIMIT_9")); }
+            else if (line[0] == 'D') { int a, b, c; if (sscanf(line + 1, "%d %d %d", &a, &b, &c) == 3) printf("%d\n", delta(a, b, c)); }
+        }
+        return 0;
+    }
     static const int dv[][3] = {{30, 0, 0}, {30, 28, 1000000}, {30, 40, 5000000}, {50, 0, 0}, {30, 100, 5000000}, {30, 30, 9699328},
                                 {100, 0, 0}, {10, 9, 123456}, {10, 90, 9000000}, {75, 20, 3000000}, {1, 0, 0}, {99, 100, 42}};
     printf("{\"sm_num\": 148, \"max_threads_per_sm\": 2048, \"total_cores\": %d, \"delta\": [", *g_total);

@@ -93,3 +93,39 @@ def test_reference_deadlocks_without_the_shim_when_nvml_calls_dlsym(tmp_path):
     r = subprocess.run([os.path.join(OREF, "trace_replay"), t], env=dict(base, LD_PRELOAD=f"{SHIM_SO}:{REF_SO}"),
                        stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=60, text=True)
     assert r.returncode == 0 and " rc=0 " in r.stdout.splitlines()[1]
+
+
+def test_fuzz_limit_parser_and_delta_against_the_reference_binary():
+    """3000 random limit strings and 3000 random delta() arguments evaluated INSIDE the reference binary
+    (get_limit_from_env@0x40d00, delta@0x45c7b) — the CPU restatement and the product's vgpu_parse_limit agree on all."""
+    import random
+    import subprocess
+    from conftest import FAKE, OREF, REF_SO, have_reference
+    if not have_reference():
+        pytest.skip("reference binary only exists in the build container")
+    import k8s_device_plugin_b200 as v
+    rng = random.Random(20260921)
+    alphabet = "0123456789" * 4 + "abcdefxXkKmMgG" + " +-._"
+    texts = []
+    for _ in range(3000):
+        kind = rng.random()
+        if kind < 0.5:
+            t = str(rng.choice([0, 1, 7, 1023, 4096, 8192, 10 ** 6, 2 ** 31, 2 ** 40, 2 ** 54, 2 ** 63, 2 ** 64 - 1, rng.randrange(10 ** 12)])) + rng.choice(["", "k", "K", "m", "M", "g", "G", "t", "b", "mm", "Mi"])
+        elif kind < 0.7:
+            t = rng.choice(["0x", "0X", "0"]) + "".join(rng.choice("0123456789abcdefABCDEF") for _ in range(rng.randint(1, 12))) + rng.choice(["", "k", "m", "g"])
+        else:
+            t = "".join(rng.choice(alphabet) for _ in range(rng.randint(1, 14)))
+        if "\n" not in t and "\0" not in t:
+            texts.append(t)
+    deltas = [(rng.randint(0, 100), rng.randint(0, 100), rng.choice([0, 1, 1000, rng.randrange(9699328 + 1), 9699328])) for _ in range(3000)]
+    feed = "".join(f"L {t}\n" for t in texts) + "".join(f"D {a} {b} {c}\n" for a, b, c in deltas)
+    env = dict(os.environ, LD_LIBRARY_PATH=FAKE + ":" + os.environ.get("LD_LIBRARY_PATH", ""), LIBCUDA_LOG_LEVEL="0")
+    r = subprocess.run([os.path.join(OREF, "ref_kat"), REF_SO, "--stdin"], input=feed, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-500:]
+    got = r.stdout.split()
+    assert len(got) == len(texts) + len(deltas)
+    for t, want in zip(texts, got):
+        assert ORA.vo_parse_limit(t.encode()) == int(want), repr(t)
+        assert v.lib().vgpu_parse_limit(t.encode()) == int(want), repr(t)
+    for (a, b, c), want in zip(deltas, got[len(texts):]):
+        assert ORA.vo_delta(148, 2048, 9699328, a, b, c) == int(want), (a, b, c)
