@@ -32,14 +32,35 @@ int put(const std::string &s, char *buf, size_t cap) {
 void copy_str(char *dst, const std::string &s) {
     std::snprintf(dst, VGPU_PLUGIN_MAX_STR, "%s", s.c_str());
 }
-// strconv.Atoi / ParseInt(…, 10, 32) with the error ignored: invalid text -> 0
-int32_t atoi32(const std::string &s) {
-    if (s.empty()) return 0;
-    char *end = nullptr;
-    long long v = std::strtoll(s.c_str(), &end, 10);
-    if (*end != 0 || v > INT32_MAX || v < INT32_MIN) return 0;
-    return (int32_t)v;
+// Go's strconv with the error IGNORED, as the reference uses it (`v, _ := strconv.Atoi(x)`): text that is not
+// [+-]?[0-9]+ (no white space, no prefixes) gives 0; a value outside the target width gives the CLAMPED limit of that
+// width (ParseInt returns it next to ErrRange). Atoi targets int (64-bit) and the reference then truncates with int32(…);
+// ParseInt(…, 10, 32) clamps to int32 directly.
+bool go_decimal(const std::string &s, bool *neg, std::string *digits) {
+    size_t i = 0;
+    *neg = false;
+    if (i < s.size() && (s[i] == '+' || s[i] == '-')) { *neg = s[i] == '-'; i++; }
+    if (i == s.size()) return false;
+    for (size_t k = i; k < s.size(); k++) if (s[k] < '0' || s[k] > '9') return false;
+    *digits = s.substr(i);
+    return true;
 }
+int64_t go_parse_int(const std::string &s, int bits) {
+    bool neg; std::string dg;
+    if (!go_decimal(s, &neg, &dg)) return 0;
+    const uint64_t maxpos = bits == 32 ? (uint64_t)INT32_MAX : (uint64_t)INT64_MAX;
+    uint64_t acc = 0;
+    bool over = false;
+    for (char c : dg) {
+        uint64_t d = (uint64_t)(c - '0');
+        if (acc > (UINT64_MAX - d) / 10) { over = true; break; }
+        acc = acc * 10 + d;
+    }
+    if (over || acc > maxpos + (neg ? 1 : 0)) return neg ? -(int64_t)maxpos - 1 : (int64_t)maxpos;
+    return neg ? (int64_t)(0 - acc) : (int64_t)acc;
+}
+int32_t atoi_to_i32(const std::string &s) { return (int32_t)(uint32_t)(uint64_t)go_parse_int(s, 64); }   // int32(strconv.Atoi(s))
+int32_t atoi32(const std::string &s) { return (int32_t)go_parse_int(s, 32); }                              // ParseInt(s, 10, 32)
 std::string enc_container(const vgpu_container_device_t *d, int n) {   // EncodeContainerDevices util.go:120-128
     std::string t;
     for (int i = 0; i < n; i++)
@@ -100,9 +121,9 @@ VGPU_API int vgpu_codec_decode_node_devices(const char *s, vgpu_node_device_t *o
         vgpu_node_device_t &d = out[(*n)++];
         std::memset(&d, 0, sizeof d);
         copy_str(d.id, f[0]);
-        d.count = atoi32(f[1]); d.devmem = atoi32(f[2]); d.devcore = atoi32(f[3]);
+        d.count = atoi_to_i32(f[1]); d.devmem = atoi_to_i32(f[2]); d.devcore = atoi_to_i32(f[3]);
         copy_str(d.type, f[4]);
-        d.numa = atoi32(f[5]);
+        d.numa = atoi_to_i32(f[5]);   // Go keeps a 64-bit int here; NUMA node numbers fit 32 bits
         // strconv.ParseBool accepts 1,t,T,TRUE,true,True (error ignored -> false)
         d.health = (f[6] == "1" || f[6] == "t" || f[6] == "T" || f[6] == "TRUE" || f[6] == "true" || f[6] == "True");
     }

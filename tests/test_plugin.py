@@ -155,3 +155,73 @@ def test_node_registration_annotation(cluster):
     a = plugin.node_annotations(now="T")
     assert a[S.HANDSHAKE] == "Reported T"
     assert a[S.REGISTER] == "GPU-fake-0,10,183359,100,NVIDIA-NVIDIA B200,0,true:GPU-fake-1,10,183359,100,NVIDIA-NVIDIA B200,0,true:"
+
+
+def test_native_codec_equals_the_python_restatement_on_random_annotations():
+    """Differential test of csrc/plugin_core.cc against oracle/codec_oracle.py (util.go:78-271 restated): well-formed,
+    ragged and malformed annotations — same values, same errors, same re-encoded bytes."""
+    import os
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import codec_oracle as O
+    from k8s_device_plugin_b200.plugin import core
+    rng = random.Random(77)
+    word = lambda: "".join(rng.choice("abcXYZ-019 _") for _ in range(rng.randint(0, 8)))
+    num = lambda: rng.choice(["0", "1", "10", "8192", "183359", "-5", "2147483647", "2147483648", "99999999999", "", "x1", "1x", "+7", " 3"])
+
+    def node_text():
+        parts = []
+        for _ in range(rng.randint(0, 4)):
+            n = rng.choice([7, 7, 7, 6, 8, 1])
+            fields = [word(), num(), num(), num(), word(), num(), rng.choice(["true", "false", "1", "T", "yes", ""])][:n] + ["z"] * max(0, n - 7)
+            parts.append(",".join(fields))
+        return ":".join(parts) + rng.choice([":", "", "::"])
+
+    def pod_text():
+        ctrs = []
+        for _ in range(rng.randint(0, 4)):
+            devs = []
+            for _ in range(rng.randint(0, 3)):
+                n = rng.choice([4, 4, 4, 3, 5, 1])
+                devs.append(",".join([word(), word(), num(), num(), "extra"][:n]))
+            ctrs.append(":".join(devs) + rng.choice([":", ""]))
+        return ";".join(ctrs) + rng.choice([";", "", ";;"])
+
+    checked = errors = 0
+    for _ in range(1500):
+        t = node_text()
+        try:
+            want = O.decode_node_devices(t)
+        except O.CodecError:
+            with pytest.raises(core.CodecError):
+                core.decode_node_devices(t)
+            errors += 1
+        else:
+            got = core.decode_node_devices(t)
+            assert [(d.Id, d.Count, d.Devmem, d.Devcore, d.Type, d.Numa, d.Health) for d in got] == \
+                [(d["Id"], d["Count"], d["Devmem"], d["Devcore"], d["Type"], d["Numa"], d["Health"]) for d in want], repr(t)
+            assert core.encode_node_devices(got) == O.encode_node_devices(want)
+        t = pod_text()
+        try:
+            want = O.decode_pod_single_device(t)
+        except O.CodecError:
+            with pytest.raises(core.CodecError):
+                core.decode_pod_single_device(t)
+            errors += 1
+        else:
+            got = core.decode_pod_single_device(t)
+            assert [[(d.UUID, d.Type, d.Usedmem, d.Usedcores) for d in c] for c in got] == \
+                [[(d["UUID"], d["Type"], d["Usedmem"], d["Usedcores"]) for d in c] for c in want], repr(t)
+            assert core.encode_pod_single_device(got) == O.encode_pod_single_device(want)
+            assert core.erase_next_device_request(t) == O.erase_next_device_request(t), repr(t)
+            try:
+                wi, wd = O.next_device_request(t)
+            except LookupError:
+                with pytest.raises(LookupError):
+                    core.next_device_request(t)
+            else:
+                gi, gd = core.next_device_request(t)
+                assert gi == wi and [(d.UUID, d.Usedmem) for d in gd] == [(d["UUID"], d["Usedmem"]) for d in wd]
+        checked += 1
+    assert checked == 1500 and errors > 100
