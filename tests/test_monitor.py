@@ -149,3 +149,71 @@ def test_swap_counter_extension_block_layout_and_export(tmp_path):
     r2 = v.Region(str(small))
     assert r2.swap_counters(0) is None and r2.snapshot().initialized == 1
     r2.close()
+
+
+def _observe_restated(regs):
+    """feedback.go:197-255 (Observe, CheckBlocking :164-179, CheckPriority :181-195) on dicts {uuids, priority, rk, us}."""
+    ut = {}
+    for r in regs:
+        if r["rk"] > 0:
+            r["rk"] -= 1
+            if r["rk"] > 0:
+                for u in r["uuids"]:
+                    if not u:
+                        continue
+                    ut.setdefault(u, [0, 0])[r["priority"]] += 1
+
+    def blocking(r):
+        for u in r["uuids"]:
+            if u in ut:
+                return any(ut[u][i] > 0 for i in range(r["priority"]))      # decided by the FIRST uuid found
+        return False
+
+    def contended(r):
+        for u in r["uuids"]:
+            if u in ut:
+                if any(ut[u][i] > 0 for i in range(r["priority"])) or ut[u][r["priority"]] > 1:
+                    return True
+        return False
+
+    for r in regs:
+        if blocking(r):
+            if r["rk"] >= 0:
+                r["rk"] = -1
+        elif r["rk"] < 0:
+            r["rk"] = 0
+        r["us"] = 1 if contended(r) else 0
+
+
+def test_observe_equals_the_restated_feedback_loop_on_random_nodes(tmp_path):
+    import random
+    rng = random.Random(4)
+    gpus = [f"GPU-{i:04d}-aaaa-bbbb" for i in range(4)]
+    for case in range(60):
+        n = rng.randint(1, 7)
+        model, regions = [], []
+        for i in range(n):
+            k = rng.randint(1, 3)
+            uu = rng.sample(gpus, k) if rng.random() < 0.9 else []
+            slots = uu + [""] * (3 - len(uu))
+            rng.shuffle(slots)
+            m = {"uuids": slots, "priority": rng.randint(0, 1), "rk": rng.choice([-1, 0, 1, 2, 2, 3]), "us": rng.randint(0, 1)}
+            d = tmp_path / f"c{case}_{i}"
+            d.mkdir()
+            r = v.Region(str(d / "x.cache"), create=True, mem_limits=[0] * 16, sm_limits=[100] * 16, priority=m["priority"])
+            for lane, u in enumerate(slots):
+                if u:
+                    r.set_uuid(lane, u)
+            r.set_feedback(recent_kernel=m["rk"], utilization_switch=m["us"])
+            model.append(m); regions.append(r)
+        for _round in range(4):
+            v.monitor_observe(regions)
+            _observe_restated(model)
+            got = [(r.snapshot().recent_kernel, r.snapshot().utilization_switch) for r in regions]
+            assert got == [(m["rk"], m["us"]) for m in model], (case, _round, model)
+            if rng.random() < 0.5:                                   # a container launches again: the hook resets its counter
+                j = rng.randrange(n)
+                if model[j]["rk"] >= 0:
+                    model[j]["rk"] = 2; regions[j].set_feedback(recent_kernel=2)
+        for r in regions:
+            r.close()
