@@ -440,5 +440,38 @@ EXPORT nvmlReturn_t nvmlDeviceGetProcessUtilization(nvmlDevice_t h, fake_procuti
 }
 EXPORT nvmlReturn_t nvmlDeviceGetMemoryInfo(nvmlDevice_t h, fake_meminfo *m) { int d = nv_index(h); m->total = g_total; m->used = proc_bytes(d); m->free = g_total - m->used; return NVML_SUCCESS; }
 EXPORT nvmlReturn_t nvmlDeviceGetMemoryInfo_v2(nvmlDevice_t h, fake_meminfo_v2 *m) { int d = nv_index(h); m->total = g_total; m->reserved = 0; m->used = proc_bytes(d); m->free = g_total - m->used; return NVML_SUCCESS; }
+/* health events (rm/health.go): FAKE_NVML_XID="<device index>:<xid>@<ms after the set was created>" injects one critical
+ * Xid event; otherwise every wait times out */
+typedef struct { nvmlDevice_t device; unsigned long long eventType, eventData; unsigned gpuInstanceId, computeInstanceId; } fake_eventdata;
+static struct { int dev; unsigned long long xid; long at_ms; int fired; struct timeval t0; int armed; } g_xid;
+EXPORT nvmlReturn_t nvmlEventSetCreate(void **set) {
+    static int obj; *set = &obj;
+    const char *e = getenv("FAKE_NVML_XID");
+    memset(&g_xid, 0, sizeof g_xid);
+    if (e && sscanf(e, "%d:%llu@%ld", &g_xid.dev, &g_xid.xid, &g_xid.at_ms) == 3) { g_xid.armed = 1; gettimeofday(&g_xid.t0, 0); }
+    return NVML_SUCCESS;
+}
+EXPORT nvmlReturn_t nvmlEventSetFree(void *set) { (void)set; return NVML_SUCCESS; }
+EXPORT nvmlReturn_t nvmlDeviceGetSupportedEventTypes(nvmlDevice_t h, unsigned long long *types) { (void)h; *types = 0x1f; return NVML_SUCCESS; }
+EXPORT nvmlReturn_t nvmlDeviceRegisterEvents(nvmlDevice_t h, unsigned long long types, void *set) { (void)h; (void)types; (void)set; return NVML_SUCCESS; }
+static nvmlReturn_t event_wait(fake_eventdata *d, unsigned timeout_ms) {
+    struct timeval now; gettimeofday(&now, 0);
+    long el = (now.tv_sec - g_xid.t0.tv_sec) * 1000 + (now.tv_usec - g_xid.t0.tv_usec) / 1000;
+    if (g_xid.armed && !g_xid.fired) {
+        long wait = g_xid.at_ms - el;
+        if (wait <= (long)timeout_ms) {
+            if (wait > 0) usleep((useconds_t)wait * 1000);
+            g_xid.fired = 1;
+            memset(d, 0, sizeof *d);
+            d->device = &g_nvdev_obj[g_xid.dev]; d->eventType = 0x8; d->eventData = g_xid.xid; d->gpuInstanceId = d->computeInstanceId = 0xFFFFFFFFu;
+            return NVML_SUCCESS;
+        }
+    }
+    usleep((useconds_t)(timeout_ms > 200 ? 200 : timeout_ms) * 1000);
+    return 10;   /* NVML_ERROR_TIMEOUT */
+}
+EXPORT nvmlReturn_t nvmlEventSetWait_v2(void *set, fake_eventdata *d, unsigned timeout_ms) { (void)set; return event_wait(d, timeout_ms); }
+EXPORT nvmlReturn_t nvmlEventSetWait(void *set, fake_eventdata *d, unsigned timeout_ms) { (void)set; return event_wait(d, timeout_ms); }
+EXPORT nvmlReturn_t nvmlDeviceGetUtilizationRates(nvmlDevice_t h, unsigned *u) { (void)h; u[0] = g_sm_util; u[1] = 0; return NVML_SUCCESS; }
 EXPORT nvmlReturn_t nvmlSystemGetDriverVersion(char *v, unsigned len) { snprintf(v, len, "580.159"); return NVML_SUCCESS; }
 EXPORT nvmlReturn_t nvmlSystemGetCudaDriverVersion(int *v) { *v = 12090; return NVML_SUCCESS; }

@@ -235,3 +235,97 @@ def test_scheduler_cli_serves_filter_and_metrics():
         except subprocess.TimeoutExpired:
             proc.kill()
         api.stop()
+
+
+def test_device_plugin_cli_end_to_end_on_fake_nvml(tmp_path):
+    """BASELINE.json configs[0] through the real entry point: `python -m k8s_device_plugin_b200.plugin device-plugin`
+    enumerates two (fake) GPUs through NVML, registers with a kubelet stub, answers ListAndWatch with 2 x split ids,
+    keeps the node annotation registered on the (scripted) apiserver, answers Allocate for a pod the scheduler bound,
+    and reports a GPU unhealthy after a critical Xid event."""
+    from conftest import FAKE
+    from k8s_device_plugin_b200.plugin import api as A
+    from k8s_device_plugin_b200.plugin.kubelet_stub import KubeletStub
+    sock = tmp_path / "dp"
+    sock.mkdir()
+    uuid0 = "GPU-b2a39081-f6e7-d4c5-3a2b-18097e6f5c00"            # what the fake NVML reports for device 0
+    pod = _pod("train", {P.RESOURCE_NAME: "1", P.RESOURCE_MEM: "8192", P.RESOURCE_CORES: "30"})
+    pod["metadata"]["annotations"] = {S.ASSIGNED_NODE: "node-a", P.BIND_TIME: "1", P.BIND_PHASE: "allocating",
+                                      P.TO_ALLOCATE: f"{uuid0},NVIDIA,8192,30:;", P.ALLOCATED: f"{uuid0},NVIDIA,8192,30:;"}
+    apisrv = FakeApiServer([{"metadata": {"name": "node-a", "annotations": {}}}], [pod])
+    stub = KubeletStub(str(sock)); stub.start()
+    env = dict(os.environ, PYTHONPATH=ROOT, LD_LIBRARY_PATH=FAKE + ":" + os.environ.get("LD_LIBRARY_PATH", ""), FAKE_GPU_COUNT="2",
+               FAKE_NVML_XID="1:79@2500", NodeName="node-a")
+    hook = tmp_path / "hook"
+    proc = subprocess.Popen([sys.executable, "-m", "k8s_device_plugin_b200.plugin", "device-plugin", "--apiserver", apisrv.url, "--socket-dir", str(sock),
+                             "--node-name", "node-a", "--device-split-count", "3", "--hook-path", str(hook), "--config-file", str(tmp_path / "none.json")],
+                            env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    try:
+        assert stub.registered.wait(30), proc.poll()
+        assert stub.request.resource_name == "nvidia.com/gpu" and stub.request.endpoint == "nvidia-gpu.sock"
+        first = stub.list_and_watch_once(1)[0]
+        ids = [d.ID for d in first.devices]
+        assert len(ids) == 6 and ids[0] == uuid0 + "-0" and all(d.health == A.HEALTHY for d in first.devices)
+        deadline = time.time() + 10
+        while P.REGISTER not in apisrv.nodes["node-a"]["metadata"]["annotations"] and time.time() < deadline:
+            time.sleep(0.05)
+        reg = apisrv.nodes["node-a"]["metadata"]["annotations"][P.REGISTER]
+        assert reg.startswith(f"{uuid0},3,183359,100,NVIDIA-NVIDIA B200 (fake),0,true:")
+        resp = stub.allocate([[ids[0]]])
+        envs = dict(resp.container_responses[0].envs)
+        assert envs["CUDA_DEVICE_MEMORY_LIMIT_0"] == "8192m" and envs["CUDA_DEVICE_SM_LIMIT"] == "30" and envs["NVIDIA_VISIBLE_DEVICES"] == uuid0
+        assert {m.container_path for m in resp.container_responses[0].mounts} >= {"/etc/ld.so.preload", "/tmp/vgpulock"}
+        annos = apisrv.pods[("default", "train")]["metadata"]["annotations"]
+        assert annos[P.BIND_PHASE] == "success" and annos[P.TO_ALLOCATE] == ";"
+        # the Xid event for GPU 1 arrives ~2.5 s after the health checker starts: its three shares go Unhealthy
+        two = stub.list_and_watch_once(2, timeout=20)
+        bad = [d.ID for d in two[-1].devices if d.health == A.UNHEALTHY]
+        assert len(bad) == 3 and all(b.startswith("GPU-b3a29180") for b in bad)
+    finally:
+        proc.terminate()
+        try:
+            proc.wait(5)
+        except subprocess.TimeoutExpired:
+            proc.kill()
+        stub.stop(); apisrv.stop()
+
+
+def test_monitor_cli_exports_region_and_host_metrics(tmp_path):
+    from conftest import FAKE, HOOK_SO, OREF
+    uid, ctr = "uid-train", "main"
+    cdir = tmp_path / "containers" / f"{uid}_{ctr}"
+    cdir.mkdir(parents=True)
+    trace = tmp_path / "t.txt"
+    trace.write_text("A 0 %d\nS 6000\n" % (100 << 20))
+    henv = dict(os.environ, LD_LIBRARY_PATH=FAKE + ":" + os.environ.get("LD_LIBRARY_PATH", ""), LD_PRELOAD=HOOK_SO, LIBCUDA_LOG_LEVEL="0",
+                CUDA_DEVICE_MEMORY_LIMIT_0="1g", CUDA_DEVICE_MEMORY_SHARED_CACHE=str(cdir / "x.cache"), FAKE_GPU_CTX_MIB="16")
+    app = subprocess.Popen([os.path.join(OREF, "trace_replay"), str(trace)], env=henv, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    pod = _pod("train", {P.RESOURCE_NAME: "1"})
+    pod["spec"]["nodeName"] = "node-a"
+    apisrv = FakeApiServer([], [pod])
+    port = _free_port()
+    env = dict(os.environ, PYTHONPATH=ROOT, LD_LIBRARY_PATH=FAKE + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    mon = subprocess.Popen([sys.executable, "-m", "k8s_device_plugin_b200.plugin", "monitor", "--apiserver", apisrv.url, "--containers-path",
+                            str(tmp_path / "containers"), "--port", str(port)], env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    try:
+        text, deadline = "", time.time() + 30
+        while time.time() < deadline:
+            try:
+                c = http.client.HTTPConnection("127.0.0.1", port, timeout=5)
+                c.request("GET", "/metrics")
+                text = c.getresponse().read().decode()
+                if "vGPU_device_memory_usage_in_bytes{" in text:
+                    break
+            except OSError:
+                pass
+            time.sleep(0.3)
+        base = 'podnamespace="default",podname="train",ctrname="main",vdeviceid="0"'
+        assert f"vGPU_device_memory_usage_in_bytes{{{base}" in text and "} %s" % float((100 << 20) + (16 << 20)) in text
+        assert f"vGPU_device_memory_limit_in_bytes{{{base}" in text and "HostGPUMemoryUsage{" in text and "HostCoreUtilization{" in text
+    finally:
+        for p in (mon, app):
+            p.terminate()
+            try:
+                p.wait(5)
+            except subprocess.TimeoutExpired:
+                p.kill()
+        apisrv.stop()
