@@ -370,17 +370,10 @@ static uint64_t room_for_engine(uint64_t lim, uint64_t fixed, const SwapEngine *
 bool Runtime::charge(int dev, size_t bytes) {
     if (!cfg_.oversubscribe) return region_->try_add(pid_, dev, bytes, VGPU_MEM_BUFFER, true);   // oom_check + add, reference semantics
     if (cfg_.limit_is_virtual) {
-        // reference meaning of the limit (hard cap on live bytes), plus: what is not swappable is resident for life
-        if (!region_->try_add(pid_, dev, bytes, VGPU_MEM_BUFFER, true)) return false;
-        uint64_t lim = region_->limit(dev);
-        if (SwapEngine *e = swap(dev)) {
-            if (lim) {
-                uint64_t u = region_->usage(dev), live = e->live_bytes();
-                uint64_t fixed = u > live ? u - live : 0;
-                e->set_resident_cap(room_for_engine(lim, fixed, e));
-            }
-        }
-        return true;
+        // reference meaning of the limit: a hard cap on live bytes and nothing else. What may be RESIDENT is bounded by
+        // the device, not by the limit (the engine sizes itself from the device's free memory and backs off under
+        // physical pressure), so nothing is taken out of its room here.
+        return region_->try_add(pid_, dev, bytes, VGPU_MEM_BUFFER, true);
     }
     // swap mode: the quota bounds RESIDENT bytes. Non-swappable allocations are resident for life, so they are checked
     // against the quota net of what the swap engine can page out, and they shrink the engine's resident budget.
@@ -398,7 +391,7 @@ bool Runtime::charge(int dev, size_t bytes) {
 
 void Runtime::uncharge(int dev, size_t bytes) {
     region_->sub(pid_, dev, bytes, VGPU_MEM_BUFFER);
-    if (!cfg_.oversubscribe) return;
+    if (!cfg_.oversubscribe || cfg_.limit_is_virtual) return;
     uint64_t lim = region_->limit(dev);
     SwapEngine *e = swap(dev);
     if (lim && e) {
@@ -416,8 +409,10 @@ CUresult Runtime::swap_alloc(CUdeviceptr *dptr, size_t bytes, int dev) {
             uint64_t lim = region_ ? region_->limit(dev) : 0;
             uint64_t fixed = region_ ? region_->usage(dev) : 0;
             uint64_t cap = lim > fixed ? lim - fixed : 0;
-            SwapConfig sc = SwapConfig::from_env(lim ? cap : 0, cfg_.limit_is_virtual ? 0 : cfg_.virtual_limit[dev]);   // virtual mode: the region check is the cap
-            if (lim) {
+            // virtual mode: the region check is the cap on live bytes; residency is bounded by the device (cap 0 = size
+            // from the device's free memory)
+            SwapConfig sc = SwapConfig::from_env(lim && !cfg_.limit_is_virtual ? cap : 0, cfg_.limit_is_virtual ? 0 : cfg_.virtual_limit[dev]);
+            if (lim && !cfg_.limit_is_virtual) {
                 uint64_t overhead = 2ull * sc.ring_slots * sc.chunk_bytes;     // == SwapEngine::device_overhead()
                 sc.resident_cap = cap > overhead ? cap - overhead : 0;
                 if (sc.resident_cap < (32ull << 20)) { LOG_ERROR("gpumem quota %lu leaves no room for swappable memory", (unsigned long)lim); return CUDA_ERROR_OUT_OF_MEMORY; }
@@ -536,7 +531,7 @@ bool Runtime::check_oom() {
     if (!ensure_initialized()) return false;
     int dev = current_device();
     if (dev < 0) return false;
-    if (cfg_.oversubscribe) {
+    if (cfg_.oversubscribe && !cfg_.limit_is_virtual) {
         // swap mode: the quota bounds resident bytes; live swappable bytes above it are the point of the mode, so only
         // the non-swappable part is held against the limit (same rule as charge())
         uint64_t lim = region_->limit(dev);
@@ -565,7 +560,7 @@ CUresult Runtime::mem_get_info(size_t *free_b, size_t *total_b) {
         if (free_b) *free_b = rt - usage;
         return CUDA_SUCCESS;
     }
-    if (cfg_.oversubscribe) {
+    if (cfg_.oversubscribe && !cfg_.limit_is_virtual) {
         // swap mode: the quota bounds residency, not live bytes (DESIGN.md "quota semantics"); report the virtual
         // capacity and never the reference's CUDA_ERROR_INVALID_VALUE for usage > limit (@0x36b3a)
         uint64_t vcap = cfg_.virtual_limit[dev];

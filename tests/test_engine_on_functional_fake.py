@@ -197,6 +197,31 @@ def test_virtual_limit_mode_is_the_references_meaning_of_the_limit_past_the_limi
     assert sum(" rc=-1 " in l for l in new) > 10                      # the limit was really crossed, many times
 
 
+@pytest.mark.parametrize("seed", [300, 306])
+def test_virtual_limit_mode_random_three_gpu_traces_match_the_reference_binary(tmp_path, seed):
+    """The randomised three-GPU differential test of tests/test_hook_parity_cpu.py, with CUDA_OVERSUBSCRIBE=true and
+    VGPU_SWAP_LIMIT_MODE=virtual on the functional fake: large allocations go through the swap engine here and through
+    cuMemAllocManaged in the reference — codes, counters, cuMemGetInfo (including its INVALID_VALUE once a cross-device
+    free has wrapped a lane) all agree."""
+    from conftest import have_reference, run_replay
+    if not have_reference():
+        pytest.skip("reference binary only exists in the build container")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz_gen", os.path.join(ROOT, "scripts", "fuzz_vs_reference.py"))
+    src = open(spec.origin).read().split("import tempfile")[0]          # the generator only, not the driver loop
+    ns = {"__file__": spec.origin}
+    exec(compile(src, spec.origin, "exec"), ns)
+    t = tmp_path / "t.txt"
+    t.write_text("\n".join(ns["gen"](seed)) + "\n")
+    env = {"CUDA_DEVICE_MEMORY_LIMIT_0": "196m", "CUDA_DEVICE_MEMORY_LIMIT_1": "164m", "CUDA_DEVICE_MEMORY_LIMIT_2": "300m", "FAKE_GPU_COUNT": "3",
+           "FAKE_GPU_CTX_MIB": "16", "VGPU_REFERENCE_COVERAGE": "1", "FAKE_GPU_EXEC": "1", "CUDA_OVERSUBSCRIBE": "true", "VGPU_SWAP_LIMIT_MODE": "virtual",
+           "VGPU_SWAP_CHUNK_MB": "4", "VGPU_SWAP_ARENA_GB": "8", "VGPU_SWAP_SLAB_MB": "64", "VGPU_SWAP_SPARE_MB": "16"}
+    new = run_replay(str(t), "new", dict(env, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "n.cache"))).splitlines()
+    ref = run_replay(str(t), "reference", dict(env, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "r.cache"))).splitlines()
+    diffs = [f"{a}   |   {b}" for a, b in zip(new, ref) if a != b]
+    assert not diffs and len(new) == len(ref), "\n".join(diffs[:8])
+
+
 def test_virtual_limit_mode_pages_only_under_physical_pressure(tmp_path):
     # 320 MiB live under a 384 MiB limit on a device that can only give ~160 MiB: admitted by the limit, paged by the engine
     out = _swap_bench(tmp_path, ["--buffers", "20", "--mib", "16", "--steps", "60", "--warmup", "4", "--order", "cyclic"],
