@@ -362,6 +362,13 @@ SwapEngine *Runtime::swap(int dev) {
 
 // what the engine may keep resident: the quota minus everything that is resident for life (context, non-swappable
 // allocations) minus the engine's own staging rings
+// resident-for-life bytes = accounted usage minus the live swappable bytes. The lanes use the reference's wrapping u64
+// arithmetic (a cross-device free can drive one below zero, see mem_free), so the difference is read as signed.
+static uint64_t fixed_bytes(uint64_t usage, uint64_t live) {
+    int64_t f = (int64_t)(usage - live);
+    return f > 0 ? (uint64_t)f : 0;
+}
+
 static uint64_t room_for_engine(uint64_t lim, uint64_t fixed, const SwapEngine *e) {
     uint64_t taken = fixed + (e ? e->device_overhead() : 0);
     return lim > taken ? lim - taken : 0;
@@ -381,7 +388,7 @@ bool Runtime::charge(int dev, size_t bytes) {
     SwapEngine *e = swap(dev);
     if (lim) {
         uint64_t u = region_->usage(dev), live = e ? e->live_bytes() : 0;
-        uint64_t fixed = u > live ? u - live : 0;
+        uint64_t fixed = fixed_bytes(u, live);
         if (fixed + bytes > lim) { LOG_ERROR("Device %d OOM %lu / %lu (non-swappable)", dev, (unsigned long)(fixed + bytes), (unsigned long)lim); return false; }
         if (e) e->set_resident_cap(room_for_engine(lim, fixed + bytes, e));
     }
@@ -396,7 +403,7 @@ void Runtime::uncharge(int dev, size_t bytes) {
     SwapEngine *e = swap(dev);
     if (lim && e) {
         uint64_t u = region_->usage(dev), live = e->live_bytes();
-        uint64_t fixed = u > live ? u - live : 0;
+        uint64_t fixed = fixed_bytes(u, live);
         e->set_resident_cap(room_for_engine(lim, fixed, e));
     }
 }
@@ -407,7 +414,7 @@ CUresult Runtime::swap_alloc(CUdeviceptr *dptr, size_t bytes, int dev) {
         std::lock_guard<std::mutex> g(swap_mu_);
         if (!swap_[dev]) {
             uint64_t lim = region_ ? region_->limit(dev) : 0;
-            uint64_t fixed = region_ ? region_->usage(dev) : 0;
+            uint64_t fixed = region_ ? fixed_bytes(region_->usage(dev), 0) : 0;
             uint64_t cap = lim > fixed ? lim - fixed : 0;
             // virtual mode: the region check is the cap on live bytes; residency is bounded by the device (cap 0 = size
             // from the device's free memory)
@@ -538,7 +545,7 @@ bool Runtime::check_oom() {
         if (!lim) return false;
         SwapEngine *e = swap(dev);
         uint64_t u = region_->usage(dev), live = e ? e->live_bytes() : 0;
-        return (u > live ? u - live : 0) > lim;
+        return fixed_bytes(u, live) > lim;
     }
     return !region_->try_add(pid_, dev, 0, VGPU_MEM_BUFFER, true, true);
 }
