@@ -49,7 +49,9 @@ static void map_region(void) {
 static void lanes(uint64_t *ctx, uint64_t *buf, uint64_t *tot, int *nproc) {
     *ctx = *buf = *tot = 0; *nproc = 0;
     if (!g_region) return;
-    for (int s = 0; s < 1024; s++) {
+    int32_t procnum; memcpy(&procnum, g_region + 0xC4738, 4);      /* only the first proc_num slots are live: the reference
+                                                                      compacts without clearing what it vacates */
+    for (int s = 0; s < procnum && s < 1024; s++) {
         const unsigned char *slot = g_region + OFF_PROCS + (size_t)s * SLOT_STRIDE;
         int32_t pid; memcpy(&pid, slot, 4);
         if (!pid) continue;

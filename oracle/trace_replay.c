@@ -95,7 +95,8 @@ static void map_region(void) {
 static void counters(int dev, uint64_t out[5]) {
     memset(out, 0, 5 * sizeof(uint64_t));
     if (!g_region) return;
-    for (int s = 0; s < MAXPROC; s++) {
+    int32_t procnum; memcpy(&procnum, g_region + OFF_PROCNUM, 4);   /* live slots only: the reference compacts without clearing */
+    for (int s = 0; s < procnum && s < MAXPROC; s++) {
         const unsigned char *slot = g_region + OFF_PROCS + (size_t)s * SLOT_STRIDE;
         int32_t pid; memcpy(&pid, slot, 4);
         if (pid == 0) continue;

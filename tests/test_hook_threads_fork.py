@@ -35,7 +35,5 @@ def test_forked_child_gets_a_slot_and_its_orphaned_bytes_are_reclaimed(tmp_path)
         os.makedirs("/tmp/vgpulock", exist_ok=True)
         ref_dir = tmp_path / "ref"; ref_dir.mkdir()
         rchild, rparent = _run(ref_dir, ["fork"], preload=SHIM_SO + ":" + REF_SO)
-        assert rchild == child and rparent["buf_after_child"] == parent["buf_after_child"] and rparent["r2"] == -1
-        # the reference admits the 32 MiB request WITHOUT dropping the dead child's slot (72 MiB charged against a
-        # 64 MiB quota, two OOM lines logged): its retry after rm_quitted_process does not re-check. Not reproduced.
-        assert rparent["r1"] == 0 and rparent["buf_after_reclaim"] == 56 * M and rparent["procs_after_reclaim"] == 2
+        # same story in the reference: "rm pid=<child>" (rm_quitted_process@0x41a8e), then the request fits
+        assert rchild == child and rparent == parent
