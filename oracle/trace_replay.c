@@ -18,6 +18,8 @@
  *   D n (make device n's primary context current; the counters printed from then on are device n's lane)
  *   N (nvmlDeviceGetMemoryInfo of NVML device 0 — the hook's exported wrapper when one is preloaded; prints
  *      " nv_total=.. nv_free=.. nv_used=..")
+ *   U ms (sleep until the absolute time <ms since the epoch>: lets several replayers act on one shared schedule)
+ *   K (kill(getpid(), SIGKILL): a process that dies without running its exit handler)
  *   Q id (cuPointerGetAttributes {MEMORY_TYPE, IS_MANAGED} of pointer id; prints " type=<n> managed=<n>")
  * Output line: "<op#> <opcode> rc=<int> ctx=<u64> mod=<u64> buf=<u64> off=<u64> tot=<u64> [free=.. total=..]"
  * where the five counters are SUMMED over every process slot of device 0 (== own slot for one process).
@@ -25,6 +27,8 @@
 #define _GNU_SOURCE
 #include <dlfcn.h>
 #include <fcntl.h>
+#include <signal.h>
+#include <time.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -154,6 +158,11 @@ int main(int argc, char **argv) {
         case 'T': r = cuDeviceTotalMem_v2(&tot, dev); fr = 0; has_info = 1; break;
         case 'L': r = cuLaunchKernel(fn, (unsigned)a, (unsigned)b, (unsigned)d, 1, 1, 1, 0, NULL, NULL, NULL); break;
         case 'S': usleep((useconds_t)a * 1000); r = 0; break;   /* sleep a ms (multi-process tests) */
+        case 'U': { struct timespec ts; clock_gettime(CLOCK_REALTIME, &ts);
+                    long long nowms = (long long)ts.tv_sec * 1000 + ts.tv_nsec / 1000000, wait = (long long)a - nowms;
+                    if (wait > 0) usleep((useconds_t)wait * 1000);
+                    r = 0; break; }
+        case 'K': fflush(stdout); kill(getpid(), SIGKILL); r = 0; break;
         case 'D': { int n2 = (int)a & 15; CUdevice d2; r = cuDeviceGet(&d2, n2);
                     if (!r && !ctxs[n2]) r = cuDevicePrimaryCtxRetain(&ctxs[n2], d2);
                     if (!r) r = cuCtxSetCurrent(ctxs[n2]);

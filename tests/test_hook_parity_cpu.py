@@ -320,3 +320,64 @@ def test_random_multi_device_traces_match_the_reference_binary(tmp_path, seed):
     diffs = [f"{a}   |   {b}" for a, b in zip(new, ref) if a != b]
     assert not diffs and len(new) == len(ref), "\n".join(diffs[:10])
     assert sum(" rc=-1 " in l for l in new) > 20 and sum(" rc=2 " in l for l in new) > 3
+
+
+def _scheduled_container(tmp_path, preload, tag, seed):
+    """Three processes of ONE container act on a shared wall-clock schedule (trace op U): allocations and frees
+    interleave across processes, one exits normally mid-way (exit handler releases its slot), one dies by SIGKILL (slot
+    left behind until a breach reclaims it). Returns the three output streams."""
+    import random
+    import time
+    rng = random.Random(seed)
+    cache = str(tmp_path / f"{tag}.cache")
+    t0 = int(time.time() * 1000) + 1500
+    slot_ms, nslots = 60, 45
+    traces = [[], [], []]
+    live = [[], [], []]
+    nid = [0, 0, 0]
+    for k in range(nslots):
+        p = k % 3
+        tr = traces[p]
+        if p == 1 and k >= 27:          # process 1 has exited by now
+            continue
+        if p == 2 and k >= 36:          # process 2 was killed
+            continue
+        tr.append(f"U {t0 + k * slot_ms}")
+        r = rng.random()
+        if p == 1 and k >= 24:
+            continue                    # (its last slots only wait, then the trace ends -> normal exit)
+        if p == 2 and k >= 33:
+            tr.append("K")
+            continue
+        if r < 0.6 or not live[p]:
+            tr.append(f"{rng.choice('AAMP')} {nid[p]} {rng.choice([3 << 20, 9 << 20, 20 << 20, 35 << 20])}".replace("P ", "P ").replace("M ", "M "))
+            if tr[-1].startswith("P"):
+                tr[-1] = f"P {nid[p]} 4096 {rng.choice([256, 2048])}"
+            live[p].append(nid[p]); nid[p] += 1
+        elif r < 0.85:
+            tr.append(f"F {live[p].pop(rng.randrange(len(live[p])))}")
+        else:
+            tr.append("I")
+    env = dict(os.environ, LD_LIBRARY_PATH=FAKE + ":" + os.environ.get("LD_LIBRARY_PATH", ""), LD_PRELOAD=preload, LIBCUDA_LOG_LEVEL="0",
+               CUDA_DEVICE_MEMORY_LIMIT_0="160m", CUDA_DEVICE_MEMORY_SHARED_CACHE=cache, FAKE_GPU_CTX_MIB="16")
+    procs = []
+    for i, tr in enumerate(traces):
+        f = tmp_path / f"{tag}_{i}.txt"
+        f.write_text("\n".join(tr) + "\n")
+        procs.append(subprocess.Popen([os.path.join(OREF, "trace_replay"), str(f)], env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
+    outs = [p.communicate(timeout=60)[0] for p in procs]
+    # drop the U lines (they carry no information and their count is the same) but keep everything else
+    # (the "init" line is a start-up race — whether a sibling has registered its context yet — not part of the schedule)
+    return [[l for l in o.splitlines() if " U rc=" not in l and not l.startswith("init")] for o in outs]
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
+def test_three_processes_of_one_container_on_a_shared_schedule_match_the_reference(tmp_path):
+    os.makedirs("/tmp/vgpulock", exist_ok=True)
+    from conftest import REF_SO, SHIM_SO
+    new = _scheduled_container(tmp_path, HOOK_SO, "new", seed=12)
+    ref = _scheduled_container(tmp_path, SHIM_SO + ":" + REF_SO, "ref", seed=12)
+    for i, (a, b) in enumerate(zip(new, ref)):
+        diffs = [f"{x}   |   {y}" for x, y in zip(a, b) if x != y]
+        assert not diffs and len(a) == len(b), f"process {i}:\n" + "\n".join(diffs[:8])
+    assert any(" rc=-1 " in l or " rc=2 " in l for o in new for l in o)     # the shared quota was crossed
