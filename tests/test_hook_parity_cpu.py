@@ -358,10 +358,11 @@ def _scheduled_container(tmp_path, preload, tag, seed):
             tr.append(f"F {live[p].pop(rng.randrange(len(live[p])))}")
         else:
             tr.append("I")
-    env = dict(os.environ, LD_LIBRARY_PATH=FAKE + ":" + os.environ.get("LD_LIBRARY_PATH", ""), LD_PRELOAD=preload, LIBCUDA_LOG_LEVEL="0",
-               CUDA_DEVICE_MEMORY_LIMIT_0="160m", CUDA_DEVICE_MEMORY_SHARED_CACHE=cache, FAKE_GPU_CTX_MIB="16")
+    preloads = preload if isinstance(preload, (list, tuple)) else [preload] * 3
     procs = []
     for i, tr in enumerate(traces):
+        env = dict(os.environ, LD_LIBRARY_PATH=FAKE + ":" + os.environ.get("LD_LIBRARY_PATH", ""), LD_PRELOAD=preloads[i], LIBCUDA_LOG_LEVEL="0",
+                   CUDA_DEVICE_MEMORY_LIMIT_0="160m", CUDA_DEVICE_MEMORY_SHARED_CACHE=cache, FAKE_GPU_CTX_MIB="16")
         f = tmp_path / f"{tag}_{i}.txt"
         f.write_text("\n".join(tr) + "\n")
         procs.append(subprocess.Popen([os.path.join(OREF, "trace_replay"), str(f)], env=env, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
@@ -381,3 +382,19 @@ def test_three_processes_of_one_container_on_a_shared_schedule_match_the_referen
         diffs = [f"{x}   |   {y}" for x, y in zip(a, b) if x != y]
         assert not diffs and len(a) == len(b), f"process {i}:\n" + "\n".join(diffs[:8])
     assert any(" rc=-1 " in l or " rc=2 " in l for o in new for l in o)     # the shared quota was crossed
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
+@pytest.mark.parametrize("mix", [(0,), (1, 2), (0, 2)])
+def test_reference_hooked_and_new_hooked_processes_share_one_region_file(tmp_path, mix):
+    """File-format and lock-protocol compatibility, live: in one container some processes run under the reference binary
+    and the others under the new hook, all on the SAME region file (same semaphore, same slots). Every process's stream
+    equals what it prints when all three run under the reference."""
+    os.makedirs("/tmp/vgpulock", exist_ok=True)
+    from conftest import REF_SO, SHIM_SO
+    refp = SHIM_SO + ":" + REF_SO
+    ref = _scheduled_container(tmp_path, refp, "allref", seed=21)
+    mixed = _scheduled_container(tmp_path, [HOOK_SO if i in mix else refp for i in range(3)], "mixed", seed=21)
+    for i, (a, b) in enumerate(zip(mixed, ref)):
+        diffs = [f"{x}   |   {y}" for x, y in zip(a, b) if x != y]
+        assert not diffs and len(a) == len(b), f"process {i} ({'new' if i in mix else 'reference'} hook):\n" + "\n".join(diffs[:8])
