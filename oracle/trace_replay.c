@@ -197,6 +197,11 @@ int main(int argc, char **argv) {
             printf(" free=%zu total=%zu", fr, tot);
         }
         if (has_q) printf(" type=%d managed=%d", qtype, qman);
+        if (op == 'L' && g_region && getenv("TRACE_SHOW_WORDS")) {   /* the monitor handshake words next to a launch */
+            int32_t w[3]; memcpy(w, g_region + 0xC473C, 12);
+            uint64_t sm; memcpy(&sm, g_region + 0x6B8, 8);
+            printf(" us=%d rk=%d pr=%d sm0=%lu", w[0], w[1], w[2], (unsigned long)sm);
+        }
         if (has_nv) printf(" nv_total=%llu nv_free=%llu nv_used=%llu", nvmem[0], nvmem[1], nvmem[2]);
         putchar('\n');
         opn++;

@@ -398,3 +398,16 @@ def test_reference_hooked_and_new_hooked_processes_share_one_region_file(tmp_pat
     for i, (a, b) in enumerate(zip(mixed, ref)):
         diffs = [f"{x}   |   {y}" for x, y in zip(a, b) if x != y]
         assert not diffs and len(a) == len(b), f"process {i} ({'new' if i in mix else 'reference'} hook):\n" + "\n".join(diffs[:8])
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
+@pytest.mark.parametrize("extra", [{}, {"CUDA_DEVICE_SM_LIMIT": "50"}, {"CUDA_DEVICE_SM_LIMIT": "50", "CUDA_TASK_PRIORITY": "0"},
+                                   {"CUDA_DEVICE_SM_LIMIT": "30", "GPU_CORE_UTILIZATION_POLICY": "disable"}, {"CUDA_TASK_PRIORITY": "0"}])
+def test_monitor_handshake_words_after_launches_match_the_reference(tmp_path, extra):
+    """recentKernel / utilizationSwitch / priority / sm_limit as a launch leaves them (the words the node monitor reads
+    and writes, feedback.go:197-255): identical to the reference binary under every limiter configuration."""
+    t = _write(tmp_path, "L 1 1 1\nA 0 4096\nL 4 4 1\nL 1 1 1\n")
+    env = _env(tmp_path, "1g", FAKE_GPU_CTX_MIB="16", FAKE_GPU_EXEC="1", TRACE_SHOW_WORDS="1", **extra)
+    new = run_replay(t, "new", env).splitlines()
+    ref = run_replay(t, "reference", dict(env, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "ref.cache"))).splitlines()
+    assert new == ref and " rk=2 " in new[1]
