@@ -446,9 +446,11 @@ VGPU_EXPORT CUresult cuGetProcAddress(const char *symbol, void **pfn, int cudaVe
 
 // dlsym override (libvgpu.so@0x11b36): libcudart and frameworks resolve the driver with dlopen("libcuda.so.1") +
 // dlsym(handle, "cu..."), which never consults LD_PRELOAD order — so the lookup itself is intercepted.
+#ifndef VGPU_NO_DLSYM_OVERRIDE   // (sanitizer builds leave it out: the sanitizer runtime calls dlsym before its shadow memory exists)
 VGPU_EXPORT void *dlsym(void *handle, const char *symbol) {
     if (symbol && !control_disabled() && ((symbol[0] == 'c' && symbol[1] == 'u') || !std::strncmp(symbol, "nvml", 4))) {
         if (void *h = find_hook_exact(symbol)) return h;
     }
     return vgpu::real_dlsym(handle, symbol);
 }
+#endif
