@@ -1,5 +1,5 @@
 #!/bin/bash
-# Builds the hook with AddressSanitizer + UBSan (into k8s-device-plugin_b200/build/asan/, never shipped) and drives it on
+# Builds the hook with AddressSanitizer + UBSan, then with ThreadSanitizer (into k8s-device-plugin_b200/build/{asan,tsan}/, never shipped) and drives it on
 # the fake driver through the scenarios the CPU suite uses: swap (cyclic / zipf / physical pressure / virtual limit mode),
 # threads + fork, randomised three-GPU traces, the limiter launch loop. Any sanitizer report fails the script.
 set -u
@@ -37,4 +37,16 @@ PY
 for s in 1 2; do run FAKE_GPU_COUNT=3 CUDA_DEVICE_MEMORY_LIMIT_0=96m CUDA_DEVICE_MEMORY_LIMIT_1=64m CUDA_DEVICE_MEMORY_LIMIT_2=200m -- $R/oracle/_ref/trace_replay $T/fz$s.txt; done
 for s in 1 2; do run $SW FAKE_GPU_COUNT=3 VGPU_SWAP_LIMIT_MODE=virtual CUDA_DEVICE_MEMORY_LIMIT_0=196m CUDA_DEVICE_MEMORY_LIMIT_1=164m CUDA_DEVICE_MEMORY_LIMIT_2=300m -- $R/oracle/_ref/trace_replay $T/fz$s.txt; done
 if ls $T/asan.* $T/ubsan.* > /dev/null 2>&1; then echo "SANITIZER REPORTS:"; head -60 $T/asan.* $T/ubsan.* 2>/dev/null; exit 1; fi
-echo "no sanitizer reports in $n scenarios"; rm -rf $T
+echo "no ASan/UBSan reports in $n scenarios"
+# ---- ThreadSanitizer: the multi-threaded scenarios (application threads racing on the allocation table; the reaper thread)
+TS=$P/build/tsan; mkdir -p $TS; ln -sf $L/libtsan.so.2 $TS/libtsan.so
+FT="-std=c++17 -O1 -g -fno-omit-frame-pointer -DVGPU_NO_DLSYM_OVERRIDE -fsanitize=thread -fPIC -fvisibility=hidden -I$R/include -I/usr/local/cuda/include"
+for f in driver region kmod swap limiter runtime cabi plugin_core sched_core hook passthrough; do g++ $FT -c -o $TS/$f.o $P/csrc/$f.cc || exit 1; done
+g++ -shared -fsanitize=thread -L$TS -Wl,-soname,libvgpu.so -o $TS/libvgpu.so $TS/{driver,region,kmod,swap,limiter,runtime,cabi,plugin_core,sched_core,hook,passthrough}.o $P/build/kernels_cubin.o -ldl -lpthread || exit 1
+PRE=$L/libtsan.so.2:$TS/libvgpu.so
+export TSAN_OPTIONS="halt_on_error=0 log_path=$T/tsan"
+run CUDA_DEVICE_MEMORY_LIMIT_0=64m -- $R/oracle/_ref/hook_stress threads 8 1500
+run $SW CUDA_DEVICE_MEMORY_LIMIT_0=256m VGPU_SWAP_ASYNC_UNMAP=1 -- $SB --buffers 24 --steps 72 --order cyclic
+run FAKE_GPU_EXEC=1 CUDA_DEVICE_SM_LIMIT=30 GPU_CORE_UTILIZATION_POLICY=force CUDA_DEVICE_MEMORY_LIMIT_0=1g -- $P/lib/launch_loop $P/build/vgpu_kernels.cubin 8 2
+if ls $T/tsan.* > /dev/null 2>&1; then echo "TSAN REPORTS:"; head -80 $T/tsan.*; exit 1; fi
+echo "no TSan reports"; rm -rf $T
