@@ -712,6 +712,10 @@ def webhook_handle(review, cfg):
     for idx, ctr in enumerate(containers):
         if ((ctr.get("securityContext") or {}).get("privileged")) is True:
             continue
+        if has_resource:
+            # webhook.go:68: `hasResource = hasResource || val.MutateAdmission(c)` — Go's || short-circuits, so once one
+            # container asked for the resource no later container is mutated (no CUDA_TASK_PRIORITY for it). Kept.
+            continue
         limits = (ctr.get("resources") or {}).get("limits") or {}
         if cfg.ResourcePriority in limits:                       # MutateAdmission (device.go:59-71)
             env = {"name": TASK_PRIORITY_ENV, "value": str(quantity_value(limits[cfg.ResourcePriority]))}

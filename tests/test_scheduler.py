@@ -303,6 +303,12 @@ def test_webhook_mutation():
     assert _patch(S.webhook_handle(_review(p), cfg)) == [
         {"op": "add", "path": "/spec/containers/0/env/-", "value": {"name": "CUDA_TASK_PRIORITY", "value": "0"}},
         {"op": "replace", "path": "/spec/schedulerName", "value": "4pd-scheduler"}]
+    # Go's short-circuit: after the first container that asks for the resource, later containers are not mutated
+    two = _pod("p", [_gpu_ctr("a", priority=1), _gpu_ctr("b", priority=0)])
+    assert _patch(S.webhook_handle(_review(two), cfg))[:-1] == [{"op": "add", "path": "/spec/containers/0/env", "value": [{"name": "CUDA_TASK_PRIORITY", "value": "1"}]}]
+    # ... but a container WITHOUT the resource in front of it is still visited (and gets its priority env)
+    mixed = _pod("p", [{"name": "side", "resources": {"limits": {"vgputaskpriority": "1"}}}, _gpu_ctr("b", priority=0)])
+    assert [op["path"] for op in _patch(S.webhook_handle(_review(mixed), cfg))] == ["/spec/containers/0/env", "/spec/containers/1/env", "/spec/schedulerName"]
     r = S.webhook_handle(_review(_pod("p", [{"name": "nginx"}])), cfg)
     assert r["response"]["allowed"] and "patch" not in r["response"] and r["response"]["status"]["message"] == "no resource found"
     priv = _gpu_ctr("main"); priv["securityContext"] = {"privileged": True}
