@@ -740,13 +740,19 @@ CUresult SwapEngine::page_in_stage(const std::vector<int> &rows) {
         s.out_slot = -1;
     }
     CU_TRY(page_in_plan(rows));
+    size_t staged = 0;
     for (InJob &j : in_jobs_) {
+        // A slot staged here holds data until page_in_finish() has launched its unpack; its `busy` event meanwhile only
+        // says "loaded". So never wrap around onto a slot this admission has already filled — an H2D that completed
+        // quickly would otherwise let job N+ring overwrite job N's staging before it is unpacked.
+        if (staged == ring_in_.size()) break;
         Slot &s = ring_in_[cur_in_];
         if (s.used && d.cuEventQuery(s.busy) != CUDA_SUCCESS) break;   // never block here
         cur_in_ = (cur_in_ + 1) % (int)ring_in_.size();
         s.used = true;
         s.seq++;
         j.slot = &s;
+        staged++;
         CU_TRY(in_issue_copies(j));
     }
     return CUDA_SUCCESS;

@@ -257,3 +257,75 @@ def test_pointer_queries_on_a_paged_out_buffer(tmp_path):
     t2.write_text("Q 5\n")
     bare = run_replay(str(t2), "bare", {"FAKE_GPU_EXEC": "1"}).splitlines()
     assert " rc=1 " in bare[1]
+
+
+_ENGINE_FUZZ = r"""
+import ctypes as C, json, os, random, sys
+sys.path.insert(0, os.environ["VGPU_ROOT"])
+import k8s_device_plugin_b200 as v
+L = v.lib()
+drv = C.CDLL("libcuda.so.1")
+ctx = C.c_void_p(); dev = C.c_int(0)
+assert drv.cuInit(0) == 0 and drv.cuDeviceGet(C.byref(dev), 0) == 0 and drv.cuDevicePrimaryCtxRetain(C.byref(ctx), dev) == 0 and drv.cuCtxSetCurrent(ctx) == 0
+M = 1 << 20
+rng = random.Random(int(os.environ["FUZZ_SEED"]))
+CAP = 48 * M
+sw = v.Swap(dev=0, resident_cap=CAP, chunk_bytes=4 * M)
+live = {}            # id -> [ptr, nbytes, fill index, touches]
+nid = 0
+bad = (C.c_uint64 * 1)(0)
+peak_resident = 0
+ops = {"alloc": 0, "free": 0, "touch": 0, "pair": 0, "verify": 0, "refused": 0}
+def resident():
+    return sum((r.size + 2 * M - 1) // (2 * M) * (2 * M) for r in sw.table() if r.state & 1)
+for step in range(int(os.environ.get("FUZZ_STEPS", "260"))):
+    r = rng.random()
+    if r < 0.22 or len(live) < 3:
+        n = rng.choice([2 * M, 3 * M + 4096, 5 * M + 8, 7 * M, 8 * M + 256 * 3, 12 * M, 16 * M + 64, 20 * M, 2 * M + 8])
+        n -= n % 8
+        try:
+            p = sw.alloc(n)
+        except Exception:
+            ops["refused"] += 1
+            continue
+        sw.acquire([p], 0); L.vgpu_wl_fill(C.c_uint64(p), C.c_uint64(n // 8), C.c_uint64(nid), None); sw.release([p], 0)
+        live[nid] = [p, n, nid, 0]; nid += 1; ops["alloc"] += 1
+    elif r < 0.34:
+        k = rng.choice(list(live)); sw.free(live.pop(k)[0]); ops["free"] += 1
+    elif r < 0.70:
+        k = rng.choice(list(live)); e = live[k]
+        sw.acquire([e[0]], 0); L.vgpu_wl_touch(C.c_uint64(e[0]), C.c_uint64(e[1] // 8), None); sw.release([e[0]], 0); e[3] += 1; ops["touch"] += 1
+    elif r < 0.85 and len(live) >= 2:
+        a, b = rng.sample(list(live), 2)
+        if (live[a][1] + 2 * M - 1) // (2 * M) * 2 * M + (live[b][1] + 2 * M - 1) // (2 * M) * 2 * M <= CAP:
+            ptrs = [live[a][0], live[b][0]]
+            sw.acquire(ptrs, 0)                       # one admission, two operands: neither may evict the other
+            for k in (a, b):
+                L.vgpu_wl_touch(C.c_uint64(live[k][0]), C.c_uint64(live[k][1] // 8), None); live[k][3] += 1
+            sw.release(ptrs, 0); ops["pair"] += 1
+    else:
+        k = rng.choice(list(live)); e = live[k]
+        sw.acquire([e[0]], 0); L.vgpu_wl_verify(C.c_uint64(e[0]), C.c_uint64(e[1] // 8), C.c_uint64(e[2]), C.c_uint64(e[3]), C.c_uint64(C.addressof(bad)), None); sw.release([e[0]], 0)
+        ops["verify"] += 1
+    if step % 10 == 0:
+        peak_resident = max(peak_resident, resident())
+for k, e in live.items():
+    sw.acquire([e[0]], 0); L.vgpu_wl_verify(C.c_uint64(e[0]), C.c_uint64(e[1] // 8), C.c_uint64(e[2]), C.c_uint64(e[3]), C.c_uint64(C.addressof(bad)), None); sw.release([e[0]], 0)
+st = sw.stats()
+print(json.dumps({"bad": int(bad[0]), "peak_resident": peak_resident, "ops": ops, "live": st["live_bytes"], "expect_live": sum(e[1] for e in live.values()),
+                  "entries": st["entries"], "expect_entries": len(live), "faults": st["faults"], "evictions": st["evictions"]}))
+"""
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_engine_fuzz_random_sizes_frees_and_two_operand_admissions(tmp_path, seed):
+    """Randomised integrity test of the engine through the C ABI on the functional fake: ragged sizes (not multiples of
+    the 2 MiB granule or the 4 MiB staging slot), frees in between, single and two-operand admissions, spot checks and a
+    final check of every word of every live buffer; residency never exceeds the cap, bookkeeping matches the model."""
+    env = _env(tmp_path, VGPU_ROOT=ROOT, FUZZ_SEED=seed)
+    r = subprocess.run([sys.executable, "-c", _ENGINE_FUZZ], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["bad"] == 0, out
+    assert out["peak_resident"] <= 48 * M and out["live"] == out["expect_live"] and out["entries"] == out["expect_entries"]
+    assert out["faults"] > 20 and out["evictions"] > 20 and out["ops"]["pair"] > 5 and out["ops"]["free"] > 5
