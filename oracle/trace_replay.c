@@ -20,6 +20,8 @@
  *      " nv_total=.. nv_free=.. nv_used=..")
  *   U ms (sleep until the absolute time <ms since the epoch>: lets several replayers act on one shared schedule)
  *   K (kill(getpid(), SIGKILL): a process that dies without running its exit handler)
+ *   W id byte (cuMemsetD8_v2 of the whole buffer) | O dst src (cuMemcpyDtoD_v2 of min(size)) | V id byte (cuMemcpyDtoH_v2 of
+ *      the whole buffer and a check that every byte equals <byte>; prints " ok=<0|1>") — data ops for the swap path
  *   Q id (cuPointerGetAttributes {MEMORY_TYPE, IS_MANAGED} of pointer id; prints " type=<n> managed=<n>")
  * Output line: "<op#> <opcode> rc=<int> ctx=<u64> mod=<u64> buf=<u64> off=<u64> tot=<u64> [free=.. total=..]"
  * where the five counters are SUMMED over every process slot of device 0 (== own slot for one process).
@@ -59,6 +61,9 @@ extern CUresult cuLaunchKernel(CUfunction, unsigned, unsigned, unsigned, unsigne
 extern CUresult cuModuleLoadData(CUmodule *, const void *) __attribute__((weak));
 extern CUresult cuModuleGetFunction(CUfunction *, CUmodule, const char *) __attribute__((weak));
 extern CUresult cuCtxSynchronize(void);
+extern CUresult cuMemsetD8_v2(CUdeviceptr, unsigned char, size_t);
+extern CUresult cuMemcpyDtoD_v2(CUdeviceptr, CUdeviceptr, size_t);
+extern CUresult cuMemcpyDtoH_v2(void *, CUdeviceptr, size_t);
 /* entry points the reference forwards untouched */
 extern CUresult cuMemAllocAsync(CUdeviceptr *, size_t, CUstream) __attribute__((weak));
 extern CUresult cuMemFreeAsync(CUdeviceptr, CUstream) __attribute__((weak));
@@ -118,6 +123,7 @@ int main(int argc, char **argv) {
     if (!tf) { perror("trace"); return 2; }
     size_t nptr = argc > 2 ? strtoull(argv[2], 0, 0) : (1u << 20);
     CUdeviceptr *ptrs = calloc(nptr, sizeof *ptrs);
+    size_t *sizes = calloc(nptr, sizeof *sizes);
 
     CUdevice dev; CUcontext ctx;
     CUresult r;
@@ -146,10 +152,17 @@ int main(int argc, char **argv) {
         if (line[0] == '#' || line[0] == '\n') continue;
         int n = sscanf(line, " %c %lli %lli %lli", &op, (long long *)&a, (long long *)&b, (long long *)&d);
         if (n < 1) continue;
-        size_t fr = 0, tot = 0; int has_info = 0, has_q = 0, qtype = 0, qman = 0, has_nv = 0;
+        size_t fr = 0, tot = 0; int has_info = 0, has_q = 0, qtype = 0, qman = 0, has_nv = 0, has_v = 0, vok = 0;
         unsigned long long nvmem[3] = {0, 0, 0};     /* nvmlMemory_t {total, free, used} */
         switch (op) {
-        case 'A': ptrs[a] = 0; r = cuMemAlloc_v2(&ptrs[a], (size_t)b); if (r) ptrs[a] = 0; break;
+        case 'A': ptrs[a] = 0; r = cuMemAlloc_v2(&ptrs[a], (size_t)b); if (r) ptrs[a] = 0; else sizes[a] = (size_t)b; break;
+        case 'W': r = ptrs[a] ? cuMemsetD8_v2(ptrs[a], (unsigned char)b, sizes[a]) : 1; break;
+        case 'O': r = (ptrs[a] && ptrs[b]) ? cuMemcpyDtoD_v2(ptrs[a], ptrs[b], sizes[a] < sizes[b] ? sizes[a] : sizes[b]) : 1; break;
+        case 'V': { r = 1; vok = 0; has_v = 1;
+                    if (ptrs[a]) { unsigned char *h = malloc(sizes[a]); r = cuMemcpyDtoH_v2(h, ptrs[a], sizes[a]);
+                        if (!r) { vok = 1; for (size_t i = 0; i < sizes[a]; i++) if (h[i] != (unsigned char)b) { vok = 0; break; } }
+                        free(h); }
+                    break; }
         case 'M': ptrs[a] = 0; r = cuMemAllocManaged(&ptrs[a], (size_t)b, 1); if (r) ptrs[a] = 0; break;
         case 'P': { size_t pitch = 0; ptrs[a] = 0; r = cuMemAllocPitch_v2(&ptrs[a], &pitch, (size_t)b, (size_t)d, 4); if (r) ptrs[a] = 0; break; }
         case 'F': r = cuMemFree_v2(ptrs[a]); if (!r) ptrs[a] = 0; break;
@@ -197,6 +210,7 @@ int main(int argc, char **argv) {
             printf(" free=%zu total=%zu", fr, tot);
         }
         if (has_q) printf(" type=%d managed=%d", qtype, qman);
+        if (has_v) printf(" ok=%d", vok);
         if (op == 'L' && g_region && getenv("TRACE_SHOW_WORDS")) {   /* the monitor handshake words next to a launch */
             int32_t w[3]; memcpy(w, g_region + 0xC473C, 12);
             uint64_t sm; memcpy(&sm, g_region + 0x6B8, 8);

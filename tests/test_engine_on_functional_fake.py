@@ -329,3 +329,39 @@ def test_engine_fuzz_random_sizes_frees_and_two_operand_admissions(tmp_path, see
     assert out["bad"] == 0, out
     assert out["peak_resident"] <= 48 * M and out["live"] == out["expect_live"] and out["entries"] == out["expect_entries"]
     assert out["faults"] > 20 and out["evictions"] > 20 and out["ops"]["pair"] > 5 and out["ops"]["free"] > 5
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+def test_hook_copy_and_fill_family_on_swapped_buffers(tmp_path, seed):
+    """The memcpy / memset intercepts under swap: whole-buffer fills, device-to-device copies between buffers and
+    device-to-host read-backs of buffers that are paged out at the time of the call (a DMA engine cannot fault, the hook
+    pages them in first). 20 buffers of ragged sizes, ~190 MiB live under a 96 MiB quota, every read-back checked."""
+    import random
+    from conftest import run_replay
+    rng = random.Random(seed)
+    sizes = [rng.choice([3 << 20, (5 << 20) + 4096, 9 << 20, (12 << 20) + 256, 17 << 20]) for _ in range(20)]
+    lines = [f"A {i} {n}" for i, n in enumerate(sizes)]
+    val = {}
+    for i in range(20):
+        val[i] = rng.randrange(1, 255); lines.append(f"W {i} {val[i]}")
+    for _ in range(120):
+        r = rng.random()
+        if r < 0.35:
+            i = rng.randrange(20); val[i] = rng.randrange(1, 255); lines.append(f"W {i} {val[i]}")
+        elif r < 0.55:
+            a, b = rng.sample(range(20), 2)
+            if sizes[a] <= sizes[b]:
+                lines.append(f"O {a} {b}"); val[a] = val[b]
+        else:
+            i = rng.randrange(20); lines.append(f"V {i} {val[i]}")
+    for i in range(20):
+        lines.append(f"V {i} {val[i]}")
+    t = tmp_path / "t.txt"
+    t.write_text("\n".join(lines) + "\n")
+    env = {"FAKE_GPU_EXEC": "1", "FAKE_GPU_CTX_MIB": "16", "CUDA_OVERSUBSCRIBE": "true", "CUDA_DEVICE_MEMORY_LIMIT_0": "96m",
+           "CUDA_DEVICE_MEMORY_SHARED_CACHE": str(tmp_path / "c.cache"),
+           "VGPU_SWAP_CHUNK_MB": "4", "VGPU_SWAP_ARENA_GB": "8", "VGPU_SWAP_SLAB_MB": "64", "VGPU_SWAP_SPARE_MB": "16"}
+    out = run_replay(str(t), "new", env).splitlines()
+    assert all(" rc=0 " in l for l in out[1:]), [l for l in out[1:] if " rc=0 " not in l][:3]
+    checks = [l for l in out if " V " in l]
+    assert len(checks) >= 40 and all(l.endswith("ok=1") for l in checks), [l for l in checks if not l.endswith("ok=1")][:3]
