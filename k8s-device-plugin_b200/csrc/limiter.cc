@@ -39,7 +39,7 @@ bool Limiter::enabled_now() const {
     // get_utilization_switch@0x45307: GPU_CORE_UTILIZATION_POLICY force -> on, disable -> off, default -> monitor's word
     if (util_policy_ == 1) return true;
     if (util_policy_ == 2) return false;
-    return !region_ || region_->utilization_switch != 0;
+    return !region_ || __atomic_load_n(&region_->utilization_switch, __ATOMIC_RELAXED) != 0;
 }
 
 bool Limiter::ensure_ring() {
@@ -114,8 +114,10 @@ void Limiter::harvest() {
 void Limiter::before_launch(CUstream st) {
     // monitor handshake first (all modes): a higher-priority task blocks us with recent_kernel = -1
     if (region_) {
-        while (region_->recent_kernel < 0) sleep(1);
-        region_->recent_kernel = 2;
+        // a word shared without a lock with the node monitor and with every thread of every process of the container
+        // (the reference does plain loads/stores on it too): relaxed atomics keep it a defined access
+        while (__atomic_load_n(&region_->recent_kernel, __ATOMIC_RELAXED) < 0) sleep(1);
+        __atomic_store_n(&region_->recent_kernel, 2, __ATOMIC_RELAXED);
     }
     if (!enabled_now()) return;
     std::lock_guard<std::mutex> g(mu_);

@@ -5,6 +5,10 @@
  *   threads <nthreads> <iters>  : every thread allocates and frees through cuMemAlloc_v2 / cuMemAllocAsync /
  *                                 cuMemFree_v2 / cuMemFreeAsync with random sizes; at the end nothing may be left
  *                                 charged (region buffer lane == 0) or allocated in the driver.
+ *   swap <nthreads> <iters>     : (functional fake, CUDA_OVERSUBSCRIBE=true) every thread owns four swappable buffers and
+ *                                 fills / touches / verifies them with kernel launches while the other threads force
+ *                                 evictions: a buffer must stay put from admission until its kernel has run, and every
+ *                                 word must survive its page-outs.
  *   fork                        : parent allocates, forks; the child (new pid, own slot) allocates and exits WITHOUT
  *                                 freeing; the parent then fills its quota — the dead child's bytes must be reclaimed
  *                                 (rm_quitted_process) before the request is refused.
@@ -33,6 +37,10 @@ extern CUresult cuMemAllocAsync(CUdeviceptr *, size_t, CUstream);
 extern CUresult cuMemFreeAsync(CUdeviceptr, CUstream);
 extern CUresult cuMemGetInfo_v2(size_t *, size_t *);
 extern unsigned long long fake_gpu_used_bytes(int) __attribute__((weak));
+extern CUresult cuModuleLoadData(void **, const void *);
+extern CUresult cuModuleGetFunction(void **, void *, const char *);
+extern CUresult cuLaunchKernel(void *, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **, void **);
+extern CUresult cuCtxSynchronize(void);
 
 #define REGION_SIZE 0xC4748
 #define OFF_PROCS 0x738
@@ -83,6 +91,43 @@ static void *worker(void *arg) {
     return NULL;
 }
 
+static void *g_fill, *g_touch, *g_verify;
+static unsigned long long g_bad;
+static void *swap_worker(void *arg) {
+    unsigned id = (unsigned)(uintptr_t)arg, seed = id * 2654435761u + 7;
+    cuCtxSetCurrent(g_ctx);
+    enum { NB = 4 };
+    CUdeviceptr buf[NB]; unsigned long long words[NB], touches[NB], idx[NB];
+    for (int k = 0; k < NB; k++) {
+        size_t n = ((size_t)(6 + rand_r(&seed) % 5) << 20) + (size_t)(rand_r(&seed) % 64) * 4096;
+        if (cuMemAlloc_v2(&buf[k], n)) { __atomic_add_fetch(&g_fail, 1, __ATOMIC_RELAXED); return NULL; }
+        words[k] = n / 8; touches[k] = 0; idx[k] = (unsigned long long)id * 100 + (unsigned)k;
+        void *a[] = {&buf[k], &words[k], &idx[k]};
+        if (cuLaunchKernel(g_fill, 64, 1, 1, 256, 1, 1, 0, NULL, a, NULL)) __atomic_add_fetch(&g_fail, 1, __ATOMIC_RELAXED);
+    }
+    for (int i = 0; i < g_iters; i++) {
+        int k = rand_r(&seed) % NB;
+        if (rand_r(&seed) % 4) {
+            void *a[] = {&buf[k], &words[k]};
+            if (cuLaunchKernel(g_touch, 64, 1, 1, 256, 1, 1, 0, NULL, a, NULL)) __atomic_add_fetch(&g_fail, 1, __ATOMIC_RELAXED);
+            touches[k]++;
+        } else {
+            unsigned long long local = 0, *lp = &local;
+            void *a[] = {&buf[k], &words[k], &idx[k], &touches[k], &lp};
+            if (cuLaunchKernel(g_verify, 64, 1, 1, 256, 1, 1, 0, NULL, a, NULL)) __atomic_add_fetch(&g_fail, 1, __ATOMIC_RELAXED);
+            if (local) __atomic_add_fetch(&g_bad, local, __ATOMIC_RELAXED);
+        }
+    }
+    for (int k = 0; k < NB; k++) {
+        unsigned long long local = 0, *lp = &local;
+        void *a[] = {&buf[k], &words[k], &idx[k], &touches[k], &lp};
+        cuLaunchKernel(g_verify, 64, 1, 1, 256, 1, 1, 0, NULL, a, NULL);
+        if (local) __atomic_add_fetch(&g_bad, local, __ATOMIC_RELAXED);
+        if (cuMemFree_v2(buf[k])) __atomic_add_fetch(&g_fail, 1, __ATOMIC_RELAXED);
+    }
+    return NULL;
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) return 2;
     CUdevice dev;
@@ -97,6 +142,20 @@ int main(int argc, char **argv) {
         lanes(&c, &b, &t, &np);
         printf("{\"mode\": \"threads\", \"free_errors\": %ld, \"ctx\": %lu, \"buf\": %lu, \"tot\": %lu, \"procs\": %d, \"driver_bytes\": %llu}\n",
                g_fail, c, b, t, np, fake_gpu_used_bytes ? fake_gpu_used_bytes(0) : 0ull);
+        return 0;
+    }
+    if (!strcmp(argv[1], "swap")) {
+        int nt = argc > 2 ? atoi(argv[2]) : 4; g_iters = argc > 3 ? atoi(argv[3]) : 200;
+        void *mod;
+        if (cuModuleLoadData(&mod, "x") || cuModuleGetFunction(&g_fill, mod, "vgpu_wl_fill") || cuModuleGetFunction(&g_touch, mod, "vgpu_wl_touch") ||
+            cuModuleGetFunction(&g_verify, mod, "vgpu_wl_verify")) { printf("{\"error\": \"module\"}\n"); return 1; }
+        pthread_t th[64];
+        for (int i = 0; i < nt; i++) pthread_create(&th[i], NULL, swap_worker, (void *)(uintptr_t)(i + 1));
+        for (int i = 0; i < nt; i++) pthread_join(th[i], NULL);
+        cuCtxSynchronize();
+        lanes(&c, &b, &t, &np);
+        printf("{\"mode\": \"swap\", \"errors\": %ld, \"bad_words\": %llu, \"buf\": %lu, \"driver_bytes\": %llu}\n", g_fail, g_bad, b,
+               fake_gpu_used_bytes ? fake_gpu_used_bytes(0) : 0ull);
         return 0;
     }
     if (!strcmp(argv[1], "fork")) {

@@ -25,6 +25,7 @@ run $SW CUDA_DEVICE_MEMORY_LIMIT_0=384m FAKE_GPU_TOTAL_MIB=200 VGPU_SWAP_LIMIT_M
 run CUDA_DEVICE_MEMORY_LIMIT_0=64m -- $R/oracle/_ref/hook_stress threads 8 2000
 run CUDA_DEVICE_MEMORY_LIMIT_0=64m -- $R/oracle/_ref/hook_stress fork
 run FAKE_GPU_EXEC=1 CUDA_DEVICE_SM_LIMIT=30 GPU_CORE_UTILIZATION_POLICY=force -- $P/lib/launch_loop $P/build/vgpu_kernels.cubin 8 2
+run $SW CUDA_DEVICE_MEMORY_LIMIT_0=128m -- $R/oracle/_ref/hook_stress swap 4 120
 python - "$T" <<'PY'
 import os, sys
 sys.path.insert(0, os.path.join(os.getcwd(), "scripts"))
@@ -48,5 +49,6 @@ export TSAN_OPTIONS="halt_on_error=0 log_path=$T/tsan"
 run CUDA_DEVICE_MEMORY_LIMIT_0=64m -- $R/oracle/_ref/hook_stress threads 8 1500
 run $SW CUDA_DEVICE_MEMORY_LIMIT_0=256m VGPU_SWAP_ASYNC_UNMAP=1 -- $SB --buffers 24 --steps 72 --order cyclic
 run FAKE_GPU_EXEC=1 CUDA_DEVICE_SM_LIMIT=30 GPU_CORE_UTILIZATION_POLICY=force CUDA_DEVICE_MEMORY_LIMIT_0=1g -- $P/lib/launch_loop $P/build/vgpu_kernels.cubin 8 2
+run $SW CUDA_DEVICE_MEMORY_LIMIT_0=128m -- $R/oracle/_ref/hook_stress swap 4 80
 if ls $T/tsan.* > /dev/null 2>&1; then echo "TSAN REPORTS:"; head -80 $T/tsan.*; exit 1; fi
 echo "no TSan reports"; rm -rf $T

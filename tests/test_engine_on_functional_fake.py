@@ -365,3 +365,15 @@ def test_hook_copy_and_fill_family_on_swapped_buffers(tmp_path, seed):
     assert all(" rc=0 " in l for l in out[1:]), [l for l in out[1:] if " rc=0 " not in l][:3]
     checks = [l for l in out if " V " in l]
     assert len(checks) >= 40 and all(l.endswith("ok=1") for l in checks), [l for l in checks if not l.endswith("ok=1")][:3]
+
+
+def test_application_threads_share_the_swap_engine(tmp_path):
+    """Six application threads, four swappable buffers each (~200 MiB live under a 128 MiB quota), launching fill / touch /
+    verify kernels concurrently through the hook: a buffer stays pinned from its admission until its kernel has run, no
+    thread's eviction tears another thread's operand away, every word survives."""
+    from conftest import OREF
+    env = _env(tmp_path, LD_PRELOAD=HOOK_SO, CUDA_OVERSUBSCRIBE="true", CUDA_DEVICE_MEMORY_LIMIT_0="128m")
+    r = subprocess.run([os.path.join(OREF, "hook_stress"), "swap", "6", "250"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["errors"] == 0 and out["bad_words"] == 0 and out["buf"] == 0, out
