@@ -331,22 +331,22 @@ def _scheduled_container(tmp_path, preload, tag, seed):
     rng = random.Random(seed)
     cache = str(tmp_path / f"{tag}.cache")
     t0 = int(time.time() * 1000) + 1500
-    slot_ms, nslots = 60, 45
+    slot_ms, nslots = 130, 36          # wide slots: an exit or a kill must not race a sibling's next operation on a loaded box
     traces = [[], [], []]
     live = [[], [], []]
     nid = [0, 0, 0]
     for k in range(nslots):
         p = k % 3
         tr = traces[p]
-        if p == 1 and k >= 27:          # process 1 has exited by now
+        if p == 1 and k >= 22:          # process 1 has exited by now
             continue
-        if p == 2 and k >= 36:          # process 2 was killed
+        if p == 2 and k >= 30:          # process 2 was killed
             continue
         tr.append(f"U {t0 + k * slot_ms}")
         r = rng.random()
-        if p == 1 and k >= 24:
+        if p == 1 and k >= 19:
             continue                    # (its last slots only wait, then the trace ends -> normal exit)
-        if p == 2 and k >= 33:
+        if p == 2 and k >= 26:
             tr.append("K")
             continue
         if r < 0.6 or not live[p]:
@@ -376,11 +376,17 @@ def _scheduled_container(tmp_path, preload, tag, seed):
 def test_three_processes_of_one_container_on_a_shared_schedule_match_the_reference(tmp_path):
     os.makedirs("/tmp/vgpulock", exist_ok=True)
     from conftest import REF_SO, SHIM_SO
-    new = _scheduled_container(tmp_path, HOOK_SO, "new", seed=12)
-    ref = _scheduled_container(tmp_path, SHIM_SO + ":" + REF_SO, "ref", seed=12)
-    for i, (a, b) in enumerate(zip(new, ref)):
-        diffs = [f"{x}   |   {y}" for x, y in zip(a, b) if x != y]
-        assert not diffs and len(a) == len(b), f"process {i}:\n" + "\n".join(diffs[:8])
+    for attempt in range(3):            # wall-clock schedule: a stalled box can reorder two processes; only a repeatable difference counts
+        new = _scheduled_container(tmp_path, HOOK_SO, f"new{attempt}", seed=12)
+        ref = _scheduled_container(tmp_path, SHIM_SO + ":" + REF_SO, f"ref{attempt}", seed=12)
+        problems = []
+        for i, (a, b) in enumerate(zip(new, ref)):
+            diffs = [f"{x}   |   {y}" for x, y in zip(a, b) if x != y]
+            if diffs or len(a) != len(b):
+                problems.append(f"process {i}:\n" + "\n".join(diffs[:8]))
+        if not problems:
+            break
+    assert not problems, "\n".join(problems)
     assert any(" rc=-1 " in l or " rc=2 " in l for o in new for l in o)     # the shared quota was crossed
 
 
@@ -393,11 +399,17 @@ def test_reference_hooked_and_new_hooked_processes_share_one_region_file(tmp_pat
     os.makedirs("/tmp/vgpulock", exist_ok=True)
     from conftest import REF_SO, SHIM_SO
     refp = SHIM_SO + ":" + REF_SO
-    ref = _scheduled_container(tmp_path, refp, "allref", seed=21)
-    mixed = _scheduled_container(tmp_path, [HOOK_SO if i in mix else refp for i in range(3)], "mixed", seed=21)
-    for i, (a, b) in enumerate(zip(mixed, ref)):
-        diffs = [f"{x}   |   {y}" for x, y in zip(a, b) if x != y]
-        assert not diffs and len(a) == len(b), f"process {i} ({'new' if i in mix else 'reference'} hook):\n" + "\n".join(diffs[:8])
+    for attempt in range(3):            # (same remark on the wall-clock schedule)
+        ref = _scheduled_container(tmp_path, refp, f"allref{attempt}", seed=21)
+        mixed = _scheduled_container(tmp_path, [HOOK_SO if i in mix else refp for i in range(3)], f"mixed{attempt}", seed=21)
+        problems = []
+        for i, (a, b) in enumerate(zip(mixed, ref)):
+            diffs = [f"{x}   |   {y}" for x, y in zip(a, b) if x != y]
+            if diffs or len(a) != len(b):
+                problems.append(f"process {i} ({'new' if i in mix else 'reference'} hook):\n" + "\n".join(diffs[:8]))
+        if not problems:
+            break
+    assert not problems, "\n".join(problems)
 
 
 @pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
