@@ -421,8 +421,11 @@ CUresult SwapEngine::map_row(int row) {
         // reference leaves this case to UVM, which pages between processes). Live within what we have: lower the working
         // cap to what is mapped now and make the room out of our own least recently used rows.
         const uint64_t need = side_[row].mapped;
-        const uint64_t held = resident_mapped_ + evicting_mapped_;
+        uint64_t held = resident_mapped_ + evicting_mapped_;
         if (held < need) break;                        // nothing of ours left to give up
+        // what the device can still give on top of what we hold (the pool was already released by get_phys)
+        size_t fr = 0, tot = 0;
+        if (d.cuMemGetInfo_v2(&fr, &tot) == CUDA_SUCCESS) held += (uint64_t)fr / gran_ * gran_;
         if (!pressure_ || cfg_.resident_cap > held) {
             if (!pressure_) {
                 quota_cap_ = std::max(quota_cap_, cfg_.resident_cap);

@@ -297,7 +297,7 @@ for step in range(int(os.environ.get("FUZZ_STEPS", "260"))):
         sw.acquire([e[0]], 0); L.vgpu_wl_touch(C.c_uint64(e[0]), C.c_uint64(e[1] // 8), None); sw.release([e[0]], 0); e[3] += 1; ops["touch"] += 1
     elif r < 0.85 and len(live) >= 2:
         a, b = rng.sample(list(live), 2)
-        if (live[a][1] + 2 * M - 1) // (2 * M) * 2 * M + (live[b][1] + 2 * M - 1) // (2 * M) * 2 * M <= CAP:
+        if (live[a][1] + 2 * M - 1) // (2 * M) * 2 * M + (live[b][1] + 2 * M - 1) // (2 * M) * 2 * M <= int(os.environ.get("FUZZ_PAIR_CAP", CAP)):
             ptrs = [live[a][0], live[b][0]]
             sw.acquire(ptrs, 0)                       # one admission, two operands: neither may evict the other
             for k in (a, b):
@@ -315,6 +315,18 @@ st = sw.stats()
 print(json.dumps({"bad": int(bad[0]), "peak_resident": peak_resident, "ops": ops, "live": st["live_bytes"], "expect_live": sum(e[1] for e in live.values()),
                   "entries": st["entries"], "expect_entries": len(live), "faults": st["faults"], "evictions": st["evictions"]}))
 """
+
+
+@pytest.mark.parametrize("seed", [21, 22])
+def test_engine_fuzz_on_a_device_that_gives_less_than_the_cap(tmp_path, seed):
+    """The same fuzz with a 48 MiB cap on a device that can only give ~42 MiB next to the staging rings: the engine
+    settles on what the device gives (cuMemCreate OOM -> working cap = held + free), keeps every word intact."""
+    env = _env(tmp_path, VGPU_ROOT=ROOT, FUZZ_SEED=seed, FAKE_GPU_TOTAL_MIB=76, FUZZ_PAIR_CAP=30 * M, FUZZ_STEPS=200, LIBCUDA_LOG_LEVEL=2)
+    r = subprocess.run([sys.executable, "-c", _ENGINE_FUZZ], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["bad"] == 0 and out["live"] == out["expect_live"] and out["peak_resident"] <= 44 * M, out
+    assert "physical memory exhausted below the quota" in r.stderr
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3, 4])
