@@ -96,9 +96,12 @@ for rnd in range(3):
     for b in bufs:
         b.add_(1)
 torch.cuda.synchronize()
-# (no whole-buffer reductions here: b.sum(dtype=int64) materialises a 12 GiB int64 copy, and a single buffer larger than
-# the resident cap can never be admitted — the engine refuses it with CUDA_ERROR_OUT_OF_MEMORY, as it must)
-ok = all(int(b[0].item()) == i + 3 and int(b[-1].item()) == i + 3 and int(b[b.numel() // 2].item()) == i + 3 for i, b in enumerate(bufs))
+# every byte of every buffer, 256 MiB at a time (a whole-buffer reduction like b.sum(dtype=int64) would materialise a
+# 12 GiB copy, and a single buffer larger than the resident cap can never be admitted — the engine refuses it with
+# CUDA_ERROR_OUT_OF_MEMORY, as it must). Each buffer is 48 staging chunks: far more than the ring has slots.
+def whole(b, val, step=256 << 20):
+    return all(bool((b[lo:lo + step] == val).all().item()) for lo in range(0, b.numel(), step))
+ok = all(int(b[0].item()) == i + 3 and int(b[-1].item()) == i + 3 and whole(b, i + 3) for i, b in enumerate(bufs))
 free, total = torch.cuda.mem_get_info()
 print(json.dumps({"ok": ok, "total": total}))
 """
