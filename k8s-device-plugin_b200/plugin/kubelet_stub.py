@@ -63,3 +63,18 @@ class KubeletStub:
             for ids in device_ids_per_container:
                 req.container_requests.add(devices_ids=list(ids))
             return call(req, timeout=timeout)
+
+    def _unary(self, method, req, resp_cls, timeout=5):
+        with self._channel() as ch:
+            return ch.unary_unary(method, request_serializer=lambda m: m.SerializeToString(), response_deserializer=resp_cls.FromString)(req, timeout=timeout)
+
+    def options(self):
+        return self._unary(api.M_OPTIONS, api.Empty(), api.DevicePluginOptions)
+
+    def preferred_allocation(self, available, must_include, size):
+        req = api.PreferredAllocationRequest()
+        req.container_requests.add(available_deviceIDs=list(available), must_include_deviceIDs=list(must_include), allocation_size=size)
+        return self._unary(api.M_PREFERRED, req, api.PreferredAllocationResponse)
+
+    def pre_start(self, ids):
+        return self._unary(api.M_PRESTART, api.PreStartContainerRequest(devices_ids=list(ids)), api.PreStartContainerResponse)

@@ -126,7 +126,7 @@ class NvidiaDevicePlugin:
 
     # ---- gRPC service methods
     def GetDevicePluginOptions(self, request, context):
-        return api.DevicePluginOptions(get_preferred_allocation_available=False)
+        return api.DevicePluginOptions(get_preferred_allocation_available=True)
 
     def ListAndWatch(self, request, context):                 # server.go:253-267
         yield api.ListAndWatchResponse(devices=self.plugin_devices())

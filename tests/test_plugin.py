@@ -131,6 +131,17 @@ def test_kubelet_stub_round_trip(cluster, tmp_path):
     print("round trip ms:", (time.perf_counter() - t0) * 1e3)
 
 
+def test_the_other_kubelet_calls_answer_like_the_reference(cluster):
+    """server.go:245-250 (options: preferred allocation advertised), :270-288 (the answer is nonetheless empty: the body is
+    commented out upstream), :501-503 (PreStartContainer: empty)."""
+    kubelet, plugin, pods, pod = cluster
+    o = kubelet.options()
+    assert o.get_preferred_allocation_available is True and o.pre_start_required is False
+    r = kubelet.preferred_allocation([f"GPU-fake-0-{i}" for i in range(4)], ["GPU-fake-0-1"], 2)
+    assert len(r.container_responses) == 0
+    assert kubelet.pre_start(["GPU-fake-0-1"]).SerializeToString() == b""
+
+
 def test_allocate_failure_paths(cluster):
     kubelet, plugin, pods, pod = cluster
     import grpc
