@@ -279,23 +279,20 @@ VGPU_EXPORT CUresult cuMemsetD2D32Async(CUdeviceptr dst, size_t pitch, unsigned 
 }
 #undef DEVPTR_IF
 
-// Pointer queries. The reference post-processes cuPointerGetAttributes@0x33187 because its swap switch turns every
-// large allocation into managed memory: MEMORY_TYPE := check_memory_type(ptr), IS_MANAGED := 0. Here swappable buffers
-// are VMM mappings — device memory to the driver — but a PAGED-OUT buffer has no mapping at all and the driver would
-// answer INVALID_VALUE, so the buffer is made resident first. The reference's overrides are applied to tracked pointers
-// only: its check_memory_type answers HOST for every pointer it did not hand out (VMM ranges mapped by the application,
-// IPC imports), which is wrong for those.
-static void fix_pointer_attribute(CUpointer_attribute a, void *data, CUdeviceptr ptr) {
-    if (!data || Runtime::get().check_memory_type(ptr) != 2) return;
-    if (a == CU_POINTER_ATTRIBUTE_MEMORY_TYPE) *static_cast<unsigned int *>(data) = CU_MEMORYTYPE_DEVICE;
-    else if (a == CU_POINTER_ATTRIBUTE_IS_MANAGED) *static_cast<unsigned int *>(data) = 0;
-}
+// Pointer queries. A PAGED-OUT swappable buffer has no mapping at all and the driver would answer INVALID_VALUE, so the
+// buffer is made resident first; resident or not, it is a VMM mapping — plain device memory to the driver — and the
+// driver's answers are passed on as they are.
+// The reference post-processes the plural call only (cuPointerGetAttributes@0x33187; the singular @0x32f8c forwards):
+// because its swap switch turns large allocations into managed memory behind the application's back, it writes 0 over
+// every CU_POINTER_ATTRIBUTE_IS_MANAGED answer — for every pointer, the application's own cuMemAllocManaged memory
+// included (run against the binary: type=3 managed=0) — and leaves MEMORY_TYPE alone (check_memory_type@0x407f2 is only
+// called for its debug log, @0x333aa-0x33447). Nothing is hidden behind managed memory here, so the blanket override
+// is not needed and would only mislead cudaMemPrefetchAsync-style callers; VGPU_REFERENCE_COVERAGE=1 restores it.
 VGPU_EXPORT CUresult cuPointerGetAttribute(void *data, CUpointer_attribute attribute, CUdeviceptr ptr) {
     if (!drv().cuPointerGetAttribute) return CUDA_ERROR_NOT_SUPPORTED;
     TOUCH1(ptr, 1, nullptr);
     CUresult r = drv().cuPointerGetAttribute(data, attribute, ptr);
     TOUCH_DONE(nullptr);
-    if (r == CUDA_SUCCESS) fix_pointer_attribute(attribute, data, ptr);
     return r;
 }
 VGPU_EXPORT CUresult cuPointerGetAttributes(unsigned int numAttributes, CUpointer_attribute *attributes, void **data, CUdeviceptr ptr) {
@@ -303,8 +300,9 @@ VGPU_EXPORT CUresult cuPointerGetAttributes(unsigned int numAttributes, CUpointe
     TOUCH1(ptr, 1, nullptr);
     CUresult r = drv().cuPointerGetAttributes(numAttributes, attributes, data, ptr);
     TOUCH_DONE(nullptr);
-    if (r == CUDA_SUCCESS && attributes && data)
-        for (unsigned int i = 0; i < numAttributes; i++) fix_pointer_attribute(attributes[i], data[i], ptr);
+    if (attributes && data && Runtime::get().reference_coverage_mode())
+        for (unsigned int i = 0; i < numAttributes; i++)
+            if (attributes[i] == CU_POINTER_ATTRIBUTE_IS_MANAGED && data[i]) *static_cast<unsigned int *>(data[i]) = 0;
     return r;
 }
 

@@ -342,6 +342,8 @@ bool Runtime::track(CUdeviceptr base, size_t size, int dev, AllocKind kind) {
     return true;
 }
 
+bool Runtime::reference_coverage_mode() const { return reference_coverage(); }
+
 int Runtime::check_memory_type(CUdeviceptr p) {
     std::lock_guard<std::mutex> g(table_mu_);
     auto it = table_.upper_bound(p);

@@ -99,6 +99,7 @@ class Runtime {
     // ---- introspection (C-ABI, tests)
     Region *region() { return region_.get(); }
     const Config &config() const { return cfg_; }
+    bool reference_coverage_mode() const;
     int check_memory_type(CUdeviceptr p);   // 2 = tracked device memory, 1 = not (check_memory_type@0x407f2)
     size_t table_size();
     uint64_t context_size() const { return context_size_; }

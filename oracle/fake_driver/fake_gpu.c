@@ -137,9 +137,26 @@ static CUresult do_alloc(CUdeviceptr *dptr, size_t size) {
     return r;
 }
 
+/* managed allocations are remembered so that pointer queries can tell them apart, like the real driver does */
+static struct { CUdeviceptr base; size_t size; } g_managed[256];
+static int g_nmanaged;
+static int is_managed(CUdeviceptr p) {
+    int hit = 0;
+    pthread_mutex_lock(&g_mu);
+    for (int i = 0; i < g_nmanaged; i++) if (p >= g_managed[i].base && p < g_managed[i].base + g_managed[i].size) hit = 1;
+    pthread_mutex_unlock(&g_mu);
+    return hit;
+}
+static void forget_managed(CUdeviceptr p) {
+    pthread_mutex_lock(&g_mu);
+    for (int i = 0; i < g_nmanaged; i++) if (g_managed[i].base == p) { g_managed[i] = g_managed[--g_nmanaged]; break; }
+    pthread_mutex_unlock(&g_mu);
+}
+
 static CUresult do_free(CUdeviceptr p) {
     fake_init();
     if (!p) return CUDA_SUCCESS;
+    forget_managed(p);
     if (g_exec) return fx_free(p);
     return fake_untrack(p, NULL);
 }
@@ -198,7 +215,12 @@ EXPORT CUresult cuCtxSynchronize(void) { return CUDA_SUCCESS; }
 EXPORT CUresult cuCtxGetApiVersion(CUcontext c, unsigned *v) { (void)c; *v = 12090; return CUDA_SUCCESS; }
 
 EXPORT CUresult cuMemAlloc_v2(CUdeviceptr *p, size_t n) { return do_alloc(p, n); }
-EXPORT CUresult cuMemAllocManaged(CUdeviceptr *p, size_t n, unsigned flags) { (void)flags; return do_alloc(p, n); }
+EXPORT CUresult cuMemAllocManaged(CUdeviceptr *p, size_t n, unsigned flags) {
+    (void)flags;
+    CUresult r = do_alloc(p, n);
+    if (!r) { pthread_mutex_lock(&g_mu); if (g_nmanaged < 256) { g_managed[g_nmanaged].base = *p; g_managed[g_nmanaged].size = n; g_nmanaged++; } pthread_mutex_unlock(&g_mu); }
+    return r;
+}
 EXPORT CUresult cuMemAllocPitch_v2(CUdeviceptr *p, size_t *pitch, size_t w, size_t h, unsigned elem) {
     (void)elem; size_t pt = (w + 511) & ~(size_t)511; if (pitch) *pitch = pt; return do_alloc(p, pt * h);
 }
@@ -288,9 +310,9 @@ static CUresult pointer_attr(int attr, void *data, CUdeviceptr p) {
     if (!(fake_is_tracked(p) || (fake_exec_on() && fx_is_mapped(p)))) return CUDA_ERROR_INVALID_VALUE;
     if (!data) return CUDA_SUCCESS;
     switch (attr) {
-    case 2: *(unsigned *)data = 2; break;                    /* MEMORY_TYPE = DEVICE */
+    case 2: *(unsigned *)data = is_managed(p) ? 3 : 2; break; /* MEMORY_TYPE = DEVICE, UNIFIED for managed memory */
     case 3: *(CUdeviceptr *)data = p; break;                 /* DEVICE_POINTER */
-    case 8: *(unsigned *)data = 0; break;                    /* IS_MANAGED */
+    case 8: *(unsigned *)data = (unsigned)is_managed(p); break; /* IS_MANAGED */
     case 9: *(int *)data = cur_dev() < 0 ? 0 : cur_dev(); break;   /* DEVICE_ORDINAL */
     default: memset(data, 0, 4); break;
     }

@@ -241,8 +241,8 @@ def test_virtual_limit_mode_pages_only_under_physical_pressure(tmp_path):
 
 def test_pointer_queries_on_a_paged_out_buffer(tmp_path):
     """A paged-out swappable buffer has no mapping, and the driver answers pointer queries on it with INVALID_VALUE; the
-    hook pages it in first. Tracked pointers report device memory and not-managed, like the reference's post-processing
-    of cuPointerGetAttributes@0x33187."""
+    hook pages it in first and passes the driver's answer on (a swappable buffer is a VMM mapping: device memory, not
+    managed)."""
     from conftest import run_replay
     t = tmp_path / "t.txt"
     t.write_text("A 0 %d\nA 1 %d\nA 2 %d\nQ 0\nQ 2\nA 3 4096\nQ 3\n" % (48 * M, 48 * M, 48 * M))

@@ -179,6 +179,25 @@ def test_stream_ordered_and_vmm_allocations_are_charged(tmp_path):
     assert f(out[14], "tot") == 16 * M
 
 
+@pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
+def test_pointer_queries_match_the_reference_binary(tmp_path):
+    """cuPointerGetAttributes@0x33187 writes 0 over every IS_MANAGED answer (the application's own managed memory
+    included) and leaves MEMORY_TYPE alone. The product passes the driver's answers on; VGPU_REFERENCE_COVERAGE=1
+    reproduces the reference."""
+    t = tmp_path / "t.txt"
+    t.write_text("M 0 8388608\nA 1 8388608\nQ 0\nQ 1\n")
+    def q(mode, extra=None):
+        env = {"CUDA_DEVICE_MEMORY_LIMIT_0": "1g", "CUDA_DEVICE_MEMORY_SHARED_CACHE": str(tmp_path / f"{mode}{len(extra or {})}.cache")}
+        env.update(extra or {})
+        return [l for l in run_replay(str(t), mode, env).splitlines() if " Q " in l]
+    ref = q("reference")
+    assert ref[0].endswith("type=3 managed=0") and ref[1].endswith("type=2 managed=0")
+    assert q("new", {"VGPU_REFERENCE_COVERAGE": "1"}) == ref
+    new = q("new")
+    assert new[0].endswith("type=3 managed=1") and new[1] == ref[1]               # the driver's own answer for managed memory
+    assert [l.split(" type=")[0] for l in new] == [l.split(" type=")[0] for l in ref]   # accounting identical either way
+
+
 def test_reference_coverage_switch_restores_the_reference_blind_spots(tmp_path):
     t = _write(tmp_path, _WIDE_TRACE)
     env = _env(tmp_path, "64m", FAKE_GPU_CTX_MIB="16", VGPU_REFERENCE_COVERAGE="1")
