@@ -602,22 +602,31 @@ CUresult Runtime::device_total_mem(size_t *bytes, CUdevice dev) {
     return CUDA_SUCCESS;
 }
 
+// Context accounting. The reference virtualises contexts (context.c: one `vdevices` record per device, filled by whichever
+// of cuDevicePrimaryCtxRetain@0x28c55 / cuCtxCreate_v2@0x29c75 / cuCtxSetCurrent@0x2afa4 reaches the device first) and
+// adds context_size as type 0 when it fills the record — so ONCE PER DEVICE per process, however the context came to be
+// and however many more are created ("Duplicate cuCtxCreate, this may indicate errors", context.c:144) or destroyed and
+// re-created; nothing is ever given back. Checked against the binary: tests/test_hook_parity_cpu.py
+// test_context_accounting_is_once_per_device.
+void Runtime::charge_context_once(CUdevice dev) {
+    if (!region_ || dev < 0 || dev >= VGPU_MAX_DEVICES) return;
+    std::lock_guard<std::mutex> g(ctx_mu_);
+    if (ctx_charged_[dev]) return;
+    ctx_charged_[dev] = true;
+    if (context_size_) region_->add(pid_, dev, context_size_, VGPU_MEM_CONTEXT);
+}
+
 CUresult Runtime::primary_ctx_retain(CUcontext *ctx, CUdevice dev) {
     ensure_initialized();
     CUresult r = drv().cuDevicePrimaryCtxRetain(ctx, dev);
-    if (r == CUDA_SUCCESS && region_ && dev >= 0 && dev < VGPU_MAX_DEVICES && !ctx_charged_[dev]) {
-        // cuDevicePrimaryCtxRetain (context.c:L72-86): add_gpu_device_memory_usage(pid, dev, context_size, 0)
-        ctx_charged_[dev] = true;
-        if (context_size_) region_->add(pid_, dev, context_size_, VGPU_MEM_CONTEXT);
-    }
+    if (r == CUDA_SUCCESS) charge_context_once(dev);
     return r;
 }
 
 CUresult Runtime::ctx_create(CUcontext *ctx, unsigned flags, CUdevice dev) {
     ensure_initialized();
     CUresult r = drv().cuCtxCreate_v2(ctx, flags, dev);
-    if (r == CUDA_SUCCESS && region_ && dev >= 0 && dev < VGPU_MAX_DEVICES && context_size_)
-        region_->add(pid_, dev, context_size_, VGPU_MEM_CONTEXT);   // cuCtxCreate_v2@0x29c75: once per created context
+    if (r == CUDA_SUCCESS) charge_context_once(dev);
     return r;
 }
 

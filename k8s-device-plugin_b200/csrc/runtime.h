@@ -128,7 +128,9 @@ class Runtime {
     int32_t pid_ = 0;
     uint64_t context_size_ = 0;
     bool pid_found_ = false;
-    bool ctx_charged_[VGPU_MAX_DEVICES] = {};
+    bool ctx_charged_[VGPU_MAX_DEVICES] = {};     // context_size added to this device's lane (once per device, see charge_context_once)
+    std::mutex ctx_mu_;
+    void charge_context_once(CUdevice dev);
 
     std::mutex table_mu_;                   // the reference's single allocator mutex (mutex@0x61180)
     std::map<CUdeviceptr, Alloc> table_;    // base -> alloc; ordered for range classification

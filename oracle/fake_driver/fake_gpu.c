@@ -41,7 +41,12 @@ static uint64_t g_total = 183359ull << 20, g_ctx_bytes = 512ull << 20;
 static unsigned g_sm_util;
 static uint64_t g_used[MAXDEV];
 static int g_ctx_refs[MAXDEV];
-static int g_ctx_obj[MAXDEV]; /* address of g_ctx_obj[d] is the CUcontext of device d */
+/* contexts: &g_ctx_obj[d] is the primary context of device d; &g_ctx_obj[MAXDEV + k] is the k-th context made by
+ * cuCtxCreate_v2, whose device is g_ctx_dev[k] (distinct handles, as on the real driver) */
+#define MAXCREATED 64
+static int g_ctx_obj[MAXDEV + MAXCREATED];
+static int g_ctx_dev[MAXCREATED];
+static int g_ncreated;
 static __thread CUcontext t_cur;
 static uint64_t g_next_va = 0x7f4000000000ull;
 static uint64_t g_launches;
@@ -68,7 +73,9 @@ static void fake_init(void) {
 
 static int cur_dev(void) {
     if (!t_cur) return -1;
-    return (int)((int *)t_cur - g_ctx_obj);
+    int i = (int)((int *)t_cur - g_ctx_obj);
+    if (i < 0 || i >= MAXDEV + MAXCREATED) return -1;
+    return i < MAXDEV ? i : g_ctx_dev[i - MAXDEV];
 }
 
 static unsigned hslot(uint64_t base) { return (unsigned)((base >> 9) * 0x9E3779B97F4A7C15ull >> 44) & (HCAP - 1); }
@@ -204,7 +211,20 @@ EXPORT CUresult cuDevicePrimaryCtxRelease(CUdevice d) { return cuDevicePrimaryCt
 EXPORT CUresult cuDevicePrimaryCtxGetState(CUdevice d, unsigned *flags, int *active) { if (flags) *flags = 0; if (active) *active = g_ctx_refs[d] > 0; return CUDA_SUCCESS; }
 EXPORT CUresult cuDevicePrimaryCtxSetFlags_v2(CUdevice d, unsigned f) { (void)d; (void)f; return CUDA_SUCCESS; }
 EXPORT CUresult cuDevicePrimaryCtxReset_v2(CUdevice d) { (void)d; return CUDA_SUCCESS; }
-EXPORT CUresult cuCtxCreate_v2(CUcontext *ctx, unsigned flags, CUdevice d) { (void)flags; CUresult r = cuDevicePrimaryCtxRetain(ctx, d); if (!r) t_cur = *ctx; return r; }
+EXPORT CUresult cuCtxCreate_v2(CUcontext *ctx, unsigned flags, CUdevice d) {
+    (void)flags;
+    fake_init();
+    if (d < 0 || d >= g_ndev) return CUDA_ERROR_INVALID_DEVICE;
+    pthread_mutex_lock(&g_mu);
+    int k = g_ncreated < MAXCREATED ? g_ncreated++ : -1;
+    if (k >= 0) g_ctx_dev[k] = d;
+    pthread_mutex_unlock(&g_mu);
+    if (k < 0) return CUDA_ERROR_OUT_OF_MEMORY;
+    *ctx = &g_ctx_obj[MAXDEV + k];
+    t_cur = *ctx;
+    LOGF("ctx create dev %d -> #%d", d, k);
+    return CUDA_SUCCESS;
+}
 EXPORT CUresult cuCtxDestroy_v2(CUcontext ctx) { (void)ctx; return CUDA_SUCCESS; }
 EXPORT CUresult cuCtxSetCurrent(CUcontext ctx) { t_cur = ctx; return CUDA_SUCCESS; }
 EXPORT CUresult cuCtxGetCurrent(CUcontext *ctx) { *ctx = t_cur; return CUDA_SUCCESS; }

@@ -51,6 +51,9 @@ extern CUresult cuInit(unsigned);
 extern CUresult cuDeviceGet(CUdevice *, int);
 extern CUresult cuDevicePrimaryCtxRetain(CUcontext *, CUdevice);
 extern CUresult cuCtxSetCurrent(CUcontext);
+extern CUresult cuCtxCreate_v2(CUcontext *, unsigned, CUdevice);
+extern CUresult cuCtxDestroy_v2(CUcontext);
+extern CUresult cuCtxGetDevice(CUdevice *);
 extern CUresult cuMemAlloc_v2(CUdeviceptr *, size_t);
 extern CUresult cuMemAllocManaged(CUdeviceptr *, size_t, unsigned);
 extern CUresult cuMemAllocPitch_v2(CUdeviceptr *, size_t *, size_t, size_t, unsigned);
@@ -147,6 +150,7 @@ int main(int argc, char **argv) {
     unsigned long opn = 0;
     int cur = 0;                       /* device whose lane is reported */
     CUcontext ctxs[16] = {ctx};
+    CUcontext uctx[16] = {0}; int udev[16] = {0};   /* contexts made with cuCtxCreate_v2 (ops E H e) */
     while (fgets(line, sizeof line, tf)) {
         char op; unsigned long long a = 0, b = 0, d = 0;
         if (line[0] == '#' || line[0] == '\n') continue;
@@ -181,6 +185,14 @@ int main(int argc, char **argv) {
                     if (!r) r = cuCtxSetCurrent(ctxs[n2]);
                     if (!r) { cur = n2; dev = d2; }
                     break; }
+        /* context family: B n = retain device n's primary context once more; E s n = cuCtxCreate_v2 on device n into
+         * slot s (becomes current); H s = make slot s current; e s = destroy slot s */
+        case 'B': { CUcontext t = NULL; CUdevice d2; r = cuDeviceGet(&d2, (int)a & 15); if (!r) r = cuDevicePrimaryCtxRetain(&t, d2);
+                    if (!r && !ctxs[a & 15]) ctxs[a & 15] = t; break; }
+        case 'E': { CUdevice d2; r = cuDeviceGet(&d2, (int)b & 15); if (!r) r = cuCtxCreate_v2(&uctx[a & 15], 0, d2);
+                    if (!r) { udev[a & 15] = (int)b & 15; cur = (int)b & 15; dev = d2; } break; }
+        case 'H': r = uctx[a & 15] ? cuCtxSetCurrent(uctx[a & 15]) : 1; if (!r) { cur = udev[a & 15]; dev = cur; } break;
+        case 'e': r = uctx[a & 15] ? cuCtxDestroy_v2(uctx[a & 15]) : 1; if (!r) uctx[a & 15] = NULL; break;
         case 'Y': ptrs[a] = 0; r = cuMemAllocAsync ? cuMemAllocAsync(&ptrs[a], (size_t)b, NULL) : 801; if (r) ptrs[a] = 0; break;
         case 'Z': r = cuMemFreeAsync ? cuMemFreeAsync(ptrs[a], NULL) : 801; if (!r) ptrs[a] = 0; break;
         case 'C': { struct mem_prop pr; memset(&pr, 0, sizeof pr); pr.type = 1 /* PINNED */; pr.location.type = 1 /* DEVICE */; pr.location.id = 0;

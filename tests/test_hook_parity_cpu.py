@@ -296,6 +296,44 @@ def test_nvml_memory_view_matches_the_reference(tmp_path, limit):
 
 
 @pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_context_accounting_is_once_per_device(tmp_path, seed):
+    """context.c: the context size is charged when a device gets its first context — by cuDevicePrimaryCtxRetain or by
+    cuCtxCreate_v2, whichever comes first — and never again: not for further cuCtxCreate_v2 calls ("Duplicate
+    cuCtxCreate"), not for more retains, not after a destroy + re-create. Seed 0 is a fixed tour, the others are random
+    mixes of retains, creates, destroys, device switches and allocations on three GPUs; every counter word after every
+    op equals the reference binary's. (cuCtxSetCurrent on a context made by a duplicate cuCtxCreate is left out: the
+    reference exit()s there, context.c:242.)"""
+    import random
+    if seed == 0:
+        lines = "A 0 1048576\nB 0\nB 0\nE 0 0\nA 1 1048576\nE 1 0\nE 2 1\nA 2 1048576\nD 1\nA 3 1048576\nB 1\nD 0\ne 1\nF 0\nI\nE 3 2\ne 3\nE 3 2\nA 4 4096\nD 2\nI".split("\n")
+    else:
+        rng = random.Random(seed)
+        lines, nid, made = [], 0, set()
+        for _ in range(150):
+            r = rng.random()
+            if r < 0.15:
+                lines.append(f"B {rng.randrange(3)}")
+            elif r < 0.35:
+                slot = rng.randrange(8); made.add(slot); lines.append(f"E {slot} {rng.randrange(3)}")
+            elif r < 0.45 and made:
+                slot = rng.choice(sorted(made)); made.discard(slot); lines.append(f"e {slot}")
+            elif r < 0.60:
+                lines.append(f"D {rng.randrange(3)}")
+            elif r < 0.90:
+                lines.append(f"A {nid} {rng.choice([4096, 1 << 20, 9 << 20])}"); nid += 1
+            else:
+                lines.append("I")
+    t = _write(tmp_path, "\n".join(lines) + "\n")
+    env = _env(tmp_path, None, CUDA_DEVICE_MEMORY_LIMIT="1g", FAKE_GPU_COUNT="3", FAKE_GPU_CTX_MIB="100")
+    new = run_replay(t, "new", env).splitlines()
+    ref = run_replay(t, "reference", dict(env, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "ref.cache"))).splitlines()
+    diffs = [f"{a}   |   {b}" for a, b in zip(new, ref) if a != b]
+    assert not diffs and len(new) == len(ref) == len(lines) + 1, "\n".join(diffs[:10])
+    assert any(" ctx=104857600 " in l for l in new) and not any(" ctx=209715200 " in l for l in new)
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_random_multi_device_traces_match_the_reference_binary(tmp_path, seed):
     """Randomised differential test on a three-GPU container: device switches, the four allocation families, frees of
