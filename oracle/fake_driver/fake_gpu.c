@@ -322,8 +322,15 @@ EXPORT CUresult cuMemsetD16Async(CUdeviceptr d, unsigned short v, size_t n, CUst
 EXPORT CUresult cuMemsetD32_v2(CUdeviceptr d, unsigned v, size_t n) { FX_ONLY(for (size_t i = 0; i < n; i++) ((unsigned *)(uintptr_t)d)[i] = v); }
 EXPORT CUresult cuMemsetD32Async(CUdeviceptr d, unsigned v, size_t n, CUstream st) { (void)st; return cuMemsetD32_v2(d, v, n); }
 EXPORT CUresult cuMemHostGetDevicePointer_v2(CUdeviceptr *d, void *h, unsigned f) { (void)f; *d = (CUdeviceptr)(uintptr_t)h; return CUDA_SUCCESS; }
+static int g_host_unregisters;
 EXPORT CUresult cuMemHostRegister_v2(void *p, size_t n, unsigned f) { (void)p; (void)n; (void)f; return CUDA_SUCCESS; }
-EXPORT CUresult cuMemHostUnregister(void *p) { (void)p; return CUDA_SUCCESS; }
+EXPORT CUresult cuMemHostUnregister(void *p) { (void)p; __atomic_add_fetch(&g_host_unregisters, 1, __ATOMIC_RELAXED); return CUDA_SUCCESS; }
+static int g_mipmaps;
+EXPORT CUresult cuMipmappedArrayCreate(void **h, const void *desc, unsigned levels) { (void)desc; (void)levels; *h = malloc(16); __atomic_add_fetch(&g_mipmaps, 1, __ATOMIC_RELAXED); return CUDA_SUCCESS; }
+EXPORT CUresult cuMipmappedArrayDestroy(void *h) { free(h); __atomic_sub_fetch(&g_mipmaps, 1, __ATOMIC_RELAXED); return CUDA_SUCCESS; }
+/* test introspection: what is still registered / alive on the "driver" side */
+EXPORT int fake_live_mipmaps(void) { return g_mipmaps; }
+EXPORT int fake_host_unregisters(void) { return g_host_unregisters; }
 /* pointer queries: device memory when the address lies in a live allocation or a mapped VMM range, INVALID_VALUE otherwise */
 static CUresult pointer_attr(int attr, void *data, CUdeviceptr p) {
     fake_init();

@@ -51,6 +51,15 @@ extern CUresult cuInit(unsigned);
 extern CUresult cuDeviceGet(CUdevice *, int);
 extern CUresult cuDevicePrimaryCtxRetain(CUcontext *, CUdevice);
 extern CUresult cuCtxSetCurrent(CUcontext);
+extern CUresult cuMemHostAlloc(void **, size_t, unsigned);
+extern CUresult cuMemAllocHost_v2(void **, size_t);
+extern CUresult cuMemFreeHost(void *);
+extern CUresult cuMemHostRegister_v2(void *, size_t, unsigned) __attribute__((weak));
+extern CUresult cuMemHostUnregister(void *) __attribute__((weak));
+extern CUresult cuMipmappedArrayCreate(void **, const void *, unsigned) __attribute__((weak));
+extern CUresult cuMipmappedArrayDestroy(void *) __attribute__((weak));
+extern int fake_live_mipmaps(void) __attribute__((weak));
+extern int fake_host_unregisters(void) __attribute__((weak));
 extern CUresult cuCtxCreate_v2(CUcontext *, unsigned, CUdevice);
 extern CUresult cuCtxDestroy_v2(CUcontext);
 extern CUresult cuCtxGetDevice(CUdevice *);
@@ -156,7 +165,7 @@ int main(int argc, char **argv) {
         if (line[0] == '#' || line[0] == '\n') continue;
         int n = sscanf(line, " %c %lli %lli %lli", &op, (long long *)&a, (long long *)&b, (long long *)&d);
         if (n < 1) continue;
-        size_t fr = 0, tot = 0; int has_info = 0, has_q = 0, qtype = 0, qman = 0, has_nv = 0, has_v = 0, vok = 0;
+        size_t fr = 0, tot = 0; int has_x = 0, xval = 0, has_info = 0, has_q = 0, qtype = 0, qman = 0, has_nv = 0, has_v = 0, vok = 0;
         unsigned long long nvmem[3] = {0, 0, 0};     /* nvmlMemory_t {total, free, used} */
         switch (op) {
         case 'A': ptrs[a] = 0; r = cuMemAlloc_v2(&ptrs[a], (size_t)b); if (r) ptrs[a] = 0; else sizes[a] = (size_t)b; break;
@@ -193,6 +202,20 @@ int main(int argc, char **argv) {
                     if (!r) { udev[a & 15] = (int)b & 15; cur = (int)b & 15; dev = d2; } break; }
         case 'H': r = uctx[a & 15] ? cuCtxSetCurrent(uctx[a & 15]) : 1; if (!r) { cur = udev[a & 15]; dev = cur; } break;
         case 'e': r = uctx[a & 15] ? cuCtxDestroy_v2(uctx[a & 15]) : 1; if (!r) uctx[a & 15] = NULL; break;
+        /* host-side family (the reference only runs check_oom after the real call): h n = cuMemHostAlloc(n) + free,
+         * a n = cuMemAllocHost_v2(n) + free, r n = cuMemHostRegister_v2 of n malloc'd bytes (+ unregister),
+         * m = cuMipmappedArrayCreate (+ destroy); the extra field says what was left behind on the driver side */
+        case 'h': { void *hp = NULL; r = cuMemHostAlloc(&hp, (size_t)a, 0); if (!r) cuMemFreeHost(hp); break; }
+        case 'a': { void *hp = NULL; r = cuMemAllocHost_v2(&hp, (size_t)a); if (!r) cuMemFreeHost(hp); break; }
+        case 'r': { void *hp = malloc((size_t)a); int before = fake_host_unregisters ? fake_host_unregisters() : 0;
+                    r = cuMemHostRegister_v2 ? cuMemHostRegister_v2(hp, (size_t)a, 0) : 801;
+                    has_x = 1; xval = (fake_host_unregisters ? fake_host_unregisters() : 0) - before;   /* undone by the hook? */
+                    if (!r && cuMemHostUnregister) cuMemHostUnregister(hp);
+                    free(hp); break; }
+        case 'm': { unsigned long long desc[5] = {64, 64, 0, 0x20 /* FLOAT */ | (1ull << 32), 0}; void *arr = NULL;
+                    r = cuMipmappedArrayCreate ? cuMipmappedArrayCreate(&arr, desc, 2) : 801;
+                    if (!r && cuMipmappedArrayDestroy) cuMipmappedArrayDestroy(arr);
+                    has_x = 1; xval = fake_live_mipmaps ? fake_live_mipmaps() : 0; break; }
         case 'Y': ptrs[a] = 0; r = cuMemAllocAsync ? cuMemAllocAsync(&ptrs[a], (size_t)b, NULL) : 801; if (r) ptrs[a] = 0; break;
         case 'Z': r = cuMemFreeAsync ? cuMemFreeAsync(ptrs[a], NULL) : 801; if (!r) ptrs[a] = 0; break;
         case 'C': { struct mem_prop pr; memset(&pr, 0, sizeof pr); pr.type = 1 /* PINNED */; pr.location.type = 1 /* DEVICE */; pr.location.id = 0;
@@ -222,6 +245,7 @@ int main(int argc, char **argv) {
             printf(" free=%zu total=%zu", fr, tot);
         }
         if (has_q) printf(" type=%d managed=%d", qtype, qman);
+        if (has_x) printf(" left=%d", xval);
         if (has_v) printf(" ok=%d", vok);
         if (op == 'L' && g_region && getenv("TRACE_SHOW_WORDS")) {   /* the monitor handshake words next to a launch */
             int32_t w[3]; memcpy(w, g_region + 0xC473C, 12);

@@ -296,6 +296,23 @@ def test_nvml_memory_view_matches_the_reference(tmp_path, limit):
 
 
 @pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
+@pytest.mark.parametrize("limit,over", [("64m", True), ("1g", False)])
+def test_host_side_calls_run_the_quota_check_like_the_reference(tmp_path, limit, over):
+    """cuMemHostAlloc@0x32577, cuMemAllocHost_v2@0x319f8, cuMemHostRegister_v2@0x32842, cuMipmappedArrayCreate@0x36d29:
+    real call, then check_oom(); on a container already over its limit (here: a 100 MiB context under a 64 MiB limit) the
+    call is undone and answers CUDA_ERROR_OUT_OF_MEMORY. Same codes, same undo, same counters as the binary."""
+    t = _write(tmp_path, "h 4096\na 4096\nr 8192\nm\nA 0 4096\nI\n")
+    env = _env(tmp_path, None, CUDA_DEVICE_MEMORY_LIMIT=limit, FAKE_GPU_CTX_MIB="100")
+    new = run_replay(t, "new", env).splitlines()
+    ref = run_replay(t, "reference", dict(env, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "ref.cache"))).splitlines()
+    assert new == ref
+    rcs = [int(l.split(" rc=")[1].split()[0]) for l in new[1:5]]
+    assert rcs == ([2, 2, 2, 2] if over else [0, 0, 0, 0])
+    if over:
+        assert new[3].endswith("left=1") and new[4].endswith("left=0")      # registration undone, array destroyed
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
 def test_context_accounting_is_once_per_device(tmp_path, seed):
     """context.c: the context size is charged when a device gets its first context — by cuDevicePrimaryCtxRetain or by
