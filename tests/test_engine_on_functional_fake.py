@@ -379,6 +379,45 @@ def test_hook_copy_and_fill_family_on_swapped_buffers(tmp_path, seed):
     assert len(checks) >= 40 and all(l.endswith("ok=1") for l in checks), [l for l in checks if not l.endswith("ok=1")][:3]
 
 
+@pytest.mark.parametrize("seed", [5, 9])
+def test_two_gpus_each_page_under_their_own_quota(tmp_path, seed):
+    """A container with two vGPUs in swap mode: one engine per device, each bounded by its own gpumem figure; the
+    application hops between the devices, fills, re-fills, verifies and frees ragged buffers on both (~2-3x each quota
+    live). Every byte read back, every lane's live bytes equal to what the trace holds there."""
+    import random
+    from conftest import run_replay
+    rng = random.Random(seed)
+    lines, live, cur, nid, fillv, size = [], {0: [], 1: []}, 0, 0, {}, {}
+    for _ in range(400):
+        r = rng.random()
+        if r < 0.1:
+            cur = rng.randrange(2); lines.append(f"D {cur}")
+        elif r < 0.35 and len(live[cur]) < 10:
+            size[nid] = rng.choice([6, 10, 12, 14]) * M + rng.choice([0, 4096, 12345])
+            fillv[nid] = rng.randrange(1, 255)
+            lines += [f"A {nid} {size[nid]}", f"W {nid} {fillv[nid]}"]; live[cur].append(nid); nid += 1
+        elif r < 0.45 and live[cur]:
+            i = live[cur].pop(rng.randrange(len(live[cur]))); lines += [f"V {i} {fillv[i]}", f"F {i}"]
+        elif r < 0.8 and live[cur]:
+            i = rng.choice(live[cur]); lines.append(f"V {i} {fillv[i]}")
+        elif live[cur]:
+            i = rng.choice(live[cur]); fillv[i] = rng.randrange(1, 255); lines.append(f"W {i} {fillv[i]}")
+    t = tmp_path / "t.txt"
+    t.write_text("\n".join(lines) + "\n")
+    env = {"FAKE_GPU_EXEC": "1", "FAKE_GPU_COUNT": "2", "FAKE_GPU_CTX_MIB": "16", "CUDA_OVERSUBSCRIBE": "true",
+           "CUDA_DEVICE_MEMORY_LIMIT_0": "96m", "CUDA_DEVICE_MEMORY_LIMIT_1": "80m", "CUDA_DEVICE_MEMORY_SHARED_CACHE": str(tmp_path / "c.cache"),
+           "VGPU_SWAP_CHUNK_MB": "2", "VGPU_SWAP_ARENA_GB": "8", "VGPU_SWAP_SLAB_MB": "16", "VGPU_SWAP_SPARE_MB": "4"}
+    out = run_replay(str(t), "new", env).splitlines()
+    assert len(out) == len(lines) + 1
+    assert all(" rc=0 " in l for l in out[1:]), [l for l in out[1:] if " rc=0 " not in l][:3]
+    checks = [l for l in out if " V " in l]
+    assert len(checks) >= 100 and all(l.endswith("ok=1") for l in checks), [l for l in checks if not l.endswith("ok=1")][:3]
+    # the lane the last line reports (device `cur`) holds exactly the bytes the trace left alive there, above its quota at times
+    buf = lambda l: int(l.split(" buf=")[1].split()[0])
+    assert buf(out[-1]) == sum(size[i] for i in live[cur])
+    assert max(buf(l) for l in out[1:]) > 96 * M
+
+
 def test_application_threads_share_the_swap_engine(tmp_path):
     """Six application threads, four swappable buffers each (~200 MiB live under a 128 MiB quota), launching fill / touch /
     verify kernels concurrently through the hook: a buffer stays pinned from its admission until its kernel has run, no
