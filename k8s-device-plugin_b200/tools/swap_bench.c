@@ -32,6 +32,7 @@ static uint64_t rng(void) { uint64_t x = (rng_state += 0x9E3779B97F4A7C15ull); x
 int main(int argc, char **argv) {
     const char *cubin = NULL, *order = "cyclic";
     long nbuf = 64, mib = 64, steps = 64, warmup = 8, managed = 0, ballast_mib = 0, verify = 1, profile = 0, seed = 0x5EED, wait_stdin = 0;
+    long ragged_lo = 0, ragged_hi = 0;   /* cfg 3 variant B: sizes log-uniform in [lo, hi] MiB, same total as --buffers x --mib */
     double zipf_s = 1.1;
     for (int i = 1; i + 1 < argc; i += 2) {
         const char *k = argv[i], *v = argv[i + 1];
@@ -48,6 +49,8 @@ int main(int argc, char **argv) {
         else if (!strcmp(k, "--seed")) seed = strtol(v, 0, 0);
         else if (!strcmp(k, "--zipf")) zipf_s = atof(v);
         else if (!strcmp(k, "--wait-stdin")) wait_stdin = atol(v);
+        else if (!strcmp(k, "--ragged-lo")) ragged_lo = atol(v);
+        else if (!strcmp(k, "--ragged-hi")) ragged_hi = atol(v);
         else { fprintf(stderr, "unknown option %s\n", k); return 2; }
     }
     if (getenv("SWAP_BENCH_HOLD_MIB")) {
@@ -64,8 +67,26 @@ int main(int argc, char **argv) {
     }
     if (!cubin) { fprintf(stderr, "--cubin required\n"); return 2; }
     rng_state = (uint64_t)seed;
-    const size_t bytes = (size_t)mib << 20;
-    const uint64_t nwords = bytes / 8;
+    /* buffer sizes: uniform (variant A), or log-uniform in [lo, hi] MiB rounded to 256 B until the same total is
+     * reached (variant B, SURVEY.md §8d cfg 3) */
+    size_t *sz;
+    if (ragged_lo > 0 && ragged_hi >= ragged_lo) {
+        const size_t want = (size_t)nbuf * ((size_t)mib << 20);
+        size_t cap = (size_t)(want / ((size_t)ragged_lo << 20)) + 2, sum = 0;
+        long n = 0;
+        sz = calloc(cap, sizeof *sz);
+        while (sum < want && (size_t)n < cap) {
+            double u = (double)(rng() >> 11) / 9007199254740992.0;
+            double m = (double)ragged_lo * pow((double)ragged_hi / (double)ragged_lo, u);
+            size_t b = ((size_t)(m * 1048576.0) + 255) & ~(size_t)255;
+            if (sum + b > want && want - sum >= ((size_t)ragged_lo << 20)) b = want - sum;
+            sz[n++] = b; sum += b;
+        }
+        nbuf = n;
+    } else {
+        sz = calloc((size_t)nbuf, sizeof *sz);
+        for (long i = 0; i < nbuf; i++) sz[i] = (size_t)mib << 20;
+    }
 
     CUdevice dev; CUcontext ctx; CUmodule mod; CUfunction f_fill, f_touch, f_verify;
     CK(cuInit(0));
@@ -89,9 +110,9 @@ int main(int argc, char **argv) {
     uint64_t *touches = calloc((size_t)nbuf, sizeof *touches);
     double t_alloc0 = now_ms();
     for (long i = 0; i < nbuf; i++) {
-        if (managed) CK(cuMemAllocManaged(&buf[i], bytes, CU_MEM_ATTACH_GLOBAL));
-        else CK(cuMemAlloc(&buf[i], bytes));
-        uint64_t idx = (uint64_t)i, nw = nwords;
+        if (managed) CK(cuMemAllocManaged(&buf[i], sz[i], CU_MEM_ATTACH_GLOBAL));
+        else CK(cuMemAlloc(&buf[i], sz[i]));
+        uint64_t idx = (uint64_t)i, nw = sz[i] / 8;
         void *a[] = {&buf[i], &nw, &idx};
         CK(cuLaunchKernel(f_fill, grid, 1, 1, 256, 1, 1, 0, 0, a, 0));
     }
@@ -120,7 +141,7 @@ int main(int argc, char **argv) {
     CUevent e0, e1; CK(cuEventCreate(&e0, 0)); CK(cuEventCreate(&e1, 0));
     swap_stats_t s0, s1; memset(&s0, 0, sizeof s0); memset(&s1, 0, sizeof s1);
     for (long t = 0; t < warmup; t++) {
-        uint64_t nw = nwords; void *a[] = {&buf[seq[t]], &nw};
+        uint64_t nw = sz[seq[t]] / 8; void *a[] = {&buf[seq[t]], &nw};
         CK(cuLaunchKernel(f_touch, grid, 1, 1, 256, 1, 1, 0, 0, a, 0));
         touches[seq[t]]++;
     }
@@ -133,10 +154,12 @@ int main(int argc, char **argv) {
     if (get_stats) get_stats(0, &s0);
     double w0 = now_ms();
     CK(cuEventRecord(e0, 0));
+    unsigned long long touched = 0;
     for (long t = warmup; t < total; t++) {
-        uint64_t nw = nwords; void *a[] = {&buf[seq[t]], &nw};
+        uint64_t nw = sz[seq[t]] / 8; void *a[] = {&buf[seq[t]], &nw};
         CK(cuLaunchKernel(f_touch, grid, 1, 1, 256, 1, 1, 0, 0, a, 0));
         touches[seq[t]]++;
+        touched += sz[seq[t]];
     }
     double w_enq = now_ms();
     CK(cuEventRecord(e1, 0));
@@ -150,7 +173,7 @@ int main(int argc, char **argv) {
     if (verify) {
         CUdeviceptr dcnt; CK(cuMemAlloc(&dcnt, 8)); CK(cuMemsetD8(dcnt, 0, 8));
         for (long i = 0; i < nbuf; i++) {
-            uint64_t nw = nwords, idx = (uint64_t)i, add = touches[i];
+            uint64_t nw = sz[i] / 8, idx = (uint64_t)i, add = touches[i];
             void *a[] = {&buf[i], &nw, &idx, &add, &dcnt};
             CK(cuLaunchKernel(f_verify, grid, 1, 1, 256, 1, 1, 0, 0, a, 0));
         }
@@ -160,7 +183,7 @@ int main(int argc, char **argv) {
     double t_ver1 = now_ms();
 
     uint64_t pin = s1.v[1] - s0.v[1], pout = s1.v[0] - s0.v[0];
-    printf("{\"buffers\": %ld, \"mib\": %ld, \"steps\": %ld, \"warmup\": %ld, \"order\": \"%s\", \"managed\": %ld, \"ballast_mib\": %ld, "
+    printf("{\"ragged_mib\": [%ld, %ld], \"buffers\": %ld, \"mib\": %ld, \"steps\": %ld, \"warmup\": %ld, \"order\": \"%s\", \"managed\": %ld, \"ballast_mib\": %ld, "
            "\"event_ms\": %.3f, \"wall_ms\": %.3f, \"enqueue_ms\": %.3f, \"alloc_fill_ms\": %.1f, \"verify_ms\": %.1f, "
            "\"hooked_stats\": %s, \"page_in_bytes\": %llu, \"page_out_bytes\": %llu, \"touched_bytes\": %llu, "
            "\"mismatches\": %llu, \"verified\": %ld, "
@@ -169,9 +192,9 @@ int main(int argc, char **argv) {
            "\"phys_creates\": %llu, \"phys_reuses\": %llu, \"scans\": %llu, \"scan_cache_hits\": %llu, "
            "\"host_ms\": {\"admit\": %.1f, \"scan\": %.1f, \"packsync\": %.1f, \"vmm\": %.1f, \"ringwait\": %.1f}, "
            "\"pack_span_ms\": %.3f, \"unpack_span_ms\": %.3f}\n",
-           nbuf, mib, steps, warmup, order, managed, ballast_mib, ev_ms, w1 - w0, w_enq - w0, t_alloc1 - t_alloc0, t_ver1 - t_ver0,
+           ragged_lo, ragged_hi, nbuf, mib, steps, warmup, order, managed, ballast_mib, ev_ms, w1 - w0, w_enq - w0, t_alloc1 - t_alloc0, t_ver1 - t_ver0,
            get_stats ? "true" : "false", (unsigned long long)pin, (unsigned long long)pout,
-           (unsigned long long)steps * bytes, mism, verify,
+           touched, mism, verify,
            s1.pack_ms - s0.pack_ms, s1.unpack_ms - s0.unpack_ms,
            (unsigned long long)(s1.v[15] - s0.v[15]), (unsigned long long)(s1.v[16] - s0.v[16]),
            (unsigned long long)(s1.v[5] - s0.v[5]), (unsigned long long)(s1.v[6] - s0.v[6]), (unsigned long long)(s1.v[7] - s0.v[7]),

@@ -49,6 +49,18 @@ def test_zipf_order_keeps_the_hot_set_resident(tmp_path):
     assert out["page_in_bytes"] < 200 * 16 * M * 0.8
 
 
+@pytest.mark.parametrize("order", ["cyclic", "zipf"])
+def test_ragged_buffer_sizes_variant_b(tmp_path, order):
+    """SURVEY.md §8d cfg 3 variant B: the same total (here 512 MiB under a 256 MiB quota) as buffers of log-uniform size,
+    3-40 MiB rounded to 256 B — admissions need a varying number of victims, rows span a varying number of staging chunks."""
+    out = _swap_bench(tmp_path, ["--buffers", "32", "--mib", "16", "--ragged-lo", "3", "--ragged-hi", "40", "--steps", "120", "--warmup", "10", "--order", order],
+                      CUDA_DEVICE_MEMORY_LIMIT_0="256m")
+    assert out["mismatches"] == 0 and out["verified"] == 1 and out["ragged_mib"] == [3, 40] and out["buffers"] != 32
+    assert out["page_in_bytes"] > 0 and out["page_out_bytes"] > 0
+    if order == "cyclic":
+        assert out["page_in_bytes"] == out["touched_bytes"]        # LRU worst case holds for ragged sizes too: every touch misses
+
+
 def test_reaper_thread_variant(tmp_path):
     out = _swap_bench(tmp_path, ["--buffers", "24", "--mib", "16", "--steps", "72", "--warmup", "8", "--order", "cyclic"], CUDA_DEVICE_MEMORY_LIMIT_0="256m",
                       VGPU_SWAP_ASYNC_UNMAP="1")
