@@ -1,7 +1,7 @@
 """Differential fuzzing of the hook against the reference BINARY on the fake driver (build container only: needs
 oracle/_ref/libvgpu.so): random three-GPU traces — device switches, every allocation family, frees of live / stale /
-foreign / cross-device pointers, cuMemGetInfo, cuDeviceTotalMem, NVML queries, launches, async and VMM allocations under
-VGPU_REFERENCE_COVERAGE=1 — compared line by line.   python scripts/fuzz_vs_reference.py <first seed> <last seed>
+foreign / cross-device pointers, cuMemGetInfo, cuDeviceTotalMem, NVML queries, launches, context creation / destruction,
+host-side allocations and registrations, pointer queries, async and VMM allocations under VGPU_REFERENCE_COVERAGE=1 — compared line by line.   python scripts/fuzz_vs_reference.py <first seed> <last seed>
 This is how the cross-device-free crediting and the wrapping NVML free figure were found (tests/test_hook_parity_cpu.py
 keeps three seeds in the suite)."""
 import sys, random, os
@@ -11,6 +11,7 @@ def gen(seed, nops=900):
     rng = random.Random(seed)
     lines, live, nid = [], {0: [], 1: [], 2: []}, 0
     cur = 0
+    made = set()
     for _ in range(nops):
         r = rng.random()
         if r < 0.08:
@@ -39,7 +40,21 @@ def gen(seed, nops=900):
             k = rng.choice("YC"); lines.append(f"{k} {nid} {rng.choice([2<<20, 4<<20, 64<<20])}"); live.setdefault(('x',cur), []).append((k, nid)); nid += 1
         elif r < 0.95 and live.get(('x',cur)):
             k, i = live[('x',cur)].pop(); lines.append(f"{'Z' if k=='Y' else 'R'} {i}")
-        elif r < 0.97 and nid:
+        elif r < 0.955:
+            # context family: more retains, cuCtxCreate_v2 on any device (becomes current), destroys. Created contexts
+            # are never made current again later (the reference exit()s on cuCtxSetCurrent of a duplicate create)
+            k = rng.choice("BEe")
+            if k == "B":
+                lines.append(f"B {rng.randrange(3)}")
+            elif k == "E":
+                slot = rng.randrange(8); made.add(slot); cur = rng.randrange(3); lines.append(f"E {slot} {cur}")
+            elif made:
+                slot = rng.choice(sorted(made)); made.discard(slot); lines.append(f"e {slot}")
+        elif r < 0.965:
+            lines.append(rng.choice(["h 4096", "a 65536", "r 8192", "m"]))      # host-side calls: quota check only
+        elif r < 0.97 and live[cur]:
+            lines.append(f"Q {rng.choice(live[cur])}")                            # pointer query on a live buffer
+        elif r < 0.98 and nid:
             lines.append(f"F {rng.randrange(nid)}")     # maybe double free / stale id
         else:
             other = [d for d in (0, 1, 2) if d != cur and live[d]]
