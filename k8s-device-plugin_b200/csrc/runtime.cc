@@ -596,7 +596,9 @@ CUresult Runtime::device_total_mem(size_t *bytes, CUdevice dev) {
     ensure_initialized();
     uint64_t limit = (region_ && dev >= 0 && dev < VGPU_MAX_DEVICES) ? region_->limit(dev) : 0;
     // cuDeviceTotalMem_v2@0x2d3f8 stores the limit unconditionally — 0 bytes for an unlimited container. That is
-    // a defect, not a contract: unlimited containers get the driver's answer here (DESIGN.md "deviations").
+    // a defect, not a contract: unlimited containers get the driver's answer here (DESIGN.md "deviations");
+    // VGPU_REFERENCE_COVERAGE=1 answers like the binary (differential fuzzing with unlimited lanes).
+    if (limit == 0 && reference_coverage()) { if (bytes) *bytes = 0; return CUDA_SUCCESS; }
     if (limit == 0) return drv().cuDeviceTotalMem_v2(bytes, dev);
     if (bytes) *bytes = limit;
     return CUDA_SUCCESS;

@@ -70,6 +70,8 @@ for seed in range(int(sys.argv[1]), int(sys.argv[2])):
     lines = gen(seed)
     open(TR,'w').write("\n".join(lines)+"\n")
     env={"CUDA_DEVICE_MEMORY_LIMIT_0":"96m","CUDA_DEVICE_MEMORY_LIMIT_1":"64m","CUDA_DEVICE_MEMORY_LIMIT_2":"200m","FAKE_GPU_COUNT":"3","FAKE_GPU_CTX_MIB":"16","VGPU_REFERENCE_COVERAGE":"1"}
+    for kv in filter(None, os.environ.get("FUZZ_ENV", "").split(",")):      # e.g. FUZZ_ENV=CUDA_DEVICE_MEMORY_LIMIT_1=0,MEMORY_OVERRIDE=1
+        k, _, val = kv.partition("="); env[k] = val
     for f in (NC, RC):
         if os.path.exists(f): os.remove(f)
     new=run_replay(TR,'new',dict(env,CUDA_DEVICE_MEMORY_SHARED_CACHE=NC)).splitlines()
