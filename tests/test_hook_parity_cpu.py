@@ -295,6 +295,21 @@ def test_nvml_memory_view_matches_the_reference(tmp_path, limit):
         assert new[3].endswith("nv_used=%d" % (26 << 20)) and "nv_total=%d" % (183359 << 20) in new[3]
 
 
+@pytest.mark.parametrize("content", [b"", b"\xff" * 1000, b"\xab" * 0xC4748, b"\0" * 0xC4748, b"\0" * (0xC4748 + 8192)],
+                         ids=["empty", "short-garbage", "full-size-garbage", "zeros", "oversize-zeros"])
+def test_a_damaged_region_file_is_reinitialised(tmp_path, content):
+    """The cache path may hold anything when the first process of a container starts (a crashed predecessor, a truncated
+    write, a file from another version). The reference copes with everything but full-size garbage (it takes the junk
+    semaphore and segfaults); the product re-initialises in every case and accounts from zero."""
+    cache = tmp_path / "d.cache"
+    cache.write_bytes(content)
+    t = _write(tmp_path, "A 0 4096\nI\n")
+    out = run_replay(t, "new", _env(tmp_path, None, CUDA_DEVICE_MEMORY_LIMIT_0="1g", CUDA_DEVICE_MEMORY_SHARED_CACHE=str(cache))).splitlines()
+    assert out[-1].split(" rc=")[1].startswith("0 ") and " buf=4096 " in out[-1] and out[-1].endswith("total=1073741824")
+    raw = cache.read_bytes()
+    assert int.from_bytes(raw[0:4], "little") == 19920718 and len(raw) >= 0xC4748        # initializedFlag (Appendix A)
+
+
 @pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
 @pytest.mark.parametrize("limit,over", [("64m", True), ("1g", False)])
 def test_host_side_calls_run_the_quota_check_like_the_reference(tmp_path, limit, over):
