@@ -18,6 +18,45 @@ def _kube(args):
     return K.RestKube.in_cluster()
 
 
+def _gobool(v):
+    """Go's strconv.ParseBool, as the flag packages apply it to --flag=value."""
+    if v in ("1", "t", "T", "TRUE", "true", "True"):
+        return True
+    if v in ("0", "f", "F", "FALSE", "false", "False"):
+        return False
+    raise argparse.ArgumentTypeError(f"invalid boolean value {v!r}")
+
+
+def _bool_flag(p, *names, default=False, env=None, help=None):
+    """A Go-style boolean flag: --flag, --flag=true, --flag=false; optional environment fallback (urfave/cli EnvVars)."""
+    if env and os.environ.get(env, "") != "":
+        try:
+            default = _gobool(os.environ[env])
+        except argparse.ArgumentTypeError:
+            pass
+    p.add_argument(*names, type=_gobool, nargs="?", const=True, default=default, help=help)
+
+
+def go_style_argv(argv):
+    """Go's flag package (and cobra / urfave/cli on top of it) accepts -name and --name alike; argparse wants --name for
+    multi-letter flags. `-v=4` / `-v=false` stay as they are (single letter)."""
+    out = []
+    for a in argv:
+        if a.startswith("-") and not a.startswith("--") and len(a.split("=", 1)[0]) > 2:
+            a = "-" + a
+        out.append(a)
+    return out
+
+
+def _klog_flags(p):
+    """klog.InitFlags (pkg/util/util.go:321-327): accepted so that the chart's `-v=4` works; only -v is looked at."""
+    p.add_argument("-v", "--v", default="0", help="log level verbosity")
+    for name in ("logtostderr", "alsologtostderr", "add_dir_header", "skip_headers", "skip_log_headers", "one_output"):
+        _bool_flag(p, "--" + name, default=(name == "logtostderr"))
+    for name in ("log_dir", "log_file", "log_file_max_size", "stderrthreshold", "vmodule", "log_backtrace_at"):
+        p.add_argument("--" + name, default="")
+
+
 def _common(p):
     p.add_argument("--apiserver", default=os.environ.get("VGPU_APISERVER", ""), help="apiserver URL (default: in-cluster config)")
     p.add_argument("--token", default=os.environ.get("VGPU_APISERVER_TOKEN"))
@@ -42,6 +81,8 @@ def main(argv=None):
     sc.add_argument("--resource-mem-percentage", default=P.RESOURCE_MEM_PERCENTAGE)
     sc.add_argument("--resource-cores", default=P.RESOURCE_CORES)
     sc.add_argument("--resource-priority", default="vgputaskpriority")
+    _bool_flag(sc, "--debug", help="debug mode (pkg/device/devices.go:98)")
+    _klog_flags(sc)
     sc.add_argument("--multi-container", action="store_true", help="per-container device bookkeeping (vgpu_sched.h mode 1) instead of the reference's")
 
     dp = sub.add_parser("device-plugin", help="NVIDIA device plugin for Kubernetes (vGPU path)")
@@ -50,19 +91,36 @@ def main(argv=None):
     dp.add_argument("--device-split-count", type=int, default=int(os.environ.get("DEVICE_SPLIT_COUNT", "2")))
     dp.add_argument("--device-memory-scaling", type=float, default=float(os.environ.get("DEVICE_MEMORY_SCALING", "1.0")))
     dp.add_argument("--device-cores-scaling", type=float, default=float(os.environ.get("DEVICE_CORES_SCALING", "1.0")))
-    dp.add_argument("--disable-core-limit", action="store_true", default=os.environ.get("DISABLE_CORE_LIMIT", "") in ("1", "true"))
+    _bool_flag(dp, "--disable-core-limit", env="DISABLE_CORE_LIMIT", help="If set, the core utilization limit will be ignored (vgpucfg.go:42)")
+    # flags of the upstream NVIDIA plugin the reference keeps (cmd/device-plugin/nvidia/main.go:49-119); the vGPU path
+    # needs none of them, but the chart passes --mig-strategy, so they parse — and what is not supported says so
+    dp.add_argument("--mig-strategy", default=os.environ.get("MIG_STRATEGY", "none"))
+    _bool_flag(dp, "--fail-on-init-error", default=True, env="FAIL_ON_INIT_ERROR")
+    dp.add_argument("--nvidia-driver-root", default=os.environ.get("NVIDIA_DRIVER_ROOT", "/"))
+    _bool_flag(dp, "--pass-device-specs", env="PASS_DEVICE_SPECS")
+    dp.add_argument("--device-list-strategy", default=os.environ.get("DEVICE_LIST_STRATEGY", "envvar"))
+    dp.add_argument("--device-id-strategy", default=os.environ.get("DEVICE_ID_STRATEGY", "uuid"))
+    _bool_flag(dp, "--gds-enabled", env="GDS_ENABLED")
+    _bool_flag(dp, "--mofed-enabled", env="MOFED_ENABLED")
+    dp.add_argument("--cdi-annotation-prefix", default=os.environ.get("CDI_ANNOTATION_PREFIX", "cdi.k8s.io/"))
+    dp.add_argument("--nvidia-ctk-path", default=os.environ.get("NVIDIA_CTK_PATH", "/usr/bin/nvidia-ctk"))
+    dp.add_argument("--container-driver-root", default=os.environ.get("CONTAINER_DRIVER_ROOT", "/driver-root"))
+    _bool_flag(dp, "-v", "--version", help="urfave/cli's built-in; the chart passes -v=false")
     dp.add_argument("--resource-name", default=P.RESOURCE_NAME)
-    dp.add_argument("--config-file", default="/config/config.json")
+    dp.add_argument("--config-file", default=os.environ.get("CONFIG_FILE", ""), help="upstream plugin config file (unused on the vGPU path)")
+    dp.add_argument("--node-config-file", default="/config/config.json", help="per-node overrides (vgpucfg.go:80: fixed path in the reference)")
     dp.add_argument("--socket-dir", default=api.DEVICE_PLUGIN_PATH)
     dp.add_argument("--hook-path", default=os.environ.get("HOOK_PATH", "/usr/local"))
 
     mo = sub.add_parser("monitor", help="vGPU monitor: region metrics + priority feedback")
     _common(mo)
-    mo.add_argument("--containers-path", default=os.path.join(os.environ.get("HOOK_PATH", "/usr/local"), "vgpu", "containers"))
+    # pathmonitor.go:31-36: containerPath = $HOOK_PATH/containers, and HOOK_PATH is required (validation.go:8-20); the chart
+    # sets HOOK_PATH=<gpuHookPath>/vgpu for this container (daemonsetnvidia.yaml:96-97)
+    mo.add_argument("--containers-path", default=os.path.join(os.environ["HOOK_PATH"], "containers") if "HOOK_PATH" in os.environ else None)
     mo.add_argument("--port", type=int, default=9394)
     mo.add_argument("--node-name", default=os.environ.get("NODE_NAME", ""))
 
-    args = ap.parse_args(argv)
+    args = ap.parse_args(go_style_argv(sys.argv[1:] if argv is None else list(argv)))
     stop = threading.Event()
 
     if args.cmd == "scheduler":
@@ -81,7 +139,16 @@ def main(argv=None):
 
     if args.cmd == "device-plugin":
         kube = _kube(args)
-        split, mscale, cscale = rm.read_node_config(args.config_file, args.node_name, args.device_split_count, args.device_memory_scaling,
+        if args.version is True:
+            print("k8s_device_plugin_b200 device-plugin")
+            return 0
+        if args.mig_strategy != "none":
+            print(f"--mig-strategy={args.mig_strategy}: MIG devices are outside this plugin's path (DESIGN.md §8); only \"none\" is supported", file=sys.stderr)
+            return 1
+        if args.device_list_strategy != "envvar" or args.device_id_strategy != "uuid":
+            print("only --device-list-strategy=envvar and --device-id-strategy=uuid are supported (the vGPU path of server.go uses no other)", file=sys.stderr)
+            return 1
+        split, mscale, cscale = rm.read_node_config(args.node_config_file, args.node_name, args.device_split_count, args.device_memory_scaling,
                                                     args.device_cores_scaling)
 
         def make():
@@ -105,6 +172,9 @@ def main(argv=None):
         return 0
 
     if args.cmd == "monitor":
+        if not args.containers_path:
+            print("required environment variable HOOK_PATH not set", file=sys.stderr)     # ValidateEnvVars (validation.go:13-20)
+            return 1
         kube = _kube(args)
 
         def list_pods():

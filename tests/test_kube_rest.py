@@ -9,6 +9,7 @@ import sys
 import threading
 import time
 import http.client
+import pytest
 from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -207,8 +208,12 @@ def test_scheduler_cli_serves_filter_and_metrics():
     api = _cluster()
     port, mport = _free_port(), _free_port()
     env = dict(os.environ, PYTHONPATH=ROOT)
-    proc = subprocess.Popen([sys.executable, "-m", "k8s_device_plugin_b200.plugin", "scheduler", "--apiserver", api.url, "--http_bind", f"127.0.0.1:{port}",
-                             "--metrics-bind-address", f"127.0.0.1:{mport}", "--scheduler-name", "4pd-scheduler"], env=env, cwd=ROOT,
+    # the argument list of charts/vgpu/templates/scheduler/deployment.yaml:55-71 (values.yaml:61-63 adds --debug -v=4), ports changed
+    proc = subprocess.Popen([sys.executable, "-m", "k8s_device_plugin_b200.plugin", "scheduler", "--apiserver", api.url,
+                             "--resource-name=nvidia.com/gpu", "--resource-mem=nvidia.com/gpumem", "--resource-cores=nvidia.com/gpucores",
+                             "--resource-mem-percentage=nvidia.com/gpumem-percentage", "--resource-priority=nvidia.com/priority",
+                             f"--http_bind=127.0.0.1:{port}", "--cert_file=", "--key_file=", "--scheduler-name=4pd-scheduler",
+                             f"--metrics-bind-address=127.0.0.1:{mport}", "--default-mem=0", "--default-cores=0", "--debug", "-v=4"], env=env, cwd=ROOT,
                             stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     try:
         body = None
@@ -257,7 +262,8 @@ def test_device_plugin_cli_end_to_end_on_fake_nvml(tmp_path):
                FAKE_NVML_XID="1:79@2500", NodeName="node-a")
     hook = tmp_path / "hook"
     proc = subprocess.Popen([sys.executable, "-m", "k8s_device_plugin_b200.plugin", "device-plugin", "--apiserver", apisrv.url, "--socket-dir", str(sock),
-                             "--node-name", "node-a", "--device-split-count", "3", "--hook-path", str(hook), "--config-file", str(tmp_path / "none.json")],
+                             "--node-name", "node-a", "--device-split-count", "3", "--hook-path", str(hook), "--node-config-file", str(tmp_path / "none.json"),
+                             "--mig-strategy=none", "--disable-core-limit=false", "-v=false"],
                             env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     try:
         assert stub.registered.wait(30), proc.poll()
@@ -303,9 +309,11 @@ def test_monitor_cli_exports_region_and_host_metrics(tmp_path):
     pod["spec"]["nodeName"] = "node-a"
     apisrv = FakeApiServer([], [pod])
     port = _free_port()
-    env = dict(os.environ, PYTHONPATH=ROOT, LD_LIBRARY_PATH=FAKE + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
-    mon = subprocess.Popen([sys.executable, "-m", "k8s_device_plugin_b200.plugin", "monitor", "--apiserver", apisrv.url, "--containers-path",
-                            str(tmp_path / "containers"), "--port", str(port)], env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    # the chart starts `vGPUmonitor` without arguments and with HOOK_PATH=<gpuHookPath>/vgpu (daemonsetnvidia.yaml:85-97):
+    # the containers directory is $HOOK_PATH/containers (pathmonitor.go:31-36)
+    env = dict(os.environ, PYTHONPATH=ROOT, LD_LIBRARY_PATH=FAKE + ":" + os.environ.get("LD_LIBRARY_PATH", ""), HOOK_PATH=str(tmp_path))
+    mon = subprocess.Popen([sys.executable, "-m", "k8s_device_plugin_b200.plugin", "monitor", "--apiserver", apisrv.url, "--port", str(port)],
+                           env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     try:
         text, deadline = "", time.time() + 30
         while time.time() < deadline:
@@ -329,3 +337,21 @@ def test_monitor_cli_exports_region_and_host_metrics(tmp_path):
             except subprocess.TimeoutExpired:
                 p.kill()
         apisrv.stop()
+
+
+def test_cli_flag_syntax_follows_the_go_binaries(monkeypatch, capsys):
+    """Go's flag packages take -name and --name alike and booleans as --flag / --flag=false; the chart relies on both
+    (`--disable-core-limit=false`, `-v=false`, `-v=4`, `--debug`). Unsupported strategies are refused loudly, and the
+    monitor insists on HOOK_PATH like validation.go:13-20."""
+    from k8s_device_plugin_b200.plugin import __main__ as M
+    assert M.go_style_argv(["-resource-name=x", "--http_bind=a", "-v=4", "-v", "--debug"]) == ["--resource-name=x", "--http_bind=a", "-v=4", "-v", "--debug"]
+    assert M._gobool("T") is True and M._gobool("0") is False
+    with pytest.raises(Exception):
+        M._gobool("yes")
+    monkeypatch.delenv("HOOK_PATH", raising=False)
+    assert M.main(["monitor", "--apiserver", "http://127.0.0.1:1"]) == 1
+    assert "HOOK_PATH" in capsys.readouterr().err
+    assert M.main(["device-plugin", "--apiserver", "http://127.0.0.1:1", "--mig-strategy=mixed"]) == 1
+    assert "mig-strategy" in capsys.readouterr().err
+    assert M.main(["device-plugin", "--apiserver", "http://127.0.0.1:1", "-device-id-strategy=index"]) == 1
+    assert M.main(["device-plugin", "--apiserver", "http://127.0.0.1:1", "--version"]) == 0
