@@ -4,6 +4,7 @@ died without freeing are reclaimed before a request is refused (rm_quitted_proce
 import json
 import os
 import subprocess
+import sys
 
 from conftest import FAKE, HOOK_SO, OREF, REF_SO, SHIM_SO, have_reference
 
@@ -37,3 +38,20 @@ def test_forked_child_gets_a_slot_and_its_orphaned_bytes_are_reclaimed(tmp_path)
         rchild, rparent = _run(ref_dir, ["fork"], preload=SHIM_SO + ":" + REF_SO)
         # same story in the reference: "rm pid=<child>" (rm_quitted_process@0x41a8e), then the request fits
         assert rchild == child and rparent == parent
+
+
+def test_preload_is_inert_in_processes_that_never_touch_cuda(tmp_path):
+    """/etc/ld.so.preload puts the hook into EVERY process of the container (server.go:386-391): shells, coreutils,
+    interpreters. With no driver library on the box at all, nothing may happen: no output, no region file, exit codes
+    intact, children and forks fine."""
+    import subprocess
+    from conftest import HOOK_SO
+    cache = tmp_path / "never.cache"
+    env = {"PATH": os.environ.get("PATH", "/usr/bin:/bin"), "LD_PRELOAD": HOOK_SO, "CUDA_DEVICE_MEMORY_LIMIT_0": "1g", "CUDA_DEVICE_SM_LIMIT": "30",
+           "CUDA_DEVICE_MEMORY_SHARED_CACHE": str(cache)}
+    r = subprocess.run(["/bin/sh", "-c", "ls / > /dev/null && echo one | cat && (exit 7)"], env=env, capture_output=True, text=True)
+    assert (r.returncode, r.stdout, r.stderr) == (7, "one\n", "")
+    code = "import os,subprocess; print(subprocess.run(['echo','kid'],capture_output=True,text=True).stdout.strip()); pid=os.fork(); os._exit(0) if pid==0 else print(os.waitpid(pid,0)[1])"
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert (r.returncode, r.stdout.split(), r.stderr) == (0, ["kid", "0"], "")
+    assert not cache.exists()
