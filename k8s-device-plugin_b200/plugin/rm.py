@@ -144,6 +144,54 @@ class NvmlEventSource(EventSource):
             pass
 
 
+def parse_nvidia_numa_info(idx, topo):
+    """parseNvidiaNumaInfo (register.go:45-93) on the text of `nvidia-smi topo -m`, quirks included: only lines containing
+    "GPU" are looked at; the header must be the very first line (its "NUMA Affinity" column index is used for the rows,
+    after collapsing double tabs); a row belongs to GPU idx when its first word CONTAINS the decimal idx (so 1 also matches
+    GPU10..GPU19 — the last matching row wins); "N/A" -> 0 at once; anything else is strconv.Atoi (ValueError here)."""
+    result, col = 0, 0
+    for index, line in enumerate(topo.split("\n")):
+        if "GPU" not in line:
+            continue
+        words = line.replace("\t\t", "\t").split("\t")
+        if index == 0:
+            for ci, header in enumerate(words):
+                if "NUMA Affinity" in header:
+                    col = ci
+            continue
+        if str(idx) in words[0]:
+            if words[col] == "N/A":           # IndexError where Go would panic on a short row
+                return 0
+            result = _go_atoi(words[col])
+    return result
+
+
+def _go_atoi(text):
+    """strconv.Atoi: optional sign, decimal digits only (no spaces, no underscores)."""
+    body = text[1:] if text[:1] in "+-" else text
+    if not body or not all("0" <= ch <= "9" for ch in body):
+        raise ValueError(f'strconv.Atoi: parsing "{text}": invalid syntax')
+    return int(text)
+
+
+def numa_node_of(idx, bus_id, run=None):
+    """NUMA node of GPU idx. sysfs first (no process to start, no text to parse); where the PCI device is not visible in
+    sysfs (some container runtimes), the reference's way: `nvidia-smi topo -m` (register.go:35-43)."""
+    bus = bus_id.lower()
+    for cand in (bus, bus[4:] if len(bus) > 12 else bus):      # NVML pads the domain to 8 hex digits, sysfs uses 4
+        try:
+            return max(int(open(f"/sys/bus/pci/devices/{cand}/numa_node").read()), 0)
+        except (OSError, ValueError):
+            continue
+    try:
+        import subprocess
+        out = (run or (lambda: subprocess.run(["nvidia-smi", "topo", "-m"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                                              timeout=30).stdout))()
+        return parse_nvidia_numa_info(idx, out)
+    except (OSError, ValueError, IndexError, Exception):
+        return 0
+
+
 def nvml_devices():
     """getApiDevices' NVML walk (register.go:96-162): every GPU with its UUID, memory, model and NUMA node."""
     import pynvml as nv
@@ -153,14 +201,7 @@ def nvml_devices():
         for i in range(nv.nvmlDeviceGetCount()):
             h = nv.nvmlDeviceGetHandleByIndex(i)
             s = lambda x: x.decode() if isinstance(x, bytes) else x
-            bus = s(nv.nvmlDeviceGetPciInfo(h).busId).lower()
-            numa = 0
-            for cand in (bus, bus[4:] if len(bus) > 12 else bus):      # NVML pads the domain to 8 hex digits, sysfs uses 4
-                try:
-                    numa = max(int(open(f"/sys/bus/pci/devices/{cand}/numa_node").read()), 0)
-                    break
-                except (OSError, ValueError):
-                    continue
+            numa = numa_node_of(i, s(nv.nvmlDeviceGetPciInfo(h).busId))
             out.append(GpuDevice(ID=s(nv.nvmlDeviceGetUUID(h)), Health=api.HEALTHY, TotalMemory=int(nv.nvmlDeviceGetMemoryInfo(h).total),
                                  Model=s(nv.nvmlDeviceGetName(h)), Numa=numa))
         return out

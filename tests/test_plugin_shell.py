@@ -6,6 +6,8 @@ import sys
 import threading
 import time
 
+import pytest
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import k8s_device_plugin_b200  # noqa: F401,E402
 from k8s_device_plugin_b200.plugin import api, rm, scheduler as S  # noqa: E402
@@ -162,3 +164,33 @@ def test_plugin_manager_retries_while_the_kubelet_is_away(tmp_path):
         assert len(stub.registrations) >= 1
     finally:
         mgr.notify("exit"); t.join(5); stub.stop()
+
+
+def test_additional_xids_vectors_of_the_reference_test():
+    """rm/health_test.go:25-88 TestGetAdditionalXids, case for case."""
+    cases = [("", []), (",", []), ("not-an-int", []), ("68", [68]), ("-68", []), ("68  ", [68]), ("68,", [68]), (",68", [68]),
+             ("68,67", [68, 67]), ("68,not-an-int,67", [68, 67])]
+    for text, want in cases:
+        assert rm.additional_xids(text) == want, text
+
+
+def test_numa_from_nvidia_smi_topo_like_the_reference():
+    """plugin/register_test.go:21-69 Test_parseNvidiaNumaInfo (its three elided topologies all want 0), then real layouts:
+    the header's NUMA Affinity column applies to the rows after double tabs are collapsed (register.go:45-93)."""
+    elided = "GPU0    CPU Affinity    NUMA Affinity ...\n                            ..."
+    assert rm.parse_nvidia_numa_info(0, elided) == 0
+    two = "GPU0    GPU1    CPU Affinity    NUMA Affinity ...\n                            ..."
+    assert rm.parse_nvidia_numa_info(0, two) == 0 and rm.parse_nvidia_numa_info(1, two) == 0
+    single = "\tGPU0\tCPU Affinity\tNUMA Affinity\tGPU NUMA ID\nGPU0\t X \t0-7\t\tN/A\t\tN/A\nLegend:\n  X = Self\n"
+    assert rm.parse_nvidia_numa_info(0, single) == 0                                    # N/A: no NUMA topology established
+    multi = ("\tGPU0\tGPU1\tGPU2\tCPU Affinity\tNUMA Affinity\tGPU NUMA ID\n"
+             "GPU0\t X \tNV18\tNV18\t0-55\t\t0\t\tN/A\n"
+             "GPU1\tNV18\t X \tNV18\t0-55\t\t0\t\tN/A\n"
+             "GPU2\tNV18\tNV18\t X \t56-111\t\t1\t\tN/A\n"
+             "\nLegend:\n\n  X    = Self\n  NV#  = Connection traversing a bonded set of # NVLinks\n")
+    assert [rm.parse_nvidia_numa_info(i, multi) for i in range(3)] == [0, 0, 1]
+    with pytest.raises(ValueError):
+        rm.parse_nvidia_numa_info(2, multi.replace("\t1\t\tN/A", "\t0-1\t\tN/A"))       # strconv.Atoi error is returned, not swallowed
+    # sysfs missing -> the nvidia-smi route; a failing or absent nvidia-smi -> 0
+    assert rm.numa_node_of(2, "0000:FF:1F.7", run=lambda: multi) == 1
+    assert rm.numa_node_of(2, "0000:FF:1F.7", run=lambda: (_ for _ in ()).throw(OSError("no nvidia-smi"))) == 0
