@@ -219,7 +219,7 @@ def test_virtual_limit_mode_random_three_gpu_traces_match_the_reference_binary(t
     if not have_reference():
         pytest.skip("reference binary only exists in the build container")
     import importlib.util
-    spec = importlib.util.spec_from_file_location("fuzz_gen", os.path.join(ROOT, "scripts", "fuzz_vs_reference.py"))
+    spec = importlib.util.spec_from_file_location("fuzz_gen", os.path.join(ROOT, "tests", "tools", "fuzz_vs_reference.py"))
     src = open(spec.origin).read().split("import tempfile")[0]          # the generator only, not the driver loop
     ns = {"__file__": spec.origin}
     exec(compile(src, spec.origin, "exec"), ns)

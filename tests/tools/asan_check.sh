@@ -3,7 +3,7 @@
 # the fake driver through the scenarios the CPU suite uses: swap (cyclic / zipf / physical pressure / virtual limit mode),
 # threads + fork, randomised three-GPU traces, the limiter launch loop. Any sanitizer report fails the script.
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 R=$PWD; P=$R/k8s-device-plugin_b200; A=$P/build/asan; L=/usr/lib/x86_64-linux-gnu
 mkdir -p $A; ln -sf $L/libasan.so.8 $A/libasan.so; ln -sf $L/libubsan.so.1 $A/libubsan.so
 FL="-std=c++17 -O1 -g -fno-omit-frame-pointer -DVGPU_NO_DLSYM_OVERRIDE -fsanitize=address,undefined -fPIC -fvisibility=hidden -I$R/include -I/usr/local/cuda/include"
@@ -29,8 +29,8 @@ run $SW CUDA_DEVICE_MEMORY_LIMIT_0=128m -- $R/oracle/_ref/hook_stress swap 4 120
 python - "$T" <<'PY'
 import os, sys
 sys.path.insert(0, os.path.join(os.getcwd(), "scripts"))
-src = open("scripts/fuzz_vs_reference.py").read().split("import tempfile")[0]
-ns = {"__file__": os.path.abspath("scripts/fuzz_vs_reference.py")}
+src = open("tests/tools/fuzz_vs_reference.py").read().split("import tempfile")[0]
+ns = {"__file__": os.path.abspath("tests/tools/fuzz_vs_reference.py")}
 exec(compile(src, "fuzz", "exec"), ns)
 for seed in (1, 2):
     open(os.path.join(sys.argv[1], f"fz{seed}.txt"), "w").write("\n".join(ns["gen"](seed)) + "\n")

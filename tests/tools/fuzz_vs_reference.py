@@ -1,11 +1,11 @@
 """Differential fuzzing of the hook against the reference BINARY on the fake driver (build container only: needs
 oracle/_ref/libvgpu.so): random three-GPU traces — device switches, every allocation family, frees of live / stale /
 foreign / cross-device pointers, cuMemGetInfo, cuDeviceTotalMem, NVML queries, launches, context creation / destruction,
-host-side allocations and registrations, pointer queries, async and VMM allocations under VGPU_REFERENCE_COVERAGE=1 — compared line by line.   python scripts/fuzz_vs_reference.py <first seed> <last seed>
+host-side allocations and registrations, pointer queries, async and VMM allocations under VGPU_REFERENCE_COVERAGE=1 — compared line by line.   python tests/tools/fuzz_vs_reference.py <first seed> <last seed>
 This is how the cross-device-free crediting and the wrapping NVML free figure were found (tests/test_hook_parity_cpu.py
 keeps three seeds in the suite)."""
 import sys, random, os
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests'))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))     # tests/ (conftest)
 from conftest import run_replay
 def gen(seed, nops=900):
     rng = random.Random(seed)
