@@ -973,6 +973,17 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
     }
     if (!missing.empty()) {
         st_.faults += missing.size();
+        if (!ctx_warned_) {
+            // The engine's module, side streams and events live in the context that was current when the first swappable
+            // allocation created it. An application that hops between SEVERAL contexts of one device is outside what swap
+            // mode supports; say so once instead of failing obscurely inside the driver.
+            CUcontext cur = nullptr;
+            if (d.cuCtxGetCurrent(&cur) == CUDA_SUCCESS && cur != ctx_) {
+                ctx_warned_ = true;
+                LOG_ERROR("device %d: a paged-out buffer is used from context %p, the swap engine lives in %p — several contexts on one "
+                          "device are not supported in swap mode", dev_, (void *)cur, (void *)ctx_);
+            }
+        }
         // order matters for overlap: packs of the victims first (short), then the H2D copies of the incoming rows
         // into staging, THEN the host-side wait for the packs and the VMM remaps, and finally the unpacks
         tr_ = nullptr;

@@ -212,6 +212,7 @@ class SwapEngine {
     std::deque<ReapJob> rq_;
     bool reaper_stop_ = false, reaper_busy_ = false;
     CUcontext ctx_ = nullptr;
+    bool ctx_warned_ = false;
     uint64_t evicting_mapped_ = 0;
     void reaper_main();
     void wait_not_evicting(int row);
