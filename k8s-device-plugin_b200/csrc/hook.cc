@@ -130,6 +130,10 @@ VGPU_EXPORT CUresult cuMemCreate(CUmemGenericAllocationHandle *handle, size_t si
     return Runtime::get().mem_create(handle, size, prop, flags);
 }
 VGPU_EXPORT CUresult cuMemRelease(CUmemGenericAllocationHandle handle) { return Runtime::get().mem_release(handle); }
+VGPU_EXPORT CUresult cuMemMap(CUdeviceptr ptr, size_t size, size_t offset, CUmemGenericAllocationHandle handle, unsigned long long flags) {
+    return Runtime::get().mem_map(ptr, size, offset, handle, flags);
+}
+VGPU_EXPORT CUresult cuMemUnmap(CUdeviceptr ptr, size_t size) { return Runtime::get().mem_unmap(ptr, size); }
 
 VGPU_EXPORT CUresult cuModuleUnload(CUmodule hmod) {
     Runtime::get().forget_function_layouts();
@@ -379,7 +383,7 @@ const std::vector<HookEntry> &hooks() {
         H(cuMemsetD8_v2), H(cuMemsetD16_v2), H(cuMemsetD32_v2), H(cuMemsetD8Async), H(cuMemsetD16Async), H(cuMemsetD32Async),
         H(cuLaunchKernel_ptsz), H(cuLaunchKernelEx_ptsz), H(cuLaunchCooperativeKernel_ptsz), H(cuGraphLaunch), H(cuGraphLaunch_ptsz),
         H(cuMemAllocAsync), H(cuMemAllocAsync_ptsz), H(cuMemAllocFromPoolAsync), H(cuMemAllocFromPoolAsync_ptsz), H(cuMemFreeAsync),
-        H(cuMemFreeAsync_ptsz), H(cuMemCreate), H(cuMemRelease),
+        H(cuMemFreeAsync_ptsz), H(cuMemCreate), H(cuMemRelease), H(cuMemMap), H(cuMemUnmap),
         H(cuMemcpyHtoD_v2_ptds), H(cuMemcpyDtoH_v2_ptds), H(cuMemcpyDtoD_v2_ptds), H(cuMemcpy_ptds), H(cuMemcpyHtoDAsync_v2_ptsz),
         H(cuMemcpyDtoHAsync_v2_ptsz), H(cuMemcpyDtoDAsync_v2_ptsz), H(cuMemcpyAsync_ptsz), H(cuMemsetD8_v2_ptds), H(cuMemsetD16_v2_ptds),
         H(cuMemsetD32_v2_ptds), H(cuMemsetD8Async_ptsz), H(cuMemsetD16Async_ptsz), H(cuMemsetD32Async_ptsz),

@@ -156,6 +156,7 @@ void Runtime::on_fork_child() {
         std::lock_guard<std::mutex> g(table_mu_);
         table_.clear();
         phys_.clear();
+        vmaps_.clear();
     }
     for (auto &c : ctx_charged_) c = false;
     // engines and the limiter own streams, events and threads of the PARENT's contexts: drop them without running
@@ -893,7 +894,7 @@ CUresult Runtime::mem_create(CUmemGenericAllocationHandle *h, size_t bytes, cons
     CUresult r = d.cuMemCreate(h, bytes, prop, flags);
     if (r != CUDA_SUCCESS) { uncharge(dev, bytes); return r; }
     std::lock_guard<std::mutex> g(table_mu_);
-    phys_[*h] = Alloc{bytes, dev, AllocKind::Device};
+    phys_[*h] = PhysAlloc{bytes, dev, 0, false};
     return CUDA_SUCCESS;
 }
 
@@ -903,15 +904,51 @@ CUresult Runtime::mem_release(CUmemGenericAllocationHandle h) {
     if (!d.cuMemRelease) return CUDA_ERROR_NOT_SUPPORTED;
     CUresult r = d.cuMemRelease(h);
     if (!region_ || r != CUDA_SUCCESS) return r;
-    Alloc a;
+    PhysAlloc a;
     {
         std::lock_guard<std::mutex> g(table_mu_);
         auto it = phys_.find(h);
         if (it == phys_.end()) return r;                        // imported / retained handle, or coverage off
+        if (it->second.maps > 0) { it->second.released = true; return r; }   // still mapped: the memory stays, so does the charge
         a = it->second;
         phys_.erase(it);
     }
     uncharge(a.dev, a.size);
+    return r;
+}
+
+// cuMemMap / cuMemUnmap of the APPLICATION's own ranges (the swap engine calls the driver directly): only bookkeeping, so
+// that a handle released while mapped — the idiom of the CUDA VMM samples — keeps its charge until the last mapping goes.
+CUresult Runtime::mem_map(CUdeviceptr ptr, size_t size, size_t offset, CUmemGenericAllocationHandle h, unsigned long long flags) {
+    ensure_initialized();
+    const DriverTable &d = drv();
+    if (!d.cuMemMap) return CUDA_ERROR_NOT_SUPPORTED;
+    CUresult r = d.cuMemMap(ptr, size, offset, h, flags);
+    if (r != CUDA_SUCCESS || !region_) return r;
+    std::lock_guard<std::mutex> g(table_mu_);
+    auto it = phys_.find(h);
+    if (it == phys_.end()) return r;
+    it->second.maps++;
+    vmaps_[ptr] = {size, h};
+    return r;
+}
+
+CUresult Runtime::mem_unmap(CUdeviceptr ptr, size_t size) {
+    ensure_initialized();
+    const DriverTable &d = drv();
+    if (!d.cuMemUnmap) return CUDA_ERROR_NOT_SUPPORTED;
+    CUresult r = d.cuMemUnmap(ptr, size);
+    if (r != CUDA_SUCCESS || !region_) return r;
+    std::vector<PhysAlloc> gone;
+    {
+        std::lock_guard<std::mutex> g(table_mu_);
+        for (auto m = vmaps_.lower_bound(ptr); m != vmaps_.end() && m->first < ptr + size;) {
+            auto it = phys_.find(m->second.second);
+            if (it != phys_.end() && --it->second.maps <= 0 && it->second.released) { gone.push_back(it->second); phys_.erase(it); }
+            m = vmaps_.erase(m);
+        }
+    }
+    for (const PhysAlloc &a : gone) uncharge(a.dev, a.size);
     return r;
 }
 

@@ -83,6 +83,8 @@ class Runtime {
     CUresult mem_free_async(CUdeviceptr dptr, CUstream st, bool ptsz);
     CUresult mem_create(CUmemGenericAllocationHandle *h, size_t bytes, const CUmemAllocationProp *prop, unsigned long long flags);
     CUresult mem_release(CUmemGenericAllocationHandle h);
+    CUresult mem_map(CUdeviceptr ptr, size_t size, size_t offset, CUmemGenericAllocationHandle h, unsigned long long flags);
+    CUresult mem_unmap(CUdeviceptr ptr, size_t size);
     CUresult graph_launch(CUgraphExec g, CUstream st, bool ptsz);
     // check_oom() of the reference (oom_check(dev, 0)): used by host-alloc style hooks
     // cuModuleUnload: CUfunction handles of the module die with it; forget their cached parameter layouts
@@ -134,7 +136,11 @@ class Runtime {
 
     std::mutex table_mu_;                   // the reference's single allocator mutex (mutex@0x61180)
     std::map<CUdeviceptr, Alloc> table_;    // base -> alloc; ordered for range classification
-    std::map<CUmemGenericAllocationHandle, Alloc> phys_;   // cuMemCreate handles charged to the quota (same mutex)
+    // cuMemCreate handles charged to the quota (same mutex). The physical memory behind a handle lives until the handle is
+    // released AND its last mapping is gone (the CUDA samples release right after cuMemMap), so the charge does too.
+    struct PhysAlloc { size_t size; int dev; int maps; bool released; };
+    std::map<CUmemGenericAllocationHandle, PhysAlloc> phys_;
+    std::map<CUdeviceptr, std::pair<size_t, CUmemGenericAllocationHandle>> vmaps_;   // application cuMemMap ranges onto charged handles
 
     std::mutex swap_mu_;
     std::unique_ptr<SwapEngine> swap_[VGPU_MAX_DEVICES];

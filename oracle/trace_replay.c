@@ -81,6 +81,9 @@ extern CUresult cuMemAllocAsync(CUdeviceptr *, size_t, CUstream) __attribute__((
 extern CUresult cuMemFreeAsync(CUdeviceptr, CUstream) __attribute__((weak));
 extern CUresult cuMemCreate(unsigned long long *, size_t, const void *, unsigned long long) __attribute__((weak));
 extern CUresult cuMemRelease(unsigned long long) __attribute__((weak));
+extern CUresult cuMemAddressReserve(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) __attribute__((weak));
+extern CUresult cuMemMap(CUdeviceptr, size_t, size_t, unsigned long long, unsigned long long) __attribute__((weak));
+extern CUresult cuMemUnmap(CUdeviceptr, size_t) __attribute__((weak));
 extern CUresult cuGraphLaunch(void *, CUstream) __attribute__((weak));
 extern CUresult cuPointerGetAttributes(unsigned, int *, void **, CUdeviceptr) __attribute__((weak));
 /* NVML: bound to a preloaded hook's exported wrappers when there is one (the reference run preloads a dlsym shim that
@@ -219,7 +222,17 @@ int main(int argc, char **argv) {
         case 'Y': ptrs[a] = 0; r = cuMemAllocAsync ? cuMemAllocAsync(&ptrs[a], (size_t)b, NULL) : 801; if (r) ptrs[a] = 0; break;
         case 'Z': r = cuMemFreeAsync ? cuMemFreeAsync(ptrs[a], NULL) : 801; if (!r) ptrs[a] = 0; break;
         case 'C': { struct mem_prop pr; memset(&pr, 0, sizeof pr); pr.type = 1 /* PINNED */; pr.location.type = 1 /* DEVICE */; pr.location.id = 0;
-                    ptrs[a] = 0; r = cuMemCreate ? cuMemCreate(&ptrs[a], (size_t)b, &pr, 0) : 801; if (r) ptrs[a] = 0; break; }
+                    ptrs[a] = 0; r = cuMemCreate ? cuMemCreate(&ptrs[a], (size_t)b, &pr, 0) : 801; if (r) ptrs[a] = 0; else sizes[a] = (size_t)b; break; }
+        /* application-side VMM mappings: p s = map the handle of slot s into its window of a reserved range, u s = unmap it
+         * (the handle may have been released in between: the CUDA samples release right after mapping) */
+        case 'p': case 'u': {
+            static CUdeviceptr vbase; static size_t vsz[64]; const size_t stride = (size_t)256 << 20; unsigned k = (unsigned)a & 63;
+            r = 801;
+            if (!cuMemAddressReserve || !cuMemMap || !cuMemUnmap) break;
+            if (!vbase && (r = cuMemAddressReserve(&vbase, 64 * stride, 0, 0, 0))) break;
+            if (op == 'p') { r = ptrs[a] ? cuMemMap(vbase + k * stride, sizes[a], 0, ptrs[a], 0) : 1; if (!r) vsz[k] = sizes[a]; }
+            else { r = vsz[k] ? cuMemUnmap(vbase + k * stride, vsz[k]) : 1; if (!r) vsz[k] = 0; }
+            break; }
         case 'R': r = cuMemRelease ? cuMemRelease(ptrs[a]) : 801; if (!r) ptrs[a] = 0; break;
         case 'G': r = cuGraphLaunch ? cuGraphLaunch(NULL, NULL) : 801; break;
         case 'N': { static void *nv; static int (*init)(void), (*byidx)(unsigned, void **), (*meminfo)(void *, void *);

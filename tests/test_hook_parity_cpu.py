@@ -198,6 +198,24 @@ def test_pointer_queries_match_the_reference_binary(tmp_path):
     assert [l.split(" type=")[0] for l in new] == [l.split(" type=")[0] for l in ref]   # accounting identical either way
 
 
+@pytest.mark.parametrize("exec_mode", ["0", "1"])
+def test_a_vmm_handle_released_while_mapped_stays_charged_until_unmapped(tmp_path, exec_mode):
+    """The idiom of the CUDA VMM samples: cuMemCreate, cuMemMap, cuMemRelease at once — the mapping keeps the physical
+    memory alive, so the charge must live as long (an application could otherwise hold any amount of HBM off the books).
+    Other orders: unmap then release (uncharged at the release), release of a never-mapped handle (at once)."""
+    t = _write(tmp_path, "C 0 67108864\np 0\nR 0\nI\nu 0\nI\nC 1 33554432\np 1\nu 1\nI\nR 1\nI\nC 2 16777216\nR 2\nI\nC 3 1073741824\n")
+    env = _env(tmp_path, None, CUDA_DEVICE_MEMORY_LIMIT="1g", FAKE_GPU_CTX_MIB="100", FAKE_GPU_EXEC=exec_mode)
+    out = run_replay(t, "new", env).splitlines()
+    buf = [int(l.split(" buf=")[1].split()[0]) for l in out[1:]]
+    assert [l.split(" rc=")[1].split()[0] for l in out[1:-1]] == ["0"] * 15
+    assert buf[:15] == [64 << 20, 64 << 20, 64 << 20, 64 << 20, 0, 0, 32 << 20, 32 << 20, 32 << 20, 32 << 20, 0, 0, 16 << 20, 0, 0]
+    assert " rc=2 " in out[-1] and buf[-1] == 0                                     # 1 GiB more than the quota has left: refused
+    if have_reference():                                                            # the reference does not account cuMemCreate at all
+        ref = run_replay(t, "reference", dict(env, FAKE_GPU_EXEC="0", CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "ref.cache"))).splitlines()
+        same = run_replay(t, "new", dict(env, FAKE_GPU_EXEC="0", VGPU_REFERENCE_COVERAGE="1", CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "cov.cache"))).splitlines()
+        assert same == ref and all(" buf=0 " in l for l in ref)
+
+
 def test_reference_coverage_switch_restores_the_reference_blind_spots(tmp_path):
     t = _write(tmp_path, _WIDE_TRACE)
     env = _env(tmp_path, "64m", FAKE_GPU_CTX_MIB="16", VGPU_REFERENCE_COVERAGE="1")
