@@ -216,6 +216,50 @@ def test_a_vmm_handle_released_while_mapped_stays_charged_until_unmapped(tmp_pat
         assert same == ref and all(" buf=0 " in l for l in ref)
 
 
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_vmm_accounting_follows_a_model_over_random_sequences(tmp_path, seed):
+    """Random create / map / unmap / release sequences (remaps of a released handle's window excluded: the handle is gone)
+    against the rule: a handle is charged from its creation until it has been released AND has no mapping left; a creation
+    that would cross the quota is refused with CUDA_ERROR_OUT_OF_MEMORY and changes nothing."""
+    import random
+    rng = random.Random(seed)
+    M = 1 << 20
+    limit, ctx = 512 * M, 100 * M
+    lines, expect = [], []
+    size, mapped, released = {}, set(), set()
+    charged = lambda: sum(n for s_, n in size.items() if s_ not in released or s_ in mapped)
+    for _ in range(300):
+        slots = list(range(24))
+        free_slots = [s_ for s_ in slots if s_ not in size]
+        live = [s_ for s_ in size if s_ not in released]
+        r = rng.random()
+        if r < 0.35 and free_slots:
+            s_ = rng.choice(free_slots); n = rng.choice([2, 8, 32, 64, 128]) * M
+            lines.append(f"C {s_} {n}")
+            if ctx + charged() + n > limit:
+                expect.append((2, charged()))
+            else:
+                size[s_] = n; expect.append((0, charged()))
+        elif r < 0.6 and [s_ for s_ in live if s_ not in mapped]:
+            s_ = rng.choice([s_ for s_ in live if s_ not in mapped]); lines.append(f"p {s_}"); mapped.add(s_); expect.append((0, charged()))
+        elif r < 0.8 and mapped:
+            s_ = rng.choice(sorted(mapped)); lines.append(f"u {s_}"); mapped.discard(s_)
+            if s_ in released:
+                del size[s_]; released.discard(s_)
+            expect.append((0, charged()))
+        elif live:
+            s_ = rng.choice(live); lines.append(f"R {s_}"); released.add(s_)
+            if s_ not in mapped:
+                del size[s_]; released.discard(s_)
+            expect.append((0, charged()))
+    t = _write(tmp_path, "\n".join(lines) + "\n")
+    out = run_replay(t, "new", _env(tmp_path, None, CUDA_DEVICE_MEMORY_LIMIT=str(limit), FAKE_GPU_CTX_MIB="100")).splitlines()[1:]
+    got = [(int(l.split(" rc=")[1].split()[0]), int(l.split(" buf=")[1].split()[0])) for l in out]
+    bad = [(i, lines[i], g, e) for i, (g, e) in enumerate(zip(got, expect)) if g != e]
+    assert not bad and len(got) == len(expect), bad[:5]
+    assert any(rc == 2 for rc, _ in got) and max(b for _, b in got) > 256 * M
+
+
 def test_reference_coverage_switch_restores_the_reference_blind_spots(tmp_path):
     t = _write(tmp_path, _WIDE_TRACE)
     env = _env(tmp_path, "64m", FAKE_GPU_CTX_MIB="16", VGPU_REFERENCE_COVERAGE="1")
