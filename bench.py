@@ -114,6 +114,12 @@ def choose_workload(n_ranks):
     return nbuf, over
 
 
+def workload_name(nbuf, over):
+    """config.workload — one string for both arms (the reference arm times a bounded sample of the same workload)."""
+    return (f"{nbuf}x{BUF_MIB}MiB alloc+touch loop, {QUOTA_MIB}MiB gpumem quota, {over >> 30} GiB oversubscribed, cyclic RMW touch, "
+            f"step={TOUCHES_PER_STEP} touches")
+
+
 def measure_link(torch, barrier=None, concurrent=False):
     """Pinned-memcpy bandwidth of this box (the end-to-end roofline): 1 GiB, each direction and both at once. Alone
     (N=1): best of 5. With several ranks every copy starts behind a barrier, so all GPUs pull on the host at the same
@@ -300,7 +306,11 @@ def reference_arm(args):
     free_b, total_b = torch.cuda.mem_get_info(0)
     ballast_mib = max(0, (free_b - QUOTA_MIB * MiB - 1536 * MiB) // MiB)
     nbuf = (QUOTA_MIB + 8192) // BUF_MIB            # 8 GiB resident + 8 GiB oversubscribed: bounded sample
-    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    # exactly the K timed steps and W warm-up steps asked for (a step = 16 touches of 64 MiB, ~0.1 s under UVM on this class
+    # of box); only absurd requests are clamped, and the line says what ran
+    steps, warmup = max(1, min(args.steps, 256)), max(1, min(args.warmup, 16))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    full_nbuf, full_over = choose_workload(world)
     kind, res, note = "reference", None, ""
     if os.path.exists(os.path.join(OREF, "libvgpu.so")):
         holder = None
@@ -314,7 +324,7 @@ def reference_arm(args):
                 if line.startswith("READY"):
                     break
             p = spawn_app(0, nbuf, steps, warmup, "refhook", False, ballast_mib=0)
-            res = finish_app(p, False, lambda: None, timeout=240)
+            res = finish_app(p, False, lambda: None, timeout=240 + 2 * steps)
             if res["event_ms"] / max(res["steps"], 1) < 0.5 * BUF_MIB * MiB / 60e6:   # faster than the link allows: nothing was paged
                 raise RuntimeError("no paging happened under the reference hook")
             note = ("lib/nvidia/libvgpu.so binary preloaded (oracle/dlsym_shim.so first; CUDA_OVERSUBSCRIBE=true -> cuMemAllocManaged); "
@@ -337,11 +347,12 @@ def reference_arm(args):
     touched = res["steps"] * BUF_MIB * MiB
     gbs = 2 * touched / (res["event_ms"] / 1e3) / 1e9   # cyclic + RMW: every touch misses, and evicts a dirty buffer
     line = {
-        "metric": "vmem_swap_GBps", "value": round(gbs, 3), "unit": "GB/s", "impl": "reference", "n_gpus": 1,
+        "metric": "vmem_swap_GBps", "value": round(gbs, 3), "unit": "GB/s", "impl": "reference", "n_gpus": world,
         "steps": steps, "warmup": warmup, "ms_per_step": round(res["event_ms"] / steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"uvm-oversubscribed alloc+touch, {nbuf}x{BUF_MIB}MiB over {QUOTA_MIB}MiB resident (ballast {ballast_mib} MiB), cyclic RMW",
-                   "inputs": "larger than L2"},
+        "config": {"workload": workload_name(full_nbuf, full_over), "inputs": "larger than L2 (each step streams 1 GiB in + 1 GiB out)",
+                   "parallelism": f"rank 0 of {world} (host-side paging by the UVM driver: one measurement per box)",
+                   "sample": f"bounded: {nbuf}x{BUF_MIB}MiB managed buffers over {QUOTA_MIB}MiB of physical memory (ballast {ballast_mib} MiB), same cyclic RMW touch"},
         "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": os.cpu_count(), "kind": kind,
                          "sample": f"{steps * TOUCHES_PER_STEP} touches of {BUF_MIB} MiB; paging by the UVM driver's fault threads on host cores + copy engines; {note}"},
         "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -469,7 +480,7 @@ def main():
             "metric": "vmem_swap_GBps", "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(t_max / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"{nbuf}x{BUF_MIB}MiB alloc+touch loop, {QUOTA_MIB}MiB gpumem quota, {over >> 30} GiB oversubscribed, cyclic RMW touch, step={TOUCHES_PER_STEP} touches",
+            "config": {"workload": workload_name(nbuf, over),
                        "inputs": "larger than L2 (each step streams 1 GiB in + 1 GiB out)", "parallelism": f"replicas x{world}", "numa_node": numa},
             "e2e": {"value": round(e2e_value, 3), "unit": "GB/s",
                     "h2d_bytes_per_step": int(e2e["page_in_bytes"] // args.steps), "d2h_bytes_per_step": int(e2e["page_out_bytes"] // args.steps),
