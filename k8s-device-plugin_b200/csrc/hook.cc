@@ -450,9 +450,13 @@ VGPU_EXPORT CUresult cuGetProcAddress(const char *symbol, void **pfn, int cudaVe
 // dlsym(handle, "cu..."), which never consults LD_PRELOAD order — so the lookup itself is intercepted.
 #ifndef VGPU_NO_DLSYM_OVERRIDE   // (sanitizer builds leave it out: the sanitizer runtime calls dlsym before its shadow memory exists)
 VGPU_EXPORT void *dlsym(void *handle, const char *symbol) {
-    if (symbol && !control_disabled() && ((symbol[0] == 'c' && symbol[1] == 'u') || !std::strncmp(symbol, "nvml", 4))) {
-        if (void *h = find_hook_exact(symbol)) return h;
+    // glibc declares the name parameter nonnull, which lets the compiler drop a plain NULL test; callers do pass NULL
+    // (and expect the real dlsym's error), so the test goes through a volatile copy
+    const char *volatile seen = symbol;
+    const char *name = seen;
+    if (name && !control_disabled() && ((name[0] == 'c' && name[1] == 'u') || !std::strncmp(name, "nvml", 4))) {
+        if (void *h = find_hook_exact(name)) return h;
     }
-    return vgpu::real_dlsym(handle, symbol);
+    return vgpu::real_dlsym(handle, name);
 }
 #endif

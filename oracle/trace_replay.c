@@ -199,8 +199,11 @@ int main(int argc, char **argv) {
                     break; }
         /* context family: B n = retain device n's primary context once more; E s n = cuCtxCreate_v2 on device n into
          * slot s (becomes current); H s = make slot s current; e s = destroy slot s */
-        case 'B': { CUcontext t = NULL; CUdevice d2; r = cuDeviceGet(&d2, (int)a & 15); if (!r) r = cuDevicePrimaryCtxRetain(&t, d2);
-                    if (!r && !ctxs[a & 15]) ctxs[a & 15] = t; break; }
+        case 'B': { CUcontext t = NULL; CUdevice d2;
+                    r = cuDeviceGet(&d2, (int)a & 15);
+                    if (!r) r = cuDevicePrimaryCtxRetain(&t, d2);
+                    if (!r && !ctxs[a & 15]) ctxs[a & 15] = t;
+                    break; }
         case 'E': { CUdevice d2; r = cuDeviceGet(&d2, (int)b & 15); if (!r) r = cuCtxCreate_v2(&uctx[a & 15], 0, d2);
                     if (!r) { udev[a & 15] = (int)b & 15; cur = (int)b & 15; dev = d2; } break; }
         case 'H': r = uctx[a & 15] ? cuCtxSetCurrent(uctx[a & 15]) : 1; if (!r) { cur = udev[a & 15]; dev = cur; } break;
