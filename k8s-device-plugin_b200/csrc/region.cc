@@ -350,14 +350,26 @@ uint64_t Region::usage(int dev) {
     return u;
 }
 
-int Region::reap_dead_locked() {
+// init_proc_slot_withlock@0x43d89 ends with clear_proc_slot_nolock(pid, 1)@0x43f42: every process that joins the container
+// through the hook sweeps the slots of processes that died without their exit handler (SIGKILL, crash) — their bytes stop
+// counting against the quota as soon as a sibling starts, not only at the next quota breach (rm_quitted_process). Same
+// compaction (last slot moved into the hole), so the caller's own slot may move. Called by the hook's initialisation
+// right after claim_slot(); host tools that claim slots on behalf of other pids (vgpu_region_claim) do not sweep.
+int Region::sweep_dead(int32_t keep) {
+    lock();
+    int n = reap_dead_locked(keep);
+    unlock();
+    return n;
+}
+
+int Region::reap_dead_locked(int32_t keep) {
     // rm_quitted_process@0x41a8e runs `ps ax` through popen on every quota breach; /proc/<pid> answers the same
     // question without forking a shell from inside a CUDA allocation call.
     int reaped = 0;
     int32_t self = getpid();
     for (int i = 0; i < r_->proc_num;) {
         int32_t p = r_->procs[i].pid;
-        if (p != self && !pid_alive(p)) {
+        if (p != self && p != keep && !pid_alive(p)) {
             clear_swap_records_locked(p);
             int last = r_->proc_num - 1;
             if (i != last) std::memcpy(&r_->procs[i], &r_->procs[last], sizeof(vgpu_proc_slot_t));

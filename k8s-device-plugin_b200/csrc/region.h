@@ -53,7 +53,8 @@ class Region {
     void add(int32_t pid, int dev, uint64_t bytes, int type) { try_add(pid, dev, bytes, type, false); }
     void sub(int32_t pid, int dev, uint64_t bytes, int type);  // rm_gpu_device_memory_usage@0x42de1
     // drop slots whose pid no longer exists; returns how many were reclaimed (lock must be held)
-    int reap_dead_locked();
+    int reap_dead_locked(int32_t keep = 0);
+    int sweep_dead(int32_t keep = 0);        // lock + reap_dead_locked: what a joining process does (clear_proc_slot_nolock@0x43bf4)
 
     // extension block (vgpu_region.h): nullptr when the file has none and cannot be grown
     vgpu_region_ext_t *ext() { return ext_; }

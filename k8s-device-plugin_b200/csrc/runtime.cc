@@ -118,6 +118,7 @@ bool Runtime::ensure_initialized() {
     } else {
         region_.reset(R);
         if (region_->claim_slot(pid_) < 0) LOG_ERROR("no free process slot in %s", cfg_.region_path.c_str());
+        region_->sweep_dead(pid_);          // init_proc_slot_withlock@0x43d89 -> clear_proc_slot_nolock: a joining process drops dead siblings' slots
         std::atexit(atexit_trampoline);
         pthread_atfork(nullptr, nullptr, atfork_child_trampoline);
     }
@@ -164,7 +165,7 @@ void Runtime::on_fork_child() {
     for (auto &e : swap_) (void)e.release();
     (void)limiter_.release();
     post_inited_.store(false, std::memory_order_release);
-    if (region_) region_->claim_slot(pid_);
+    if (region_) { region_->claim_slot(pid_); region_->sweep_dead(pid_); }
 }
 
 int Runtime::current_device() {

@@ -157,6 +157,8 @@ int main(int argc, char **argv) {
     uint64_t c[5];
     counters(0, c);
     printf("init rc=0 ctx=%lu mod=%lu buf=%lu off=%lu tot=%lu region=%d\n", c[0], c[1], c[2], c[3], c[4], g_region != NULL);
+    const int flush_each = getenv("TRACE_FLUSH") != NULL;   /* op-by-op driving over pipes (tests/tools/multiproc_fuzz.py) */
+    if (flush_each) fflush(stdout);
 
     char line[256];
     unsigned long opn = 0;
@@ -270,6 +272,7 @@ int main(int argc, char **argv) {
         }
         if (has_nv) printf(" nv_total=%llu nv_free=%llu nv_used=%llu", nvmem[0], nvmem[1], nvmem[2]);
         putchar('\n');
+        if (flush_each) fflush(stdout);
         opn++;
     }
     cuCtxSynchronize();

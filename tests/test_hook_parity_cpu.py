@@ -574,3 +574,20 @@ def test_monitor_handshake_words_after_launches_match_the_reference(tmp_path, ex
     new = run_replay(t, "new", env).splitlines()
     ref = run_replay(t, "reference", dict(env, CUDA_DEVICE_MEMORY_SHARED_CACHE=str(tmp_path / "ref.cache"))).splitlines()
     assert new == ref and " rk=2 " in new[1]
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_processes_of_one_container_driven_op_by_op_match_the_reference(tmp_path, seed):
+    """tests/tools/multiproc_fuzz.py: up to four processes of one container (one region file) are driven op by op over pipes,
+    so the interleaving is identical under both hooks — random allocations / frees / queries, normal exits, SIGKILLs and
+    respawns under a limit that is crossed often. Return codes and the container-wide counters agree after every op. This
+    is the test that showed the reference sweeping dead processes' slots whenever a process JOINS
+    (init_proc_slot_withlock -> clear_proc_slot_nolock), not only on a quota breach."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mpfuzz", os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "multiproc_fuzz.py"))
+    mp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mp)
+    sched, res, diffs = mp.compare(seed, str(tmp_path))
+    assert not diffs and len(res["new"]) == len(res["reference"]) == len(sched), diffs[:3]
+    assert any(a == "kill" for _, a in sched) and any(" rc=-1 " in l for l in res["new"])     # kills and quota breaches happened
