@@ -3,7 +3,7 @@ over pipes by this coordinator, so the interleaving is exactly the same under th
 no wall-clock schedule. Random allocations / frees / queries in up to four concurrent processes, normal exits (exit
 handler), SIGKILLs (slot left behind, reclaimed by a sibling's next quota breach — rm_quitted_process) and respawns, under
 a limit that is crossed often. Every output line (return code + the container-wide counter words) must be identical.
-    python tests/tools/multiproc_fuzz.py <first seed> <last seed>        (build container: needs oracle/_ref/libvgpu.so)"""
+    python tests/tools/multiproc_fuzz.py <first seed> <last seed> [wide]  (build container: needs oracle/_ref/libvgpu.so)"""
 import os
 import random
 import signal
@@ -17,7 +17,7 @@ from conftest import FAKE, HOOK_SO, OREF, REF_SO, SHIM_SO  # noqa: E402
 M = 1 << 20
 
 
-def gen(seed, nsteps=260, nproc=4):
+def gen(seed, nsteps=260, nproc=4, wide=False):
     """The schedule: (slot, action) pairs; action is a trace line, "spawn", "exit" or "kill"."""
     rng = random.Random(seed)
     sched, alive, live, nid = [], set(), {}, 0
@@ -38,6 +38,8 @@ def gen(seed, nsteps=260, nproc=4):
             live[s].append(nid); nid += 1
         elif r < 0.80 and live[s]:
             sched.append((s, f"F {live[s].pop(rng.randrange(len(live[s])))}"))
+        elif r < 0.84 and wide:
+            sched.append((s, rng.choice([f"D {rng.randrange(3)}", f"B {rng.randrange(3)}", f"E {rng.randrange(8)} {rng.randrange(3)}", "N", "h 4096", "m"])))
         elif r < 0.88:
             sched.append((s, "I"))
         elif r < 0.92:
@@ -49,10 +51,11 @@ def gen(seed, nsteps=260, nproc=4):
     return sched
 
 
-def run(mode, sched, cache, limit="160m"):
+def run(mode, sched, cache, limit="160m", extra=None):
     env = {"PATH": os.environ.get("PATH", ""), "LD_LIBRARY_PATH": FAKE, "LIBCUDA_LOG_LEVEL": "0", "TRACE_FLUSH": "1", "FAKE_GPU_CTX_MIB": "16",
            "CUDA_DEVICE_MEMORY_LIMIT_0": limit, "CUDA_DEVICE_MEMORY_SHARED_CACHE": cache,
            "LD_PRELOAD": HOOK_SO if mode == "new" else SHIM_SO + ":" + REF_SO}
+    env.update(extra or {})
     os.makedirs("/tmp/vgpulock", exist_ok=True)
     procs, out = {}, []
     try:
@@ -80,14 +83,16 @@ def run(mode, sched, cache, limit="160m"):
     return out
 
 
-def compare(seed, workdir):
-    sched = gen(seed)
+def compare(seed, workdir, wide=False):
+    """wide: three GPUs with their own limits, device switches, context creation, NVML queries and host-side calls mixed in."""
+    sched = gen(seed, wide=wide)
+    extra = {"FAKE_GPU_COUNT": "3", "CUDA_DEVICE_MEMORY_LIMIT_1": "96m", "CUDA_DEVICE_MEMORY_LIMIT_2": "300m"} if wide else None
     res = {}
     for mode in ("new", "reference"):
         cache = os.path.join(workdir, f"{mode}.cache")
         if os.path.exists(cache):
             os.remove(cache)
-        res[mode] = run(mode, sched, cache)
+        res[mode] = run(mode, sched, cache, extra=extra)
     diffs = [(i, sched[i], a, b) for i, (a, b) in enumerate(zip(res["new"], res["reference"])) if a != b]
     return sched, res, diffs
 
@@ -95,8 +100,9 @@ def compare(seed, workdir):
 if __name__ == "__main__":
     work = tempfile.mkdtemp(prefix="vgpu_mpfuzz_")
     bad = 0
+    wide = len(sys.argv) > 3 and sys.argv[3] == "wide"
     for seed in range(int(sys.argv[1]), int(sys.argv[2])):
-        sched, res, diffs = compare(seed, work)
+        sched, res, diffs = compare(seed, work, wide)
         if diffs or len(res["new"]) != len(res["reference"]):
             bad += 1
             i, act, a, b = diffs[0] if diffs else (-1, None, len(res["new"]), len(res["reference"]))
