@@ -579,6 +579,10 @@ def test_monitor_handshake_words_after_launches_match_the_reference(tmp_path, ex
 @pytest.mark.skipif(not have_reference(), reason="reference binary only exists in the build container")
 @pytest.mark.parametrize("seed,wide", [(1, False), (2, False), (3, False), (4, True), (5, True)])
 def test_processes_of_one_container_driven_op_by_op_match_the_reference(tmp_path, seed, wide):
+    _driven_op_by_op(tmp_path, seed, wide, mixed=(seed % 2 == 1))    # odd seeds also run a MIXED container (new + reference processes)
+
+
+def _driven_op_by_op(tmp_path, seed, wide, mixed):
     """tests/tools/multiproc_fuzz.py: up to four processes of one container (one region file) are driven op by op over pipes,
     so the interleaving is identical under both hooks — random allocations / frees / queries, normal exits, SIGKILLs and
     respawns under a limit that is crossed often. Return codes and the container-wide counters agree after every op. This
@@ -588,6 +592,6 @@ def test_processes_of_one_container_driven_op_by_op_match_the_reference(tmp_path
     spec = importlib.util.spec_from_file_location("mpfuzz", os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "multiproc_fuzz.py"))
     mp = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mp)
-    sched, res, diffs = mp.compare(seed, str(tmp_path), wide)      # wide: three GPUs, device switches, contexts, NVML and host-side calls too
+    sched, res, diffs = mp.compare(seed, str(tmp_path), wide, mixed)      # wide: three GPUs, device switches, contexts, NVML and host-side calls too
     assert not diffs and len(res["new"]) == len(res["reference"]) == len(sched), diffs[:3]
     assert any(a == "kill" for _, a in sched) and any(" rc=-1 " in l for l in res["new"])     # kills and quota breaches happened

@@ -3,7 +3,7 @@ over pipes by this coordinator, so the interleaving is exactly the same under th
 no wall-clock schedule. Random allocations / frees / queries in up to four concurrent processes, normal exits (exit
 handler), SIGKILLs (slot left behind, reclaimed by a sibling's next quota breach — rm_quitted_process) and respawns, under
 a limit that is crossed often. Every output line (return code + the container-wide counter words) must be identical.
-    python tests/tools/multiproc_fuzz.py <first seed> <last seed> [wide]  (build container: needs oracle/_ref/libvgpu.so)"""
+    python tests/tools/multiproc_fuzz.py <first seed> <last seed> [wide] [mixed]  (build container: needs oracle/_ref/libvgpu.so)"""
 import os
 import random
 import signal
@@ -56,13 +56,15 @@ def run(mode, sched, cache, limit="160m", extra=None):
            "CUDA_DEVICE_MEMORY_LIMIT_0": limit, "CUDA_DEVICE_MEMORY_SHARED_CACHE": cache,
            "LD_PRELOAD": HOOK_SO if mode == "new" else SHIM_SO + ":" + REF_SO}
     env.update(extra or {})
+    # mode "mixed": a container whose even process slots run under the new hook and odd ones under the reference binary
+    preload = lambda slot: (HOOK_SO if slot % 2 == 0 else SHIM_SO + ":" + REF_SO) if mode == "mixed" else env["LD_PRELOAD"]
     os.makedirs("/tmp/vgpulock", exist_ok=True)
     procs, out = {}, []
     try:
         for s, act in sched:
             if act == "spawn":
                 p = subprocess.Popen([os.path.join(OREF, "trace_replay"), "/dev/stdin"], stdin=subprocess.PIPE, stdout=subprocess.PIPE,
-                                     stderr=subprocess.DEVNULL, env=env, text=True, bufsize=1)
+                                     stderr=subprocess.DEVNULL, env=dict(env, LD_PRELOAD=preload(s)), text=True, bufsize=1)
                 procs[s] = p
                 out.append(f"[{s}] " + p.stdout.readline().rstrip("\n"))
             elif act == "exit":
@@ -83,26 +85,28 @@ def run(mode, sched, cache, limit="160m", extra=None):
     return out
 
 
-def compare(seed, workdir, wide=False):
+def compare(seed, workdir, wide=False, mixed=False):
     """wide: three GPUs with their own limits, device switches, context creation, NVML queries and host-side calls mixed in."""
     sched = gen(seed, wide=wide)
     extra = {"FAKE_GPU_COUNT": "3", "CUDA_DEVICE_MEMORY_LIMIT_1": "96m", "CUDA_DEVICE_MEMORY_LIMIT_2": "300m"} if wide else None
     res = {}
-    for mode in ("new", "reference"):
+    for mode in ("new", "reference") + (("mixed",) if mixed else ()):
         cache = os.path.join(workdir, f"{mode}.cache")
         if os.path.exists(cache):
             os.remove(cache)
         res[mode] = run(mode, sched, cache, extra=extra)
     diffs = [(i, sched[i], a, b) for i, (a, b) in enumerate(zip(res["new"], res["reference"])) if a != b]
+    if mixed:       # a mixed container must behave like an all-reference one as well
+        diffs += [(i, sched[i], a, b) for i, (a, b) in enumerate(zip(res["mixed"], res["reference"])) if a != b]
     return sched, res, diffs
 
 
 if __name__ == "__main__":
     work = tempfile.mkdtemp(prefix="vgpu_mpfuzz_")
     bad = 0
-    wide = len(sys.argv) > 3 and sys.argv[3] == "wide"
+    wide, mixed = "wide" in sys.argv[3:], "mixed" in sys.argv[3:]
     for seed in range(int(sys.argv[1]), int(sys.argv[2])):
-        sched, res, diffs = compare(seed, work, wide)
+        sched, res, diffs = compare(seed, work, wide, mixed)
         if diffs or len(res["new"]) != len(res["reference"]):
             bad += 1
             i, act, a, b = diffs[0] if diffs else (-1, None, len(res["new"]), len(res["reference"]))
