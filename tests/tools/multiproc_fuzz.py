@@ -56,6 +56,8 @@ def run(mode, sched, cache, limit="160m", extra=None):
            "CUDA_DEVICE_MEMORY_LIMIT_0": limit, "CUDA_DEVICE_MEMORY_SHARED_CACHE": cache,
            "LD_PRELOAD": HOOK_SO if mode == "new" else SHIM_SO + ":" + REF_SO}
     env.update(extra or {})
+    for kv in filter(None, os.environ.get("MPFUZZ_ENV", "").split(",")):      # e.g. MPFUZZ_ENV=CUDA_OVERSUBSCRIBE=true,VGPU_SWAP_LIMIT_MODE=virtual,FAKE_GPU_EXEC=1
+        k, _, val = kv.partition("="); env[k] = val
     # mode "mixed": a container whose even process slots run under the new hook and odd ones under the reference binary
     preload = lambda slot: (HOOK_SO if slot % 2 == 0 else SHIM_SO + ":" + REF_SO) if mode == "mixed" else env["LD_PRELOAD"]
     os.makedirs("/tmp/vgpulock", exist_ok=True)
