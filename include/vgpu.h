@@ -115,17 +115,28 @@ typedef struct vgpu_swap_config {
     uint64_t chunk_bytes;      /* staging slot size; 0 = 32 MiB */
     uint32_t ring_slots;       /* staging slots per direction; 0 = 4 */
     uint32_t profile;          /* 1 = time pack/unpack launches with events */
+    uint64_t prefetch_bytes;   /* how far the pager runs ahead of the application; 0 = default (VGPU_SWAP_PREFETCH_MB), ~0 = off */
+    uint64_t copy_bytes;       /* piece size of the direct DMA copies; 0 = default (VGPU_SWAP_COPY_MB) */
 } vgpu_swap_config_t;
 typedef struct vgpu_swap_stats {
     uint64_t page_out_bytes, page_in_bytes, evictions, faults, admissions;
     uint64_t pack_launches, unpack_launches, scan_launches, scans;
     uint64_t resident_bytes, live_bytes, host_bytes, entries, phys_creates, phys_reuses;
-    uint64_t pack_bytes, unpack_bytes;
+    uint64_t pack_bytes, unpack_bytes;         /* bytes moved by the staged path's TMA kernels */
     double pack_ms, unpack_ms;
     uint64_t scan_cache_hits;   /* evictions served from the previous scan's surplus (no new scan) */
-    /* calling-thread time inside admissions (ns): total, victim scan, wait for last pack, VMM calls, ring back-pressure */
-    uint64_t host_admit_ns, host_scan_ns, host_packsync_ns, host_vmm_ns, host_ring_ns;
+    /* APPLICATION-thread time inside admissions (ns): total, blocked until the pager had issued the page-in, and inside VMM
+     * calls (zero by construction: the pager thread owns them) */
+    uint64_t host_admit_ns, host_wait_ns, host_vmm_ns;
+    /* pager-thread time (ns): VMM calls, victim scans, waiting for the last pack of a staged batch, staging back-pressure,
+     * all steps that made progress; and the number of cuMemUnmap + cuMemSetAccess calls after batching */
+    uint64_t pager_vmm_ns, pager_scan_ns, pager_packsync_ns, pager_ring_ns, pager_busy_ns, vmm_calls;
     double pack_span_ms, unpack_span_ms;   /* exact in-kernel %globaltimer execution spans (profiling), valid after vgpu_swap_drain */
+    uint64_t direct_out_bytes, direct_in_bytes;   /* bytes moved by plain DMA between a buffer's own range and its pinned block */
+    uint64_t prefetch_issued, prefetch_hits, prefetch_wasted;   /* rows paged in ahead of need / touched afterwards / evicted untouched */
+    uint64_t demand_waits;      /* admissions that had to block for the pager */
+    uint64_t clean_evictions;   /* evictions without a copy (pinned block still valid) */
+    uint64_t host_slabs, host_slabs_local;   /* pinned slabs allocated / of those on the GPU's NUMA node */
 } vgpu_swap_stats_t;
 int vgpu_swap_create(int dev, const vgpu_swap_config_t *cfg, vgpu_swap_t **out);
 void vgpu_swap_destroy(vgpu_swap_t *s);
@@ -134,6 +145,12 @@ int vgpu_swap_free(vgpu_swap_t *s, uint64_t dptr);
 /* make the buffers containing ptrs[] resident and order `stream` behind the page-ins; pair with vgpu_swap_release */
 int vgpu_swap_acquire(vgpu_swap_t *s, const uint64_t *ptrs, int n, void *stream);
 int vgpu_swap_release(vgpu_swap_t *s, const uint64_t *ptrs, int n, void *stream);
+/* like vgpu_swap_release for work that only READ the buffers (they stay clean: evicting them later needs no copy) */
+int vgpu_swap_release_ro(vgpu_swap_t *s, const uint64_t *ptrs, int n, void *stream);
+/* cuMemAdvise(SET/UNSET_READ_MOSTLY) for a swappable buffer: kernel launches no longer mark it dirty */
+int vgpu_swap_advise_read_mostly(vgpu_swap_t *s, uint64_t ptr, int on);
+/* keep a buffer resident for good (operands the argument scan cannot see: device-side pointer tables) */
+int vgpu_swap_pin(vgpu_swap_t *s, uint64_t ptr, int on);
 int vgpu_swap_stats(vgpu_swap_t *s, vgpu_swap_stats_t *out);
 int vgpu_swap_drain(vgpu_swap_t *s);
 int vgpu_swap_table(vgpu_swap_t *s, vgpu_entry_t *out, uint32_t cap, uint32_t *n);
@@ -154,6 +171,7 @@ int vgpu_limiter_stats(vgpu_limiter_t *l, vgpu_limiter_stats_t *out);
 int vgpu_runtime_swap_stats(int dev, vgpu_swap_stats_t *out);       /* nonzero when no engine exists on dev */
 int vgpu_runtime_limiter_stats(vgpu_limiter_stats_t *out);
 int vgpu_runtime_set_swap_profile(int dev, int on);
+int vgpu_runtime_swap_pin(uint64_t dptr, int on);                     /* vgpu_swap_pin on the hook's engine of the current device */
 uint64_t vgpu_runtime_context_size(void);
 int vgpu_runtime_check_memory_type(uint64_t dptr);                    /* check_memory_type@0x407f2: 2 tracked, 1 not */
 

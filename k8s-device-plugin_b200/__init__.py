@@ -54,7 +54,8 @@ class Entry(C.Structure):
 
 class SwapConfig(C.Structure):
     _fields_ = [("resident_cap", C.c_uint64), ("virtual_cap", C.c_uint64), ("host_pool_cap", C.c_uint64),
-                ("chunk_bytes", C.c_uint64), ("ring_slots", C.c_uint32), ("profile", C.c_uint32)]
+                ("chunk_bytes", C.c_uint64), ("ring_slots", C.c_uint32), ("profile", C.c_uint32),
+                ("prefetch_bytes", C.c_uint64), ("copy_bytes", C.c_uint64)]
 
 
 class SwapStats(C.Structure):
@@ -62,8 +63,11 @@ class SwapStats(C.Structure):
         "page_out_bytes", "page_in_bytes", "evictions", "faults", "admissions", "pack_launches", "unpack_launches",
         "scan_launches", "scans", "resident_bytes", "live_bytes", "host_bytes", "entries", "phys_creates",
         "phys_reuses", "pack_bytes", "unpack_bytes")] + [("pack_ms", C.c_double), ("unpack_ms", C.c_double)] + [(n, C.c_uint64) for n in (
-        "scan_cache_hits", "host_admit_ns", "host_scan_ns", "host_packsync_ns", "host_vmm_ns", "host_ring_ns")] + [
-        ("pack_span_ms", C.c_double), ("unpack_span_ms", C.c_double)]
+        "scan_cache_hits", "host_admit_ns", "host_wait_ns", "host_vmm_ns", "pager_vmm_ns", "pager_scan_ns", "pager_packsync_ns",
+        "pager_ring_ns", "pager_busy_ns", "vmm_calls")] + [
+        ("pack_span_ms", C.c_double), ("unpack_span_ms", C.c_double)] + [(n, C.c_uint64) for n in (
+        "direct_out_bytes", "direct_in_bytes", "prefetch_issued", "prefetch_hits", "prefetch_wasted", "demand_waits",
+        "clean_evictions", "host_slabs", "host_slabs_local")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -111,6 +115,9 @@ ABI = {
     "vgpu_swap_free": (_INT, [_P, _U64]),
     "vgpu_swap_acquire": (_INT, [_P, C.POINTER(_U64), _INT, _P]),
     "vgpu_swap_release": (_INT, [_P, C.POINTER(_U64), _INT, _P]),
+    "vgpu_swap_release_ro": (_INT, [_P, C.POINTER(_U64), _INT, _P]),
+    "vgpu_swap_advise_read_mostly": (_INT, [_P, _U64, _INT]),
+    "vgpu_swap_pin": (_INT, [_P, _U64, _INT]),
     "vgpu_swap_stats": (_INT, [_P, C.POINTER(SwapStats)]),
     "vgpu_swap_drain": (_INT, [_P]),
     "vgpu_swap_table": (_INT, [_P, C.POINTER(Entry), _U32, C.POINTER(_U32)]),
@@ -122,6 +129,7 @@ ABI = {
     "vgpu_runtime_swap_stats": (_INT, [_INT, C.POINTER(SwapStats)]),
     "vgpu_runtime_limiter_stats": (_INT, [C.POINTER(LimiterStats)]),
     "vgpu_runtime_set_swap_profile": (_INT, [_INT, _INT]),
+    "vgpu_runtime_swap_pin": (_INT, [_U64, _INT]),
     "vgpu_runtime_context_size": (_U64, []),
     "vgpu_runtime_check_memory_type": (_INT, [_U64]),
 }
@@ -250,8 +258,11 @@ def victim_scan(d_table, n, need, max_touch, stream=0):
 class Swap:
     """The swap engine through the C ABI (the same object the hook creates under CUDA_OVERSUBSCRIBE=true)."""
 
-    def __init__(self, dev=0, resident_cap=0, virtual_cap=0, host_pool_cap=0, chunk_bytes=0, ring_slots=0, profile=False):
-        cfg = SwapConfig(resident_cap, virtual_cap, host_pool_cap, chunk_bytes, ring_slots, int(profile))
+    def __init__(self, dev=0, resident_cap=0, virtual_cap=0, host_pool_cap=0, chunk_bytes=0, ring_slots=0, profile=False,
+                 prefetch_bytes=0, copy_bytes=0):
+        """prefetch_bytes: 0 = default window, None = prefetch off."""
+        cfg = SwapConfig(resident_cap, virtual_cap, host_pool_cap, chunk_bytes, ring_slots, int(profile),
+                         (1 << 64) - 1 if prefetch_bytes is None else prefetch_bytes, copy_bytes)
         h = _P()
         _check("vgpu_swap_create", lib().vgpu_swap_create(dev, C.byref(cfg), C.byref(h)))
         self._h = h
@@ -271,6 +282,17 @@ class Swap:
     def release(self, ptrs, stream=0):
         a = (_U64 * len(ptrs))(*ptrs)
         _check("vgpu_swap_release", lib().vgpu_swap_release(self._h, a, len(ptrs), _P(stream)))
+
+    def release_ro(self, ptrs, stream=0):
+        """release() for work that only read the buffers: they stay clean."""
+        a = (_U64 * len(ptrs))(*ptrs)
+        _check("vgpu_swap_release_ro", lib().vgpu_swap_release_ro(self._h, a, len(ptrs), _P(stream)))
+
+    def advise_read_mostly(self, ptr, on=True):
+        _check("vgpu_swap_advise_read_mostly", lib().vgpu_swap_advise_read_mostly(self._h, ptr, int(on)))
+
+    def pin(self, ptr, on=True):
+        _check("vgpu_swap_pin", lib().vgpu_swap_pin(self._h, ptr, int(on)))
 
     def stats(self):
         s = SwapStats()

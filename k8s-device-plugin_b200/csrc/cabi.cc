@@ -234,9 +234,14 @@ static void fill_stats(const SwapStats &s, vgpu_swap_stats_t *o) {
     o->entries = s.entries; o->phys_creates = s.phys_creates; o->phys_reuses = s.phys_reuses;
     o->pack_bytes = s.pack_bytes; o->unpack_bytes = s.unpack_bytes; o->pack_ms = s.pack_ms; o->unpack_ms = s.unpack_ms;
     o->scan_cache_hits = s.scan_cache_hits;
-    o->host_admit_ns = s.host_admit_ns; o->host_scan_ns = s.host_scan_ns; o->host_packsync_ns = s.host_packsync_ns;
-    o->host_vmm_ns = s.host_vmm_ns; o->host_ring_ns = s.host_ring_ns;
+    o->host_admit_ns = s.host_admit_ns; o->host_wait_ns = s.host_wait_ns; o->host_vmm_ns = s.host_vmm_ns;
+    o->pager_vmm_ns = s.pager_vmm_ns; o->pager_scan_ns = s.pager_scan_ns; o->pager_packsync_ns = s.pager_packsync_ns;
+    o->pager_ring_ns = s.pager_ring_ns; o->pager_busy_ns = s.pager_busy_ns; o->vmm_calls = s.vmm_calls;
     o->pack_span_ms = s.pack_span_ms; o->unpack_span_ms = s.unpack_span_ms;
+    o->direct_out_bytes = s.direct_out_bytes; o->direct_in_bytes = s.direct_in_bytes;
+    o->prefetch_issued = s.prefetch_issued; o->prefetch_hits = s.prefetch_hits; o->prefetch_wasted = s.prefetch_wasted;
+    o->demand_waits = s.demand_waits; o->clean_evictions = s.clean_evictions;
+    o->host_slabs = s.host_slabs; o->host_slabs_local = s.host_slabs_local;
 }
 VGPU_API int vgpu_swap_create(int dev, const vgpu_swap_config_t *cfg, vgpu_swap_t **out) {
     if (!out) return CUDA_ERROR_INVALID_VALUE;
@@ -246,6 +251,9 @@ VGPU_API int vgpu_swap_create(int dev, const vgpu_swap_config_t *cfg, vgpu_swap_
         if (cfg->chunk_bytes) c.chunk_bytes = cfg->chunk_bytes;
         if (cfg->ring_slots) c.ring_slots = (int)cfg->ring_slots;
         c.profile = cfg->profile != 0;
+        if (cfg->prefetch_bytes == ~0ull) c.prefetch_bytes = 0;
+        else if (cfg->prefetch_bytes) c.prefetch_bytes = cfg->prefetch_bytes;
+        if (cfg->copy_bytes) c.copy_bytes = cfg->copy_bytes;
     }
     SwapEngine *e = SwapEngine::create(dev, c);
     if (!e) return CUDA_ERROR_NOT_SUPPORTED;
@@ -285,6 +293,27 @@ VGPU_API int vgpu_swap_release(vgpu_swap_t *s, const uint64_t *ptrs, int n, void
     if (rc) return rc;
     s->e->note_use(rows.data(), (int)rows.size(), static_cast<CUstream>(stream));
     return CUDA_SUCCESS;
+}
+VGPU_API int vgpu_swap_release_ro(vgpu_swap_t *s, const uint64_t *ptrs, int n, void *stream) {
+    if (!s) return CUDA_ERROR_INVALID_VALUE;
+    std::vector<int> rows;
+    int rc = rows_of(s, ptrs, n, &rows);
+    if (rc) return rc;
+    s->e->note_use(rows.data(), (int)rows.size(), static_cast<CUstream>(stream), /*writes=*/false);
+    return CUDA_SUCCESS;
+}
+VGPU_API int vgpu_swap_advise_read_mostly(vgpu_swap_t *s, uint64_t ptr, int on) {
+    if (!s) return CUDA_ERROR_INVALID_VALUE;
+    int row = s->e->lookup(ptr);
+    if (row < 0) return CUDA_ERROR_INVALID_VALUE;
+    s->e->advise_read_mostly(row, on != 0);
+    return CUDA_SUCCESS;
+}
+VGPU_API int vgpu_swap_pin(vgpu_swap_t *s, uint64_t ptr, int on) {
+    if (!s) return CUDA_ERROR_INVALID_VALUE;
+    int row = s->e->lookup(ptr);
+    if (row < 0) return CUDA_ERROR_INVALID_VALUE;
+    return s->e->pin_resident(row, on != 0);
 }
 VGPU_API int vgpu_swap_stats(vgpu_swap_t *s, vgpu_swap_stats_t *out) {
     if (!s || !out) return CUDA_ERROR_INVALID_VALUE;
@@ -338,6 +367,15 @@ VGPU_API int vgpu_runtime_set_swap_profile(int dev, int on) {
     if (!e) return CUDA_ERROR_NOT_INITIALIZED;
     e->set_profile(on != 0);
     return CUDA_SUCCESS;
+}
+VGPU_API int vgpu_runtime_swap_pin(uint64_t dptr, int on) {
+    CUdevice dev = -1;
+    if (drv().cuCtxGetDevice(&dev) != CUDA_SUCCESS) return CUDA_ERROR_INVALID_CONTEXT;
+    SwapEngine *e = Runtime::get().swap((int)dev);
+    if (!e) return CUDA_ERROR_NOT_INITIALIZED;
+    int row = e->lookup(dptr);
+    if (row < 0) return CUDA_ERROR_INVALID_VALUE;
+    return e->pin_resident(row, on != 0);
 }
 VGPU_API uint64_t vgpu_runtime_context_size(void) { return Runtime::get().context_size(); }
 VGPU_API int vgpu_runtime_check_memory_type(uint64_t dptr) { return Runtime::get().check_memory_type(dptr); }

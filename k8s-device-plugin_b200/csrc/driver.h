@@ -34,6 +34,7 @@ namespace vgpu {
     X(cuModuleLoadData) X(cuModuleGetFunction) X(cuModuleUnload) X(cuFuncSetAttribute) X(cuFuncGetParamInfo)      \
     X(cuLaunchKernel) X(cuLaunchKernelEx) X(cuLaunchCooperativeKernel) X(cuOccupancyMaxActiveBlocksPerMultiprocessor) \
     X(cuMemAllocAsync) X(cuMemAllocFromPoolAsync) X(cuMemFreeAsync) X(cuGraphLaunch)                              \
+    X(cuMemAdvise) X(cuMemAdvise_v2) X(cuMemPrefetchAsync)                                                        \
     X(cuGetProcAddress_v2) X(cuGetErrorString) X(cuGetErrorName)
 
 // per-thread-default-stream twins (cuda.h hides their prototypes behind __CUDA_API_VERSION_INTERNAL; the signatures

@@ -143,13 +143,14 @@ VGPU_EXPORT CUresult cuModuleUnload(CUmodule hmod) {
 // memcpy / memset: pass-through, except that in swap mode the device ranges they touch are paged in first (a DMA
 // engine cannot fault on an unmapped VMM range the way UVM-managed memory does in the reference)
 #define TOUCH1(p, n, st) Runtime::get().touch_range((p), (n), (st))
+#define TOUCH1R(p, n, st) Runtime::get().touch_range((p), (n), (st), /*writes=*/false)   /* the range is only read */
 #define TOUCH2(a, an, b, bn, st) Runtime::get().touch_range2((a), (an), (b), (bn), (st))
 #define TOUCH_DONE(st) Runtime::get().touch_done(st)
 VGPU_EXPORT CUresult cuMemcpyHtoD_v2(CUdeviceptr dst, const void *src, size_t n) {
     TOUCH1(dst, n, nullptr); CUresult r = drv().cuMemcpyHtoD_v2(dst, src, n); TOUCH_DONE(nullptr); return r;
 }
 VGPU_EXPORT CUresult cuMemcpyDtoH_v2(void *dst, CUdeviceptr src, size_t n) {
-    TOUCH1(src, n, nullptr); CUresult r = drv().cuMemcpyDtoH_v2(dst, src, n); TOUCH_DONE(nullptr); return r;
+    TOUCH1R(src, n, nullptr); CUresult r = drv().cuMemcpyDtoH_v2(dst, src, n); TOUCH_DONE(nullptr); return r;
 }
 VGPU_EXPORT CUresult cuMemcpyDtoD_v2(CUdeviceptr dst, CUdeviceptr src, size_t n) {
     TOUCH2(dst, n, src, n, nullptr); CUresult r = drv().cuMemcpyDtoD_v2(dst, src, n); TOUCH_DONE(nullptr); return r;
@@ -158,7 +159,7 @@ VGPU_EXPORT CUresult cuMemcpyHtoDAsync_v2(CUdeviceptr dst, const void *src, size
     TOUCH1(dst, n, st); CUresult r = drv().cuMemcpyHtoDAsync_v2(dst, src, n, st); TOUCH_DONE(st); return r;
 }
 VGPU_EXPORT CUresult cuMemcpyDtoHAsync_v2(void *dst, CUdeviceptr src, size_t n, CUstream st) {
-    TOUCH1(src, n, st); CUresult r = drv().cuMemcpyDtoHAsync_v2(dst, src, n, st); TOUCH_DONE(st); return r;
+    TOUCH1R(src, n, st); CUresult r = drv().cuMemcpyDtoHAsync_v2(dst, src, n, st); TOUCH_DONE(st); return r;
 }
 VGPU_EXPORT CUresult cuMemcpyDtoDAsync_v2(CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream st) {
     TOUCH2(dst, n, src, n, st); CUresult r = drv().cuMemcpyDtoDAsync_v2(dst, src, n, st); TOUCH_DONE(st); return r;
@@ -194,7 +195,7 @@ VGPU_EXPORT CUresult cuMemcpyHtoD_v2_ptds(CUdeviceptr dst, const void *src, size
     TOUCH1(dst, n, CU_STREAM_PER_THREAD); CUresult r = drv().cuMemcpyHtoD_v2_ptds(dst, src, n); TOUCH_DONE(CU_STREAM_PER_THREAD); return r;
 }
 VGPU_EXPORT CUresult cuMemcpyDtoH_v2_ptds(void *dst, CUdeviceptr src, size_t n) {
-    TOUCH1(src, n, CU_STREAM_PER_THREAD); CUresult r = drv().cuMemcpyDtoH_v2_ptds(dst, src, n); TOUCH_DONE(CU_STREAM_PER_THREAD); return r;
+    TOUCH1R(src, n, CU_STREAM_PER_THREAD); CUresult r = drv().cuMemcpyDtoH_v2_ptds(dst, src, n); TOUCH_DONE(CU_STREAM_PER_THREAD); return r;
 }
 VGPU_EXPORT CUresult cuMemcpyDtoD_v2_ptds(CUdeviceptr dst, CUdeviceptr src, size_t n) {
     TOUCH2(dst, n, src, n, CU_STREAM_PER_THREAD); CUresult r = drv().cuMemcpyDtoD_v2_ptds(dst, src, n); TOUCH_DONE(CU_STREAM_PER_THREAD); return r;
@@ -206,7 +207,7 @@ VGPU_EXPORT CUresult cuMemcpyHtoDAsync_v2_ptsz(CUdeviceptr dst, const void *src,
     TOUCH1(dst, n, PTS(st)); CUresult r = drv().cuMemcpyHtoDAsync_v2_ptsz(dst, src, n, st); TOUCH_DONE(PTS(st)); return r;
 }
 VGPU_EXPORT CUresult cuMemcpyDtoHAsync_v2_ptsz(void *dst, CUdeviceptr src, size_t n, CUstream st) {
-    TOUCH1(src, n, PTS(st)); CUresult r = drv().cuMemcpyDtoHAsync_v2_ptsz(dst, src, n, st); TOUCH_DONE(PTS(st)); return r;
+    TOUCH1R(src, n, PTS(st)); CUresult r = drv().cuMemcpyDtoHAsync_v2_ptsz(dst, src, n, st); TOUCH_DONE(PTS(st)); return r;
 }
 VGPU_EXPORT CUresult cuMemcpyDtoDAsync_v2_ptsz(CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream st) {
     TOUCH2(dst, n, src, n, PTS(st)); CUresult r = drv().cuMemcpyDtoDAsync_v2_ptsz(dst, src, n, st); TOUCH_DONE(PTS(st)); return r;
@@ -294,20 +295,38 @@ VGPU_EXPORT CUresult cuMemsetD2D32Async(CUdeviceptr dst, size_t pitch, unsigned 
 // is not needed and would only mislead cudaMemPrefetchAsync-style callers; VGPU_REFERENCE_COVERAGE=1 restores it.
 VGPU_EXPORT CUresult cuPointerGetAttribute(void *data, CUpointer_attribute attribute, CUdeviceptr ptr) {
     if (!drv().cuPointerGetAttribute) return CUDA_ERROR_NOT_SUPPORTED;
-    TOUCH1(ptr, 1, nullptr);
+    TOUCH1R(ptr, 1, nullptr);
     CUresult r = drv().cuPointerGetAttribute(data, attribute, ptr);
     TOUCH_DONE(nullptr);
     return r;
 }
 VGPU_EXPORT CUresult cuPointerGetAttributes(unsigned int numAttributes, CUpointer_attribute *attributes, void **data, CUdeviceptr ptr) {
     if (!drv().cuPointerGetAttributes) return CUDA_ERROR_NOT_SUPPORTED;
-    TOUCH1(ptr, 1, nullptr);
+    TOUCH1R(ptr, 1, nullptr);
     CUresult r = drv().cuPointerGetAttributes(numAttributes, attributes, data, ptr);
     TOUCH_DONE(nullptr);
     if (attributes && data && Runtime::get().reference_coverage_mode())
         for (unsigned int i = 0; i < numAttributes; i++)
             if (attributes[i] == CU_POINTER_ATTRIBUTE_IS_MANAGED && data[i]) *static_cast<unsigned int *>(data[i]) = 0;
     return r;
+}
+
+// cuMemAdvise / cuMemPrefetchAsync. In the reference a large allocation under CUDA_OVERSUBSCRIBE IS managed memory
+// (cuMemoryAllocate@0x315da -> cuMemAllocManaged), so both calls work on it and steer UVM. Here the same pointers are the
+// swap engine's: SET_READ_MOSTLY keeps kernel launches from dirtying the range (eviction without write-back), a prefetch
+// to the device queues a page-in with the pager; everything else about them is accepted and ignored. Other pointers go to
+// the driver unchanged.
+VGPU_EXPORT CUresult cuMemAdvise(CUdeviceptr devPtr, size_t count, CUmem_advise advice, CUdevice device) {
+    if (Runtime::get().swap_advise(devPtr, advice)) return CUDA_SUCCESS;
+    return drv().cuMemAdvise ? drv().cuMemAdvise(devPtr, count, advice, device) : CUDA_ERROR_NOT_SUPPORTED;
+}
+VGPU_EXPORT CUresult cuMemAdvise_v2(CUdeviceptr devPtr, size_t count, CUmem_advise advice, CUmemLocation location) {
+    if (Runtime::get().swap_advise(devPtr, advice)) return CUDA_SUCCESS;
+    return drv().cuMemAdvise_v2 ? drv().cuMemAdvise_v2(devPtr, count, advice, location) : CUDA_ERROR_NOT_SUPPORTED;
+}
+VGPU_EXPORT CUresult cuMemPrefetchAsync(CUdeviceptr devPtr, size_t count, CUdevice dstDevice, CUstream hStream) {
+    if (Runtime::get().swap_prefetch(devPtr, dstDevice >= 0)) return CUDA_SUCCESS;
+    return drv().cuMemPrefetchAsync ? drv().cuMemPrefetchAsync(devPtr, count, dstDevice, hStream) : CUDA_ERROR_NOT_SUPPORTED;
 }
 
 // extras the reference exports for its own tooling
@@ -387,6 +406,7 @@ const std::vector<HookEntry> &hooks() {
         H(cuMemcpyHtoD_v2_ptds), H(cuMemcpyDtoH_v2_ptds), H(cuMemcpyDtoD_v2_ptds), H(cuMemcpy_ptds), H(cuMemcpyHtoDAsync_v2_ptsz),
         H(cuMemcpyDtoHAsync_v2_ptsz), H(cuMemcpyDtoDAsync_v2_ptsz), H(cuMemcpyAsync_ptsz), H(cuMemsetD8_v2_ptds), H(cuMemsetD16_v2_ptds),
         H(cuMemsetD32_v2_ptds), H(cuMemsetD8Async_ptsz), H(cuMemsetD16Async_ptsz), H(cuMemsetD32Async_ptsz),
+        H(cuMemAdvise), H(cuMemAdvise_v2), H(cuMemPrefetchAsync),
         HN(cuMemoryAllocate), HN(cuMemoryFree), HN(cuVGPUViewAllocator),
         HN(nvmlDeviceGetMemoryInfo), HN(nvmlDeviceGetMemoryInfo_v2),
     };

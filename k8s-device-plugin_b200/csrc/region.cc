@@ -101,13 +101,17 @@ Region *Region::open(const char *path, bool create, const uint64_t *mem_limits, 
         if (err) *err = std::string("open ") + path + ": " + std::strerror(errno);
         return nullptr;
     }
+    // size check and growth under the whole-file lock, and never downwards: a second creator that saw size 0 must not cut
+    // off the extension block a first creator has already appended behind the reference's bytes
+    if (lockf(fd, F_LOCK, 0) != 0) LOG_WARN("lockf(%s): %s", path, std::strerror(errno));
     struct stat st;
-    if (fstat(fd, &st) != 0 || static_cast<uint64_t>(st.st_size) < VGPU_REGION_SIZE) {
-        if (!create || ftruncate(fd, VGPU_REGION_SIZE) != 0) {
-            if (err) *err = "region file too small";
-            ::close(fd);
-            return nullptr;
-        }
+    bool size_ok = fstat(fd, &st) == 0 && static_cast<uint64_t>(st.st_size) >= VGPU_REGION_SIZE;
+    if (!size_ok && create) size_ok = ftruncate(fd, VGPU_REGION_SIZE) == 0;
+    if (lockf(fd, F_ULOCK, 0) != 0) {}
+    if (!size_ok) {
+        if (err) *err = "region file too small";
+        ::close(fd);
+        return nullptr;
     }
     void *m = mmap(nullptr, VGPU_REGION_SIZE, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
     if (m == MAP_FAILED) {
@@ -257,14 +261,18 @@ void Region::lock() {
         }
         int32_t owner = static_cast<int32_t>(r_->owner_pid);
         bool takeover = false;
+        ++trials;
         if (owner == getpid() || (owner != 0 && !pid_alive(owner))) takeover = true;
-        else if (owner == 0 && ++trials >= 3) takeover = true;   // reference: 30 trials (5 min); a holder that never
-                                                                 // recorded itself died inside a microsecond window
-        else ++trials;
+        else if (owner == 0 && trials >= 30) takeover = true;    // 30 timeouts (5 min) like the reference: a holder that
+                                                                 // never recorded itself died inside a microsecond window
         if (takeover) {
             if (lockf(fd_, F_LOCK, VGPU_REGION_SIZE) == 0) {
                 int32_t now = static_cast<int32_t>(r_->owner_pid);
                 bool still = (now == owner);
+                // owner 0 is also the normal state between unlock()'s store and its sem_post: if the semaphore is
+                // available after all, take it the ordinary way so that the count can never reach 2
+                int sv = 0;
+                if (still && owner == 0 && sem_getvalue(sem_of(r_), &sv) == 0 && sv > 0) still = false;
                 if (still) r_->owner_pid = static_cast<uint64_t>(getpid());
                 if (lockf(fd_, F_ULOCK, VGPU_REGION_SIZE) != 0) {}
                 if (still) {

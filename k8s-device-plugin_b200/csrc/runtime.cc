@@ -139,9 +139,12 @@ void Runtime::on_exit() {
         for (int d = 0; d < VGPU_MAX_DEVICES; d++)
             if (swap_[d]) {
                 SwapStats s = swap_[d]->stats();
-                swap_[d]->dump_trace(stderr);
-                std::fprintf(stderr, "[vgpu-b200 stats] swap dev %d host ms: admit=%.1f scan=%.1f packsync=%.1f vmm=%.1f ringwait=%.1f slabs=%lu local=%lu\n", d, s.host_admit_ns / 1e6,
-                             s.host_scan_ns / 1e6, s.host_packsync_ns / 1e6, s.host_vmm_ns / 1e6, s.host_ring_ns / 1e6, (unsigned long)s.host_slabs, (unsigned long)s.host_slabs_local);
+                std::fprintf(stderr, "[vgpu-b200 stats] swap dev %d ms: app admit=%.1f wait=%.1f vmm=%.1f | pager busy=%.1f vmm=%.1f (%lu calls) scan=%.1f packsync=%.1f ringwait=%.1f slabs=%lu local=%lu\n", d,
+                             s.host_admit_ns / 1e6, s.host_wait_ns / 1e6, s.host_vmm_ns / 1e6, s.pager_busy_ns / 1e6, s.pager_vmm_ns / 1e6, (unsigned long)s.vmm_calls,
+                             s.pager_scan_ns / 1e6, s.pager_packsync_ns / 1e6, s.pager_ring_ns / 1e6, (unsigned long)s.host_slabs, (unsigned long)s.host_slabs_local);
+                std::fprintf(stderr, "[vgpu-b200 stats] swap dev %d: prefetch issued=%lu hits=%lu wasted=%lu demand_waits=%lu clean_evictions=%lu direct in=%lu out=%lu\n", d,
+                             (unsigned long)s.prefetch_issued, (unsigned long)s.prefetch_hits, (unsigned long)s.prefetch_wasted, (unsigned long)s.demand_waits,
+                             (unsigned long)s.clean_evictions, (unsigned long)s.direct_in_bytes, (unsigned long)s.direct_out_bytes);
                 std::fprintf(stderr, "[vgpu-b200 stats] swap dev %d: in=%lu out=%lu faults=%lu evictions=%lu scans=%lu cache_hits=%lu creates=%lu reuses=%lu\n", d,
                              (unsigned long)s.page_in_bytes, (unsigned long)s.page_out_bytes, (unsigned long)s.faults, (unsigned long)s.evictions,
                              (unsigned long)s.scans, (unsigned long)s.scan_cache_hits, (unsigned long)s.phys_creates, (unsigned long)s.phys_reuses);
@@ -953,20 +956,23 @@ CUresult Runtime::mem_unmap(CUdeviceptr ptr, size_t size) {
     return r;
 }
 
-static thread_local std::vector<int> t_touch_rows;   // rows pinned between touch_range*() and touch_done()
+static thread_local std::vector<int> t_touch_w, t_touch_r;   // rows pinned between touch_range*() and touch_done(): written / only read
 
-void Runtime::touch_range(CUdeviceptr p, size_t bytes, CUstream st) { touch_range2(p, bytes, 0, 0, st); }
+void Runtime::touch_range(CUdeviceptr p, size_t bytes, CUstream st, bool writes) {
+    if (writes) touch_range2(p, bytes, 0, 0, st);
+    else touch_range2(0, 0, p, bytes, st);
+}
 
-void Runtime::touch_range2(CUdeviceptr a, size_t abytes, CUdeviceptr b, size_t bbytes, CUstream st) {
+void Runtime::touch_range2(CUdeviceptr dst, size_t dbytes, CUdeviceptr src, size_t sbytes, CUstream st) {
     if (!cfg_.oversubscribe) return;
     int dev = current_device();
     SwapEngine *e = swap(dev);
     if (!e) return;
     int rows[2]; int n = 0;
-    (void)abytes; (void)bbytes;
-    int ra = a ? e->lookup(a) : -1, rb = b ? e->lookup(b) : -1;
-    if (ra >= 0) rows[n++] = ra;
-    if (rb >= 0 && rb != ra) rows[n++] = rb;
+    (void)dbytes; (void)sbytes;
+    int rd = dst ? e->lookup(dst) : -1, rs = src ? e->lookup(src) : -1;
+    if (rd >= 0) rows[n++] = rd;
+    if (rs >= 0 && rs != rd) rows[n++] = rs;
     if (!n) return;
     if (stream_is_capturing(st)) {   // captured copy node: operands pinned resident, nothing recorded into the capture
         if (e->ensure_resident(rows, n, SwapEngine::kHostWait) != CUDA_SUCCESS) LOG_ERROR("captured memcpy/memset target could not be made resident");
@@ -974,14 +980,42 @@ void Runtime::touch_range2(CUdeviceptr a, size_t abytes, CUdeviceptr b, size_t b
     }
     if (e->ensure_resident(rows, n, st) != CUDA_SUCCESS) { LOG_ERROR("memcpy/memset target could not be made resident"); return; }
     // the copy itself is enqueued by the caller right after this returns; note_use after it keeps the rows pinned
-    t_touch_rows.assign(rows, rows + n);
+    t_touch_w.clear(); t_touch_r.clear();
+    if (rd >= 0) t_touch_w.push_back(rd);
+    if (rs >= 0 && rs != rd) t_touch_r.push_back(rs);
 }
 
 void Runtime::touch_done(CUstream st) {
-    if (t_touch_rows.empty()) return;
+    if (t_touch_w.empty() && t_touch_r.empty()) return;
     int dev = current_device();
-    if (SwapEngine *e = swap(dev)) e->note_use(t_touch_rows.data(), (int)t_touch_rows.size(), st);
-    t_touch_rows.clear();
+    if (SwapEngine *e = swap(dev)) {
+        if (!t_touch_w.empty()) e->note_use(t_touch_w.data(), (int)t_touch_w.size(), st, true);
+        if (!t_touch_r.empty()) e->note_use(t_touch_r.data(), (int)t_touch_r.size(), st, false);
+    }
+    t_touch_w.clear(); t_touch_r.clear();
+}
+
+bool Runtime::swap_advise(CUdeviceptr p, CUmem_advise advice) {
+    if (!cfg_.oversubscribe) return false;
+    SwapEngine *e = swap(current_device());
+    if (!e || !e->owns(p)) return false;
+    int row = e->lookup(p);
+    if (row < 0) return false;
+    // the only advice with a meaning for explicit paging: a read-mostly range is not dirtied by kernel launches, so
+    // evicting it needs no write-back (UVM: read duplication). Location / accessed-by hints are accepted and ignored.
+    if (advice == CU_MEM_ADVISE_SET_READ_MOSTLY) e->advise_read_mostly(row, true);
+    else if (advice == CU_MEM_ADVISE_UNSET_READ_MOSTLY) e->advise_read_mostly(row, false);
+    return true;
+}
+
+bool Runtime::swap_prefetch(CUdeviceptr p, bool to_device) {
+    if (!cfg_.oversubscribe) return false;
+    SwapEngine *e = swap(current_device());
+    if (!e || !e->owns(p)) return false;
+    int row = e->lookup(p);
+    if (row < 0) return false;
+    if (to_device) e->hint_prefetch(row);
+    return true;
 }
 
 }  // namespace vgpu

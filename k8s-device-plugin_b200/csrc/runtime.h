@@ -91,8 +91,14 @@ class Runtime {
     void forget_function_layouts();
     bool check_oom();
     // memcpy/memset family: make the touched device ranges resident before the real call (swap mode only)
-    void touch_range(CUdeviceptr p, size_t bytes, CUstream st);
-    void touch_range2(CUdeviceptr a, size_t abytes, CUdeviceptr b, size_t bbytes, CUstream st);
+    // a device range a copy / fill / query is about to touch; `writes` = the operation writes it (a range that is only
+    // read stays clean: evicting it later needs no copy)
+    void touch_range(CUdeviceptr p, size_t bytes, CUstream st, bool writes = true);
+    void touch_range2(CUdeviceptr dst, size_t dbytes, CUdeviceptr src, size_t sbytes, CUstream st);   // dst written, src read
+    // cuMemAdvise / cuMemPrefetchAsync on a swappable range (the reference's swappable memory is UVM-managed, where both
+    // are meaningful): true when the pointer is the swap engine's and the call has been handled
+    bool swap_advise(CUdeviceptr p, CUmem_advise advice);
+    bool swap_prefetch(CUdeviceptr p, bool to_device);
     void touch_done(CUstream st);   // after the real copy has been enqueued: unpins + records the use
 
     // NVML view: nvmlDeviceGetMemoryInfo under the quota (nvml/hook.c:L327-334)

@@ -7,6 +7,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,11 +45,14 @@ SwapConfig SwapConfig::from_env(uint64_t resident_cap, uint64_t virtual_cap) {
     c.arena_bytes = env_u64("VGPU_SWAP_ARENA_GB", 1024) << 30;
     c.profile = env_u64("VGPU_SWAP_PROFILE", 0) != 0;
     c.scan_lookahead = (uint32_t)env_u64("VGPU_SWAP_SCAN_LOOKAHEAD", 8);
-    c.async_unmap = env_u64("VGPU_SWAP_ASYNC_UNMAP", 0) != 0;
-    c.trace = (uint32_t)env_u64("VGPU_SWAP_TRACE", 0);
-    c.spare_bytes = env_u64("VGPU_SWAP_SPARE_MB", 128) << 20;
+    c.prefetch_bytes = env_u64("VGPU_SWAP_PREFETCH_MB", c.prefetch_bytes >> 20) << 20;
+    c.copy_bytes = (size_t)env_u64("VGPU_SWAP_COPY_MB", c.copy_bytes >> 20) << 20;
+    c.batch_rows = (uint32_t)env_u64("VGPU_SWAP_BATCH_ROWS", c.batch_rows);
+    c.host_backed = env_u64("VGPU_SWAP_HOST_BACKED", 0) != 0;
     if (c.ring_slots < 2) c.ring_slots = 2;
     if (c.chunk_bytes < (1u << 20)) c.chunk_bytes = 1u << 20;
+    if (c.copy_bytes < (1u << 20)) c.copy_bytes = 1u << 20;
+    if (c.batch_rows < 1) c.batch_rows = 1;
     return c;
 }
 
@@ -129,9 +133,7 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
     const DriverTable &d = drv();
     dev_ = dev;
     cfg_ = cfg;
-    scan_lookahead_ = cfg.scan_lookahead;
-    trace_want_ = cfg.trace;
-    trace_skip_ = 300;   // let the pipeline reach steady state first
+    profile_.store(cfg.profile);
     k_ = kernels_for_current_ctx();
     if (!k_) return false;
     numa_node_ = std::getenv("VGPU_SWAP_NO_NUMA") ? -1 : gpu_numa_node(dev);
@@ -150,6 +152,7 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
         uint64_t overhead = 2ull * cfg_.ring_slots * cfg_.chunk_bytes + (512ull << 20);
         cfg_.resident_cap = fr > overhead ? fr - overhead : fr / 2;
     }
+    quota_cap_ = cfg_.resident_cap;
     uint64_t want = round_up(cfg_.arena_bytes, gran_);
     CUresult r = CUDA_ERROR_UNKNOWN;
     // base alignment: buffers sit at multiples of their own (power-of-two-ish) sizes from the arena base, so a base
@@ -191,27 +194,30 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
     scanner_.reset(new VictimScanner());
     if (scanner_->init(k_, tbl_cap_) != CUDA_SUCCESS) return false;
     use_ring_.resize(1024);
+    use_stream_.assign(1024, nullptr);
     for (auto &e : use_ring_) if (d.cuEventCreate(&e, CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) return false;
     d.cuCtxGetCurrent(&ctx_);
-    if (cfg_.async_unmap) reaper_ = std::thread([this] { reaper_main(); });
-    LOG_INFO("swap engine dev %d (numa %d): resident cap %lu MiB, virtual cap %lu MiB, chunk %zu MiB x %d, arena %lu GiB, gran %zu",
+    pager_ = std::thread([this] { pager_main(); });
+    LOG_INFO("swap engine dev %d (numa %d): resident cap %lu MiB, virtual cap %lu MiB, staging %zu MiB x %d, copies %zu MiB, prefetch %lu MiB, arena %lu GiB, gran %zu",
              dev_, numa_node_, (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(cfg_.virtual_cap >> 20), cfg_.chunk_bytes >> 20,
-             cfg_.ring_slots, (unsigned long)(cfg_.arena_bytes >> 30), gran_);
+             cfg_.ring_slots, cfg_.copy_bytes >> 20, (unsigned long)(cfg_.prefetch_bytes >> 20), (unsigned long)(cfg_.arena_bytes >> 30), gran_);
     return true;
 }
 
 SwapEngine::~SwapEngine() {
     const DriverTable &d = drv();
-    if (!d.loaded) return;
-    drain();
-    if (reaper_.joinable()) {
-        { std::lock_guard<std::mutex> g(rq_mu_); reaper_stop_ = true; }
-        rq_cv_.notify_all();
-        reaper_.join();
+    if (pager_.joinable()) {
+        if (d.loaded) drain();
+        { std::lock_guard<std::mutex> g(mu_); stop_ = true; kick_ = true; }
+        cv_pager_.notify_all();
+        pager_.join();
     }
+    if (!d.loaded) return;
+    for (CUstream s : {s_scan_, s_pack_, s_unpack_, s_out_, s_in_}) if (s) d.cuStreamSynchronize(s);
     for (size_t i = 0; i < rows_.size(); i++) {
-        if (rows_[i].state == VGPU_ST_FREE) continue;
-        if (rows_[i].state & VGPU_ST_RESIDENT) { d.cuMemUnmap(rows_[i].base, side_[i].mapped); if (side_[i].has_handle) d.cuMemRelease(side_[i].handle); }
+        if (side_[i].has_handle) { d.cuMemUnmap(rows_[i].base, side_[i].mapped); d.cuMemRelease(side_[i].handle); }
+        if (side_[i].ready) d.cuEventDestroy_v2(side_[i].ready);
+        if (side_[i].evict_done) d.cuEventDestroy_v2(side_[i].evict_done);
     }
     for (auto &p : phys_pool_) d.cuMemRelease(p.second);
     for (auto &s : ring_out_) { if (s.buf) d.cuMemFree_v2(s.buf); if (s.busy) d.cuEventDestroy_v2(s.busy); }
@@ -219,6 +225,10 @@ SwapEngine::~SwapEngine() {
     for (auto &sl : slabs_) if (sl.host) d.cuMemFreeHost(sl.host);
     for (auto &e : use_ring_) if (e) d.cuEventDestroy_v2(e);
     for (auto &e : ready_free_) d.cuEventDestroy_v2(e);
+    for (auto &e : ev_pool_) d.cuEventDestroy_v2(e);
+    for (auto &p : prof_) { d.cuEventDestroy_v2(p.a); d.cuEventDestroy_v2(p.b); }
+    if (d_span_) d.cuMemFree_v2(d_span_);
+    scanner_.reset();
     if (d_tbl_) d.cuMemFree_v2(d_tbl_);
     if (h_tbl_stage_) d.cuMemFreeHost(h_tbl_stage_);
     if (arena_) d.cuMemAddressFree(arena_, cfg_.arena_bytes);
@@ -251,28 +261,19 @@ static void map_free(std::map<uint64_t, uint64_t> &fl, uint64_t off, uint64_t by
 bool SwapEngine::va_alloc(size_t bytes, uint64_t *off) { return map_alloc(va_free_, bytes, off); }
 void SwapEngine::va_free(uint64_t off, size_t bytes) { map_free(va_free_, off, bytes); }
 
-// pinned pool: global offset = slab_index << 44 | offset-in-slab
+// pinned pool: global offset = slab_index << 44 | offset-in-slab. Called by the pager (page-out) and, for releases, by
+// application threads (free of a paged-out buffer): own leaf mutex.
 bool SwapEngine::host_alloc(size_t bytes, uint64_t *off) {
     const DriverTable &d = drv();
     bytes = round_up(bytes, 256);
-    for (int attempt = 0; attempt < 2; attempt++) {
-        // second try: wait for parked ranges (their H2D reads finish within ~1 ms) rather than pin a new slab (~100 ms) —
-        // but only when enough bytes are parked to make the wait worthwhile
-        if (attempt == 1) {
-            uint64_t parked = 0;
-            for (auto &p : pending_host_) parked += p.len;
-            if (parked < bytes) break;
+    std::lock_guard<std::mutex> g(host_mu_);
+    for (size_t i = 0; i < slabs_.size(); i++) {
+        uint64_t o;
+        if (map_alloc(slabs_[i].free, bytes, &o)) {
+            *off = ((uint64_t)i << 44) | o;
+            host_used_ += bytes;
+            return true;
         }
-        reap_pending_host(attempt == 1);
-        for (size_t i = 0; i < slabs_.size(); i++) {
-            uint64_t o;
-            if (map_alloc(slabs_[i].free, bytes, &o)) {
-                *off = ((uint64_t)i << 44) | o;
-                host_used_ += bytes;
-                return true;
-            }
-        }
-        if (pending_host_.empty()) break;
     }
     size_t sb = std::max<size_t>(cfg_.slab_bytes, bytes);
     uint64_t have = 0;
@@ -290,10 +291,10 @@ bool SwapEngine::host_alloc(size_t bytes, uint64_t *off) {
         if (numa_node_ >= 0) default_policy();
     }
     if (r != CUDA_SUCCESS) { LOG_ERROR("pinned slab of %zu MiB failed: %d %s", sb >> 20, (int)r, cu_err(r)); return false; }
-    st_.host_slabs++;
+    pst_.host_slabs++;
     if (numa_node_ >= 0) {
         int got = node_of(s.host + sb / 2);
-        if (got == numa_node_) st_.host_slabs_local++;
+        if (got == numa_node_) pst_.host_slabs_local++;
         else LOG_WARN("pinned slab landed on NUMA node %d, GPU is on node %d: page traffic will cross the socket link", got, numa_node_);
     }
     s.bytes = sb;
@@ -303,42 +304,83 @@ bool SwapEngine::host_alloc(size_t bytes, uint64_t *off) {
     host_used_ += bytes;
     return true;
 }
-unsigned char *SwapEngine::host_ptr(uint64_t off) { return slabs_[off >> 44].host + (off & ((1ull << 44) - 1)); }
+unsigned char *SwapEngine::host_ptr(uint64_t off) {
+    std::lock_guard<std::mutex> g(host_mu_);
+    return slabs_[off >> 44].host + (off & ((1ull << 44) - 1));
+}
+void SwapEngine::release_host_range(uint64_t off, uint64_t len) {
+    std::lock_guard<std::mutex> g(host_mu_);
+    len = round_up(len, 256);
+    map_free(slabs_[off >> 44].free, off & ((1ull << 44) - 1), len);
+    host_used_ -= std::min<uint64_t>(len, host_used_.load());
+}
+// Pinned pool exhausted: resident rows keep their blocks so that a clean eviction needs no copy — those blocks are the
+// first thing to give up (dirty rows' blocks hold stale bytes anyway).
+bool SwapEngine::reclaim_host_blocks(Lock &lk, uint64_t bytes) {
+    (void)lk;
+    uint64_t got = 0;
+    for (int pass = 0; pass < 2 && got < bytes; pass++) {
+        for (size_t i = 0; i < rows_.size() && got < bytes; i++) {
+            Side &s = side_[i];
+            if (!(rows_[i].state & VGPU_ST_RESIDENT) || s.phase != PH_IDLE || !s.has_host || s.ready) continue;
+            if (pass == 0 && !s.dirty) continue;
+            release_host_range(s.host_off, round_up(rows_[i].size, 256));
+            s.has_host = false;
+            s.dirty = true;          // the HBM copy is the only one now
+            got += round_up(rows_[i].size, 256);
+        }
+    }
+    return got >= bytes;
+}
 
 // ---------------------------------------------------------------------------------------------- table
 int SwapEngine::new_row() {
     if (!free_rows_.empty()) { int r = free_rows_.back(); free_rows_.pop_back(); return r; }
     rows_.push_back(VgpuEntry{});
     side_.push_back(Side{});
+    succ_.push_back(-1);
     return (int)rows_.size() - 1;
 }
 void SwapEngine::mark_dirty(int row) {
     dirty_lo_ = std::min<uint32_t>(dirty_lo_, (uint32_t)row);
     dirty_hi_ = std::max<uint32_t>(dirty_hi_, (uint32_t)row + 1);
 }
-CUresult SwapEngine::sync_table(CUstream s) {
+// pager thread, mu_ held on entry and exit (released while the scan stream is synchronised)
+CUresult SwapEngine::sync_table(Lock &lk, CUstream s) {
     const DriverTable &d = drv();
     uint32_t n = (uint32_t)rows_.size();
     if (n > tbl_cap_) {
         uint32_t nc = tbl_cap_;
         while (nc < n) nc *= 2;
-        CU_TRY(d.cuStreamSynchronize(s));
-        d.cuMemFree_v2(d_tbl_);
-        d.cuMemFreeHost(h_tbl_stage_);
-        CU_TRY(d.cuMemAlloc_v2(&d_tbl_, (size_t)nc * sizeof(VgpuEntry)));
-        CU_TRY(d.cuMemHostAlloc((void **)&h_tbl_stage_, (size_t)nc * sizeof(VgpuEntry), 0));
-        scanner_.reset(new VictimScanner());
-        CU_TRY(scanner_->init(k_, nc));
+        lk.unlock();
+        CUresult r = d.cuStreamSynchronize(s);
+        if (r == CUDA_SUCCESS) {
+            d.cuMemFree_v2(d_tbl_);
+            d.cuMemFreeHost(h_tbl_stage_);
+            d_tbl_ = 0; h_tbl_stage_ = nullptr;
+            r = d.cuMemAlloc_v2(&d_tbl_, (size_t)nc * sizeof(VgpuEntry));
+            if (r == CUDA_SUCCESS) r = d.cuMemHostAlloc((void **)&h_tbl_stage_, (size_t)nc * sizeof(VgpuEntry), 0);
+            if (r == CUDA_SUCCESS) { scanner_.reset(new VictimScanner()); r = scanner_->init(k_, nc); }
+        }
+        lk.lock();
+        if (r != CUDA_SUCCESS) return r;
         tbl_cap_ = nc;
-        dirty_lo_ = 0; dirty_hi_ = n;
+        dirty_lo_ = 0; dirty_hi_ = (uint32_t)rows_.size();
     }
     if (dirty_lo_ >= dirty_hi_) return CUDA_SUCCESS;
+    // the pinned staging copy must not be overwritten while a previous upload is in flight (scans synchronise the stream,
+    // so this is immediate in practice)
+    lk.unlock();
+    CUresult r = d.cuStreamSynchronize(s);
+    lk.lock();
+    if (r != CUDA_SUCCESS) return r;
+    n = (uint32_t)rows_.size();
+    if (n > tbl_cap_) return sync_table(lk, s);          // grew meanwhile
     uint32_t lo = dirty_lo_, hi = std::min(dirty_hi_, n);
-    // the pinned staging copy must not be overwritten while a previous upload is in flight
-    CU_TRY(d.cuStreamSynchronize(s));
+    if (lo >= hi) return CUDA_SUCCESS;
     std::memcpy(h_tbl_stage_ + lo, rows_.data() + lo, (size_t)(hi - lo) * sizeof(VgpuEntry));
-    CU_TRY(d.cuMemcpyHtoDAsync_v2(d_tbl_ + (size_t)lo * sizeof(VgpuEntry), h_tbl_stage_ + lo, (size_t)(hi - lo) * sizeof(VgpuEntry), s));
     dirty_lo_ = UINT32_MAX; dirty_hi_ = 0;
+    CU_TRY(d.cuMemcpyHtoDAsync_v2(d_tbl_ + (size_t)lo * sizeof(VgpuEntry), h_tbl_stage_ + lo, (size_t)(hi - lo) * sizeof(VgpuEntry), s));
     return CUDA_SUCCESS;
 }
 
@@ -365,107 +407,19 @@ void SwapEngine::collect_rows(const void *param, size_t bytes, std::vector<int> 
     }
 }
 
-// ---------------------------------------------------------------------------------------------- physical memory
-void SwapEngine::trim_phys_pool(uint64_t need) {
-    const DriverTable &d = drv();
-    const uint64_t allowed = cfg_.resident_cap + (cfg_.async_unmap ? cfg_.spare_bytes : 0);
-    while (!phys_pool_.empty() && resident_mapped_ + evicting_mapped_ + phys_pool_bytes_ + need > allowed) {
-        auto it = std::prev(phys_pool_.end());
-        d.cuMemRelease(it->second);
-        phys_pool_bytes_ -= it->first;
-        phys_pool_.erase(it);
-    }
-}
-CUresult SwapEngine::get_phys(size_t mapped, CUmemGenericAllocationHandle *h) {
-    const DriverTable &d = drv();
-    for (;;) {
-        auto it = phys_pool_.find(mapped);
-        if (it != phys_pool_.end()) {
-            *h = it->second;
-            phys_pool_bytes_ -= mapped;
-            phys_pool_.erase(it);
-            st_.phys_reuses++;
-            return CUDA_SUCCESS;
-        }
-        // physical memory held = resident + victims awaiting their unmap + pooled handles; it may exceed the quota
-        // by at most spare_bytes (a documented overhead like the staging rings) so that mapping the incoming row
-        // does not have to wait for the reaper
-        uint64_t held = resident_mapped_ + evicting_mapped_ + phys_pool_bytes_;
-        uint64_t allowed = cfg_.resident_cap + (cfg_.async_unmap ? cfg_.spare_bytes : 0);
-        if (held + mapped <= allowed) break;
-        if (!phys_pool_.empty()) { trim_phys_pool(mapped); held = resident_mapped_ + evicting_mapped_ + phys_pool_bytes_; if (held + mapped <= allowed) break; }
-        if (evicting_mapped_ == 0) break;            // nothing more will come back: create and let the driver decide
-        reap_cv_.wait(mu_);                          // a reaper batch will return handles
-    }
-    CUmemAllocationProp prop = {};
-    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
-    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
-    prop.location.id = dev_;
-    CUresult r = d.cuMemCreate(h, mapped, &prop, 0);
-    if (r == CUDA_ERROR_OUT_OF_MEMORY && !phys_pool_.empty()) {
-        for (auto &p : phys_pool_) d.cuMemRelease(p.second);
-        phys_pool_.clear();
-        phys_pool_bytes_ = 0;
-        r = d.cuMemCreate(h, mapped, &prop, 0);
-    }
-    if (r == CUDA_SUCCESS) st_.phys_creates++;
-    return r;
-}
-CUresult SwapEngine::map_row(int row) {
-    const DriverTable &d = drv();
-    wait_not_evicting(row);                      // its own previous mapping may still be queued at the reaper
-    CUmemGenericAllocationHandle h;
-    CUresult r = get_phys(side_[row].mapped, &h);   // may wait for the reaper with mu_ released: take references after
-    for (int attempt = 0; r == CUDA_ERROR_OUT_OF_MEMORY && attempt < 4; attempt++) {
-        // The device cannot give what the quota promises: on an overcommitted GPU other containers hold the rest (the
-        // reference leaves this case to UVM, which pages between processes). Live within what we have: lower the working
-        // cap to what is mapped now and make the room out of our own least recently used rows.
-        const uint64_t need = side_[row].mapped;
-        uint64_t held = resident_mapped_ + evicting_mapped_;
-        if (held < need) break;                        // nothing of ours left to give up
-        // what the device can still give on top of what we hold (the pool was already released by get_phys)
-        size_t fr = 0, tot = 0;
-        if (d.cuMemGetInfo_v2(&fr, &tot) == CUDA_SUCCESS) held += (uint64_t)fr / gran_ * gran_;
-        if (!pressure_ || cfg_.resident_cap > held) {
-            if (!pressure_) {
-                quota_cap_ = std::max(quota_cap_, cfg_.resident_cap);
-                LOG_WARN("device %d: physical memory exhausted below the quota; resident cap %lu -> %lu MiB", dev_,
-                         (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(held >> 20));
-            } else {
-                LOG_INFO("device %d: upward probe failed; resident cap back to %lu MiB", dev_, (unsigned long)(held >> 20));
-            }
-            cfg_.resident_cap = held;
-            pressure_ = true;
-        }
-        pressure_events_++;
-        if (make_room(need, true) != CUDA_SUCCESS) break;
-        r = get_phys(need, &h);
-    }
-    if (r != CUDA_SUCCESS) return r;
-    ScopedNs t(&st_.host_vmm_ns);
+void SwapEngine::retire_row_locked(int row) {
     Side &s = side_[row];
-    r = d.cuMemMap(rows_[row].base, s.mapped, 0, h, 0);
-    if (r != CUDA_SUCCESS) { d.cuMemRelease(h); LOG_ERROR("cuMemMap failed: %d %s", (int)r, cu_err(r)); return r; }
-    CUmemAccessDesc acc = {};
-    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
-    acc.location.id = dev_;
-    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-    r = d.cuMemSetAccess(rows_[row].base, s.mapped, &acc, 1);
-    if (r != CUDA_SUCCESS) { d.cuMemUnmap(rows_[row].base, s.mapped); d.cuMemRelease(h); LOG_ERROR("cuMemSetAccess failed: %d %s", (int)r, cu_err(r)); return r; }
-    s.handle = h;
-    s.has_handle = true;
-    resident_mapped_ += s.mapped;
-    return CUDA_SUCCESS;
-}
-void SwapEngine::unmap_row(int row) {
-    const DriverTable &d = drv();
-    ScopedNs t(&st_.host_vmm_ns);
-    Side &s = side_[row];
-    d.cuMemUnmap(rows_[row].base, s.mapped);
-    phys_pool_.emplace(s.mapped, s.handle);
-    phys_pool_bytes_ += s.mapped;
-    s.has_handle = false;
-    resident_mapped_ -= s.mapped;
+    va_free(s.va_off, s.mapped);
+    uint32_t gen = s.gen + 1;
+    CUevent keep_done = s.evict_done;
+    if (s.ready) ready_free_.push_back(s.ready);
+    s = Side{};
+    s.gen = gen;
+    if (keep_done) ready_free_.push_back(keep_done);
+    rows_[row] = VgpuEntry{};
+    succ_[row] = -1;
+    mark_dirty(row);
+    free_rows_.push_back(row);
 }
 
 // ---------------------------------------------------------------------------------------------- events / rings
@@ -474,16 +428,24 @@ CUevent SwapEngine::use_event(uint64_t seq) {
     if (seq + use_ring_.size() <= use_seq_) return nullptr;  // slot was recycled: that use is known complete (note_use)
     return use_ring_[seq % use_ring_.size()];
 }
+CUevent SwapEngine::get_event() {
+    if (!ev_pool_.empty()) { CUevent e = ev_pool_.back(); ev_pool_.pop_back(); return e; }
+    CUevent e = nullptr;
+    if (drv().cuEventCreate(&e, CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) return nullptr;
+    return e;
+}
+void SwapEngine::put_event(CUevent e) { if (e) ev_pool_.push_back(e); }
+
 SwapEngine::Slot &SwapEngine::acquire_slot(std::vector<Slot> &ring, int *cursor) {
     Slot &s = ring[*cursor];
     *cursor = (*cursor + 1) % (int)ring.size();
-    if (s.used) { ScopedNs t(&st_.host_ring_ns); drv().cuEventSynchronize(s.busy); }  // back-pressure: the only place the host waits for the link
+    if (s.used) { ScopedNs t(&pst_.pager_ring_ns); drv().cuEventSynchronize(s.busy); }  // back-pressure of the staged path
     s.used = true;
     s.seq++;
     return s;
 }
 CUdeviceptr SwapEngine::next_span(bool unpack) {
-    if (!cfg_.profile) return 0;
+    if (!profile_.load(std::memory_order_relaxed)) return 0;
     const DriverTable &d = drv();
     if (!d_span_) {
         span_cap_ = 1u << 16;
@@ -505,14 +467,13 @@ void SwapEngine::harvest_spans() {
     for (uint32_t i = 0; i < span_next_ - span_read_; i++) {
         uint64_t a = v[2 * i], b = v[2 * i + 1];
         if (a == ~0ull || b <= a) continue;
-        (span_unpack_[span_read_ + i] ? st_.unpack_span_ms : st_.pack_span_ms) += (double)(b - a) / 1e6;
+        (span_unpack_[span_read_ + i] ? pst_.unpack_span_ms : pst_.pack_span_ms) += (double)(b - a) / 1e6;
     }
     span_read_ = span_next_;
 }
-
 void SwapEngine::prof_begin(CUstream s, CUevent *a) {
     *a = nullptr;
-    if (!cfg_.profile) return;
+    if (!profile_.load(std::memory_order_relaxed)) return;
     const DriverTable &d = drv();
     if (d.cuEventCreate(a, CU_EVENT_DEFAULT) != CUDA_SUCCESS) { *a = nullptr; return; }
     d.cuEventRecord(*a, s);
@@ -535,8 +496,8 @@ void SwapEngine::harvest_prof(bool wait) {
         if (d.cuEventQuery(p.b) == CUDA_SUCCESS) {
             float ms = 0;
             if (d.cuEventElapsedTime(&ms, p.a, p.b) == CUDA_SUCCESS) {
-                if (p.unpack) { st_.unpack_ms += ms; st_.unpack_bytes += p.bytes; }
-                else { st_.pack_ms += ms; st_.pack_bytes += p.bytes; }
+                if (p.unpack) { pst_.unpack_ms += ms; pst_.unpack_bytes += p.bytes; }
+                else { pst_.pack_ms += ms; pst_.pack_bytes += p.bytes; }
             }
             d.cuEventDestroy_v2(p.a);
             d.cuEventDestroy_v2(p.b);
@@ -546,35 +507,486 @@ void SwapEngine::harvest_prof(bool wait) {
     }
     prof_.resize(keep);
 }
+void SwapEngine::set_profile(bool on) { profile_.store(on); }
 
-// ---------------------------------------------------------------------------------------------- page-out / page-in
-CUresult SwapEngine::page_out(const std::vector<uint32_t> &victims, bool finish) {
+void SwapEngine::flush_pager_stats_locked() {
+    SwapStats &p = pst_;
+    st_.page_out_bytes += p.page_out_bytes; st_.page_in_bytes += p.page_in_bytes; st_.evictions += p.evictions;
+    st_.pack_launches += p.pack_launches; st_.unpack_launches += p.unpack_launches; st_.scan_launches += p.scan_launches;
+    st_.scans += p.scans; st_.scan_cache_hits += p.scan_cache_hits; st_.phys_creates += p.phys_creates; st_.phys_reuses += p.phys_reuses;
+    st_.host_slabs += p.host_slabs; st_.host_slabs_local += p.host_slabs_local;
+    st_.pack_ms += p.pack_ms; st_.unpack_ms += p.unpack_ms; st_.pack_span_ms += p.pack_span_ms; st_.unpack_span_ms += p.unpack_span_ms;
+    st_.pager_vmm_ns += p.pager_vmm_ns; st_.pager_scan_ns += p.pager_scan_ns; st_.pager_packsync_ns += p.pager_packsync_ns;
+    st_.pager_ring_ns += p.pager_ring_ns; st_.pager_busy_ns += p.pager_busy_ns; st_.vmm_calls += p.vmm_calls;
+    st_.pack_bytes += p.pack_bytes; st_.unpack_bytes += p.unpack_bytes; st_.direct_out_bytes += p.direct_out_bytes; st_.direct_in_bytes += p.direct_in_bytes;
+    st_.prefetch_issued += p.prefetch_issued; st_.prefetch_wasted += p.prefetch_wasted; st_.clean_evictions += p.clean_evictions;
+    p = SwapStats{};
+}
+
+// ---------------------------------------------------------------------------------------------- physical memory (pager)
+void SwapEngine::pool_phys(size_t mapped, CUmemGenericAllocationHandle h) {
+    phys_pool_.emplace(mapped, h);
+    phys_pool_bytes_ += mapped;
+}
+void SwapEngine::trim_phys_pool(uint64_t keep) {
+    const DriverTable &d = drv();
+    while (!phys_pool_.empty() && phys_pool_bytes_ > keep) {
+        auto it = std::prev(phys_pool_.end());
+        d.cuMemRelease(it->second);
+        phys_pool_bytes_ -= it->first;
+        phys_pool_.erase(it);
+    }
+}
+// A handle of exactly `mapped` bytes: recycled from an evicted row of the same size when there is one (steady state:
+// no cuMemCreate / cuMemRelease at all), else created — after releasing pooled handles of other sizes when the
+// quota would otherwise be exceeded or the device is full.
+CUresult SwapEngine::obtain_phys(size_t mapped, CUmemGenericAllocationHandle *h, bool *pressure) {
+    const DriverTable &d = drv();
+    *pressure = false;
+    auto it = phys_pool_.find(mapped);
+    if (it != phys_pool_.end()) {
+        *h = it->second;
+        phys_pool_bytes_ -= mapped;
+        phys_pool_.erase(it);
+        pst_.phys_reuses++;
+        return CUDA_SUCCESS;
+    }
+    // the caller has already reserved `mapped` in resident_mapped_; the pool may keep what is left under the cap
+    uint64_t held, cap;
+    { std::lock_guard<std::mutex> g(mu_); held = resident_mapped_ + evicting_mapped_; cap = cfg_.resident_cap; }
+    trim_phys_pool(cap > held ? cap - held : 0);
+    CUmemAllocationProp prop = {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = dev_;
+    CUresult r;
+    { ScopedNs t(&pst_.pager_vmm_ns); r = d.cuMemCreate(h, mapped, &prop, 0); }
+    if (r == CUDA_ERROR_OUT_OF_MEMORY && !phys_pool_.empty()) {
+        trim_phys_pool(0);
+        ScopedNs t(&pst_.pager_vmm_ns);
+        r = d.cuMemCreate(h, mapped, &prop, 0);
+    }
+    if (r == CUDA_SUCCESS) pst_.phys_creates++;
+    else if (r == CUDA_ERROR_OUT_OF_MEMORY) *pressure = true;
+    return r;
+}
+
+static void merge_runs(std::vector<std::pair<CUdeviceptr, size_t>> &v) {
+    std::sort(v.begin(), v.end());
+    size_t k = 0;
+    for (size_t i = 0; i < v.size(); i++) {
+        if (k && v[k - 1].first + v[k - 1].second == v[i].first) v[k - 1].second += v[i].second;
+        else v[k++] = v[i];
+    }
+    v.resize(k);
+}
+// One cuMemUnmap per run of adjacent ranges. Every VMM call on B200 / driver 580 waits for the copy in flight
+// (profiles/r02_hostvmm_probe.md), so the number of calls matters more than their size.
+void SwapEngine::unmap_batch(std::vector<std::pair<CUdeviceptr, size_t>> &ranges) {
+    const DriverTable &d = drv();
+    if (ranges.empty()) return;
+    ScopedNs t(&pst_.pager_vmm_ns);
+    std::vector<std::pair<CUdeviceptr, size_t>> runs = ranges;
+    if (unmap_runs_ok_) {
+        merge_runs(runs);
+        bool ok = true;
+        size_t done = 0;
+        for (; done < runs.size(); done++) {
+            pst_.vmm_calls++;
+            if (d.cuMemUnmap(runs[done].first, runs[done].second) != CUDA_SUCCESS) { ok = false; break; }
+        }
+        if (ok) return;
+        // this driver wants one call per mapping: finish the rest range by range (a failed call unmapped nothing)
+        unmap_runs_ok_ = false;
+        CUdeviceptr from = runs[done].first;
+        for (auto &r : ranges) if (r.first >= from) { pst_.vmm_calls++; d.cuMemUnmap(r.first, r.second); }
+        return;
+    }
+    for (auto &r : ranges) { pst_.vmm_calls++; d.cuMemUnmap(r.first, r.second); }
+}
+CUresult SwapEngine::set_access_batch(std::vector<std::pair<CUdeviceptr, size_t>> &ranges) {
+    const DriverTable &d = drv();
+    if (ranges.empty()) return CUDA_SUCCESS;
+    ScopedNs t(&pst_.pager_vmm_ns);
+    CUmemAccessDesc acc = {};
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = dev_;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    std::vector<std::pair<CUdeviceptr, size_t>> runs = ranges;
+    merge_runs(runs);
+    CUresult rc = CUDA_SUCCESS;
+    for (auto &r : runs) {
+        pst_.vmm_calls++;
+        CUresult x = d.cuMemSetAccess(r.first, r.second, &acc, 1);
+        if (x != CUDA_SUCCESS && runs.size() != ranges.size()) {
+            // fall back to one call per mapping inside this run
+            for (auto &q : ranges)
+                if (q.first >= r.first && q.first < r.first + r.second) { pst_.vmm_calls++; x = d.cuMemSetAccess(q.first, q.second, &acc, 1); if (x != CUDA_SUCCESS) rc = x; }
+        } else if (x != CUDA_SUCCESS) rc = x;
+    }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------- predictor (mu_)
+// For every row: which row was touched right after it the last time. Training steps, sweeps and inference loops repeat
+// their access sequence, so following these links from the row just touched names the next misses. Every touch scores
+// the link it arrives by; the pager only prefetches while most recent predictions were right, which keeps random
+// access patterns (no repeating order) from generating page traffic.
+void SwapEngine::observe_touch(int row) {
+    if (row == last_row_) return;
+    if (last_row_ >= 0 && (size_t)last_row_ < succ_.size()) {
+        int32_t predicted = succ_[last_row_];
+        if (predicted >= 0) {
+            pred_hist_ = (pred_hist_ << 1) | (predicted == row ? 1u : 0u);
+            if (pred_count_ < 32) pred_count_++;
+        }
+        succ_[last_row_] = row;
+    }
+    last_row_ = row;
+}
+bool SwapEngine::predictor_confident() const {
+    if (pred_count_ < 8) return false;
+    uint32_t n = pred_count_ < 16 ? pred_count_ : 16;
+    uint32_t mask = n >= 32 ? ~0u : ((1u << n) - 1u);
+    return (uint32_t)__builtin_popcount(pred_hist_ & mask) * 4 >= n * 3;    // >= 75 % of the last n
+}
+void SwapEngine::hint_prefetch(int row) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (!row_live(row)) return;
+    Side &s = side_[row];
+    if (rows_[row].state != VGPU_ST_PAGED_OUT || s.phase != PH_IDLE) return;
+    s.phase = PH_QUEUED;
+    s.demand = false;
+    prefetch_q_.push_back(QEntry{row, s.gen});
+    queued_prefetch_bytes_ += s.mapped;
+    kick_pager_locked();
+}
+void SwapEngine::schedule_prefetch() {
+    if (!cfg_.prefetch_bytes || last_row_ < 0 || resident_mapped_ >= live_mapped_ || !predictor_confident()) return;
+    uint64_t window = std::min<uint64_t>(cfg_.prefetch_bytes, cfg_.resident_cap / 4);
+    uint64_t ahead = queued_prefetch_bytes_ + prefetched_bytes_;
+    int cur = last_row_;
+    bool queued = false;
+    for (int steps = 0; steps < 64 && ahead < window; steps++) {
+        int nxt = (size_t)cur < succ_.size() ? succ_[cur] : -1;
+        if (nxt < 0 || nxt == last_row_ || !row_live(nxt)) break;
+        cur = nxt;
+        Side &s = side_[cur];
+        if (rows_[cur].state != VGPU_ST_PAGED_OUT || s.phase != PH_IDLE) continue;   // resident, loading or already queued
+        if (s.mapped > window) break;
+        s.phase = PH_QUEUED;
+        s.demand = false;
+        prefetch_q_.push_back(QEntry{cur, s.gen});
+        queued_prefetch_bytes_ += s.mapped;
+        ahead += s.mapped;
+        queued = true;
+    }
+    if (queued) kick_pager_locked();
+}
+
+// ---------------------------------------------------------------------------------------------- pager: victims
+void SwapEngine::collect_waits_locked(int row, std::vector<CUevent> *out) {
+    Side &s = side_[row];
+    for (int i = 0; i < s.nuses; i++) if (CUevent e = use_event(s.uses[i])) out->push_back(e);
+    if (s.ready) out->push_back(s.ready);
+}
+
+// Exact-LRU victims for `shortage` bytes: the surplus of the previous GPU scan while it is still valid, else a new scan
+// (asking for scan_lookahead times the need). mu_ is released while the scan runs; what it returns is re-validated
+// against the table afterwards. *evictable < shortage means even all candidates do not suffice.
+CUresult SwapEngine::choose_victims(Lock &lk, uint64_t shortage, std::vector<uint32_t> *victims, uint64_t *evictable) {
+    victims->clear();
+    *evictable = 0;
+    auto valid = [&](const Cand &c) {
+        return c.row < rows_.size() && rows_[c.row].state == VGPU_ST_RESIDENT && rows_[c.row].last_touch == c.touch &&
+               rows_[c.row].base == c.base && side_[c.row].phase == PH_IDLE;
+    };
+    uint64_t freed = 0;
+    {
+        std::deque<Cand> keep = victim_cache_;
+        std::vector<uint32_t> got;
+        uint64_t f = 0;
+        while (f < shortage && !keep.empty()) {
+            Cand cnd = keep.front();
+            keep.pop_front();
+            if (!valid(cnd)) continue;
+            got.push_back(cnd.row);
+            f += side_[cnd.row].mapped;
+        }
+        if (f >= shortage) { *victims = got; victim_cache_.swap(keep); pst_.scan_cache_hits++; *evictable = f; return CUDA_SUCCESS; }
+        victim_cache_.clear();   // not enough left: start over from a fresh scan (nothing was consumed)
+    }
+    for (int attempt = 0; attempt < 3; attempt++) {
+        ScopedNs t(&pst_.pager_scan_ns);
+        CUresult r = sync_table(lk, s_scan_);
+        if (r != CUDA_SUCCESS) return r;
+        std::vector<uint32_t> found;
+        uint64_t found_bytes = 0;
+        bool insufficient = false;
+        int launches = 0;
+        // the table holds requested sizes, the shortage is in mapped (granule-rounded) bytes: ask for a little more per row
+        uint64_t ask = shortage * (uint64_t)(cfg_.scan_lookahead ? cfg_.scan_lookahead : 1);
+        uint32_t n = (uint32_t)rows_.size();
+        uint64_t tick = tick_;
+        CUdeviceptr tbl = d_tbl_;
+        lk.unlock();
+        r = scanner_->scan(tbl, n, ask, tick, s_scan_, &found, &found_bytes, &insufficient, &launches);
+        lk.lock();
+        pst_.scan_launches += launches;
+        pst_.scans++;
+        if (r != CUDA_SUCCESS) { LOG_ERROR("victim scan failed: %d %s", (int)r, cu_err(r)); return r; }
+        // the kernel returns the prefix SET in index order; LRU order within it comes from the host mirror. Rows that
+        // changed while the lock was released (touched, pinned, freed) are dropped.
+        std::vector<Cand> cands;
+        for (uint32_t v : found) {
+            if (v >= rows_.size()) continue;
+            Cand c{v, rows_[v].last_touch, rows_[v].base};
+            if (rows_[v].state == VGPU_ST_RESIDENT && side_[v].phase == PH_IDLE) cands.push_back(c);
+        }
+        std::sort(cands.begin(), cands.end(), [](const Cand &a, const Cand &b) { return a.touch != b.touch ? a.touch < b.touch : a.row < b.row; });
+        freed = 0;
+        victims->clear();
+        size_t k = 0;
+        while (k < cands.size() && freed < shortage) { victims->push_back(cands[k].row); freed += side_[cands[k].row].mapped; k++; }
+        if (freed >= shortage) {
+            for (; k < cands.size(); k++) victim_cache_.push_back(cands[k]);
+            *evictable = freed;
+            return CUDA_SUCCESS;
+        }
+        *evictable = freed;
+        if (insufficient || found.size() == cands.size()) break;    // nothing was lost to races: that is all there is
+    }
+    return CUDA_SUCCESS;
+}
+
+// mu_ held: the victims leave the resident set (the scan must not pick them again, an application thread that touches
+// one queues a demand for it) but keep their physical memory until the pager has unmapped them.
+void SwapEngine::begin_evict_locked(const std::vector<uint32_t> &victims, std::vector<OutItem> *items) {
+    for (uint32_t v : victims) {
+        Side &s = side_[v];
+        OutItem it;
+        it.row = v; it.base = rows_[v].base; it.len = round_up(rows_[v].size, 256); it.mapped = s.mapped;
+        it.host_off = s.host_off; it.has_host = s.has_host;
+        it.copy = s.dirty;                        // clean (block still valid) or never written: nothing to copy
+        collect_waits_locked((int)v, &it.wait);
+        if (s.evict_done) it.wait.push_back(s.evict_done);       // an earlier page-out of this row may still be writing its block
+        rows_[v].state = VGPU_ST_PAGED_OUT;
+        mark_dirty((int)v);
+        s.phase = PH_EVICTING;
+        s.nuses = 0;
+        resident_mapped_ -= s.mapped;
+        evicting_mapped_ += s.mapped;
+        if (s.prefetched) { s.prefetched = false; prefetched_bytes_ -= s.mapped; pst_.prefetch_wasted++; }
+        items->push_back(std::move(it));
+    }
+}
+
+// Direct page-out: the copy engine reads the victims' own ranges (no pack kernel, no staging, no extra HBM traffic). Their
+// physical memory comes back when the copy is done — the pager evicts ahead of need, so nobody waits for that.
+CUresult SwapEngine::evict_direct(Lock &lk, const std::vector<uint32_t> &victims) {
     const DriverTable &d = drv();
     if (victims.empty()) return CUDA_SUCCESS;
-    // one contiguous pinned block for the whole batch so the staging layout equals the host layout (one DMA per
-    // chunk even when the victims are many small buffers); fall back to one block per victim when fragmented
-    std::vector<uint64_t> len(victims.size());
-    uint64_t total = 0;
-    for (size_t i = 0; i < victims.size(); i++) { len[i] = round_up(rows_[victims[i]].size, 256); total += len[i]; }
-    uint64_t block = 0;
-    bool contiguous = host_alloc(total, &block);
-    if (contiguous) {
-        uint64_t o = 0;
-        for (size_t i = 0; i < victims.size(); i++) { side_[victims[i]].host_off = block + o; o += len[i]; }
-    } else {
-        if (victims.size() == 1) { LOG_ERROR("pinned host pool exhausted (%lu MiB in use)", (unsigned long)(host_used_ >> 20)); return CUDA_ERROR_OUT_OF_MEMORY; }
-        for (uint32_t v : victims) { CUresult r = page_out(std::vector<uint32_t>{v}, false); if (r != CUDA_SUCCESS) return r; }
-        return finish ? page_out_finish() : CUDA_SUCCESS;
+    std::vector<OutItem> items;
+    begin_evict_locked(victims, &items);
+    lk.unlock();
+    CUresult rc = CUDA_SUCCESS;
+    for (OutItem &it : items) {
+        it.done = get_event();
+        if (it.copy && !it.has_host) {
+            if (!host_alloc(it.len, &it.host_off)) {
+                lk.lock();
+                bool ok = reclaim_host_blocks(lk, it.len);
+                lk.unlock();
+                if (!ok || !host_alloc(it.len, &it.host_off)) { rc = CUDA_ERROR_OUT_OF_MEMORY; it.failed = true; put_event(it.done); it.done = nullptr; continue; }
+            }
+            it.has_host = true;
+        }
+        CUstream s = it.copy ? s_out_ : s_scan_;
+        for (CUevent e : it.wait) d.cuStreamWaitEvent(s, e, 0);
+        if (it.copy) {
+            unsigned char *hp = host_ptr(it.host_off);
+            for (uint64_t o = 0; o < it.len; o += cfg_.copy_bytes) {
+                uint64_t n = std::min<uint64_t>(cfg_.copy_bytes, it.len - o);
+                CUresult r = d.cuMemcpyDtoHAsync_v2(hp + o, it.base + o, n, s);
+                if (r != CUDA_SUCCESS) { LOG_ERROR("page-out copy failed: %d %s", (int)r, cu_err(r)); rc = r; break; }
+            }
+            pst_.page_out_bytes += it.len;
+            pst_.direct_out_bytes += it.len;
+        } else {
+            pst_.clean_evictions++;
+        }
+        d.cuEventRecord(it.done, s);
     }
-    // order the pack behind the victims' last users
-    for (uint32_t v : victims) {
-        if (CUevent e = use_event(side_[v].use_seq)) d.cuStreamWaitEvent(s_pack_, e, 0);
-        if (side_[v].ready) d.cuStreamWaitEvent(s_pack_, side_[v].ready, 0);   // its own page-in may still be in flight
+    lk.lock();
+    for (OutItem &it : items) {
+        Side &s = side_[it.row];
+        if (it.failed) {
+            // the pinned pool is exhausted: this victim stays resident
+            rows_[it.row].state = VGPU_ST_RESIDENT;
+            mark_dirty((int)it.row);
+            s.phase = PH_IDLE;
+            evicting_mapped_ -= s.mapped;
+            resident_mapped_ += s.mapped;
+            LOG_ERROR("pinned host pool exhausted (%lu MiB in use): cannot page out", (unsigned long)(host_used_.load() >> 20));
+            continue;
+        }
+        s.host_off = it.host_off;
+        s.has_host = it.has_host;
+        if (it.copy) s.dirty = false;              // once the copy is done the block equals the HBM content
+        if (s.ready) { ready_free_.push_back(s.ready); s.ready = nullptr; }   // its waiters are enqueued; the record they refer to is fixed
+        if (s.evict_done) put_event(s.evict_done);
+        s.evict_done = it.done;
+        s.out_slot = -1;
+        rows_[it.row].host_slot = (uint32_t)(s.host_off >> 12);
+        evicting_.push_back(it.row);
     }
+    flush_pager_stats_locked();
+    return rc;
+}
 
+// ---------------------------------------------------------------------------------------------- pager: page-in
+void SwapEngine::begin_load_locked(int row, bool prefetch, InItem *it) {
+    Side &s = side_[row];
+    it->row = row; it->base = rows_[row].base; it->len = round_up(rows_[row].size, 256); it->mapped = s.mapped;
+    it->host_off = s.host_off; it->has_host = s.has_host; it->prefetch = prefetch;
+    it->after = nullptr;
+    s.phase = PH_LOADING;
+    resident_mapped_ += s.mapped;
+    if (!ready_free_.empty()) { it->ready = ready_free_.back(); ready_free_.pop_back(); }
+}
+void SwapEngine::commit_load_locked(InItem &it) {
+    Side &s = side_[it.row];
+    s.handle = it.h;
+    s.has_handle = true;
+    s.phase = PH_IDLE;
+    s.fail = CUDA_SUCCESS;
+    s.dirty = false;
+    s.demand = false;
+    if (s.ready) ready_free_.push_back(s.ready);
+    s.ready = it.ready;
+    rows_[it.row].state = VGPU_ST_RESIDENT | ((s.pins > 0 || s.locked) ? VGPU_ST_PINNED : 0u);
+    if (it.prefetch && s.pins == 0) {
+        // newest on the LRU clock, like a touch: the exact-LRU scan must not take what is about to be used
+        rows_[it.row].last_touch = tick_;
+        s.prefetched = true;
+        prefetched_bytes_ += s.mapped;
+        pst_.prefetch_issued++;
+    }
+    mark_dirty(it.row);
+}
+void SwapEngine::fail_load_locked(InItem &it, CUresult rc) {
+    Side &s = side_[it.row];
+    resident_mapped_ -= s.mapped;
+    if (it.ready) ready_free_.push_back(it.ready);
+    it.ready = nullptr;
+    s.phase = PH_IDLE;
+    s.fail = rc;
+    s.demand = false;
+}
+
+// The device cannot give what the quota promises: on an overcommitted GPU other containers hold the rest (the reference
+// leaves this case to UVM, which pages between processes). Live within what we have: lower the working cap to what is
+// held plus what the device still has, and queue the row again — the pager then makes the room out of our own LRU rows.
+bool SwapEngine::requeue_under_pressure_locked(int row, bool was_demand, size_t free_dev) {
+    Side &s = side_[row];
+    uint64_t held = resident_mapped_ + evicting_mapped_ + (uint64_t)free_dev / gran_ * gran_;
+    if (held < s.mapped || ++s.retries > 8) return false;          // nothing of ours left to give up
+    if (!pressure_ || cfg_.resident_cap > held) {
+        if (!pressure_) LOG_WARN("device %d: physical memory exhausted below the quota; resident cap %lu -> %lu MiB", dev_,
+                                 (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(held >> 20));
+        else LOG_INFO("device %d: upward probe failed; resident cap back to %lu MiB", dev_, (unsigned long)(held >> 20));
+        cfg_.resident_cap = std::min(cfg_.resident_cap, held);
+        pressure_ = true;
+    }
+    pressure_events_++;
+    s.fail = CUDA_SUCCESS;
+    s.phase = PH_QUEUED;
+    s.demand = was_demand;
+    if (was_demand) demand_q_.push_front(QEntry{row, s.gen});
+    else { prefetch_q_.push_front(QEntry{row, s.gen}); queued_prefetch_bytes_ += s.mapped; }
+    return true;
+}
+
+// Direct page-in of a batch: map every row (cuMemMap is cheap), ONE cuMemSetAccess per run of adjacent ranges, then the
+// copy engine writes each row's own range from its pinned block and the row's `ready` event is recorded behind it.
+CUresult SwapEngine::load_direct(Lock &lk, std::vector<InItem> &items) {
+    const DriverTable &d = drv();
+    if (items.empty()) return CUDA_SUCCESS;
+    lk.unlock();
+    std::vector<std::pair<CUdeviceptr, size_t>> ranges;
+    bool pressure_seen = false;
+    for (InItem &it : items) {
+        bool pressure = false;
+        it.rc = obtain_phys(it.mapped, &it.h, &pressure);
+        pressure_seen |= pressure;
+        if (it.rc != CUDA_SUCCESS) continue;
+        {
+            ScopedNs t(&pst_.pager_vmm_ns);
+            it.rc = d.cuMemMap(it.base, it.mapped, 0, it.h, 0);
+        }
+        if (it.rc != CUDA_SUCCESS) { LOG_ERROR("cuMemMap failed: %d %s", (int)it.rc, cu_err(it.rc)); pool_phys(it.mapped, it.h); continue; }
+        ranges.emplace_back(it.base, it.mapped);
+    }
+    CUresult arc = set_access_batch(ranges);
+    for (InItem &it : items) {
+        if (it.rc != CUDA_SUCCESS) continue;
+        if (arc != CUDA_SUCCESS) {
+            LOG_ERROR("cuMemSetAccess failed: %d %s", (int)arc, cu_err(arc));
+            d.cuMemUnmap(it.base, it.mapped); pool_phys(it.mapped, it.h); it.rc = arc;
+            continue;
+        }
+        if (!it.has_host) { if (it.ready) { ev_pool_.push_back(it.ready); it.ready = nullptr; } continue; }   // never written: nothing to load
+        if (!it.ready) it.ready = get_event();
+        if (it.after) d.cuStreamWaitEvent(s_in_, it.after, 0);
+        unsigned char *hp = host_ptr(it.host_off);
+        for (uint64_t o = 0; o < it.len; o += cfg_.copy_bytes) {
+            uint64_t n = std::min<uint64_t>(cfg_.copy_bytes, it.len - o);
+            CUresult r = d.cuMemcpyHtoDAsync_v2(it.base + o, hp + o, n, s_in_);
+            if (r != CUDA_SUCCESS) { LOG_ERROR("page-in copy failed: %d %s", (int)r, cu_err(r)); it.rc = r; break; }
+        }
+        d.cuEventRecord(it.ready, s_in_);
+        pst_.page_in_bytes += it.len;
+        pst_.direct_in_bytes += it.len;
+    }
+    size_t fr = 0, tot = 0;
+    if (pressure_seen) d.cuMemGetInfo_v2(&fr, &tot);
+    lk.lock();
+    CUresult rc = CUDA_SUCCESS;
+    for (InItem &it : items) {
+        if (it.rc == CUDA_SUCCESS) { side_[it.row].retries = 0; commit_load_locked(it); continue; }
+        Side &s = side_[it.row];
+        bool was_demand = s.demand;
+        fail_load_locked(it, it.rc);
+        if (it.rc == CUDA_ERROR_OUT_OF_MEMORY && requeue_under_pressure_locked(it.row, was_demand, fr)) continue;
+        rc = it.rc;
+    }
+    flush_pager_stats_locked();
+    publish_locked();
+    cv_admit_.notify_all();
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------- pager: staged path
+// Pack the victims' dirty bytes into staging slots with the TMA kernel and drain every slot to the victims' pinned
+// blocks. *packed fires when the LAST PACK has read the victims: from then on their physical memory may be recycled,
+// one PCIe transfer earlier than with a direct copy.
+CUresult SwapEngine::staged_out(std::vector<OutItem> &items, CUevent *packed) {
+    const DriverTable &d = drv();
+    *packed = nullptr;
+    for (OutItem &it : items) {
+        if (!it.copy) { pst_.clean_evictions++; for (CUevent e : it.wait) d.cuStreamWaitEvent(s_pack_, e, 0); continue; }
+        if (!it.has_host) {
+            if (!host_alloc(it.len, &it.host_off)) { LOG_ERROR("pinned host pool exhausted (%lu MiB in use)", (unsigned long)(host_used_.load() >> 20)); return CUDA_ERROR_OUT_OF_MEMORY; }
+            it.has_host = true;
+        }
+        // order the pack behind the victim's last users and its own page-in
+        for (CUevent e : it.wait) d.cuStreamWaitEvent(s_pack_, e, 0);
+    }
+    struct OutRun { unsigned char *dst; uint64_t pos, len; };
     std::vector<PackSegment> segs;
+    std::vector<OutRun> runs;
     Slot *slot = nullptr;
-    uint64_t pos = 0, host_pos = 0, slot_host_start = 0;
+    uint64_t pos = 0;
     auto flush = [&]() -> CUresult {
         if (!slot || segs.empty()) return CUDA_SUCCESS;
         int launches = 0;
@@ -583,322 +995,470 @@ CUresult SwapEngine::page_out(const std::vector<uint32_t> &victims, bool finish)
         CUresult r = launch_pack(k_, segs.data(), segs.size(), s_pack_, &launches, next_span(false));
         if (r != CUDA_SUCCESS) return r;
         prof_end(s_pack_, pa, false, pos);
-        st_.pack_launches += launches;
+        pst_.pack_launches += launches;
         // slot.busy doubles as "packed" marker for the copy stream, then is re-recorded as "drained"
         CU_TRY(d.cuEventRecord(slot->busy, s_pack_));
         CU_TRY(d.cuStreamWaitEvent(s_out_, slot->busy, 0));
-        if (tr_) trace_mark(&tr_->d2h, s_out_);
-        CU_TRY(d.cuMemcpyDtoHAsync_v2(host_ptr(block) + slot_host_start, slot->buf, pos, s_out_));
-        if (tr_) trace_mark(&tr_->d2h, s_out_);
+        for (const OutRun &rn : runs) CU_TRY(d.cuMemcpyDtoHAsync_v2(rn.dst, slot->buf + rn.pos, rn.len, s_out_));
         CU_TRY(d.cuEventRecord(slot->busy, s_out_));
-        st_.page_out_bytes += pos;
-        segs.clear();
+        pst_.page_out_bytes += pos;
+        segs.clear(); runs.clear();
         slot = nullptr;
         return CUDA_SUCCESS;
     };
-    for (size_t i = 0; i < victims.size(); i++) {
+    for (OutItem &it : items) {
+        if (!it.copy) continue;
+        unsigned char *hp = host_ptr(it.host_off);
         uint64_t off = 0;
-        while (off < len[i]) {
-            if (!slot) { slot = &acquire_slot(ring_out_, &cur_out_); pos = 0; slot_host_start = host_pos; }
-            uint64_t piece = std::min<uint64_t>(len[i] - off, cfg_.chunk_bytes - pos);
-            segs.push_back(PackSegment{rows_[victims[i]].base + off, slot->buf + pos, piece});
-            side_[victims[i]].out_slot = (int)(slot - ring_out_.data());
-            side_[victims[i]].out_seq = slot->seq;
-            off += piece; pos += piece; host_pos += piece;
+        while (off < it.len) {
+            if (!slot) { slot = &acquire_slot(ring_out_, &cur_out_); pos = 0; }
+            uint64_t piece = std::min<uint64_t>(it.len - off, cfg_.chunk_bytes - pos);
+            segs.push_back(PackSegment{it.base + off, slot->buf + pos, piece});
+            if (!runs.empty() && runs.back().dst + runs.back().len == hp + off && runs.back().pos + runs.back().len == pos) runs.back().len += piece;
+            else runs.push_back(OutRun{hp + off, pos, piece});
+            // the staging slot that carries this row's tail: a page-in of the same row orders its H2D behind THAT slot's
+            // drain only (not behind the whole page-out queue, which would serialise the two link directions)
+            it.out_slot = (int)(slot - ring_out_.data());
+            it.out_seq = slot->seq;
+            off += piece; pos += piece;
             if (pos == cfg_.chunk_bytes || segs.size() == VGPU_PACK_MAX_SEG) { CUresult r = flush(); if (r != CUDA_SUCCESS) return r; }
         }
     }
     { CUresult r = flush(); if (r != CUDA_SUCCESS) return r; }
-    // the victims' physical pages may be recycled as soon as the LAST PACK has read them — not when the DMA is done.
-    // The wait for that pack is deferred to page_out_finish() so the caller can put the page-in's H2D copies on
-    // the wire first (they only need staging slots, not the physical memory being freed here).
-    for (uint32_t v : victims) out_pending_.push_back(v);
-    return finish ? page_out_finish() : CUDA_SUCCESS;
-}
-
-void SwapEngine::reaper_main() {
-    const DriverTable &d = drv();
-    d.cuCtxSetCurrent(ctx_);
-    for (;;) {
-        ReapJob job;
-        {
-            std::unique_lock<std::mutex> lk(rq_mu_);
-            rq_cv_.wait(lk, [&] { return reaper_stop_ || !rq_.empty(); });
-            if (rq_.empty()) return;
-            job = std::move(rq_.front());
-            rq_.pop_front();
-            reaper_busy_ = true;
-        }
-        d.cuEventSynchronize(job.packed);                       // the last pack of the batch has read the victims
-        for (size_t i = 0; i < job.rows.size(); i++) d.cuMemUnmap(job.bases[i], job.mapped[i]);   // no engine lock held
-        {
-            std::lock_guard<std::mutex> g(mu_);
-            for (size_t i = 0; i < job.rows.size(); i++) {
-                Side &s = side_[job.rows[i]];
-                phys_pool_.emplace(s.mapped, s.handle);
-                phys_pool_bytes_ += s.mapped;
-                s.has_handle = false;
-                s.evicting = false;
-                evicting_mapped_ -= s.mapped;
-            }
-            ready_free_.push_back(job.packed);
-        }
-        { std::lock_guard<std::mutex> lk(rq_mu_); reaper_busy_ = false; }
-        reap_cv_.notify_all();
-    }
-}
-
-void SwapEngine::wait_not_evicting(int row) {
-    while (side_[row].evicting) reap_cv_.wait(mu_);            // mu_ is held by the caller; released while waiting
-}
-
-CUresult SwapEngine::page_out_finish() {
-    const DriverTable &d = drv();
-    if (out_pending_.empty()) return CUDA_SUCCESS;
-    CUevent packed = get_event();
-    if (!packed) return CUDA_ERROR_OUT_OF_MEMORY;
-    CU_TRY(d.cuEventRecord(packed, s_pack_));
-    if (cfg_.async_unmap) {
-        ReapJob job;
-        job.packed = packed;
-        for (uint32_t v : out_pending_) {
-            Side &sd = side_[v];
-            job.rows.push_back(v); job.bases.push_back(rows_[v].base); job.mapped.push_back(sd.mapped);
-            sd.evicting = true;
-            sd.has_host = true;
-            resident_mapped_ -= sd.mapped;
-            evicting_mapped_ += sd.mapped;
-            rows_[v].state = VGPU_ST_PAGED_OUT;
-            rows_[v].host_slot = (uint32_t)(sd.host_off >> 12);
-            if (sd.ready) { ready_free_.push_back(sd.ready); sd.ready = nullptr; }
-            mark_dirty((int)v);
-            st_.evictions++;
-        }
-        out_pending_.clear();
-        { std::lock_guard<std::mutex> lk(rq_mu_); rq_.push_back(std::move(job)); }
-        rq_cv_.notify_one();
-        return CUDA_SUCCESS;
-    }
-    { ScopedNs t(&st_.host_packsync_ns); CU_TRY(d.cuEventSynchronize(packed)); }
-    ready_free_.push_back(packed);
-    for (uint32_t v : out_pending_) {
-        unmap_row((int)v);
-        side_[v].has_host = true;
-        rows_[v].state = VGPU_ST_PAGED_OUT;
-        rows_[v].host_slot = (uint32_t)(side_[v].host_off >> 12);
-        if (side_[v].ready) { ready_free_.push_back(side_[v].ready); side_[v].ready = nullptr; }
-        mark_dirty((int)v);
-        st_.evictions++;
-    }
-    out_pending_.clear();
+    *packed = get_event();
+    if (!*packed) return CUDA_ERROR_OUT_OF_MEMORY;
+    CU_TRY(d.cuEventRecord(*packed, s_pack_));
     return CUDA_SUCCESS;
 }
 
-// Page-in is planned first (which pieces of which rows travel in which staging-slot job), then runs in two phases:
-//   stage  : host -> staging H2D copies for as many jobs as there are free staging slots, WITHOUT blocking. Needs
-//            neither the rows' physical memory nor their mappings, so it is issued before the victims are unmapped
-//            and overlaps the VMM calls (0.3-0.8 ms per remap on B200, profiles/README.md) with the transfer;
-//   finish : map the rows, then for every job (staged or not) launch the unpack kernel behind its H2D.
-CUresult SwapEngine::page_in_plan(const std::vector<int> &rows) {
-    in_jobs_.clear();
+void SwapEngine::plan_staged_in(const InItem &it, std::vector<InJob> *jobs) {
+    jobs->clear();
+    if (!it.has_host) return;
+    unsigned char *hp = host_ptr(it.host_off);
     InJob cur;
-    uint64_t pos = 0;
-    auto close = [&]() { if (!cur.segs.empty()) { cur.bytes = pos; in_jobs_.push_back(std::move(cur)); cur = InJob(); pos = 0; } };
-    for (int r : rows) {
-        uint64_t len = round_up(rows_[r].size, 256), off = 0;
-        while (off < len) {
-            uint64_t piece = std::min<uint64_t>(len - off, cfg_.chunk_bytes - pos);
-            unsigned char *src = host_ptr(side_[r].host_off) + off;
-            if (!cur.runs.empty() && cur.runs.back().src + cur.runs.back().len == src && cur.runs.back().pos + cur.runs.back().len == pos) cur.runs.back().len += piece;
-            else cur.runs.push_back(InRun{src, pos, piece});
-            cur.segs.push_back(PackSegment{pos, rows_[r].base + off, piece});   // src = offset inside the slot, fixed up at issue time
-            off += piece; pos += piece;
-            if (off == len) cur.done_rows.push_back(r);
-            if (pos == cfg_.chunk_bytes || cur.segs.size() == VGPU_PACK_MAX_SEG) close();
-        }
+    uint64_t pos = 0, off = 0;
+    while (off < it.len) {
+        uint64_t piece = std::min<uint64_t>(it.len - off, cfg_.chunk_bytes - pos);
+        if (!cur.runs.empty() && cur.runs.back().src + cur.runs.back().len == hp + off && cur.runs.back().pos + cur.runs.back().len == pos) cur.runs.back().len += piece;
+        else cur.runs.push_back(InRun{hp + off, pos, piece});
+        cur.segs.push_back(PackSegment{pos, it.base + off, piece});   // src = offset inside the slot, fixed up at issue time
+        off += piece; pos += piece;
+        if (pos == cfg_.chunk_bytes || cur.segs.size() == VGPU_PACK_MAX_SEG) { cur.bytes = pos; jobs->push_back(std::move(cur)); cur = InJob(); pos = 0; }
     }
-    close();
-    return CUDA_SUCCESS;
+    if (!cur.segs.empty()) { cur.bytes = pos; jobs->push_back(std::move(cur)); }
 }
 
 CUresult SwapEngine::in_issue_copies(InJob &j) {
     const DriverTable &d = drv();
-    if (tr_) trace_mark(&tr_->h2d, s_in_);
     for (const InRun &r : j.runs) {
         CU_TRY(d.cuMemcpyHtoDAsync_v2(j.slot->buf + r.pos, r.src, r.len, s_in_));
-        st_.page_in_bytes += r.len;
+        pst_.page_in_bytes += r.len;
     }
-    if (tr_) trace_mark(&tr_->h2d, s_in_);
-    CU_TRY(d.cuEventRecord(j.slot->busy, s_in_));     // "loaded"; re-recorded as "unpacked" in finish
+    CU_TRY(d.cuEventRecord(j.slot->busy, s_in_));     // "loaded"; re-recorded as "unpacked" after the unpack launch
     return CUDA_SUCCESS;
 }
 
-CUresult SwapEngine::page_in_stage(const std::vector<int> &rows) {
+// The latency path of a demand miss that finds no free physical memory and no eviction in flight:
+//   packs of the victims (short) -> H2D of the incoming row into staging (needs no physical memory yet) -> wait for the
+//   last pack, unmap the victims -> map the incoming row with a recycled handle -> unpack behind the H2D.
+// The incoming transfer starts before the victims' memory is free, and that memory is free after an HBM-speed pack
+// instead of after a PCIe transfer.
+CUresult SwapEngine::swap_staged(Lock &lk, int row, const std::vector<uint32_t> &victims) {
     const DriverTable &d = drv();
-    for (int r : rows) {
-        // a row that was paged out moments ago: its D2H may still be in flight -> order the H2D behind that chunk
-        // only (not behind the whole page-out queue, which would serialise the two link directions)
+    std::vector<OutItem> outs;
+    begin_evict_locked(victims, &outs);
+    InItem in;
+    {
+        Side &s = side_[row];
+        in.row = row; in.base = rows_[row].base; in.len = round_up(rows_[row].size, 256); in.mapped = s.mapped;
+        in.host_off = s.host_off; in.has_host = s.has_host; in.prefetch = false;
+        s.phase = PH_LOADING;                      // owned by the pager from here on (accounted once the victims are gone)
+        if (!ready_free_.empty()) { in.ready = ready_free_.back(); ready_free_.pop_back(); }
+    }
+    int in_out_slot = side_[row].out_slot;
+    uint64_t in_out_seq = side_[row].out_seq;
+    lk.unlock();
+
+    CUevent packed = nullptr;
+    CUresult rc = staged_out(outs, &packed);
+    std::vector<InJob> jobs;
+    size_t staged = 0;
+    if (rc == CUDA_SUCCESS) {
+        // a row that was paged out moments ago: its D2H may still be in flight -> order the H2D behind that chunk only
+        if (in_out_slot >= 0 && ring_out_[in_out_slot].seq == in_out_seq) d.cuStreamWaitEvent(s_in_, ring_out_[in_out_slot].busy, 0);
+        plan_staged_in(in, &jobs);
+        for (InJob &j : jobs) {
+            // A slot staged here holds data until its unpack has been launched below; its `busy` event meanwhile only says
+            // "loaded". So never wrap around onto a slot this admission has already filled.
+            if (staged == ring_in_.size()) break;
+            Slot &s = ring_in_[cur_in_];
+            if (s.used && d.cuEventQuery(s.busy) != CUDA_SUCCESS) break;   // never block here
+            cur_in_ = (cur_in_ + 1) % (int)ring_in_.size();
+            s.used = true;
+            s.seq++;
+            j.slot = &s;
+            staged++;
+            if ((rc = in_issue_copies(j)) != CUDA_SUCCESS) break;
+        }
+    }
+    // victims: wait for the last pack, then their ranges can go
+    std::vector<std::pair<CUdeviceptr, size_t>> ranges;
+    if (packed) { ScopedNs t(&pst_.pager_packsync_ns); d.cuEventSynchronize(packed); put_event(packed); }
+    else if (rc != CUDA_SUCCESS) d.cuStreamSynchronize(s_pack_);
+    bool evicted = rc == CUDA_SUCCESS;
+    if (evicted) {
+        for (OutItem &it : outs) ranges.emplace_back(it.base, it.mapped);
+        unmap_batch(ranges);
+    }
+    lk.lock();
+    for (OutItem &it : outs) {
+        Side &s = side_[it.row];
+        if (!evicted) {                              // nothing was unmapped: the victims stay where they are
+            s.host_off = it.host_off; s.has_host = it.has_host;   // a block taken for it stays its block
+            rows_[it.row].state = VGPU_ST_RESIDENT;
+            s.phase = PH_IDLE;
+            evicting_mapped_ -= s.mapped;
+            resident_mapped_ += s.mapped;
+            mark_dirty((int)it.row);
+            continue;
+        }
+        pool_phys(s.mapped, s.handle);
+        s.has_handle = false;
+        s.host_off = it.host_off; s.has_host = it.has_host;
+        if (it.copy) { s.dirty = false; s.out_slot = it.out_slot; s.out_seq = it.out_seq; }
+        if (s.ready) { ready_free_.push_back(s.ready); s.ready = nullptr; }
+        rows_[it.row].host_slot = (uint32_t)(s.host_off >> 12);
+        evicting_mapped_ -= s.mapped;
+        pst_.evictions++;
+        if (s.demand) { s.phase = PH_QUEUED; demand_q_.push_back(QEntry{(int)it.row, s.gen}); }
+        else s.phase = PH_IDLE;
+        mark_dirty((int)it.row);
+    }
+    if (rc != CUDA_SUCCESS) {
+        side_[row].phase = PH_IDLE;
+        side_[row].fail = rc;
+        side_[row].demand = false;
+        if (in.ready) ready_free_.push_back(in.ready);
+        flush_pager_stats_locked();
+        cv_admit_.notify_all();
+        return rc;
+    }
+    resident_mapped_ += in.mapped;
+    lk.unlock();
+
+    bool pressure = false;
+    rc = obtain_phys(in.mapped, &in.h, &pressure);
+    if (rc == CUDA_SUCCESS) {
+        { ScopedNs t(&pst_.pager_vmm_ns); rc = d.cuMemMap(in.base, in.mapped, 0, in.h, 0); }
+        if (rc != CUDA_SUCCESS) pool_phys(in.mapped, in.h);
+    }
+    if (rc == CUDA_SUCCESS) {
+        std::vector<std::pair<CUdeviceptr, size_t>> r1{{in.base, in.mapped}};
+        rc = set_access_batch(r1);
+        if (rc != CUDA_SUCCESS) { d.cuMemUnmap(in.base, in.mapped); pool_phys(in.mapped, in.h); }
+    }
+    if (rc == CUDA_SUCCESS && !jobs.empty()) {
+        if (!in.ready) in.ready = get_event();
+        for (InJob &j : jobs) {
+            if (!j.slot) {
+                j.slot = &acquire_slot(ring_in_, &cur_in_);
+                if ((rc = in_issue_copies(j)) != CUDA_SUCCESS) break;
+            }
+            for (PackSegment &sg : j.segs) sg.src += j.slot->buf;
+            d.cuStreamWaitEvent(s_unpack_, j.slot->busy, 0);
+            int launches = 0;
+            CUevent pa;
+            prof_begin(s_unpack_, &pa);
+            rc = launch_pack(k_, j.segs.data(), j.segs.size(), s_unpack_, &launches, next_span(true));
+            if (rc != CUDA_SUCCESS) break;
+            prof_end(s_unpack_, pa, true, j.bytes);
+            pst_.unpack_launches += launches;
+            d.cuEventRecord(j.slot->busy, s_unpack_);
+        }
+        if (rc == CUDA_SUCCESS) d.cuEventRecord(in.ready, s_unpack_);
+    } else if (rc == CUDA_SUCCESS && in.ready) { ev_pool_.push_back(in.ready); in.ready = nullptr; }
+    size_t fr = 0, tot = 0;
+    if (pressure) d.cuMemGetInfo_v2(&fr, &tot);
+    lk.lock();
+    in.rc = rc;
+    if (rc == CUDA_SUCCESS) { side_[row].retries = 0; commit_load_locked(in); }
+    else {
+        // staged copies that were issued for nothing only wrote staging slots; the row stays paged out
+        fail_load_locked(in, rc);
+        if (rc == CUDA_ERROR_OUT_OF_MEMORY && requeue_under_pressure_locked(row, true, fr)) rc = CUDA_SUCCESS;
+        else LOG_ERROR("page-in of row %d failed: %d %s", row, (int)rc, cu_err(rc));
+    }
+    flush_pager_stats_locked();
+    publish_locked();
+    cv_admit_.notify_all();
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------- pager: main loop
+bool SwapEngine::step_zombies(Lock &lk) {
+    const DriverTable &d = drv();
+    if (zombies_.empty()) return false;
+    std::vector<uint32_t> ready_rows;
+    for (auto it = zombies_.begin(); it != zombies_.end();) {
+        Side &s = side_[*it];
+        bool busy = false;
+        for (int i = 0; i < s.nuses && !busy; i++) if (CUevent e = use_event(s.uses[i])) busy = d.cuEventQuery(e) != CUDA_SUCCESS;
+        if (!busy && s.ready) busy = d.cuEventQuery(s.ready) != CUDA_SUCCESS;
+        if (!busy && s.evict_done) busy = d.cuEventQuery(s.evict_done) != CUDA_SUCCESS;
+        if (busy) { ++it; continue; }
+        ready_rows.push_back(*it);
+        it = zombies_.erase(it);
+    }
+    if (ready_rows.empty()) return false;
+    std::vector<std::pair<CUdeviceptr, size_t>> ranges;
+    for (uint32_t r : ready_rows) ranges.emplace_back(rows_[r].base, side_[r].mapped);
+    lk.unlock();
+    unmap_batch(ranges);
+    lk.lock();
+    for (uint32_t r : ready_rows) {
         Side &s = side_[r];
-        if (s.out_slot >= 0 && ring_out_[s.out_slot].seq == s.out_seq) CU_TRY(d.cuStreamWaitEvent(s_in_, ring_out_[s.out_slot].busy, 0));
+        pool_phys(s.mapped, s.handle);
+        s.has_handle = false;
+        resident_mapped_ -= s.mapped;
+        if (s.has_host) release_host_range(s.host_off, round_up(rows_[r].size, 256));
+        s.has_host = false;
+        retire_row_locked((int)r);
+    }
+    flush_pager_stats_locked();
+    publish_locked();
+    cv_admit_.notify_all();
+    return true;
+}
+
+// Evictions whose copy is done: unmap (one call per run of adjacent ranges), recycle the handles.
+bool SwapEngine::step_reap(Lock &lk) {
+    const DriverTable &d = drv();
+    if (evicting_.empty()) return false;
+    std::vector<uint32_t> done;
+    for (auto it = evicting_.begin(); it != evicting_.end();) {
+        Side &s = side_[*it];
+        if (s.phase != PH_EVICTING) { it = evicting_.erase(it); continue; }
+        if (s.evict_done && d.cuEventQuery(s.evict_done) != CUDA_SUCCESS) { ++it; continue; }
+        done.push_back(*it);
+        it = evicting_.erase(it);
+        if (done.size() >= 4u * cfg_.batch_rows) break;
+    }
+    if (done.empty()) return false;
+    std::vector<std::pair<CUdeviceptr, size_t>> ranges;
+    for (uint32_t r : done) ranges.emplace_back(rows_[r].base, side_[r].mapped);
+    lk.unlock();
+    unmap_batch(ranges);
+    lk.lock();
+    for (uint32_t r : done) {
+        Side &s = side_[r];
+        pool_phys(s.mapped, s.handle);
+        s.has_handle = false;
+        evicting_mapped_ -= s.mapped;
+        pst_.evictions++;
+        put_event(s.evict_done);
+        s.evict_done = nullptr;
+        if (s.demand) { s.phase = PH_QUEUED; demand_q_.push_front(QEntry{(int)r, s.gen}); }   // touched while it was on its way out
+        else s.phase = PH_IDLE;
+    }
+    flush_pager_stats_locked();
+    publish_locked();
+    cv_admit_.notify_all();
+    return true;
+}
+
+bool SwapEngine::step_demand(Lock &lk) {
+    while (!demand_q_.empty()) {
+        QEntry e = demand_q_.front();
+        if ((size_t)e.row < side_.size() && side_[e.row].gen == e.gen && side_[e.row].phase == PH_QUEUED && side_[e.row].demand) break;
+        demand_q_.pop_front();
+    }
+    if (demand_q_.empty()) return false;
+    const int row = demand_q_.front().row;
+    const uint64_t need = side_[row].mapped;
+    if (pressure_ && cfg_.resident_cap < quota_cap_ && (++pressure_probe_ & 31u) == 0) {
+        // probe upwards: the other tenants may have let go; a failed cuMemCreate simply lowers the cap again
+        cfg_.resident_cap = std::min(quota_cap_, cfg_.resident_cap + need);
+        if (cfg_.resident_cap == quota_cap_) pressure_ = false;
+    }
+    auto fail = [&](CUresult rc) {
+        demand_q_.pop_front();
+        side_[row].phase = PH_IDLE;
+        side_[row].fail = rc;
+        side_[row].demand = false;
+        cv_admit_.notify_all();
+        return true;
+    };
+    if (need > cfg_.resident_cap) return fail(CUDA_ERROR_OUT_OF_MEMORY);
+    int64_t free_now = free_phys_locked();
+    if (free_now >= (int64_t)need) {
+        // room is there (freed by the pager ahead of need, or never used): map + direct copy, together with whatever
+        // other demanded rows fit
+        std::vector<InItem> items;
+        while (!demand_q_.empty() && items.size() < cfg_.batch_rows) {
+            QEntry e = demand_q_.front();
+            Side &s = side_[e.row];
+            bool ok = s.gen == e.gen && s.phase == PH_QUEUED && s.demand;
+            if (ok && free_phys_locked() < (int64_t)s.mapped) break;
+            demand_q_.pop_front();
+            if (!ok) continue;
+            items.emplace_back();
+            begin_load_locked(e.row, false, &items.back());
+            Side &sr = side_[e.row];
+            if (sr.out_slot >= 0 && ring_out_[sr.out_slot].seq == sr.out_seq) items.back().after = ring_out_[sr.out_slot].busy;
+            sr.out_slot = -1;
+        }
+        load_direct(lk, items);
+        return true;
+    }
+    if (free_now + (int64_t)evicting_mapped_ >= (int64_t)need) return false;     // on its way: the reap will free it
+    const uint64_t shortage = (uint64_t)((int64_t)need - free_now - (int64_t)evicting_mapped_);
+    std::vector<uint32_t> victims;
+    uint64_t evictable = 0;
+    CUresult r = choose_victims(lk, shortage, &victims, &evictable);
+    if (r != CUDA_SUCCESS) return fail(r);
+    // the lock was released during the scan: the world may have moved on
+    if (demand_q_.empty() || demand_q_.front().row != row || side_[row].phase != PH_QUEUED) return true;
+    if (evictable < shortage) {
+        bool in_flight = evicting_mapped_ > 0 || !zombies_.empty();
+        if (in_flight) return false;
+        LOG_ERROR("resident quota %lu MiB cannot hold the working set of this launch (need %lu MiB more, evictable %lu MiB)",
+                  (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(shortage >> 20), (unsigned long)(evictable >> 20));
+        return fail(CUDA_ERROR_OUT_OF_MEMORY);
+    }
+    if (evicting_mapped_ == 0) {
+        demand_q_.pop_front();
+        swap_staged(lk, row, victims);           // latency path
+    } else if (evict_direct(lk, victims) != CUDA_SUCCESS) {   // the pipeline is running: add to it and wait for the reap
+        fail_demands_locked(CUDA_ERROR_OUT_OF_MEMORY);
+    }
+    return true;
+}
+
+bool SwapEngine::step_prefetch(Lock &lk) {
+    std::vector<InItem> items;
+    while (!prefetch_q_.empty() && items.size() < cfg_.batch_rows) {
+        QEntry e = prefetch_q_.front();
+        bool ok = (size_t)e.row < side_.size() && side_[e.row].gen == e.gen && side_[e.row].phase == PH_QUEUED && !side_[e.row].demand;
+        if (!ok) { prefetch_q_.pop_front(); continue; }
+        Side &s = side_[e.row];
+        if (free_phys_locked() < (int64_t)s.mapped) break;
+        prefetch_q_.pop_front();
+        queued_prefetch_bytes_ -= s.mapped;
+        items.emplace_back();
+        begin_load_locked(e.row, true, &items.back());
+        if (s.out_slot >= 0 && ring_out_[s.out_slot].seq == s.out_seq) items.back().after = ring_out_[s.out_slot].busy;
         s.out_slot = -1;
     }
-    CU_TRY(page_in_plan(rows));
-    size_t staged = 0;
-    for (InJob &j : in_jobs_) {
-        // A slot staged here holds data until page_in_finish() has launched its unpack; its `busy` event meanwhile only
-        // says "loaded". So never wrap around onto a slot this admission has already filled — an H2D that completed
-        // quickly would otherwise let job N+ring overwrite job N's staging before it is unpacked.
-        if (staged == ring_in_.size()) break;
-        Slot &s = ring_in_[cur_in_];
-        if (s.used && d.cuEventQuery(s.busy) != CUDA_SUCCESS) break;   // never block here
-        cur_in_ = (cur_in_ + 1) % (int)ring_in_.size();
-        s.used = true;
-        s.seq++;
-        j.slot = &s;
-        staged++;
-        CU_TRY(in_issue_copies(j));
-    }
-    return CUDA_SUCCESS;
+    if (items.empty()) return false;
+    load_direct(lk, items);
+    return true;
 }
 
-CUresult SwapEngine::page_in_finish(const std::vector<int> &rows) {
-    const DriverTable &d = drv();
-    for (int r : rows) {
-        CUresult rc = map_row(r);
-        if (rc != CUDA_SUCCESS) return rc;
-    }
-    std::vector<PendingHost> fresh;
-    for (InJob &j : in_jobs_) {
-        if (!j.slot) {
-            j.slot = &acquire_slot(ring_in_, &cur_in_);
-            CU_TRY(in_issue_copies(j));
-        }
-        for (PackSegment &sg : j.segs) sg.src += j.slot->buf;
-        CU_TRY(d.cuStreamWaitEvent(s_unpack_, j.slot->busy, 0));
-        int launches = 0;
-        CUevent pa;
-        prof_begin(s_unpack_, &pa);
-        CUresult r = launch_pack(k_, j.segs.data(), j.segs.size(), s_unpack_, &launches, next_span(true));
-        if (r != CUDA_SUCCESS) return r;
-        prof_end(s_unpack_, pa, true, j.bytes);
-        st_.unpack_launches += launches;
-        CU_TRY(d.cuEventRecord(j.slot->busy, s_unpack_));
-        for (int row : j.done_rows) {
-            CUevent ev = get_event();
-            if (!ev) return CUDA_ERROR_OUT_OF_MEMORY;
-            CU_TRY(d.cuEventRecord(ev, s_unpack_));
-            side_[row].ready = ev;
-            fresh.push_back(PendingHost{side_[row].host_off, round_up(rows_[row].size, 256), nullptr});
-            side_[row].has_host = false;
-            rows_[row].state = VGPU_ST_RESIDENT;
-            mark_dirty(row);
-        }
-    }
-    in_jobs_.clear();
-    if (!fresh.empty()) {
-        // the pinned ranges go back to the pool only after the H2D copies above have READ them (a later page-out
-        // would otherwise overwrite them): parked with one event, reaped by host_alloc() once it has fired
-        CUevent ev = get_event();
-        if (!ev) return CUDA_ERROR_OUT_OF_MEMORY;
-        CU_TRY(d.cuEventRecord(ev, s_in_));
-        for (size_t i = 0; i < fresh.size(); i++) { fresh[i].done = (i + 1 == fresh.size()) ? ev : nullptr; pending_host_.push_back(fresh[i]); }
-    }
-    return CUDA_SUCCESS;
-}
-
-CUevent SwapEngine::get_event() {
-    if (!ready_free_.empty()) { CUevent e = ready_free_.back(); ready_free_.pop_back(); return e; }
-    CUevent e = nullptr;
-    if (drv().cuEventCreate(&e, CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) return nullptr;
-    return e;
-}
-
-void SwapEngine::reap_pending_host(bool wait) {
-    const DriverTable &d = drv();
-    // entries are in issue order; an entry without its own event completes with the next one that has one
-    size_t done_upto = 0;
-    for (size_t i = 0; i < pending_host_.size(); i++) {
-        if (!pending_host_[i].done) continue;
-        if (wait) d.cuEventSynchronize(pending_host_[i].done);
-        if (d.cuEventQuery(pending_host_[i].done) != CUDA_SUCCESS) break;
-        done_upto = i + 1;
-    }
-    for (size_t i = 0; i < done_upto; i++) {
-        release_host_range(pending_host_[i].off, pending_host_[i].len);
-        if (pending_host_[i].done) ready_free_.push_back(pending_host_[i].done);
-    }
-    pending_host_.erase(pending_host_.begin(), pending_host_.begin() + done_upto);
-}
-
-void SwapEngine::release_host_range(uint64_t off, uint64_t len) {
-    // page_out carves one block per batch; every victim gives back exactly its own 256-byte-granular sub-range
-    map_free(slabs_[off >> 44].free, off & ((1ull << 44) - 1), len);
-    host_used_ = host_used_ > len ? host_used_ - len : 0;
-}
-
-CUresult SwapEngine::make_room(uint64_t need_mapped, bool finish) {
-    if (need_mapped > cfg_.resident_cap) return CUDA_ERROR_OUT_OF_MEMORY;
-    if (resident_mapped_ + need_mapped <= cfg_.resident_cap) return CUDA_SUCCESS;
-    const uint64_t deficit = resident_mapped_ + need_mapped - cfg_.resident_cap;
+// Everything that is queued (demanded rows waiting for room, rows the predictor wants) must fit next to what is
+// resident: evict the LRU rows ahead of need so that both DMA queues always have work.
+bool SwapEngine::step_evict_ahead(Lock &lk) {
+    uint64_t wanted = queued_prefetch_bytes_;
+    for (const QEntry &e : demand_q_)
+        if ((size_t)e.row < side_.size() && side_[e.row].gen == e.gen && side_[e.row].phase == PH_QUEUED && side_[e.row].demand) wanted += side_[e.row].mapped;
+    if (resident_mapped_ + wanted <= cfg_.resident_cap) return false;
+    uint64_t shortage = resident_mapped_ + wanted - cfg_.resident_cap;
     std::vector<uint32_t> victims;
-    uint64_t freed = 0;
-    auto valid = [&](const Cand &c) {
-        return c.row < rows_.size() && rows_[c.row].state == VGPU_ST_RESIDENT && rows_[c.row].last_touch == c.touch && rows_[c.row].base == c.base;
-    };
-    // 1. leftovers of the previous scan (still the exact LRU prefix, see swap.h)
-    {
-        std::deque<Cand> keep = victim_cache_;
-        std::vector<uint32_t> got;
-        uint64_t f = 0;
-        while (f < deficit && !keep.empty()) {
-            Cand cnd = keep.front();
-            keep.pop_front();
-            if (!valid(cnd)) continue;
-            got.push_back(cnd.row);
-            f += rows_[cnd.row].size;
-        }
-        if (f >= deficit) { victims = got; freed = f; victim_cache_.swap(keep); st_.scan_cache_hits++; }
-        else victim_cache_.clear();   // not enough left: start over from a fresh scan (nothing was consumed)
+    uint64_t evictable = 0;
+    if (choose_victims(lk, shortage, &victims, &evictable) != CUDA_SUCCESS || victims.empty()) {
+        // nothing can be evicted (everything resident is in use): wishes are dropped, demands keep waiting for a release
+        bool had = !prefetch_q_.empty();
+        drop_prefetch_queue_locked();
+        return had;
     }
-    // 2. GPU scan, asking for `scan_lookahead_` times the deficit so the next evictions need no scan
-    if (victims.empty()) {
-        ScopedNs t(&st_.host_scan_ns);
-        CUresult r = sync_table(s_scan_);
-        if (r != CUDA_SUCCESS) return r;
-        std::vector<uint32_t> found;
-        uint64_t found_bytes = 0;
-        bool insufficient = false;
-        int launches = 0;
-        uint64_t ask = deficit * (uint64_t)(scan_lookahead_ ? scan_lookahead_ : 1);
-        r = scanner_->scan(d_tbl_, (uint32_t)rows_.size(), ask, tick_, s_scan_, &found, &found_bytes, &insufficient, &launches);
-        st_.scan_launches += launches;
-        st_.scans++;
-        if (r != CUDA_SUCCESS) { LOG_ERROR("victim scan failed: %d %s", (int)r, cu_err(r)); return r; }
-        if (found_bytes < deficit) {
-            LOG_ERROR("resident quota %lu MiB cannot hold the working set of this launch (need %lu MiB more, evictable %lu MiB)",
-                      (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(deficit >> 20), (unsigned long)(found_bytes >> 20));
-            return CUDA_ERROR_OUT_OF_MEMORY;
+    if (evictable < shortage && wanted == queued_prefetch_bytes_ && wanted > 0) {
+        // prefetch must never squeeze out what is in use: drop the tail of the wish list instead
+        while (!prefetch_q_.empty() && evictable < shortage) {
+            QEntry e = prefetch_q_.back();
+            prefetch_q_.pop_back();
+            if ((size_t)e.row >= side_.size() || side_[e.row].gen != e.gen || side_[e.row].phase != PH_QUEUED || side_[e.row].demand) continue;
+            side_[e.row].phase = PH_IDLE;
+            queued_prefetch_bytes_ -= side_[e.row].mapped;
+            shortage = shortage > side_[e.row].mapped ? shortage - side_[e.row].mapped : 0;
         }
-        // the kernel returns the prefix SET in index order; LRU order within it comes from the host mirror
-        std::sort(found.begin(), found.end(), [&](uint32_t a, uint32_t b) {
-            if (rows_[a].last_touch != rows_[b].last_touch) return rows_[a].last_touch < rows_[b].last_touch;
-            return a < b;
-        });
-        size_t k = 0;
-        while (k < found.size() && freed < deficit) { victims.push_back(found[k]); freed += rows_[found[k]].size; k++; }
-        for (; k < found.size(); k++) victim_cache_.push_back(Cand{found[k], rows_[found[k]].last_touch, rows_[found[k]].base});
+        if (shortage == 0) { victim_cache_.clear(); return true; }
     }
-    // the victims' physical handles are now pooled; get_phys() re-maps a same-size one under the incoming buffer
-    // (no cuMemCreate/cuMemRelease in steady state) and only trims the pool when it has to create
-    return page_out(victims, finish);
+    if (evict_direct(lk, victims) != CUDA_SUCCESS) {
+        // the pinned pool is exhausted: nothing more can be paged out
+        drop_prefetch_queue_locked();
+        fail_demands_locked(CUDA_ERROR_OUT_OF_MEMORY);
+    }
+    return true;
+}
+
+void SwapEngine::drop_prefetch_queue_locked() {
+    for (const QEntry &e : prefetch_q_) {
+        if ((size_t)e.row >= side_.size() || side_[e.row].gen != e.gen || side_[e.row].phase != PH_QUEUED || side_[e.row].demand) continue;
+        side_[e.row].phase = PH_IDLE;
+    }
+    prefetch_q_.clear();
+    queued_prefetch_bytes_ = 0;
+}
+void SwapEngine::fail_demands_locked(CUresult rc) {
+    for (const QEntry &e : demand_q_) {
+        if ((size_t)e.row >= side_.size() || side_[e.row].gen != e.gen || side_[e.row].phase != PH_QUEUED || !side_[e.row].demand) continue;
+        side_[e.row].phase = PH_IDLE;
+        side_[e.row].fail = rc;
+        side_[e.row].demand = false;
+    }
+    demand_q_.clear();
+    cv_admit_.notify_all();
+}
+
+void SwapEngine::pager_main() {
+    const DriverTable &d = drv();
+    d.cuCtxSetCurrent(ctx_);
+    Lock lk(mu_);
+    for (;;) {
+        if (stop_) break;
+        uint64_t t0 = mono_ns();
+        bool progress = false;
+        progress |= step_zombies(lk);
+        progress |= step_reap(lk);
+        progress |= step_demand(lk);
+        progress |= step_prefetch(lk);
+        progress |= step_evict_ahead(lk);
+        if (progress) { pst_.pager_busy_ns += mono_ns() - t0; continue; }
+        bool outstanding = !evicting_.empty() || !zombies_.empty() || !demand_q_.empty();
+        if (!outstanding) {
+            // idle: fold the profiling samples in while nobody waits for the link
+            if (!prof_.empty() || span_read_ < span_next_) { lk.unlock(); harvest_prof(false); lk.lock(); }
+            flush_pager_stats_locked();
+            pager_idle_ = true;
+            cv_admit_.notify_all();
+            cv_pager_.wait(lk, [&] { return stop_ || kick_; });
+            kick_ = false;
+            pager_idle_ = false;
+        } else {
+            // GPU work outstanding (copies to reap, users to wait for): poll at a period far below one transfer
+            cv_pager_.wait_for(lk, std::chrono::microseconds(40));
+        }
+    }
+    flush_pager_stats_locked();
+    pager_idle_ = true;
+    cv_admit_.notify_all();
 }
 
 // ---------------------------------------------------------------------------------------------- public operations
+void SwapEngine::set_resident_cap(uint64_t cap) {
+    std::lock_guard<std::mutex> g(mu_);
+    quota_cap_ = cap;
+    // under physical pressure (see load_direct) the working cap stays at what the device could actually give
+    cfg_.resident_cap = pressure_ ? std::min(cap, cfg_.resident_cap) : cap;
+    kick_pager_locked();
+}
+
 CUresult SwapEngine::alloc(CUdeviceptr *dptr, size_t bytes) {
     if (!dptr || bytes == 0) return CUDA_ERROR_INVALID_VALUE;
-    std::lock_guard<std::mutex> g(mu_);
-    if (cfg_.virtual_cap && live_bytes_ + bytes > cfg_.virtual_cap) {
-        LOG_ERROR("Device %d OOM (virtual) %lu / %lu", dev_, (unsigned long)(live_bytes_ + bytes), (unsigned long)cfg_.virtual_cap);
+    std::lock_guard<std::mutex> gate(gate_mu_);
+    Lock lk(mu_);
+    ScopedNs t_admit(&st_.host_admit_ns);
+    if (cfg_.virtual_cap && live_bytes_.load() + bytes > cfg_.virtual_cap) {
+        LOG_ERROR("Device %d OOM (virtual) %lu / %lu", dev_, (unsigned long)(live_bytes_.load() + bytes), (unsigned long)cfg_.virtual_cap);
         return CUDA_ERROR_OUT_OF_MEMORY;
     }
     uint64_t mapped = round_up(bytes, gran_);
@@ -909,70 +1469,119 @@ CUresult SwapEngine::alloc(CUdeviceptr *dptr, size_t bytes) {
     }
     uint64_t off;
     if (!va_alloc(mapped, &off)) { LOG_ERROR("swap arena exhausted"); return CUDA_ERROR_OUT_OF_MEMORY; }
-    CUresult r = make_room(mapped);
-    if (r != CUDA_SUCCESS) { va_free(off, mapped); return r; }
     int row = new_row();
-    rows_[row] = VgpuEntry{arena_ + off, bytes, ++tick_, VGPU_ST_RESIDENT, 0};
+    uint32_t gen = side_[row].gen;
+    rows_[row] = VgpuEntry{arena_ + off, bytes, ++tick_, VGPU_ST_PAGED_OUT, 0};
     side_[row] = Side{};
-    side_[row].mapped = mapped;
-    side_[row].va_off = off;
-    r = map_row(row);
-    if (r != CUDA_SUCCESS) {
-        rows_[row].state = VGPU_ST_FREE;
-        free_rows_.push_back(row);
-        va_free(off, mapped);
-        return r;
+    Side &s = side_[row];
+    s.gen = gen;
+    s.mapped = mapped;
+    s.va_off = off;
+    s.pins = 1;                                  // until this call returns
+    s.phase = PH_QUEUED;
+    s.demand = true;
+    mark_dirty(row);
+    demand_q_.push_back(QEntry{row, s.gen});
+    kick_pager_locked();
+    {
+        ScopedNs t_wait(&st_.host_wait_ns);
+        cv_admit_.wait(lk, [&] { return side_[row].phase == PH_IDLE && !side_[row].demand; });
     }
+    Side &s2 = side_[row];
+    if (!(rows_[row].state & VGPU_ST_RESIDENT)) {
+        CUresult rc = s2.fail != CUDA_SUCCESS ? s2.fail : CUDA_ERROR_OUT_OF_MEMORY;
+        s2.pins = 0;
+        retire_row_locked(row);
+        return rc;
+    }
+    s2.pins = 0;
+    rows_[row].state = VGPU_ST_RESIDENT | (s2.locked ? VGPU_ST_PINNED : 0u);
     for (uint64_t gidx = off / gran_; gidx < (off + mapped) / gran_; gidx++) owner_[gidx] = row;
     mark_dirty(row);
     live_bytes_ += bytes;
+    live_mapped_ += mapped;
     *dptr = arena_ + off;
     publish_locked();
     return CUDA_SUCCESS;
 }
 
 CUresult SwapEngine::free(CUdeviceptr dptr) {
-    const DriverTable &d = drv();
     if (!owns(dptr)) return CUDA_ERROR_INVALID_VALUE;
-    std::lock_guard<std::mutex> g(mu_);
+    Lock lk(mu_);
     int row = owner_[(dptr - arena_) / gran_];
     if (row < 0 || rows_[row].base != dptr) return CUDA_ERROR_INVALID_VALUE;
-    wait_not_evicting(row);
+    // the pager may be working on it with the lock released
+    cv_admit_.wait(lk, [&] { return side_[row].phase != PH_LOADING && side_[row].phase != PH_EVICTING; });
     Side &s = side_[row];
-    if (CUevent e = use_event(s.use_seq)) d.cuEventSynchronize(e);
-    if (s.ready) { d.cuEventSynchronize(s.ready); ready_free_.push_back(s.ready); s.ready = nullptr; }
-    if (rows_[row].state & VGPU_ST_RESIDENT) unmap_row(row);
-    else if (s.has_host) release_host_range(s.host_off, round_up(rows_[row].size, 256));
+    if (s.phase == PH_QUEUED) {                  // stale queue entries are recognised by their phase
+        if (!s.demand) queued_prefetch_bytes_ -= s.mapped;
+        else { s.demand = false; s.fail = CUDA_ERROR_INVALID_VALUE; cv_admit_.notify_all(); }   // freed under a waiting admission
+        s.phase = PH_IDLE;
+    }
+    if (s.prefetched) { s.prefetched = false; prefetched_bytes_ -= s.mapped; st_.prefetch_wasted++; }
     for (uint64_t gidx = s.va_off / gran_; gidx < (s.va_off + s.mapped) / gran_; gidx++) owner_[gidx] = -1;
-    va_free(s.va_off, s.mapped);
     live_bytes_ -= rows_[row].size;
-    s.pins = 0;                       // rows pinned for a stream capture are never unpinned by note_use
-    rows_[row].state = VGPU_ST_FREE;
-    rows_[row].size = 0;
-    mark_dirty(row);
-    free_rows_.push_back(row);
+    live_mapped_ -= s.mapped;
+    s.pins = 0;                                  // rows pinned for a stream capture are never unpinned by note_use
+    s.locked = false;
+    if (last_row_ == row) last_row_ = -1;
+    if (rows_[row].state & VGPU_ST_RESIDENT) {
+        // still mapped, maybe still in use by queued work: the pager unmaps it once its last users are done and only then
+        // hands the address range out again
+        rows_[row].state = VGPU_ST_FREE;
+        rows_[row].size = 0;
+        mark_dirty(row);
+        s.phase = PH_ZOMBIE;
+        zombies_.push_back((uint32_t)row);
+        kick_pager_locked();
+    } else {
+        if (s.has_host) release_host_range(s.host_off, round_up(rows_[row].size, 256));
+        s.has_host = false;
+        retire_row_locked(row);                    // a staged D2H into its block may still be queued: harmless, the block's
+                                                   // next writer queues behind it on the same stream
+    }
     publish_locked();
     return CUDA_SUCCESS;
 }
 
 CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
     const DriverTable &d = drv();
-    std::lock_guard<std::mutex> g(mu_);
+    Lock lk(mu_);
     ScopedNs t_admit(&st_.host_admit_ns);
+    // an admission that has to wait for the pager takes the gate first: two of them could otherwise each hold (pin) part
+    // of what the other needs
+    bool gated = false;
+    auto any_missing = [&] {
+        for (int i = 0; i < n; i++) if (!(rows_[rows[i]].state & VGPU_ST_RESIDENT)) return true;
+        return false;
+    };
+    if (any_missing()) {
+        lk.unlock();
+        gate_mu_.lock();
+        gated = true;
+        lk.lock();
+    }
     st_.admissions++;
     tick_++;
     std::vector<int> missing;
-    uint64_t need = 0;
     for (int i = 0; i < n; i++) {
         int r = rows[i];
+        Side &s = side_[r];
+        observe_touch(r);
         rows_[r].last_touch = tick_;
-        side_[r].pins++;
-        if (rows_[r].state & VGPU_ST_RESIDENT) rows_[r].state = VGPU_ST_RESIDENT | VGPU_ST_PINNED;
-        else { missing.push_back(r); need += side_[r].mapped; }
+        s.pins++;
+        if (rows_[r].state & VGPU_ST_RESIDENT) {
+            rows_[r].state = VGPU_ST_RESIDENT | VGPU_ST_PINNED;
+            if (s.prefetched) { s.prefetched = false; prefetched_bytes_ -= s.mapped; st_.prefetch_hits++; st_.faults++; }
+        } else {
+            missing.push_back(r);
+        }
         mark_dirty(r);
     }
+    CUresult rc = CUDA_SUCCESS;
     if (!missing.empty()) {
         st_.faults += missing.size();
+        st_.demand_waits++;
         if (!ctx_warned_) {
             // The engine's module, side streams and events live in the context that was current when the first swappable
             // allocation created it. An application that hops between SEVERAL contexts of one device is outside what swap
@@ -984,145 +1593,172 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
                           "device are not supported in swap mode", dev_, (void *)cur, (void *)ctx_);
             }
         }
-        // order matters for overlap: packs of the victims first (short), then the H2D copies of the incoming rows
-        // into staging, THEN the host-side wait for the packs and the VMM remaps, and finally the unpacks
-        tr_ = nullptr;
-        if (trace_want_ && trace_.size() == trace_want_ && !trace_dumped_) {
-            // the driver is gone by the time atexit handlers run: print as soon as the window is full
-            trace_dumped_ = true;
-            mu_.unlock();
-            dump_trace(stderr);
-            mu_.lock();
-        }
-        if (trace_want_ && trace_.size() < trace_want_) {
-            if (trace_skip_) trace_skip_--;
-            else {
-                if (!trace_base_) { d.cuEventCreate(&trace_base_, CU_EVENT_DEFAULT); d.cuEventRecord(trace_base_, s_out_); d.cuEventSynchronize(trace_base_); trace_base_ns_ = mono_ns(); trace_.reserve(trace_want_); }
-                trace_.emplace_back();
-                tr_ = &trace_.back();
-                tr_->t_begin = mono_ns();
+        uint64_t need = 0, pinned = 0;
+        for (int r : missing) need += side_[r].mapped;
+        for (int i = 0; i < n; i++) if (rows_[rows[i]].state & VGPU_ST_RESIDENT) pinned += side_[rows[i]].mapped;
+        if (need + pinned > cfg_.resident_cap) {
+            LOG_ERROR("resident quota %lu MiB cannot hold the working set of this launch (%lu MiB)", (unsigned long)(cfg_.resident_cap >> 20),
+                      (unsigned long)((need + pinned) >> 20));
+            rc = CUDA_ERROR_OUT_OF_MEMORY;
+        } else {
+            for (int r : missing) {
+                Side &s = side_[r];
+                s.fail = CUDA_SUCCESS;
+                if (s.phase == PH_IDLE) { s.phase = PH_QUEUED; s.demand = true; demand_q_.push_back(QEntry{r, s.gen}); }
+                else if (s.phase == PH_QUEUED && !s.demand) { s.demand = true; queued_prefetch_bytes_ -= s.mapped; demand_q_.push_back(QEntry{r, s.gen}); }
+                else s.demand = true;            // loading or on its way out: the pager brings it (back) in
+            }
+            kick_pager_locked();
+            {
+                ScopedNs t_wait(&st_.host_wait_ns);
+                cv_admit_.wait(lk, [&] {
+                    for (int r : missing) {
+                        const Side &s = side_[r];
+                        bool settled = s.phase == PH_IDLE && !s.demand;
+                        if (!settled) return false;
+                    }
+                    return true;
+                });
+            }
+            for (int r : missing) {
+                if (rows_[r].state & VGPU_ST_RESIDENT) rows_[r].state = VGPU_ST_RESIDENT | VGPU_ST_PINNED;
+                else if (rc == CUDA_SUCCESS) rc = side_[r].fail != CUDA_SUCCESS ? side_[r].fail : CUDA_ERROR_OUT_OF_MEMORY;
+                mark_dirty(r);
             }
         }
-        if (pressure_ && cfg_.resident_cap < quota_cap_ && (++pressure_probe_ & 31u) == 0) {
-            // probe upwards: the other tenants may have let go; a failed cuMemCreate simply lowers the cap again
-            cfg_.resident_cap = std::min(quota_cap_, cfg_.resident_cap + need);
-            if (cfg_.resident_cap == quota_cap_) pressure_ = false;
-        }
-        CUresult r = make_room(need, false);
-        if (tr_) tr_->t_packs = mono_ns();
-        if (r == CUDA_SUCCESS) r = page_in_stage(missing);
-        if (tr_) tr_->t_staged = mono_ns();
-        if (r == CUDA_SUCCESS) r = page_out_finish();
-        if (tr_) tr_->t_unmapped = mono_ns();
-        if (r == CUDA_SUCCESS) r = page_in_finish(missing);
-        if (tr_) { tr_->t_end = mono_ns(); tr_ = nullptr; }
-        if (r != CUDA_SUCCESS) { page_out_finish(); in_jobs_.clear(); }
-        if (r != CUDA_SUCCESS) {
+        if (rc != CUDA_SUCCESS) {
             for (int i = 0; i < n; i++) {
                 Side &s = side_[rows[i]];
-                if (--s.pins == 0 && (rows_[rows[i]].state & VGPU_ST_RESIDENT)) rows_[rows[i]].state = VGPU_ST_RESIDENT;
+                if (--s.pins == 0 && !s.locked && (rows_[rows[i]].state & VGPU_ST_RESIDENT)) rows_[rows[i]].state = VGPU_ST_RESIDENT;
                 mark_dirty(rows[i]);
             }
-            return r;
+            if (gated) gate_mu_.unlock();
+            return rc;
         }
-        for (int r2 : missing) rows_[r2].state = VGPU_ST_RESIDENT | VGPU_ST_PINNED;
     }
+    schedule_prefetch();
+    std::vector<CUevent> host_wait;
     for (int i = 0; i < n; i++) {
         Side &s = side_[rows[i]];
         if (!s.ready) continue;
-        if (stream == kHostWait) d.cuEventSynchronize(s.ready);
+        if (stream == kHostWait) { host_wait.push_back(s.ready); continue; }
         if (d.cuEventQuery(s.ready) == CUDA_SUCCESS) { ready_free_.push_back(s.ready); s.ready = nullptr; }
         else d.cuStreamWaitEvent(stream, s.ready, 0);
     }
     if (!missing.empty()) publish_locked();
+    if (!host_wait.empty()) {
+        // the rows are pinned, so their `ready` events stay theirs while the lock is released
+        lk.unlock();
+        for (CUevent e : host_wait) d.cuEventSynchronize(e);
+        lk.lock();
+    }
+    if (gated) gate_mu_.unlock();
     return CUDA_SUCCESS;
 }
 
-void SwapEngine::note_use(const int *rows, int n, CUstream stream) {
+void SwapEngine::note_use(const int *rows, int n, CUstream stream, bool writes) {
     const DriverTable &d = drv();
     std::lock_guard<std::mutex> g(mu_);
     uint64_t seq = ++use_seq_;
-    CUevent ev = use_ring_[seq % use_ring_.size()];
+    size_t ring = use_ring_.size();
+    CUevent ev = use_ring_[seq % ring];
     // the slot's previous owner (seq - ring size) is only forgotten once it is known complete, see use_event()
-    if (seq > use_ring_.size()) d.cuEventSynchronize(ev);
-    d.cuEventRecord(ev, stream);
+    if (seq > ring) d.cuEventSynchronize(ev);
+    // A row remembers one outstanding use per stream (up to kMaxUses): a later eviction or free waits for ALL of them — work
+    // queued on stream A must not lose its operand because stream B used it afterwards. A row used from more streams than
+    // that gets its oldest use chained in front of this one.
     for (int i = 0; i < n; i++) {
         Side &s = side_[rows[i]];
-        s.use_seq = seq;
-        if (s.pins > 0 && --s.pins == 0 && (rows_[rows[i]].state & VGPU_ST_RESIDENT)) {
+        int k = 0;
+        for (int j = 0; j < s.nuses; j++) {
+            uint64_t q = s.uses[j];
+            if (q + ring <= seq) continue;                                 // recycled: complete
+            if (use_stream_[q % ring] == stream) continue;                 // same stream: this use supersedes it
+            s.uses[k++] = q;
+        }
+        s.nuses = k;
+        if (s.nuses == kMaxUses) {
+            if (CUevent old = use_event(s.uses[0])) d.cuStreamWaitEvent(stream, old, 0);
+            for (int j = 1; j < s.nuses; j++) s.uses[j - 1] = s.uses[j];
+            s.nuses--;
+        }
+    }
+    d.cuEventRecord(ev, stream);
+    use_stream_[seq % ring] = stream;
+    for (int i = 0; i < n; i++) {
+        Side &s = side_[rows[i]];
+        s.uses[s.nuses++] = seq;
+        if (writes && !s.read_mostly) s.dirty = true;
+        if (s.pins > 0 && --s.pins == 0 && !s.locked && (rows_[rows[i]].state & VGPU_ST_RESIDENT)) {
             rows_[rows[i]].state = VGPU_ST_RESIDENT;
             mark_dirty(rows[i]);
         }
     }
 }
 
+void SwapEngine::advise_read_mostly(int row, bool on) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (row_live(row)) side_[row].read_mostly = on;
+}
+
+CUresult SwapEngine::pin_resident(int row, bool on) {
+    if (on) {
+        CUresult rc = ensure_resident(&row, 1, kHostWait);
+        if (rc != CUDA_SUCCESS) return rc;
+        std::lock_guard<std::mutex> g(mu_);
+        Side &s = side_[row];
+        s.locked = true;
+        if (s.pins > 0) s.pins--;                 // the lock keeps it; the admission's pin is not needed
+        s.dirty = true;                           // whoever reaches it behind the hook's back may write
+        rows_[row].state = VGPU_ST_RESIDENT | VGPU_ST_PINNED;
+        mark_dirty(row);
+        return CUDA_SUCCESS;
+    }
+    std::lock_guard<std::mutex> g(mu_);
+    if (!row_live(row)) return CUDA_ERROR_INVALID_VALUE;
+    Side &s = side_[row];
+    s.locked = false;
+    if (s.pins == 0 && (rows_[row].state & VGPU_ST_RESIDENT)) { rows_[row].state = VGPU_ST_RESIDENT; mark_dirty(row); }
+    return CUDA_SUCCESS;
+}
+
 void SwapEngine::publish_locked() {
+    resident_pub_.store(resident_mapped_ + evicting_mapped_, std::memory_order_relaxed);
     vgpu_swap_record_t *r = shared_;
     if (!r) return;
     __atomic_store_n(&r->page_out_bytes, st_.page_out_bytes, __ATOMIC_RELAXED);
     __atomic_store_n(&r->page_in_bytes, st_.page_in_bytes, __ATOMIC_RELAXED);
     __atomic_store_n(&r->evictions, st_.evictions, __ATOMIC_RELAXED);
     __atomic_store_n(&r->faults, st_.faults, __ATOMIC_RELAXED);
-    __atomic_store_n(&r->resident_bytes, (uint64_t)resident_mapped_, __ATOMIC_RELAXED);
-    __atomic_store_n(&r->live_bytes, (uint64_t)live_bytes_, __ATOMIC_RELAXED);
-    __atomic_store_n(&r->host_bytes, (uint64_t)host_used_, __ATOMIC_RELAXED);
+    __atomic_store_n(&r->resident_bytes, (uint64_t)(resident_mapped_ + evicting_mapped_), __ATOMIC_RELAXED);
+    __atomic_store_n(&r->live_bytes, (uint64_t)live_bytes_.load(), __ATOMIC_RELAXED);
+    __atomic_store_n(&r->host_bytes, (uint64_t)host_used_.load(), __ATOMIC_RELAXED);
 }
 
 CUresult SwapEngine::drain() {
     const DriverTable &d = drv();
-    std::lock_guard<std::mutex> g(mu_);
-    while (evicting_mapped_ != 0) reap_cv_.wait(mu_);
+    Lock lk(mu_);
+    drop_prefetch_queue_locked();                // wishes, not work
+    kick_pager_locked();
+    cv_admit_.wait(lk, [&] { return stop_ || (pager_idle_ && !kick_ && demand_q_.empty() && evicting_.empty() && zombies_.empty()); });
     CUresult r = CUDA_SUCCESS, t;
+    // the pager is parked on its condition variable: its private state may be touched from here
     for (CUstream s : {s_scan_, s_pack_, s_unpack_, s_out_, s_in_})
         if (s && (t = d.cuStreamSynchronize(s)) != CUDA_SUCCESS) r = t;
-    reap_pending_host(true);
     harvest_spans();
     harvest_prof(true);
+    flush_pager_stats_locked();
     return r;
 }
 
 SwapStats SwapEngine::stats() {
     std::lock_guard<std::mutex> g(mu_);
-    harvest_prof(false);
-    harvest_spans();
     SwapStats s = st_;
-    s.resident_bytes = resident_mapped_;
-    s.live_bytes = live_bytes_;
-    s.host_bytes = host_used_;
-    s.entries = rows_.size() - free_rows_.size();
+    s.resident_bytes = resident_mapped_ + evicting_mapped_;
+    s.live_bytes = live_bytes_.load();
+    s.host_bytes = host_used_.load();
+    s.entries = rows_.size() - free_rows_.size() - zombies_.size();
     return s;
-}
-
-void SwapEngine::trace_mark(std::vector<CUevent> *v, CUstream s) {
-    CUevent e = nullptr;
-    if (drv().cuEventCreate(&e, CU_EVENT_DEFAULT) != CUDA_SUCCESS) return;
-    drv().cuEventRecord(e, s);
-    v->push_back(e);
-}
-
-void SwapEngine::dump_trace(FILE *f) {
-    const DriverTable &d = drv();
-    std::lock_guard<std::mutex> g(mu_);
-    if (trace_.empty() || !trace_base_) return;
-    for (CUstream s : {s_out_, s_in_}) d.cuStreamSynchronize(s);
-    auto rel = [&](uint64_t ns) { return (double)(ns - trace_base_ns_) / 1e3; };
-    for (size_t i = 0; i < trace_.size(); i++) {
-        TraceRec &t = trace_[i];
-        std::fprintf(f, "[vgpu-b200 trace] {\"i\": %zu, \"host_us\": {\"begin\": %.0f, \"packs\": %.0f, \"staged\": %.0f, \"unmapped\": %.0f, \"end\": %.0f}",
-                     i, rel(t.t_begin), rel(t.t_packs), rel(t.t_staged), rel(t.t_unmapped), rel(t.t_end));
-        for (int dir = 0; dir < 2; dir++) {
-            std::vector<CUevent> &v = dir ? t.h2d : t.d2h;
-            std::fprintf(f, ", \"%s_us\": [", dir ? "h2d" : "d2h");
-            for (size_t k = 0; k + 1 < v.size(); k += 2) {
-                float a = 0, b = 0;
-                d.cuEventElapsedTime(&a, trace_base_, v[k]);
-                d.cuEventElapsedTime(&b, trace_base_, v[k + 1]);
-                std::fprintf(f, "%s[%.0f, %.0f]", k ? ", " : "", a * 1e3, b * 1e3);
-            }
-            std::fprintf(f, "]");
-        }
-        std::fprintf(f, "}\n");
-    }
 }
 
 std::vector<VgpuEntry> SwapEngine::snapshot_table() {

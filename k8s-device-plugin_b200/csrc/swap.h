@@ -6,21 +6,36 @@
 // kernel driver on host cores), this engine keeps explicit control:
 //   * every swappable allocation is a stable virtual range (cuMemAddressReserve arena) backed by VMM physical
 //     handles that are mapped only while the buffer is resident;
-//   * a device-resident allocation table (32-byte rows) records residency and a logical LRU clock;
-//   * when an admission (kernel launch / memcpy / new allocation) needs more physical memory than the container's
-//     resident quota allows, a GPU victim scan picks exact-LRU victims, a TMA pack kernel compacts them into a
-//     staging ring in HBM, and a copy stream drains the ring to pinned host memory while the next chunk is packed;
-//     page-in is the mirror image (pinned host -> staging ring -> unpack kernel into the re-mapped range);
-//   * pack, unpack, scan, D2H and H2D each have their own stream, ordered only by the events that express real
-//     data dependencies, so the two link directions and the HBM compaction all overlap;
-//   * nothing on the host ever waits for a PCIe transfer except for ring back-pressure: the application stream is
-//     ordered behind the page-in with events.
+//   * a device-resident allocation table (32-byte rows) records residency and a logical LRU clock; a GPU victim scan
+//     picks exact-LRU victims from it;
+//   * ONE PAGER THREAD per engine owns every driver call that is slow or that feeds the host link: cuMemUnmap /
+//     cuMemMap / cuMemSetAccess / cuMemCreate (batched: one cuMemSetAccess / cuMemUnmap per run of adjacent ranges),
+//     the victim scan, and the enqueueing of both DMA directions. Application threads (kernel launches, memcpys,
+//     allocations) only do bookkeeping under a mutex, hand their misses to the pager and order their stream behind
+//     the page-in's event. A stall inside the driver's VMM calls (0.1-20 ms under load on B200 / driver 580,
+//     profiles/README.md) therefore no longer idles the link: the queues it feeds are deep, and it is not the
+//     application thread that sits in the driver;
+//   * two data paths between HBM and pinned host memory:
+//       direct  — cuMemcpyDtoHAsync / HtoDAsync straight between the buffer's own range and its pinned block, in
+//                 copy_bytes pieces: no staging, no kernel, no extra HBM traffic. Used whenever the pipeline runs ahead
+//                 of need (prefetch + eviction ahead), i.e. for the bulk of the traffic;
+//       staged  — the TMA pack kernel compacts the victims into a staging ring at HBM speed (their physical memory is
+//                 free for the incoming buffer ~25 us later instead of one PCIe transfer later) while the copy
+//                 stream drains the ring; page-in is the mirror image (pinned -> ring -> unpack kernel). Used for a
+//                 demand miss that finds neither free physical memory nor an eviction in flight: latency path;
+//   * a successor predictor (for every row: which row was touched next last time) drives prefetch: training loops and
+//     sweeps repeat their access sequence, so the pager pages the next rows in — and evicts LRU rows ahead for them —
+//     before the application asks; it only acts while its recent predictions were right (random access: off);
+//   * clean rows: a row that was paged in and not written since keeps its pinned block; evicting it is an unmap, no
+//     copy. Kernel launches count as writes unless the range was advised read-mostly (cuMemAdvise SET_READ_MOSTLY,
+//     the hint UVM applications already give); memcpy sources never dirty.
 #pragma once
 #include <cuda.h>
 
 #include <algorithm>
-#include <cstdint>
+#include <atomic>
 #include <condition_variable>
+#include <cstdint>
 #include <deque>
 #include <map>
 #include <memory>
@@ -29,8 +44,8 @@
 #include <vector>
 
 #include "kernels.h"
-#include "vgpu_region.h"
 #include "kmod.h"
+#include "vgpu_region.h"
 
 namespace vgpu {
 
@@ -38,17 +53,17 @@ struct SwapConfig {
     uint64_t resident_cap = 0;            // bytes of physical backing the container may hold (its gpumem quota); 0 = device free memory
     uint64_t virtual_cap = 0;             // live swappable bytes allowed; 0 = bounded by host pool only
     uint64_t host_pool_cap = 0;           // pinned bytes allowed; 0 = unbounded
-    size_t chunk_bytes = 32u << 20;       // staging slot size (one DMA)
+    size_t chunk_bytes = 32u << 20;       // staging slot size (staged path: one DMA per slot)
     int ring_slots = 4;                   // staging slots per direction
     size_t slab_bytes = 1ull << 30;       // pinned pool growth unit
     uint64_t arena_bytes = 1ull << 40;    // virtual address arena
-    bool profile = false;                 // bracket pack/unpack launches with events (bench roofline)
+    bool profile = false;                 // bracket pack/unpack launches with events + in-kernel spans (bench roofline pass)
     uint32_t scan_lookahead = 8;          // a scan selects this many times the bytes needed; the surplus is consumed by later evictions
-    uint32_t trace = 0;                   // VGPU_SWAP_TRACE=n: timeline of n steady-state misses (diagnostics)
-    bool async_unmap = false;             // VGPU_SWAP_ASYNC_UNMAP=1: victims are unmapped by a reaper thread instead of the admitting
-                                          // thread. Measured neutral on B200/driver 580 (VMM calls from two threads serialise in the driver:
-                                          // 68 vs 70 GB/s, profiles/README.md), kept as the building block of the prefetch pipeline
-    uint64_t spare_bytes = 128u << 20;    // physical memory the engine may hold beyond the quota while victims await their unmap
+    uint64_t prefetch_bytes = 512ull << 20;   // VGPU_SWAP_PREFETCH_MB: how far the pager runs ahead of the application (0 = no prefetch)
+    size_t copy_bytes = 16u << 20;        // VGPU_SWAP_COPY_MB: piece size of the direct copies (VMM calls wait for the copy in flight)
+    uint32_t batch_rows = 8;              // rows per pager batch (one cuMemSetAccess / cuMemUnmap per run of adjacent ranges)
+    bool host_backed = false;             // VGPU_SWAP_HOST_BACKED=1: an evicted range is re-mapped onto its host copy (VMM host
+                                          // memory) instead of being left unmapped, so an access the hook could not see is slow, not fatal
     static SwapConfig from_env(uint64_t resident_cap, uint64_t virtual_cap);
 };
 
@@ -59,13 +74,21 @@ struct SwapStats {
     uint64_t resident_bytes = 0, live_bytes = 0, host_bytes = 0, entries = 0;
     uint64_t phys_creates = 0, phys_reuses = 0;
     uint64_t host_slabs = 0, host_slabs_local = 0;   // pinned slabs allocated / of those on the GPU's NUMA node
-    double pack_ms = 0, unpack_ms = 0;     // CUDA-event brackets around each launch, only when profiling (include the
-                                           // host's event->launch gap when the stream is idle)
+    double pack_ms = 0, unpack_ms = 0;     // CUDA-event brackets around each launch, only when profiling
     double pack_span_ms = 0, unpack_span_ms = 0;   // exact execution spans from in-kernel %globaltimer stamps (profiling)
-    // where the calling thread's time goes inside ensure_resident/alloc (ns): victim scan incl. its sync, waiting for
-    // the last pack of a batch, VMM calls (unmap/map/setaccess/create), staging-ring back-pressure, whole admissions
-    uint64_t host_scan_ns = 0, host_packsync_ns = 0, host_vmm_ns = 0, host_ring_ns = 0, host_admit_ns = 0;
-    uint64_t pack_bytes = 0, unpack_bytes = 0;
+    // APPLICATION-thread time inside ensure_resident/alloc (ns): whole admissions, and the part of it spent blocked until
+    // the pager had issued the page-in. host_vmm_ns is the time application threads spend in VMM calls: zero by
+    // construction since the pager owns them (kept in the ABI so that a regression shows).
+    uint64_t host_admit_ns = 0, host_wait_ns = 0, host_vmm_ns = 0;
+    // pager-thread time (ns): VMM calls, victim scans incl. their sync, waiting for the last pack of a staged batch,
+    // staging-ring back-pressure
+    uint64_t pager_vmm_ns = 0, pager_scan_ns = 0, pager_packsync_ns = 0, pager_ring_ns = 0, pager_busy_ns = 0;
+    uint64_t vmm_calls = 0;                // cuMemUnmap + cuMemSetAccess calls issued (after batching)
+    uint64_t pack_bytes = 0, unpack_bytes = 0;       // bytes moved by the staged path's kernels
+    uint64_t direct_out_bytes = 0, direct_in_bytes = 0;   // bytes moved by the direct path (subset of page_out/in_bytes)
+    uint64_t prefetch_issued = 0, prefetch_hits = 0, prefetch_wasted = 0;   // rows paged in ahead / touched afterwards / evicted untouched
+    uint64_t demand_waits = 0;             // admissions that had to block for the pager
+    uint64_t clean_evictions = 0;          // evictions that needed no copy (host block still valid)
 };
 
 class SwapEngine {
@@ -86,151 +109,186 @@ class SwapEngine {
     // passed to note_use() stay pinned resident — what a captured kernel's operands need.
     static inline CUstream kHostWait = reinterpret_cast<CUstream>(~uintptr_t(0));
     CUresult ensure_resident(const int *rows, int n, CUstream stream);
-    void note_use(const int *rows, int n, CUstream stream);
+    // writes = false: the work just enqueued only READS the rows (memcpy source): they stay clean
+    void note_use(const int *rows, int n, CUstream stream, bool writes = true);
     // Scans kernel parameter bytes for pointers into the arena; appends distinct row indices.
     void collect_rows(const void *param, size_t bytes, std::vector<int> *rows) const;
+    // cuMemAdvise(SET/UNSET_READ_MOSTLY) on a swappable range: kernel launches no longer mark it dirty
+    void advise_read_mostly(int row, bool on);
+    // cuMemPrefetchAsync(range, device): queue a page-in with the pager, do not wait
+    void hint_prefetch(int row);
+    // never evict this row (operands the argument scan cannot see: device-side pointer tables)
+    CUresult pin_resident(int row, bool on);
 
     SwapStats stats();
-    void set_profile(bool on) { cfg_.profile = on; }
+    void set_profile(bool on);
     // the quota left for swappable memory shrinks/grows with the container's non-swappable bytes (context, small buffers)
-    void set_resident_cap(uint64_t cap) {
-        std::lock_guard<std::mutex> g(mu_);
-        quota_cap_ = cap;
-        // under physical pressure (see map_row) the working cap stays at what the device could actually give
-        cfg_.resident_cap = pressure_ ? std::min(cap, cfg_.resident_cap) : cap;
-    }
+    void set_resident_cap(uint64_t cap);
     // publish the counters into the container's shared region (vgpu_region.h extension block) after every call that
     // changes them; nullptr = do not publish
     void set_shared_record(vgpu_swap_record_t *rec) { std::lock_guard<std::mutex> g(mu_); shared_ = rec; publish_locked(); }
-    CUresult drain();                          // wait for all side-stream work (tests / shutdown)
+    CUresult drain();                          // wait for the pager and all side-stream work (tests / shutdown)
     const SwapConfig &config() const { return cfg_; }
     // device memory the engine itself holds next to the application's resident buffers: both staging rings (the table,
     // scan scratch and span words are a few hundred KiB and not counted). The hook takes it out of the room it gives
     // the engine, so that the container's PHYSICAL footprint stays within its gpumem quota.
     uint64_t device_overhead() const { return 2ull * cfg_.ring_slots * cfg_.chunk_bytes; }
-    uint64_t live_bytes() const { return live_bytes_; }
-
-    // diagnostics (VGPU_SWAP_TRACE=n): host timestamps and timed GPU events of the first n missing admissions after
-    // warm-up, printed as JSON lines by dump_trace() — where do the two DMA queues idle?
-    void dump_trace(FILE *f);
+    uint64_t live_bytes() const { return live_bytes_.load(std::memory_order_relaxed); }
+    uint64_t resident_bytes() const { return resident_pub_.load(std::memory_order_relaxed); }
 
     // test hook: copy of the host mirror of the table
     std::vector<VgpuEntry> snapshot_table();
 
    private:
+    enum Phase : uint8_t {
+        PH_IDLE = 0,      // stable: resident or paged out
+        PH_QUEUED,        // paged out, waiting in demand_q_/prefetch_q_
+        PH_LOADING,       // the pager is mapping it / enqueueing its page-in (mu_ released meanwhile)
+        PH_EVICTING,      // page-out enqueued, still mapped; logically paged out
+        PH_ZOMBIE,        // freed by the application while resident: the pager unmaps it once its last users are done
+    };
+    static constexpr int kMaxUses = 4;
     struct Side {                // host-only companion of a table row
         size_t mapped = 0;
         CUmemGenericAllocationHandle handle = 0;
         bool has_handle = false;
-        uint64_t host_off = 0;   // pinned pool location while paged out
+        uint64_t host_off = 0;   // pinned block (kept across page-ins: a clean row is evicted without a copy)
         bool has_host = false;
-        CUevent ready = nullptr; // pending page-in completion (owned by ready_pool_)
-        uint64_t use_seq = 0;    // sequence number of the last-use event
+        bool dirty = false;      // HBM content differs from the pinned block (or there is none yet and the row was written)
+        bool read_mostly = false;
+        bool prefetched = false; // paged in ahead of need and not touched since
+        bool demand = false;     // an application thread is waiting for this row
+        bool locked = false;     // pin_resident(): never a victim
+        Phase phase = PH_IDLE;
+        CUresult fail = CUDA_SUCCESS;   // why the pager could not bring it in (reported to the waiting admission)
+        CUevent ready = nullptr; // pending page-in completion
+        uint64_t uses[kMaxUses] = {0, 0, 0, 0};   // sequence numbers of the outstanding last-use events, one per stream
+        int nuses = 0;
         int pins = 0;
         uint64_t va_off = 0;
-        bool evicting = false;   // packed and logically paged out, but its unmap is still queued at the reaper
-        int out_slot = -1;       // staging slot of the last page-out chunk of this row ...
+        CUevent evict_done = nullptr;   // after it the row's physical memory is no longer read by its page-out
+        int out_slot = -1;       // staging slot of the last staged page-out chunk of this row ...
         uint64_t out_seq = 0;    // ... and that slot's use counter at the time (stale => the D2H is known complete)
+        uint32_t gen = 0;        // bumped when the row index is recycled (stale queue entries are skipped)
+        int retries = 0;         // page-in attempts that met a device with less memory than the cap promises
     };
     struct Slab { unsigned char *host = nullptr; size_t bytes = 0; std::map<uint64_t, uint64_t> free; };
     struct Slot { CUdeviceptr buf = 0; CUevent busy = nullptr; bool used = false; uint64_t seq = 0; };
-    struct PendingHost { uint64_t off, len; CUevent done; };
+    typedef std::unique_lock<std::mutex> Lock;
 
     SwapEngine() = default;
     bool init(int dev, const SwapConfig &cfg);
+
+    // ---- table (mu_)
     int new_row();
     void mark_dirty(int row);
-    CUresult sync_table(CUstream s);
-    CUresult make_room(uint64_t need_mapped, bool finish = true);
-    CUresult page_out(const std::vector<uint32_t> &victims, bool finish = true);
-    CUresult page_out_finish();
-    struct InRun { unsigned char *src; uint64_t pos, len; };
-    struct InJob { Slot *slot = nullptr; std::vector<PackSegment> segs; std::vector<InRun> runs; std::vector<int> done_rows; uint64_t bytes = 0; };
-    CUresult page_in_plan(const std::vector<int> &rows);
-    CUresult page_in_stage(const std::vector<int> &rows);
-    CUresult page_in_finish(const std::vector<int> &rows);
-    CUresult in_issue_copies(InJob &j);
-    CUresult map_row(int row);
-    void unmap_row(int row);
-    CUresult get_phys(size_t mapped, CUmemGenericAllocationHandle *h);
+    CUresult sync_table(Lock &lk, CUstream s);
+    void publish_locked();
+    bool row_live(int row) const { return row >= 0 && (size_t)row < rows_.size() && rows_[row].state != VGPU_ST_FREE; }
+    void retire_row_locked(int row);          // give the index and the VA range back (row is unmapped)
+
+    // ---- predictor (mu_)
+    void observe_touch(int row);
+    bool predictor_confident() const;
+    void schedule_prefetch();
+
+    // ---- pager thread
+    void pager_main();
+    bool step_zombies(Lock &lk);
+    bool step_reap(Lock &lk);
+    bool step_demand(Lock &lk);
+    bool step_prefetch(Lock &lk);
+    bool step_evict_ahead(Lock &lk);
+    struct OutItem { uint32_t row; CUdeviceptr base; uint64_t len; size_t mapped; uint64_t host_off; bool has_host, copy; std::vector<CUevent> wait; CUevent done = nullptr; int out_slot = -1; uint64_t out_seq = 0; bool failed = false; };
+    struct InItem { int row; CUdeviceptr base; uint64_t len; size_t mapped; uint64_t host_off; bool has_host; bool prefetch; CUmemGenericAllocationHandle h = 0; CUevent ready = nullptr;
+                    CUevent after = nullptr; CUresult rc = CUDA_SUCCESS; };
+    CUresult choose_victims(Lock &lk, uint64_t shortage, std::vector<uint32_t> *victims, uint64_t *evictable);
+    void begin_evict_locked(const std::vector<uint32_t> &victims, std::vector<OutItem> *items);
+    CUresult evict_direct(Lock &lk, const std::vector<uint32_t> &victims);
+    void begin_load_locked(int row, bool prefetch, InItem *it);
+    CUresult load_direct(Lock &lk, std::vector<InItem> &items);
+    void commit_load_locked(InItem &it);
+    void fail_load_locked(InItem &it, CUresult rc);
+    bool requeue_under_pressure_locked(int row, bool was_demand, size_t free_dev);
+    CUresult swap_staged(Lock &lk, int row, const std::vector<uint32_t> &victims);
+    void unmap_batch(std::vector<std::pair<CUdeviceptr, size_t>> &ranges);
+    CUresult set_access_batch(std::vector<std::pair<CUdeviceptr, size_t>> &ranges);
+    CUresult obtain_phys(size_t mapped, CUmemGenericAllocationHandle *h, bool *pressure);
+    void pool_phys(size_t mapped, CUmemGenericAllocationHandle h);
     void trim_phys_pool(uint64_t need);
+    int64_t free_phys_locked() const { return (int64_t)cfg_.resident_cap - (int64_t)resident_mapped_ - (int64_t)evicting_mapped_; }
+    void flush_pager_stats_locked();
+    void collect_waits_locked(int row, std::vector<CUevent> *out);
+
+    // ---- staged path pieces (pager thread)
+    struct InRun { unsigned char *src; uint64_t pos, len; };
+    struct InJob { Slot *slot = nullptr; std::vector<PackSegment> segs; std::vector<InRun> runs; uint64_t bytes = 0; };
+    Slot &acquire_slot(std::vector<Slot> &ring, int *cursor);
+    CUresult staged_out(std::vector<OutItem> &items, CUevent *packed);
+    void plan_staged_in(const InItem &it, std::vector<InJob> *jobs);
+    CUresult in_issue_copies(InJob &j);
+
+    // ---- pinned pool (host_mu_)
     bool host_alloc(size_t bytes, uint64_t *off);
     void release_host_range(uint64_t off, uint64_t len);
-    void reap_pending_host(bool wait);
-    CUevent get_event();
     unsigned char *host_ptr(uint64_t off);
+    bool reclaim_host_blocks(Lock &lk, uint64_t bytes);
+
+    // ---- misc
+    CUevent get_event();                       // pager-private pool
+    void put_event(CUevent e);
     bool va_alloc(size_t bytes, uint64_t *off);
     void va_free(uint64_t off, size_t bytes);
     CUevent use_event(uint64_t seq);
-    Slot &acquire_slot(std::vector<Slot> &ring, int *cursor);
     void prof_begin(CUstream s, CUevent *a);
     void prof_end(CUstream s, CUevent a, bool unpack, uint64_t bytes);
     void harvest_prof(bool wait);
+    CUdeviceptr next_span(bool unpack);
+    void harvest_spans();
 
     mutable std::mutex mu_;
+    std::condition_variable cv_pager_;              // work for the pager
+    std::condition_variable cv_admit_;              // progress for application threads (and drain)
+    std::mutex gate_mu_;                            // one admission WITH misses at a time (a second one could hold the rows the first needs)
     int dev_ = 0;
     int numa_node_ = -1;                            // NUMA node of the GPU (pinned slabs are allocated there)
     SwapConfig cfg_;
     const Kernels *k_ = nullptr;
     size_t gran_ = 2u << 20;
     CUdeviceptr arena_ = 0;
+    CUcontext ctx_ = nullptr;
+    bool ctx_warned_ = false;
+
+    // ---- shared state (mu_)
     std::map<uint64_t, uint64_t> va_free_;          // offset -> len
     std::vector<int32_t> owner_;                    // granule -> row (or -1)
-
     std::vector<VgpuEntry> rows_;                   // host mirror (authoritative)
     std::vector<Side> side_;
     std::vector<int> free_rows_;
-    CUdeviceptr d_tbl_ = 0;
-    uint32_t tbl_cap_ = 0;
     uint32_t dirty_lo_ = UINT32_MAX, dirty_hi_ = 0;
-    VgpuEntry *h_tbl_stage_ = nullptr;              // pinned upload buffer
     uint64_t tick_ = 0;
-
-    uint64_t resident_mapped_ = 0, live_bytes_ = 0, host_used_ = 0;
-    std::multimap<size_t, CUmemGenericAllocationHandle> phys_pool_;
-    uint64_t phys_pool_bytes_ = 0;
-    std::vector<Slab> slabs_;
-
-    // independent queues: a pack never waits behind an unpack that is itself waiting for its H2D, and a victim
-    // scan never waits behind either
-    CUstream s_scan_ = nullptr, s_pack_ = nullptr, s_unpack_ = nullptr, s_out_ = nullptr, s_in_ = nullptr;
-    std::vector<Slot> ring_out_, ring_in_;
-    int cur_out_ = 0, cur_in_ = 0;
+    uint64_t resident_mapped_ = 0;                  // mapped bytes of rows that are resident or loading
+    uint64_t evicting_mapped_ = 0;                  // mapped bytes of rows whose eviction is in flight (still hold physical memory)
+    std::atomic<uint64_t> live_bytes_{0}, resident_pub_{0};
+    std::atomic<uint64_t> host_used_{0};
+    struct QEntry { int row; uint32_t gen; };
+    std::deque<QEntry> demand_q_, prefetch_q_;
+    uint64_t queued_prefetch_bytes_ = 0, prefetched_bytes_ = 0;
+    uint64_t live_mapped_ = 0;                      // mapped-size sum of the live rows (all resident => nothing to prefetch)
+    std::deque<uint32_t> evicting_;                 // rows in PH_EVICTING, issue order
+    std::deque<uint32_t> zombies_;
     std::vector<CUevent> use_ring_;                 // last-use events, indexed by seq % size
+    std::vector<CUstream> use_stream_;              // stream each use event was recorded on
     uint64_t use_seq_ = 0;
-    std::vector<CUevent> ready_free_;
-    std::unique_ptr<VictimScanner> scanner_;
-    std::vector<PendingHost> pending_host_;
-    std::vector<uint32_t> out_pending_;             // victims packed but not yet unmapped (page_out_finish)
-    // reaper: waits for a batch's last pack, unmaps the victims (VMM calls cost 0.1-1 ms each under load on B200) and
-    // returns their physical handles to the pool while the admitting thread is already mapping the incoming rows
-    struct ReapJob { std::vector<uint32_t> rows; std::vector<CUdeviceptr> bases; std::vector<size_t> mapped; CUevent packed; };
-    std::thread reaper_;
-    std::mutex rq_mu_;
-    std::condition_variable rq_cv_;
-    std::condition_variable_any reap_cv_;          // waited on with mu_ held
-    std::deque<ReapJob> rq_;
-    bool reaper_stop_ = false, reaper_busy_ = false;
-    CUcontext ctx_ = nullptr;
-    bool ctx_warned_ = false;
-    uint64_t evicting_mapped_ = 0;
-    void reaper_main();
-    void wait_not_evicting(int row);
-    std::vector<InJob> in_jobs_;                    // page-in plan of the admission in progress
-    struct TraceRec { uint64_t t_begin = 0, t_packs = 0, t_staged = 0, t_unmapped = 0, t_mapped = 0, t_end = 0; std::vector<CUevent> d2h, h2d; };
-    std::vector<TraceRec> trace_;
-    uint32_t trace_want_ = 0, trace_skip_ = 0;
-    bool trace_dumped_ = false;
-    CUevent trace_base_ = nullptr;
-    uint64_t trace_base_ns_ = 0;
-    TraceRec *tr_ = nullptr;                        // record of the admission in progress (or null)
-    void trace_mark(std::vector<CUevent> *v, CUstream s);
-    // victims selected by the last scan beyond what was needed then, in LRU order. They stay the exact LRU prefix for
-    // as long as they are untouched (anything touched or created since carries a larger tick), so consuming them
-    // is equivalent to re-scanning; an entry whose row changed is simply skipped.
-    struct Cand { uint32_t row; uint64_t touch, base; };
-    std::deque<Cand> victim_cache_;
-    uint32_t scan_lookahead_ = 8;
+    std::vector<CUevent> ready_free_;               // event pool shared by application threads and the pager (mu_)
+    bool stop_ = false, pager_idle_ = true, kick_ = false;
+    void kick_pager_locked() { kick_ = true; cv_pager_.notify_one(); }
+    void drop_prefetch_queue_locked();
+    void fail_demands_locked(CUresult rc);
+    // predictor
+    std::vector<int32_t> succ_;                     // row -> row touched right after it last time
+    int last_row_ = -1;
+    uint32_t pred_hist_ = 0, pred_count_ = 0;       // last 32 predictions (1 = right)
     SwapStats st_;
     vgpu_swap_record_t *shared_ = nullptr;
     // Physical pressure: the quota (quota_cap_) promises more than the device can give right now — other containers of an
@@ -240,14 +298,38 @@ class SwapEngine {
     bool pressure_ = false;
     uint32_t pressure_probe_ = 0;
     uint64_t pressure_events_ = 0;
-    void publish_locked();
+
+    // ---- pager-private state (touched by the pager thread only, no lock)
+    std::thread pager_;
+    SwapStats pst_;                                 // deltas, folded into st_ under mu_
+    std::multimap<size_t, CUmemGenericAllocationHandle> phys_pool_;
+    uint64_t phys_pool_bytes_ = 0;
+    CUdeviceptr d_tbl_ = 0;
+    uint32_t tbl_cap_ = 0;
+    VgpuEntry *h_tbl_stage_ = nullptr;              // pinned upload buffer
+    // independent queues: a pack never waits behind an unpack that is itself waiting for its H2D, and a victim
+    // scan never waits behind either
+    CUstream s_scan_ = nullptr, s_pack_ = nullptr, s_unpack_ = nullptr, s_out_ = nullptr, s_in_ = nullptr;
+    std::vector<Slot> ring_out_, ring_in_;
+    int cur_out_ = 0, cur_in_ = 0;
+    std::unique_ptr<VictimScanner> scanner_;
+    std::vector<CUevent> ev_pool_;
+    bool unmap_runs_ok_ = true;                     // one cuMemUnmap may span several adjacent mappings (probed at run time)
+    // victims selected by the last scan beyond what was needed then, in LRU order. They stay the exact LRU prefix for
+    // as long as they are untouched (anything touched or created since carries a larger tick), so consuming them
+    // is equivalent to re-scanning; an entry whose row changed is simply skipped.
+    struct Cand { uint32_t row; uint64_t touch, base; };
+    std::deque<Cand> victim_cache_;
     struct Prof { CUevent a, b; bool unpack; uint64_t bytes; };
     CUdeviceptr d_span_ = 0;                        // profiling: {min start, max end} per launch, pre-set to {~0, 0}
     uint32_t span_cap_ = 0, span_next_ = 0, span_read_ = 0;
     std::vector<uint8_t> span_unpack_;
-    CUdeviceptr next_span(bool unpack);
-    void harvest_spans();
     std::vector<Prof> prof_;
+    std::atomic<bool> profile_{false};
+
+    // ---- pinned pool (host_mu_)
+    std::mutex host_mu_;
+    std::vector<Slab> slabs_;
 };
 
 }  // namespace vgpu

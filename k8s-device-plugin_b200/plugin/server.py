@@ -175,8 +175,11 @@ class NvidiaDevicePlugin:
                 return self._abort(context, "device allocate number not matched")
             self.pods.patch_pod_annotations(current, {TO_ALLOCATE: core.erase_next_device_request(anno)})
             try:                                               # server.go:364-367
-                os.makedirs(cache_dir, mode=0o777, exist_ok=True)
-                os.makedirs("/tmp/vgpulock", mode=0o777, exist_ok=True)
+                # MkdirAll + Chmod(0777): the mode passed to makedirs is masked by the daemon's umask, and a
+                # runAsNonRoot container must be able to create its region file in there
+                for d in (cache_dir, "/tmp/vgpulock"):
+                    os.makedirs(d, mode=0o777, exist_ok=True)
+                    os.chmod(d, 0o777)
             except OSError:
                 pass
             c = resp.container_responses.add()

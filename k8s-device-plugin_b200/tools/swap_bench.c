@@ -21,7 +21,13 @@
 #define CK(x) do { CUresult _r = (x); if (_r != CUDA_SUCCESS) { const char *s = 0; cuGetErrorName(_r, &s); \
     fprintf(stderr, "swap_bench: %s -> %d %s (line %d)\n", #x, (int)_r, s ? s : "?", __LINE__); printf("{\"error\": \"%s rc=%d\"}\n", #x, (int)_r); exit(3); } } while (0)
 
-typedef struct { uint64_t v[17]; double pack_ms, unpack_ms; uint64_t scan_cache_hits, host_admit_ns, host_scan_ns, host_packsync_ns, host_vmm_ns, host_ring_ns; double pack_span_ms, unpack_span_ms; } swap_stats_t; /* mirrors vgpu_swap_stats_t */
+/* mirrors vgpu_swap_stats_t (include/vgpu.h) */
+typedef struct {
+    uint64_t v[17]; double pack_ms, unpack_ms; uint64_t scan_cache_hits, host_admit_ns, host_wait_ns, host_vmm_ns;
+    uint64_t pager_vmm_ns, pager_scan_ns, pager_packsync_ns, pager_ring_ns, pager_busy_ns, vmm_calls;
+    double pack_span_ms, unpack_span_ms;
+    uint64_t direct_out_bytes, direct_in_bytes, prefetch_issued, prefetch_hits, prefetch_wasted, demand_waits, clean_evictions, host_slabs, host_slabs_local;
+} swap_stats_t;
 typedef int (*stats_fn)(int, swap_stats_t *);
 typedef int (*prof_fn)(int, int);
 
@@ -190,7 +196,10 @@ int main(int argc, char **argv) {
            "\"pack_ms\": %.3f, \"unpack_ms\": %.3f, \"pack_bytes\": %llu, \"unpack_bytes\": %llu, "
            "\"pack_launches\": %llu, \"unpack_launches\": %llu, \"scan_launches\": %llu, \"faults\": %llu, \"evictions\": %llu, "
            "\"phys_creates\": %llu, \"phys_reuses\": %llu, \"scans\": %llu, \"scan_cache_hits\": %llu, "
-           "\"host_ms\": {\"admit\": %.1f, \"scan\": %.1f, \"packsync\": %.1f, \"vmm\": %.1f, \"ringwait\": %.1f}, "
+           "\"host_ms\": {\"admit\": %.1f, \"wait\": %.1f, \"vmm\": %.1f}, "
+           "\"pager_ms\": {\"busy\": %.1f, \"vmm\": %.1f, \"scan\": %.1f, \"packsync\": %.1f, \"ringwait\": %.1f}, \"vmm_calls\": %llu, "
+           "\"direct_in_bytes\": %llu, \"direct_out_bytes\": %llu, \"prefetch\": {\"issued\": %llu, \"hits\": %llu, \"wasted\": %llu}, "
+           "\"demand_waits\": %llu, \"clean_evictions\": %llu, \"host_slabs\": [%llu, %llu], "
            "\"pack_span_ms\": %.3f, \"unpack_span_ms\": %.3f}\n",
            ragged_lo, ragged_hi, nbuf, mib, steps, warmup, order, managed, ballast_mib, ev_ms, w1 - w0, w_enq - w0, t_alloc1 - t_alloc0, t_ver1 - t_ver0,
            get_stats ? "true" : "false", (unsigned long long)pin, (unsigned long long)pout,
@@ -201,8 +210,13 @@ int main(int argc, char **argv) {
            (unsigned long long)(s1.v[3] - s0.v[3]), (unsigned long long)(s1.v[2] - s0.v[2]),
            (unsigned long long)(s1.v[13] - s0.v[13]), (unsigned long long)(s1.v[14] - s0.v[14]),
            (unsigned long long)(s1.v[8] - s0.v[8]), (unsigned long long)(s1.scan_cache_hits - s0.scan_cache_hits),
-           (s1.host_admit_ns - s0.host_admit_ns) / 1e6, (s1.host_scan_ns - s0.host_scan_ns) / 1e6, (s1.host_packsync_ns - s0.host_packsync_ns) / 1e6,
-           (s1.host_vmm_ns - s0.host_vmm_ns) / 1e6, (s1.host_ring_ns - s0.host_ring_ns) / 1e6,
+           (s1.host_admit_ns - s0.host_admit_ns) / 1e6, (s1.host_wait_ns - s0.host_wait_ns) / 1e6, (s1.host_vmm_ns - s0.host_vmm_ns) / 1e6,
+           (s1.pager_busy_ns - s0.pager_busy_ns) / 1e6, (s1.pager_vmm_ns - s0.pager_vmm_ns) / 1e6, (s1.pager_scan_ns - s0.pager_scan_ns) / 1e6,
+           (s1.pager_packsync_ns - s0.pager_packsync_ns) / 1e6, (s1.pager_ring_ns - s0.pager_ring_ns) / 1e6, (unsigned long long)(s1.vmm_calls - s0.vmm_calls),
+           (unsigned long long)(s1.direct_in_bytes - s0.direct_in_bytes), (unsigned long long)(s1.direct_out_bytes - s0.direct_out_bytes),
+           (unsigned long long)(s1.prefetch_issued - s0.prefetch_issued), (unsigned long long)(s1.prefetch_hits - s0.prefetch_hits),
+           (unsigned long long)(s1.prefetch_wasted - s0.prefetch_wasted), (unsigned long long)(s1.demand_waits - s0.demand_waits),
+           (unsigned long long)(s1.clean_evictions - s0.clean_evictions), (unsigned long long)s1.host_slabs, (unsigned long long)s1.host_slabs_local,
            s1.pack_span_ms - s0.pack_span_ms, s1.unpack_span_ms - s0.unpack_span_ms);
     fflush(stdout);
     return mism ? 4 : 0;

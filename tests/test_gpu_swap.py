@@ -45,7 +45,7 @@ def _verify(sw, bufs, sizes, touches):
 
 
 def test_cyclic_oversubscription_keeps_every_word():
-    sw = v.Swap(resident_cap=256 * MiB, chunk_bytes=16 * MiB, ring_slots=3)
+    sw = v.Swap(resident_cap=256 * MiB, chunk_bytes=16 * MiB, ring_slots=3, prefetch_bytes=None)   # pure demand paging: exact counts
     n, nbytes = 12, 64 * MiB                       # 768 MiB live under a 256 MiB quota
     bufs = [sw.alloc(nbytes) for _ in range(n)]
     for i, p in enumerate(bufs):
@@ -63,6 +63,58 @@ def test_cyclic_oversubscription_keeps_every_word():
     for p in bufs:
         sw.free(p)
     assert sw.stats()["live_bytes"] == 0
+    sw.close()
+
+
+def test_cyclic_oversubscription_with_the_prefetch_pipeline():
+    """Default engine: after one sweep the predictor knows the cycle; the pager pages the next buffers in and evicts LRU
+    buffers ahead with plain DMA (no pack kernel). Every word must still be right, and no VMM call may run on this thread."""
+    sw = v.Swap(resident_cap=512 * MiB)
+    n, nbytes = 24, 64 * MiB                       # 1.5 GiB live under a 512 MiB quota
+    bufs = [sw.alloc(nbytes) for _ in range(n)]
+    for i, p in enumerate(bufs):
+        _fill(sw, p, nbytes, i)
+    touches = [0] * n
+    for t in range(4 * n):
+        _touch(sw, bufs[t % n], nbytes)
+        touches[t % n] += 1
+    assert _verify(sw, bufs, [nbytes] * n, touches) == 0
+    sw.drain()
+    s = sw.stats()
+    assert s["resident_bytes"] <= 512 * MiB
+    assert s["faults"] >= 4 * n - 8
+    assert s["prefetch_issued"] > n and s["direct_in_bytes"] > 2 * n * nbytes and s["direct_out_bytes"] > 2 * n * nbytes
+    assert s["host_vmm_ns"] == 0 and s["pager_vmm_ns"] > 0
+    for p in bufs:
+        sw.free(p)
+    sw.drain()
+    assert sw.stats()["live_bytes"] == 0 and sw.stats()["resident_bytes"] == 0
+    sw.close()
+
+
+def test_clean_buffers_are_evicted_without_a_copy_and_read_mostly_advice_keeps_them_clean():
+    """A buffer that was paged in and only READ since keeps its pinned block: evicting it moves no bytes. Kernel launches
+    count as writes unless the buffer was advised read-mostly (cuMemAdvise SET_READ_MOSTLY under the hook)."""
+    sw = v.Swap(resident_cap=128 * MiB, chunk_bytes=8 * MiB, ring_slots=2, prefetch_bytes=None)
+    n, nbytes = 8, 32 * MiB
+    bufs = [sw.alloc(nbytes) for _ in range(n)]
+    for i, p in enumerate(bufs):
+        _fill(sw, p, nbytes, i)
+        sw.advise_read_mostly(p)
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize(); sw.drain()
+    s0 = sw.stats()
+    for sweep in range(3):                         # read-only sweeps: page-ins only after the first eviction wrote each block
+        for i, p in enumerate(bufs):
+            sw.acquire([p], _stream())
+            assert v.lib().vgpu_wl_verify(p, nbytes // 8, i, 0, cnt.data_ptr(), C.c_void_p(_stream())) == 0
+            sw.release([p], _stream())             # a launch: would dirty the buffer without the advice
+    torch.cuda.synchronize(); sw.drain()
+    s1 = sw.stats()
+    assert int(cnt.item()) == 0
+    assert s1["page_in_bytes"] - s0["page_in_bytes"] >= 3 * n * nbytes - 4 * nbytes
+    assert s1["page_out_bytes"] - s0["page_out_bytes"] <= 4 * nbytes        # only the buffers still dirty from the fill
+    assert s1["clean_evictions"] - s0["clean_evictions"] >= 2 * n
     sw.close()
 
 
