@@ -137,6 +137,9 @@ typedef struct vgpu_swap_stats {
     uint64_t demand_waits;      /* admissions that had to block for the pager */
     uint64_t clean_evictions;   /* evictions without a copy (pinned block still valid) */
     uint64_t host_slabs, host_slabs_local;   /* pinned slabs allocated / of those on the GPU's NUMA node */
+    /* diagnostics: where the pager's time goes (ns) — cuMemUnmap, cuMemSetAccess, copy/event enqueue calls, event polling,
+     * re-taking the engine lock, and busy time per step (freed rows, reap, demand, prefetch, evict-ahead) */
+    uint64_t pager_unmap_ns, pager_setaccess_ns, pager_issue_ns, pager_poll_ns, pager_lock_ns, pager_step_ns[5];
 } vgpu_swap_stats_t;
 int vgpu_swap_create(int dev, const vgpu_swap_config_t *cfg, vgpu_swap_t **out);
 void vgpu_swap_destroy(vgpu_swap_t *s);

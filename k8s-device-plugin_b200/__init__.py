@@ -67,10 +67,11 @@ class SwapStats(C.Structure):
         "pager_ring_ns", "pager_busy_ns", "vmm_calls")] + [
         ("pack_span_ms", C.c_double), ("unpack_span_ms", C.c_double)] + [(n, C.c_uint64) for n in (
         "direct_out_bytes", "direct_in_bytes", "prefetch_issued", "prefetch_hits", "prefetch_wasted", "demand_waits",
-        "clean_evictions", "host_slabs", "host_slabs_local")]
+        "clean_evictions", "host_slabs", "host_slabs_local", "pager_unmap_ns", "pager_setaccess_ns", "pager_issue_ns",
+        "pager_poll_ns", "pager_lock_ns")] + [("pager_step_ns", C.c_uint64 * 5)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        return {n: (list(getattr(self, n)) if n == "pager_step_ns" else getattr(self, n)) for n, _ in self._fields_}
 
 
 class LimiterStats(C.Structure):

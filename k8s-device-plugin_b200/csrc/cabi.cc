@@ -242,6 +242,9 @@ static void fill_stats(const SwapStats &s, vgpu_swap_stats_t *o) {
     o->prefetch_issued = s.prefetch_issued; o->prefetch_hits = s.prefetch_hits; o->prefetch_wasted = s.prefetch_wasted;
     o->demand_waits = s.demand_waits; o->clean_evictions = s.clean_evictions;
     o->host_slabs = s.host_slabs; o->host_slabs_local = s.host_slabs_local;
+    o->pager_unmap_ns = s.pager_unmap_ns; o->pager_setaccess_ns = s.pager_setaccess_ns; o->pager_issue_ns = s.pager_issue_ns;
+    o->pager_poll_ns = s.pager_poll_ns; o->pager_lock_ns = s.pager_lock_ns;
+    for (int i = 0; i < 5; i++) o->pager_step_ns[i] = s.pager_step_ns[i];
 }
 VGPU_API int vgpu_swap_create(int dev, const vgpu_swap_config_t *cfg, vgpu_swap_t **out) {
     if (!out) return CUDA_ERROR_INVALID_VALUE;

@@ -477,6 +477,13 @@ extern "C" __global__ void __launch_bounds__(1024) vgpu_victim_small(const VgpuE
     }
 }
 
+// Small control-plane copies (table rows up, scan results down) done by the SMs straight from / into pinned host memory:
+// a cuMemcpyAsync of a few KiB would queue behind tens of MiB of page traffic on the copy engines (they serve copies in
+// submission order across streams) and stall the pager for milliseconds; a load/store over PCIe does not.
+extern "C" __global__ void vgpu_copy16(uint4 *__restrict__ dst, const uint4 *__restrict__ src, uint64_t n16) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 // ------------------------------------------------------------------------------------------------ limiter stamp
 extern "C" __global__ void vgpu_stamp(uint64_t *slot) {
     uint64_t t = globaltimer();

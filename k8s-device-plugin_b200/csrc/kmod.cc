@@ -50,7 +50,7 @@ const Kernels *kernels_for_current_ctx() {
     struct { const char *name; CUfunction *fn; } tab[] = {
         {"vgpu_pack_tma", &k->pack_tma}, {"vgpu_pack_generic", &k->pack_generic},
         {"vgpu_victim_init", &k->victim_init}, {"vgpu_victim_hist", &k->victim_hist}, {"vgpu_victim_emit", &k->victim_emit}, {"vgpu_victim_count", &k->victim_count}, {"vgpu_victim_small", &k->victim_small},
-        {"vgpu_stamp", &k->stamp}, {"vgpu_wl_fill", &k->wl_fill}, {"vgpu_wl_touch", &k->wl_touch},
+        {"vgpu_stamp", &k->stamp}, {"vgpu_copy16", &k->copy16}, {"vgpu_wl_fill", &k->wl_fill}, {"vgpu_wl_touch", &k->wl_touch},
         {"vgpu_wl_verify", &k->wl_verify}, {"vgpu_wl_empty", &k->wl_empty},
     };
     for (auto &t : tab) {
@@ -127,6 +127,16 @@ CUresult launch_pack(const Kernels *k, const PackSegment *segs, size_t nseg, CUs
     return r;
 }
 
+CUresult launch_copy16(const Kernels *k, CUdeviceptr dst, CUdeviceptr src, size_t bytes, CUstream stream) {
+    if (!k) return CUDA_ERROR_NOT_INITIALIZED;
+    if (bytes == 0) return CUDA_SUCCESS;
+    if ((dst | src | bytes) & 15u) return CUDA_ERROR_INVALID_VALUE;
+    uint64_t n16 = bytes / 16;
+    unsigned grid = (unsigned)std::min<uint64_t>((n16 + 255) / 256, (uint64_t)k->sm_count * 4);
+    void *a[] = {&dst, &src, &n16};
+    return drv().cuLaunchKernel(k->copy16, grid, 1, 1, 256, 1, 1, 0, stream, a, nullptr);
+}
+
 VictimScanner::~VictimScanner() {
     const DriverTable &d = drv();
     if (d_state_) d.cuMemFree_v2(d_state_);
@@ -141,9 +151,12 @@ CUresult VictimScanner::init(const Kernels *k, uint32_t max_rows) {
     cap_ = max_rows;
     CUresult r;
     if ((r = d.cuMemAlloc_v2(&d_state_, sizeof(VgpuScanState))) != CUDA_SUCCESS) return r;
-    if ((r = d.cuMemAlloc_v2(&d_out_, (size_t)cap_ * 4)) != CUDA_SUCCESS) return r;
-    if ((r = d.cuMemHostAlloc(&h_state_, 64, 0)) != CUDA_SUCCESS) return r;
-    if ((r = d.cuMemHostAlloc((void **)&h_out_, (size_t)cap_ * 4, 0)) != CUDA_SUCCESS) return r;
+    if ((r = d.cuMemAlloc_v2(&d_out_, ((size_t)cap_ * 4 + 15) & ~(size_t)15)) != CUDA_SUCCESS) return r;
+    if ((r = d.cuMemHostAlloc(&h_state_, 64, CU_MEMHOSTALLOC_DEVICEMAP)) != CUDA_SUCCESS) return r;
+    if ((r = d.cuMemHostAlloc((void **)&h_out_, ((size_t)cap_ * 4 + 15) & ~(size_t)15, CU_MEMHOSTALLOC_DEVICEMAP)) != CUDA_SUCCESS) return r;
+    // the results travel down by kernel stores into pinned memory, not by a copy engine (see vgpu_copy16)
+    if ((r = d.cuMemHostGetDevicePointer_v2(&dh_state_, h_state_, 0)) != CUDA_SUCCESS) return r;
+    if ((r = d.cuMemHostGetDevicePointer_v2(&dh_out_, h_out_, 0)) != CUDA_SUCCESS) return r;
     return CUDA_SUCCESS;
 }
 
@@ -203,15 +216,16 @@ CUresult VictimScanner::scan(CUdeviceptr d_tbl, uint32_t n, uint64_t need, uint6
     }
     }
     if (launches_out) *launches_out += launches;
-    if ((r = d.cuMemcpyDtoHAsync_v2(h_state_, d_state_, 64, stream)) != CUDA_SUCCESS) return r;
+    if ((r = launch_copy16(k_, dh_state_, d_state_, 64, stream)) != CUDA_SUCCESS) return r;
     // optimistic first page of indices; the rest (rare) after the count is known
     uint32_t first = cap_ < 1024 ? cap_ : 1024;
-    if ((r = d.cuMemcpyDtoHAsync_v2(h_out_, d_out_, (size_t)first * 4, stream)) != CUDA_SUCCESS) return r;
+    if ((r = launch_copy16(k_, dh_out_, d_out_, ((size_t)first * 4 + 15) & ~(size_t)15, stream)) != CUDA_SUCCESS) return r;
     if ((r = d.cuStreamSynchronize(stream)) != CUDA_SUCCESS) return r;
     const VgpuScanState *hs = static_cast<const VgpuScanState *>(h_state_);
     uint32_t cnt = hs->out_count;
     if (cnt > first) {
-        if ((r = d.cuMemcpyDtoHAsync_v2(h_out_ + first, d_out_ + (size_t)first * 4, (size_t)(cnt - first) * 4, stream)) != CUDA_SUCCESS) return r;
+        size_t from = (size_t)first * 4 & ~(size_t)15, to = ((size_t)cnt * 4 + 15) & ~(size_t)15;
+        if ((r = launch_copy16(k_, dh_out_ + from, d_out_ + from, to - from, stream)) != CUDA_SUCCESS) return r;
         if ((r = d.cuStreamSynchronize(stream)) != CUDA_SUCCESS) return r;
     }
     victims->assign(h_out_, h_out_ + cnt);

@@ -14,7 +14,7 @@ struct Kernels {
     CUmodule mod = nullptr;
     CUfunction pack_tma = nullptr, pack_generic = nullptr;
     CUfunction victim_init = nullptr, victim_hist = nullptr, victim_emit = nullptr, victim_count = nullptr, victim_small = nullptr;
-    CUfunction stamp = nullptr;
+    CUfunction stamp = nullptr, copy16 = nullptr;
     CUfunction wl_fill = nullptr, wl_touch = nullptr, wl_verify = nullptr, wl_empty = nullptr;
     int sm_count = 0;
 };
@@ -35,6 +35,10 @@ PackConfig &pack_config();
 CUresult launch_pack(const Kernels *k, const PackSegment *segs, size_t nseg, CUstream stream, int *launches_out = nullptr,
                      CUdeviceptr span = 0);   // span: optional {min start, max end} %globaltimer slot, pre-set to {~0, 0}
 
+// dst/src: device addresses (device memory or the device view of pinned host memory), bytes a multiple of 16. Done by a
+// kernel, not by a copy engine: see vgpu_copy16 in kernels.cu.
+CUresult launch_copy16(const Kernels *k, CUdeviceptr dst, CUdeviceptr src, size_t bytes, CUstream stream);
+
 // Exact-LRU victim selection on the GPU (see kernels.cu). Owns its device/pinned scratch.
 class VictimScanner {
    public:
@@ -48,7 +52,7 @@ class VictimScanner {
 
    private:
     const Kernels *k_ = nullptr;
-    CUdeviceptr d_state_ = 0, d_out_ = 0;
+    CUdeviceptr d_state_ = 0, d_out_ = 0, dh_state_ = 0, dh_out_ = 0;   // dh_*: device view of the pinned result buffers
     uint32_t cap_ = 0;
     void *h_state_ = nullptr;   // pinned: VgpuScanState header readback
     uint32_t *h_out_ = nullptr; // pinned

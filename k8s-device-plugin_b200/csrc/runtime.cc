@@ -127,6 +127,8 @@ bool Runtime::ensure_initialized() {
 }
 
 void Runtime::on_exit() {
+    // the pager threads must not be inside the driver when it tears itself down behind this handler
+    for (int d = 0; d < VGPU_MAX_DEVICES; d++) if (swap_[d]) swap_[d]->stop_pager();
     if (std::getenv("VGPU_PRINT_STATS")) {
         if (limiter_) {
             LimiterStats s = limiter_->stats();
@@ -142,6 +144,9 @@ void Runtime::on_exit() {
                 std::fprintf(stderr, "[vgpu-b200 stats] swap dev %d ms: app admit=%.1f wait=%.1f vmm=%.1f | pager busy=%.1f vmm=%.1f (%lu calls) scan=%.1f packsync=%.1f ringwait=%.1f slabs=%lu local=%lu\n", d,
                              s.host_admit_ns / 1e6, s.host_wait_ns / 1e6, s.host_vmm_ns / 1e6, s.pager_busy_ns / 1e6, s.pager_vmm_ns / 1e6, (unsigned long)s.vmm_calls,
                              s.pager_scan_ns / 1e6, s.pager_packsync_ns / 1e6, s.pager_ring_ns / 1e6, (unsigned long)s.host_slabs, (unsigned long)s.host_slabs_local);
+                std::fprintf(stderr, "[vgpu-b200 stats] swap dev %d pager vmm ms: unmap=%.1f setaccess=%.1f map=%.1f create=%.1f | issue=%.1f | steps zombies=%.1f reap=%.1f demand=%.1f prefetch=%.1f evict=%.1f\n", d, s.pager_unmap_ns / 1e6,
+                             s.pager_setaccess_ns / 1e6, s.pager_map_ns / 1e6, s.pager_create_ns / 1e6, s.pager_issue_ns / 1e6, s.pager_step_ns[0] / 1e6, s.pager_step_ns[1] / 1e6,
+                             s.pager_step_ns[2] / 1e6, s.pager_step_ns[3] / 1e6, s.pager_step_ns[4] / 1e6);
                 std::fprintf(stderr, "[vgpu-b200 stats] swap dev %d: prefetch issued=%lu hits=%lu wasted=%lu demand_waits=%lu clean_evictions=%lu direct in=%lu out=%lu\n", d,
                              (unsigned long)s.prefetch_issued, (unsigned long)s.prefetch_hits, (unsigned long)s.prefetch_wasted, (unsigned long)s.demand_waits,
                              (unsigned long)s.clean_evictions, (unsigned long)s.direct_in_bytes, (unsigned long)s.direct_out_bytes);

@@ -44,10 +44,11 @@ SwapConfig SwapConfig::from_env(uint64_t resident_cap, uint64_t virtual_cap) {
     c.slab_bytes = (size_t)env_u64("VGPU_SWAP_SLAB_MB", 1024) << 20;
     c.arena_bytes = env_u64("VGPU_SWAP_ARENA_GB", 1024) << 30;
     c.profile = env_u64("VGPU_SWAP_PROFILE", 0) != 0;
-    c.scan_lookahead = (uint32_t)env_u64("VGPU_SWAP_SCAN_LOOKAHEAD", 8);
+    c.scan_lookahead = (uint32_t)env_u64("VGPU_SWAP_SCAN_LOOKAHEAD", c.scan_lookahead);
     c.prefetch_bytes = env_u64("VGPU_SWAP_PREFETCH_MB", c.prefetch_bytes >> 20) << 20;
     c.copy_bytes = (size_t)env_u64("VGPU_SWAP_COPY_MB", c.copy_bytes >> 20) << 20;
     c.batch_rows = (uint32_t)env_u64("VGPU_SWAP_BATCH_ROWS", c.batch_rows);
+    if (std::getenv("VGPU_SWAP_HEADROOM_MB")) c.headroom_bytes = env_u64("VGPU_SWAP_HEADROOM_MB", 0) << 20;
     c.host_backed = env_u64("VGPU_SWAP_HOST_BACKED", 0) != 0;
     if (c.ring_slots < 2) c.ring_slots = 2;
     if (c.chunk_bytes < (1u << 20)) c.chunk_bytes = 1u << 20;
@@ -190,7 +191,8 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
 
     tbl_cap_ = 4096;
     if (d.cuMemAlloc_v2(&d_tbl_, (size_t)tbl_cap_ * sizeof(VgpuEntry)) != CUDA_SUCCESS) return false;
-    if (d.cuMemHostAlloc((void **)&h_tbl_stage_, (size_t)tbl_cap_ * sizeof(VgpuEntry), 0) != CUDA_SUCCESS) return false;
+    if (d.cuMemHostAlloc((void **)&h_tbl_stage_, (size_t)tbl_cap_ * sizeof(VgpuEntry), CU_MEMHOSTALLOC_DEVICEMAP) != CUDA_SUCCESS) return false;
+    if (d.cuMemHostGetDevicePointer_v2(&dh_tbl_stage_, h_tbl_stage_, 0) != CUDA_SUCCESS) return false;
     scanner_.reset(new VictimScanner());
     if (scanner_->init(k_, tbl_cap_) != CUDA_SUCCESS) return false;
     use_ring_.resize(1024);
@@ -204,13 +206,19 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
     return true;
 }
 
+void SwapEngine::stop_pager() {
+    if (!pager_.joinable()) return;
+    { std::lock_guard<std::mutex> g(mu_); drop_prefetch_queue_locked(); stop_ = true; kick_ = true; }
+    cv_pager_.notify_all();
+    cv_admit_.notify_all();
+    pager_.join();
+}
+
 SwapEngine::~SwapEngine() {
     const DriverTable &d = drv();
     if (pager_.joinable()) {
         if (d.loaded) drain();
-        { std::lock_guard<std::mutex> g(mu_); stop_ = true; kick_ = true; }
-        cv_pager_.notify_all();
-        pager_.join();
+        stop_pager();
     }
     if (!d.loaded) return;
     for (CUstream s : {s_scan_, s_pack_, s_unpack_, s_out_, s_in_}) if (s) d.cuStreamSynchronize(s);
@@ -334,6 +342,7 @@ bool SwapEngine::reclaim_host_blocks(Lock &lk, uint64_t bytes) {
 }
 
 // ---------------------------------------------------------------------------------------------- table
+void SwapEngine::relock(Lock &lk) { uint64_t t0 = mono_ns(); lk.lock(); pst_.pager_lock_ns += mono_ns() - t0; }
 int SwapEngine::new_row() {
     if (!free_rows_.empty()) { int r = free_rows_.back(); free_rows_.pop_back(); return r; }
     rows_.push_back(VgpuEntry{});
@@ -359,10 +368,11 @@ CUresult SwapEngine::sync_table(Lock &lk, CUstream s) {
             d.cuMemFreeHost(h_tbl_stage_);
             d_tbl_ = 0; h_tbl_stage_ = nullptr;
             r = d.cuMemAlloc_v2(&d_tbl_, (size_t)nc * sizeof(VgpuEntry));
-            if (r == CUDA_SUCCESS) r = d.cuMemHostAlloc((void **)&h_tbl_stage_, (size_t)nc * sizeof(VgpuEntry), 0);
+            if (r == CUDA_SUCCESS) r = d.cuMemHostAlloc((void **)&h_tbl_stage_, (size_t)nc * sizeof(VgpuEntry), CU_MEMHOSTALLOC_DEVICEMAP);
+            if (r == CUDA_SUCCESS) r = d.cuMemHostGetDevicePointer_v2(&dh_tbl_stage_, h_tbl_stage_, 0);
             if (r == CUDA_SUCCESS) { scanner_.reset(new VictimScanner()); r = scanner_->init(k_, nc); }
         }
-        lk.lock();
+        relock(lk);
         if (r != CUDA_SUCCESS) return r;
         tbl_cap_ = nc;
         dirty_lo_ = 0; dirty_hi_ = (uint32_t)rows_.size();
@@ -372,7 +382,7 @@ CUresult SwapEngine::sync_table(Lock &lk, CUstream s) {
     // so this is immediate in practice)
     lk.unlock();
     CUresult r = d.cuStreamSynchronize(s);
-    lk.lock();
+    relock(lk);
     if (r != CUDA_SUCCESS) return r;
     n = (uint32_t)rows_.size();
     if (n > tbl_cap_) return sync_table(lk, s);          // grew meanwhile
@@ -380,7 +390,8 @@ CUresult SwapEngine::sync_table(Lock &lk, CUstream s) {
     if (lo >= hi) return CUDA_SUCCESS;
     std::memcpy(h_tbl_stage_ + lo, rows_.data() + lo, (size_t)(hi - lo) * sizeof(VgpuEntry));
     dirty_lo_ = UINT32_MAX; dirty_hi_ = 0;
-    CU_TRY(d.cuMemcpyHtoDAsync_v2(d_tbl_ + (size_t)lo * sizeof(VgpuEntry), h_tbl_stage_ + lo, (size_t)(hi - lo) * sizeof(VgpuEntry), s));
+    // by kernel, not by a copy engine: a 30 KiB cuMemcpyAsync would queue behind all the page traffic (see vgpu_copy16)
+    CU_TRY(launch_copy16(k_, d_tbl_ + (size_t)lo * sizeof(VgpuEntry), dh_tbl_stage_ + (size_t)lo * sizeof(VgpuEntry), (size_t)(hi - lo) * sizeof(VgpuEntry), s));
     return CUDA_SUCCESS;
 }
 
@@ -518,6 +529,9 @@ void SwapEngine::flush_pager_stats_locked() {
     st_.pack_ms += p.pack_ms; st_.unpack_ms += p.unpack_ms; st_.pack_span_ms += p.pack_span_ms; st_.unpack_span_ms += p.unpack_span_ms;
     st_.pager_vmm_ns += p.pager_vmm_ns; st_.pager_scan_ns += p.pager_scan_ns; st_.pager_packsync_ns += p.pager_packsync_ns;
     st_.pager_ring_ns += p.pager_ring_ns; st_.pager_busy_ns += p.pager_busy_ns; st_.vmm_calls += p.vmm_calls;
+    st_.pager_issue_ns += p.pager_issue_ns; st_.pager_poll_ns += p.pager_poll_ns; st_.pager_lock_ns += p.pager_lock_ns;
+    for (int i = 0; i < 5; i++) st_.pager_step_ns[i] += p.pager_step_ns[i];
+    st_.pager_unmap_ns += p.pager_unmap_ns; st_.pager_setaccess_ns += p.pager_setaccess_ns; st_.pager_map_ns += p.pager_map_ns; st_.pager_create_ns += p.pager_create_ns;
     st_.pack_bytes += p.pack_bytes; st_.unpack_bytes += p.unpack_bytes; st_.direct_out_bytes += p.direct_out_bytes; st_.direct_in_bytes += p.direct_in_bytes;
     st_.prefetch_issued += p.prefetch_issued; st_.prefetch_wasted += p.prefetch_wasted; st_.clean_evictions += p.clean_evictions;
     p = SwapStats{};
@@ -560,10 +574,10 @@ CUresult SwapEngine::obtain_phys(size_t mapped, CUmemGenericAllocationHandle *h,
     prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
     prop.location.id = dev_;
     CUresult r;
-    { ScopedNs t(&pst_.pager_vmm_ns); r = d.cuMemCreate(h, mapped, &prop, 0); }
+    { ScopedNs t(&pst_.pager_vmm_ns), t2(&pst_.pager_create_ns); r = d.cuMemCreate(h, mapped, &prop, 0); }
     if (r == CUDA_ERROR_OUT_OF_MEMORY && !phys_pool_.empty()) {
         trim_phys_pool(0);
-        ScopedNs t(&pst_.pager_vmm_ns);
+        ScopedNs t(&pst_.pager_vmm_ns), t2(&pst_.pager_create_ns);
         r = d.cuMemCreate(h, mapped, &prop, 0);
     }
     if (r == CUDA_SUCCESS) pst_.phys_creates++;
@@ -585,7 +599,7 @@ static void merge_runs(std::vector<std::pair<CUdeviceptr, size_t>> &v) {
 void SwapEngine::unmap_batch(std::vector<std::pair<CUdeviceptr, size_t>> &ranges) {
     const DriverTable &d = drv();
     if (ranges.empty()) return;
-    ScopedNs t(&pst_.pager_vmm_ns);
+    ScopedNs t(&pst_.pager_vmm_ns), t2(&pst_.pager_unmap_ns);
     std::vector<std::pair<CUdeviceptr, size_t>> runs = ranges;
     if (unmap_runs_ok_) {
         merge_runs(runs);
@@ -607,7 +621,7 @@ void SwapEngine::unmap_batch(std::vector<std::pair<CUdeviceptr, size_t>> &ranges
 CUresult SwapEngine::set_access_batch(std::vector<std::pair<CUdeviceptr, size_t>> &ranges) {
     const DriverTable &d = drv();
     if (ranges.empty()) return CUDA_SUCCESS;
-    ScopedNs t(&pst_.pager_vmm_ns);
+    ScopedNs t(&pst_.pager_vmm_ns), t2(&pst_.pager_setaccess_ns);
     CUmemAccessDesc acc = {};
     acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
     acc.location.id = dev_;
@@ -731,7 +745,7 @@ CUresult SwapEngine::choose_victims(Lock &lk, uint64_t shortage, std::vector<uin
         CUdeviceptr tbl = d_tbl_;
         lk.unlock();
         r = scanner_->scan(tbl, n, ask, tick, s_scan_, &found, &found_bytes, &insufficient, &launches);
-        lk.lock();
+        relock(lk);
         pst_.scan_launches += launches;
         pst_.scans++;
         if (r != CUDA_SUCCESS) { LOG_ERROR("victim scan failed: %d %s", (int)r, cu_err(r)); return r; }
@@ -794,7 +808,7 @@ CUresult SwapEngine::evict_direct(Lock &lk, const std::vector<uint32_t> &victims
         it.done = get_event();
         if (it.copy && !it.has_host) {
             if (!host_alloc(it.len, &it.host_off)) {
-                lk.lock();
+                relock(lk);
                 bool ok = reclaim_host_blocks(lk, it.len);
                 lk.unlock();
                 if (!ok || !host_alloc(it.len, &it.host_off)) { rc = CUDA_ERROR_OUT_OF_MEMORY; it.failed = true; put_event(it.done); it.done = nullptr; continue; }
@@ -802,6 +816,7 @@ CUresult SwapEngine::evict_direct(Lock &lk, const std::vector<uint32_t> &victims
             it.has_host = true;
         }
         CUstream s = it.copy ? s_out_ : s_scan_;
+        ScopedNs t_issue(&pst_.pager_issue_ns);
         for (CUevent e : it.wait) d.cuStreamWaitEvent(s, e, 0);
         if (it.copy) {
             unsigned char *hp = host_ptr(it.host_off);
@@ -817,7 +832,7 @@ CUresult SwapEngine::evict_direct(Lock &lk, const std::vector<uint32_t> &victims
         }
         d.cuEventRecord(it.done, s);
     }
-    lk.lock();
+    relock(lk);
     for (OutItem &it : items) {
         Side &s = side_[it.row];
         if (it.failed) {
@@ -921,7 +936,7 @@ CUresult SwapEngine::load_direct(Lock &lk, std::vector<InItem> &items) {
         pressure_seen |= pressure;
         if (it.rc != CUDA_SUCCESS) continue;
         {
-            ScopedNs t(&pst_.pager_vmm_ns);
+            ScopedNs t(&pst_.pager_vmm_ns), t2(&pst_.pager_map_ns);
             it.rc = d.cuMemMap(it.base, it.mapped, 0, it.h, 0);
         }
         if (it.rc != CUDA_SUCCESS) { LOG_ERROR("cuMemMap failed: %d %s", (int)it.rc, cu_err(it.rc)); pool_phys(it.mapped, it.h); continue; }
@@ -937,6 +952,7 @@ CUresult SwapEngine::load_direct(Lock &lk, std::vector<InItem> &items) {
         }
         if (!it.has_host) { if (it.ready) { ev_pool_.push_back(it.ready); it.ready = nullptr; } continue; }   // never written: nothing to load
         if (!it.ready) it.ready = get_event();
+        ScopedNs t_issue(&pst_.pager_issue_ns);
         if (it.after) d.cuStreamWaitEvent(s_in_, it.after, 0);
         unsigned char *hp = host_ptr(it.host_off);
         for (uint64_t o = 0; o < it.len; o += cfg_.copy_bytes) {
@@ -950,7 +966,7 @@ CUresult SwapEngine::load_direct(Lock &lk, std::vector<InItem> &items) {
     }
     size_t fr = 0, tot = 0;
     if (pressure_seen) d.cuMemGetInfo_v2(&fr, &tot);
-    lk.lock();
+    relock(lk);
     CUresult rc = CUDA_SUCCESS;
     for (InItem &it : items) {
         if (it.rc == CUDA_SUCCESS) { side_[it.row].retries = 0; commit_load_locked(it); continue; }
@@ -1110,7 +1126,7 @@ CUresult SwapEngine::swap_staged(Lock &lk, int row, const std::vector<uint32_t> 
         for (OutItem &it : outs) ranges.emplace_back(it.base, it.mapped);
         unmap_batch(ranges);
     }
-    lk.lock();
+    relock(lk);
     for (OutItem &it : outs) {
         Side &s = side_[it.row];
         if (!evicted) {                              // nothing was unmapped: the victims stay where they are
@@ -1149,7 +1165,7 @@ CUresult SwapEngine::swap_staged(Lock &lk, int row, const std::vector<uint32_t> 
     bool pressure = false;
     rc = obtain_phys(in.mapped, &in.h, &pressure);
     if (rc == CUDA_SUCCESS) {
-        { ScopedNs t(&pst_.pager_vmm_ns); rc = d.cuMemMap(in.base, in.mapped, 0, in.h, 0); }
+        { ScopedNs t(&pst_.pager_vmm_ns), t2(&pst_.pager_map_ns); rc = d.cuMemMap(in.base, in.mapped, 0, in.h, 0); }
         if (rc != CUDA_SUCCESS) pool_phys(in.mapped, in.h);
     }
     if (rc == CUDA_SUCCESS) {
@@ -1179,7 +1195,7 @@ CUresult SwapEngine::swap_staged(Lock &lk, int row, const std::vector<uint32_t> 
     } else if (rc == CUDA_SUCCESS && in.ready) { ev_pool_.push_back(in.ready); in.ready = nullptr; }
     size_t fr = 0, tot = 0;
     if (pressure) d.cuMemGetInfo_v2(&fr, &tot);
-    lk.lock();
+    relock(lk);
     in.rc = rc;
     if (rc == CUDA_SUCCESS) { side_[row].retries = 0; commit_load_locked(in); }
     else {
@@ -1214,7 +1230,7 @@ bool SwapEngine::step_zombies(Lock &lk) {
     for (uint32_t r : ready_rows) ranges.emplace_back(rows_[r].base, side_[r].mapped);
     lk.unlock();
     unmap_batch(ranges);
-    lk.lock();
+    relock(lk);
     for (uint32_t r : ready_rows) {
         Side &s = side_[r];
         pool_phys(s.mapped, s.handle);
@@ -1235,6 +1251,7 @@ bool SwapEngine::step_reap(Lock &lk) {
     const DriverTable &d = drv();
     if (evicting_.empty()) return false;
     std::vector<uint32_t> done;
+    uint64_t t_poll = mono_ns();
     for (auto it = evicting_.begin(); it != evicting_.end();) {
         Side &s = side_[*it];
         if (s.phase != PH_EVICTING) { it = evicting_.erase(it); continue; }
@@ -1243,12 +1260,13 @@ bool SwapEngine::step_reap(Lock &lk) {
         it = evicting_.erase(it);
         if (done.size() >= 4u * cfg_.batch_rows) break;
     }
+    pst_.pager_poll_ns += mono_ns() - t_poll;
     if (done.empty()) return false;
     std::vector<std::pair<CUdeviceptr, size_t>> ranges;
     for (uint32_t r : done) ranges.emplace_back(rows_[r].base, side_[r].mapped);
     lk.unlock();
     unmap_batch(ranges);
-    lk.lock();
+    relock(lk);
     for (uint32_t r : done) {
         Side &s = side_[r];
         pool_phys(s.mapped, s.handle);
@@ -1360,6 +1378,13 @@ bool SwapEngine::step_evict_ahead(Lock &lk) {
     uint64_t wanted = queued_prefetch_bytes_;
     for (const QEntry &e : demand_q_)
         if ((size_t)e.row < side_.size() && side_[e.row].gen == e.gen && side_[e.row].phase == PH_QUEUED && side_[e.row].demand) wanted += side_[e.row].mapped;
+    // While the prefetch pipeline runs, keep some physical memory free AHEAD of the page-in queue: a page-in can then be
+    // mapped and put on the wire the moment it is wished for, instead of one eviction + one unmap later — the H2D queue
+    // stays as deep as the D2H queue, and a slow VMM call stalls neither.
+    if (queued_prefetch_bytes_ + prefetched_bytes_ > 0) {
+        uint64_t window = std::min<uint64_t>(cfg_.prefetch_bytes, cfg_.resident_cap / 4);
+        wanted += cfg_.headroom_bytes == ~0ull ? window / 2 : std::min<uint64_t>(cfg_.headroom_bytes, cfg_.resident_cap / 8);
+    }
     if (resident_mapped_ + wanted <= cfg_.resident_cap) return false;
     uint64_t shortage = resident_mapped_ + wanted - cfg_.resident_cap;
     std::vector<uint32_t> victims;
@@ -1417,16 +1442,18 @@ void SwapEngine::pager_main() {
         if (stop_) break;
         uint64_t t0 = mono_ns();
         bool progress = false;
-        progress |= step_zombies(lk);
-        progress |= step_reap(lk);
-        progress |= step_demand(lk);
-        progress |= step_prefetch(lk);
-        progress |= step_evict_ahead(lk);
-        if (progress) { pst_.pager_busy_ns += mono_ns() - t0; continue; }
+        uint64_t ts = t0, te;
+        bool p0 = step_zombies(lk);     te = mono_ns(); if (p0) pst_.pager_step_ns[0] += te - ts; ts = te;
+        bool p1 = step_reap(lk);        te = mono_ns(); if (p1) pst_.pager_step_ns[1] += te - ts; ts = te;
+        bool p2 = step_demand(lk);      te = mono_ns(); if (p2) pst_.pager_step_ns[2] += te - ts; ts = te;
+        bool p3 = step_prefetch(lk);    te = mono_ns(); if (p3) pst_.pager_step_ns[3] += te - ts; ts = te;
+        bool p4 = step_evict_ahead(lk); te = mono_ns(); if (p4) pst_.pager_step_ns[4] += te - ts;
+        progress = p0 || p1 || p2 || p3 || p4;
+        if (progress) { pst_.pager_busy_ns += te - t0; continue; }
         bool outstanding = !evicting_.empty() || !zombies_.empty() || !demand_q_.empty();
         if (!outstanding) {
             // idle: fold the profiling samples in while nobody waits for the link
-            if (!prof_.empty() || span_read_ < span_next_) { lk.unlock(); harvest_prof(false); lk.lock(); }
+            if (!prof_.empty() || span_read_ < span_next_) { lk.unlock(); harvest_prof(false); relock(lk); }
             flush_pager_stats_locked();
             pager_idle_ = true;
             cv_admit_.notify_all();

@@ -58,10 +58,12 @@ struct SwapConfig {
     size_t slab_bytes = 1ull << 30;       // pinned pool growth unit
     uint64_t arena_bytes = 1ull << 40;    // virtual address arena
     bool profile = false;                 // bracket pack/unpack launches with events + in-kernel spans (bench roofline pass)
-    uint32_t scan_lookahead = 8;          // a scan selects this many times the bytes needed; the surplus is consumed by later evictions
+    uint32_t scan_lookahead = 16;         // a scan selects this many times the bytes needed; the surplus is consumed by later evictions
     uint64_t prefetch_bytes = 512ull << 20;   // VGPU_SWAP_PREFETCH_MB: how far the pager runs ahead of the application (0 = no prefetch)
     size_t copy_bytes = 16u << 20;        // VGPU_SWAP_COPY_MB: piece size of the direct copies (VMM calls wait for the copy in flight)
-    uint32_t batch_rows = 8;              // rows per pager batch (one cuMemSetAccess / cuMemUnmap per run of adjacent ranges)
+    uint32_t batch_rows = 2;              // rows per pager batch (VMM cost is per mapping, not per call: small batches keep latency low)
+    uint64_t headroom_bytes = ~0ull;      // VGPU_SWAP_HEADROOM_MB: free physical memory the pager keeps ahead of the page-in queue while
+                                          // the prefetch pipeline runs (~0 = half the prefetch window)
     bool host_backed = false;             // VGPU_SWAP_HOST_BACKED=1: an evicted range is re-mapped onto its host copy (VMM host
                                           // memory) instead of being left unmapped, so an access the hook could not see is slow, not fatal
     static SwapConfig from_env(uint64_t resident_cap, uint64_t virtual_cap);
@@ -84,6 +86,8 @@ struct SwapStats {
     // staging-ring back-pressure
     uint64_t pager_vmm_ns = 0, pager_scan_ns = 0, pager_packsync_ns = 0, pager_ring_ns = 0, pager_busy_ns = 0;
     uint64_t vmm_calls = 0;                // cuMemUnmap + cuMemSetAccess calls issued (after batching)
+    uint64_t pager_unmap_ns = 0, pager_setaccess_ns = 0, pager_map_ns = 0, pager_create_ns = 0;   // breakdown of pager_vmm_ns (diagnostics)
+    uint64_t pager_issue_ns = 0, pager_poll_ns = 0, pager_lock_ns = 0, pager_step_ns[5] = {0, 0, 0, 0, 0};   // copy/event enqueue calls; busy time per step (zombies, reap, demand, prefetch, evict-ahead)
     uint64_t pack_bytes = 0, unpack_bytes = 0;       // bytes moved by the staged path's kernels
     uint64_t direct_out_bytes = 0, direct_in_bytes = 0;   // bytes moved by the direct path (subset of page_out/in_bytes)
     uint64_t prefetch_issued = 0, prefetch_hits = 0, prefetch_wasted = 0;   // rows paged in ahead / touched afterwards / evicted untouched
@@ -128,6 +132,7 @@ class SwapEngine {
     // changes them; nullptr = do not publish
     void set_shared_record(vgpu_swap_record_t *rec) { std::lock_guard<std::mutex> g(mu_); shared_ = rec; publish_locked(); }
     CUresult drain();                          // wait for the pager and all side-stream work (tests / shutdown)
+    void stop_pager();                         // process exit: no driver call may be in flight when the driver deinitialises
     const SwapConfig &config() const { return cfg_; }
     // device memory the engine itself holds next to the application's resident buffers: both staging rings (the table,
     // scan scratch and span words are a few hundred KiB and not counted). The hook takes it out of the room it gives
@@ -218,6 +223,7 @@ class SwapEngine {
     void trim_phys_pool(uint64_t need);
     int64_t free_phys_locked() const { return (int64_t)cfg_.resident_cap - (int64_t)resident_mapped_ - (int64_t)evicting_mapped_; }
     void flush_pager_stats_locked();
+    void relock(Lock &lk);
     void collect_waits_locked(int row, std::vector<CUevent> *out);
 
     // ---- staged path pieces (pager thread)
@@ -307,6 +313,7 @@ class SwapEngine {
     CUdeviceptr d_tbl_ = 0;
     uint32_t tbl_cap_ = 0;
     VgpuEntry *h_tbl_stage_ = nullptr;              // pinned upload buffer
+    CUdeviceptr dh_tbl_stage_ = 0;                  // ... and its device view (the upload is done by a kernel)
     // independent queues: a pack never waits behind an unpack that is itself waiting for its H2D, and a victim
     // scan never waits behind either
     CUstream s_scan_ = nullptr, s_pack_ = nullptr, s_unpack_ = nullptr, s_out_ = nullptr, s_in_ = nullptr;

@@ -131,7 +131,7 @@ CUresult fx_event_elapsed(float *ms, CUevent a, CUevent b) { *ms = (float)((doub
 CUresult fx_event_destroy(CUevent e) { free(e); return CUDA_SUCCESS; }
 
 /* ------------------------------------------------------------------ functions by name */
-enum { K_OTHER, K_PACK, K_VINIT, K_VHIST, K_VCOUNT, K_VEMIT, K_VSMALL, K_STAMP, K_FILL, K_TOUCH, K_VERIFY, K_EMPTY };
+enum { K_OTHER, K_PACK, K_VINIT, K_VHIST, K_VCOUNT, K_VEMIT, K_VSMALL, K_STAMP, K_FILL, K_TOUCH, K_VERIFY, K_EMPTY, K_COPY16 };
 typedef struct { const char *name; int kind; int nparam; size_t psize[8]; } fx_func;
 static fx_func g_funcs[] = {
     {"vgpu_pack_tma", K_PACK, 1, {sizeof(VgpuPackParams)}}, {"vgpu_pack_generic", K_PACK, 1, {sizeof(VgpuPackParams)}},
@@ -139,7 +139,7 @@ static fx_func g_funcs[] = {
     {"vgpu_victim_count", K_VCOUNT, 5, {8, 4, 8, 4, 4}}, {"vgpu_victim_emit", K_VEMIT, 7, {8, 4, 8, 4, 4, 8, 4}},
     {"vgpu_victim_small", K_VSMALL, 8, {8, 4, 8, 8, 4, 4, 8, 4}}, {"vgpu_stamp", K_STAMP, 1, {8}},
     {"vgpu_wl_fill", K_FILL, 3, {8, 8, 8}}, {"vgpu_wl_touch", K_TOUCH, 2, {8, 8}}, {"vgpu_wl_verify", K_VERIFY, 5, {8, 8, 8, 8, 8}},
-    {"vgpu_wl_empty", K_EMPTY, 0, {0}}, {"vgpu_empty", K_EMPTY, 0, {0}},
+    {"vgpu_wl_empty", K_EMPTY, 0, {0}}, {"vgpu_empty", K_EMPTY, 0, {0}}, {"vgpu_copy16", K_COPY16, 3, {8, 8, 8}},
 };
 static fx_func g_other = {"?", K_OTHER, 0, {0}};
 CUresult fx_get_function(CUfunction *f, const char *name) {
@@ -214,6 +214,7 @@ CUresult fx_launch(CUfunction f, void **params) {
         victim_select(ARG(const VgpuEntry *, 0), ARG(uint32_t, 1), st, st->need, ARG(uint32_t *, 5), ARG(uint32_t, 6)); break; }
     case K_VSMALL: victim_select(ARG(const VgpuEntry *, 0), ARG(uint32_t, 1), ARG(VgpuScanState *, 2), ARG(uint64_t, 3), ARG(uint32_t *, 6), ARG(uint32_t, 7)); break;
     case K_STAMP: *ARG(volatile uint64_t *, 0) = now_ns(); break;
+    case K_COPY16: memmove(ARG(void *, 0), ARG(const void *, 1), (size_t)ARG(uint64_t, 2) * 16); break;
     case K_FILL: { uint64_t *b = ARG(uint64_t *, 0), n = ARG(uint64_t, 1), bi = ARG(uint64_t, 2); for (uint64_t j = 0; j < n; j++) b[j] = splitmix64((bi << 32) + j); break; }
     case K_TOUCH: { uint64_t *b = ARG(uint64_t *, 0), n = ARG(uint64_t, 1); for (uint64_t j = 0; j < n; j++) b[j] += 1; break; }
     case K_VERIFY: { const uint64_t *b = ARG(const uint64_t *, 0); uint64_t n = ARG(uint64_t, 1), bi = ARG(uint64_t, 2), add = ARG(uint64_t, 3);
