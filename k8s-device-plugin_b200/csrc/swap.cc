@@ -26,6 +26,7 @@ namespace vgpu {
         }                                                                                \
     } while (0)
 
+static uint64_t g_dbg_ns[8];
 static uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 static uint64_t mono_ns() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec; }
 struct ScopedNs { uint64_t *acc; uint64_t t0; explicit ScopedNs(uint64_t *a) : acc(a), t0(mono_ns()) {} ~ScopedNs() { *acc += mono_ns() - t0; } };
@@ -135,6 +136,8 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
     dev_ = dev;
     cfg_ = cfg;
     profile_.store(cfg.profile);
+    trace_want_ = (uint32_t)env_u64("VGPU_SWAP_TRACE", 0);
+    trace_skip_ = (uint32_t)env_u64("VGPU_SWAP_TRACE_SKIP", 1200);
     k_ = kernels_for_current_ctx();
     if (!k_) return false;
     numa_node_ = std::getenv("VGPU_SWAP_NO_NUMA") ? -1 : gpu_numa_node(dev);
@@ -175,7 +178,7 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
     int prio_lo = 0, prio_hi = 0;
     if (d.cuCtxGetStreamPriorityRange) d.cuCtxGetStreamPriorityRange(&prio_lo, &prio_hi);
     for (CUstream *s : {&s_scan_, &s_pack_, &s_unpack_, &s_out_, &s_in_}) {
-        CUresult sr = d.cuStreamCreateWithPriority ? d.cuStreamCreateWithPriority(s, CU_STREAM_NON_BLOCKING, prio_hi)
+        CUresult sr = (d.cuStreamCreateWithPriority && env_u64("VGPU_SWAP_STREAM_PRIO", 1)) ? d.cuStreamCreateWithPriority(s, CU_STREAM_NON_BLOCKING, prio_hi)
                                                    : d.cuStreamCreate(s, CU_STREAM_NON_BLOCKING);
         if (sr != CUDA_SUCCESS) { LOG_ERROR("side stream creation failed"); return false; }
     }
@@ -208,10 +211,14 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
 
 void SwapEngine::stop_pager() {
     if (!pager_.joinable()) return;
+    if (std::getenv("VGPU_PRINT_STATS")) std::fprintf(stderr, "[vgpu-b200 dbg] evict begin=%.1f ms, evict body=%.1f ms, choose=%.1f ms over %lu calls; get_event=%.1f loop=%.1f relock=%.1f commit=%.1f\n", g_dbg_ns[0] / 1e6, g_dbg_ns[1] / 1e6, g_dbg_ns[2] / 1e6, (unsigned long)g_dbg_ns[3], g_dbg_ns[4] / 1e6, g_dbg_ns[5] / 1e6, g_dbg_ns[6] / 1e6, g_dbg_ns[7] / 1e6);
     { std::lock_guard<std::mutex> g(mu_); drop_prefetch_queue_locked(); stop_ = true; kick_ = true; }
     cv_pager_.notify_all();
     cv_admit_.notify_all();
     pager_.join();
+    { std::lock_guard<std::mutex> g(host_mu_); grow_stop_ = true; }
+    host_cv_.notify_all();
+    if (grower_.joinable()) grower_.join();
 }
 
 SwapEngine::~SwapEngine() {
@@ -232,7 +239,6 @@ SwapEngine::~SwapEngine() {
     for (auto &s : ring_in_) { if (s.buf) d.cuMemFree_v2(s.buf); if (s.busy) d.cuEventDestroy_v2(s.busy); }
     for (auto &sl : slabs_) if (sl.host) d.cuMemFreeHost(sl.host);
     for (auto &e : use_ring_) if (e) d.cuEventDestroy_v2(e);
-    for (auto &e : ready_free_) d.cuEventDestroy_v2(e);
     for (auto &e : ev_pool_) d.cuEventDestroy_v2(e);
     for (auto &p : prof_) { d.cuEventDestroy_v2(p.a); d.cuEventDestroy_v2(p.b); }
     if (d_span_) d.cuMemFree_v2(d_span_);
@@ -269,46 +275,100 @@ static void map_free(std::map<uint64_t, uint64_t> &fl, uint64_t off, uint64_t by
 bool SwapEngine::va_alloc(size_t bytes, uint64_t *off) { return map_alloc(va_free_, bytes, off); }
 void SwapEngine::va_free(uint64_t off, size_t bytes) { map_free(va_free_, off, bytes); }
 
-// pinned pool: global offset = slab_index << 44 | offset-in-slab. Called by the pager (page-out) and, for releases, by
-// application threads (free of a paged-out buffer): own leaf mutex.
-bool SwapEngine::host_alloc(size_t bytes, uint64_t *off) {
+// Pins one slab (on the GPU's NUMA node) WITHOUT holding host_mu_: a 1 GiB cuMemHostAlloc takes 50-150 ms.
+bool SwapEngine::pin_slab(size_t sb, Slab *out, bool *local) {
     const DriverTable &d = drv();
-    bytes = round_up(bytes, 256);
-    std::lock_guard<std::mutex> g(host_mu_);
-    for (size_t i = 0; i < slabs_.size(); i++) {
-        uint64_t o;
-        if (map_alloc(slabs_[i].free, bytes, &o)) {
-            *off = ((uint64_t)i << 44) | o;
-            host_used_ += bytes;
-            return true;
-        }
-    }
-    size_t sb = std::max<size_t>(cfg_.slab_bytes, bytes);
-    uint64_t have = 0;
-    for (auto &s : slabs_) have += s.bytes;
-    if (cfg_.host_pool_cap && have + sb > cfg_.host_pool_cap) {
-        if (have + bytes > cfg_.host_pool_cap) return false;
-        sb = bytes;
-    }
-    Slab s;
     CUresult r;
     {
         NodeAffinity on_node(numa_node_);
         if (numa_node_ >= 0) prefer_node(numa_node_);
-        r = d.cuMemHostAlloc((void **)&s.host, sb, CU_MEMHOSTALLOC_PORTABLE);
+        r = d.cuMemHostAlloc((void **)&out->host, sb, CU_MEMHOSTALLOC_PORTABLE);
         if (numa_node_ >= 0) default_policy();
     }
     if (r != CUDA_SUCCESS) { LOG_ERROR("pinned slab of %zu MiB failed: %d %s", sb >> 20, (int)r, cu_err(r)); return false; }
-    pst_.host_slabs++;
+    *local = false;
     if (numa_node_ >= 0) {
-        int got = node_of(s.host + sb / 2);
-        if (got == numa_node_) pst_.host_slabs_local++;
-        else LOG_WARN("pinned slab landed on NUMA node %d, GPU is on node %d: page traffic will cross the socket link", got, numa_node_);
+        int got = node_of(out->host + sb / 2);
+        *local = got == numa_node_;
+        if (!*local) LOG_WARN("pinned slab landed on NUMA node %d, GPU is on node %d: page traffic will cross the socket link", got, numa_node_);
     }
-    s.bytes = sb;
-    if (sb > bytes) s.free[bytes] = sb - bytes;
+    out->bytes = sb;
+    out->free.clear();
+    out->free[0] = sb;
+    return true;
+}
+
+// Every live row will need a pinned block sooner or later (a block stays with its row, so that a clean row is evicted
+// without a copy): the pool is grown TOWARDS the live bytes by a helper thread as soon as they are allocated, so that the
+// pinning happens while the application populates its buffers and not, slab by slab, inside the pager's evictions.
+void SwapEngine::grow_main() {
+    drv().cuCtxSetCurrent(ctx_);
+    for (;;) {
+        size_t sb;
+        {
+            std::lock_guard<std::mutex> g(host_mu_);
+            uint64_t want = host_want_.load();
+            if (grow_stop_ || host_total_ >= want) { growing_ = false; host_cv_.notify_all(); return; }
+            sb = cfg_.slab_bytes;
+            if (cfg_.host_pool_cap && host_total_ + sb > cfg_.host_pool_cap) {
+                if (host_total_ >= cfg_.host_pool_cap) { growing_ = false; host_cv_.notify_all(); return; }
+                sb = cfg_.host_pool_cap - host_total_;
+            }
+        }
+        Slab s;
+        bool local = false;
+        bool ok = pin_slab(sb, &s, &local);
+        std::lock_guard<std::mutex> g(host_mu_);
+        if (!ok) { growing_ = false; host_cv_.notify_all(); return; }
+        host_total_ += sb;
+        host_slabs_++; if (local) host_slabs_local_++;
+        slabs_.push_back(std::move(s));
+        host_cv_.notify_all();
+    }
+}
+void SwapEngine::want_host_pool(uint64_t live_bytes) {
+    host_want_.store(live_bytes);
+    std::lock_guard<std::mutex> g(host_mu_);
+    if (growing_ || grow_stop_ || host_total_ >= live_bytes) return;
+    if (cfg_.host_pool_cap && host_total_ >= cfg_.host_pool_cap) return;
+    if (grower_.joinable()) grower_.join();
+    growing_ = true;
+    grower_ = std::thread([this] { grow_main(); });
+}
+
+// pinned pool: global offset = slab_index << 44 | offset-in-slab. Called by the pager (page-out) and, for releases, by
+// application threads (free of a paged-out buffer): own leaf mutex.
+bool SwapEngine::host_alloc(size_t bytes, uint64_t *off) {
+    bytes = round_up(bytes, 256);
+    std::unique_lock<std::mutex> g(host_mu_);
+    for (;;) {
+        for (size_t i = 0; i < slabs_.size(); i++) {
+            uint64_t o;
+            if (map_alloc(slabs_[i].free, bytes, &o)) {
+                *off = ((uint64_t)i << 44) | o;
+                host_used_ += bytes;
+                return true;
+            }
+        }
+        if (growing_ && bytes <= cfg_.slab_bytes) { host_cv_.wait(g); continue; }   // a slab is on its way
+        break;
+    }
+    size_t sb = std::max<size_t>(cfg_.slab_bytes, bytes);
+    if (cfg_.host_pool_cap && host_total_ + sb > cfg_.host_pool_cap) {
+        if (host_total_ + bytes > cfg_.host_pool_cap) return false;
+        sb = bytes;
+    }
+    g.unlock();
+    Slab s;
+    bool local = false;
+    if (!pin_slab(sb, &s, &local)) return false;
+    g.lock();
+    host_total_ += sb;
+    host_slabs_++; if (local) host_slabs_local_++;
+    uint64_t o = 0;
+    map_alloc(s.free, bytes, &o);
     slabs_.push_back(std::move(s));
-    *off = ((uint64_t)(slabs_.size() - 1) << 44);
+    *off = ((uint64_t)(slabs_.size() - 1) << 44) | o;
     host_used_ += bytes;
     return true;
 }
@@ -423,10 +483,10 @@ void SwapEngine::retire_row_locked(int row) {
     va_free(s.va_off, s.mapped);
     uint32_t gen = s.gen + 1;
     CUevent keep_done = s.evict_done;
-    if (s.ready) ready_free_.push_back(s.ready);
+    if (s.ready) put_event(s.ready);
     s = Side{};
     s.gen = gen;
-    if (keep_done) ready_free_.push_back(keep_done);
+    if (keep_done) put_event(keep_done);
     rows_[row] = VgpuEntry{};
     succ_[row] = -1;
     mark_dirty(row);
@@ -439,13 +499,19 @@ CUevent SwapEngine::use_event(uint64_t seq) {
     if (seq + use_ring_.size() <= use_seq_) return nullptr;  // slot was recycled: that use is known complete (note_use)
     return use_ring_[seq % use_ring_.size()];
 }
+// ONE pool of (timing-disabled) events for page-in completions, eviction completions and pack markers, shared by the
+// pager and the application threads behind its own leaf mutex: cuEventCreate takes the same driver lock the VMM calls
+// stall on, so events are recycled, never created in steady state.
 CUevent SwapEngine::get_event() {
-    if (!ev_pool_.empty()) { CUevent e = ev_pool_.back(); ev_pool_.pop_back(); return e; }
+    {
+        std::lock_guard<std::mutex> g(ev_mu_);
+        if (!ev_pool_.empty()) { CUevent e = ev_pool_.back(); ev_pool_.pop_back(); return e; }
+    }
     CUevent e = nullptr;
     if (drv().cuEventCreate(&e, CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) return nullptr;
     return e;
 }
-void SwapEngine::put_event(CUevent e) { if (e) ev_pool_.push_back(e); }
+void SwapEngine::put_event(CUevent e) { if (e) { std::lock_guard<std::mutex> g(ev_mu_); ev_pool_.push_back(e); } }
 
 SwapEngine::Slot &SwapEngine::acquire_slot(std::vector<Slot> &ring, int *cursor) {
     Slot &s = ring[*cursor];
@@ -520,15 +586,38 @@ void SwapEngine::harvest_prof(bool wait) {
 }
 void SwapEngine::set_profile(bool on) { profile_.store(on); }
 
+bool SwapEngine::trace_begin(int dir, int row, CUstream s) {
+    if (!trace_want_ || trace_.size() >= 2u * trace_want_) return false;
+    if (trace_skip_) { trace_skip_--; return false; }
+    const DriverTable &d = drv();
+    if (!trace_base_) { d.cuEventCreate(&trace_base_, CU_EVENT_DEFAULT); d.cuEventRecord(trace_base_, s); d.cuEventSynchronize(trace_base_); trace_base_ns_ = mono_ns(); trace_.reserve(2u * trace_want_); }
+    TraceRec r{dir, row, mono_ns(), nullptr, nullptr};
+    d.cuEventCreate(&r.a, CU_EVENT_DEFAULT); d.cuEventCreate(&r.b, CU_EVENT_DEFAULT);
+    d.cuEventRecord(r.a, s);
+    trace_.push_back(r);
+    return true;
+}
+void SwapEngine::trace_end(CUstream s) { drv().cuEventRecord(trace_.back().b, s); }
+void SwapEngine::dump_trace(FILE *f) {
+    const DriverTable &d = drv();
+    if (trace_.empty()) return;
+    for (const TraceRec &r : trace_) {
+        float a = 0, b = 0;
+        d.cuEventSynchronize(r.b);
+        d.cuEventElapsedTime(&a, trace_base_, r.a); d.cuEventElapsedTime(&b, trace_base_, r.b);
+        std::fprintf(f, "[vgpu-b200 trace] %s row %d issued %.0f us, ran %.0f..%.0f us (%.0f)\n", r.dir ? "H2D" : "D2H", r.row, (double)(r.host_ns - trace_base_ns_) / 1e3, a * 1e3, b * 1e3, (b - a) * 1e3);
+    }
+}
+
 void SwapEngine::flush_pager_stats_locked() {
     SwapStats &p = pst_;
     st_.page_out_bytes += p.page_out_bytes; st_.page_in_bytes += p.page_in_bytes; st_.evictions += p.evictions;
     st_.pack_launches += p.pack_launches; st_.unpack_launches += p.unpack_launches; st_.scan_launches += p.scan_launches;
     st_.scans += p.scans; st_.scan_cache_hits += p.scan_cache_hits; st_.phys_creates += p.phys_creates; st_.phys_reuses += p.phys_reuses;
-    st_.host_slabs += p.host_slabs; st_.host_slabs_local += p.host_slabs_local;
     st_.pack_ms += p.pack_ms; st_.unpack_ms += p.unpack_ms; st_.pack_span_ms += p.pack_span_ms; st_.unpack_span_ms += p.unpack_span_ms;
     st_.pager_vmm_ns += p.pager_vmm_ns; st_.pager_scan_ns += p.pager_scan_ns; st_.pager_packsync_ns += p.pager_packsync_ns;
     st_.pager_ring_ns += p.pager_ring_ns; st_.pager_busy_ns += p.pager_busy_ns; st_.vmm_calls += p.vmm_calls;
+    st_.vmm_slow_calls += p.vmm_slow_calls; st_.vmm_slow_ns += p.vmm_slow_ns; st_.vmm_max_ns = std::max(st_.vmm_max_ns, p.vmm_max_ns);
     st_.pager_issue_ns += p.pager_issue_ns; st_.pager_poll_ns += p.pager_poll_ns; st_.pager_lock_ns += p.pager_lock_ns;
     for (int i = 0; i < 5; i++) st_.pager_step_ns[i] += p.pager_step_ns[i];
     st_.pager_unmap_ns += p.pager_unmap_ns; st_.pager_setaccess_ns += p.pager_setaccess_ns; st_.pager_map_ns += p.pager_map_ns; st_.pager_create_ns += p.pager_create_ns;
@@ -585,6 +674,14 @@ CUresult SwapEngine::obtain_phys(size_t mapped, CUmemGenericAllocationHandle *h,
     return r;
 }
 
+void SwapEngine::note_vmm_call(const char *what, uint64_t ns) {
+    pst_.vmm_calls++;
+    if (ns > pst_.vmm_max_ns) pst_.vmm_max_ns = ns;
+    if (ns > 2000000ull) {
+        pst_.vmm_slow_calls++; pst_.vmm_slow_ns += ns;
+        if (trace_want_) std::fprintf(stderr, "[vgpu-b200 trace] slow %s: %.1f ms at %.0f us\n", what, ns / 1e6, trace_base_ns_ ? (double)(mono_ns() - trace_base_ns_) / 1e3 : 0.0);
+    }
+}
 static void merge_runs(std::vector<std::pair<CUdeviceptr, size_t>> &v) {
     std::sort(v.begin(), v.end());
     size_t k = 0;
@@ -606,17 +703,19 @@ void SwapEngine::unmap_batch(std::vector<std::pair<CUdeviceptr, size_t>> &ranges
         bool ok = true;
         size_t done = 0;
         for (; done < runs.size(); done++) {
-            pst_.vmm_calls++;
-            if (d.cuMemUnmap(runs[done].first, runs[done].second) != CUDA_SUCCESS) { ok = false; break; }
+            uint64_t t0 = mono_ns();
+            CUresult ur = d.cuMemUnmap(runs[done].first, runs[done].second);
+            note_vmm_call("cuMemUnmap", mono_ns() - t0);
+            if (ur != CUDA_SUCCESS) { ok = false; break; }
         }
         if (ok) return;
         // this driver wants one call per mapping: finish the rest range by range (a failed call unmapped nothing)
         unmap_runs_ok_ = false;
         CUdeviceptr from = runs[done].first;
-        for (auto &r : ranges) if (r.first >= from) { pst_.vmm_calls++; d.cuMemUnmap(r.first, r.second); }
+        for (auto &r : ranges) if (r.first >= from) { uint64_t t0 = mono_ns(); d.cuMemUnmap(r.first, r.second); note_vmm_call("cuMemUnmap", mono_ns() - t0); }
         return;
     }
-    for (auto &r : ranges) { pst_.vmm_calls++; d.cuMemUnmap(r.first, r.second); }
+    for (auto &r : ranges) { uint64_t t0 = mono_ns(); d.cuMemUnmap(r.first, r.second); note_vmm_call("cuMemUnmap", mono_ns() - t0); }
 }
 CUresult SwapEngine::set_access_batch(std::vector<std::pair<CUdeviceptr, size_t>> &ranges) {
     const DriverTable &d = drv();
@@ -630,8 +729,9 @@ CUresult SwapEngine::set_access_batch(std::vector<std::pair<CUdeviceptr, size_t>
     merge_runs(runs);
     CUresult rc = CUDA_SUCCESS;
     for (auto &r : runs) {
-        pst_.vmm_calls++;
+        uint64_t t0 = mono_ns();
         CUresult x = d.cuMemSetAccess(r.first, r.second, &acc, 1);
+        note_vmm_call("cuMemSetAccess", mono_ns() - t0);
         if (x != CUDA_SUCCESS && runs.size() != ranges.size()) {
             // fall back to one call per mapping inside this run
             for (auto &q : ranges)
@@ -679,6 +779,9 @@ void SwapEngine::schedule_prefetch() {
     if (!cfg_.prefetch_bytes || last_row_ < 0 || resident_mapped_ >= live_mapped_ || !predictor_confident()) return;
     uint64_t window = std::min<uint64_t>(cfg_.prefetch_bytes, cfg_.resident_cap / 4);
     uint64_t ahead = queued_prefetch_bytes_ + prefetched_bytes_;
+    // top the window up in halves, not row by row: rows wished for together are mapped together (one cuMemSetAccess per
+    // run of adjacent ranges) and their victims are unmapped together — VMM calls are where the driver stalls
+    if (ahead > window / 2) return;
     int cur = last_row_;
     bool queued = false;
     for (int steps = 0; steps < 64 && ahead < window; steps++) {
@@ -801,11 +904,15 @@ CUresult SwapEngine::evict_direct(Lock &lk, const std::vector<uint32_t> &victims
     const DriverTable &d = drv();
     if (victims.empty()) return CUDA_SUCCESS;
     std::vector<OutItem> items;
+    uint64_t tA = mono_ns();
     begin_evict_locked(victims, &items);
     lk.unlock();
+    g_dbg_ns[0] += mono_ns() - tA;
+    ScopedNs dbg1(&g_dbg_ns[1]);
     CUresult rc = CUDA_SUCCESS;
     for (OutItem &it : items) {
-        it.done = get_event();
+        { ScopedNs dbg4(&g_dbg_ns[4]); it.done = get_event(); }
+        ScopedNs dbg5(&g_dbg_ns[5]);
         if (it.copy && !it.has_host) {
             if (!host_alloc(it.len, &it.host_off)) {
                 relock(lk);
@@ -820,11 +927,13 @@ CUresult SwapEngine::evict_direct(Lock &lk, const std::vector<uint32_t> &victims
         for (CUevent e : it.wait) d.cuStreamWaitEvent(s, e, 0);
         if (it.copy) {
             unsigned char *hp = host_ptr(it.host_off);
+            bool tr = trace_begin(0, (int)it.row, s);
             for (uint64_t o = 0; o < it.len; o += cfg_.copy_bytes) {
                 uint64_t n = std::min<uint64_t>(cfg_.copy_bytes, it.len - o);
                 CUresult r = d.cuMemcpyDtoHAsync_v2(hp + o, it.base + o, n, s);
                 if (r != CUDA_SUCCESS) { LOG_ERROR("page-out copy failed: %d %s", (int)r, cu_err(r)); rc = r; break; }
             }
+            if (tr) trace_end(s);
             pst_.page_out_bytes += it.len;
             pst_.direct_out_bytes += it.len;
         } else {
@@ -832,7 +941,10 @@ CUresult SwapEngine::evict_direct(Lock &lk, const std::vector<uint32_t> &victims
         }
         d.cuEventRecord(it.done, s);
     }
+    uint64_t tR = mono_ns();
     relock(lk);
+    g_dbg_ns[6] += mono_ns() - tR;
+    ScopedNs dbg7(&g_dbg_ns[7]);
     for (OutItem &it : items) {
         Side &s = side_[it.row];
         if (it.failed) {
@@ -848,7 +960,7 @@ CUresult SwapEngine::evict_direct(Lock &lk, const std::vector<uint32_t> &victims
         s.host_off = it.host_off;
         s.has_host = it.has_host;
         if (it.copy) s.dirty = false;              // once the copy is done the block equals the HBM content
-        if (s.ready) { ready_free_.push_back(s.ready); s.ready = nullptr; }   // its waiters are enqueued; the record they refer to is fixed
+        if (s.ready) { put_event(s.ready); s.ready = nullptr; }   // its waiters are enqueued; the record they refer to is fixed
         if (s.evict_done) put_event(s.evict_done);
         s.evict_done = it.done;
         s.out_slot = -1;
@@ -867,7 +979,7 @@ void SwapEngine::begin_load_locked(int row, bool prefetch, InItem *it) {
     it->after = nullptr;
     s.phase = PH_LOADING;
     resident_mapped_ += s.mapped;
-    if (!ready_free_.empty()) { it->ready = ready_free_.back(); ready_free_.pop_back(); }
+    it->ready = get_event();
 }
 void SwapEngine::commit_load_locked(InItem &it) {
     Side &s = side_[it.row];
@@ -877,7 +989,7 @@ void SwapEngine::commit_load_locked(InItem &it) {
     s.fail = CUDA_SUCCESS;
     s.dirty = false;
     s.demand = false;
-    if (s.ready) ready_free_.push_back(s.ready);
+    if (s.ready) put_event(s.ready);
     s.ready = it.ready;
     rows_[it.row].state = VGPU_ST_RESIDENT | ((s.pins > 0 || s.locked) ? VGPU_ST_PINNED : 0u);
     if (it.prefetch && s.pins == 0) {
@@ -892,7 +1004,7 @@ void SwapEngine::commit_load_locked(InItem &it) {
 void SwapEngine::fail_load_locked(InItem &it, CUresult rc) {
     Side &s = side_[it.row];
     resident_mapped_ -= s.mapped;
-    if (it.ready) ready_free_.push_back(it.ready);
+    if (it.ready) put_event(it.ready);
     it.ready = nullptr;
     s.phase = PH_IDLE;
     s.fail = rc;
@@ -950,16 +1062,18 @@ CUresult SwapEngine::load_direct(Lock &lk, std::vector<InItem> &items) {
             d.cuMemUnmap(it.base, it.mapped); pool_phys(it.mapped, it.h); it.rc = arc;
             continue;
         }
-        if (!it.has_host) { if (it.ready) { ev_pool_.push_back(it.ready); it.ready = nullptr; } continue; }   // never written: nothing to load
+        if (!it.has_host) { if (it.ready) { put_event(it.ready); it.ready = nullptr; } continue; }   // never written: nothing to load
         if (!it.ready) it.ready = get_event();
         ScopedNs t_issue(&pst_.pager_issue_ns);
         if (it.after) d.cuStreamWaitEvent(s_in_, it.after, 0);
         unsigned char *hp = host_ptr(it.host_off);
+        bool tr = trace_begin(1, it.row, s_in_);
         for (uint64_t o = 0; o < it.len; o += cfg_.copy_bytes) {
             uint64_t n = std::min<uint64_t>(cfg_.copy_bytes, it.len - o);
             CUresult r = d.cuMemcpyHtoDAsync_v2(it.base + o, hp + o, n, s_in_);
             if (r != CUDA_SUCCESS) { LOG_ERROR("page-in copy failed: %d %s", (int)r, cu_err(r)); it.rc = r; break; }
         }
+        if (tr) trace_end(s_in_);
         d.cuEventRecord(it.ready, s_in_);
         pst_.page_in_bytes += it.len;
         pst_.direct_in_bytes += it.len;
@@ -1089,7 +1203,7 @@ CUresult SwapEngine::swap_staged(Lock &lk, int row, const std::vector<uint32_t> 
         in.row = row; in.base = rows_[row].base; in.len = round_up(rows_[row].size, 256); in.mapped = s.mapped;
         in.host_off = s.host_off; in.has_host = s.has_host; in.prefetch = false;
         s.phase = PH_LOADING;                      // owned by the pager from here on (accounted once the victims are gone)
-        if (!ready_free_.empty()) { in.ready = ready_free_.back(); ready_free_.pop_back(); }
+        in.ready = get_event();
     }
     int in_out_slot = side_[row].out_slot;
     uint64_t in_out_seq = side_[row].out_seq;
@@ -1142,7 +1256,7 @@ CUresult SwapEngine::swap_staged(Lock &lk, int row, const std::vector<uint32_t> 
         s.has_handle = false;
         s.host_off = it.host_off; s.has_host = it.has_host;
         if (it.copy) { s.dirty = false; s.out_slot = it.out_slot; s.out_seq = it.out_seq; }
-        if (s.ready) { ready_free_.push_back(s.ready); s.ready = nullptr; }
+        if (s.ready) { put_event(s.ready); s.ready = nullptr; }
         rows_[it.row].host_slot = (uint32_t)(s.host_off >> 12);
         evicting_mapped_ -= s.mapped;
         pst_.evictions++;
@@ -1154,7 +1268,7 @@ CUresult SwapEngine::swap_staged(Lock &lk, int row, const std::vector<uint32_t> 
         side_[row].phase = PH_IDLE;
         side_[row].fail = rc;
         side_[row].demand = false;
-        if (in.ready) ready_free_.push_back(in.ready);
+        if (in.ready) put_event(in.ready);
         flush_pager_stats_locked();
         cv_admit_.notify_all();
         return rc;
@@ -1192,7 +1306,7 @@ CUresult SwapEngine::swap_staged(Lock &lk, int row, const std::vector<uint32_t> 
             d.cuEventRecord(j.slot->busy, s_unpack_);
         }
         if (rc == CUDA_SUCCESS) d.cuEventRecord(in.ready, s_unpack_);
-    } else if (rc == CUDA_SUCCESS && in.ready) { ev_pool_.push_back(in.ready); in.ready = nullptr; }
+    } else if (rc == CUDA_SUCCESS && in.ready) { put_event(in.ready); in.ready = nullptr; }
     size_t fr = 0, tot = 0;
     if (pressure) d.cuMemGetInfo_v2(&fr, &tot);
     relock(lk);
@@ -1262,6 +1376,15 @@ bool SwapEngine::step_reap(Lock &lk) {
     }
     pst_.pager_poll_ns += mono_ns() - t_poll;
     if (done.empty()) return false;
+    // Unmap in batches (adjacent victims go in one call) unless somebody is waiting for the memory: the evictions were
+    // issued ahead of need, so their frames are not urgent, and fewer VMM calls means fewer chances to stall in the driver.
+    bool urgent = !demand_q_.empty() || (!prefetch_q_.empty() && free_phys_locked() <= 0) || stop_;
+    if (!urgent && done.size() < cfg_.batch_rows && !evicting_.empty() && reap_defer_ < 64) {
+        reap_defer_++;
+        for (auto it = done.rbegin(); it != done.rend(); ++it) evicting_.push_front(*it);
+        return false;
+    }
+    reap_defer_ = 0;
     std::vector<std::pair<CUdeviceptr, size_t>> ranges;
     for (uint32_t r : done) ranges.emplace_back(rows_[r].base, side_[r].mapped);
     lk.unlock();
@@ -1383,13 +1506,16 @@ bool SwapEngine::step_evict_ahead(Lock &lk) {
     // stays as deep as the D2H queue, and a slow VMM call stalls neither.
     if (queued_prefetch_bytes_ + prefetched_bytes_ > 0) {
         uint64_t window = std::min<uint64_t>(cfg_.prefetch_bytes, cfg_.resident_cap / 4);
-        wanted += cfg_.headroom_bytes == ~0ull ? window / 2 : std::min<uint64_t>(cfg_.headroom_bytes, cfg_.resident_cap / 8);
+        wanted += cfg_.headroom_bytes == ~0ull ? window : std::min<uint64_t>(cfg_.headroom_bytes, cfg_.resident_cap / 4);
     }
     if (resident_mapped_ + wanted <= cfg_.resident_cap) return false;
     uint64_t shortage = resident_mapped_ + wanted - cfg_.resident_cap;
     std::vector<uint32_t> victims;
     uint64_t evictable = 0;
-    if (choose_victims(lk, shortage, &victims, &evictable) != CUDA_SUCCESS || victims.empty()) {
+    uint64_t tC = mono_ns();
+    CUresult crc = choose_victims(lk, shortage, &victims, &evictable);
+    g_dbg_ns[2] += mono_ns() - tC; g_dbg_ns[3]++;
+    if (crc != CUDA_SUCCESS || victims.empty()) {
         // nothing can be evicted (everything resident is in use): wishes are dropped, demands keep waiting for a release
         bool had = !prefetch_q_.empty();
         drop_prefetch_queue_locked();
@@ -1438,8 +1564,14 @@ void SwapEngine::pager_main() {
     const DriverTable &d = drv();
     d.cuCtxSetCurrent(ctx_);
     Lock lk(mu_);
+    const auto poll = std::chrono::microseconds(env_u64("VGPU_SWAP_POLL_US", 40));
+    bool trace_dumped = false;
     for (;;) {
         if (stop_) break;
+        if (trace_want_ && !trace_dumped && trace_.size() >= 2u * trace_want_) {   // the driver is gone by the time atexit handlers run
+            trace_dumped = true;
+            lk.unlock(); dump_trace(stderr); lk.lock();
+        }
         uint64_t t0 = mono_ns();
         bool progress = false;
         uint64_t ts = t0, te;
@@ -1462,7 +1594,7 @@ void SwapEngine::pager_main() {
             pager_idle_ = false;
         } else {
             // GPU work outstanding (copies to reap, users to wait for): poll at a period far below one transfer
-            cv_pager_.wait_for(lk, std::chrono::microseconds(40));
+            cv_pager_.wait_for(lk, poll);
         }
     }
     flush_pager_stats_locked();
@@ -1527,8 +1659,13 @@ CUresult SwapEngine::alloc(CUdeviceptr *dptr, size_t bytes) {
     mark_dirty(row);
     live_bytes_ += bytes;
     live_mapped_ += mapped;
+    host_need_ += round_up(bytes, 256);
+    uint64_t need_now = host_need_;
     *dptr = arena_ + off;
     publish_locked();
+    lk.unlock();
+    // only what cannot stay resident will ever be paged out: grow the pinned pool once the live bytes pass the cap
+    if (need_now > cfg_.resident_cap) want_host_pool(need_now);
     return CUDA_SUCCESS;
 }
 
@@ -1549,6 +1686,8 @@ CUresult SwapEngine::free(CUdeviceptr dptr) {
     for (uint64_t gidx = s.va_off / gran_; gidx < (s.va_off + s.mapped) / gran_; gidx++) owner_[gidx] = -1;
     live_bytes_ -= rows_[row].size;
     live_mapped_ -= s.mapped;
+    host_need_ -= std::min<uint64_t>(host_need_, round_up(rows_[row].size, 256));
+    host_want_.store(host_need_);
     s.pins = 0;                                  // rows pinned for a stream capture are never unpinned by note_use
     s.locked = false;
     if (last_row_ == row) last_row_ = -1;
@@ -1669,7 +1808,7 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
         Side &s = side_[rows[i]];
         if (!s.ready) continue;
         if (stream == kHostWait) { host_wait.push_back(s.ready); continue; }
-        if (d.cuEventQuery(s.ready) == CUDA_SUCCESS) { ready_free_.push_back(s.ready); s.ready = nullptr; }
+        if (d.cuEventQuery(s.ready) == CUDA_SUCCESS) { put_event(s.ready); s.ready = nullptr; }
         else d.cuStreamWaitEvent(stream, s.ready, 0);
     }
     if (!missing.empty()) publish_locked();
@@ -1784,6 +1923,7 @@ SwapStats SwapEngine::stats() {
     s.resident_bytes = resident_mapped_ + evicting_mapped_;
     s.live_bytes = live_bytes_.load();
     s.host_bytes = host_used_.load();
+    { std::lock_guard<std::mutex> h(host_mu_); s.host_slabs = host_slabs_; s.host_slabs_local = host_slabs_local_; }
     s.entries = rows_.size() - free_rows_.size() - zombies_.size();
     return s;
 }

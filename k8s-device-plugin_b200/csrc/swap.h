@@ -61,9 +61,9 @@ struct SwapConfig {
     uint32_t scan_lookahead = 16;         // a scan selects this many times the bytes needed; the surplus is consumed by later evictions
     uint64_t prefetch_bytes = 512ull << 20;   // VGPU_SWAP_PREFETCH_MB: how far the pager runs ahead of the application (0 = no prefetch)
     size_t copy_bytes = 16u << 20;        // VGPU_SWAP_COPY_MB: piece size of the direct copies (VMM calls wait for the copy in flight)
-    uint32_t batch_rows = 2;              // rows per pager batch (VMM cost is per mapping, not per call: small batches keep latency low)
+    uint32_t batch_rows = 4;              // rows per pager batch (VMM cost is per mapping, not per call: small batches keep latency low)
     uint64_t headroom_bytes = ~0ull;      // VGPU_SWAP_HEADROOM_MB: free physical memory the pager keeps ahead of the page-in queue while
-                                          // the prefetch pipeline runs (~0 = half the prefetch window)
+                                          // the prefetch pipeline runs (~0 = as much as the prefetch window)
     bool host_backed = false;             // VGPU_SWAP_HOST_BACKED=1: an evicted range is re-mapped onto its host copy (VMM host
                                           // memory) instead of being left unmapped, so an access the hook could not see is slow, not fatal
     static SwapConfig from_env(uint64_t resident_cap, uint64_t virtual_cap);
@@ -87,6 +87,7 @@ struct SwapStats {
     uint64_t pager_vmm_ns = 0, pager_scan_ns = 0, pager_packsync_ns = 0, pager_ring_ns = 0, pager_busy_ns = 0;
     uint64_t vmm_calls = 0;                // cuMemUnmap + cuMemSetAccess calls issued (after batching)
     uint64_t pager_unmap_ns = 0, pager_setaccess_ns = 0, pager_map_ns = 0, pager_create_ns = 0;   // breakdown of pager_vmm_ns (diagnostics)
+    uint64_t vmm_slow_calls = 0, vmm_slow_ns = 0, vmm_max_ns = 0;   // VMM calls that took > 2 ms (driver stalls), their time, the worst one
     uint64_t pager_issue_ns = 0, pager_poll_ns = 0, pager_lock_ns = 0, pager_step_ns[5] = {0, 0, 0, 0, 0};   // copy/event enqueue calls; busy time per step (zombies, reap, demand, prefetch, evict-ahead)
     uint64_t pack_bytes = 0, unpack_bytes = 0;       // bytes moved by the staged path's kernels
     uint64_t direct_out_bytes = 0, direct_in_bytes = 0;   // bytes moved by the direct path (subset of page_out/in_bytes)
@@ -132,6 +133,7 @@ class SwapEngine {
     // changes them; nullptr = do not publish
     void set_shared_record(vgpu_swap_record_t *rec) { std::lock_guard<std::mutex> g(mu_); shared_ = rec; publish_locked(); }
     CUresult drain();                          // wait for the pager and all side-stream work (tests / shutdown)
+    void dump_trace(FILE *f);                  // VGPU_SWAP_TRACE=n: device-side start/end times of the first n direct copies per direction after warm-up
     void stop_pager();                         // process exit: no driver call may be in flight when the driver deinitialises
     const SwapConfig &config() const { return cfg_; }
     // device memory the engine itself holds next to the application's resident buffers: both staging rings (the table,
@@ -224,6 +226,7 @@ class SwapEngine {
     int64_t free_phys_locked() const { return (int64_t)cfg_.resident_cap - (int64_t)resident_mapped_ - (int64_t)evicting_mapped_; }
     void flush_pager_stats_locked();
     void relock(Lock &lk);
+    void note_vmm_call(const char *what, uint64_t ns);
     void collect_waits_locked(int row, std::vector<CUevent> *out);
 
     // ---- staged path pieces (pager thread)
@@ -235,13 +238,16 @@ class SwapEngine {
     CUresult in_issue_copies(InJob &j);
 
     // ---- pinned pool (host_mu_)
+    bool pin_slab(size_t sb, Slab *out, bool *local);
+    void grow_main();
+    void want_host_pool(uint64_t live_bytes);
     bool host_alloc(size_t bytes, uint64_t *off);
     void release_host_range(uint64_t off, uint64_t len);
     unsigned char *host_ptr(uint64_t off);
     bool reclaim_host_blocks(Lock &lk, uint64_t bytes);
 
     // ---- misc
-    CUevent get_event();                       // pager-private pool
+    CUevent get_event();                       // shared pool (ev_mu_)
     void put_event(CUevent e);
     bool va_alloc(size_t bytes, uint64_t *off);
     void va_free(uint64_t off, size_t bytes);
@@ -286,7 +292,6 @@ class SwapEngine {
     std::vector<CUevent> use_ring_;                 // last-use events, indexed by seq % size
     std::vector<CUstream> use_stream_;              // stream each use event was recorded on
     uint64_t use_seq_ = 0;
-    std::vector<CUevent> ready_free_;               // event pool shared by application threads and the pager (mu_)
     bool stop_ = false, pager_idle_ = true, kick_ = false;
     void kick_pager_locked() { kick_ = true; cv_pager_.notify_one(); }
     void drop_prefetch_queue_locked();
@@ -320,7 +325,9 @@ class SwapEngine {
     std::vector<Slot> ring_out_, ring_in_;
     int cur_out_ = 0, cur_in_ = 0;
     std::unique_ptr<VictimScanner> scanner_;
-    std::vector<CUevent> ev_pool_;
+    std::mutex ev_mu_;
+    std::vector<CUevent> ev_pool_;                  // (ev_mu_) recycled events: page-in / eviction completions, pack markers
+    uint32_t reap_defer_ = 0;                       // polls a partial reap batch has been held back
     bool unmap_runs_ok_ = true;                     // one cuMemUnmap may span several adjacent mappings (probed at run time)
     // victims selected by the last scan beyond what was needed then, in LRU order. They stay the exact LRU prefix for
     // as long as they are untouched (anything touched or created since carries a larger tick), so consuming them
@@ -333,10 +340,24 @@ class SwapEngine {
     std::vector<uint8_t> span_unpack_;
     std::vector<Prof> prof_;
     std::atomic<bool> profile_{false};
+    // diagnostics (VGPU_SWAP_TRACE): timed events around direct copies, host time of issue
+    struct TraceRec { int dir; int row; uint64_t host_ns; CUevent a, b; };
+    std::vector<TraceRec> trace_;
+    uint32_t trace_want_ = 0, trace_skip_ = 0;
+    CUevent trace_base_ = nullptr;
+    uint64_t trace_base_ns_ = 0;
+    bool trace_begin(int dir, int row, CUstream s);
+    void trace_end(CUstream s);
 
     // ---- pinned pool (host_mu_)
     std::mutex host_mu_;
+    std::condition_variable host_cv_;
     std::vector<Slab> slabs_;
+    uint64_t host_total_ = 0, host_slabs_ = 0, host_slabs_local_ = 0;
+    std::atomic<uint64_t> host_want_{0};            // pool size the grower works towards (= pinned blocks the live rows will need)
+    uint64_t host_need_ = 0;                        // (mu_) sum of the live rows' block sizes
+    std::thread grower_;
+    bool growing_ = false, grow_stop_ = false;
 };
 
 }  // namespace vgpu

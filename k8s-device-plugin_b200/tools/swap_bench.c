@@ -28,6 +28,7 @@ typedef struct {
     double pack_span_ms, unpack_span_ms;
     uint64_t direct_out_bytes, direct_in_bytes, prefetch_issued, prefetch_hits, prefetch_wasted, demand_waits, clean_evictions, host_slabs, host_slabs_local;
     uint64_t pager_unmap_ns, pager_setaccess_ns, pager_issue_ns, pager_poll_ns, pager_lock_ns, pager_step_ns[5];
+    uint64_t vmm_slow_calls, vmm_slow_ns, vmm_max_ns;
 } swap_stats_t;
 typedef int (*stats_fn)(int, swap_stats_t *);
 typedef int (*prof_fn)(int, int);
@@ -199,7 +200,7 @@ int main(int argc, char **argv) {
            "\"phys_creates\": %llu, \"phys_reuses\": %llu, \"scans\": %llu, \"scan_cache_hits\": %llu, "
            "\"host_ms\": {\"admit\": %.1f, \"wait\": %.1f, \"vmm\": %.1f}, "
            "\"pager_ms\": {\"busy\": %.1f, \"vmm\": %.1f, \"scan\": %.1f, \"packsync\": %.1f, \"ringwait\": %.1f, \"unmap\": %.1f, \"setaccess\": %.1f, \"issue\": %.1f, \"poll\": %.1f, \"lock\": %.1f, "
-           "\"steps\": [%.1f, %.1f, %.1f, %.1f, %.1f]}, \"vmm_calls\": %llu, "
+           "\"steps\": [%.1f, %.1f, %.1f, %.1f, %.1f]}, \"vmm_slow\": {\"calls\": %llu, \"ms\": %.1f, \"max_ms\": %.1f}, \"vmm_calls\": %llu, "
            "\"direct_in_bytes\": %llu, \"direct_out_bytes\": %llu, \"prefetch\": {\"issued\": %llu, \"hits\": %llu, \"wasted\": %llu}, "
            "\"demand_waits\": %llu, \"clean_evictions\": %llu, \"host_slabs\": [%llu, %llu], "
            "\"pack_span_ms\": %.3f, \"unpack_span_ms\": %.3f}\n",
@@ -218,7 +219,8 @@ int main(int argc, char **argv) {
            (s1.pager_unmap_ns - s0.pager_unmap_ns) / 1e6, (s1.pager_setaccess_ns - s0.pager_setaccess_ns) / 1e6, (s1.pager_issue_ns - s0.pager_issue_ns) / 1e6,
            (s1.pager_poll_ns - s0.pager_poll_ns) / 1e6, (s1.pager_lock_ns - s0.pager_lock_ns) / 1e6,
            (s1.pager_step_ns[0] - s0.pager_step_ns[0]) / 1e6, (s1.pager_step_ns[1] - s0.pager_step_ns[1]) / 1e6, (s1.pager_step_ns[2] - s0.pager_step_ns[2]) / 1e6,
-           (s1.pager_step_ns[3] - s0.pager_step_ns[3]) / 1e6, (s1.pager_step_ns[4] - s0.pager_step_ns[4]) / 1e6, (unsigned long long)(s1.vmm_calls - s0.vmm_calls),
+           (s1.pager_step_ns[3] - s0.pager_step_ns[3]) / 1e6, (s1.pager_step_ns[4] - s0.pager_step_ns[4]) / 1e6,
+           (unsigned long long)(s1.vmm_slow_calls - s0.vmm_slow_calls), (s1.vmm_slow_ns - s0.vmm_slow_ns) / 1e6, s1.vmm_max_ns / 1e6, (unsigned long long)(s1.vmm_calls - s0.vmm_calls),
            (unsigned long long)(s1.direct_in_bytes - s0.direct_in_bytes), (unsigned long long)(s1.direct_out_bytes - s0.direct_out_bytes),
            (unsigned long long)(s1.prefetch_issued - s0.prefetch_issued), (unsigned long long)(s1.prefetch_hits - s0.prefetch_hits),
            (unsigned long long)(s1.prefetch_wasted - s0.prefetch_wasted), (unsigned long long)(s1.demand_waits - s0.demand_waits),

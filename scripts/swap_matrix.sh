@@ -19,7 +19,7 @@ import json,sys
 d=json.loads(sys.stdin.read()); r=d["result"] or {}
 if r and "event_ms" in r:
     gb=(r["page_in_bytes"]+r["page_out_bytes"])/1e9
-    print(d["variant"], "GB/s=%.1f"%(gb/(r["event_ms"]/1e3)), "mism=%s"%r["mismatches"], "host", r["host_ms"], "pager", r["pager_ms"], "vmm_calls", r["vmm_calls"], "prefetch", r["prefetch"], "direct_in_GB=%.1f out=%.1f"%(r["direct_in_bytes"]/1e9, r["direct_out_bytes"]/1e9), "waits", r["demand_waits"], "pack", r["pack_launches"], "fill_ms", r["alloc_fill_ms"])
+    print(d["variant"], "GB/s=%.1f"%(gb/(r["event_ms"]/1e3)), "mism=%s"%r["mismatches"], "host", r["host_ms"], "pager", r["pager_ms"], "vmm_calls", r["vmm_calls"], "slow", r.get("vmm_slow"), "prefetch", r["prefetch"], "direct_in_GB=%.1f out=%.1f"%(r["direct_in_bytes"]/1e9, r["direct_out_bytes"]/1e9), "waits", r["demand_waits"], "pack", r["pack_launches"], "fill_ms", r["alloc_fill_ms"])
 else: print(d["variant"], "FAILED", r)
 '
     tail -3 gpurun_out/swap_matrix_$name.err
