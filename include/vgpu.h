@@ -157,6 +157,7 @@ int vgpu_swap_advise_read_mostly(vgpu_swap_t *s, uint64_t ptr, int on);
 int vgpu_swap_pin(vgpu_swap_t *s, uint64_t ptr, int on);
 int vgpu_swap_stats(vgpu_swap_t *s, vgpu_swap_stats_t *out);
 int vgpu_swap_drain(vgpu_swap_t *s);
+int vgpu_swap_set_profile(vgpu_swap_t *s, int on);   /* event brackets + in-kernel spans around pack/unpack launches from now on */
 int vgpu_swap_table(vgpu_swap_t *s, vgpu_entry_t *out, uint32_t cap, uint32_t *n);
 
 /* ---- gpucores limiter (reference: rate_limiter@0x4591a / utilization_watcher@0x46710) */

@@ -122,6 +122,7 @@ ABI = {
     "vgpu_swap_pin": (_INT, [_P, _U64, _INT]),
     "vgpu_swap_stats": (_INT, [_P, C.POINTER(SwapStats)]),
     "vgpu_swap_drain": (_INT, [_P]),
+    "vgpu_swap_set_profile": (_INT, [_P, _INT]),
     "vgpu_swap_table": (_INT, [_P, C.POINTER(Entry), _U32, C.POINTER(_U32)]),
     "vgpu_limiter_create": (_INT, [_INT, C.POINTER(_P)]),
     "vgpu_limiter_destroy": (None, [_P]),
@@ -303,6 +304,9 @@ class Swap:
 
     def drain(self):
         _check("vgpu_swap_drain", lib().vgpu_swap_drain(self._h))
+
+    def set_profile(self, on=True):
+        _check("vgpu_swap_set_profile", lib().vgpu_swap_set_profile(self._h, int(on)))
 
     def table(self):
         n = _U32(0)

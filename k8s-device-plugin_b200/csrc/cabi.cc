@@ -325,6 +325,7 @@ VGPU_API int vgpu_swap_stats(vgpu_swap_t *s, vgpu_swap_stats_t *out) {
     return CUDA_SUCCESS;
 }
 VGPU_API int vgpu_swap_drain(vgpu_swap_t *s) { return s ? s->e->drain() : CUDA_ERROR_INVALID_VALUE; }
+VGPU_API int vgpu_swap_set_profile(vgpu_swap_t *s, int on) { if (!s) return CUDA_ERROR_INVALID_VALUE; s->e->set_profile(on != 0); return CUDA_SUCCESS; }
 VGPU_API int vgpu_swap_table(vgpu_swap_t *s, vgpu_entry_t *out, uint32_t cap, uint32_t *n) {
     if (!s) return CUDA_ERROR_INVALID_VALUE;
     static_assert(sizeof(vgpu_entry_t) == sizeof(VgpuEntry), "table row layout");

@@ -26,7 +26,6 @@ namespace vgpu {
         }                                                                                \
     } while (0)
 
-static uint64_t g_dbg_ns[8];
 static uint64_t round_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 static uint64_t mono_ns() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec; }
 struct ScopedNs { uint64_t *acc; uint64_t t0; explicit ScopedNs(uint64_t *a) : acc(a), t0(mono_ns()) {} ~ScopedNs() { *acc += mono_ns() - t0; } };
@@ -211,7 +210,6 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
 
 void SwapEngine::stop_pager() {
     if (!pager_.joinable()) return;
-    if (std::getenv("VGPU_PRINT_STATS")) std::fprintf(stderr, "[vgpu-b200 dbg] evict begin=%.1f ms, evict body=%.1f ms, choose=%.1f ms over %lu calls; get_event=%.1f loop=%.1f relock=%.1f commit=%.1f\n", g_dbg_ns[0] / 1e6, g_dbg_ns[1] / 1e6, g_dbg_ns[2] / 1e6, (unsigned long)g_dbg_ns[3], g_dbg_ns[4] / 1e6, g_dbg_ns[5] / 1e6, g_dbg_ns[6] / 1e6, g_dbg_ns[7] / 1e6);
     { std::lock_guard<std::mutex> g(mu_); drop_prefetch_queue_locked(); stop_ = true; kick_ = true; }
     cv_pager_.notify_all();
     cv_admit_.notify_all();
@@ -904,15 +902,11 @@ CUresult SwapEngine::evict_direct(Lock &lk, const std::vector<uint32_t> &victims
     const DriverTable &d = drv();
     if (victims.empty()) return CUDA_SUCCESS;
     std::vector<OutItem> items;
-    uint64_t tA = mono_ns();
     begin_evict_locked(victims, &items);
     lk.unlock();
-    g_dbg_ns[0] += mono_ns() - tA;
-    ScopedNs dbg1(&g_dbg_ns[1]);
     CUresult rc = CUDA_SUCCESS;
     for (OutItem &it : items) {
-        { ScopedNs dbg4(&g_dbg_ns[4]); it.done = get_event(); }
-        ScopedNs dbg5(&g_dbg_ns[5]);
+        it.done = get_event();
         if (it.copy && !it.has_host) {
             if (!host_alloc(it.len, &it.host_off)) {
                 relock(lk);
@@ -941,10 +935,7 @@ CUresult SwapEngine::evict_direct(Lock &lk, const std::vector<uint32_t> &victims
         }
         d.cuEventRecord(it.done, s);
     }
-    uint64_t tR = mono_ns();
     relock(lk);
-    g_dbg_ns[6] += mono_ns() - tR;
-    ScopedNs dbg7(&g_dbg_ns[7]);
     for (OutItem &it : items) {
         Side &s = side_[it.row];
         if (it.failed) {
@@ -1512,9 +1503,7 @@ bool SwapEngine::step_evict_ahead(Lock &lk) {
     uint64_t shortage = resident_mapped_ + wanted - cfg_.resident_cap;
     std::vector<uint32_t> victims;
     uint64_t evictable = 0;
-    uint64_t tC = mono_ns();
     CUresult crc = choose_victims(lk, shortage, &victims, &evictable);
-    g_dbg_ns[2] += mono_ns() - tC; g_dbg_ns[3]++;
     if (crc != CUDA_SUCCESS || victims.empty()) {
         // nothing can be evicted (everything resident is in use): wishes are dropped, demands keep waiting for a release
         bool had = !prefetch_q_.empty();

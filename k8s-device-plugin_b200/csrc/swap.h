@@ -59,7 +59,9 @@ struct SwapConfig {
     uint64_t arena_bytes = 1ull << 40;    // virtual address arena
     bool profile = false;                 // bracket pack/unpack launches with events + in-kernel spans (bench roofline pass)
     uint32_t scan_lookahead = 16;         // a scan selects this many times the bytes needed; the surplus is consumed by later evictions
-    uint64_t prefetch_bytes = 512ull << 20;   // VGPU_SWAP_PREFETCH_MB: how far the pager runs ahead of the application (0 = no prefetch)
+    uint64_t prefetch_bytes = 2048ull << 20;  // VGPU_SWAP_PREFETCH_MB: how far the pager runs ahead of the application, capped at a quarter
+                                          // of the resident cap (0 = no prefetch). Deep on purpose: VMM calls stall for 10-500 ms now and
+                                          // then while DMA is running (profiles/r02_*), and only queued work keeps the link busy meanwhile
     size_t copy_bytes = 16u << 20;        // VGPU_SWAP_COPY_MB: piece size of the direct copies (VMM calls wait for the copy in flight)
     uint32_t batch_rows = 4;              // rows per pager batch (VMM cost is per mapping, not per call: small batches keep latency low)
     uint64_t headroom_bytes = ~0ull;      // VGPU_SWAP_HEADROOM_MB: free physical memory the pager keeps ahead of the page-in queue while

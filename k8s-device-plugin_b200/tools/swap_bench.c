@@ -40,6 +40,7 @@ static uint64_t rng(void) { uint64_t x = (rng_state += 0x9E3779B97F4A7C15ull); x
 int main(int argc, char **argv) {
     const char *cubin = NULL, *order = "cyclic";
     long nbuf = 64, mib = 64, steps = 64, warmup = 8, managed = 0, ballast_mib = 0, verify = 1, profile = 0, seed = 0x5EED, wait_stdin = 0;
+    long ro_every = 0;                   /* > 0: every ro_every-th buffer is advised read-mostly (cuMemAdvise) and only ever READ after the fill */
     long ragged_lo = 0, ragged_hi = 0;   /* cfg 3 variant B: sizes log-uniform in [lo, hi] MiB, same total as --buffers x --mib */
     double zipf_s = 1.1;
     for (int i = 1; i + 1 < argc; i += 2) {
@@ -57,6 +58,7 @@ int main(int argc, char **argv) {
         else if (!strcmp(k, "--seed")) seed = strtol(v, 0, 0);
         else if (!strcmp(k, "--zipf")) zipf_s = atof(v);
         else if (!strcmp(k, "--wait-stdin")) wait_stdin = atol(v);
+        else if (!strcmp(k, "--ro-every")) ro_every = atol(v);
         else if (!strcmp(k, "--ragged-lo")) ragged_lo = atol(v);
         else if (!strcmp(k, "--ragged-hi")) ragged_hi = atol(v);
         else { fprintf(stderr, "unknown option %s\n", k); return 2; }
@@ -125,6 +127,10 @@ int main(int argc, char **argv) {
         CK(cuLaunchKernel(f_fill, grid, 1, 1, 256, 1, 1, 0, 0, a, 0));
     }
     CK(cuCtxSynchronize());
+    /* read-mostly buffers: the hint a UVM application gives (the reference's swappable memory IS managed memory); a plain
+     * cuMemAlloc pointer makes the bare driver refuse it, which is fine */
+    if (ro_every > 0) for (long i = ro_every - 1; i < nbuf; i += ro_every) (void)cuMemAdvise(buf[i], sz[i], CU_MEM_ADVISE_SET_READ_MOSTLY, dev);
+    CUdeviceptr d_ro_bad = 0; CK(cuMemAlloc(&d_ro_bad, 8)); CK(cuMemsetD8(d_ro_bad, 0, 8));
     double t_alloc1 = now_ms();
     if (profile && set_prof) set_prof(0, 1);
 
@@ -148,11 +154,11 @@ int main(int argc, char **argv) {
 
     CUevent e0, e1; CK(cuEventCreate(&e0, 0)); CK(cuEventCreate(&e1, 0));
     swap_stats_t s0, s1; memset(&s0, 0, sizeof s0); memset(&s1, 0, sizeof s1);
-    for (long t = 0; t < warmup; t++) {
-        uint64_t nw = sz[seq[t]] / 8; void *a[] = {&buf[seq[t]], &nw};
-        CK(cuLaunchKernel(f_touch, grid, 1, 1, 256, 1, 1, 0, 0, a, 0));
-        touches[seq[t]]++;
-    }
+#define IS_RO(i) (ro_every > 0 && ((i) + 1) % ro_every == 0)
+#define TOUCH(i) do { uint64_t nw_ = sz[i] / 8; \
+        if (IS_RO(i)) { uint64_t idx_ = (uint64_t)(i), add_ = 0; void *a_[] = {&buf[i], &nw_, &idx_, &add_, &d_ro_bad}; CK(cuLaunchKernel(f_verify, grid, 1, 1, 256, 1, 1, 0, 0, a_, 0)); } \
+        else { void *a_[] = {&buf[i], &nw_}; CK(cuLaunchKernel(f_touch, grid, 1, 1, 256, 1, 1, 0, 0, a_, 0)); touches[i]++; } } while (0)
+    for (long t = 0; t < warmup; t++) TOUCH(seq[t]);
     CK(cuCtxSynchronize());
     if (wait_stdin) {   /* multi-GPU runs: the launcher releases every rank's timed region together */
         char line[16];
@@ -163,12 +169,7 @@ int main(int argc, char **argv) {
     double w0 = now_ms();
     CK(cuEventRecord(e0, 0));
     unsigned long long touched = 0;
-    for (long t = warmup; t < total; t++) {
-        uint64_t nw = sz[seq[t]] / 8; void *a[] = {&buf[seq[t]], &nw};
-        CK(cuLaunchKernel(f_touch, grid, 1, 1, 256, 1, 1, 0, 0, a, 0));
-        touches[seq[t]]++;
-        touched += sz[seq[t]];
-    }
+    for (long t = warmup; t < total; t++) { TOUCH(seq[t]); touched += sz[seq[t]]; }
     double w_enq = now_ms();
     CK(cuEventRecord(e1, 0));
     CK(cuCtxSynchronize());
@@ -188,10 +189,11 @@ int main(int argc, char **argv) {
         CK(cuCtxSynchronize());
         CK(cuMemcpyDtoH(&mism, dcnt, 8));
     }
+    { unsigned long long ro_bad = 0; CK(cuMemcpyDtoH(&ro_bad, d_ro_bad, 8)); mism += ro_bad; }   /* what the read-only touches saw */
     double t_ver1 = now_ms();
 
     uint64_t pin = s1.v[1] - s0.v[1], pout = s1.v[0] - s0.v[0];
-    printf("{\"ragged_mib\": [%ld, %ld], \"buffers\": %ld, \"mib\": %ld, \"steps\": %ld, \"warmup\": %ld, \"order\": \"%s\", \"managed\": %ld, \"ballast_mib\": %ld, "
+    printf("{\"ro_every\": %ld, \"ragged_mib\": [%ld, %ld], \"buffers\": %ld, \"mib\": %ld, \"steps\": %ld, \"warmup\": %ld, \"order\": \"%s\", \"managed\": %ld, \"ballast_mib\": %ld, "
            "\"event_ms\": %.3f, \"wall_ms\": %.3f, \"enqueue_ms\": %.3f, \"alloc_fill_ms\": %.1f, \"verify_ms\": %.1f, "
            "\"hooked_stats\": %s, \"page_in_bytes\": %llu, \"page_out_bytes\": %llu, \"touched_bytes\": %llu, "
            "\"mismatches\": %llu, \"verified\": %ld, "
@@ -204,7 +206,7 @@ int main(int argc, char **argv) {
            "\"direct_in_bytes\": %llu, \"direct_out_bytes\": %llu, \"prefetch\": {\"issued\": %llu, \"hits\": %llu, \"wasted\": %llu}, "
            "\"demand_waits\": %llu, \"clean_evictions\": %llu, \"host_slabs\": [%llu, %llu], "
            "\"pack_span_ms\": %.3f, \"unpack_span_ms\": %.3f}\n",
-           ragged_lo, ragged_hi, nbuf, mib, steps, warmup, order, managed, ballast_mib, ev_ms, w1 - w0, w_enq - w0, t_alloc1 - t_alloc0, t_ver1 - t_ver0,
+           ro_every, ragged_lo, ragged_hi, nbuf, mib, steps, warmup, order, managed, ballast_mib, ev_ms, w1 - w0, w_enq - w0, t_alloc1 - t_alloc0, t_ver1 - t_ver0,
            get_stats ? "true" : "false", (unsigned long long)pin, (unsigned long long)pout,
            touched, mism, verify,
            s1.pack_ms - s0.pack_ms, s1.unpack_ms - s0.unpack_ms,
