@@ -153,11 +153,12 @@ class Workload:
 
 
 def measure_link(torch, barrier=None, concurrent=False):
-    """Pinned-memcpy bandwidth of this box (the end-to-end roofline): 1 GiB, each direction and both at once. Alone
-    (N=1): best of 5. With several ranks every copy starts behind a barrier, so all GPUs pull on the host at the same
-    time — GPUs behind one PCIe switch share its uplink — and the MEDIAN of 5 is kept: the ceiling the replicas
-    actually share, not the one a lone GPU sees."""
-    n = 1 * GiB
+    """Pinned-memcpy bandwidth of this box (the end-to-end roofline): each direction alone (1 GiB) and both at once (4 x
+    1 GiB per direction as 32 MiB copies back to back on two streams, timed with CUDA events from a common start to the
+    later of the two ends). Alone (N=1): best of 5. With several ranks every copy starts behind a barrier, so all GPUs
+    pull on the host at the same time — GPUs behind one PCIe switch share its uplink — and the MEDIAN of 5 is kept: the
+    ceiling the replicas actually share, not the one a lone GPU sees."""
+    n, piece = 1 * GiB, 32 * MiB
     h1 = torch.empty(n, dtype=torch.uint8).pin_memory()
     h2 = torch.empty(n, dtype=torch.uint8).pin_memory()
     d1 = torch.empty(n, dtype=torch.uint8, device="cuda")
@@ -174,13 +175,23 @@ def measure_link(torch, barrier=None, concurrent=False):
             b.synchronize()
             got[key].append(n / a.elapsed_time(b) / 1e6)
         sync()
-        t0 = time.perf_counter()
+        a, b1, b2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        reps = 4
         with torch.cuda.stream(s1):
-            d1.copy_(h1, non_blocking=True)
+            a.record()
+        s2.wait_event(a)
+        for _r in range(reps):
+            for o in range(0, n, piece):
+                with torch.cuda.stream(s1):
+                    d1[o:o + piece].copy_(h1[o:o + piece], non_blocking=True)
+                with torch.cuda.stream(s2):
+                    h2[o:o + piece].copy_(d2[o:o + piece], non_blocking=True)
+        with torch.cuda.stream(s1):
+            b1.record()
         with torch.cuda.stream(s2):
-            h2.copy_(d2, non_blocking=True)
+            b2.record()
         torch.cuda.synchronize()
-        got["bidir"].append(2 * n / (time.perf_counter() - t0) / 1e9)
+        got["bidir"].append(2 * reps * n / max(a.elapsed_time(b1), a.elapsed_time(b2)) / 1e6)
     del h1, h2, d1, d2
     pick = (lambda v: sorted(v)[len(v) // 2]) if concurrent else max
     return {k: pick(v) for k, v in got.items()}
@@ -664,16 +675,17 @@ def main():
                     "frac": round(value / world / link_mean["bidir"], 4) if link_mean["bidir"] else None,
                     "h2d_peak": round(link_mean["h2d"], 2), "d2h_peak": round(link_mean["d2h"], 2),
                     "peak_min_over_ranks": round(link_min, 2),
-                    "peak_source": ("pinned 1 GiB cudaMemcpyAsync both directions at once, measured in this run" if world == 1 else
+                    "peak_source": ("pinned memcpy both directions at once (4 GiB each way as 32 MiB copies, CUDA events), measured in this run" if world == 1 else
                                     f"per-GPU mean over {world} ranks copying 1 GiB each way AT THE SAME TIME (barrier-started, median of 5): "
                                     "the host link the replicas share, measured in this run")}
         eng = engine_summary(d, args.steps)
         eng["pinned_slabs_on_gpu_numa_node_min_over_ranks"] = round(local_frac, 3)
+        eng["numa_node_rank0"] = numa
         line = {
             "metric": "vmem_swap_GBps", "value": round(value, 3), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(t_max / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": dict(wl.config(world), numa_node=numa),
+            "config": wl.config(world),
             "e2e": {"value": round(e2e_value, 3), "unit": "GB/s",
                     "h2d_bytes_per_step": int(e2e["page_in_bytes"] // args.steps), "d2h_bytes_per_step": int(e2e["page_out_bytes"] // args.steps),
                     "via": "LD_PRELOAD=libvgpu.so on an unmodified driver-API app (cuMemAlloc_v2/cuLaunchKernel intercept)",
