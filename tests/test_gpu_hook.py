@@ -66,18 +66,35 @@ def _swap_bench(tmp_path, extra_env, args):
 
 
 def test_unmodified_app_under_hook_swaps_and_verifies(tmp_path):
-    out = _swap_bench(tmp_path, {"CUDA_OVERSUBSCRIBE": "true", "CUDA_DEVICE_MEMORY_LIMIT_0": "2048m"},
+    """Pure demand paging (prefetch off): exact counts, every byte through the staged path's TMA kernels."""
+    out = _swap_bench(tmp_path, {"CUDA_OVERSUBSCRIBE": "true", "CUDA_DEVICE_MEMORY_LIMIT_0": "2048m", "VGPU_SWAP_PREFETCH_MB": "0"},
                       ["--buffers", "48", "--mib", "64", "--steps", "96", "--warmup", "8", "--order", "cyclic"])
     assert out["mismatches"] == 0 and out["hooked_stats"] is True
     assert out["page_in_bytes"] == 96 * (64 << 20)          # every cyclic touch misses: 64 MiB in ...
     assert out["page_out_bytes"] >= 95 * (64 << 20)         # ... and 64 MiB out
-    assert out["phys_reuses"] > 0
+    assert out["phys_reuses"] > 0 and out["pack_launches"] > 0 and out["unpack_launches"] > 0
+    assert out["host_ms"]["vmm"] == 0                       # VMM calls belong to the pager thread
 
 
-def test_reaper_thread_variant_keeps_every_word(tmp_path):
-    out = _swap_bench(tmp_path, {"CUDA_OVERSUBSCRIBE": "true", "CUDA_DEVICE_MEMORY_LIMIT_0": "2048m", "VGPU_SWAP_ASYNC_UNMAP": "1"},
-                      ["--buffers", "48", "--mib", "64", "--steps", "144", "--warmup", "8", "--order", "cyclic"])
-    assert out["mismatches"] == 0 and out["page_in_bytes"] == 144 * (64 << 20)
+def test_prefetch_pipeline_under_the_hook_keeps_every_word(tmp_path):
+    """Default engine: after the populate phase the predictor knows the cycle, the pager pages ahead with plain DMA."""
+    out = _swap_bench(tmp_path, {"CUDA_OVERSUBSCRIBE": "true", "CUDA_DEVICE_MEMORY_LIMIT_0": "2048m"},
+                      ["--buffers", "48", "--mib", "64", "--steps", "144", "--warmup", "24", "--order", "cyclic"])
+    assert out["mismatches"] == 0 and out["faults"] == 144
+    window = 8                                             # quota / 4 = 512 MiB = 8 buffers
+    assert (144 - window) * (64 << 20) <= out["page_in_bytes"] <= (144 + window) * (64 << 20)
+    assert out["direct_in_bytes"] >= 0.8 * out["page_in_bytes"] and out["direct_out_bytes"] >= 0.8 * out["page_out_bytes"]
+    assert out["host_ms"]["vmm"] == 0
+
+
+def test_read_mostly_advice_through_cumemadvise_saves_the_write_back(tmp_path):
+    """Every second buffer is advised read-mostly with cuMemAdvise (what a UVM application does; the reference's swappable
+    memory is managed memory) and only read: its evictions are clean, so page-out traffic is about half the page-in's."""
+    out = _swap_bench(tmp_path, {"CUDA_OVERSUBSCRIBE": "true", "CUDA_DEVICE_MEMORY_LIMIT_0": "2048m"},
+                      ["--buffers", "48", "--mib", "64", "--steps", "192", "--warmup", "48", "--order", "cyclic", "--ro-every", "2"])
+    assert out["mismatches"] == 0
+    assert out["clean_evictions"] >= 60
+    assert out["page_out_bytes"] <= 0.65 * out["page_in_bytes"]
 
 
 def test_zipf_order_hits_resident_set(tmp_path):
