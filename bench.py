@@ -10,7 +10,9 @@ buffers (8 GiB + 64 GiB oversubscribed) and touches them cyclically with a read-
 case, every touch pages 64 MiB in and 64 MiB out. One "step" = 16 touches = 1 GiB in + 1 GiB out over the host link.
 
   value : page traffic GB/s (in + out) with the loop driven straight through the engine's C ABI in this process, timed with
-          profiling OFF (no event brackets, no in-kernel stamps)
+          profiling OFF (no event brackets, no in-kernel stamps). Bytes = 2 x 64 MiB x (touches of the timed region that
+          found their buffer paged out) — the workload's definition, the same one the reference arm uses — NOT the engine's
+          counters, which run ahead of the last touch by the prefetch window (they are reported under `engine.bytes`)
   e2e   : the same loop as an UNMODIFIED driver-API program (swap_bench) under LD_PRELOAD=libvgpu.so — the
           reference-facing boundary; h2d/d2h bytes per step are the page-in/page-out bytes the hook moved
   roofline      : vgpu_pack_tma (the engine's HBM-bound kernel) against the measured HBM copy bandwidth. In the headline
@@ -237,8 +239,7 @@ def run_engine_arm(torch, v, wl, steps, warmup, barrier):
 
     for _ in range(warmup):
         step()
-    torch.cuda.synchronize()
-    sw.drain()
+    torch.cuda.synchronize()                   # NOT drained: the pager's pipeline is as full at the start of the timed region as at its end
     s0 = sw.stats()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -255,6 +256,12 @@ def run_engine_arm(torch, v, wl, steps, warmup, barrier):
     s1 = sw.stats()
     d = {k: s1[k] - s0[k] for k in s1 if isinstance(s1[k], (int, float))}
     d["vmm_max_ns"] = s1["vmm_max_ns"]
+    # Page traffic of the timed region BY THE WORKLOAD'S DEFINITION: every touch that found its buffer paged out needed its
+    # 64 MiB brought in and — the set being full of dirty buffers — 64 MiB written back. The engine's own byte counters
+    # (reported under `engine.bytes`) also include whatever the prefetch window has in flight when the region ends, which
+    # the timing (an event behind the LAST TOUCH) does not wait for; the reference arm is computed the same way.
+    d["paged_bytes"] = 2 * d["faults"] * nbytes
+    d["touches"] = steps * TOUCHES_PER_STEP
     d["host_slabs"], d["host_slabs_local"] = s1["host_slabs"], s1["host_slabs_local"]        # totals, not deltas
 
     # ---- secondary pass (outside the headline timing): Zipf order, odd buffers read-mostly and only read; profiling on so
@@ -493,6 +500,8 @@ def reference_arm(args):
         if float(t.item()) < 1.0:
             res = None
     if res is None:
+        if world > 1 and ok == 1.0:
+            note = "reference binary ran here but not on every rank of this box (it looks its pid up on NVML device 0, and NVML sees all GPUs outside a container); all ranks: "
         p = spawn_app(local, wl, steps, warmup, "managed", True, ballast_mib=ballast_mib)
         res = finish_app(p, True, barrier, timeout=900 + 4 * steps)
         kind = "port"
@@ -565,9 +574,9 @@ def engine_summary(d, steps):
     """Counters of the timed region: where the bytes went and where the threads' time went (per step, rank 0)."""
     per = lambda k: round(d.get(k, 0) / 1e6 / steps, 3)
     return {
-        "faults": d["faults"], "evictions": d["evictions"], "scans": d["scans"], "scan_launches": d["scan_launches"],
+        "touches": d.get("touches"), "faults": d["faults"], "evictions": d["evictions"], "scans": d["scans"], "scan_launches": d["scan_launches"],
         "phys_creates": d["phys_creates"], "phys_reuses": d["phys_reuses"],
-        "bytes": {"direct_in": d["direct_in_bytes"], "direct_out": d["direct_out_bytes"], "via_pack_kernel": max(0, d["page_out_bytes"] - d["direct_out_bytes"]),
+        "bytes": {"paged_by_definition": d.get("paged_bytes"), "counted_in": d["page_in_bytes"], "counted_out": d["page_out_bytes"], "direct_in": d["direct_in_bytes"], "direct_out": d["direct_out_bytes"], "via_pack_kernel": max(0, d["page_out_bytes"] - d["direct_out_bytes"]),
                   "via_unpack_kernel": max(0, d["page_in_bytes"] - d["direct_in_bytes"])},
         "prefetch": {"issued": d["prefetch_issued"], "hits": d["prefetch_hits"], "wasted": d["prefetch_wasted"]},
         "clean_evictions": d["clean_evictions"], "demand_waits": d["demand_waits"],
@@ -625,7 +634,7 @@ def main():
 
     # ---- arm 1: engine through the C ABI (headline pass, then the profiled Zipf read-mostly pass)
     ms, d, bad, z_ms, z = run_engine_arm(torch, v, wl, args.steps, args.warmup, barrier)
-    page_bytes = d["page_in_bytes"] + d["page_out_bytes"]
+    page_bytes = d["paged_bytes"]
     t_max, total_bytes, value = aggregate(dist, "cuda", ms, page_bytes)
     z_tmax, z_total, z_value = aggregate(dist, "cuda", z_ms, z["page_in_bytes"] + z["page_out_bytes"])
     launches = d["pack_launches"] + d["unpack_launches"] + d["scan_launches"] + args.steps * TOUCHES_PER_STEP
@@ -636,7 +645,8 @@ def main():
     # ---- arm 2: unmodified app under LD_PRELOAD (reference-facing boundary)
     p = spawn_app(local, wl, args.steps, args.warmup, "new", True)
     e2e = finish_app(p, True, barrier)
-    e2e_ms, e2e_bytes, e2e_value = aggregate(dist, "cuda", e2e["event_ms"], e2e["page_in_bytes"] + e2e["page_out_bytes"])
+    e2e_paged = 2 * e2e["faults"] * BUF_MIB * MiB               # same definition as `value`: touches that missed x (64 MiB in + 64 MiB out)
+    e2e_ms, e2e_bytes, e2e_value = aggregate(dist, "cuda", e2e["event_ms"], e2e_paged)
     e2e_bad = reduce(e2e["mismatches"], "SUM")
 
     # ---- N > 1: BASELINE.json configs[4] (every container at 50 % of its GPU's memory + swap) as an extra, shorter pass
@@ -645,7 +655,7 @@ def main():
         wl5 = Workload("cfg5", world, total_b)
         k5 = max(2, min(args.steps, 8))
         ms5, d5, bad5, _, _ = run_engine_arm(torch, v, wl5, k5, 3, barrier)
-        t5, b5, v5 = aggregate(dist, "cuda", ms5, d5["page_in_bytes"] + d5["page_out_bytes"])
+        t5, b5, v5 = aggregate(dist, "cuda", ms5, d5["paged_bytes"])
         bad5 = reduce(bad5, "SUM")
         cfg5 = {"value": round(v5, 3), "unit": "GB/s", "per_gpu": round(v5 / world, 3), "steps": k5, "workload": wl5.describe(),
                 "frac_of_link_peak": round(v5 / world / link_mean["bidir"], 4) if link_mean["bidir"] else None, "mismatches": int(bad5)}
@@ -687,7 +697,9 @@ def main():
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": wl.config(world),
             "e2e": {"value": round(e2e_value, 3), "unit": "GB/s",
-                    "h2d_bytes_per_step": int(e2e["page_in_bytes"] // args.steps), "d2h_bytes_per_step": int(e2e["page_out_bytes"] // args.steps),
+                    "h2d_bytes_per_step": int(e2e_paged // 2 // args.steps), "d2h_bytes_per_step": int(e2e_paged // 2 // args.steps),
+                    "faults": int(e2e["faults"]), "touches": args.steps * TOUCHES_PER_STEP,
+                    "hook_counted_bytes": {"page_in": int(e2e["page_in_bytes"]), "page_out": int(e2e["page_out_bytes"])},
                     "via": "LD_PRELOAD=libvgpu.so on an unmodified driver-API app (cuMemAlloc_v2/cuLaunchKernel intercept)",
                     "wall_ms": e2e["wall_ms"], "mismatches": int(e2e_bad),
                     "app_thread_vmm_ms": e2e["host_ms"]["vmm"], "vmm_slow": e2e.get("vmm_slow"), "engine": eng},
@@ -706,7 +718,8 @@ def main():
                                      "device_span_achieved": round(zk_bytes / (zk_span / 1e3) / 1e9, 1) if zk_span > 0 else None,
                                      "device_span_frac": round(zk_bytes / (zk_span / 1e3) / 1e9 / peak, 4) if zk_span > 0 else None},
                          "headline_pass": {"pack_launches": int(d["pack_launches"]), "unpack_launches": int(d["unpack_launches"]),
-                                           "bytes_by_plain_dma": int(d["direct_in_bytes"] + d["direct_out_bytes"]), "bytes_total": int(page_bytes)},
+                                           "bytes_by_plain_dma": int(d["direct_in_bytes"] + d["direct_out_bytes"]),
+                                           "bytes_counted": int(d["page_in_bytes"] + d["page_out_bytes"])},
                          "note": "the headline (cyclic) pass is link-bound and moves its bytes by DMA, not by this kernel: see `link`; the kernel "
                                  "is the latency path's (unpredicted misses) and is timed here outside the headline region",
                          "link": link_obj},

@@ -75,3 +75,30 @@ b = full("prof_pack.ncu-rep", "vgpu_pack_tma")
 if b:
     open(os.path.join(ROOT, "profiles", f"{tag}_pack_tma_full.md"), "w").write(b)
     print(b)
+    # bench.py's roofline.traffic: DRAM bytes of ONE launch, read from the capture (never typed in)
+    import json
+    r = subprocess.run(["ncu", "-i", os.path.join(OUT, "prof_pack.ncu-rep"), "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    rows = list(csv.reader(io.StringIO(r.stdout)))
+    idx = {h: i for i, h in enumerate(rows[0])}
+    units = rows[1]
+
+    def to_bytes(row, m):
+        val = float(row[idx[m]].replace(",", ""))
+        return val * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[idx[m]], 1)
+
+    per = []
+    for row in rows[2:]:
+        dur_unit = units[idx["gpu__time_duration.sum"]]
+        dur = float(row[idx["gpu__time_duration.sum"]].replace(",", "")) * {"ns": 1e-3, "us": 1, "ms": 1e3}.get(dur_unit, 1)
+        per.append({"duration_us": round(dur, 2), "dram_read_bytes": int(to_bytes(row, "dram__bytes_read.sum")), "dram_write_bytes": int(to_bytes(row, "dram__bytes_write.sum"))})
+    small = [p for p in per if p["duration_us"] < 100]
+    big = [p for p in per if p["duration_us"] >= 100]
+    out = {"source": f"profiles/{tag}_pack_tma_full.md (ncu --set full --clock-control none, scripts/ncu_pack_target.py)", "launches": per}
+    if small:
+        out["dram_bytes_per_launch"] = small[-1]["dram_read_bytes"] + small[-1]["dram_write_bytes"]
+        out["algorithmic_bytes_per_launch"] = 2 * 32 * 1024 * 1024
+        out["note"] = "32 MiB chunk launch: reads 33.55 MB from DRAM; most of the 33.55 MB it writes are still dirty in the 126 MB L2 when the kernel ends"
+    if big:
+        out["launch_1GiB"] = {"dram_bytes": big[-1]["dram_read_bytes"] + big[-1]["dram_write_bytes"], "algorithmic_bytes": 2 * 1024 ** 3, "duration_us": big[-1]["duration_us"]}
+    json.dump(out, open(os.path.join(ROOT, "profiles", f"{tag}_pack_traffic.json"), "w"), indent=1)
+    print(json.dumps(out))

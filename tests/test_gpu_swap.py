@@ -120,6 +120,56 @@ def test_clean_buffers_are_evicted_without_a_copy_and_read_mostly_advice_keeps_t
     sw.close()
 
 
+def _splitmix64_words(buf_index, nwords):
+    """Host restatement of the fill pattern (SURVEY.md §8d cfg 3): word j of buffer i = splitmix64((i << 32) + j)."""
+    import numpy as np
+    with np.errstate(over="ignore"):
+        x = (np.uint64(buf_index) << np.uint64(32)) + np.arange(nwords, dtype=np.uint64)
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+
+
+def test_swapped_bytes_verified_on_the_host_with_the_drivers_own_copy():
+    """Integrity check that uses none of this repository's device code for the read-back: after several sweeps through the
+    engine (ragged sizes, both page paths) every buffer is copied to the host with the driver's cuMemcpyDtoH_v2 and compared
+    with a numpy restatement of splitmix64 + the number of touches."""
+    import numpy as np
+    cu = C.CDLL("libcuda.so.1")
+    cu.cuMemcpyDtoH_v2.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t]
+    sw = v.Swap(resident_cap=192 * MiB, chunk_bytes=8 * MiB, ring_slots=2)
+    sizes = [24 * MiB, 40 * MiB + 4096, 3 * MiB + 8, 64 * MiB, 17 * MiB + 256, 33 * MiB, 9 * MiB + 8, 48 * MiB, 5 * MiB, 26 * MiB + 64, 12 * MiB, 56 * MiB]
+    bufs = [sw.alloc(s) for s in sizes]
+    for i, p in enumerate(bufs):
+        _fill(sw, p, sizes[i] // 8 * 8, i)
+    touches = [0] * len(bufs)
+    for sweep in range(4):                          # cyclic: the predictor locks on, later sweeps go over the direct path
+        for i, p in enumerate(bufs):
+            _touch(sw, p, sizes[i] // 8 * 8)
+            touches[i] += 1
+    import random
+    rng = random.Random(11)
+    for _ in range(30):                             # random: unpredicted misses, staged path
+        i = rng.randrange(len(bufs))
+        _touch(sw, bufs[i], sizes[i] // 8 * 8)
+        touches[i] += 1
+    torch.cuda.synchronize()
+    for i, p in enumerate(bufs):
+        nwords = sizes[i] // 8
+        host = np.empty(nwords, dtype=np.uint64)
+        sw.acquire([p], v.Swap.HOST_WAIT if hasattr(v.Swap, "HOST_WAIT") else _stream())
+        torch.cuda.synchronize()
+        assert cu.cuMemcpyDtoH_v2(host.ctypes.data_as(C.c_void_p), C.c_uint64(p), C.c_size_t(nwords * 8)) == 0
+        sw.release_ro([p], _stream())
+        with np.errstate(over="ignore"):
+            want = _splitmix64_words(i, nwords) + np.uint64(touches[i])
+        assert np.array_equal(host, want), f"buffer {i} ({sizes[i]} bytes) differs after {touches[i]} touches"
+    s = sw.stats()
+    assert s["evictions"] > 20 and s["unpack_launches"] > 0 and s["direct_in_bytes"] > 0, s
+    sw.close()
+
+
 def test_ragged_sizes_and_multi_buffer_admission():
     sw = v.Swap(resident_cap=128 * MiB, chunk_bytes=8 * MiB, ring_slots=2)
     sizes = [3 * MiB + 8, 17 * MiB + 4096, 2 * MiB + 16, 40 * MiB, 5 * MiB + 1000 * 8, 33 * MiB, 9 * MiB + 8, 26 * MiB]
