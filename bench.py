@@ -658,7 +658,7 @@ def main():
         t5, b5, v5 = aggregate(dist, "cuda", ms5, d5["paged_bytes"])
         bad5 = reduce(bad5, "SUM")
         cfg5 = {"value": round(v5, 3), "unit": "GB/s", "per_gpu": round(v5 / world, 3), "steps": k5, "workload": wl5.describe(),
-                "frac_of_link_peak": round(v5 / world / link_mean["bidir"], 4) if link_mean["bidir"] else None, "mismatches": int(bad5)}
+                "frac_of_link_peak": round(v5 / world / (link_mean["h2d"] + link_mean["d2h"]), 4), "mismatches": int(bad5)}
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the reference's swap path on this box's host cores
     cpu = None
@@ -681,13 +681,18 @@ def main():
         zk_span = z["pack_span_ms"] + z["unpack_span_ms"]
         chunk = iso["chunk_32MiB"]
         traffic = pack_traffic()
-        link_obj = {"bound": "host-link", "achieved": round(value / world, 3), "peak": round(link_mean["bidir"], 2), "unit": "GB/s",
-                    "frac": round(value / world / link_mean["bidir"], 4) if link_mean["bidir"] else None,
+        # The bound: the two one-direction pinned-memcpy peaks of this run ADDED (PCIe is full duplex). The naive both-at-once
+        # measurement (two streams of 32 MiB copies) is reported next to it: it reaches 97-100 GB/s on these boxes, less than
+        # the pager's deep queues of 16 MiB copies sustain, so it is a floor of the bound, not the bound.
+        link_peak = link_mean["h2d"] + link_mean["d2h"]
+        link_obj = {"bound": "host-link", "achieved": round(value / world, 3), "peak": round(link_peak, 2), "unit": "GB/s",
+                    "frac": round(value / world / link_peak, 4) if link_peak else None,
                     "h2d_peak": round(link_mean["h2d"], 2), "d2h_peak": round(link_mean["d2h"], 2),
-                    "peak_min_over_ranks": round(link_min, 2),
-                    "peak_source": ("pinned memcpy both directions at once (4 GiB each way as 32 MiB copies, CUDA events), measured in this run" if world == 1 else
-                                    f"per-GPU mean over {world} ranks copying 1 GiB each way AT THE SAME TIME (barrier-started, median of 5): "
-                                    "the host link the replicas share, measured in this run")}
+                    "both_at_once_naive": round(link_mean["bidir"], 2), "both_at_once_naive_min_over_ranks": round(link_min, 2),
+                    "frac_of_naive_both_at_once": round(value / world / link_mean["bidir"], 4) if link_mean["bidir"] else None,
+                    "peak_source": ("h2d_peak + d2h_peak: pinned 1 GiB cudaMemcpyAsync, each direction alone, best of 5, measured in this run" if world == 1 else
+                                    f"h2d_peak + d2h_peak, each the per-GPU mean over {world} ranks copying 1 GiB in that direction AT THE SAME TIME "
+                                    "(barrier-started, median of 5): the host link the replicas share, measured in this run")}
         eng = engine_summary(d, args.steps)
         eng["pinned_slabs_on_gpu_numa_node_min_over_ranks"] = round(local_frac, 3)
         eng["numa_node_rank0"] = numa
