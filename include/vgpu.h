@@ -104,6 +104,8 @@ int vgpu_victim_scan(uint64_t d_table, uint32_t n, uint64_t need, uint64_t max_t
 /* synthetic workload kernels (SURVEY.md §8d cfg 3): word j of buffer i = splitmix64((i << 32) + j) */
 int vgpu_wl_fill(uint64_t dptr, uint64_t nwords, uint64_t buf_index, void *stream);
 int vgpu_wl_touch(uint64_t dptr, uint64_t nwords, void *stream);                         /* x += 1 */
+/* x += 1 on nptr buffers of nwords each, reached through a table of device pointers that itself lives in device memory */
+int vgpu_wl_touch_indirect(uint64_t d_table, uint32_t nptr, uint64_t nwords, void *stream);
 int vgpu_wl_verify(uint64_t dptr, uint64_t nwords, uint64_t buf_index, uint64_t added, uint64_t d_mismatch_counter, void *stream);
 
 /* ---- swap engine (new functionality behind CUDA_OVERSUBSCRIBE; reference switch cuMemoryAllocate@0x315da) */

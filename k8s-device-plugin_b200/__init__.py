@@ -111,6 +111,7 @@ ABI = {
     "vgpu_wl_fill": (_INT, [_U64, _U64, _U64, _P]),
     "vgpu_wl_touch": (_INT, [_U64, _U64, _P]),
     "vgpu_wl_verify": (_INT, [_U64, _U64, _U64, _U64, _U64, _P]),
+    "vgpu_wl_touch_indirect": (_INT, [_U64, _U32, _U64, _P]),
     "vgpu_swap_create": (_INT, [_INT, C.POINTER(SwapConfig), C.POINTER(_P)]),
     "vgpu_swap_destroy": (None, [_P]),
     "vgpu_swap_alloc": (_INT, [_P, _U64, C.POINTER(_U64)]),

@@ -218,6 +218,16 @@ VGPU_API int vgpu_wl_touch(uint64_t dptr, uint64_t nwords, void *stream) {
     void *a[] = {&dptr, &nwords};
     return wl_launch(k->wl_touch, nwords / 2, a, stream, k->sm_count);
 }
+VGPU_API int vgpu_wl_touch_indirect(uint64_t d_table, uint32_t nptr, uint64_t nwords, void *stream) {
+    const Kernels *k = kernels_for_current_ctx();
+    if (!k) return CUDA_ERROR_NOT_INITIALIZED;
+    if (nptr == 0) return CUDA_SUCCESS;
+    void *a[] = {&d_table, &nptr, &nwords};
+    uint64_t bx = (nwords + 255) / 256, cap = (uint64_t)k->sm_count * 4;
+    if (bx > cap) bx = cap;
+    if (bx == 0) bx = 1;
+    return drv().cuLaunchKernel(k->wl_touch_indirect, (unsigned)bx, nptr < 65535u ? nptr : 65535u, 1, 256, 1, 1, 0, static_cast<CUstream>(stream), a, nullptr);
+}
 VGPU_API int vgpu_wl_verify(uint64_t dptr, uint64_t nwords, uint64_t buf_index, uint64_t added, uint64_t d_counter, void *stream) {
     const Kernels *k = kernels_for_current_ctx();
     if (!k) return CUDA_ERROR_NOT_INITIALIZED;

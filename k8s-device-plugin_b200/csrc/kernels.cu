@@ -514,6 +514,14 @@ extern "C" __global__ void vgpu_wl_touch(uint64_t *buf, uint64_t nwords) {
     }
     if ((nwords & 1) && blockIdx.x == 0 && threadIdx.x == 0) buf[nwords - 1] += 1;
 }
+// the touch through a POINTER TABLE in device memory (what cuBLAS batched GEMM, torch._foreach_* and NCCL do with their
+// operands): the launch parameters hold the table's address only, so no argument scan can see the buffers
+extern "C" __global__ void vgpu_wl_touch_indirect(uint64_t *const *__restrict__ table, uint32_t nptr, uint64_t nwords) {
+    for (uint32_t b = blockIdx.y; b < nptr; b += gridDim.y) {
+        uint64_t *buf = table[b];
+        for (uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < nwords; j += (uint64_t)gridDim.x * blockDim.x) buf[j] += 1;
+    }
+}
 extern "C" __global__ void vgpu_wl_verify(const uint64_t *buf, uint64_t nwords, uint64_t buf_index, uint64_t added,
                                           unsigned long long *mismatches) {
     unsigned long long bad = 0;

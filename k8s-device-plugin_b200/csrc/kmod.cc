@@ -51,7 +51,7 @@ const Kernels *kernels_for_current_ctx() {
         {"vgpu_pack_tma", &k->pack_tma}, {"vgpu_pack_generic", &k->pack_generic},
         {"vgpu_victim_init", &k->victim_init}, {"vgpu_victim_hist", &k->victim_hist}, {"vgpu_victim_emit", &k->victim_emit}, {"vgpu_victim_count", &k->victim_count}, {"vgpu_victim_small", &k->victim_small},
         {"vgpu_stamp", &k->stamp}, {"vgpu_copy16", &k->copy16}, {"vgpu_wl_fill", &k->wl_fill}, {"vgpu_wl_touch", &k->wl_touch},
-        {"vgpu_wl_verify", &k->wl_verify}, {"vgpu_wl_empty", &k->wl_empty},
+        {"vgpu_wl_verify", &k->wl_verify}, {"vgpu_wl_empty", &k->wl_empty}, {"vgpu_wl_touch_indirect", &k->wl_touch_indirect},
     };
     for (auto &t : tab) {
         r = d.cuModuleGetFunction(t.fn, k->mod, t.name);

@@ -15,7 +15,7 @@ struct Kernels {
     CUfunction pack_tma = nullptr, pack_generic = nullptr;
     CUfunction victim_init = nullptr, victim_hist = nullptr, victim_emit = nullptr, victim_count = nullptr, victim_small = nullptr;
     CUfunction stamp = nullptr, copy16 = nullptr;
-    CUfunction wl_fill = nullptr, wl_touch = nullptr, wl_verify = nullptr, wl_empty = nullptr;
+    CUfunction wl_fill = nullptr, wl_touch = nullptr, wl_verify = nullptr, wl_empty = nullptr, wl_touch_indirect = nullptr;
     int sm_count = 0;
 };
 

@@ -169,6 +169,19 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
     }
     if (r != CUDA_SUCCESS) { LOG_ERROR("cuMemAddressReserve failed: %d %s", (int)r, cu_err(r)); return false; }
     cfg_.arena_bytes = want;
+    if (cfg_.host_backed) {
+        CUmemAllocationProp hp = {};
+        hp.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        hp.location.type = CU_MEM_LOCATION_TYPE_HOST_NUMA;
+        hp.location.id = numa_node_ >= 0 ? numa_node_ : 0;
+        size_t hg = 0;
+        if (d.cuMemGetAllocationGranularity(&hg, &hp, CU_MEM_ALLOC_GRANULARITY_MINIMUM) != CUDA_SUCCESS || hg > gran_ ||
+            d.cuMemAddressReserve(&harena_, want, align, 0, 0) != CUDA_SUCCESS) {
+            LOG_ERROR("VGPU_SWAP_HOST_BACKED: this driver has no host-located VMM memory (CU_MEM_LOCATION_TYPE_HOST_NUMA); evicted ranges stay unmapped");
+            cfg_.host_backed = false;
+            harena_ = 0;
+        }
+    }
     va_free_[0] = want;
     owner_.assign(want / gran_, -1);
 
@@ -229,6 +242,7 @@ SwapEngine::~SwapEngine() {
     for (CUstream s : {s_scan_, s_pack_, s_unpack_, s_out_, s_in_}) if (s) d.cuStreamSynchronize(s);
     for (size_t i = 0; i < rows_.size(); i++) {
         if (side_[i].has_handle) { d.cuMemUnmap(rows_[i].base, side_[i].mapped); d.cuMemRelease(side_[i].handle); }
+        if (side_[i].has_hh) drop_host_handle(rows_[i].base, side_[i].mapped, side_[i].va_off, side_[i].hhandle, side_[i].hosted);
         if (side_[i].ready) d.cuEventDestroy_v2(side_[i].ready);
         if (side_[i].evict_done) d.cuEventDestroy_v2(side_[i].evict_done);
     }
@@ -244,6 +258,7 @@ SwapEngine::~SwapEngine() {
     if (d_tbl_) d.cuMemFree_v2(d_tbl_);
     if (h_tbl_stage_) d.cuMemFreeHost(h_tbl_stage_);
     if (arena_) d.cuMemAddressFree(arena_, cfg_.arena_bytes);
+    if (harena_) d.cuMemAddressFree(harena_, cfg_.arena_bytes);
     for (CUstream s : {s_scan_, s_pack_, s_unpack_, s_out_, s_in_}) if (s) d.cuStreamDestroy_v2(s);
 }
 
@@ -672,6 +687,37 @@ CUresult SwapEngine::obtain_phys(size_t mapped, CUmemGenericAllocationHandle *h,
     return r;
 }
 
+// Host-backed mode: the row's backing store is a host-located VMM handle, mapped for good at the alias address (what the
+// copy engines target). Costs one cuMemCreate + cuMemSetAccess of host memory (~50 us per MiB: the GPU maps system
+// memory in small pages) the first time a row is evicted.
+CUresult SwapEngine::make_host_handle(size_t mapped, uint64_t va_off, CUmemGenericAllocationHandle *h) {
+    const DriverTable &d = drv();
+    ScopedNs t(&pst_.pager_vmm_ns);
+    CUmemAllocationProp hp = {};
+    hp.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    hp.location.type = CU_MEM_LOCATION_TYPE_HOST_NUMA;
+    hp.location.id = numa_node_ >= 0 ? numa_node_ : 0;
+    CUresult r = d.cuMemCreate(h, mapped, &hp, 0);
+    if (r != CUDA_SUCCESS) { LOG_ERROR("host-located cuMemCreate of %zu MiB failed: %d %s", mapped >> 20, (int)r, cu_err(r)); return r; }
+    r = d.cuMemMap(harena_ + va_off, mapped, 0, *h, 0);
+    if (r == CUDA_SUCCESS) {
+        CUmemAccessDesc acc = {};
+        acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        acc.location.id = dev_;
+        acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        r = d.cuMemSetAccess(harena_ + va_off, mapped, &acc, 1);
+        if (r != CUDA_SUCCESS) d.cuMemUnmap(harena_ + va_off, mapped);
+    }
+    if (r != CUDA_SUCCESS) { LOG_ERROR("mapping the host backing failed: %d %s", (int)r, cu_err(r)); d.cuMemRelease(*h); }
+    return r;
+}
+void SwapEngine::drop_host_handle(CUdeviceptr base, size_t mapped, uint64_t va_off, CUmemGenericAllocationHandle h, bool hosted) {
+    const DriverTable &d = drv();
+    if (hosted) d.cuMemUnmap(base, mapped);
+    d.cuMemUnmap(harena_ + va_off, mapped);
+    d.cuMemRelease(h);
+}
+
 void SwapEngine::note_vmm_call(const char *what, uint64_t ns) {
     pst_.vmm_calls++;
     if (ns > pst_.vmm_max_ns) pst_.vmm_max_ns = ns;
@@ -839,8 +885,10 @@ CUresult SwapEngine::choose_victims(Lock &lk, uint64_t shortage, std::vector<uin
         uint64_t found_bytes = 0;
         bool insufficient = false;
         int launches = 0;
-        // the table holds requested sizes, the shortage is in mapped (granule-rounded) bytes: ask for a little more per row
-        uint64_t ask = shortage * (uint64_t)(cfg_.scan_lookahead ? cfg_.scan_lookahead : 1);
+        // Look ahead in units of what is being brought in, not of the shortage: the cap is rarely a multiple of the granule
+        // (the container's small allocations come out of it byte by byte), so a shortage can be a few bytes — and the
+        // next admissions will each need a whole buffer's worth again.
+        uint64_t ask = std::max<uint64_t>(shortage, scan_unit_) * (uint64_t)(cfg_.scan_lookahead ? cfg_.scan_lookahead : 1);
         uint32_t n = (uint32_t)rows_.size();
         uint64_t tick = tick_;
         CUdeviceptr tbl = d_tbl_;
@@ -882,7 +930,11 @@ void SwapEngine::begin_evict_locked(const std::vector<uint32_t> &victims, std::v
         OutItem it;
         it.row = v; it.base = rows_[v].base; it.len = round_up(rows_[v].size, 256); it.mapped = s.mapped;
         it.host_off = s.host_off; it.has_host = s.has_host;
+        it.va_off = s.va_off; it.hh = s.hhandle; it.has_hh = s.has_hh;
         it.copy = s.dirty;                        // clean (block still valid) or never written: nothing to copy
+        // host-backed mode exists for accesses the hook cannot see — it cannot see their writes either: only a range the
+        // application declared read-mostly is trusted to be clean
+        if (cfg_.host_backed && !(s.read_mostly && s.has_host && !s.dirty)) it.copy = true;
         collect_waits_locked((int)v, &it.wait);
         if (s.evict_done) it.wait.push_back(s.evict_done);       // an earlier page-out of this row may still be writing its block
         rows_[v].state = VGPU_ST_PAGED_OUT;
@@ -907,7 +959,14 @@ CUresult SwapEngine::evict_direct(Lock &lk, const std::vector<uint32_t> &victims
     CUresult rc = CUDA_SUCCESS;
     for (OutItem &it : items) {
         it.done = get_event();
-        if (it.copy && !it.has_host) {
+        if (cfg_.host_backed) {
+            if (!it.has_hh) {
+                // every evicted row gets its host backing, copied or not: its own range will be re-mapped onto it
+                if (make_host_handle(it.mapped, it.va_off, &it.hh) != CUDA_SUCCESS) { rc = CUDA_ERROR_OUT_OF_MEMORY; it.failed = true; put_event(it.done); it.done = nullptr; continue; }
+                it.has_hh = true;
+            }
+            if (it.copy) it.has_host = true;
+        } else if (it.copy && !it.has_host) {
             if (!host_alloc(it.len, &it.host_off)) {
                 relock(lk);
                 bool ok = reclaim_host_blocks(lk, it.len);
@@ -920,11 +979,12 @@ CUresult SwapEngine::evict_direct(Lock &lk, const std::vector<uint32_t> &victims
         ScopedNs t_issue(&pst_.pager_issue_ns);
         for (CUevent e : it.wait) d.cuStreamWaitEvent(s, e, 0);
         if (it.copy) {
-            unsigned char *hp = host_ptr(it.host_off);
+            unsigned char *hp = cfg_.host_backed ? nullptr : host_ptr(it.host_off);
             bool tr = trace_begin(0, (int)it.row, s);
             for (uint64_t o = 0; o < it.len; o += cfg_.copy_bytes) {
                 uint64_t n = std::min<uint64_t>(cfg_.copy_bytes, it.len - o);
-                CUresult r = d.cuMemcpyDtoHAsync_v2(hp + o, it.base + o, n, s);
+                CUresult r = cfg_.host_backed ? d.cuMemcpyDtoDAsync_v2(harena_ + it.va_off + o, it.base + o, n, s)     // the alias range IS host memory
+                                              : d.cuMemcpyDtoHAsync_v2(hp + o, it.base + o, n, s);
                 if (r != CUDA_SUCCESS) { LOG_ERROR("page-out copy failed: %d %s", (int)r, cu_err(r)); rc = r; break; }
             }
             if (tr) trace_end(s);
@@ -950,6 +1010,7 @@ CUresult SwapEngine::evict_direct(Lock &lk, const std::vector<uint32_t> &victims
         }
         s.host_off = it.host_off;
         s.has_host = it.has_host;
+        s.hhandle = it.hh; s.has_hh = it.has_hh;
         if (it.copy) s.dirty = false;              // once the copy is done the block equals the HBM content
         if (s.ready) { put_event(s.ready); s.ready = nullptr; }   // its waiters are enqueued; the record they refer to is fixed
         if (s.evict_done) put_event(s.evict_done);
@@ -967,6 +1028,7 @@ void SwapEngine::begin_load_locked(int row, bool prefetch, InItem *it) {
     Side &s = side_[row];
     it->row = row; it->base = rows_[row].base; it->len = round_up(rows_[row].size, 256); it->mapped = s.mapped;
     it->host_off = s.host_off; it->has_host = s.has_host; it->prefetch = prefetch;
+    it->va_off = s.va_off; it->hosted = s.hosted;
     it->after = nullptr;
     s.phase = PH_LOADING;
     resident_mapped_ += s.mapped;
@@ -976,6 +1038,7 @@ void SwapEngine::commit_load_locked(InItem &it) {
     Side &s = side_[it.row];
     s.handle = it.h;
     s.has_handle = true;
+    s.hosted = false;
     s.phase = PH_IDLE;
     s.fail = CUDA_SUCCESS;
     s.dirty = false;
@@ -997,6 +1060,7 @@ void SwapEngine::fail_load_locked(InItem &it, CUresult rc) {
     resident_mapped_ -= s.mapped;
     if (it.ready) put_event(it.ready);
     it.ready = nullptr;
+    s.hosted = it.hosted;                        // false when its host mapping was already taken down for this attempt
     s.phase = PH_IDLE;
     s.fail = rc;
     s.demand = false;
@@ -1038,6 +1102,11 @@ CUresult SwapEngine::load_direct(Lock &lk, std::vector<InItem> &items) {
         it.rc = obtain_phys(it.mapped, &it.h, &pressure);
         pressure_seen |= pressure;
         if (it.rc != CUDA_SUCCESS) continue;
+        if (it.hosted) {                             // host-backed mode: the range maps the host backing right now
+            std::vector<std::pair<CUdeviceptr, size_t>> one{{it.base, it.mapped}};
+            unmap_batch(one);
+            it.hosted = false;
+        }
         {
             ScopedNs t(&pst_.pager_vmm_ns), t2(&pst_.pager_map_ns);
             it.rc = d.cuMemMap(it.base, it.mapped, 0, it.h, 0);
@@ -1057,11 +1126,12 @@ CUresult SwapEngine::load_direct(Lock &lk, std::vector<InItem> &items) {
         if (!it.ready) it.ready = get_event();
         ScopedNs t_issue(&pst_.pager_issue_ns);
         if (it.after) d.cuStreamWaitEvent(s_in_, it.after, 0);
-        unsigned char *hp = host_ptr(it.host_off);
+        unsigned char *hp = cfg_.host_backed ? nullptr : host_ptr(it.host_off);
         bool tr = trace_begin(1, it.row, s_in_);
         for (uint64_t o = 0; o < it.len; o += cfg_.copy_bytes) {
             uint64_t n = std::min<uint64_t>(cfg_.copy_bytes, it.len - o);
-            CUresult r = d.cuMemcpyHtoDAsync_v2(it.base + o, hp + o, n, s_in_);
+            CUresult r = cfg_.host_backed ? d.cuMemcpyDtoDAsync_v2(it.base + o, harena_ + it.va_off + o, n, s_in_)
+                                          : d.cuMemcpyHtoDAsync_v2(it.base + o, hp + o, n, s_in_);
             if (r != CUDA_SUCCESS) { LOG_ERROR("page-in copy failed: %d %s", (int)r, cu_err(r)); it.rc = r; break; }
         }
         if (tr) trace_end(s_in_);
@@ -1332,16 +1402,24 @@ bool SwapEngine::step_zombies(Lock &lk) {
     }
     if (ready_rows.empty()) return false;
     std::vector<std::pair<CUdeviceptr, size_t>> ranges;
-    for (uint32_t r : ready_rows) ranges.emplace_back(rows_[r].base, side_[r].mapped);
+    struct DropHost { CUdeviceptr base; size_t mapped; uint64_t va_off; CUmemGenericAllocationHandle hh; bool hosted; };
+    std::vector<DropHost> drops;
+    for (uint32_t r : ready_rows) {
+        if (side_[r].has_handle) ranges.emplace_back(rows_[r].base, side_[r].mapped);
+        if (side_[r].has_hh) drops.push_back(DropHost{rows_[r].base, side_[r].mapped, side_[r].va_off, side_[r].hhandle, side_[r].hosted});
+    }
     lk.unlock();
     unmap_batch(ranges);
+    for (DropHost &x : drops) drop_host_handle(x.base, x.mapped, x.va_off, x.hh, x.hosted);
     relock(lk);
     for (uint32_t r : ready_rows) {
         Side &s = side_[r];
+        s.has_hh = false; s.hosted = false;
+        if (!s.has_handle) { if (s.has_host && !cfg_.host_backed) release_host_range(s.host_off, round_up(rows_[r].size, 256)); s.has_host = false; retire_row_locked((int)r); continue; }
         pool_phys(s.mapped, s.handle);
         s.has_handle = false;
         resident_mapped_ -= s.mapped;
-        if (s.has_host) release_host_range(s.host_off, round_up(rows_[r].size, 256));
+        if (s.has_host && !cfg_.host_backed) release_host_range(s.host_off, round_up(rows_[r].size, 256));
         s.has_host = false;
         retire_row_locked((int)r);
     }
@@ -1377,12 +1455,30 @@ bool SwapEngine::step_reap(Lock &lk) {
     }
     reap_defer_ = 0;
     std::vector<std::pair<CUdeviceptr, size_t>> ranges;
-    for (uint32_t r : done) ranges.emplace_back(rows_[r].base, side_[r].mapped);
+    struct Rehost { CUdeviceptr base; size_t mapped; CUmemGenericAllocationHandle hh; bool ok; };
+    std::vector<Rehost> rehost;
+    for (uint32_t r : done) {
+        ranges.emplace_back(rows_[r].base, side_[r].mapped);
+        if (cfg_.host_backed && side_[r].has_hh) rehost.push_back(Rehost{rows_[r].base, side_[r].mapped, side_[r].hhandle, false});
+    }
     lk.unlock();
     unmap_batch(ranges);
+    if (!rehost.empty()) {
+        // host-backed mode: the range does not stay a hole — it is mapped onto the row's host backing, so that an access the
+        // hook never saw is served over PCIe instead of killing the context (between the two calls it IS a hole: ~1 ms)
+        ScopedNs t(&pst_.pager_vmm_ns);
+        std::vector<std::pair<CUdeviceptr, size_t>> hr;
+        for (Rehost &x : rehost) {
+            x.ok = d.cuMemMap(x.base, x.mapped, 0, x.hh, 0) == CUDA_SUCCESS;
+            if (x.ok) hr.emplace_back(x.base, x.mapped);
+        }
+        if (set_access_batch(hr) != CUDA_SUCCESS) for (Rehost &x : rehost) if (x.ok) { d.cuMemUnmap(x.base, x.mapped); x.ok = false; }
+    }
     relock(lk);
+    size_t rh = 0;
     for (uint32_t r : done) {
         Side &s = side_[r];
+        if (cfg_.host_backed && s.has_hh) s.hosted = rehost[rh++].ok;
         pool_phys(s.mapped, s.handle);
         s.has_handle = false;
         evicting_mapped_ -= s.mapped;
@@ -1407,6 +1503,7 @@ bool SwapEngine::step_demand(Lock &lk) {
     if (demand_q_.empty()) return false;
     const int row = demand_q_.front().row;
     const uint64_t need = side_[row].mapped;
+    scan_unit_ = need;
     if (pressure_ && cfg_.resident_cap < quota_cap_ && (++pressure_probe_ & 31u) == 0) {
         // probe upwards: the other tenants may have let go; a failed cuMemCreate simply lowers the cap again
         cfg_.resident_cap = std::min(quota_cap_, cfg_.resident_cap + need);
@@ -1457,7 +1554,7 @@ bool SwapEngine::step_demand(Lock &lk) {
                   (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(shortage >> 20), (unsigned long)(evictable >> 20));
         return fail(CUDA_ERROR_OUT_OF_MEMORY);
     }
-    if (evicting_mapped_ == 0) {
+    if (evicting_mapped_ == 0 && !cfg_.host_backed) {
         demand_q_.pop_front();
         swap_staged(lk, row, victims);           // latency path
     } else if (evict_direct(lk, victims) != CUDA_SUCCESS) {   // the pipeline is running: add to it and wait for the reap
@@ -1683,6 +1780,14 @@ CUresult SwapEngine::free(CUdeviceptr dptr) {
     if (rows_[row].state & VGPU_ST_RESIDENT) {
         // still mapped, maybe still in use by queued work: the pager unmaps it once its last users are done and only then
         // hands the address range out again
+        rows_[row].state = VGPU_ST_FREE;
+        rows_[row].size = 0;
+        mark_dirty(row);
+        s.phase = PH_ZOMBIE;
+        zombies_.push_back((uint32_t)row);
+        kick_pager_locked();
+    } else if (s.has_hh) {
+        // host-backed mode: the range (and the alias range) still map the host backing — VMM calls are the pager's
         rows_[row].state = VGPU_ST_FREE;
         rows_[row].size = 0;
         mark_dirty(row);

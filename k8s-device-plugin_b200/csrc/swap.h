@@ -178,6 +178,13 @@ class SwapEngine {
         CUevent evict_done = nullptr;   // after it the row's physical memory is no longer read by its page-out
         int out_slot = -1;       // staging slot of the last staged page-out chunk of this row ...
         uint64_t out_seq = 0;    // ... and that slot's use counter at the time (stale => the D2H is known complete)
+        // host-backed mode (VGPU_SWAP_HOST_BACKED=1): the pinned block is a host-located VMM handle of its own, mapped for good at
+        // the row's alias address (harena_ + va_off, the DMA target) and, WHILE THE ROW IS PAGED OUT, also at the row's own
+        // address — an access the hook could not see (a pointer table in device memory) then reads and writes host memory
+        // over PCIe instead of faulting on an unmapped range, which is what UVM gives the reference
+        CUmemGenericAllocationHandle hhandle = 0;
+        bool has_hh = false;
+        bool hosted = false;     // the row's own range currently maps hhandle
         uint32_t gen = 0;        // bumped when the row index is recycled (stale queue entries are skipped)
         int retries = 0;         // page-in attempts that met a device with less memory than the cap promises
     };
@@ -208,8 +215,8 @@ class SwapEngine {
     bool step_demand(Lock &lk);
     bool step_prefetch(Lock &lk);
     bool step_evict_ahead(Lock &lk);
-    struct OutItem { uint32_t row; CUdeviceptr base; uint64_t len; size_t mapped; uint64_t host_off; bool has_host, copy; std::vector<CUevent> wait; CUevent done = nullptr; int out_slot = -1; uint64_t out_seq = 0; bool failed = false; };
-    struct InItem { int row; CUdeviceptr base; uint64_t len; size_t mapped; uint64_t host_off; bool has_host; bool prefetch; CUmemGenericAllocationHandle h = 0; CUevent ready = nullptr;
+    struct OutItem { uint32_t row; CUdeviceptr base; uint64_t len; size_t mapped; uint64_t host_off; bool has_host, copy; uint64_t va_off = 0; CUmemGenericAllocationHandle hh = 0; bool has_hh = false; std::vector<CUevent> wait; CUevent done = nullptr; int out_slot = -1; uint64_t out_seq = 0; bool failed = false; };
+    struct InItem { int row; CUdeviceptr base; uint64_t len; size_t mapped; uint64_t host_off; bool has_host; bool prefetch; uint64_t va_off = 0; bool hosted = false; CUmemGenericAllocationHandle h = 0; CUevent ready = nullptr;
                     CUevent after = nullptr; CUresult rc = CUDA_SUCCESS; };
     CUresult choose_victims(Lock &lk, uint64_t shortage, std::vector<uint32_t> *victims, uint64_t *evictable);
     void begin_evict_locked(const std::vector<uint32_t> &victims, std::vector<OutItem> *items);
@@ -221,6 +228,8 @@ class SwapEngine {
     bool requeue_under_pressure_locked(int row, bool was_demand, size_t free_dev);
     CUresult swap_staged(Lock &lk, int row, const std::vector<uint32_t> &victims);
     void unmap_batch(std::vector<std::pair<CUdeviceptr, size_t>> &ranges);
+    CUresult make_host_handle(size_t mapped, uint64_t va_off, CUmemGenericAllocationHandle *h);
+    void drop_host_handle(CUdeviceptr base, size_t mapped, uint64_t va_off, CUmemGenericAllocationHandle h, bool hosted);
     CUresult set_access_batch(std::vector<std::pair<CUdeviceptr, size_t>> &ranges);
     CUresult obtain_phys(size_t mapped, CUmemGenericAllocationHandle *h, bool *pressure);
     void pool_phys(size_t mapped, CUmemGenericAllocationHandle h);
@@ -270,6 +279,7 @@ class SwapEngine {
     const Kernels *k_ = nullptr;
     size_t gran_ = 2u << 20;
     CUdeviceptr arena_ = 0;
+    CUdeviceptr harena_ = 0;                        // host-backed mode: alias range, same size and layout as the arena
     CUcontext ctx_ = nullptr;
     bool ctx_warned_ = false;
 
@@ -329,6 +339,7 @@ class SwapEngine {
     std::unique_ptr<VictimScanner> scanner_;
     std::mutex ev_mu_;
     std::vector<CUevent> ev_pool_;                  // (ev_mu_) recycled events: page-in / eviction completions, pack markers
+    uint64_t scan_unit_ = 0;                        // mapped size of the last demanded row: the unit of the scan look-ahead
     uint32_t reap_defer_ = 0;                       // polls a partial reap batch has been held back
     bool unmap_runs_ok_ = true;                     // one cuMemUnmap may span several adjacent mappings (probed at run time)
     // victims selected by the last scan beyond what was needed then, in LRU order. They stay the exact LRU prefix for

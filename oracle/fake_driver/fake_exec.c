@@ -71,20 +71,20 @@ CUresult fx_address_free(CUdeviceptr p, size_t n) { munmap((void *)(uintptr_t)p,
 CUresult fx_mem_create(unsigned long long *h, size_t n, const void *prop, unsigned long long flags) {
     (void)flags;
     if (!h || !n || (n % GRAN)) return CUDA_ERROR_INVALID_VALUE;
-    int dev = 0;
-    if (prop) { const int *pi = (const int *)prop; if (pi[2] == 1) dev = pi[3]; }   /* location {type, id} */
-    if (fake_charge(dev, (int64_t)n)) return CUDA_ERROR_OUT_OF_MEMORY;
+    int dev = 0, host = 0;
+    if (prop) { const int *pi = (const int *)prop; if (pi[2] == 1) dev = pi[3]; else if (pi[2] == 2 || pi[2] == 3) host = 1; }   /* location {type, id}: 2/3 = host memory */
+    if (!host && fake_charge(dev, (int64_t)n)) return CUDA_ERROR_OUT_OF_MEMORY;
     fx_handle *x = calloc(1, sizeof *x);
     x->fd = memfd_create("fake-gpu-phys", 0);
-    if (x->fd < 0 || ftruncate(x->fd, (off_t)n) != 0) { fake_charge(dev, -(int64_t)n); if (x->fd >= 0) close(x->fd); free(x); return CUDA_ERROR_OUT_OF_MEMORY; }
-    x->size = n; x->dev = dev;
+    if (x->fd < 0 || ftruncate(x->fd, (off_t)n) != 0) { if (!host) fake_charge(dev, -(int64_t)n); if (x->fd >= 0) close(x->fd); free(x); return CUDA_ERROR_OUT_OF_MEMORY; }
+    x->size = n; x->dev = host ? -1 : dev;
     *h = (unsigned long long)(uintptr_t)x;
     return CUDA_SUCCESS;
 }
 CUresult fx_mem_release(unsigned long long h) {
     fx_handle *x = (fx_handle *)(uintptr_t)h;
     if (!x) return CUDA_ERROR_INVALID_VALUE;
-    fake_charge(x->dev, -(int64_t)x->size);
+    if (x->dev >= 0) fake_charge(x->dev, -(int64_t)x->size);
     close(x->fd);           /* existing mappings keep the pages alive until unmapped, like a retained CUDA allocation */
     free(x);
     return CUDA_SUCCESS;
@@ -131,7 +131,7 @@ CUresult fx_event_elapsed(float *ms, CUevent a, CUevent b) { *ms = (float)((doub
 CUresult fx_event_destroy(CUevent e) { free(e); return CUDA_SUCCESS; }
 
 /* ------------------------------------------------------------------ functions by name */
-enum { K_OTHER, K_PACK, K_VINIT, K_VHIST, K_VCOUNT, K_VEMIT, K_VSMALL, K_STAMP, K_FILL, K_TOUCH, K_VERIFY, K_EMPTY, K_COPY16 };
+enum { K_OTHER, K_PACK, K_VINIT, K_VHIST, K_VCOUNT, K_VEMIT, K_VSMALL, K_STAMP, K_FILL, K_TOUCH, K_VERIFY, K_EMPTY, K_COPY16, K_TOUCH_IND };
 typedef struct { const char *name; int kind; int nparam; size_t psize[8]; } fx_func;
 static fx_func g_funcs[] = {
     {"vgpu_pack_tma", K_PACK, 1, {sizeof(VgpuPackParams)}}, {"vgpu_pack_generic", K_PACK, 1, {sizeof(VgpuPackParams)}},
@@ -139,7 +139,7 @@ static fx_func g_funcs[] = {
     {"vgpu_victim_count", K_VCOUNT, 5, {8, 4, 8, 4, 4}}, {"vgpu_victim_emit", K_VEMIT, 7, {8, 4, 8, 4, 4, 8, 4}},
     {"vgpu_victim_small", K_VSMALL, 8, {8, 4, 8, 8, 4, 4, 8, 4}}, {"vgpu_stamp", K_STAMP, 1, {8}},
     {"vgpu_wl_fill", K_FILL, 3, {8, 8, 8}}, {"vgpu_wl_touch", K_TOUCH, 2, {8, 8}}, {"vgpu_wl_verify", K_VERIFY, 5, {8, 8, 8, 8, 8}},
-    {"vgpu_wl_empty", K_EMPTY, 0, {0}}, {"vgpu_empty", K_EMPTY, 0, {0}}, {"vgpu_copy16", K_COPY16, 3, {8, 8, 8}},
+    {"vgpu_wl_empty", K_EMPTY, 0, {0}}, {"vgpu_empty", K_EMPTY, 0, {0}}, {"vgpu_copy16", K_COPY16, 3, {8, 8, 8}}, {"vgpu_wl_touch_indirect", K_TOUCH_IND, 3, {8, 4, 8}},
 };
 static fx_func g_other = {"?", K_OTHER, 0, {0}};
 CUresult fx_get_function(CUfunction *f, const char *name) {
@@ -214,6 +214,9 @@ CUresult fx_launch(CUfunction f, void **params) {
         victim_select(ARG(const VgpuEntry *, 0), ARG(uint32_t, 1), st, st->need, ARG(uint32_t *, 5), ARG(uint32_t, 6)); break; }
     case K_VSMALL: victim_select(ARG(const VgpuEntry *, 0), ARG(uint32_t, 1), ARG(VgpuScanState *, 2), ARG(uint64_t, 3), ARG(uint32_t *, 6), ARG(uint32_t, 7)); break;
     case K_STAMP: *ARG(volatile uint64_t *, 0) = now_ns(); break;
+    case K_TOUCH_IND: { uint64_t **t = ARG(uint64_t **, 0); uint32_t np = ARG(uint32_t, 1); uint64_t n = ARG(uint64_t, 2);
+        for (uint32_t b = 0; b < np; b++) for (uint64_t j = 0; j < n; j++) t[b][j] += 1;
+        break; }
     case K_COPY16: memmove(ARG(void *, 0), ARG(const void *, 1), (size_t)ARG(uint64_t, 2) * 16); break;
     case K_FILL: { uint64_t *b = ARG(uint64_t *, 0), n = ARG(uint64_t, 1), bi = ARG(uint64_t, 2); for (uint64_t j = 0; j < n; j++) b[j] = splitmix64((bi << 32) + j); break; }
     case K_TOUCH: { uint64_t *b = ARG(uint64_t *, 0), n = ARG(uint64_t, 1); for (uint64_t j = 0; j < n; j++) b[j] += 1; break; }

@@ -170,6 +170,44 @@ def test_swapped_bytes_verified_on_the_host_with_the_drivers_own_copy():
     sw.close()
 
 
+_POINTER_TABLE = r"""
+import ctypes as C, json, os, sys
+sys.path.insert(0, os.environ["VGPU_ROOT"])
+import torch
+import k8s_device_plugin_b200 as v
+torch.zeros(1, device="cuda")
+L = v.lib(); st = torch.cuda.current_stream().cuda_stream; stp = C.c_void_p(st)
+M = 1 << 20
+sw = v.Swap(resident_cap=128 * M)
+n, nbytes = 8, 64 * M                                     # 512 MiB live under a 128 MiB quota
+bufs = [sw.alloc(nbytes) for _ in range(n)]
+for i, p in enumerate(bufs):
+    sw.acquire([p], st); assert L.vgpu_wl_fill(p, nbytes // 8, i, stp) == 0; sw.release([p], st)
+torch.cuda.synchronize(); sw.drain()
+paged_out = sum(1 for e in sw.table() if e.state == 2)
+table = torch.tensor(bufs, dtype=torch.int64, device="cuda")                    # the pointer table lives in DEVICE memory
+assert L.vgpu_wl_touch_indirect(table.data_ptr(), n, nbytes // 8, stp) == 0     # no acquire: the engine cannot see the operands
+torch.cuda.synchronize()
+cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+for i, p in enumerate(bufs):
+    sw.acquire([p], st); assert L.vgpu_wl_verify(p, nbytes // 8, i, 1, cnt.data_ptr(), stp) == 0; sw.release([p], st)
+torch.cuda.synchronize()
+print(json.dumps({"bad": int(cnt.item()), "paged_out_before": paged_out}))
+"""
+
+
+def test_kernel_dereferencing_a_device_side_pointer_table_reads_paged_out_buffers(tmp_path):
+    """VERDICT r1 'missing' #1, the done-criterion: a kernel reaches PAGED-OUT buffers through a pointer table in device
+    memory and reads/writes the right bytes. In host-backed mode (VGPU_SWAP_HOST_BACKED=1) an evicted range maps its host
+    backing — a host-located VMM handle — so the access goes over PCIe instead of hitting an unmapped range."""
+    import json, os, subprocess, sys
+    env = dict(os.environ, VGPU_ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), VGPU_SWAP_HOST_BACKED="1")
+    r = subprocess.run([sys.executable, "-c", _POINTER_TABLE], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["bad"] == 0 and out["paged_out_before"] >= 5, out
+
+
 def test_ragged_sizes_and_multi_buffer_admission():
     sw = v.Swap(resident_cap=128 * MiB, chunk_bytes=8 * MiB, ring_slots=2)
     sizes = [3 * MiB + 8, 17 * MiB + 4096, 2 * MiB + 16, 40 * MiB, 5 * MiB + 1000 * 8, 33 * MiB, 9 * MiB + 8, 26 * MiB]

@@ -112,3 +112,28 @@ def test_pytorch_oversubscribes_through_the_swap_engine(tmp_path):
                PYTORCH_NO_CUDA_MEMORY_CACHING="1")           # one cudaMalloc per tensor: the engine sees whole buffers
     out = _torch_under_hook(tmp_path, _SWAP, env, timeout=600)
     assert out["ok"] is True
+
+
+_FOREACH = r"""
+import json, torch
+# 12 tensors of 512 MiB = 6 GiB live under a 3 GiB quota; torch._foreach_add_ reaches them through multi_tensor_apply,
+# whose kernels carry the tensors' addresses inside a metadata struct (and, for long lists, in device memory)
+bufs = [torch.full((128 << 20,), float(i), dtype=torch.float32, device="cuda") for i in range(12)]
+for rnd in range(3):
+    torch._foreach_add_(bufs, 1.0)
+torch.cuda.synchronize()
+ok = all(bool((b[::4097] == i + 3).all().item()) and float(b[0].item()) == i + 3 and float(b[-1].item()) == i + 3 for i, b in enumerate(bufs))
+print(json.dumps({"ok": ok}))
+"""
+
+
+@pytest.mark.parametrize("host_backed", ["1", "0"])
+def test_pytorch_foreach_over_twice_the_quota(tmp_path, host_backed):
+    """VERDICT r1 'missing' #1: torch._foreach_add_ over 6 GiB under a 3 GiB quota. With VGPU_SWAP_HOST_BACKED=1 every
+    evicted tensor's range maps its host backing, so even an operand no argument scan can see is served (slowly) instead
+    of faulting; in the default mode the multi_tensor_apply metadata travels in the kernel parameters and the scan finds
+    the addresses there."""
+    env = dict(v.hook_env(limit_mib=3072, oversubscribe=True, cache_path=str(tmp_path / f"fe{host_backed}.cache")), VGPU_PRINT_STATS="1",
+               PYTORCH_NO_CUDA_MEMORY_CACHING="1", VGPU_SWAP_HOST_BACKED=host_backed)
+    out = _torch_under_hook(tmp_path, _FOREACH, env, timeout=900)
+    assert out["ok"] is True
