@@ -228,6 +228,58 @@ bool Region::swap_counters(int dev, vgpu_swap_record_t *out) {
     return true;
 }
 
+uint64_t Region::swap_live(int dev, int32_t except_pid) const {
+    if (!ext_) return 0;
+    uint64_t sum = 0;
+    for (int i = 0; i < VGPU_REGION_EXT_RECORDS; i++) {
+        const vgpu_swap_record_t &rec = ext_->swap[i];
+        if (rec.pid == 0 || rec.dev != dev || rec.pid == except_pid) continue;
+        sum += __atomic_load_n(&rec.live_bytes, __ATOMIC_RELAXED);
+    }
+    return sum;
+}
+
+uint64_t Region::swap_reserve(int32_t pid, int dev, uint64_t want_total, uint64_t live_mapped, uint64_t overhead, bool *granted, int *engines) {
+    *granted = false;
+    if (engines) *engines = 1;
+    if (!ext_) { *granted = true; return ~0ull; }
+    lock();
+    const uint64_t lim = r_->limit[dev];
+    vgpu_swap_record_t *mine = nullptr;
+    uint64_t live_all = 0;
+    int n = 0;
+    for (int i = 0; i < VGPU_REGION_EXT_RECORDS; i++) {
+        vgpu_swap_record_t &rec = ext_->swap[i];
+        if (rec.pid == 0 || rec.dev != dev) continue;
+        if (rec.pid == pid) { mine = &rec; rec.live_bytes = live_mapped; }
+        if (rec.live_bytes == 0 && rec.resident_bytes == 0 && rec.pid != pid) continue;   // an engine that holds nothing takes no share
+        n++;
+        live_all += rec.live_bytes;
+    }
+    if (n == 0) n = 1;
+    if (engines) *engines = n;
+    if (lim == 0) { if (mine) mine->resident_bytes = want_total; unlock(); *granted = true; return ~0ull; }
+    // non-swappable bytes of the whole container = accounted usage - every engine's live swappable bytes (the lanes use the
+    // reference's wrapping arithmetic, so the difference is read as signed)
+    int64_t fixed = (int64_t)(usage_locked(dev) - live_all);
+    if (fixed < 0) fixed = 0;
+    uint64_t taken = (uint64_t)fixed + (uint64_t)n * overhead;
+    uint64_t room = lim > taken ? lim - taken : 0;
+    uint64_t share = room / (uint64_t)n;
+    uint64_t others = 0;
+    for (int i = 0; i < VGPU_REGION_EXT_RECORDS; i++) {
+        const vgpu_swap_record_t &rec = ext_->swap[i];
+        if (rec.pid == 0 || rec.dev != dev || rec.pid == pid) continue;
+        if (rec.live_bytes == 0 && rec.resident_bytes == 0) continue;
+        uint64_t entitled = rec.live_bytes < share ? rec.live_bytes : share;
+        others += rec.resident_bytes > entitled ? rec.resident_bytes : entitled;
+    }
+    uint64_t cap = room > others ? room - others : 0;
+    if (want_total <= cap) { *granted = true; if (mine) mine->resident_bytes = want_total; }
+    unlock();
+    return cap;
+}
+
 void Region::clear_swap_records_locked(int32_t pid) {
     if (!ext_) return;
     for (int i = 0; i < VGPU_REGION_EXT_RECORDS; i++)

@@ -62,6 +62,13 @@ class Region {
     vgpu_swap_record_t *swap_record(int32_t pid, int dev);
     // sum of the live records of `dev`; out->pid = records summed. false: no extension block
     bool swap_counters(int dev, vgpu_swap_record_t *out);
+    uint64_t swap_live(int dev, int32_t except_pid = 0) const;   // live swappable bytes of the container's engines on dev (relaxed reads)
+    // Shared RESIDENT budget of the container's swap engines on one device (several processes, one quota), under the region
+    // lock: the room for swappable memory is limit - everything non-swappable - every engine's staging rings; of that an
+    // engine may hold what the OTHERS neither hold nor are entitled to (their fair share, bounded by what they have
+    // live). Grants `want_total` (publishes it as the caller's resident_bytes, i.e. reserves it) when it fits; returns the
+    // caller's cap either way. live_mapped: the caller's live swappable bytes; overhead: its staging rings.
+    uint64_t swap_reserve(int32_t pid, int dev, uint64_t want_total, uint64_t live_mapped, uint64_t overhead, bool *granted, int *engines);
 
    private:
     Region() = default;

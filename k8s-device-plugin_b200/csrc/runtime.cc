@@ -399,7 +399,8 @@ bool Runtime::charge(int dev, size_t bytes) {
     uint64_t lim = region_->limit(dev);
     SwapEngine *e = swap(dev);
     if (lim) {
-        uint64_t u = region_->usage(dev), live = e ? e->live_bytes() : 0;
+        // live swappable bytes of EVERY engine of the container on this device (sibling processes publish theirs in the region)
+        uint64_t u = region_->usage(dev), live = (e ? e->live_bytes() : 0) + region_->swap_live(dev, pid_);
         uint64_t fixed = fixed_bytes(u, live);
         if (fixed + bytes > lim) { LOG_ERROR("Device %d OOM %lu / %lu (non-swappable)", dev, (unsigned long)(fixed + bytes), (unsigned long)lim); return false; }
         if (e) e->set_resident_cap(room_for_engine(lim, fixed + bytes, e));
@@ -414,7 +415,7 @@ void Runtime::uncharge(int dev, size_t bytes) {
     uint64_t lim = region_->limit(dev);
     SwapEngine *e = swap(dev);
     if (lim && e) {
-        uint64_t u = region_->usage(dev), live = e->live_bytes();
+        uint64_t u = region_->usage(dev), live = e->live_bytes() + region_->swap_live(dev, pid_);
         uint64_t fixed = fixed_bytes(u, live);
         e->set_resident_cap(room_for_engine(lim, fixed, e));
     }
@@ -426,7 +427,7 @@ CUresult Runtime::swap_alloc(CUdeviceptr *dptr, size_t bytes, int dev) {
         std::lock_guard<std::mutex> g(swap_mu_);
         if (!swap_[dev]) {
             uint64_t lim = region_ ? region_->limit(dev) : 0;
-            uint64_t fixed = region_ ? fixed_bytes(region_->usage(dev), 0) : 0;
+            uint64_t fixed = region_ ? fixed_bytes(region_->usage(dev), region_->swap_live(dev, pid_)) : 0;
             uint64_t cap = lim > fixed ? lim - fixed : 0;
             // virtual mode: the region check is the cap on live bytes; residency is bounded by the device (cap 0 = size
             // from the device's free memory)
@@ -439,6 +440,16 @@ CUresult Runtime::swap_alloc(CUdeviceptr *dptr, size_t bytes, int dev) {
             swap_[dev].reset(SwapEngine::create(dev, sc));
             if (!swap_[dev]) { LOG_ERROR("swap engine unavailable on device %d", dev); return CUDA_ERROR_NOT_SUPPORTED; }
             if (region_) swap_[dev]->set_shared_record(region_->swap_record(pid_, dev));   // counters for the node monitor
+            if (region_ && lim && !cfg_.limit_is_virtual) {
+                // the resident quota is the CONTAINER's: several processes on this device share it through the region
+                // (reference: get_gpu_memory_usage@0x420bd sums the usage of all process slots; UVM arbitrates residency)
+                SwapEngine *eng = swap_[dev].get();
+                Region *reg = region_.get();
+                int32_t pid = pid_;
+                eng->set_budget_fn([reg, eng, pid, dev](uint64_t want_total, uint64_t live, bool *granted, int *engines) {
+                    return reg->swap_reserve(pid, dev, want_total, live, eng->device_overhead(), granted, engines);
+                });
+            }
         }
         e = swap_[dev].get();
     }
@@ -556,7 +567,7 @@ bool Runtime::check_oom() {
         uint64_t lim = region_->limit(dev);
         if (!lim) return false;
         SwapEngine *e = swap(dev);
-        uint64_t u = region_->usage(dev), live = e ? e->live_bytes() : 0;
+        uint64_t u = region_->usage(dev), live = (e ? e->live_bytes() : 0) + region_->swap_live(dev, pid_);
         return fixed_bytes(u, live) > lim;
     }
     return !region_->try_add(pid_, dev, 0, VGPU_MEM_BUFFER, true, true);

@@ -1385,6 +1385,22 @@ CUresult SwapEngine::swap_staged(Lock &lk, int row, const std::vector<uint32_t> 
     return rc;
 }
 
+// Shared budget (several processes, one quota): refresh this engine's cap from the container's region and reserve the
+// growth there. Without a budget function the cap is local and the growth is granted when it fits.
+bool SwapEngine::reserve_locked(uint64_t extra) {
+    if (!budget_fn_) return (int64_t)extra <= free_phys_locked();
+    bool granted = false;
+    int engines = 1;
+    uint64_t cap = budget_fn_(resident_mapped_ + evicting_mapped_ + extra, live_bytes_.load(), &granted, &engines);
+    budget_checked_ns_ = mono_ns();
+    sibling_engines_ = engines;
+    if (cap != ~0ull) {
+        quota_cap_ = cap;
+        cfg_.resident_cap = pressure_ ? std::min(cap, cfg_.resident_cap) : cap;
+    }
+    return granted && (int64_t)extra <= free_phys_locked();
+}
+
 // ---------------------------------------------------------------------------------------------- pager: main loop
 bool SwapEngine::step_zombies(Lock &lk) {
     const DriverTable &d = drv();
@@ -1517,9 +1533,10 @@ bool SwapEngine::step_demand(Lock &lk) {
         cv_admit_.notify_all();
         return true;
     };
-    if (need > cfg_.resident_cap) return fail(CUDA_ERROR_OUT_OF_MEMORY);
+    if (budget_fn_) reserve_locked(0);                // the siblings may have grown or let go: refresh the cap
+    if (need > cfg_.resident_cap && sibling_engines_ <= 1) return fail(CUDA_ERROR_OUT_OF_MEMORY);
     int64_t free_now = free_phys_locked();
-    if (free_now >= (int64_t)need) {
+    if (free_now >= (int64_t)need && reserve_locked(need)) {
         // room is there (freed by the pager ahead of need, or never used): map + direct copy, together with whatever
         // other demanded rows fit
         std::vector<InItem> items;
@@ -1527,7 +1544,7 @@ bool SwapEngine::step_demand(Lock &lk) {
             QEntry e = demand_q_.front();
             Side &s = side_[e.row];
             bool ok = s.gen == e.gen && s.phase == PH_QUEUED && s.demand;
-            if (ok && free_phys_locked() < (int64_t)s.mapped) break;
+            if (ok && (free_phys_locked() < (int64_t)s.mapped || (budget_fn_ && !items.empty() && !reserve_locked(s.mapped)))) break;
             demand_q_.pop_front();
             if (!ok) continue;
             items.emplace_back();
@@ -1550,6 +1567,12 @@ bool SwapEngine::step_demand(Lock &lk) {
     if (evictable < shortage) {
         bool in_flight = evicting_mapped_ > 0 || !zombies_.empty();
         if (in_flight) return false;
+        if (sibling_engines_ > 1 && need <= quota_cap_ + resident_mapped_) {
+            // the room is held by a sibling process of the container: its pager gives it up as soon as it sees our live bytes
+            // (fair share of the common quota); evict what we can meanwhile and keep waiting
+            if (!victims.empty()) evict_direct(lk, victims);
+            return false;
+        }
         LOG_ERROR("resident quota %lu MiB cannot hold the working set of this launch (need %lu MiB more, evictable %lu MiB)",
                   (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(shortage >> 20), (unsigned long)(evictable >> 20));
         return fail(CUDA_ERROR_OUT_OF_MEMORY);
@@ -1570,7 +1593,7 @@ bool SwapEngine::step_prefetch(Lock &lk) {
         bool ok = (size_t)e.row < side_.size() && side_[e.row].gen == e.gen && side_[e.row].phase == PH_QUEUED && !side_[e.row].demand;
         if (!ok) { prefetch_q_.pop_front(); continue; }
         Side &s = side_[e.row];
-        if (free_phys_locked() < (int64_t)s.mapped) break;
+        if (free_phys_locked() < (int64_t)s.mapped || (budget_fn_ && !reserve_locked(s.mapped))) break;
         prefetch_q_.pop_front();
         queued_prefetch_bytes_ -= s.mapped;
         items.emplace_back();
@@ -1668,6 +1691,9 @@ void SwapEngine::pager_main() {
         bool p4 = step_evict_ahead(lk); te = mono_ns(); if (p4) pst_.pager_step_ns[4] += te - ts;
         progress = p0 || p1 || p2 || p3 || p4;
         if (progress) { pst_.pager_busy_ns += te - t0; continue; }
+        // a sibling process may have started, grown or be waiting for its share of the common quota: look at the region about
+        // once a millisecond (one semaphore round trip)
+        if (budget_fn_ && mono_ns() - budget_checked_ns_ > 1000000ull) reserve_locked(0);
         bool outstanding = !evicting_.empty() || !zombies_.empty() || !demand_q_.empty();
         if (!outstanding) {
             // idle: fold the profiling samples in while nobody waits for the link
@@ -1675,7 +1701,8 @@ void SwapEngine::pager_main() {
             flush_pager_stats_locked();
             pager_idle_ = true;
             cv_admit_.notify_all();
-            cv_pager_.wait(lk, [&] { return stop_ || kick_; });
+            if (budget_fn_) cv_pager_.wait_for(lk, std::chrono::milliseconds(sibling_engines_ > 1 ? 2 : 50), [&] { return stop_ || kick_; });
+            else cv_pager_.wait(lk, [&] { return stop_ || kick_; });
             kick_ = false;
             pager_idle_ = false;
         } else {
@@ -1691,6 +1718,7 @@ void SwapEngine::pager_main() {
 // ---------------------------------------------------------------------------------------------- public operations
 void SwapEngine::set_resident_cap(uint64_t cap) {
     std::lock_guard<std::mutex> g(mu_);
+    if (budget_fn_) { budget_checked_ns_ = 0; kick_pager_locked(); return; }   // the cap comes from the container's shared budget: just look again
     quota_cap_ = cap;
     // under physical pressure (see load_direct) the working cap stays at what the device could actually give
     cfg_.resident_cap = pressure_ ? std::min(cap, cfg_.resident_cap) : cap;

@@ -37,6 +37,7 @@
 #include <condition_variable>
 #include <cstdint>
 #include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -133,6 +134,12 @@ class SwapEngine {
     void set_resident_cap(uint64_t cap);
     // publish the counters into the container's shared region (vgpu_region.h extension block) after every call that
     // changes them; nullptr = do not publish
+    // Several processes of one container on one device share ONE resident quota: before the pager lets the resident set
+    // grow it asks this function (the hook implements it on the container's shared region, under its lock) whether
+    // `want_total` resident bytes fit next to what the sibling engines hold or are entitled to; the answer is also this
+    // engine's current cap. Without it (one engine per device, the C ABI) the cap is the one given at creation.
+    typedef std::function<uint64_t(uint64_t want_total, uint64_t live_mapped, bool *granted, int *engines)> BudgetFn;
+    void set_budget_fn(BudgetFn fn) { std::lock_guard<std::mutex> g(mu_); budget_fn_ = std::move(fn); kick_pager_locked(); }
     void set_shared_record(vgpu_swap_record_t *rec) { std::lock_guard<std::mutex> g(mu_); shared_ = rec; publish_locked(); }
     CUresult drain();                          // wait for the pager and all side-stream work (tests / shutdown)
     void dump_trace(FILE *f);                  // VGPU_SWAP_TRACE=n: device-side start/end times of the first n direct copies per direction after warm-up
@@ -313,6 +320,10 @@ class SwapEngine {
     int last_row_ = -1;
     uint32_t pred_hist_ = 0, pred_count_ = 0;       // last 32 predictions (1 = right)
     SwapStats st_;
+    BudgetFn budget_fn_;
+    uint64_t budget_checked_ns_ = 0;
+    int sibling_engines_ = 1;                       // engines of the container on this device (from the last budget query)
+    bool reserve_locked(uint64_t extra);            // may the resident set grow by `extra`? (refreshes the cap from the shared budget)
     vgpu_swap_record_t *shared_ = nullptr;
     // Physical pressure: the quota (quota_cap_) promises more than the device can give right now — other containers of an
     // overcommitted GPU (DeviceMemoryScaling > 1, server.go:356) hold the rest. The working cap (cfg_.resident_cap) is

@@ -111,6 +111,47 @@ def test_prefetch_pipeline_under_the_hook_keeps_every_word(tmp_path):
     assert out["host_ms"]["vmm"] == 0
 
 
+def test_two_processes_of_one_container_share_one_resident_quota_on_the_gpu(tmp_path):
+    """VERDICT r1 'next' #4, the done-criterion: 2 processes x 6 GiB live under ONE 4 GiB quota (one region file = one
+    container). Both make progress and verify every word; the node monitor's view of the region never shows more than the
+    quota resident for the two engines together."""
+    import threading
+    import time
+    cache = str(tmp_path / "shared.cache")
+    env = dict(os.environ)
+    env.update(v.hook_env(limit_mib=4096, oversubscribe=True, cache_path=cache))
+    env["LIBCUDA_LOG_LEVEL"] = "1"
+    args = [os.path.join(LIBDIR, "swap_bench"), "--cubin", CUBIN, "--buffers", "96", "--mib", "64", "--steps", "288", "--warmup", "16", "--order", "cyclic"]
+    procs = [subprocess.Popen(args, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for _ in range(2)]
+    seen, stop = [], threading.Event()
+
+    def monitor():
+        reg = None
+        while not stop.is_set():
+            try:
+                reg = reg or v.Region(cache)
+                c = reg.swap_counters(0)
+                seen.append((c["processes"], c["resident_bytes"], c["live_bytes"]))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    th = threading.Thread(target=monitor)
+    th.start()
+    outs = []
+    for p in procs:
+        out, err = p.communicate(timeout=900)
+        assert p.returncode == 0, err[-2000:] + out[-300:]
+        outs.append(json.loads(out.strip().splitlines()[-1]))
+    stop.set(); th.join()
+    assert all(o["mismatches"] == 0 and o["verified"] == 1 for o in outs)
+    assert all(o["page_in_bytes"] >= 250 * (64 << 20) for o in outs)          # both made progress through their whole loop
+    both = [s for s in seen if s[0] == 2]
+    assert len(both) > 20
+    assert max(s[1] for s in both) <= 4096 << 20, max(s[1] for s in both)     # sum of both resident sets within the ONE quota
+    assert max(s[2] for s in both) >= 11 << 30                                 # with 12 GiB live
+
+
 def test_read_mostly_advice_through_cumemadvise_saves_the_write_back(tmp_path):
     """Every second buffer is advised read-mostly with cuMemAdvise (what a UVM application does; the reference's swappable
     memory is managed memory) and only read: its evictions are clean, so page-out traffic is about half the page-in's."""
