@@ -484,6 +484,160 @@ extern "C" __global__ void vgpu_copy16(uint4 *__restrict__ dst, const uint4 *__r
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+// Tables above 8192 rows, ONE launch: the multi-launch path above costs a launch per digit plus two for the
+// ordered compaction and re-reads the 32-byte rows from L2/HBM in every pass (7 launches, 117 us cold for 1 Mi rows).
+// Here every CTA of a co-resident grid (cooperative launch, one CTA of 1024 threads per SM, up to 8192 rows each) loads its
+// slice ONCE into registers (key + size, like vgpu_victim_small) and keeps it there across the digit passes:
+//   per digit : shared-memory histogram of the slice -> non-zero bins added to a global histogram -> grid barrier; the LAST
+//               CTA to arrive picks the digit (2048 bins, two per thread, block scan), clears the histogram it read and
+//               only then releases the barrier. The passes alternate between two global histograms, so one barrier per
+//               digit suffices.
+//   emit      : per-CTA count of the selected rows -> grid barrier -> every CTA sums the counts of the CTAs before it and
+//               writes its rows' indices in order (thread order == index order).
+// Same selection rule and outputs as the other two paths (exact LRU prefix, ascending index).
+__device__ __forceinline__ void grid_arrive_and_wait(VgpuScanState *st, unsigned nctas, unsigned &gen, bool *is_last_smem) {
+    __threadfence();                                 // this thread's histogram atomics / count writes, before the CTA reports in
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned ticket = atomicAdd(&st->bar_count, 1u);
+        *is_last_smem = (ticket == nctas - 1);
+        if (!*is_last_smem) {
+            while (*reinterpret_cast<volatile unsigned *>(&st->bar_gen) == gen) { __nanosleep(32); }
+            __threadfence();
+        }
+    }
+    gen++;
+    __syncthreads();
+}
+__device__ __forceinline__ void grid_release(VgpuScanState *st) {      // by the last arriver, after its exclusive work
+    __syncthreads();
+    if (threadIdx.x == 0) { st->bar_count = 0; __threadfence(); atomicAdd(&st->bar_gen, 1u); }
+}
+
+extern "C" __global__ void __launch_bounds__(1024, 1) vgpu_victim_persist(const VgpuEntry *__restrict__ tbl, uint32_t n, VgpuScanState *st,
+                                                                          uint64_t need, uint32_t idx_bits, uint32_t key_bits,
+                                                                          uint32_t *__restrict__ out_idx, uint32_t out_cap) {
+    constexpr int R = VGPU_SCAN_SMALL_ROWS_PER_THREAD;
+    __shared__ unsigned long long hist[VGPU_SCAN_BINS];
+    __shared__ unsigned long long warp_sum[32];
+    __shared__ uint32_t warp_cnt[32];
+    __shared__ bool is_last;
+    __shared__ unsigned long long s_bytes;
+    const unsigned nctas = gridDim.x;
+    unsigned gen = 0;
+    if (threadIdx.x == 0) gen = *reinterpret_cast<volatile unsigned *>(&st->bar_gen);   // no CTA passes a barrier before all have arrived
+    uint64_t key[R], size[R];
+    uint32_t valid = 0;
+    const uint32_t base = blockIdx.x * VGPU_SCAN_PERSIST_ROWS_PER_CTA + threadIdx.x * R;
+#pragma unroll
+    for (int u = 0; u < R; u++) {
+        uint32_t i = base + u;
+        key[u] = 0; size[u] = 0;
+        if (i < n) {
+            VgpuEntry e = load_row(tbl, i);
+            if (e.state == VGPU_ST_RESIDENT) { valid |= 1u << u; key[u] = row_key(e, i, idx_bits); size[u] = e.size; }
+        }
+    }
+    uint64_t prefix = 0, need_left = need;
+    uint32_t insufficient = 0;
+    int pass = 0;
+    for (int hi = (int)key_bits; hi > 0 && !insufficient; hi -= VGPU_SCAN_DIGIT_BITS, pass++) {
+        const uint32_t shift = hi > VGPU_SCAN_DIGIT_BITS ? (uint32_t)(hi - VGPU_SCAN_DIGIT_BITS) : 0u;
+        const uint32_t width = (uint32_t)hi - shift;
+        const uint32_t mask = (1u << width) - 1u;
+        unsigned long long *ghist = reinterpret_cast<unsigned long long *>((pass & 1) ? st->hist2 : st->hist);
+        for (int i = threadIdx.x; i < VGPU_SCAN_BINS; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < R; u++) {
+            if (!(valid >> u & 1u)) continue;
+            uint64_t top = hi >= 64 ? 0 : (key[u] >> hi);
+            if (top != prefix) continue;
+            atomicAdd(&hist[static_cast<uint32_t>(key[u] >> shift) & mask], static_cast<unsigned long long>(size[u]));
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < VGPU_SCAN_BINS; i += blockDim.x)
+            if (hist[i]) atomicAdd(&ghist[i], hist[i]);
+        grid_arrive_and_wait(st, nctas, gen, &is_last);
+        if (is_last) {
+            // pick the digit: thread t owns bins 2t and 2t+1 of the global histogram
+            volatile unsigned long long *gh = ghist;
+            unsigned long long h0 = gh[2 * threadIdx.x], h1 = gh[2 * threadIdx.x + 1];
+            unsigned long long mine = h0 + h1, incl = mine;
+            const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+            for (int d = 1; d < 32; d <<= 1) { unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (unsigned)d) incl += o; }
+            if (lane == 31) warp_sum[wid] = incl;
+            __syncthreads();
+            unsigned long long woff = 0, total = 0;
+            for (unsigned w = 0; w < 32; w++) { if (w < wid) woff += warp_sum[w]; total += warp_sum[w]; }
+            incl += woff;
+            unsigned long long excl = incl - mine;
+            if (threadIdx.x == 0) { st->insufficient = total < need_left ? 1u : 0u; if (total < need_left) st->cand_bytes = total; }
+            if (total >= need_left && excl < need_left && need_left <= incl) {       // exactly one thread (need_left >= 1)
+                unsigned b = 2 * threadIdx.x;
+                unsigned long long cum = excl;
+                if (cum + h0 < need_left) { cum += h0; b++; }
+                st->prefix = (prefix << width) | static_cast<uint64_t>(b);
+                st->need_left = need_left - cum;
+            }
+            gh[2 * threadIdx.x] = 0; gh[2 * threadIdx.x + 1] = 0;     // leave the histogram clean for the pass after next
+            __threadfence();
+            grid_release(st);
+        }
+        __syncthreads();
+        // every CTA picks up the decision (written before the release, read after the barrier)
+        prefix = *reinterpret_cast<volatile uint64_t *>(&st->prefix);
+        need_left = *reinterpret_cast<volatile uint64_t *>(&st->need_left);
+        insufficient = *reinterpret_cast<volatile uint32_t *>(&st->insufficient);
+    }
+    const bool all = insufficient != 0;
+    const bool none = need == 0;
+    const uint64_t kstar = prefix;
+    uint32_t cnt = 0, pick = 0;
+    unsigned long long bytes = 0;
+#pragma unroll
+    for (int u = 0; u < R; u++)
+        if (!none && (valid >> u & 1u) && (all || key[u] <= kstar)) { pick |= 1u << u; cnt++; bytes += size[u]; }
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = cnt;
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+    for (int d = 16; d; d >>= 1) bytes += __shfl_down_sync(0xffffffffu, bytes, d);
+    if (threadIdx.x == 0) s_bytes = 0;
+    __syncthreads();
+    if (lane == 31) warp_cnt[wid] = incl;
+    if (lane == 0 && bytes) atomicAdd(&s_bytes, bytes);
+    __syncthreads();
+    uint32_t woff = 0, cta_total = 0;
+    for (uint32_t w = 0; w < 32; w++) { if (w < wid) woff += warp_cnt[w]; cta_total += warp_cnt[w]; }
+    if (threadIdx.x == 0) { st->cta_off[blockIdx.x] = cta_total; st->cta_bytes[blockIdx.x] = s_bytes; }
+    grid_arrive_and_wait(st, nctas, gen, &is_last);
+    if (is_last) grid_release(st);                    // nothing exclusive to do: the counts are all there
+    __syncthreads();
+    // offset of this CTA = counts of the CTAs before it (<= 148 values: one warp)
+    __shared__ uint32_t s_off;
+    __shared__ unsigned long long s_tot_bytes;
+    __shared__ uint32_t s_tot;
+    if (threadIdx.x < 32) {
+        uint32_t before = 0, tot = 0;
+        unsigned long long tb = 0;
+        volatile uint32_t *co = st->cta_off;
+        volatile uint64_t *cb = st->cta_bytes;
+        for (uint32_t c = threadIdx.x; c < nctas; c += 32) { uint32_t v = co[c]; if (c < blockIdx.x) before += v; tot += v; tb += cb[c]; }
+        for (int d = 16; d; d >>= 1) { before += __shfl_down_sync(0xffffffffu, before, d); tot += __shfl_down_sync(0xffffffffu, tot, d); tb += __shfl_down_sync(0xffffffffu, tb, d); }
+        if (threadIdx.x == 0) { s_off = before; s_tot = tot; s_tot_bytes = tb; }
+    }
+    __syncthreads();
+    uint32_t o = s_off + woff + (incl - cnt);
+#pragma unroll
+    for (int u = 0; u < R; u++)
+        if (pick >> u & 1u) { if (o < out_cap) out_idx[o] = base + u; o++; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->need = need; st->out_count = s_tot; st->out_freed = s_tot_bytes; st->done_ctas = 0;
+        if (!insufficient) st->cand_bytes = 0;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ limiter stamp
 extern "C" __global__ void vgpu_stamp(uint64_t *slot) {
     uint64_t t = globaltimer();

@@ -64,4 +64,10 @@ typedef struct VgpuScanState {
     /* ordered emit: per-CTA victim counts, turned into exclusive offsets by the last CTA of the count launch */
     uint32_t cta_off[VGPU_SCAN_MAX_CTAS];
     uint64_t cta_bytes[VGPU_SCAN_MAX_CTAS];
+    /* vgpu_victim_persist: second histogram (the digit passes alternate between the two, so that the CTA that picks a digit
+     * can clear the one it just read without a second grid barrier) and the grid barrier's arrival counter / generation.
+     * Invariant between launches: both histograms and bar_count are zero. */
+    uint64_t hist2[VGPU_SCAN_BINS];
+    uint32_t bar_count, bar_gen;
 } VgpuScanState;
+#define VGPU_SCAN_PERSIST_ROWS_PER_CTA (1024u * VGPU_SCAN_SMALL_ROWS_PER_THREAD)   /* rows a CTA of vgpu_victim_persist keeps in registers */

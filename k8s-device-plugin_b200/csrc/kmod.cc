@@ -49,7 +49,7 @@ const Kernels *kernels_for_current_ctx() {
     }
     struct { const char *name; CUfunction *fn; } tab[] = {
         {"vgpu_pack_tma", &k->pack_tma}, {"vgpu_pack_generic", &k->pack_generic},
-        {"vgpu_victim_init", &k->victim_init}, {"vgpu_victim_hist", &k->victim_hist}, {"vgpu_victim_emit", &k->victim_emit}, {"vgpu_victim_count", &k->victim_count}, {"vgpu_victim_small", &k->victim_small},
+        {"vgpu_victim_init", &k->victim_init}, {"vgpu_victim_hist", &k->victim_hist}, {"vgpu_victim_emit", &k->victim_emit}, {"vgpu_victim_count", &k->victim_count}, {"vgpu_victim_small", &k->victim_small}, {"vgpu_victim_persist", &k->victim_persist},
         {"vgpu_stamp", &k->stamp}, {"vgpu_copy16", &k->copy16}, {"vgpu_wl_fill", &k->wl_fill}, {"vgpu_wl_touch", &k->wl_touch},
         {"vgpu_wl_verify", &k->wl_verify}, {"vgpu_wl_empty", &k->wl_empty}, {"vgpu_wl_touch_indirect", &k->wl_touch_indirect},
     };
@@ -61,6 +61,9 @@ const Kernels *kernels_for_current_ctx() {
     d.cuCtxGetDevice(&dev);
     d.cuDeviceGetAttribute(&k->sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, dev);
     if (k->sm_count <= 0) k->sm_count = 148;
+    int coop = 0;
+    d.cuDeviceGetAttribute(&coop, CU_DEVICE_ATTRIBUTE_COOPERATIVE_LAUNCH, dev);
+    k->cooperative = coop != 0 && d.cuLaunchCooperativeKernel != nullptr;
     const int smem = 227 * 1024;   // opt in to the maximum; each launch requests 128 + stages * tile bytes
     r = d.cuFuncSetAttribute(k->pack_tma, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, smem);
     if (r != CUDA_SUCCESS) LOG_ERROR("cuFuncSetAttribute(max dynamic smem %d) failed: %d", smem, (int)r);
@@ -151,6 +154,7 @@ CUresult VictimScanner::init(const Kernels *k, uint32_t max_rows) {
     cap_ = max_rows;
     CUresult r;
     if ((r = d.cuMemAlloc_v2(&d_state_, sizeof(VgpuScanState))) != CUDA_SUCCESS) return r;
+    if ((r = d.cuMemsetD8_v2(d_state_, 0, sizeof(VgpuScanState))) != CUDA_SUCCESS) return r;   // vgpu_victim_persist's invariant: histograms and barrier start at zero
     if ((r = d.cuMemAlloc_v2(&d_out_, ((size_t)cap_ * 4 + 15) & ~(size_t)15)) != CUDA_SUCCESS) return r;
     if ((r = d.cuMemHostAlloc(&h_state_, 64, CU_MEMHOSTALLOC_DEVICEMAP)) != CUDA_SUCCESS) return r;
     if ((r = d.cuMemHostAlloc((void **)&h_out_, ((size_t)cap_ * 4 + 15) & ~(size_t)15, CU_MEMHOSTALLOC_DEVICEMAP)) != CUDA_SUCCESS) return r;
@@ -160,6 +164,7 @@ CUresult VictimScanner::init(const Kernels *k, uint32_t max_rows) {
     return CUDA_SUCCESS;
 }
 
+static bool multilaunch_only() { static const bool v = std::getenv("VGPU_SCAN_MULTILAUNCH") != nullptr; return v; }   // experiments / tests of the multi-launch path
 static uint32_t bit_length(uint64_t v) { uint32_t b = 0; while (v) { b++; v >>= 1; } return b; }
 
 CUresult VictimScanner::scan(CUdeviceptr d_tbl, uint32_t n, uint64_t need, uint64_t max_touch, CUstream stream,
@@ -182,6 +187,12 @@ CUresult VictimScanner::scan(CUdeviceptr d_tbl, uint32_t n, uint64_t need, uint6
         // the whole scan in one launch: a single 1024-thread CTA with its rows in registers (kernels.cu)
         void *a[] = {&d_tbl, &n, &d_state_, &need, &idx_bits, &key_bits, &d_out_, &cap_};
         if ((r = d.cuLaunchKernel(k_->victim_small, 1, 1, 1, 1024, 1, 1, 0, stream, a, nullptr)) != CUDA_SUCCESS) return r;
+        launches++;
+    } else if (k_->cooperative && k_->victim_persist && n <= (uint64_t)k_->sm_count * VGPU_SCAN_PERSIST_ROWS_PER_CTA && !multilaunch_only()) {
+        // one cooperative launch, the table slice of every CTA stays in registers across the digit passes (kernels.cu)
+        unsigned grid = (unsigned)((n + VGPU_SCAN_PERSIST_ROWS_PER_CTA - 1) / VGPU_SCAN_PERSIST_ROWS_PER_CTA);
+        void *a[] = {&d_tbl, &n, &d_state_, &need, &idx_bits, &key_bits, &d_out_, &cap_};
+        if ((r = d.cuLaunchCooperativeKernel(k_->victim_persist, grid, 1, 1, 1024, 1, 1, 0, stream, a)) != CUDA_SUCCESS) return r;
         launches++;
     } else {
     {

@@ -13,10 +13,11 @@ namespace vgpu {
 struct Kernels {
     CUmodule mod = nullptr;
     CUfunction pack_tma = nullptr, pack_generic = nullptr;
-    CUfunction victim_init = nullptr, victim_hist = nullptr, victim_emit = nullptr, victim_count = nullptr, victim_small = nullptr;
+    CUfunction victim_init = nullptr, victim_hist = nullptr, victim_emit = nullptr, victim_count = nullptr, victim_small = nullptr, victim_persist = nullptr;
     CUfunction stamp = nullptr, copy16 = nullptr;
     CUfunction wl_fill = nullptr, wl_touch = nullptr, wl_verify = nullptr, wl_empty = nullptr, wl_touch_indirect = nullptr;
     int sm_count = 0;
+    bool cooperative = false;                    // the device supports cooperative launches (vgpu_victim_persist)
 };
 
 // Loads (once per CUcontext) and returns the kernels for the calling thread's current context. Returns nullptr and

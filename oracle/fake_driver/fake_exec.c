@@ -131,13 +131,13 @@ CUresult fx_event_elapsed(float *ms, CUevent a, CUevent b) { *ms = (float)((doub
 CUresult fx_event_destroy(CUevent e) { free(e); return CUDA_SUCCESS; }
 
 /* ------------------------------------------------------------------ functions by name */
-enum { K_OTHER, K_PACK, K_VINIT, K_VHIST, K_VCOUNT, K_VEMIT, K_VSMALL, K_STAMP, K_FILL, K_TOUCH, K_VERIFY, K_EMPTY, K_COPY16, K_TOUCH_IND };
+enum { K_OTHER, K_PACK, K_VINIT, K_VHIST, K_VCOUNT, K_VEMIT, K_VSMALL, K_STAMP, K_FILL, K_TOUCH, K_VERIFY, K_EMPTY, K_COPY16, K_TOUCH_IND, K_VPERSIST };
 typedef struct { const char *name; int kind; int nparam; size_t psize[8]; } fx_func;
 static fx_func g_funcs[] = {
     {"vgpu_pack_tma", K_PACK, 1, {sizeof(VgpuPackParams)}}, {"vgpu_pack_generic", K_PACK, 1, {sizeof(VgpuPackParams)}},
     {"vgpu_victim_init", K_VINIT, 2, {8, 8}}, {"vgpu_victim_hist", K_VHIST, 6, {8, 4, 8, 4, 4, 4}},
     {"vgpu_victim_count", K_VCOUNT, 5, {8, 4, 8, 4, 4}}, {"vgpu_victim_emit", K_VEMIT, 7, {8, 4, 8, 4, 4, 8, 4}},
-    {"vgpu_victim_small", K_VSMALL, 8, {8, 4, 8, 8, 4, 4, 8, 4}}, {"vgpu_stamp", K_STAMP, 1, {8}},
+    {"vgpu_victim_small", K_VSMALL, 8, {8, 4, 8, 8, 4, 4, 8, 4}}, {"vgpu_victim_persist", K_VPERSIST, 8, {8, 4, 8, 8, 4, 4, 8, 4}}, {"vgpu_stamp", K_STAMP, 1, {8}},
     {"vgpu_wl_fill", K_FILL, 3, {8, 8, 8}}, {"vgpu_wl_touch", K_TOUCH, 2, {8, 8}}, {"vgpu_wl_verify", K_VERIFY, 5, {8, 8, 8, 8, 8}},
     {"vgpu_wl_empty", K_EMPTY, 0, {0}}, {"vgpu_empty", K_EMPTY, 0, {0}}, {"vgpu_copy16", K_COPY16, 3, {8, 8, 8}}, {"vgpu_wl_touch_indirect", K_TOUCH_IND, 3, {8, 4, 8}},
 };
@@ -212,6 +212,7 @@ CUresult fx_launch(CUfunction f, void **params) {
     case K_VHIST: case K_VCOUNT: break;          /* the selection happens in one piece at emit time */
     case K_VEMIT: { VgpuScanState *st = ARG(VgpuScanState *, 2);
         victim_select(ARG(const VgpuEntry *, 0), ARG(uint32_t, 1), st, st->need, ARG(uint32_t *, 5), ARG(uint32_t, 6)); break; }
+    case K_VPERSIST:
     case K_VSMALL: victim_select(ARG(const VgpuEntry *, 0), ARG(uint32_t, 1), ARG(VgpuScanState *, 2), ARG(uint64_t, 3), ARG(uint32_t *, 6), ARG(uint32_t, 7)); break;
     case K_STAMP: *ARG(volatile uint64_t *, 0) = now_ns(); break;
     case K_TOUCH_IND: { uint64_t **t = ARG(uint64_t **, 0); uint32_t np = ARG(uint32_t, 1); uint64_t n = ARG(uint64_t, 2);

@@ -181,6 +181,19 @@ def test_victim_scan_large_table_and_wide_clock(ora):
     _scan_case(ora, 1 << 20, 4 << 40, seed=3, touch_max=123456789)
 
 
+def test_victim_scan_persistent_kernel_boundaries_and_repeated_use(ora):
+    """8192 < rows <= 148 x 8192: ONE cooperative launch, every CTA keeps its slice in registers across the digit passes
+    (vgpu_victim_persist). Boundaries of the path (8193 rows = 2 CTAs, 1 212 416 = 148 full CTAs, one more row = back to the
+    multi-launch path), an unmeetable need (all candidates, flag set), a wide clock (five digit passes), all ties, and many
+    scans in a row on the same scanner state (the kernel must leave its histograms and barrier clean)."""
+    for n, need, kw in ((8193, 60 << 30, {}), (16384, 1 << 62, {}), (50000, 700 << 30, {"touch_max": (1 << 40) - 1}),
+                        (148 * 8192, 3 << 40, {"touch_max": 999}), (148 * 8192 + 1, 3 << 40, {"touch_max": 999}),
+                        (30000, 200 << 30, {"touch_max": 0}), (300000, 1, {}), (300000, 2 << 40, {"resident_frac": 0.05})):
+        _scan_case(ora, n, need, seed=n % 97, **kw)
+    for rep in range(12):
+        _scan_case(ora, 20000 + rep * 1000, (rep + 1) << 33, seed=rep)
+
+
 def test_victim_scan_prefix_property_at_scale():
     # size-independent property on 1 M rows: the chosen set is a prefix of the (touch, index) order and is minimal
     n = 1 << 20
