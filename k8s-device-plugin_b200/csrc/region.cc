@@ -239,7 +239,7 @@ uint64_t Region::swap_live(int dev, int32_t except_pid) const {
     return sum;
 }
 
-uint64_t Region::swap_reserve(int32_t pid, int dev, uint64_t want_total, uint64_t live_mapped, uint64_t overhead, bool *granted, int *engines) {
+uint64_t Region::swap_reserve(int32_t pid, int dev, uint64_t want_total, uint64_t live_mapped, uint64_t overhead, bool *granted, int *engines, uint64_t *share_out) {
     *granted = false;
     if (engines) *engines = 1;
     if (!ext_) { *granted = true; return ~0ull; }
@@ -266,6 +266,7 @@ uint64_t Region::swap_reserve(int32_t pid, int dev, uint64_t want_total, uint64_
     uint64_t taken = (uint64_t)fixed + (uint64_t)n * overhead;
     uint64_t room = lim > taken ? lim - taken : 0;
     uint64_t share = room / (uint64_t)n;
+    if (share_out) *share_out = share;
     uint64_t others = 0;
     for (int i = 0; i < VGPU_REGION_EXT_RECORDS; i++) {
         const vgpu_swap_record_t &rec = ext_->swap[i];

@@ -68,7 +68,7 @@ class Region {
     // engine may hold what the OTHERS neither hold nor are entitled to (their fair share, bounded by what they have
     // live). Grants `want_total` (publishes it as the caller's resident_bytes, i.e. reserves it) when it fits; returns the
     // caller's cap either way. live_mapped: the caller's live swappable bytes; overhead: its staging rings.
-    uint64_t swap_reserve(int32_t pid, int dev, uint64_t want_total, uint64_t live_mapped, uint64_t overhead, bool *granted, int *engines);
+    uint64_t swap_reserve(int32_t pid, int dev, uint64_t want_total, uint64_t live_mapped, uint64_t overhead, bool *granted, int *engines, uint64_t *share = nullptr);
 
    private:
     Region() = default;

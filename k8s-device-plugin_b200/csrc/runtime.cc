@@ -446,8 +446,8 @@ CUresult Runtime::swap_alloc(CUdeviceptr *dptr, size_t bytes, int dev) {
                 SwapEngine *eng = swap_[dev].get();
                 Region *reg = region_.get();
                 int32_t pid = pid_;
-                eng->set_budget_fn([reg, eng, pid, dev](uint64_t want_total, uint64_t live, bool *granted, int *engines) {
-                    return reg->swap_reserve(pid, dev, want_total, live, eng->device_overhead(), granted, engines);
+                eng->set_budget_fn([reg, eng, pid, dev](uint64_t want_total, uint64_t live, bool *granted, int *engines, uint64_t *share) {
+                    return reg->swap_reserve(pid, dev, want_total, live, eng->device_overhead(), granted, engines, share);
                 });
             }
         }

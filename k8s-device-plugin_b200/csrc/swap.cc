@@ -1391,7 +1391,9 @@ bool SwapEngine::reserve_locked(uint64_t extra) {
     if (!budget_fn_) return (int64_t)extra <= free_phys_locked();
     bool granted = false;
     int engines = 1;
-    uint64_t cap = budget_fn_(resident_mapped_ + evicting_mapped_ + extra, live_bytes_.load(), &granted, &engines);
+    uint64_t share = 0;
+    uint64_t cap = budget_fn_(resident_mapped_ + evicting_mapped_ + extra, live_bytes_.load(), &granted, &engines, &share);
+    fair_share_ = share;
     budget_checked_ns_ = mono_ns();
     sibling_engines_ = engines;
     if (cap != ~0ull) {
@@ -1567,11 +1569,15 @@ bool SwapEngine::step_demand(Lock &lk) {
     if (evictable < shortage) {
         bool in_flight = evicting_mapped_ > 0 || !zombies_.empty();
         if (in_flight) return false;
-        if (sibling_engines_ > 1 && need <= quota_cap_ + resident_mapped_) {
+        if (sibling_engines_ > 1 && need <= fair_share_) {
             // the room is held by a sibling process of the container: its pager gives it up as soon as it sees our live bytes
-            // (fair share of the common quota); evict what we can meanwhile and keep waiting
-            if (!victims.empty()) evict_direct(lk, victims);
-            return false;
+            // (fair share of the common quota); evict what we can meanwhile and keep waiting — but not for ever (a sibling
+            // that is stopped in a debugger never shrinks)
+            if (demand_row_ != row) { demand_row_ = row; demand_since_ns_ = mono_ns(); }
+            if (mono_ns() - demand_since_ns_ < 20000000000ull) {
+                if (!victims.empty()) evict_direct(lk, victims);
+                return false;
+            }
         }
         LOG_ERROR("resident quota %lu MiB cannot hold the working set of this launch (need %lu MiB more, evictable %lu MiB)",
                   (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(shortage >> 20), (unsigned long)(evictable >> 20));
@@ -1735,7 +1741,7 @@ CUresult SwapEngine::alloc(CUdeviceptr *dptr, size_t bytes) {
         return CUDA_ERROR_OUT_OF_MEMORY;
     }
     uint64_t mapped = round_up(bytes, gran_);
-    if (cfg_.resident_cap && mapped > cfg_.resident_cap) {
+    if (cfg_.resident_cap && mapped > cfg_.resident_cap && !budget_fn_) {      // (with sibling engines the cap moves: the pager decides)
         // a buffer is resident as a whole while a kernel uses it: one that exceeds the resident cap can never be admitted
         LOG_ERROR("Device %d OOM: a single %lu-byte buffer exceeds the resident cap of %lu bytes", dev_, (unsigned long)bytes, (unsigned long)cfg_.resident_cap);
         return CUDA_ERROR_OUT_OF_MEMORY;
@@ -1754,6 +1760,10 @@ CUresult SwapEngine::alloc(CUdeviceptr *dptr, size_t bytes) {
     s.phase = PH_QUEUED;
     s.demand = true;
     mark_dirty(row);
+    // live from now on: sibling engines of the container (other processes, same device) give up room for what is LIVE here
+    live_bytes_ += bytes;
+    live_mapped_ += mapped;
+    host_need_ += round_up(bytes, 256);
     demand_q_.push_back(QEntry{row, s.gen});
     kick_pager_locked();
     {
@@ -1764,6 +1774,9 @@ CUresult SwapEngine::alloc(CUdeviceptr *dptr, size_t bytes) {
     if (!(rows_[row].state & VGPU_ST_RESIDENT)) {
         CUresult rc = s2.fail != CUDA_SUCCESS ? s2.fail : CUDA_ERROR_OUT_OF_MEMORY;
         s2.pins = 0;
+        live_bytes_ -= bytes;
+        live_mapped_ -= mapped;
+        host_need_ -= std::min<uint64_t>(host_need_, round_up(bytes, 256));
         retire_row_locked(row);
         return rc;
     }
@@ -1771,9 +1784,6 @@ CUresult SwapEngine::alloc(CUdeviceptr *dptr, size_t bytes) {
     rows_[row].state = VGPU_ST_RESIDENT | (s2.locked ? VGPU_ST_PINNED : 0u);
     for (uint64_t gidx = off / gran_; gidx < (off + mapped) / gran_; gidx++) owner_[gidx] = row;
     mark_dirty(row);
-    live_bytes_ += bytes;
-    live_mapped_ += mapped;
-    host_need_ += round_up(bytes, 256);
     uint64_t need_now = host_need_;
     *dptr = arena_ + off;
     publish_locked();
@@ -1884,7 +1894,8 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
         uint64_t need = 0, pinned = 0;
         for (int r : missing) need += side_[r].mapped;
         for (int i = 0; i < n; i++) if (rows_[rows[i]].state & VGPU_ST_RESIDENT) pinned += side_[rows[i]].mapped;
-        if (need + pinned > cfg_.resident_cap) {
+        // with sibling engines the cap moves (they give room up as they see our demand): judge against the fair share then
+        if (need + pinned > (budget_fn_ && sibling_engines_ > 1 ? std::max(cfg_.resident_cap, fair_share_) : cfg_.resident_cap)) {
             LOG_ERROR("resident quota %lu MiB cannot hold the working set of this launch (%lu MiB)", (unsigned long)(cfg_.resident_cap >> 20),
                       (unsigned long)((need + pinned) >> 20));
             rc = CUDA_ERROR_OUT_OF_MEMORY;

@@ -138,7 +138,7 @@ class SwapEngine {
     // grow it asks this function (the hook implements it on the container's shared region, under its lock) whether
     // `want_total` resident bytes fit next to what the sibling engines hold or are entitled to; the answer is also this
     // engine's current cap. Without it (one engine per device, the C ABI) the cap is the one given at creation.
-    typedef std::function<uint64_t(uint64_t want_total, uint64_t live_mapped, bool *granted, int *engines)> BudgetFn;
+    typedef std::function<uint64_t(uint64_t want_total, uint64_t live_mapped, bool *granted, int *engines, uint64_t *fair_share)> BudgetFn;
     void set_budget_fn(BudgetFn fn) { std::lock_guard<std::mutex> g(mu_); budget_fn_ = std::move(fn); kick_pager_locked(); }
     void set_shared_record(vgpu_swap_record_t *rec) { std::lock_guard<std::mutex> g(mu_); shared_ = rec; publish_locked(); }
     CUresult drain();                          // wait for the pager and all side-stream work (tests / shutdown)
@@ -321,7 +321,8 @@ class SwapEngine {
     uint32_t pred_hist_ = 0, pred_count_ = 0;       // last 32 predictions (1 = right)
     SwapStats st_;
     BudgetFn budget_fn_;
-    uint64_t budget_checked_ns_ = 0;
+    uint64_t budget_checked_ns_ = 0, fair_share_ = 0, demand_since_ns_ = 0;
+    int demand_row_ = -1;
     int sibling_engines_ = 1;                       // engines of the container on this device (from the last budget query)
     bool reserve_locked(uint64_t extra);            // may the resident set grow by `extra`? (refreshes the cap from the shared budget)
     vgpu_swap_record_t *shared_ = nullptr;

@@ -44,7 +44,14 @@ for n in sizes:
         scan()
         us += (time.perf_counter() - t0) * 1e6
     us /= reps
-    out.append({"rows": n, "call_us": round(us, 1), "victims": cnt.value, "algorithmic_GBps_of_call": round(32 * n / us / 1e3, 1)})
+    warm = 0.0
+    for _ in range(reps):                             # warm: the table stays in L2 (32 MB << 126 MB), as between two real admissions
+        t0 = time.perf_counter()
+        scan()
+        warm += (time.perf_counter() - t0) * 1e6
+    warm /= reps
+    out.append({"rows": n, "call_us": round(us, 1), "call_us_warm": round(warm, 1), "victims": cnt.value, "algorithmic_GBps_of_call": round(32 * n / us / 1e3, 1),
+                "path": "small" if n <= 8192 else ("persist" if n <= 148 * 8192 and not os.environ.get("VGPU_SCAN_MULTILAUNCH") else "multi-launch")})
     print(out[-1], flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/scan_scaling.json", "w"), indent=1)

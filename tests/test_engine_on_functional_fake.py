@@ -422,17 +422,63 @@ def test_two_processes_of_one_container_share_the_resident_quota(tmp_path):
     th = threading.Thread(target=monitor)
     th.start()
     outs = []
-    for p in procs:
-        out, err = p.communicate(timeout=600)
-        assert p.returncode == 0, err[-2000:] + out[-300:]
-        outs.append(json.loads(out.strip().splitlines()[-1]))
-    stop.set(); th.join()
+    try:
+        for p in procs:
+            out, err = p.communicate(timeout=300)
+            assert p.returncode == 0, err[-2000:] + out[-300:]
+            outs.append(json.loads(out.strip().splitlines()[-1]))
+    finally:
+        stop.set(); th.join()
+        for p in procs:                      # never leave a sibling running behind a failed assertion
+            if p.poll() is None:
+                p.kill(); p.communicate()
     assert all(o["mismatches"] == 0 and o["verified"] == 1 for o in outs)
     assert all(o["page_in_bytes"] > 100 * 16 * M for o in outs)               # both really paged
     both = [s for s in seen if s[0] == 2]
     assert len(both) > 20, "the monitor must have seen both engines at once"
     assert max(s[1] for s in both) <= 256 * M, max(s[1] for s in both)           # sum of both resident sets within ONE quota
     assert max(s[2] for s in both) > 600 * M                                     # while far more than the quota was live
+
+
+def test_a_late_sibling_gets_its_share_from_a_process_that_already_fills_the_quota(tmp_path):
+    """The hard ordering: process 1 populates and fills the whole resident quota, THEN process 2 starts. Its first
+    allocation must not be refused and must not wait for ever: process 1's pager sees the sibling's live bytes in the
+    region and gives up room down to its fair share, even while its application thread is idle."""
+    cache = str(tmp_path / "late.cache")
+    env = _env(tmp_path, LD_PRELOAD=HOOK_SO, CUDA_OVERSUBSCRIBE="true", CUDA_DEVICE_MEMORY_LIMIT_0="256m", CUDA_DEVICE_MEMORY_SHARED_CACHE=cache,
+               VGPU_SWAP_CHUNK_MB="2", VGPU_SWAP_RING="2")
+    args = [os.path.join(LIBDIR, "swap_bench"), "--cubin", CUBIN, "--buffers", "24", "--mib", "16", "--steps", "120", "--warmup", "8", "--order", "cyclic",
+            "--wait-stdin", "1"]
+    procs = []
+    try:
+        for _ in range(2):
+            p = subprocess.Popen(args, env=env, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            procs.append(p)
+            import select
+            deadline = 120
+            ready = False
+            while deadline > 0 and not ready:           # populated + warmed up (for the second one: next to a full first one)
+                r, _, _ = select.select([p.stderr], [], [], 1.0)
+                deadline -= 1
+                if r:
+                    line = p.stderr.readline()
+                    ready = line.startswith("READY")
+                    if not line:
+                        break
+            assert ready, "process did not get through its populate phase"
+        reg = v.Region(cache)
+        c = reg.swap_counters(0)
+        assert c["processes"] == 2 and c["resident_bytes"] <= 256 * M and c["live_bytes"] > 700 * M, c
+        for p in procs:
+            p.stdin.write("go\n"); p.stdin.flush()
+        for p in procs:
+            out, err = p.communicate(timeout=300)
+            assert p.returncode == 0, err[-2000:]
+            assert json.loads(out.strip().splitlines()[-1])["mismatches"] == 0
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill(); p.communicate()
 
 
 @pytest.mark.parametrize("seed", [31, 32])

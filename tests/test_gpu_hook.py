@@ -139,11 +139,16 @@ def test_two_processes_of_one_container_share_one_resident_quota_on_the_gpu(tmp_
     th = threading.Thread(target=monitor)
     th.start()
     outs = []
-    for p in procs:
-        out, err = p.communicate(timeout=900)
-        assert p.returncode == 0, err[-2000:] + out[-300:]
-        outs.append(json.loads(out.strip().splitlines()[-1]))
-    stop.set(); th.join()
+    try:
+        for p in procs:
+            out, err = p.communicate(timeout=300)
+            assert p.returncode == 0, err[-2000:] + out[-300:]
+            outs.append(json.loads(out.strip().splitlines()[-1]))
+    finally:
+        stop.set(); th.join()
+        for p in procs:                      # never leave a sibling running behind a failed assertion
+            if p.poll() is None:
+                p.kill(); p.communicate()
     assert all(o["mismatches"] == 0 and o["verified"] == 1 for o in outs)
     assert all(o["page_in_bytes"] >= 250 * (64 << 20) for o in outs)          # both made progress through their whole loop
     both = [s for s in seen if s[0] == 2]
