@@ -454,6 +454,32 @@ static uint64_t *lane(vgpu_device_memory_t &m, int type) {
     }
 }
 
+bool Region::try_add_fixed(int32_t pid, int dev, uint64_t bytes, uint64_t own_live, uint64_t *fixed_after) {
+    lock();
+    uint64_t lim = r_->limit[dev];
+    int64_t fixed = (int64_t)(usage_locked(dev) - own_live - swap_live(dev, pid));
+    if (fixed < 0) fixed = 0;
+    if (fixed_after) *fixed_after = (uint64_t)fixed + bytes;
+    if (lim && (uint64_t)fixed + bytes > lim) {
+        bool ok = false;
+        if (reap_dead_locked() > 0) {
+            fixed = (int64_t)(usage_locked(dev) - own_live - swap_live(dev, pid));
+            if (fixed < 0) fixed = 0;
+            ok = !((uint64_t)fixed + bytes > lim);
+            if (fixed_after) *fixed_after = (uint64_t)fixed + bytes;
+        }
+        if (!ok) { unlock(); return false; }
+    }
+    int s = find_slot_locked(pid);
+    if (s >= 0) {
+        vgpu_device_memory_t &m = r_->procs[s].used[dev];
+        m.total += bytes;
+        if (uint64_t *l = lane(m, VGPU_MEM_BUFFER)) *l += bytes;
+    }
+    unlock();
+    return true;
+}
+
 bool Region::try_add(int32_t pid, int dev, uint64_t bytes, int type, bool enforce, bool check_only) {
     lock();
     if (enforce) {

@@ -62,7 +62,9 @@ class Region {
     vgpu_swap_record_t *swap_record(int32_t pid, int dev);
     // sum of the live records of `dev`; out->pid = records summed. false: no extension block
     bool swap_counters(int dev, vgpu_swap_record_t *out);
-    uint64_t swap_live(int dev, int32_t except_pid = 0) const;   // live swappable bytes of the container's engines on dev (relaxed reads)
+    uint64_t swap_live(int dev, int32_t except_pid = 0) const;
+    // swap mode, non-swappable charge: under the lock, (usage - live swappable bytes of all engines) + bytes <= limit ? add : refuse
+    bool try_add_fixed(int32_t pid, int dev, uint64_t bytes, uint64_t own_live, uint64_t *fixed_after);   // live swappable bytes of the container's engines on dev (relaxed reads)
     // Shared RESIDENT budget of the container's swap engines on one device (several processes, one quota), under the region
     // lock: the room for swappable memory is limit - everything non-swappable - every engine's staging rings; of that an
     // engine may hold what the OTHERS neither hold nor are entitled to (their fair share, bounded by what they have

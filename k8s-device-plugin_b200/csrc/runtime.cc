@@ -114,7 +114,16 @@ bool Runtime::ensure_initialized() {
     std::string err;
     Region *R = Region::open(cfg_.region_path.c_str(), true, cfg_.mem_limit, cfg_.sm_limit, cfg_.priority, uuids, ndev, &err);
     if (!R) {
-        LOG_ERROR("shared region %s unavailable (%s): limits are NOT enforced in this process", cfg_.region_path.c_str(), err.c_str());
+        // Without the region nothing can be accounted. If the container HAS a gpumem quota, running on without it would
+        // silently hand the process the whole GPU (a runAsNonRoot container that cannot create its cache file):
+        // fail closed — device allocations are refused — unless the operator opts out with VGPU_FAIL_OPEN=1.
+        bool limited = false;
+        for (int d = 0; d < VGPU_MAX_DEVICES; d++) limited |= cfg_.mem_limit[d] != 0;
+        const char *open_env = std::getenv("VGPU_FAIL_OPEN");
+        fail_closed_ = limited && !(open_env && *open_env && *open_env != '0');
+        LOG_ERROR("shared region %s unavailable (%s): %s", cfg_.region_path.c_str(), err.c_str(),
+                  fail_closed_ ? "a gpumem quota is configured and cannot be enforced, device allocations are REFUSED (VGPU_FAIL_OPEN=1 to run unenforced)"
+                               : "limits are NOT enforced in this process");
     } else {
         region_.reset(R);
         if (region_->claim_slot(pid_) < 0) LOG_ERROR("no free process slot in %s", cfg_.region_path.c_str());
@@ -399,11 +408,16 @@ bool Runtime::charge(int dev, size_t bytes) {
     uint64_t lim = region_->limit(dev);
     SwapEngine *e = swap(dev);
     if (lim) {
-        // live swappable bytes of EVERY engine of the container on this device (sibling processes publish theirs in the region)
-        uint64_t u = region_->usage(dev), live = (e ? e->live_bytes() : 0) + region_->swap_live(dev, pid_);
-        uint64_t fixed = fixed_bytes(u, live);
-        if (fixed + bytes > lim) { LOG_ERROR("Device %d OOM %lu / %lu (non-swappable)", dev, (unsigned long)(fixed + bytes), (unsigned long)lim); return false; }
-        if (e) e->set_resident_cap(room_for_engine(lim, fixed + bytes, e));
+        // check and add in ONE critical section of the region (two processes of a container could both pass a
+        // check-then-add): non-swappable bytes = accounted usage - live swappable bytes of EVERY engine of the container on
+        // this device (sibling processes publish theirs in the region)
+        uint64_t fixed_after = 0;
+        if (!region_->try_add_fixed(pid_, dev, bytes, e ? e->live_bytes() : 0, &fixed_after)) {
+            LOG_ERROR("Device %d OOM %lu / %lu (non-swappable)", dev, (unsigned long)fixed_after, (unsigned long)lim);
+            return false;
+        }
+        if (e) e->set_resident_cap(room_for_engine(lim, fixed_after, e));
+        return true;
     }
     region_->add(pid_, dev, bytes, VGPU_MEM_BUFFER);
     return true;
@@ -471,7 +485,7 @@ CUresult Runtime::swap_alloc(CUdeviceptr *dptr, size_t bytes, int dev) {
 CUresult Runtime::mem_alloc(CUdeviceptr *dptr, size_t bytes) {
     ensure_initialized();
     const DriverTable &d = drv();
-    if (!region_) return d.cuMemAlloc_v2(dptr, bytes);
+    if (!region_) return fail_closed_ ? CUDA_ERROR_OUT_OF_MEMORY : d.cuMemAlloc_v2(dptr, bytes);
     int dev = current_device();
     if (dev < 0) return d.cuMemAlloc_v2(dptr, bytes);  // no context: let the driver report it
     std::lock_guard<std::mutex> g(table_mu_);          // allocate_raw@0x40a10 holds the allocator mutex across add_chunk
@@ -495,7 +509,7 @@ CUresult Runtime::mem_alloc(CUdeviceptr *dptr, size_t bytes) {
 CUresult Runtime::mem_alloc_managed(CUdeviceptr *dptr, size_t bytes, unsigned flags) {
     ensure_initialized();
     const DriverTable &d = drv();
-    if (!region_) return d.cuMemAllocManaged(dptr, bytes, flags);
+    if (!region_) return fail_closed_ ? CUDA_ERROR_OUT_OF_MEMORY : d.cuMemAllocManaged(dptr, bytes, flags);
     int dev = current_device();
     if (dev < 0) return d.cuMemAllocManaged(dptr, bytes, flags);
     if (!charge(dev, bytes)) return CUDA_ERROR_OUT_OF_MEMORY;  // @0x31eab
@@ -509,6 +523,7 @@ CUresult Runtime::mem_alloc_managed(CUdeviceptr *dptr, size_t bytes, unsigned fl
 CUresult Runtime::mem_alloc_pitch(CUdeviceptr *dptr, size_t *pitch, size_t width, size_t height, unsigned elem) {
     ensure_initialized();
     const DriverTable &d = drv();
+    if (!region_ && fail_closed_) return CUDA_ERROR_OUT_OF_MEMORY;
     if (!region_ || elem == 0) return d.cuMemAllocPitch_v2(dptr, pitch, width, height, elem);
     int dev = current_device();
     if (dev < 0) return d.cuMemAllocPitch_v2(dptr, pitch, width, height, elem);
@@ -860,6 +875,7 @@ CUresult Runtime::mem_alloc_async(CUdeviceptr *dptr, size_t bytes, CUmemoryPool 
         auto f = ptsz ? d.cuMemAllocAsync_ptsz : d.cuMemAllocAsync;
         return f ? f(dptr, bytes, st) : CUDA_ERROR_NOT_SUPPORTED;
     };
+    if (!region_ && fail_closed_) return CUDA_ERROR_OUT_OF_MEMORY;
     if (!region_ || reference_coverage()) return real();
     int dev = current_device();
     if (dev < 0) return real();
@@ -906,6 +922,7 @@ CUresult Runtime::mem_create(CUmemGenericAllocationHandle *h, size_t bytes, cons
     ensure_initialized();
     const DriverTable &d = drv();
     if (!d.cuMemCreate) return CUDA_ERROR_NOT_SUPPORTED;
+    if (!region_ && fail_closed_ && prop && prop->location.type == CU_MEM_LOCATION_TYPE_DEVICE) return CUDA_ERROR_OUT_OF_MEMORY;
     if (!region_ || reference_coverage() || !prop || prop->location.type != CU_MEM_LOCATION_TYPE_DEVICE)
         return d.cuMemCreate(h, bytes, prop, flags);
     int dev = prop->location.id;

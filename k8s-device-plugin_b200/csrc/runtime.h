@@ -133,6 +133,7 @@ class Runtime {
     std::mutex init_mu_;
     Config cfg_;
     std::unique_ptr<Region> region_;
+    bool fail_closed_ = false;                   // a quota is configured but the region could not be opened: refuse device allocations
     int32_t pid_ = 0;
     uint64_t context_size_ = 0;
     bool pid_found_ = false;

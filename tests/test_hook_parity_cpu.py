@@ -595,3 +595,18 @@ def _driven_op_by_op(tmp_path, seed, wide, mixed):
     sched, res, diffs = mp.compare(seed, str(tmp_path), wide, mixed)      # wide: three GPUs, device switches, contexts, NVML and host-side calls too
     assert not diffs and len(res["new"]) == len(res["reference"]) == len(sched), diffs[:3]
     assert any(a == "kill" for _, a in sched) and any(" rc=-1 " in l for l in res["new"])     # kills and quota breaches happened
+
+
+def test_a_quota_that_cannot_be_enforced_fails_closed(tmp_path):
+    """when the container has a gpumem quota but the hook cannot open its region file (a runAsNonRoot container
+    and a cache directory it may not write), running on unenforced would silently hand the process the whole GPU. Device
+    allocations are refused instead; VGPU_FAIL_OPEN=1 restores the old behaviour; without a quota nothing changes."""
+    t = tmp_path / "t.txt"
+    t.write_text("A 0 1048576\nF 0\n")
+    bad = "/proc/definitely/not/writable/x.cache"
+    out = run_replay(str(t), "new", {"CUDA_DEVICE_MEMORY_LIMIT_0": "64m", "CUDA_DEVICE_MEMORY_SHARED_CACHE": bad})
+    assert "rc=2" in out.splitlines()[1], out                                   # CUDA_ERROR_OUT_OF_MEMORY for the allocation
+    out = run_replay(str(t), "new", {"CUDA_DEVICE_MEMORY_LIMIT_0": "64m", "CUDA_DEVICE_MEMORY_SHARED_CACHE": bad, "VGPU_FAIL_OPEN": "1"})
+    assert "rc=0" in out.splitlines()[1], out
+    out = run_replay(str(t), "new", {"CUDA_DEVICE_MEMORY_SHARED_CACHE": bad})    # no quota configured: nothing to enforce
+    assert "rc=0" in out.splitlines()[1], out

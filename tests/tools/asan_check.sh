@@ -19,7 +19,9 @@ n=0; run() { n=$((n+1)); local vars=(); while [ "$1" != "--" ]; do vars+=("$1");
   env "${vars[@]}" CUDA_DEVICE_MEMORY_SHARED_CACHE=$T/c$n.cache LD_PRELOAD=$PRE "$@" > $T/out$n.txt 2>&1; echo "  [$n] rc=$? $(tail -c 120 $T/out$n.txt | tr '\n' ' ' | cut -c1-100)"; }
 run $SW CUDA_DEVICE_MEMORY_LIMIT_0=256m -- $SB --buffers 32 --steps 96 --order cyclic
 run $SW CUDA_DEVICE_MEMORY_LIMIT_0=256m -- $SB --buffers 32 --steps 200 --order zipf
-run $SW CUDA_DEVICE_MEMORY_LIMIT_0=256m VGPU_SWAP_ASYNC_UNMAP=1 -- $SB --buffers 24 --steps 72 --order cyclic
+run $SW CUDA_DEVICE_MEMORY_LIMIT_0=256m VGPU_SWAP_PREFETCH_MB=0 -- $SB --buffers 24 --steps 72 --order cyclic
+run $SW CUDA_DEVICE_MEMORY_LIMIT_0=256m VGPU_SWAP_HOST_BACKED=1 -- $SB --buffers 24 --steps 72 --order cyclic
+run $SW CUDA_DEVICE_MEMORY_LIMIT_0=256m -- $SB --buffers 24 --steps 96 --order zipf --ro-every 2
 run $SW CUDA_DEVICE_MEMORY_LIMIT_0=384m FAKE_GPU_TOTAL_MIB=200 -- $SB --buffers 32 --steps 96 --order cyclic
 run $SW CUDA_DEVICE_MEMORY_LIMIT_0=384m FAKE_GPU_TOTAL_MIB=200 VGPU_SWAP_LIMIT_MODE=virtual -- $SB --buffers 20 --steps 60 --order cyclic
 run CUDA_DEVICE_MEMORY_LIMIT_0=64m -- $R/oracle/_ref/hook_stress threads 8 2000
@@ -39,7 +41,7 @@ for s in 1 2; do run FAKE_GPU_COUNT=3 CUDA_DEVICE_MEMORY_LIMIT_0=96m CUDA_DEVICE
 for s in 1 2; do run $SW FAKE_GPU_COUNT=3 VGPU_SWAP_LIMIT_MODE=virtual CUDA_DEVICE_MEMORY_LIMIT_0=196m CUDA_DEVICE_MEMORY_LIMIT_1=164m CUDA_DEVICE_MEMORY_LIMIT_2=300m -- $R/oracle/_ref/trace_replay $T/fz$s.txt; done
 if ls $T/asan.* $T/ubsan.* > /dev/null 2>&1; then echo "SANITIZER REPORTS:"; head -60 $T/asan.* $T/ubsan.* 2>/dev/null; exit 1; fi
 echo "no ASan/UBSan reports in $n scenarios"
-# ---- ThreadSanitizer: the multi-threaded scenarios (application threads racing on the allocation table; the reaper thread)
+# ---- ThreadSanitizer: the multi-threaded scenarios (application threads racing on the allocation table; the pager and the pool-grower threads)
 TS=$P/build/tsan; mkdir -p $TS; ln -sf $L/libtsan.so.2 $TS/libtsan.so
 FT="-std=c++17 -O1 -g -fno-omit-frame-pointer -DVGPU_NO_DLSYM_OVERRIDE -fsanitize=thread -fPIC -fvisibility=hidden -I$R/include -I/usr/local/cuda/include"
 for f in driver region kmod swap limiter runtime cabi plugin_core sched_core hook passthrough; do g++ $FT -c -o $TS/$f.o $P/csrc/$f.cc || exit 1; done
@@ -47,7 +49,9 @@ g++ -shared -fsanitize=thread -L$TS -Wl,-soname,libvgpu.so -o $TS/libvgpu.so $TS
 PRE=$L/libtsan.so.2:$TS/libvgpu.so
 export TSAN_OPTIONS="halt_on_error=0 log_path=$T/tsan"
 run CUDA_DEVICE_MEMORY_LIMIT_0=64m -- $R/oracle/_ref/hook_stress threads 8 1500
-run $SW CUDA_DEVICE_MEMORY_LIMIT_0=256m VGPU_SWAP_ASYNC_UNMAP=1 -- $SB --buffers 24 --steps 72 --order cyclic
+run $SW CUDA_DEVICE_MEMORY_LIMIT_0=256m -- $SB --buffers 24 --steps 96 --order cyclic
+run $SW CUDA_DEVICE_MEMORY_LIMIT_0=256m VGPU_SWAP_PREFETCH_MB=0 -- $SB --buffers 24 --steps 72 --order cyclic
+run $SW CUDA_DEVICE_MEMORY_LIMIT_0=256m VGPU_SWAP_HOST_BACKED=1 -- $SB --buffers 24 --steps 72 --order zipf
 run FAKE_GPU_EXEC=1 CUDA_DEVICE_SM_LIMIT=30 GPU_CORE_UTILIZATION_POLICY=force CUDA_DEVICE_MEMORY_LIMIT_0=1g -- $P/lib/launch_loop $P/build/vgpu_kernels.cubin 8 2
 run $SW CUDA_DEVICE_MEMORY_LIMIT_0=128m -- $R/oracle/_ref/hook_stress swap 4 80
 if ls $T/tsan.* > /dev/null 2>&1; then echo "TSAN REPORTS:"; head -80 $T/tsan.*; exit 1; fi
