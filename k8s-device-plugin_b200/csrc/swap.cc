@@ -210,9 +210,11 @@ bool SwapEngine::init(int dev, const SwapConfig &cfg) {
     if (d.cuMemHostGetDevicePointer_v2(&dh_tbl_stage_, h_tbl_stage_, 0) != CUDA_SUCCESS) return false;
     scanner_.reset(new VictimScanner());
     if (scanner_->init(k_, tbl_cap_) != CUDA_SUCCESS) return false;
-    use_ring_.resize(1024);
+    own_events_.resize(1024);
+    for (auto &e : own_events_) if (d.cuEventCreate(&e, CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) return false;
+    use_ring_.assign(1024, nullptr);
     use_stream_.assign(1024, nullptr);
-    for (auto &e : use_ring_) if (d.cuEventCreate(&e, CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) return false;
+    use_ctx_.assign(1024, nullptr);
     d.cuCtxGetCurrent(&ctx_);
     pager_ = std::thread([this] { pager_main(); });
     LOG_INFO("swap engine dev %d (numa %d): resident cap %lu MiB, virtual cap %lu MiB, staging %zu MiB x %d, copies %zu MiB, prefetch %lu MiB, arena %lu GiB, gran %zu",
@@ -250,7 +252,8 @@ SwapEngine::~SwapEngine() {
     for (auto &s : ring_out_) { if (s.buf) d.cuMemFree_v2(s.buf); if (s.busy) d.cuEventDestroy_v2(s.busy); }
     for (auto &s : ring_in_) { if (s.buf) d.cuMemFree_v2(s.buf); if (s.busy) d.cuEventDestroy_v2(s.busy); }
     for (auto &sl : slabs_) if (sl.host) d.cuMemFreeHost(sl.host);
-    for (auto &e : use_ring_) if (e) d.cuEventDestroy_v2(e);
+    for (auto &e : own_events_) if (e) d.cuEventDestroy_v2(e);
+    for (auto &c : ctx_events_) for (auto &e : c.ev) if (e) d.cuEventDestroy_v2(e);
     for (auto &e : ev_pool_) d.cuEventDestroy_v2(e);
     for (auto &p : prof_) { d.cuEventDestroy_v2(p.a); d.cuEventDestroy_v2(p.b); }
     if (d_span_) d.cuMemFree_v2(d_span_);
@@ -507,6 +510,17 @@ void SwapEngine::retire_row_locked(int row) {
 }
 
 // ---------------------------------------------------------------------------------------------- events / rings
+// the last-use event of ring slot `slot` that belongs to context `cur` (an event is recorded on a stream of its own context)
+CUevent SwapEngine::use_slot_event(CUcontext cur, size_t slot) {
+    if (cur == ctx_) return own_events_[slot];
+    for (CtxEvents &c : ctx_events_) if (c.ctx == cur) return c.ev[slot];
+    CtxEvents c;
+    c.ctx = cur;
+    c.ev.assign(own_events_.size(), nullptr);
+    for (auto &e : c.ev) if (drv().cuEventCreate(&e, CU_EVENT_DISABLE_TIMING) != CUDA_SUCCESS) { e = nullptr; LOG_ERROR("cuEventCreate in a second context failed"); }
+    ctx_events_.push_back(std::move(c));
+    return ctx_events_.back().ev[slot];
+}
 CUevent SwapEngine::use_event(uint64_t seq) {
     if (seq == 0) return nullptr;
     if (seq + use_ring_.size() <= use_seq_) return nullptr;  // slot was recycled: that use is known complete (note_use)
@@ -1881,14 +1895,13 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
         st_.faults += missing.size();
         st_.demand_waits++;
         if (!ctx_warned_) {
-            // The engine's module, side streams and events live in the context that was current when the first swappable
-            // allocation created it. An application that hops between SEVERAL contexts of one device is outside what swap
-            // mode supports; say so once instead of failing obscurely inside the driver.
+            // The engine's module, side streams and page-in events live in the context that was current when the first
+            // swappable allocation created it; another context of the same device can use the buffers all the same (events
+            // are waited on across contexts, last-use events are kept per context, see note_use). Said once, for the log.
             CUcontext cur = nullptr;
-            if (d.cuCtxGetCurrent(&cur) == CUDA_SUCCESS && cur != ctx_) {
+            if (d.cuCtxGetCurrent(&cur) == CUDA_SUCCESS && cur && cur != ctx_) {
                 ctx_warned_ = true;
-                LOG_ERROR("device %d: a paged-out buffer is used from context %p, the swap engine lives in %p — several contexts on one "
-                          "device are not supported in swap mode", dev_, (void *)cur, (void *)ctx_);
+                LOG_INFO("device %d: swappable buffers are used from context %p, the swap engine lives in %p", dev_, (void *)cur, (void *)ctx_);
             }
         }
         uint64_t need = 0, pinned = 0;
@@ -1960,9 +1973,12 @@ void SwapEngine::note_use(const int *rows, int n, CUstream stream, bool writes) 
     std::lock_guard<std::mutex> g(mu_);
     uint64_t seq = ++use_seq_;
     size_t ring = use_ring_.size();
-    CUevent ev = use_ring_[seq % ring];
+    CUcontext cur = nullptr;
+    d.cuCtxGetCurrent(&cur);
+    if (!cur) cur = ctx_;
     // the slot's previous owner (seq - ring size) is only forgotten once it is known complete, see use_event()
-    if (seq > ring) d.cuEventSynchronize(ev);
+    if (CUevent prev = use_ring_[seq % ring]) d.cuEventSynchronize(prev);
+    CUevent ev = use_slot_event(cur, seq % ring);
     // A row remembers one outstanding use per stream (up to kMaxUses): a later eviction or free waits for ALL of them — work
     // queued on stream A must not lose its operand because stream B used it afterwards. A row used from more streams than
     // that gets its oldest use chained in front of this one.
@@ -1972,7 +1988,7 @@ void SwapEngine::note_use(const int *rows, int n, CUstream stream, bool writes) 
         for (int j = 0; j < s.nuses; j++) {
             uint64_t q = s.uses[j];
             if (q + ring <= seq) continue;                                 // recycled: complete
-            if (use_stream_[q % ring] == stream) continue;                 // same stream: this use supersedes it
+            if (use_stream_[q % ring] == stream && use_ctx_[q % ring] == cur) continue;   // same stream: this use supersedes it
             s.uses[k++] = q;
         }
         s.nuses = k;
@@ -1982,8 +1998,10 @@ void SwapEngine::note_use(const int *rows, int n, CUstream stream, bool writes) 
             s.nuses--;
         }
     }
-    d.cuEventRecord(ev, stream);
+    if (ev) d.cuEventRecord(ev, stream);
+    use_ring_[seq % ring] = ev;
     use_stream_[seq % ring] = stream;
+    use_ctx_[seq % ring] = cur;
     for (int i = 0; i < n; i++) {
         Side &s = side_[rows[i]];
         s.uses[s.nuses++] = seq;

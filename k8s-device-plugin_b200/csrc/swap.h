@@ -308,8 +308,16 @@ class SwapEngine {
     uint64_t live_mapped_ = 0;                      // mapped-size sum of the live rows (all resident => nothing to prefetch)
     std::deque<uint32_t> evicting_;                 // rows in PH_EVICTING, issue order
     std::deque<uint32_t> zombies_;
-    std::vector<CUevent> use_ring_;                 // last-use events, indexed by seq % size
-    std::vector<CUstream> use_stream_;              // stream each use event was recorded on
+    std::vector<CUevent> use_ring_;                 // the last-use event recorded for sequence number seq, at seq % size
+    std::vector<CUstream> use_stream_;              // stream each use event was recorded on ...
+    std::vector<CUcontext> use_ctx_;                // ... and the context that stream belongs to (stream 0 exists once per context)
+    // An event must be recorded on a stream of ITS OWN context, so every context the application uses the buffers from gets
+    // its own set of last-use events (the engine context's set is own_events_). Waiting on them from the pager's streams and
+    // on the page-in events from the application's streams works across contexts.
+    std::vector<CUevent> own_events_;
+    struct CtxEvents { CUcontext ctx; std::vector<CUevent> ev; };
+    std::vector<CtxEvents> ctx_events_;
+    CUevent use_slot_event(CUcontext cur, size_t slot);
     uint64_t use_seq_ = 0;
     bool stop_ = false, pager_idle_ = true, kick_ = false;
     void kick_pager_locked() { kick_ = true; cv_pager_.notify_one(); }

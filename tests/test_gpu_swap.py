@@ -208,6 +208,55 @@ def test_kernel_dereferencing_a_device_side_pointer_table_reads_paged_out_buffer
     assert out["bad"] == 0 and out["paged_out_before"] >= 5, out
 
 
+_TWO_CONTEXTS = r"""
+import ctypes as C, json, os, sys
+sys.path.insert(0, os.environ["VGPU_ROOT"])
+import torch
+import k8s_device_plugin_b200 as v
+torch.zeros(1, device="cuda")                                   # context A: the device's primary context (the engine lives here)
+L = v.lib(); cu = C.CDLL("libcuda.so.1")
+M = 1 << 20
+sw = v.Swap(resident_cap=128 * M, prefetch_bytes=None)
+n, nbytes = 8, 32 * M                                           # 256 MiB live under a 128 MiB quota
+stA = torch.cuda.current_stream().cuda_stream
+bufs = [sw.alloc(nbytes) for _ in range(n)]
+for i, p in enumerate(bufs):
+    sw.acquire([p], stA); assert L.vgpu_wl_fill(p, nbytes // 8, i, C.c_void_p(stA)) == 0; sw.release([p], stA)
+torch.cuda.synchronize()
+ctxB = C.c_void_p()
+assert cu.cuCtxCreate_v2(C.byref(ctxB), 0, 0) == 0              # context B on the SAME device, current on this thread now
+stB = C.c_void_p()
+assert cu.cuStreamCreate(C.byref(stB), 1) == 0
+touches = [0] * n
+for t in range(3 * n):                                          # every touch misses: page-ins are waited for across contexts,
+    i = t % n                                                   # last-use events are recorded in context B
+    sw.acquire([bufs[i]], stB.value); assert L.vgpu_wl_touch(bufs[i], nbytes // 8, stB) == 0; sw.release([bufs[i]], stB.value)
+    touches[i] += 1
+assert cu.cuStreamSynchronize(stB) == 0
+popped = C.c_void_p()
+assert cu.cuCtxPopCurrent_v2(C.byref(popped)) == 0              # back to context A
+cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+for i, p in enumerate(bufs):
+    sw.acquire([p], stA); assert L.vgpu_wl_verify(p, nbytes // 8, i, touches[i], cnt.data_ptr(), C.c_void_p(stA)) == 0; sw.release([p], stA)
+torch.cuda.synchronize()
+s = sw.stats()
+print(json.dumps({"bad": int(cnt.item()), "faults": s["faults"], "evictions": s["evictions"]}))
+"""
+
+
+def test_buffers_used_from_a_second_context_of_the_same_device(tmp_path):
+    """VERDICT r1 'missing' #3: several contexts on one device in swap mode. The engine (pager, streams, page-in events) lives
+    in the context it was created in; a second context of the same device touches the same buffers: every touch misses,
+    its stream waits on a page-in event of the other context, its last-use event is created in ITS context (an event is
+    recorded on a stream of its own context), and evictions wait on those. Every word must be right afterwards."""
+    import json, os, subprocess, sys
+    env = dict(os.environ, VGPU_ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", _TWO_CONTEXTS], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["bad"] == 0 and out["faults"] >= 3 * 8 and out["evictions"] >= 3 * 8 - 4, out
+
+
 def test_ragged_sizes_and_multi_buffer_admission():
     sw = v.Swap(resident_cap=128 * MiB, chunk_bytes=8 * MiB, ring_slots=2)
     sizes = [3 * MiB + 8, 17 * MiB + 4096, 2 * MiB + 16, 40 * MiB, 5 * MiB + 1000 * 8, 33 * MiB, 9 * MiB + 8, 26 * MiB]
