@@ -188,13 +188,22 @@ CUresult VictimScanner::scan(CUdeviceptr d_tbl, uint32_t n, uint64_t need, uint6
         void *a[] = {&d_tbl, &n, &d_state_, &need, &idx_bits, &key_bits, &d_out_, &cap_};
         if ((r = d.cuLaunchKernel(k_->victim_small, 1, 1, 1, 1024, 1, 1, 0, stream, a, nullptr)) != CUDA_SUCCESS) return r;
         launches++;
-    } else if (k_->cooperative && k_->victim_persist && n <= (uint64_t)k_->sm_count * VGPU_SCAN_PERSIST_ROWS_PER_CTA && !multilaunch_only()) {
+    } else {
+    bool persisted = false;
+    if (k_->cooperative && k_->victim_persist && !persist_refused_ && n <= (uint64_t)k_->sm_count * VGPU_SCAN_PERSIST_ROWS_PER_CTA && !multilaunch_only()) {
         // one cooperative launch, the table slice of every CTA stays in registers across the digit passes (kernels.cu)
         unsigned grid = (unsigned)((n + VGPU_SCAN_PERSIST_ROWS_PER_CTA - 1) / VGPU_SCAN_PERSIST_ROWS_PER_CTA);
         void *a[] = {&d_tbl, &n, &d_state_, &need, &idx_bits, &key_bits, &d_out_, &cap_};
-        if ((r = d.cuLaunchCooperativeKernel(k_->victim_persist, grid, 1, 1, 1024, 1, 1, 0, stream, a)) != CUDA_SUCCESS) return r;
-        launches++;
-    } else {
+        r = d.cuLaunchCooperativeKernel(k_->victim_persist, grid, 1, 1, 1024, 1, 1, 0, stream, a);
+        if (r == CUDA_SUCCESS) { launches++; persisted = true; }
+        else {
+            // a context that cannot co-schedule the grid (MPS, a partitioned device): nothing has run — use the launch-per-digit
+            // path from now on
+            persist_refused_ = true;
+            LOG_WARN("cooperative launch of the single-launch victim scan refused (%d %s): using the multi-launch path", (int)r, cu_err(r));
+        }
+    }
+    if (!persisted) {
     {
         void *a[] = {&d_state_, &need};
         if ((r = d.cuLaunchKernel(k_->victim_init, 1, 1, 1, 256, 1, 1, 0, stream, a, nullptr)) != CUDA_SUCCESS) return r;
@@ -224,6 +233,7 @@ CUresult VictimScanner::scan(CUdeviceptr d_tbl, uint32_t n, uint64_t need, uint6
         void *a[] = {&d_tbl, &n, &d_state_, &idx_bits, &chunk, &d_out_, &cap_};
         if ((r = d.cuLaunchKernel(k_->victim_emit, grid, 1, 1, 256, 1, 1, 0, stream, a, nullptr)) != CUDA_SUCCESS) return r;
         launches++;
+    }
     }
     }
     if (launches_out) *launches_out += launches;

@@ -55,6 +55,7 @@ class VictimScanner {
     const Kernels *k_ = nullptr;
     CUdeviceptr d_state_ = 0, d_out_ = 0, dh_state_ = 0, dh_out_ = 0;   // dh_*: device view of the pinned result buffers
     uint32_t cap_ = 0;
+    bool persist_refused_ = false;   // the context refused the cooperative launch once: stay on the multi-launch path
     void *h_state_ = nullptr;   // pinned: VgpuScanState header readback
     uint32_t *h_out_ = nullptr; // pinned
 };

@@ -625,3 +625,70 @@ def test_application_threads_share_the_swap_engine(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["errors"] == 0 and out["bad_words"] == 0 and out["buf"] == 0, out
+
+
+def test_uvm_style_hints_and_pinning_through_the_hook(tmp_path):
+    """An unmodified driver-API program under LD_PRELOAD on the functional fake: cuMemAdvise(SET_READ_MOSTLY) and
+    cuMemPrefetchAsync on swappable pointers are intercepted (the driver would refuse a non-managed pointer; under the
+    reference they are legal because its swappable memory is managed), vgpu_runtime_swap_pin keeps a buffer resident while
+    everything else cycles through the quota."""
+    code = r"""
+import ctypes as C, json, os, sys
+cu = C.CDLL("libcuda.so.1")                     # the fake driver; the hook sits in front of it (LD_PRELOAD)
+def ck(rc, what):
+    assert rc == 0, (what, rc)
+ck(cu.cuInit(0), "init")
+dev, ctx, mod = C.c_int(), C.c_void_p(), C.c_void_p()
+ck(cu.cuDeviceGet(C.byref(dev), 0), "dev"); ck(cu.cuDevicePrimaryCtxRetain(C.byref(ctx), dev), "ctx"); ck(cu.cuCtxSetCurrent(ctx), "cur")
+ck(cu.cuModuleLoad(C.byref(mod), os.environ["CUBIN"].encode()), "mod")
+f_fill, f_touch, f_verify = C.c_void_p(), C.c_void_p(), C.c_void_p()
+for f, nm in ((f_fill, b"vgpu_wl_fill"), (f_touch, b"vgpu_wl_touch"), (f_verify, b"vgpu_wl_verify")):
+    ck(cu.cuModuleGetFunction(C.byref(f), mod, nm), nm)
+M = 1 << 20
+n, nbytes = 12, 16 * M                                       # 192 MiB live under a 96 MiB quota
+bufs = []
+for i in range(n):
+    p = C.c_uint64()
+    ck(cu.cuMemAlloc_v2(C.byref(p), C.c_size_t(nbytes)), "alloc")
+    bufs.append(p)
+def launch(f, *vals):
+    holders = [C.c_uint64(v) for v in vals]
+    arr = (C.c_void_p * len(holders))(*[C.cast(C.byref(h), C.c_void_p) for h in holders])
+    ck(cu.cuLaunchKernel(f, 64, 1, 1, 256, 1, 1, 0, None, arr, None), "launch")
+for i, p in enumerate(bufs):
+    launch(f_fill, p.value, nbytes // 8, i)
+hook = C.CDLL(None)
+pin = hook.vgpu_runtime_swap_pin; pin.argtypes = [C.c_uint64, C.c_int]
+class St(C.Structure):
+    _fields_ = [("v", C.c_uint64 * 17), ("pack_ms", C.c_double), ("unpack_ms", C.c_double), ("rest", C.c_uint64 * 64)]
+stats = hook.vgpu_runtime_swap_stats; stats.argtypes = [C.c_int, C.POINTER(St)]
+ck(pin(bufs[0].value, 1), "pin")                              # buffer 0 stays resident from here on
+for i in range(1, n, 2):
+    ck(cu.cuMemAdvise(C.c_uint64(bufs[i].value), C.c_size_t(nbytes), 1, dev), "advise read-mostly")      # CU_MEM_ADVISE_SET_READ_MOSTLY = 1
+ck(cu.cuMemAdvise(C.c_uint64(bufs[2].value), C.c_size_t(nbytes), 3, dev), "advise preferred location")  # accepted, ignored
+cnt = C.c_uint64()
+ck(cu.cuMemAlloc_v2(C.byref(cnt), 8), "cnt"); ck(cu.cuMemsetD8_v2(cnt, 0, 8), "cnt0")
+touches = [0] * n
+for sweep in range(4):
+    for i, p in enumerate(bufs):
+        if i % 2:                                             # read-mostly buffers are only read
+            launch(f_verify, p.value, nbytes // 8, i, 0, cnt.value)
+        else:
+            launch(f_touch, p.value, nbytes // 8); touches[i] += 1
+ck(cu.cuMemPrefetchAsync(C.c_uint64(bufs[5].value), C.c_size_t(nbytes), dev, None), "prefetch")
+ck(cu.cuCtxSynchronize(), "sync")
+for i, p in enumerate(bufs):
+    launch(f_verify, p.value, nbytes // 8, i, touches[i], cnt.value)
+ck(cu.cuCtxSynchronize(), "sync")
+bad = C.c_uint64(); ck(cu.cuMemcpyDtoH_v2(C.byref(bad), cnt, 8), "read")
+s = St(); ck(stats(0, C.byref(s)), "stats")
+print(json.dumps({"bad": bad.value, "page_out": s.v[0], "page_in": s.v[1], "evictions": s.v[2], "faults": s.v[3]}))
+"""
+    env = _env(tmp_path, LD_PRELOAD=HOOK_SO, CUDA_OVERSUBSCRIBE="true", CUDA_DEVICE_MEMORY_LIMIT_0="96m", CUBIN=CUBIN, VGPU_SWAP_CHUNK_MB="2", VGPU_SWAP_RING="2",
+               VGPU_SWAP_PREFETCH_MB="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["bad"] == 0 and out["faults"] > 30
+    # half of the buffers are read-mostly: their evictions carry no write-back, so far less went out than came in
+    assert out["page_out"] < 0.7 * out["page_in"], out
