@@ -236,8 +236,9 @@ CUresult VictimScanner::scan(CUdeviceptr d_tbl, uint32_t n, uint64_t need, uint6
     }
     }
     }
-    if (launches_out) *launches_out += launches;
     if ((r = launch_copy16(k_, dh_state_, d_state_, 64, stream)) != CUDA_SUCCESS) return r;
+    launches += 2;                                        // the two result copies below are kernels too (vgpu_copy16)
+    if (launches_out) *launches_out += launches;
     // optimistic first page of indices; the rest (rare) after the count is known
     uint32_t first = cap_ < 1024 ? cap_ : 1024;
     if ((r = launch_copy16(k_, dh_out_, d_out_, ((size_t)first * 4 + 15) & ~(size_t)15, stream)) != CUDA_SUCCESS) return r;

@@ -468,6 +468,7 @@ CUresult SwapEngine::sync_table(Lock &lk, CUstream s) {
     dirty_lo_ = UINT32_MAX; dirty_hi_ = 0;
     // by kernel, not by a copy engine: a 30 KiB cuMemcpyAsync would queue behind all the page traffic (see vgpu_copy16)
     CU_TRY(launch_copy16(k_, d_tbl_ + (size_t)lo * sizeof(VgpuEntry), dh_tbl_stage_ + (size_t)lo * sizeof(VgpuEntry), (size_t)(hi - lo) * sizeof(VgpuEntry), s));
+    pst_.scan_launches++;                                 // the upload is a kernel launch of ours like the scan itself
     return CUDA_SUCCESS;
 }
 
@@ -954,7 +955,6 @@ void SwapEngine::begin_evict_locked(const std::vector<uint32_t> &victims, std::v
         rows_[v].state = VGPU_ST_PAGED_OUT;
         mark_dirty((int)v);
         s.phase = PH_EVICTING;
-        s.nuses = 0;
         resident_mapped_ -= s.mapped;
         evicting_mapped_ += s.mapped;
         if (s.prefetched) { s.prefetched = false; prefetched_bytes_ -= s.mapped; pst_.prefetch_wasted++; }
@@ -1026,6 +1026,7 @@ CUresult SwapEngine::evict_direct(Lock &lk, const std::vector<uint32_t> &victims
         s.has_host = it.has_host;
         s.hhandle = it.hh; s.has_hh = it.has_hh;
         if (it.copy) s.dirty = false;              // once the copy is done the block equals the HBM content
+        s.nuses = 0;                               // the page-out is ordered behind every outstanding use (it.wait)
         if (s.ready) { put_event(s.ready); s.ready = nullptr; }   // its waiters are enqueued; the record they refer to is fixed
         if (s.evict_done) put_event(s.evict_done);
         s.evict_done = it.done;
@@ -1329,6 +1330,7 @@ CUresult SwapEngine::swap_staged(Lock &lk, int row, const std::vector<uint32_t> 
         }
         pool_phys(s.mapped, s.handle);
         s.has_handle = false;
+        s.nuses = 0;
         s.host_off = it.host_off; s.has_host = it.has_host;
         if (it.copy) { s.dirty = false; s.out_slot = it.out_slot; s.out_seq = it.out_seq; }
         if (s.ready) { put_event(s.ready); s.ready = nullptr; }
@@ -1549,7 +1551,9 @@ bool SwapEngine::step_demand(Lock &lk) {
         cv_admit_.notify_all();
         return true;
     };
-    if (budget_fn_) reserve_locked(0);                // the siblings may have grown or let go: refresh the cap
+    // the siblings may have grown or let go: refresh the cap (a semaphore round trip on the container's region: at most
+    // every 200 us — this step runs every 40 us while a demand waits)
+    if (budget_fn_ && mono_ns() - budget_checked_ns_ > 200000ull) reserve_locked(0);
     if (need > cfg_.resident_cap && sibling_engines_ <= 1) return fail(CUDA_ERROR_OUT_OF_MEMORY);
     int64_t free_now = free_phys_locked();
     if (free_now >= (int64_t)need && reserve_locked(need)) {
