@@ -988,6 +988,7 @@ CUresult SwapEngine::evict_direct(Lock &lk, const std::vector<uint32_t> &victims
                 if (!ok || !host_alloc(it.len, &it.host_off)) { rc = CUDA_ERROR_OUT_OF_MEMORY; it.failed = true; put_event(it.done); it.done = nullptr; continue; }
             }
             it.has_host = true;
+            it.new_host = true;
         }
         CUstream s = it.copy ? s_out_ : s_scan_;
         ScopedNs t_issue(&pst_.pager_issue_ns);
@@ -999,9 +1000,15 @@ CUresult SwapEngine::evict_direct(Lock &lk, const std::vector<uint32_t> &victims
                 uint64_t n = std::min<uint64_t>(cfg_.copy_bytes, it.len - o);
                 CUresult r = cfg_.host_backed ? d.cuMemcpyDtoDAsync_v2(harena_ + it.va_off + o, it.base + o, n, s)     // the alias range IS host memory
                                               : d.cuMemcpyDtoHAsync_v2(hp + o, it.base + o, n, s);
-                if (r != CUDA_SUCCESS) { LOG_ERROR("page-out copy failed: %d %s", (int)r, cu_err(r)); rc = r; break; }
+                if (r != CUDA_SUCCESS) { LOG_ERROR("page-out copy failed: %d %s", (int)r, cu_err(r)); rc = r; it.failed = true; break; }
             }
             if (tr) trace_end(s);
+            if (it.failed) {
+                // the block would hold part of the buffer: the victim stays resident (and dirty), a block taken for it goes back
+                if (it.new_host) { release_host_range(it.host_off, it.len); it.has_host = false; }
+                put_event(it.done); it.done = nullptr;
+                continue;
+            }
             pst_.page_out_bytes += it.len;
             pst_.direct_out_bytes += it.len;
         } else {
@@ -1013,13 +1020,14 @@ CUresult SwapEngine::evict_direct(Lock &lk, const std::vector<uint32_t> &victims
     for (OutItem &it : items) {
         Side &s = side_[it.row];
         if (it.failed) {
-            // the pinned pool is exhausted: this victim stays resident
+            // no block for it (the pinned pool is exhausted) or the copy could not be issued: this victim stays resident
             rows_[it.row].state = VGPU_ST_RESIDENT;
             mark_dirty((int)it.row);
             s.phase = PH_IDLE;
             evicting_mapped_ -= s.mapped;
             resident_mapped_ += s.mapped;
-            LOG_ERROR("pinned host pool exhausted (%lu MiB in use): cannot page out", (unsigned long)(host_used_.load() >> 20));
+            if (cfg_.host_backed) { s.hhandle = it.hh; s.has_hh = it.has_hh; }      // a backing made for it is kept for the next time
+            LOG_ERROR("cannot page out row %u (pinned host pool: %lu MiB in use)", it.row, (unsigned long)(host_used_.load() >> 20));
             continue;
         }
         s.host_off = it.host_off;
@@ -1150,6 +1158,14 @@ CUresult SwapEngine::load_direct(Lock &lk, std::vector<InItem> &items) {
             if (r != CUDA_SUCCESS) { LOG_ERROR("page-in copy failed: %d %s", (int)r, cu_err(r)); it.rc = r; break; }
         }
         if (tr) trace_end(s_in_);
+        if (it.rc != CUDA_SUCCESS) {
+            // part of the row may be on its way in: let the stream run dry before the range goes away again
+            d.cuStreamSynchronize(s_in_);
+            std::vector<std::pair<CUdeviceptr, size_t>> one{{it.base, it.mapped}};
+            unmap_batch(one);
+            pool_phys(it.mapped, it.h);
+            continue;
+        }
         d.cuEventRecord(it.ready, s_in_);
         pst_.page_in_bytes += it.len;
         pst_.direct_in_bytes += it.len;
@@ -1449,11 +1465,11 @@ bool SwapEngine::step_zombies(Lock &lk) {
     for (uint32_t r : ready_rows) {
         Side &s = side_[r];
         s.has_hh = false; s.hosted = false;
-        if (!s.has_handle) { if (s.has_host && !cfg_.host_backed) release_host_range(s.host_off, round_up(rows_[r].size, 256)); s.has_host = false; retire_row_locked((int)r); continue; }
+        if (!s.has_handle) { if (s.has_host && !cfg_.host_backed) release_host_range(s.host_off, s.zombie_len); s.has_host = false; retire_row_locked((int)r); continue; }
         pool_phys(s.mapped, s.handle);
         s.has_handle = false;
         resident_mapped_ -= s.mapped;
-        if (s.has_host && !cfg_.host_backed) release_host_range(s.host_off, round_up(rows_[r].size, 256));
+        if (s.has_host && !cfg_.host_backed) release_host_range(s.host_off, s.zombie_len);
         s.has_host = false;
         retire_row_locked((int)r);
     }
@@ -1832,6 +1848,7 @@ CUresult SwapEngine::free(CUdeviceptr dptr) {
     host_want_.store(host_need_);
     s.pins = 0;                                  // rows pinned for a stream capture are never unpinned by note_use
     s.locked = false;
+    s.zombie_len = round_up(rows_[row].size, 256);
     if (last_row_ == row) last_row_ = -1;
     if (rows_[row].state & VGPU_ST_RESIDENT) {
         // still mapped, maybe still in use by queued work: the pager unmaps it once its last users are done and only then

@@ -170,6 +170,7 @@ class SwapEngine {
         bool has_handle = false;
         uint64_t host_off = 0;   // pinned block (kept across page-ins: a clean row is evicted without a copy)
         bool has_host = false;
+        uint64_t zombie_len = 0; // free(): the block's length, kept for the pager (the table row's size is zeroed at once)
         bool dirty = false;      // HBM content differs from the pinned block (or there is none yet and the row was written)
         bool read_mostly = false;
         bool prefetched = false; // paged in ahead of need and not touched since
@@ -222,7 +223,7 @@ class SwapEngine {
     bool step_demand(Lock &lk);
     bool step_prefetch(Lock &lk);
     bool step_evict_ahead(Lock &lk);
-    struct OutItem { uint32_t row; CUdeviceptr base; uint64_t len; size_t mapped; uint64_t host_off; bool has_host, copy; uint64_t va_off = 0; CUmemGenericAllocationHandle hh = 0; bool has_hh = false; std::vector<CUevent> wait; CUevent done = nullptr; int out_slot = -1; uint64_t out_seq = 0; bool failed = false; };
+    struct OutItem { uint32_t row; CUdeviceptr base; uint64_t len; size_t mapped; uint64_t host_off; bool has_host, copy; bool new_host = false; uint64_t va_off = 0; CUmemGenericAllocationHandle hh = 0; bool has_hh = false; std::vector<CUevent> wait; CUevent done = nullptr; int out_slot = -1; uint64_t out_seq = 0; bool failed = false; };
     struct InItem { int row; CUdeviceptr base; uint64_t len; size_t mapped; uint64_t host_off; bool has_host; bool prefetch; uint64_t va_off = 0; bool hosted = false; CUmemGenericAllocationHandle h = 0; CUevent ready = nullptr;
                     CUevent after = nullptr; CUresult rc = CUDA_SUCCESS; };
     CUresult choose_victims(Lock &lk, uint64_t shortage, std::vector<uint32_t> *victims, uint64_t *evictable);

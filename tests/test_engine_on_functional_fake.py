@@ -361,8 +361,23 @@ for step in range(int(os.environ.get("FUZZ_STEPS", "260"))):
 for k, e in live.items():
     sw.acquire([e[0]], 0); L.vgpu_wl_verify(C.c_uint64(e[0]), C.c_uint64(e[1] // 8), C.c_uint64(e[2]), C.c_uint64(e[3]), C.c_uint64(C.addressof(bad)), None); sw.release([e[0]], 0)
 st = sw.stats()
+if os.environ.get("FUZZ_FREE_ALL") == "1":
+    # every buffer goes — resident ones (clean ones still own a pinned block), paged-out ones: the pinned pool must be empty after
+    for e in live.values():
+        sw.free(e[0])
+    sw.drain()
+    import time
+    for _ in range(200):
+        after = sw.stats()
+        if after["host_bytes"] == 0 and after["resident_bytes"] == 0:
+            break
+        time.sleep(0.01)
+else:
+    after = st
 print(json.dumps({"bad": int(bad[0]), "peak_resident": peak_resident, "ops": ops, "live": st["live_bytes"], "expect_live": sum(e[1] for e in live.values()),
-                  "entries": st["entries"], "expect_entries": len(live), "faults": st["faults"], "evictions": st["evictions"]}))
+                  "entries": st["entries"], "expect_entries": len(live), "faults": st["faults"], "evictions": st["evictions"],
+                  "host_before_free": st["host_bytes"], "host_after_free": after["host_bytes"], "resident_after_free": after["resident_bytes"],
+                  "live_after_free": after["live_bytes"]}))
 """
 
 
@@ -383,12 +398,14 @@ def test_engine_fuzz_random_sizes_frees_and_two_operand_admissions(tmp_path, see
     """Randomised integrity test of the engine through the C ABI on the functional fake: ragged sizes (not multiples of
     the 2 MiB granule or the 4 MiB staging slot), frees in between, single and two-operand admissions, spot checks and a
     final check of every word of every live buffer; residency never exceeds the cap, bookkeeping matches the model."""
-    env = _env(tmp_path, VGPU_ROOT=ROOT, FUZZ_SEED=seed)
+    env = _env(tmp_path, VGPU_ROOT=ROOT, FUZZ_SEED=seed, FUZZ_FREE_ALL=1)
     r = subprocess.run([sys.executable, "-c", _ENGINE_FUZZ], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["bad"] == 0, out
     assert out["peak_resident"] <= 48 * M and out["live"] == out["expect_live"] and out["entries"] == out["expect_entries"]
+    # freeing everything returns every pinned block (a freed RESIDENT buffer gives its clean block back through the pager)
+    assert out["host_before_free"] > 0 and out["host_after_free"] == 0 and out["resident_after_free"] == 0 and out["live_after_free"] == 0, out
     assert out["faults"] > 20 and out["evictions"] > 20 and out["ops"]["pair"] > 5 and out["ops"]["free"] > 5
 
 
