@@ -21,7 +21,7 @@ namespace vgpu {
     X(cuMemAllocHost_v2) X(cuMemGetAddressRange_v2) X(cuMemHostUnregister) X(cuMipmappedArrayCreate) X(cuMipmappedArrayDestroy) X(cuPointerGetAttribute) X(cuPointerGetAttributes)                                                            \
     X(cuMemcpy2D_v2) X(cuMemcpy2DUnaligned_v2) X(cuMemcpy2DAsync_v2) X(cuMemcpy3D_v2) X(cuMemcpy3DAsync_v2)            \
     X(cuMemsetD2D8_v2) X(cuMemsetD2D16_v2) X(cuMemsetD2D32_v2) X(cuMemsetD2D8Async) X(cuMemsetD2D16Async) X(cuMemsetD2D32Async) \
-    X(cuMemcpyPeer) X(cuMemcpyPeerAsync)                                                               \
+    X(cuMemcpyPeer) X(cuMemcpyPeerAsync) X(cuMemcpyBatchAsync) X(cuMemcpy3DBatchAsync)                 \
     X(cuMemAddressReserve) X(cuMemAddressFree) X(cuMemCreate) X(cuMemRelease) X(cuMemMap) X(cuMemUnmap)           \
     X(cuMemSetAccess) X(cuMemGetAllocationGranularity)                                                            \
     X(cuMemcpyHtoD_v2) X(cuMemcpyDtoH_v2) X(cuMemcpyDtoD_v2) X(cuMemcpyHtoDAsync_v2) X(cuMemcpyDtoHAsync_v2)      \
@@ -44,7 +44,7 @@ namespace vgpu {
     X(cuMemAllocAsync, _ptsz) X(cuMemAllocFromPoolAsync, _ptsz) X(cuMemFreeAsync, _ptsz)                          \
     X(cuMemcpyHtoD_v2, _ptds) X(cuMemcpyDtoH_v2, _ptds) X(cuMemcpyDtoD_v2, _ptds) X(cuMemcpy, _ptds)              \
     X(cuMemcpyHtoDAsync_v2, _ptsz) X(cuMemcpyDtoHAsync_v2, _ptsz) X(cuMemcpyDtoDAsync_v2, _ptsz)                  \
-    X(cuMemcpyAsync, _ptsz)                                                                                       \
+    X(cuMemcpyAsync, _ptsz) X(cuMemcpyBatchAsync, _ptsz) X(cuMemcpy3DBatchAsync, _ptsz)                           \
     X(cuMemsetD8_v2, _ptds) X(cuMemsetD16_v2, _ptds) X(cuMemsetD32_v2, _ptds)                                     \
     X(cuMemsetD8Async, _ptsz) X(cuMemsetD16Async, _ptsz) X(cuMemsetD32Async, _ptsz)
 

@@ -215,6 +215,58 @@ VGPU_EXPORT CUresult cuMemcpyDtoDAsync_v2_ptsz(CUdeviceptr dst, CUdeviceptr src,
 VGPU_EXPORT CUresult cuMemcpyAsync_ptsz(CUdeviceptr dst, CUdeviceptr src, size_t n, CUstream st) {
     TOUCH2(dst, n, src, n, PTS(st)); CUresult r = drv().cuMemcpyAsync_ptsz(dst, src, n, st); TOUCH_DONE(PTS(st)); return r;
 }
+// Batched copies (CUDA 12.8). The reference predates them: its managed buffers simply fault in under the copy engines. Here
+// every swappable operand of the batch is admitted at once; a batch whose operands do not fit the resident quota together
+// is issued as single copies, each with its own admission (the batch's attributes are placement / ordering hints).
+template <typename Batch, typename Single>
+static CUresult batch_copy(CUdeviceptr *dsts, CUdeviceptr *srcs, size_t *sizes, size_t count, size_t *failIdx, CUstream eff, Batch batch, Single single) {
+    if (!dsts || !srcs || !sizes || count == 0) return batch();
+    if (Runtime::get().touch_batch(dsts, count, srcs, count, eff)) { CUresult r = batch(); TOUCH_DONE(eff); return r; }
+    for (size_t i = 0; i < count; i++) {
+        TOUCH2(dsts[i], sizes[i], srcs[i], sizes[i], eff);
+        CUresult r = single(dsts[i], srcs[i], sizes[i]);
+        TOUCH_DONE(eff);
+        if (r != CUDA_SUCCESS) { if (failIdx) *failIdx = i; return r; }
+    }
+    return CUDA_SUCCESS;
+}
+VGPU_EXPORT CUresult cuMemcpyBatchAsync(CUdeviceptr *dsts, CUdeviceptr *srcs, size_t *sizes, size_t count, CUmemcpyAttributes *attrs, size_t *attrsIdxs,
+                                        size_t numAttrs, size_t *failIdx, CUstream st) {
+    if (!drv().cuMemcpyBatchAsync) return CUDA_ERROR_NOT_SUPPORTED;
+    return batch_copy(dsts, srcs, sizes, count, failIdx, st,
+                      [&] { return drv().cuMemcpyBatchAsync(dsts, srcs, sizes, count, attrs, attrsIdxs, numAttrs, failIdx, st); },
+                      [&](CUdeviceptr d, CUdeviceptr s, size_t n) { return drv().cuMemcpyAsync(d, s, n, st); });
+}
+VGPU_EXPORT CUresult cuMemcpyBatchAsync_ptsz(CUdeviceptr *dsts, CUdeviceptr *srcs, size_t *sizes, size_t count, CUmemcpyAttributes *attrs, size_t *attrsIdxs,
+                                             size_t numAttrs, size_t *failIdx, CUstream st) {
+    if (!drv().cuMemcpyBatchAsync_ptsz) return CUDA_ERROR_NOT_SUPPORTED;
+    return batch_copy(dsts, srcs, sizes, count, failIdx, PTS(st),
+                      [&] { return drv().cuMemcpyBatchAsync_ptsz(dsts, srcs, sizes, count, attrs, attrsIdxs, numAttrs, failIdx, st); },
+                      [&](CUdeviceptr d, CUdeviceptr s, size_t n) { return drv().cuMemcpyAsync_ptsz(d, s, n, st); });
+}
+// 3D batches: pointer operands are admitted together (array operands are not swappable); a batch that cannot be resident
+// at once is refused — there is no one-by-one form of a 3D batch op that keeps its meaning.
+template <typename Real>
+static CUresult batch_copy_3d(size_t numOps, CUDA_MEMCPY3D_BATCH_OP *ops, CUstream eff, Real real) {
+    if (!ops || numOps == 0) return real();
+    std::vector<CUdeviceptr> w, r;
+    for (size_t i = 0; i < numOps; i++) {
+        if (ops[i].dst.type == CU_MEMCPY_OPERAND_TYPE_POINTER) w.push_back(ops[i].dst.op.ptr.ptr);
+        if (ops[i].src.type == CU_MEMCPY_OPERAND_TYPE_POINTER) r.push_back(ops[i].src.op.ptr.ptr);
+    }
+    if (!Runtime::get().touch_batch(w.data(), w.size(), r.data(), r.size(), eff)) return CUDA_ERROR_OUT_OF_MEMORY;
+    CUresult rc = real();
+    TOUCH_DONE(eff);
+    return rc;
+}
+VGPU_EXPORT CUresult cuMemcpy3DBatchAsync(size_t numOps, CUDA_MEMCPY3D_BATCH_OP *opList, size_t *failIdx, unsigned long long flags, CUstream st) {
+    if (!drv().cuMemcpy3DBatchAsync) return CUDA_ERROR_NOT_SUPPORTED;
+    return batch_copy_3d(numOps, opList, st, [&] { return drv().cuMemcpy3DBatchAsync(numOps, opList, failIdx, flags, st); });
+}
+VGPU_EXPORT CUresult cuMemcpy3DBatchAsync_ptsz(size_t numOps, CUDA_MEMCPY3D_BATCH_OP *opList, size_t *failIdx, unsigned long long flags, CUstream st) {
+    if (!drv().cuMemcpy3DBatchAsync_ptsz) return CUDA_ERROR_NOT_SUPPORTED;
+    return batch_copy_3d(numOps, opList, PTS(st), [&] { return drv().cuMemcpy3DBatchAsync_ptsz(numOps, opList, failIdx, flags, st); });
+}
 VGPU_EXPORT CUresult cuMemsetD8_v2_ptds(CUdeviceptr dst, unsigned char v, size_t n) {
     TOUCH1(dst, n, CU_STREAM_PER_THREAD); CUresult r = drv().cuMemsetD8_v2_ptds(dst, v, n); TOUCH_DONE(CU_STREAM_PER_THREAD); return r;
 }
@@ -407,6 +459,7 @@ const std::vector<HookEntry> &hooks() {
         H(cuMemcpyDtoHAsync_v2_ptsz), H(cuMemcpyDtoDAsync_v2_ptsz), H(cuMemcpyAsync_ptsz), H(cuMemsetD8_v2_ptds), H(cuMemsetD16_v2_ptds),
         H(cuMemsetD32_v2_ptds), H(cuMemsetD8Async_ptsz), H(cuMemsetD16Async_ptsz), H(cuMemsetD32Async_ptsz),
         H(cuMemAdvise), H(cuMemAdvise_v2), H(cuMemPrefetchAsync),
+        H(cuMemcpyBatchAsync), H(cuMemcpyBatchAsync_ptsz), H(cuMemcpy3DBatchAsync), H(cuMemcpy3DBatchAsync_ptsz),
         HN(cuMemoryAllocate), HN(cuMemoryFree), HN(cuVGPUViewAllocator),
         HN(nvmlDeviceGetMemoryInfo), HN(nvmlDeviceGetMemoryInfo_v2),
     };

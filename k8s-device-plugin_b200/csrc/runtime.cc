@@ -1,4 +1,5 @@
 // runtime.cc — see runtime.h.
+#include <algorithm>
 #include "runtime.h"
 #include <thread>
 #include <csignal>
@@ -1016,6 +1017,32 @@ void Runtime::touch_range2(CUdeviceptr dst, size_t dbytes, CUdeviceptr src, size
     t_touch_w.clear(); t_touch_r.clear();
     if (rd >= 0) t_touch_w.push_back(rd);
     if (rs >= 0 && rs != rd) t_touch_r.push_back(rs);
+}
+
+bool Runtime::touch_batch(const CUdeviceptr *written, size_t nw, const CUdeviceptr *read, size_t nr, CUstream st) {
+    t_touch_w.clear(); t_touch_r.clear();
+    if (!cfg_.oversubscribe) return true;
+    SwapEngine *e = swap(current_device());
+    if (!e) return true;
+    auto add = [&](std::vector<int> &v, CUdeviceptr p) {
+        if (!p || !e->owns(p)) return;
+        int r = e->lookup(p);
+        if (r < 0) return;
+        if (std::find(t_touch_w.begin(), t_touch_w.end(), r) != t_touch_w.end()) return;     // written wins over read
+        if (std::find(v.begin(), v.end(), r) == v.end()) v.push_back(r);
+    };
+    for (size_t i = 0; i < nw; i++) add(t_touch_w, written[i]);
+    for (size_t i = 0; i < nr; i++) add(t_touch_r, read[i]);
+    if (t_touch_w.empty() && t_touch_r.empty()) return true;
+    std::vector<int> all(t_touch_w);
+    all.insert(all.end(), t_touch_r.begin(), t_touch_r.end());
+    bool capturing = stream_is_capturing(st);
+    CUresult r = e->ensure_resident(all.data(), (int)all.size(), capturing ? SwapEngine::kHostWait : st);
+    if (r != CUDA_SUCCESS || capturing) {          // captured: the operands stay pinned, nothing is recorded into the capture
+        t_touch_w.clear(); t_touch_r.clear();
+        return r == CUDA_SUCCESS;
+    }
+    return true;                                   // touch_done() after the real call unpins and records the use
 }
 
 void Runtime::touch_done(CUstream st) {

@@ -100,6 +100,9 @@ class Runtime {
     bool swap_advise(CUdeviceptr p, CUmem_advise advice);
     bool swap_prefetch(CUdeviceptr p, bool to_device);
     void touch_done(CUstream st);   // after the real copy has been enqueued: unpins + records the use
+    // Batched copies (cuMemcpyBatchAsync / cuMemcpy3DBatchAsync, CUDA 12.8): every swappable operand of the batch is admitted
+    // together. false = they do not fit the resident quota at once (the caller then issues the copies one by one).
+    bool touch_batch(const CUdeviceptr *written, size_t nw, const CUdeviceptr *read, size_t nr, CUstream st);
 
     // NVML view: nvmlDeviceGetMemoryInfo under the quota (nvml/hook.c:L327-334)
     bool nvml_memory_view(int nvml_index, unsigned long long *total, unsigned long long *free_b, unsigned long long *used);

@@ -315,6 +315,15 @@ EXPORT CUresult cuMemcpyDtoHAsync_v2(void *d, CUdeviceptr s, size_t n, CUstream 
 EXPORT CUresult cuMemcpyDtoDAsync_v2(CUdeviceptr d, CUdeviceptr s, size_t n, CUstream st) { (void)st; FX_ONLY(memmove((void *)(uintptr_t)d, (const void *)(uintptr_t)s, n)); }
 EXPORT CUresult cuMemcpy(CUdeviceptr d, CUdeviceptr s, size_t n) { FX_ONLY(memmove((void *)(uintptr_t)d, (const void *)(uintptr_t)s, n)); }
 EXPORT CUresult cuMemcpyAsync(CUdeviceptr d, CUdeviceptr s, size_t n, CUstream st) { (void)st; FX_ONLY(memmove((void *)(uintptr_t)d, (const void *)(uintptr_t)s, n)); }
+/* batched copies (CUDA 12.8): attributes are hints, the copies are plain moves; a counter tells tests which form arrived */
+static int g_batch_calls;
+EXPORT int fake_batch_calls(void) { return g_batch_calls; }
+EXPORT CUresult cuMemcpyBatchAsync(CUdeviceptr *d, CUdeviceptr *s, size_t *n, size_t count, void *attrs, size_t *idx, size_t nattrs, size_t *fail, CUstream st) {
+    (void)attrs; (void)idx; (void)nattrs; (void)fail; (void)st;
+    __atomic_add_fetch(&g_batch_calls, 1, __ATOMIC_RELAXED);
+    if (fake_exec_on()) for (size_t i = 0; i < count; i++) memmove((void *)(uintptr_t)d[i], (const void *)(uintptr_t)s[i], n[i]);
+    return CUDA_SUCCESS;
+}
 EXPORT CUresult cuMemsetD8_v2(CUdeviceptr d, unsigned char v, size_t n) { FX_ONLY(memset((void *)(uintptr_t)d, v, n)); }
 EXPORT CUresult cuMemsetD8Async(CUdeviceptr d, unsigned char v, size_t n, CUstream st) { (void)st; FX_ONLY(memset((void *)(uintptr_t)d, v, n)); }
 EXPORT CUresult cuMemsetD16_v2(CUdeviceptr d, unsigned short v, size_t n) { FX_ONLY(for (size_t i = 0; i < n; i++) ((unsigned short *)(uintptr_t)d)[i] = v); }

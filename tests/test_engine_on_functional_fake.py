@@ -709,3 +709,55 @@ print(json.dumps({"bad": bad.value, "page_out": s.v[0], "page_in": s.v[1], "evic
     assert out["bad"] == 0 and out["faults"] > 30
     # half of the buffers are read-mostly: their evictions carry no write-back, so far less went out than came in
     assert out["page_out"] < 0.7 * out["page_in"], out
+
+
+def test_batched_copies_admit_all_their_operands(tmp_path):
+    """cuMemcpyBatchAsync (CUDA 12.8) through the hook on the functional fake (an access to a paged-out range is a
+    SIGSEGV there): a batch whose operands fit the quota is admitted as a whole and reaches the driver as ONE batch; a batch
+    that names more than the quota can hold at once is issued copy by copy, each with its own admission. Every word arrives."""
+    code = r"""
+import ctypes as C, json, os
+cu = C.CDLL("libcuda.so.1")
+def ck(rc, what):
+    assert rc == 0, (what, rc)
+ck(cu.cuInit(0), "init")
+dev, ctx, mod = C.c_int(), C.c_void_p(), C.c_void_p()
+ck(cu.cuDeviceGet(C.byref(dev), 0), "dev"); ck(cu.cuDevicePrimaryCtxRetain(C.byref(ctx), dev), "ctx"); ck(cu.cuCtxSetCurrent(ctx), "cur")
+ck(cu.cuModuleLoad(C.byref(mod), os.environ["CUBIN"].encode()), "mod")
+f_fill, f_verify = C.c_void_p(), C.c_void_p()
+for f, nm in ((f_fill, b"vgpu_wl_fill"), (f_verify, b"vgpu_wl_verify")):
+    ck(cu.cuModuleGetFunction(C.byref(f), mod, nm), nm)
+M = 1 << 20
+n, nbytes = 16, 8 * M                                        # 16 sources + 16 destinations = 256 MiB live under a 96 MiB quota
+def alloc():
+    p = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(p), C.c_size_t(nbytes)), "alloc"); return p.value
+src, dst = [alloc() for _ in range(n)], [alloc() for _ in range(n)]
+def launch(f, *vals):
+    holders = [C.c_uint64(v) for v in vals]
+    arr = (C.c_void_p * len(holders))(*[C.cast(C.byref(h), C.c_void_p) for h in holders])
+    ck(cu.cuLaunchKernel(f, 64, 1, 1, 256, 1, 1, 0, None, arr, None), "launch")
+for i, p in enumerate(src):
+    launch(f_fill, p, nbytes // 8, 100 + i)
+cnt = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(cnt), 8), "cnt"); ck(cu.cuMemsetD8_v2(cnt, 0, 8), "cnt0")
+def batch(idx):
+    k = len(idx)
+    d = (C.c_uint64 * k)(*[dst[i] for i in idx]); s = (C.c_uint64 * k)(*[src[i] for i in idx]); z = (C.c_size_t * k)(*[nbytes] * k)
+    fail = C.c_size_t(~0 & 0xffffffffffffffff)
+    ck(cu.cuMemcpyBatchAsync(d, s, z, C.c_size_t(k), None, None, C.c_size_t(0), C.byref(fail), None), "batch")
+calls = cu.fake_batch_calls
+batch([0, 1, 2, 3])                                           # 8 operands x 8 MiB = 64 MiB: fits, one driver batch
+after_small = calls()
+batch(list(range(4, n)))                                      # 24 operands = 192 MiB: cannot be resident at once -> single copies
+after_big = calls()
+ck(cu.cuCtxSynchronize(), "sync")
+for i, p in enumerate(dst):
+    launch(f_verify, p, nbytes // 8, 100 + i, 0, cnt.value)
+ck(cu.cuCtxSynchronize(), "sync")
+bad = C.c_uint64(); ck(cu.cuMemcpyDtoH_v2(C.byref(bad), cnt, 8), "read")
+print(json.dumps({"bad": bad.value, "after_small": after_small, "after_big": after_big}))
+"""
+    env = _env(tmp_path, LD_PRELOAD=HOOK_SO, CUDA_OVERSUBSCRIBE="true", CUDA_DEVICE_MEMORY_LIMIT_0="96m", CUBIN=CUBIN, VGPU_SWAP_CHUNK_MB="2", VGPU_SWAP_RING="2")
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out == {"bad": 0, "after_small": 1, "after_big": 1}, out
