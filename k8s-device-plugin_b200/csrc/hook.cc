@@ -363,6 +363,14 @@ VGPU_EXPORT CUresult cuPointerGetAttributes(unsigned int numAttributes, CUpointe
     return r;
 }
 
+// cuMemGetAddressRange: a swappable buffer is answered from the engine's table — base and size as the application allocated
+// it, resident or not (the driver knows a resident one as a VMM mapping rounded to the 2 MiB granule, and a paged-out one
+// not at all). The reference forwards: its managed allocation is an ordinary allocation to the driver.
+VGPU_EXPORT CUresult cuMemGetAddressRange_v2(CUdeviceptr *pbase, size_t *psize, CUdeviceptr dptr) {
+    if (Runtime::get().swap_address_range(dptr, pbase, psize)) return CUDA_SUCCESS;
+    return drv().cuMemGetAddressRange_v2 ? drv().cuMemGetAddressRange_v2(pbase, psize, dptr) : CUDA_ERROR_NOT_SUPPORTED;
+}
+
 // cuMemAdvise / cuMemPrefetchAsync. In the reference a large allocation under CUDA_OVERSUBSCRIBE IS managed memory
 // (cuMemoryAllocate@0x315da -> cuMemAllocManaged), so both calls work on it and steer UVM. Here the same pointers are the
 // swap engine's: SET_READ_MOSTLY keeps kernel launches from dirtying the range (eviction without write-back), a prefetch
@@ -459,6 +467,7 @@ const std::vector<HookEntry> &hooks() {
         H(cuMemcpyDtoHAsync_v2_ptsz), H(cuMemcpyDtoDAsync_v2_ptsz), H(cuMemcpyAsync_ptsz), H(cuMemsetD8_v2_ptds), H(cuMemsetD16_v2_ptds),
         H(cuMemsetD32_v2_ptds), H(cuMemsetD8Async_ptsz), H(cuMemsetD16Async_ptsz), H(cuMemsetD32Async_ptsz),
         H(cuMemAdvise), H(cuMemAdvise_v2), H(cuMemPrefetchAsync),
+        H(cuMemGetAddressRange_v2),
         H(cuMemcpyBatchAsync), H(cuMemcpyBatchAsync_ptsz), H(cuMemcpy3DBatchAsync), H(cuMemcpy3DBatchAsync_ptsz),
         HN(cuMemoryAllocate), HN(cuMemoryFree), HN(cuVGPUViewAllocator),
         HN(nvmlDeviceGetMemoryInfo), HN(nvmlDeviceGetMemoryInfo_v2),

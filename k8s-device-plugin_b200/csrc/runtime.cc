@@ -1068,6 +1068,12 @@ bool Runtime::swap_advise(CUdeviceptr p, CUmem_advise advice) {
     return true;
 }
 
+bool Runtime::swap_address_range(CUdeviceptr p, CUdeviceptr *base, size_t *size) {
+    if (!cfg_.oversubscribe) return false;
+    SwapEngine *e = swap(current_device());
+    return e && e->range_of(p, base, size);
+}
+
 bool Runtime::swap_prefetch(CUdeviceptr p, bool to_device) {
     if (!cfg_.oversubscribe) return false;
     SwapEngine *e = swap(current_device());

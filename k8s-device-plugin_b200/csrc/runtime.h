@@ -99,6 +99,7 @@ class Runtime {
     // are meaningful): true when the pointer is the swap engine's and the call has been handled
     bool swap_advise(CUdeviceptr p, CUmem_advise advice);
     bool swap_prefetch(CUdeviceptr p, bool to_device);
+    bool swap_address_range(CUdeviceptr p, CUdeviceptr *base, size_t *size);   // true: p is a swappable buffer, answered from the table
     void touch_done(CUstream st);   // after the real copy has been enqueued: unpins + records the use
     // Batched copies (cuMemcpyBatchAsync / cuMemcpy3DBatchAsync, CUDA 12.8): every swappable operand of the batch is admitted
     // together. false = they do not fit the resident quota at once (the caller then issues the copies one by one).

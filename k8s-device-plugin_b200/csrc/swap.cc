@@ -481,6 +481,16 @@ int SwapEngine::lookup(CUdeviceptr p) const {
     return r;
 }
 
+bool SwapEngine::range_of(CUdeviceptr p, CUdeviceptr *base, size_t *size) const {
+    if (!owns(p)) return false;
+    std::lock_guard<std::mutex> g(mu_);
+    int r = owner_[(p - arena_) / gran_];
+    if (r < 0 || rows_[r].state == VGPU_ST_FREE || p >= rows_[r].base + rows_[r].size) return false;
+    if (base) *base = rows_[r].base;
+    if (size) *size = rows_[r].size;
+    return true;
+}
+
 void SwapEngine::collect_rows(const void *param, size_t bytes, std::vector<int> *rows) const {
     if (bytes < 8) return;
     const unsigned char *b = static_cast<const unsigned char *>(param);

@@ -754,10 +754,21 @@ for i, p in enumerate(dst):
     launch(f_verify, p, nbytes // 8, 100 + i, 0, cnt.value)
 ck(cu.cuCtxSynchronize(), "sync")
 bad = C.c_uint64(); ck(cu.cuMemcpyDtoH_v2(C.byref(bad), cnt, 8), "read")
-print(json.dumps({"bad": bad.value, "after_small": after_small, "after_big": after_big}))
+# cuMemGetAddressRange answers for every swappable buffer, resident or paged out (most of these 33 are out), with the base
+# and the size the application asked for (not the 2 MiB-rounded mapping)
+odd = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(odd), C.c_size_t(5 * M + 4096)), "odd")
+ranges_ok = 0
+for p, sz in [(q, nbytes) for q in src + dst] + [(odd.value, 5 * M + 4096)]:
+    b, z = C.c_uint64(), C.c_size_t()
+    ck(cu.cuMemGetAddressRange_v2(C.byref(b), C.byref(z), C.c_uint64(p + sz - 8)), "range")
+    ranges_ok += int(b.value == p and z.value == sz)
+b, z = C.c_uint64(), C.c_size_t()
+past_end = cu.cuMemGetAddressRange_v2(C.byref(b), C.byref(z), C.c_uint64(odd.value + 5 * M + 4096 + 8))   # inside the granule, outside the buffer
+print(json.dumps({"bad": bad.value, "after_small": after_small, "after_big": after_big, "ranges_ok": ranges_ok, "past_end_rc": past_end}))
 """
     env = _env(tmp_path, LD_PRELOAD=HOOK_SO, CUDA_OVERSUBSCRIBE="true", CUDA_DEVICE_MEMORY_LIMIT_0="96m", CUBIN=CUBIN, VGPU_SWAP_CHUNK_MB="2", VGPU_SWAP_RING="2")
     r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
-    assert out == {"bad": 0, "after_small": 1, "after_big": 1}, out
+    assert out["bad"] == 0 and out["after_small"] == 1 and out["after_big"] == 1, out
+    assert out["ranges_ok"] == 33 and out["past_end_rc"] != 0, out
