@@ -34,7 +34,7 @@ namespace vgpu {
     X(cuModuleLoadData) X(cuModuleGetFunction) X(cuModuleUnload) X(cuFuncSetAttribute) X(cuFuncGetParamInfo)      \
     X(cuLaunchKernel) X(cuLaunchKernelEx) X(cuLaunchCooperativeKernel) X(cuOccupancyMaxActiveBlocksPerMultiprocessor) \
     X(cuMemAllocAsync) X(cuMemAllocFromPoolAsync) X(cuMemFreeAsync) X(cuGraphLaunch)                              \
-    X(cuMemAdvise) X(cuMemAdvise_v2) X(cuMemPrefetchAsync)                                                        \
+    X(cuMemAdvise) X(cuMemAdvise_v2) X(cuMemPrefetchAsync) X(cuMemPrefetchAsync_v2)                                                      \
     X(cuGetProcAddress_v2) X(cuGetErrorString) X(cuGetErrorName)
 
 // per-thread-default-stream twins (cuda.h hides their prototypes behind __CUDA_API_VERSION_INTERNAL; the signatures
@@ -45,6 +45,7 @@ namespace vgpu {
     X(cuMemcpyHtoD_v2, _ptds) X(cuMemcpyDtoH_v2, _ptds) X(cuMemcpyDtoD_v2, _ptds) X(cuMemcpy, _ptds)              \
     X(cuMemcpyHtoDAsync_v2, _ptsz) X(cuMemcpyDtoHAsync_v2, _ptsz) X(cuMemcpyDtoDAsync_v2, _ptsz)                  \
     X(cuMemcpyAsync, _ptsz) X(cuMemcpyBatchAsync, _ptsz) X(cuMemcpy3DBatchAsync, _ptsz)                           \
+    X(cuMemPrefetchAsync, _ptsz) X(cuMemPrefetchAsync_v2, _ptsz)                                                  \
     X(cuMemsetD8_v2, _ptds) X(cuMemsetD16_v2, _ptds) X(cuMemsetD32_v2, _ptds)                                     \
     X(cuMemsetD8Async, _ptsz) X(cuMemsetD16Async, _ptsz) X(cuMemsetD32Async, _ptsz)
 

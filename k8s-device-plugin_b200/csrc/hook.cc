@@ -388,6 +388,18 @@ VGPU_EXPORT CUresult cuMemPrefetchAsync(CUdeviceptr devPtr, size_t count, CUdevi
     if (Runtime::get().swap_prefetch(devPtr, dstDevice >= 0)) return CUDA_SUCCESS;
     return drv().cuMemPrefetchAsync ? drv().cuMemPrefetchAsync(devPtr, count, dstDevice, hStream) : CUDA_ERROR_NOT_SUPPORTED;
 }
+VGPU_EXPORT CUresult cuMemPrefetchAsync_ptsz(CUdeviceptr devPtr, size_t count, CUdevice dstDevice, CUstream hStream) {
+    if (Runtime::get().swap_prefetch(devPtr, dstDevice >= 0)) return CUDA_SUCCESS;
+    return drv().cuMemPrefetchAsync_ptsz ? drv().cuMemPrefetchAsync_ptsz(devPtr, count, dstDevice, hStream) : CUDA_ERROR_NOT_SUPPORTED;
+}
+VGPU_EXPORT CUresult cuMemPrefetchAsync_v2(CUdeviceptr devPtr, size_t count, CUmemLocation location, unsigned int flags, CUstream hStream) {
+    if (Runtime::get().swap_prefetch(devPtr, location.type == CU_MEM_LOCATION_TYPE_DEVICE)) return CUDA_SUCCESS;
+    return drv().cuMemPrefetchAsync_v2 ? drv().cuMemPrefetchAsync_v2(devPtr, count, location, flags, hStream) : CUDA_ERROR_NOT_SUPPORTED;
+}
+VGPU_EXPORT CUresult cuMemPrefetchAsync_v2_ptsz(CUdeviceptr devPtr, size_t count, CUmemLocation location, unsigned int flags, CUstream hStream) {
+    if (Runtime::get().swap_prefetch(devPtr, location.type == CU_MEM_LOCATION_TYPE_DEVICE)) return CUDA_SUCCESS;
+    return drv().cuMemPrefetchAsync_v2_ptsz ? drv().cuMemPrefetchAsync_v2_ptsz(devPtr, count, location, flags, hStream) : CUDA_ERROR_NOT_SUPPORTED;
+}
 
 // extras the reference exports for its own tooling
 VGPU_EXPORT CUresult cuMemoryAllocate(CUdeviceptr *dptr, size_t bytesize, size_t *bytesallocated, void *data) {
@@ -468,6 +480,7 @@ const std::vector<HookEntry> &hooks() {
         H(cuMemsetD32_v2_ptds), H(cuMemsetD8Async_ptsz), H(cuMemsetD16Async_ptsz), H(cuMemsetD32Async_ptsz),
         H(cuMemAdvise), H(cuMemAdvise_v2), H(cuMemPrefetchAsync),
         H(cuMemGetAddressRange_v2),
+        H(cuMemPrefetchAsync_ptsz), H(cuMemPrefetchAsync_v2), H(cuMemPrefetchAsync_v2_ptsz),
         H(cuMemcpyBatchAsync), H(cuMemcpyBatchAsync_ptsz), H(cuMemcpy3DBatchAsync), H(cuMemcpy3DBatchAsync_ptsz),
         HN(cuMemoryAllocate), HN(cuMemoryFree), HN(cuVGPUViewAllocator),
         HN(nvmlDeviceGetMemoryInfo), HN(nvmlDeviceGetMemoryInfo_v2),

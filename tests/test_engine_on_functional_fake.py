@@ -693,6 +693,10 @@ for sweep in range(4):
         else:
             launch(f_touch, p.value, nbytes // 8); touches[i] += 1
 ck(cu.cuMemPrefetchAsync(C.c_uint64(bufs[5].value), C.c_size_t(nbytes), dev, None), "prefetch")
+class Loc(C.Structure):
+    _fields_ = [("type", C.c_int), ("id", C.c_int)]
+cu.cuMemPrefetchAsync_v2.argtypes = [C.c_uint64, C.c_size_t, Loc, C.c_uint, C.c_void_p]
+ck(cu.cuMemPrefetchAsync_v2(bufs[7].value, nbytes, Loc(1, 0), 0, None), "prefetch v2")     # CU_MEM_LOCATION_TYPE_DEVICE
 ck(cu.cuCtxSynchronize(), "sync")
 for i, p in enumerate(bufs):
     launch(f_verify, p.value, nbytes // 8, i, touches[i], cnt.value)
