@@ -35,6 +35,9 @@ namespace vgpu {
     X(cuLaunchKernel) X(cuLaunchKernelEx) X(cuLaunchCooperativeKernel) X(cuOccupancyMaxActiveBlocksPerMultiprocessor) \
     X(cuMemAllocAsync) X(cuMemAllocFromPoolAsync) X(cuMemFreeAsync) X(cuGraphLaunch)                              \
     X(cuMemAdvise) X(cuMemAdvise_v2) X(cuMemPrefetchAsync) X(cuMemPrefetchAsync_v2)                                                      \
+    X(cuGraphAddKernelNode_v2) X(cuGraphKernelNodeSetParams_v2) X(cuGraphExecKernelNodeSetParams_v2)              \
+    X(cuGraphAddMemcpyNode) X(cuGraphMemcpyNodeSetParams) X(cuGraphExecMemcpyNodeSetParams) X(cuGraphAddMemsetNode) \
+    X(cuGraphAddNode) X(cuGraphAddNode_v2)                                                                        \
     X(cuGetProcAddress_v2) X(cuGetErrorString) X(cuGetErrorName)
 
 // per-thread-default-stream twins (cuda.h hides their prototypes behind __CUDA_API_VERSION_INTERNAL; the signatures

@@ -334,7 +334,6 @@ VGPU_EXPORT CUresult cuMemsetD2D16Async(CUdeviceptr dst, size_t pitch, unsigned 
 VGPU_EXPORT CUresult cuMemsetD2D32Async(CUdeviceptr dst, size_t pitch, unsigned int v, size_t w, size_t h, CUstream st) {
     TOUCH1(dst, pitch * h, st); CUresult r = drv().cuMemsetD2D32Async(dst, pitch, v, w, h, st); TOUCH_DONE(st); return r;
 }
-#undef DEVPTR_IF
 
 // Pointer queries. A PAGED-OUT swappable buffer has no mapping at all and the driver would answer INVALID_VALUE, so the
 // buffer is made resident first; resident or not, it is a VMM mapping — plain device memory to the driver — and the
@@ -361,6 +360,73 @@ VGPU_EXPORT CUresult cuPointerGetAttributes(unsigned int numAttributes, CUpointe
         for (unsigned int i = 0; i < numAttributes; i++)
             if (attributes[i] == CU_POINTER_ATTRIBUTE_IS_MANAGED && data[i]) *static_cast<unsigned int *>(data[i]) = 0;
     return r;
+}
+
+// Explicitly built graphs. Stream capture is handled at the captured call (guarded_launch / touch_range2); a graph built node
+// by node never passes there, and its replay (cuGraphLaunch) cannot be admitted operand by operand. So the swappable
+// buffers a kernel / memcpy / memset node names are made resident when the node is defined or re-parameterised and stay
+// pinned from then on. The reference needs nothing here: UVM faults under a replay as under any launch.
+static CUresult pin_kernel_node(const CUDA_KERNEL_NODE_PARAMS *p) {
+    return p ? Runtime::get().pin_graph_kernel(p->func, p->kernelParams, p->extra) : CUDA_SUCCESS;
+}
+static CUresult pin_copy_node(const CUDA_MEMCPY3D *c) {
+    if (!c) return CUDA_SUCCESS;
+    CUdeviceptr p[2] = {DEVPTR_IF(c->dstMemoryType, c->dstDevice), DEVPTR_IF(c->srcMemoryType, c->srcDevice)};
+    return Runtime::get().pin_graph_ptrs(p, 2);
+}
+VGPU_EXPORT CUresult cuGraphAddKernelNode_v2(CUgraphNode *node, CUgraph g, const CUgraphNode *deps, size_t ndeps, const CUDA_KERNEL_NODE_PARAMS *p) {
+    if (!drv().cuGraphAddKernelNode_v2) return CUDA_ERROR_NOT_SUPPORTED;
+    if (CUresult r = pin_kernel_node(p)) return r;
+    return drv().cuGraphAddKernelNode_v2(node, g, deps, ndeps, p);
+}
+VGPU_EXPORT CUresult cuGraphKernelNodeSetParams_v2(CUgraphNode node, const CUDA_KERNEL_NODE_PARAMS *p) {
+    if (!drv().cuGraphKernelNodeSetParams_v2) return CUDA_ERROR_NOT_SUPPORTED;
+    if (CUresult r = pin_kernel_node(p)) return r;
+    return drv().cuGraphKernelNodeSetParams_v2(node, p);
+}
+VGPU_EXPORT CUresult cuGraphExecKernelNodeSetParams_v2(CUgraphExec ge, CUgraphNode node, const CUDA_KERNEL_NODE_PARAMS *p) {
+    if (!drv().cuGraphExecKernelNodeSetParams_v2) return CUDA_ERROR_NOT_SUPPORTED;
+    if (CUresult r = pin_kernel_node(p)) return r;
+    return drv().cuGraphExecKernelNodeSetParams_v2(ge, node, p);
+}
+VGPU_EXPORT CUresult cuGraphAddMemcpyNode(CUgraphNode *node, CUgraph g, const CUgraphNode *deps, size_t ndeps, const CUDA_MEMCPY3D *c, CUcontext ctx) {
+    if (!drv().cuGraphAddMemcpyNode) return CUDA_ERROR_NOT_SUPPORTED;
+    if (CUresult r = pin_copy_node(c)) return r;
+    return drv().cuGraphAddMemcpyNode(node, g, deps, ndeps, c, ctx);
+}
+VGPU_EXPORT CUresult cuGraphMemcpyNodeSetParams(CUgraphNode node, const CUDA_MEMCPY3D *c) {
+    if (!drv().cuGraphMemcpyNodeSetParams) return CUDA_ERROR_NOT_SUPPORTED;
+    if (CUresult r = pin_copy_node(c)) return r;
+    return drv().cuGraphMemcpyNodeSetParams(node, c);
+}
+VGPU_EXPORT CUresult cuGraphExecMemcpyNodeSetParams(CUgraphExec ge, CUgraphNode node, const CUDA_MEMCPY3D *c, CUcontext ctx) {
+    if (!drv().cuGraphExecMemcpyNodeSetParams) return CUDA_ERROR_NOT_SUPPORTED;
+    if (CUresult r = pin_copy_node(c)) return r;
+    return drv().cuGraphExecMemcpyNodeSetParams(ge, node, c, ctx);
+}
+VGPU_EXPORT CUresult cuGraphAddMemsetNode(CUgraphNode *node, CUgraph g, const CUgraphNode *deps, size_t ndeps, const CUDA_MEMSET_NODE_PARAMS *m, CUcontext ctx) {
+    if (!drv().cuGraphAddMemsetNode) return CUDA_ERROR_NOT_SUPPORTED;
+    if (m) if (CUresult r = Runtime::get().pin_graph_ptrs(&m->dst, 1)) return r;
+    return drv().cuGraphAddMemsetNode(node, g, deps, ndeps, m, ctx);
+}
+static CUresult pin_generic_node(const CUgraphNodeParams *np) {
+    if (!np) return CUDA_SUCCESS;
+    switch (np->type) {
+    case CU_GRAPH_NODE_TYPE_KERNEL: return Runtime::get().pin_graph_kernel(np->kernel.func, np->kernel.kernelParams, np->kernel.extra);
+    case CU_GRAPH_NODE_TYPE_MEMCPY: return pin_copy_node(&np->memcpy.copyParams);
+    case CU_GRAPH_NODE_TYPE_MEMSET: return Runtime::get().pin_graph_ptrs(&np->memset.dst, 1);
+    default: return CUDA_SUCCESS;
+    }
+}
+VGPU_EXPORT CUresult cuGraphAddNode(CUgraphNode *node, CUgraph g, const CUgraphNode *deps, size_t ndeps, CUgraphNodeParams *np) {
+    if (!drv().cuGraphAddNode) return CUDA_ERROR_NOT_SUPPORTED;
+    if (CUresult r = pin_generic_node(np)) return r;
+    return drv().cuGraphAddNode(node, g, deps, ndeps, np);
+}
+VGPU_EXPORT CUresult cuGraphAddNode_v2(CUgraphNode *node, CUgraph g, const CUgraphNode *deps, const CUgraphEdgeData *edges, size_t ndeps, CUgraphNodeParams *np) {
+    if (!drv().cuGraphAddNode_v2) return CUDA_ERROR_NOT_SUPPORTED;
+    if (CUresult r = pin_generic_node(np)) return r;
+    return drv().cuGraphAddNode_v2(node, g, deps, edges, ndeps, np);
 }
 
 // cuMemGetAddressRange: a swappable buffer is answered from the engine's table — base and size as the application allocated
@@ -480,6 +546,8 @@ const std::vector<HookEntry> &hooks() {
         H(cuMemsetD32_v2_ptds), H(cuMemsetD8Async_ptsz), H(cuMemsetD16Async_ptsz), H(cuMemsetD32Async_ptsz),
         H(cuMemAdvise), H(cuMemAdvise_v2), H(cuMemPrefetchAsync),
         H(cuMemGetAddressRange_v2),
+        H(cuGraphAddKernelNode_v2), H(cuGraphKernelNodeSetParams_v2), H(cuGraphExecKernelNodeSetParams_v2), H(cuGraphAddMemcpyNode),
+        H(cuGraphMemcpyNodeSetParams), H(cuGraphExecMemcpyNodeSetParams), H(cuGraphAddMemsetNode), H(cuGraphAddNode), H(cuGraphAddNode_v2),
         H(cuMemPrefetchAsync_ptsz), H(cuMemPrefetchAsync_v2), H(cuMemPrefetchAsync_v2_ptsz),
         H(cuMemcpyBatchAsync), H(cuMemcpyBatchAsync_ptsz), H(cuMemcpy3DBatchAsync), H(cuMemcpy3DBatchAsync_ptsz),
         HN(cuMemoryAllocate), HN(cuMemoryFree), HN(cuVGPUViewAllocator),

@@ -1068,6 +1068,29 @@ bool Runtime::swap_advise(CUdeviceptr p, CUmem_advise advice) {
     return true;
 }
 
+CUresult Runtime::pin_graph_kernel(CUfunction f, void **params, void **extra) {
+    if (!cfg_.oversubscribe || !f) return CUDA_SUCCESS;
+    SwapEngine *e = swap(current_device());
+    if (!e) return CUDA_SUCCESS;
+    std::vector<int> rows;
+    collect_launch_rows(e, f, params, extra, &rows);
+    if (rows.empty()) return CUDA_SUCCESS;
+    return e->ensure_resident(rows.data(), (int)rows.size(), SwapEngine::kHostWait);
+}
+
+CUresult Runtime::pin_graph_ptrs(const CUdeviceptr *p, size_t n) {
+    if (!cfg_.oversubscribe) return CUDA_SUCCESS;
+    SwapEngine *e = swap(current_device());
+    if (!e) return CUDA_SUCCESS;
+    std::vector<int> rows;
+    for (size_t i = 0; i < n; i++) {
+        int r = p[i] ? e->lookup(p[i]) : -1;
+        if (r >= 0 && std::find(rows.begin(), rows.end(), r) == rows.end()) rows.push_back(r);
+    }
+    if (rows.empty()) return CUDA_SUCCESS;
+    return e->ensure_resident(rows.data(), (int)rows.size(), SwapEngine::kHostWait);
+}
+
 bool Runtime::swap_address_range(CUdeviceptr p, CUdeviceptr *base, size_t *size) {
     if (!cfg_.oversubscribe) return false;
     SwapEngine *e = swap(current_device());

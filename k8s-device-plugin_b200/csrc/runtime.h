@@ -99,6 +99,10 @@ class Runtime {
     // are meaningful): true when the pointer is the swap engine's and the call has been handled
     bool swap_advise(CUdeviceptr p, CUmem_advise advice);
     bool swap_prefetch(CUdeviceptr p, bool to_device);
+    // Explicitly built graphs (cuGraphAdd*Node / *SetParams): a replay cannot be admitted node by node, so the swappable
+    // operands named by a node are made resident when the node is defined and stay pinned (same rule as stream capture).
+    CUresult pin_graph_kernel(CUfunction f, void **params, void **extra);
+    CUresult pin_graph_ptrs(const CUdeviceptr *p, size_t n);
     bool swap_address_range(CUdeviceptr p, CUdeviceptr *base, size_t *size);   // true: p is a swappable buffer, answered from the table
     void touch_done(CUstream st);   // after the real copy has been enqueued: unpins + records the use
     // Batched copies (cuMemcpyBatchAsync / cuMemcpy3DBatchAsync, CUDA 12.8): every swappable operand of the batch is admitted

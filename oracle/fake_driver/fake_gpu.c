@@ -392,7 +392,73 @@ EXPORT CUresult cuMemRelease(unsigned long long h) { if (fake_exec_on()) return 
 EXPORT CUresult cuMemAllocAsync(CUdeviceptr *p, size_t n, CUstream st) { (void)st; return do_alloc(p, n); }
 EXPORT CUresult cuMemAllocFromPoolAsync(CUdeviceptr *p, size_t n, void *pool, CUstream st) { (void)pool; (void)st; return do_alloc(p, n); }
 EXPORT CUresult cuMemFreeAsync(CUdeviceptr p, CUstream st) { (void)st; return do_free(p); }
-EXPORT CUresult cuGraphLaunch(void *g, CUstream st) { (void)g; (void)st; __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); return CUDA_SUCCESS; }
+/* explicitly built graphs, just enough to replay kernel and 1-D memset nodes in insertion order (exec mode): a replay touches
+ * its operands with no further call into the hook, which is the property the swap-mode tests need */
+#define FG_MAGIC 0x6772617068ull
+struct fg_node { int kind; CUfunction f; void *pv[16]; unsigned long long val[16][4]; int np; CUdeviceptr dst; unsigned value, esize; size_t width; };
+struct fg_graph { unsigned long long magic; int n; struct fg_node node[64]; };
+struct fg_kparams { CUfunction func; unsigned gx, gy, gz, bx, by, bz, smem; void **kernelParams; void **extra; void *kern; void *ctx; };
+struct fg_msparams { CUdeviceptr dst; size_t pitch; unsigned value, elementSize; size_t width, height; };
+static void *g_fg_live[128];                                     /* graphs and instances made here (cuGraphLaunch is also called with opaque handles) */
+static void fg_reg(void *p, int on) { pthread_mutex_lock(&g_mu); for (int i = 0; i < 128; i++) if (g_fg_live[i] == (on ? NULL : p)) { g_fg_live[i] = on ? p : NULL; break; } pthread_mutex_unlock(&g_mu); }
+static int fake_is_heap_graph(void *p) { int hit = 0; pthread_mutex_lock(&g_mu); for (int i = 0; i < 128; i++) hit |= g_fg_live[i] == p; pthread_mutex_unlock(&g_mu); return hit; }
+EXPORT CUresult cuGraphCreate(void **g, unsigned flags) { (void)flags; struct fg_graph *x = calloc(1, sizeof *x); x->magic = FG_MAGIC; *g = x; fg_reg(x, 1); return CUDA_SUCCESS; }
+EXPORT CUresult cuGraphDestroy(void *g) { struct fg_graph *x = g; if (x && fake_is_heap_graph(x)) { fg_reg(x, 0); x->magic = 0; free(x); } return CUDA_SUCCESS; }
+EXPORT CUresult cuGraphAddKernelNode_v2(void **node, void *g, const void *deps, size_t ndeps, const struct fg_kparams *p) {
+    (void)deps; (void)ndeps;
+    struct fg_graph *x = g;
+    if (!x || x->magic != FG_MAGIC || !p || x->n >= 64) return CUDA_ERROR_INVALID_VALUE;
+    struct fg_node *nd = &x->node[x->n];
+    memset(nd, 0, sizeof *nd);
+    nd->kind = 0; nd->f = p->func;
+    for (size_t i = 0; i < 16 && p->kernelParams; i++) {          /* the parameter VALUES are captured when the node is defined */
+        size_t off, size;
+        if (!fake_exec_on() || fx_param_info(p->func, i, &off, &size) != CUDA_SUCCESS) break;
+        if (size > sizeof nd->val[i]) return CUDA_ERROR_INVALID_VALUE;
+        memcpy(nd->val[i], p->kernelParams[i], size);
+        nd->pv[i] = nd->val[i];
+        nd->np = (int)i + 1;
+    }
+    if (node) *node = nd;
+    x->n++;
+    return CUDA_SUCCESS;
+}
+EXPORT CUresult cuGraphAddMemsetNode(void **node, void *g, const void *deps, size_t ndeps, const struct fg_msparams *m, void *ctx) {
+    (void)deps; (void)ndeps; (void)ctx;
+    struct fg_graph *x = g;
+    if (!x || x->magic != FG_MAGIC || !m || x->n >= 64 || m->height > 1) return CUDA_ERROR_INVALID_VALUE;
+    struct fg_node *nd = &x->node[x->n];
+    memset(nd, 0, sizeof *nd);
+    nd->kind = 1; nd->dst = m->dst; nd->value = m->value; nd->esize = m->elementSize; nd->width = m->width;
+    if (node) *node = nd;
+    x->n++;
+    return CUDA_SUCCESS;
+}
+EXPORT CUresult cuGraphInstantiateWithFlags(void **ge, void *g, unsigned long long flags) {
+    (void)flags;
+    struct fg_graph *x = g;
+    if (!x || x->magic != FG_MAGIC) return CUDA_ERROR_INVALID_VALUE;
+    struct fg_graph *c = malloc(sizeof *c);
+    memcpy(c, x, sizeof *c);
+    for (int i = 0; i < c->n; i++) for (int k = 0; k < c->node[i].np; k++) c->node[i].pv[k] = c->node[i].val[k];
+    *ge = c;
+    fg_reg(c, 1);
+    return CUDA_SUCCESS;
+}
+EXPORT CUresult cuGraphExecDestroy(void *ge) { return cuGraphDestroy(ge); }
+EXPORT CUresult cuGraphLaunch(void *g, CUstream st) {
+    (void)st; __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED);
+    struct fg_graph *x = g;
+    if (!fake_exec_on() || !x || !fake_is_heap_graph(x)) return CUDA_SUCCESS;    /* tests of the limiter pass opaque handles */
+    for (int i = 0; i < x->n; i++) {
+        struct fg_node *nd = &x->node[i];
+        if (nd->kind == 0) { CUresult r = fx_launch(nd->f, nd->pv); if (r != CUDA_SUCCESS) return r; }
+        else if (nd->esize == 1) memset((void *)(uintptr_t)nd->dst, (int)nd->value, nd->width);
+        else if (nd->esize == 2) for (size_t k = 0; k < nd->width; k++) ((unsigned short *)(uintptr_t)nd->dst)[k] = (unsigned short)nd->value;
+        else for (size_t k = 0; k < nd->width; k++) ((unsigned *)(uintptr_t)nd->dst)[k] = nd->value;
+    }
+    return CUDA_SUCCESS;
+}
 EXPORT CUresult cuMemSetAccess(CUdeviceptr p, size_t n, const void *d, size_t c) { if (fake_exec_on()) return fx_mem_set_access(p, n, d, c); return CUDA_SUCCESS; }
 EXPORT CUresult cuMemUnmap(CUdeviceptr p, size_t n) { if (fake_exec_on()) return fx_mem_unmap(p, n); return CUDA_SUCCESS; }
 

@@ -776,3 +776,73 @@ print(json.dumps({"bad": bad.value, "after_small": after_small, "after_big": aft
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["bad"] == 0 and out["after_small"] == 1 and out["after_big"] == 1, out
     assert out["ranges_ok"] == 33 and out["past_end_rc"] != 0, out
+
+
+def test_explicitly_built_graph_keeps_its_operands_resident(tmp_path):
+    """A graph built node by node (cuGraphAddKernelNode / cuGraphAddMemsetNode — no stream capture, so no launch ever passes
+    the hook): the buffers its nodes name are pinned resident when the nodes are defined, everything else keeps cycling
+    through the quota, and replays (which touch the operands with no call into the hook; a paged-out range is a SIGSEGV on
+    the functional fake) find them in place."""
+    code = r"""
+import ctypes as C, json, os
+cu = C.CDLL("libcuda.so.1")
+def ck(rc, what):
+    assert rc == 0, (what, rc)
+ck(cu.cuInit(0), "init")
+dev, ctx, mod = C.c_int(), C.c_void_p(), C.c_void_p()
+ck(cu.cuDeviceGet(C.byref(dev), 0), "dev"); ck(cu.cuDevicePrimaryCtxRetain(C.byref(ctx), dev), "ctx"); ck(cu.cuCtxSetCurrent(ctx), "cur")
+ck(cu.cuModuleLoad(C.byref(mod), os.environ["CUBIN"].encode()), "mod")
+f_fill, f_touch, f_verify = C.c_void_p(), C.c_void_p(), C.c_void_p()
+for f, nm in ((f_fill, b"vgpu_wl_fill"), (f_touch, b"vgpu_wl_touch"), (f_verify, b"vgpu_wl_verify")):
+    ck(cu.cuModuleGetFunction(C.byref(f), mod, nm), nm)
+M = 1 << 20
+n, nbytes = 14, 16 * M                                        # 224 MiB live under a 96 MiB quota
+bufs = []
+for i in range(n):
+    p = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(p), C.c_size_t(nbytes)), "alloc"); bufs.append(p.value)
+def params(*vals):
+    holders = [C.c_uint64(v) for v in vals]
+    return holders, (C.c_void_p * len(holders))(*[C.cast(C.byref(h), C.c_void_p) for h in holders])
+def launch(f, *vals):
+    keep, arr = params(*vals)
+    ck(cu.cuLaunchKernel(f, 64, 1, 1, 256, 1, 1, 0, None, arr, None), "launch")
+for i, p in enumerate(bufs):
+    launch(f_fill, p, nbytes // 8, i)
+class KP(C.Structure):
+    _fields_ = [("func", C.c_void_p), ("g", C.c_uint * 3), ("b", C.c_uint * 3), ("smem", C.c_uint), ("kernelParams", C.c_void_p), ("extra", C.c_void_p),
+                ("kern", C.c_void_p), ("ctx", C.c_void_p)]
+class MS(C.Structure):
+    _fields_ = [("dst", C.c_uint64), ("pitch", C.c_size_t), ("value", C.c_uint), ("elementSize", C.c_uint), ("width", C.c_size_t), ("height", C.c_size_t)]
+g, ge, node = C.c_void_p(), C.c_void_p(), C.c_void_p()
+ck(cu.cuGraphCreate(C.byref(g), 0), "graph")
+scratch = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(scratch), C.c_size_t(4 * M)), "scratch")     # swappable too (> 2 MiB)
+in_graph = [0, 5]                                             # buffers 0 and 5 are touched by the graph: evicted by now (LRU), paged back in to be pinned
+for i in in_graph:
+    keep, arr = params(bufs[i], nbytes // 8)
+    kp = KP(f_touch.value, (64, 1, 1), (256, 1, 1), 0, C.cast(arr, C.c_void_p), None, None, None)
+    ck(cu.cuGraphAddKernelNode_v2(C.byref(node), g, None, C.c_size_t(0), C.byref(kp)), "kernel node")
+ms = MS(scratch.value, 0, 0xAB, 1, 4 * M, 1)
+ck(cu.cuGraphAddMemsetNode(C.byref(node), g, None, C.c_size_t(0), C.byref(ms), ctx), "memset node")
+ck(cu.cuGraphInstantiateWithFlags(C.byref(ge), g, C.c_ulonglong(0)), "instantiate")
+touches = [0] * n
+for rep in range(3):
+    for i, p in enumerate(bufs):                              # everything else cycles through the quota between replays
+        if i not in in_graph:
+            launch(f_touch, p, nbytes // 8); touches[i] += 1
+    ck(cu.cuGraphLaunch(ge, None), "replay")
+    for i in in_graph:
+        touches[i] += 1
+ck(cu.cuCtxSynchronize(), "sync")
+cnt = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(cnt), 8), "cnt"); ck(cu.cuMemsetD8_v2(cnt, 0, 8), "cnt0")
+for i, p in enumerate(bufs):
+    launch(f_verify, p, nbytes // 8, i, touches[i], cnt.value)
+ck(cu.cuCtxSynchronize(), "sync")
+bad = C.c_uint64(); ck(cu.cuMemcpyDtoH_v2(C.byref(bad), cnt, 8), "read")
+word = C.c_uint64(); ck(cu.cuMemcpyDtoH_v2(C.byref(word), C.c_uint64(scratch.value + 4 * M - 8), 8), "scratch")
+print(json.dumps({"bad": bad.value, "scratch": hex(word.value)}))
+"""
+    env = _env(tmp_path, LD_PRELOAD=HOOK_SO, CUDA_OVERSUBSCRIBE="true", CUDA_DEVICE_MEMORY_LIMIT_0="96m", CUBIN=CUBIN, VGPU_SWAP_CHUNK_MB="2", VGPU_SWAP_RING="2")
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out == {"bad": 0, "scratch": "0xabababababababab"}, out
