@@ -143,6 +143,7 @@ typedef struct vgpu_swap_stats {
      * re-taking the engine lock, and busy time per step (freed rows, reap, demand, prefetch, evict-ahead) */
     uint64_t pager_unmap_ns, pager_setaccess_ns, pager_issue_ns, pager_poll_ns, pager_lock_ns, pager_step_ns[5];
     uint64_t vmm_slow_calls, vmm_slow_ns, vmm_max_ns;   /* VMM calls that took > 2 ms (stalls inside the driver), their total, the worst */
+    uint64_t inplace_uses;      /* host-backed mode: operands of oversized launches that were used where they were (host-mapped) */
 } vgpu_swap_stats_t;
 int vgpu_swap_create(int dev, const vgpu_swap_config_t *cfg, vgpu_swap_t **out);
 void vgpu_swap_destroy(vgpu_swap_t *s);

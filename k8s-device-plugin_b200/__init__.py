@@ -69,7 +69,7 @@ class SwapStats(C.Structure):
         "direct_out_bytes", "direct_in_bytes", "prefetch_issued", "prefetch_hits", "prefetch_wasted", "demand_waits",
         "clean_evictions", "host_slabs", "host_slabs_local", "pager_unmap_ns", "pager_setaccess_ns", "pager_issue_ns",
         "pager_poll_ns", "pager_lock_ns")] + [("pager_step_ns", C.c_uint64 * 5)] + [(n, C.c_uint64) for n in (
-        "vmm_slow_calls", "vmm_slow_ns", "vmm_max_ns")]
+        "vmm_slow_calls", "vmm_slow_ns", "vmm_max_ns", "inplace_uses")]
 
     def as_dict(self):
         return {n: (list(getattr(self, n)) if n == "pager_step_ns" else getattr(self, n)) for n, _ in self._fields_}

@@ -256,6 +256,7 @@ static void fill_stats(const SwapStats &s, vgpu_swap_stats_t *o) {
     o->pager_poll_ns = s.pager_poll_ns; o->pager_lock_ns = s.pager_lock_ns;
     for (int i = 0; i < 5; i++) o->pager_step_ns[i] = s.pager_step_ns[i];
     o->vmm_slow_calls = s.vmm_slow_calls; o->vmm_slow_ns = s.vmm_slow_ns; o->vmm_max_ns = s.vmm_max_ns;
+    o->inplace_uses = s.inplace_uses;
 }
 VGPU_API int vgpu_swap_create(int dev, const vgpu_swap_config_t *cfg, vgpu_swap_t **out) {
     if (!out) return CUDA_ERROR_INVALID_VALUE;

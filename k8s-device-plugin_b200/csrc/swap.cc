@@ -837,7 +837,7 @@ void SwapEngine::hint_prefetch(int row) {
     std::lock_guard<std::mutex> g(mu_);
     if (!row_live(row)) return;
     Side &s = side_[row];
-    if (rows_[row].state != VGPU_ST_PAGED_OUT || s.phase != PH_IDLE) return;
+    if (rows_[row].state != VGPU_ST_PAGED_OUT || s.phase != PH_IDLE || s.inplace > 0) return;
     s.phase = PH_QUEUED;
     s.demand = false;
     prefetch_q_.push_back(QEntry{row, s.gen});
@@ -858,7 +858,7 @@ void SwapEngine::schedule_prefetch() {
         if (nxt < 0 || nxt == last_row_ || !row_live(nxt)) break;
         cur = nxt;
         Side &s = side_[cur];
-        if (rows_[cur].state != VGPU_ST_PAGED_OUT || s.phase != PH_IDLE) continue;   // resident, loading or already queued
+        if (rows_[cur].state != VGPU_ST_PAGED_OUT || s.phase != PH_IDLE || s.inplace > 0) continue;   // resident, loading, already queued, or in use where it is
         if (s.mapped > window) break;
         s.phase = PH_QUEUED;
         s.demand = false;
@@ -1063,6 +1063,8 @@ void SwapEngine::begin_load_locked(int row, bool prefetch, InItem *it) {
     it->host_off = s.host_off; it->has_host = s.has_host; it->prefetch = prefetch;
     it->va_off = s.va_off; it->hosted = s.hosted;
     it->after = nullptr;
+    it->wait.clear();
+    if (s.hosted) collect_waits_locked(row, &it->wait);      // uses of the row where it was (in-place operands of oversized launches)
     s.phase = PH_LOADING;
     resident_mapped_ += s.mapped;
     it->ready = get_event();
@@ -1136,6 +1138,7 @@ CUresult SwapEngine::load_direct(Lock &lk, std::vector<InItem> &items) {
         pressure_seen |= pressure;
         if (it.rc != CUDA_SUCCESS) continue;
         if (it.hosted) {                             // host-backed mode: the range maps the host backing right now
+            for (CUevent e : it.wait) d.cuEventSynchronize(e);    // ... and work that was told to use it there must be through with it
             std::vector<std::pair<CUdeviceptr, size_t>> one{{it.base, it.mapped}};
             unmap_batch(one);
             it.hosted = false;
@@ -1561,6 +1564,13 @@ bool SwapEngine::step_demand(Lock &lk) {
         demand_q_.pop_front();
     }
     if (demand_q_.empty()) return false;
+    if (side_[demand_q_.front().row].inplace > 0) {
+        // somebody is using this row where it is (host-mapped, an oversized launch): it cannot move before that use is over
+        QEntry e = demand_q_.front();
+        demand_q_.pop_front();
+        demand_q_.push_back(e);
+        return false;
+    }
     const int row = demand_q_.front().row;
     const uint64_t need = side_[row].mapped;
     scan_unit_ = need;
@@ -1570,6 +1580,7 @@ bool SwapEngine::step_demand(Lock &lk) {
         if (cfg_.resident_cap == quota_cap_) pressure_ = false;
     }
     auto fail = [&](CUresult rc) {
+        demand_row_ = -1;
         demand_q_.pop_front();
         side_[row].phase = PH_IDLE;
         side_[row].fail = rc;
@@ -1586,10 +1597,12 @@ bool SwapEngine::step_demand(Lock &lk) {
         // room is there (freed by the pager ahead of need, or never used): map + direct copy, together with whatever
         // other demanded rows fit
         std::vector<InItem> items;
+        demand_row_ = -1;                                // (the waiting clocks below restart with the next demand)
         while (!demand_q_.empty() && items.size() < cfg_.batch_rows) {
             QEntry e = demand_q_.front();
             Side &s = side_[e.row];
             bool ok = s.gen == e.gen && s.phase == PH_QUEUED && s.demand;
+            if (ok && s.inplace > 0) break;
             if (ok && (free_phys_locked() < (int64_t)s.mapped || (budget_fn_ && !items.empty() && !reserve_locked(s.mapped)))) break;
             demand_q_.pop_front();
             if (!ok) continue;
@@ -1606,13 +1619,25 @@ bool SwapEngine::step_demand(Lock &lk) {
     const uint64_t shortage = (uint64_t)((int64_t)need - free_now - (int64_t)evicting_mapped_);
     std::vector<uint32_t> victims;
     uint64_t evictable = 0;
+    const uint64_t epoch_before = release_epoch_;
     CUresult r = choose_victims(lk, shortage, &victims, &evictable);
     if (r != CUDA_SUCCESS) return fail(r);
     // the lock was released during the scan: the world may have moved on
     if (demand_q_.empty() || demand_q_.front().row != row || side_[row].phase != PH_QUEUED) return true;
+    if (evictable < shortage && release_epoch_ != epoch_before) return true;   // pins were released while the scan ran: it saw them, look again
     if (evictable < shortage) {
         bool in_flight = evicting_mapped_ > 0 || !zombies_.empty();
         if (in_flight) return false;
+        if (open_admissions_ > 0) {
+            // what is in the way is pinned by admissions of other threads whose launch is being issued right now: their pins go
+            // with their note_use. Evict what can be evicted and look again — for a bounded time (an application that nests
+            // acquisitions on one thread would wait for itself)
+            if (demand_row_ != row) { demand_row_ = row; demand_since_ns_ = mono_ns(); }
+            if (mono_ns() - demand_since_ns_ < 2000000000ull) {
+                if (!victims.empty()) evict_direct(lk, victims);
+                return false;
+            }
+        }
         if (sibling_engines_ > 1 && need <= fair_share_) {
             // the room is held by a sibling process of the container: its pager gives it up as soon as it sees our live bytes
             // (fair share of the common quota); evict what we can meanwhile and keep waiting — but not for ever (a sibling
@@ -1623,10 +1648,16 @@ bool SwapEngine::step_demand(Lock &lk) {
                 return false;
             }
         }
-        LOG_ERROR("resident quota %lu MiB cannot hold the working set of this launch (need %lu MiB more, evictable %lu MiB)",
-                  (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(shortage >> 20), (unsigned long)(evictable >> 20));
+        LOG_ERROR("resident quota %lu MiB cannot hold the working set of this launch (need %lu MiB more, evictable %lu MiB; %d admissions in flight, waited %lu ms)",
+                  (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(shortage >> 20), (unsigned long)(evictable >> 20), open_admissions_,
+                  (unsigned long)(demand_row_ == row ? (mono_ns() - demand_since_ns_) / 1000000 : 0));
+        if (std::getenv("VGPU_SWAP_DEBUG_DUMP"))
+            for (size_t i = 0; i < rows_.size(); i++)
+                std::fprintf(stderr, "  row %zu state=%u pins=%d inplace=%d phase=%d locked=%d demand=%d hosted=%d mapped=%zu%s\n", i, rows_[i].state, side_[i].pins,
+                             side_[i].inplace, (int)side_[i].phase, (int)side_[i].locked, (int)side_[i].demand, (int)side_[i].hosted, side_[i].mapped, (int)i == row ? "  <- demanded" : "");
         return fail(CUDA_ERROR_OUT_OF_MEMORY);
     }
+    demand_row_ = -1;
     if (evicting_mapped_ == 0 && !cfg_.host_backed) {
         demand_q_.pop_front();
         swap_staged(lk, row, victims);           // latency path
@@ -1641,6 +1672,7 @@ bool SwapEngine::step_prefetch(Lock &lk) {
     while (!prefetch_q_.empty() && items.size() < cfg_.batch_rows) {
         QEntry e = prefetch_q_.front();
         bool ok = (size_t)e.row < side_.size() && side_[e.row].gen == e.gen && side_[e.row].phase == PH_QUEUED && !side_[e.row].demand;
+        if (ok && side_[e.row].inplace > 0) { side_[e.row].phase = PH_IDLE; queued_prefetch_bytes_ -= side_[e.row].mapped; ok = false; }   // in use where it is
         if (!ok) { prefetch_q_.pop_front(); continue; }
         Side &s = side_[e.row];
         if (free_phys_locked() < (int64_t)s.mapped || (budget_fn_ && !reserve_locked(s.mapped))) break;
@@ -1939,7 +1971,30 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
         for (int r : missing) need += side_[r].mapped;
         for (int i = 0; i < n; i++) if (rows_[rows[i]].state & VGPU_ST_RESIDENT) pinned += side_[rows[i]].mapped;
         // with sibling engines the cap moves (they give room up as they see our demand): judge against the fair share then
-        if (need + pinned > (budget_fn_ && sibling_engines_ > 1 ? std::max(cfg_.resident_cap, fair_share_) : cfg_.resident_cap)) {
+        const uint64_t room = budget_fn_ && sibling_engines_ > 1 ? std::max(cfg_.resident_cap, fair_share_) : cfg_.resident_cap;
+        std::vector<int> inplace;
+        if (need + pinned > room && cfg_.host_backed) {
+            // Host-backed mode: a launch whose operands do not fit the quota together still runs (under UVM, the reference's
+            // swap, it would thrash but work): as many operands as fit are paged in, in argument order; the others are used
+            // WHERE THEY ARE — a paged-out row's own range maps its host backing — at PCIe speed. The pager leaves such a row
+            // alone until this use has been recorded and has completed (Side::inplace, load_direct).
+            uint64_t take = pinned;
+            std::vector<int> fit;
+            for (int r : missing) {
+                if (take + side_[r].mapped <= room) { take += side_[r].mapped; fit.push_back(r); }
+                else inplace.push_back(r);
+            }
+            missing.swap(fit);
+            need = take - pinned;
+            for (int r : inplace) {
+                Side &s = side_[r];
+                s.inplace++;
+                if (s.phase == PH_QUEUED && !s.demand) { s.phase = PH_IDLE; queued_prefetch_bytes_ -= s.mapped; }    // a wish for it: dropped
+            }
+            st_.inplace_uses += inplace.size();
+            st_.faults -= inplace.size();
+        }
+        if (need + pinned > room) {
             LOG_ERROR("resident quota %lu MiB cannot hold the working set of this launch (%lu MiB)", (unsigned long)(cfg_.resident_cap >> 20),
                       (unsigned long)((need + pinned) >> 20));
             rc = CUDA_ERROR_OUT_OF_MEMORY;
@@ -1968,7 +2023,20 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
                 else if (rc == CUDA_SUCCESS) rc = side_[r].fail != CUDA_SUCCESS ? side_[r].fail : CUDA_ERROR_OUT_OF_MEMORY;
                 mark_dirty(r);
             }
+            if (!inplace.empty()) {
+                // a row on its way out or in is a hole for a moment: wait until the pager is done with it
+                cv_admit_.wait(lk, [&] {
+                    for (int r : inplace) if (side_[r].phase == PH_EVICTING || side_[r].phase == PH_LOADING) return false;
+                    return true;
+                });
+                for (int r : inplace) {
+                    Side &s = side_[r];
+                    if (rows_[r].state & VGPU_ST_RESIDENT) { rows_[r].state = VGPU_ST_RESIDENT | VGPU_ST_PINNED; mark_dirty(r); s.inplace--; }   // paged in meanwhile: an ordinary pinned operand
+                    else if (!s.hosted && rc == CUDA_SUCCESS) rc = CUDA_ERROR_OUT_OF_MEMORY;   // its host mapping could not be made (reap)
+                }
+            }
         }
+        if (rc != CUDA_SUCCESS) for (int r : inplace) if (!(rows_[r].state & VGPU_ST_RESIDENT)) side_[r].inplace--;
         if (rc != CUDA_SUCCESS) {
             for (int i = 0; i < n; i++) {
                 Side &s = side_[rows[i]];
@@ -1989,6 +2057,7 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
         else d.cuStreamWaitEvent(stream, s.ready, 0);
     }
     if (!missing.empty()) publish_locked();
+    if (stream != kHostWait) open_admissions_++;     // (host-wait admissions — capture, pin, graph nodes — keep their pins for good)
     if (!host_wait.empty()) {
         // the rows are pinned, so their `ready` events stay theirs while the lock is released
         lk.unlock();
@@ -2002,6 +2071,8 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
 void SwapEngine::note_use(const int *rows, int n, CUstream stream, bool writes) {
     const DriverTable &d = drv();
     std::lock_guard<std::mutex> g(mu_);
+    if (open_admissions_ > 0) open_admissions_--;
+    release_epoch_++;
     uint64_t seq = ++use_seq_;
     size_t ring = use_ring_.size();
     CUcontext cur = nullptr;
@@ -2037,6 +2108,7 @@ void SwapEngine::note_use(const int *rows, int n, CUstream stream, bool writes) 
         Side &s = side_[rows[i]];
         s.uses[s.nuses++] = seq;
         if (writes && !s.read_mostly) s.dirty = true;
+        if (s.inplace > 0 && !(rows_[rows[i]].state & VGPU_ST_RESIDENT)) s.inplace--;     // used where it was (host-mapped): the pager may move it again once this use is done
         if (s.pins > 0 && --s.pins == 0 && !s.locked && (rows_[rows[i]].state & VGPU_ST_RESIDENT)) {
             rows_[rows[i]].state = VGPU_ST_RESIDENT;
             mark_dirty(rows[i]);
@@ -2055,6 +2127,11 @@ CUresult SwapEngine::pin_resident(int row, bool on) {
         if (rc != CUDA_SUCCESS) return rc;
         std::lock_guard<std::mutex> g(mu_);
         Side &s = side_[row];
+        if (!(rows_[row].state & VGPU_ST_RESIDENT)) {            // (host-backed mode served it in place: it does not fit the quota at all)
+            if (s.inplace > 0) s.inplace--;
+            if (s.pins > 0) s.pins--;
+            return CUDA_ERROR_OUT_OF_MEMORY;
+        }
         s.locked = true;
         if (s.pins > 0) s.pins--;                 // the lock keeps it; the admission's pin is not needed
         s.dirty = true;                           // whoever reaches it behind the hook's back may write

@@ -90,6 +90,7 @@ struct SwapStats {
     uint64_t pager_vmm_ns = 0, pager_scan_ns = 0, pager_packsync_ns = 0, pager_ring_ns = 0, pager_busy_ns = 0;
     uint64_t vmm_calls = 0;                // cuMemUnmap + cuMemSetAccess calls issued (after batching)
     uint64_t pager_unmap_ns = 0, pager_setaccess_ns = 0, pager_map_ns = 0, pager_create_ns = 0;   // breakdown of pager_vmm_ns (diagnostics)
+    uint64_t inplace_uses = 0;             // host-backed mode: operands of oversized launches used in place (host-mapped)
     uint64_t vmm_slow_calls = 0, vmm_slow_ns = 0, vmm_max_ns = 0;   // VMM calls that took > 2 ms (driver stalls), their time, the worst one
     uint64_t pager_issue_ns = 0, pager_poll_ns = 0, pager_lock_ns = 0, pager_step_ns[5] = {0, 0, 0, 0, 0};   // copy/event enqueue calls; busy time per step (zombies, reap, demand, prefetch, evict-ahead)
     uint64_t pack_bytes = 0, unpack_bytes = 0;       // bytes moved by the staged path's kernels
@@ -183,6 +184,7 @@ class SwapEngine {
         uint64_t uses[kMaxUses] = {0, 0, 0, 0};   // sequence numbers of the outstanding last-use events, one per stream
         int nuses = 0;
         int pins = 0;
+        int inplace = 0;         // host-backed mode: admissions that were told to use the row where it is (host-mapped); no page-in meanwhile
         uint64_t va_off = 0;
         CUevent evict_done = nullptr;   // after it the row's physical memory is no longer read by its page-out
         int out_slot = -1;       // staging slot of the last staged page-out chunk of this row ...
@@ -226,7 +228,7 @@ class SwapEngine {
     bool step_evict_ahead(Lock &lk);
     struct OutItem { uint32_t row; CUdeviceptr base; uint64_t len; size_t mapped; uint64_t host_off; bool has_host, copy; bool new_host = false; uint64_t va_off = 0; CUmemGenericAllocationHandle hh = 0; bool has_hh = false; std::vector<CUevent> wait; CUevent done = nullptr; int out_slot = -1; uint64_t out_seq = 0; bool failed = false; };
     struct InItem { int row; CUdeviceptr base; uint64_t len; size_t mapped; uint64_t host_off; bool has_host; bool prefetch; uint64_t va_off = 0; bool hosted = false; CUmemGenericAllocationHandle h = 0; CUevent ready = nullptr;
-                    CUevent after = nullptr; CUresult rc = CUDA_SUCCESS; };
+                    CUevent after = nullptr; CUresult rc = CUDA_SUCCESS; std::vector<CUevent> wait; };
     CUresult choose_victims(Lock &lk, uint64_t shortage, std::vector<uint32_t> *victims, uint64_t *evictable);
     void begin_evict_locked(const std::vector<uint32_t> &victims, std::vector<OutItem> *items);
     CUresult evict_direct(Lock &lk, const std::vector<uint32_t> &victims);
@@ -321,6 +323,8 @@ class SwapEngine {
     std::vector<CtxEvents> ctx_events_;
     CUevent use_slot_event(CUcontext cur, size_t slot);
     uint64_t use_seq_ = 0;
+    uint64_t release_epoch_ = 0;                    // bumped by every note_use: pins were released
+    int open_admissions_ = 0;                       // admissions whose use has not been recorded yet (ensure_resident .. note_use): their pins are about to go
     bool stop_ = false, pager_idle_ = true, kick_ = false;
     void kick_pager_locked() { kick_ = true; cv_pager_.notify_one(); }
     void drop_prefetch_queue_locked();

@@ -29,6 +29,7 @@ typedef struct {
     uint64_t direct_out_bytes, direct_in_bytes, prefetch_issued, prefetch_hits, prefetch_wasted, demand_waits, clean_evictions, host_slabs, host_slabs_local;
     uint64_t pager_unmap_ns, pager_setaccess_ns, pager_issue_ns, pager_poll_ns, pager_lock_ns, pager_step_ns[5];
     uint64_t vmm_slow_calls, vmm_slow_ns, vmm_max_ns;
+    uint64_t inplace_uses;
 } swap_stats_t;
 typedef int (*stats_fn)(int, swap_stats_t *);
 typedef int (*prof_fn)(int, int);

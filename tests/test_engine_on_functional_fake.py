@@ -846,3 +846,133 @@ print(json.dumps({"bad": bad.value, "scratch": hex(word.value)}))
     assert r.returncode == 0, r.stderr[-3000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out == {"bad": 0, "scratch": "0xabababababababab"}, out
+
+
+def test_host_backed_mode_runs_a_launch_whose_operands_exceed_the_quota(tmp_path):
+    """Under the reference (UVM) a kernel whose operands together exceed the quota thrashes but runs. The default engine
+    refuses such a launch (every operand must be resident while the kernel runs); in host-backed mode the operands that fit
+    are paged in and the others are used where they are — their own range maps the host backing — and only move again once
+    that use is over. Random operand sets of 1-5 buffers x 20 MiB under a 48 MiB cap, every word checked at the end."""
+    code = r"""
+import ctypes as C, json, os, random, sys
+sys.path.insert(0, os.environ["VGPU_ROOT"])
+import k8s_device_plugin_b200 as v
+L = v.lib()
+drv = C.CDLL("libcuda.so.1")
+assert drv.cuInit(0) == 0
+dev, ctx = C.c_int(), C.c_void_p()
+assert drv.cuDeviceGet(C.byref(dev), 0) == 0 and drv.cuDevicePrimaryCtxRetain(C.byref(ctx), dev) == 0 and drv.cuCtxSetCurrent(ctx) == 0
+M = 1 << 20
+sw = v.Swap(resident_cap=48 * M, chunk_bytes=4 * M, ring_slots=2)
+n, nbytes = 8, 20 * M
+bufs = [sw.alloc(nbytes) for _ in range(n)]
+for i, p in enumerate(bufs):
+    sw.acquire([p], 0); assert L.vgpu_wl_fill(p, nbytes // 8, i, None) == 0; sw.release([p], 0)
+rng = random.Random(7)
+touches = [0] * n
+refused = oversized = 0
+for step in range(60):
+    k = rng.choice([1, 2, 2, 3, 4, 5])
+    idx = rng.sample(range(n), k)
+    ptrs = [bufs[i] for i in idx]
+    try:
+        sw.acquire(ptrs, 0)
+    except Exception:
+        refused += 1
+        continue
+    oversized += int(k * nbytes > 48 * M)
+    for i in idx:
+        assert L.vgpu_wl_touch(bufs[i], nbytes // 8, None) == 0; touches[i] += 1
+    sw.release(ptrs, 0)
+    if step % 7 == 0:
+        peak = sum(e.size for e in sw.table() if e.state & 1)
+        assert peak <= 48 * M, peak
+cnt = C.c_uint64()
+assert drv.cuMemAlloc_v2(C.byref(cnt), 8) == 0 and drv.cuMemsetD8_v2(cnt, 0, 8) == 0
+for i, p in enumerate(bufs):
+    sw.acquire([p], 0); assert L.vgpu_wl_verify(p, nbytes // 8, i, touches[i], cnt.value, None) == 0; sw.release([p], 0)
+assert drv.cuCtxSynchronize() == 0
+bad = C.c_uint64()
+assert drv.cuMemcpyDtoH_v2(C.byref(bad), cnt, 8) == 0
+st = sw.stats()
+for p in bufs:
+    sw.free(p)
+sw.drain()
+print(json.dumps({"bad": bad.value, "refused": refused, "oversized": oversized, "inplace_uses": st["inplace_uses"], "faults": st["faults"],
+                  "touches": sum(touches), "live_after": sw.stats()["live_bytes"]}))
+"""
+    env = _env(tmp_path, VGPU_ROOT=ROOT, VGPU_SWAP_HOST_BACKED=1)
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["bad"] == 0 and out["refused"] == 0 and out["oversized"] >= 15 and out["inplace_uses"] >= out["oversized"] and out["live_after"] == 0, out
+    env = _env(tmp_path, VGPU_ROOT=ROOT)                                # default mode refuses exactly the oversized ones, everything else is intact
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    dflt = json.loads(r.stdout.strip().splitlines()[-1])
+    assert dflt["bad"] == 0 and dflt["refused"] == out["oversized"] and dflt["inplace_uses"] == 0, dflt
+
+
+@pytest.mark.parametrize("mode", ["host_backed", "default"])
+def test_multi_operand_launches_from_several_threads(tmp_path, mode):
+    """Three application threads share one engine (64 MiB cap, 260 MiB live): each admits random sets of operands — its own
+    buffers (touched) plus buffers all threads read. Host-backed mode, 1-4 operands (4 x 20 MiB exceeds the cap): one thread
+    uses a row in place while another demands the same row resident; the pager must not move a row under a use in place.
+    Default mode, 1-3 operands: at times everything resident is pinned by the other threads' admissions — the demand then
+    waits for their release instead of failing. Every word is checked."""
+    code = r"""
+import ctypes as C, json, os, random, sys, threading
+sys.path.insert(0, os.environ["VGPU_ROOT"])
+import k8s_device_plugin_b200 as v
+L = v.lib()
+drv = C.CDLL("libcuda.so.1")
+assert drv.cuInit(0) == 0
+dev, ctx = C.c_int(), C.c_void_p()
+assert drv.cuDeviceGet(C.byref(dev), 0) == 0 and drv.cuDevicePrimaryCtxRetain(C.byref(ctx), dev) == 0 and drv.cuCtxSetCurrent(ctx) == 0
+M = 1 << 20
+sw = v.Swap(resident_cap=64 * M, chunk_bytes=4 * M, ring_slots=2)
+nbytes, T = 20 * M, 3
+shared = [sw.alloc(nbytes) for _ in range(4)]
+own = [[sw.alloc(nbytes) for _ in range(3)] for _ in range(T)]
+def fill(p, i):
+    sw.acquire([p], 0); assert L.vgpu_wl_fill(p, nbytes // 8, i, None) == 0; sw.release([p], 0)
+for i, p in enumerate(shared): fill(p, 100 + i)
+for t in range(T):
+    for j, p in enumerate(own[t]): fill(p, 10 * t + j)
+touches = [[0] * 3 for _ in range(T)]
+bad = [C.c_uint64() for _ in range(T)]
+errors = []
+def worker(t):
+    try:
+        assert drv.cuCtxSetCurrent(ctx) == 0
+        rng = random.Random(40 + t)
+        cnt = C.c_uint64()
+        assert drv.cuMemAlloc_v2(C.byref(cnt), 8) == 0 and drv.cuMemsetD8_v2(cnt, 0, 8) == 0
+        for step in range(50):
+            k = rng.choice([1, 2, 3, 4, 4] if os.environ.get("VGPU_SWAP_HOST_BACKED") == "1" else [1, 2, 3, 3])
+            pool = [("o", j) for j in range(3)] + [("s", j) for j in range(4)]
+            pick = rng.sample(pool, k)
+            ptrs = [own[t][j] if w == "o" else shared[j] for w, j in pick]
+            sw.acquire(ptrs, 0)
+            for w, j in pick:
+                if w == "o":
+                    assert L.vgpu_wl_touch(own[t][j], nbytes // 8, None) == 0; touches[t][j] += 1
+                else:
+                    assert L.vgpu_wl_verify(shared[j], nbytes // 8, 100 + j, 0, cnt.value, None) == 0
+            sw.release(ptrs, 0)
+        for j, p in enumerate(own[t]):
+            sw.acquire([p], 0); assert L.vgpu_wl_verify(p, nbytes // 8, 10 * t + j, touches[t][j], cnt.value, None) == 0; sw.release([p], 0)
+        assert drv.cuMemcpyDtoH_v2(C.byref(bad[t]), cnt, 8) == 0
+    except BaseException as e:
+        errors.append(repr(e))
+ths = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+[x.start() for x in ths]; [x.join() for x in ths]
+st = sw.stats()
+print(json.dumps({"errors": errors, "bad": sum(b.value for b in bad), "inplace_uses": st["inplace_uses"], "faults": st["faults"]}))
+"""
+    env = _env(tmp_path, VGPU_ROOT=ROOT, VGPU_SWAP_HOST_BACKED=int(mode == "host_backed"))
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["errors"] == [] and out["bad"] == 0, out
+    assert out["inplace_uses"] > 10 if mode == "host_backed" else out["inplace_uses"] == 0, out
