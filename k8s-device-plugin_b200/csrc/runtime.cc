@@ -1050,7 +1050,7 @@ void Runtime::touch_done(CUstream st) {
     int dev = current_device();
     if (SwapEngine *e = swap(dev)) {
         if (!t_touch_w.empty()) e->note_use(t_touch_w.data(), (int)t_touch_w.size(), st, true);
-        if (!t_touch_r.empty()) e->note_use(t_touch_r.data(), (int)t_touch_r.size(), st, false);
+        if (!t_touch_r.empty()) e->note_use(t_touch_r.data(), (int)t_touch_r.size(), st, false, /*closes_admission=*/t_touch_w.empty());
     }
     t_touch_w.clear(); t_touch_r.clear();
 }

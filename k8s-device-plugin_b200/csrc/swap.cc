@@ -2068,10 +2068,10 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
     return CUDA_SUCCESS;
 }
 
-void SwapEngine::note_use(const int *rows, int n, CUstream stream, bool writes) {
+void SwapEngine::note_use(const int *rows, int n, CUstream stream, bool writes, bool closes_admission) {
     const DriverTable &d = drv();
     std::lock_guard<std::mutex> g(mu_);
-    if (open_admissions_ > 0) open_admissions_--;
+    if (closes_admission && open_admissions_ > 0) open_admissions_--;
     release_epoch_++;
     uint64_t seq = ++use_seq_;
     size_t ring = use_ring_.size();

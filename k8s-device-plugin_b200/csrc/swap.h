@@ -120,7 +120,8 @@ class SwapEngine {
     static inline CUstream kHostWait = reinterpret_cast<CUstream>(~uintptr_t(0));
     CUresult ensure_resident(const int *rows, int n, CUstream stream);
     // writes = false: the work just enqueued only READS the rows (memcpy source): they stay clean
-    void note_use(const int *rows, int n, CUstream stream, bool writes = true);
+    // closes_admission = false: a second call for the same admission (its read-only operands after its written ones)
+    void note_use(const int *rows, int n, CUstream stream, bool writes = true, bool closes_admission = true);
     // Scans kernel parameter bytes for pointers into the arena; appends distinct row indices.
     void collect_rows(const void *param, size_t bytes, std::vector<int> *rows) const;
     // cuMemAdvise(SET/UNSET_READ_MOSTLY) on a swappable range: kernel launches no longer mark it dirty
