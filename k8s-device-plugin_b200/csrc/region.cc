@@ -244,6 +244,8 @@ uint64_t Region::swap_reserve(int32_t pid, int dev, uint64_t want_total, uint64_
     if (engines) *engines = 1;
     if (!ext_) { *granted = true; return ~0ull; }
     lock();
+    bool swept = false;
+again:
     const uint64_t lim = r_->limit[dev];
     vgpu_swap_record_t *mine = nullptr;
     uint64_t live_all = 0;
@@ -276,6 +278,18 @@ uint64_t Region::swap_reserve(int32_t pid, int dev, uint64_t want_total, uint64_
         others += rec.resident_bytes > entitled ? rec.resident_bytes : entitled;
     }
     uint64_t cap = room > others ? room - others : 0;
+    if (n > 1 && !swept) {
+        // What siblings hold or are entitled to shapes this engine's cap: a sibling that was killed (no exit handler ran)
+        // still has its record and its slot. Look — /proc, at most every 100 ms — and judge again without the dead.
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        uint64_t now = (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+        if (now - last_dead_sweep_ns_ > 100000000ull) {
+            last_dead_sweep_ns_ = now;
+            swept = true;
+            if (reap_dead_locked() > 0) goto again;
+        }
+    }
     if (want_total <= cap) { *granted = true; if (mine) mine->resident_bytes = want_total; }
     unlock();
     return cap;

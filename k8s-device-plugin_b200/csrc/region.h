@@ -84,6 +84,7 @@ class Region {
     int fd_ = -1;
     std::string path_;
     int cached_slot_ = -1;
+    uint64_t last_dead_sweep_ns_ = 0;           // swap_reserve: when the siblings' liveness was last checked
 };
 
 }  // namespace vgpu

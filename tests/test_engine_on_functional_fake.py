@@ -498,6 +498,54 @@ def test_a_late_sibling_gets_its_share_from_a_process_that_already_fills_the_quo
                 p.kill(); p.communicate()
 
 
+def test_a_killed_sibling_gives_its_share_back(tmp_path):
+    """Two processes share the quota, then one is SIGKILLed (no exit handler: its slot and its swap record stay in the
+    region). The survivor's pager notices within its periodic look at the region (/proc says the pid is gone), the dead
+    process's bytes and share are dropped, and the survivor grows back to the whole quota."""
+    import select, signal, time
+    cache = str(tmp_path / "killed.cache")
+    env = _env(tmp_path, LD_PRELOAD=HOOK_SO, CUDA_OVERSUBSCRIBE="true", CUDA_DEVICE_MEMORY_LIMIT_0="256m", CUDA_DEVICE_MEMORY_SHARED_CACHE=cache,
+               VGPU_SWAP_CHUNK_MB="2", VGPU_SWAP_RING="2")
+    args = [os.path.join(LIBDIR, "swap_bench"), "--cubin", CUBIN, "--buffers", "24", "--mib", "16", "--steps", "400", "--warmup", "8", "--order", "cyclic",
+            "--wait-stdin", "1"]
+    procs = []
+    try:
+        for _ in range(2):
+            p = subprocess.Popen(args, env=env, stdin=subprocess.PIPE, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            procs.append(p)
+            deadline, ready = 120, False
+            while deadline > 0 and not ready:
+                r, _, _ = select.select([p.stderr], [], [], 1.0)
+                deadline -= 1
+                if r:
+                    line = p.stderr.readline()
+                    ready = line.startswith("READY")
+                    if not line:
+                        break
+            assert ready, "process did not get through its populate phase"
+        reg = v.Region(cache)
+        c = reg.swap_counters(0)
+        assert c["processes"] == 2 and c["resident_bytes"] <= 256 * M, c
+        procs[1].send_signal(signal.SIGKILL); procs[1].communicate()
+        procs[0].stdin.write("go\n"); procs[0].stdin.flush()
+        peak_alone = 0
+        t0 = time.time()
+        while procs[0].poll() is None and time.time() - t0 < 280:
+            c = reg.swap_counters(0)
+            if c["processes"] == 1:
+                peak_alone = max(peak_alone, c["resident_bytes"])
+            time.sleep(0.005)
+        out, err = procs[0].communicate(timeout=30)
+        assert procs[0].returncode == 0, err[-2000:]
+        assert json.loads(out.strip().splitlines()[-1])["mismatches"] == 0
+        # two engines: each at most (256 - 2 x 8 MiB of staging rings) / 2 = 120 MiB; alone again: far above that
+        assert peak_alone > 200 * M, peak_alone
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill(); p.communicate()
+
+
 @pytest.mark.parametrize("seed", [31, 32])
 def test_engine_fuzz_in_host_backed_mode(tmp_path, seed):
     """VGPU_SWAP_HOST_BACKED=1: an evicted range is re-mapped onto its host backing (a host-located VMM handle) instead of
