@@ -434,13 +434,55 @@ EXPORT CUresult cuGraphAddMemsetNode(void **node, void *g, const void *deps, siz
     x->n++;
     return CUDA_SUCCESS;
 }
+/* CUDA_MEMCPY3D as cuda.h lays it out (200 bytes); only linear device/host operands with Height = Depth = 1 are replayed */
+struct fg_copy3d {
+    size_t srcXInBytes, srcY, srcZ, srcLOD; unsigned srcMemoryType, pad0; const void *srcHost; CUdeviceptr srcDevice; void *srcArray; void *reserved0; size_t srcPitch, srcHeight;
+    size_t dstXInBytes, dstY, dstZ, dstLOD; unsigned dstMemoryType, pad1; void *dstHost; CUdeviceptr dstDevice; void *dstArray; void *reserved1; size_t dstPitch, dstHeight;
+    size_t WidthInBytes, Height, Depth;
+};
+static CUresult fg_copy_now(const struct fg_copy3d *c) {
+    if (!c || c->Height > 1 || c->Depth > 1 || c->srcArray || c->dstArray) return CUDA_ERROR_INVALID_VALUE;
+    const void *src = c->srcMemoryType == 1 ? c->srcHost : (const void *)(uintptr_t)c->srcDevice;      /* CU_MEMORYTYPE_HOST = 1, DEVICE = 2, UNIFIED = 4 */
+    void *dst = c->dstMemoryType == 1 ? c->dstHost : (void *)(uintptr_t)c->dstDevice;
+    if (fake_exec_on()) memmove((char *)dst + c->dstXInBytes, (const char *)src + c->srcXInBytes, c->WidthInBytes);
+    return CUDA_SUCCESS;
+}
+EXPORT CUresult cuMemcpy3D_v2(const struct fg_copy3d *c) { return fg_copy_now(c); }
+EXPORT CUresult cuMemcpy3DAsync_v2(const struct fg_copy3d *c, CUstream st) { (void)st; return fg_copy_now(c); }
+static struct fg_copy3d g_fg_copies[64];
+static int g_fg_ncopies;
+EXPORT CUresult cuGraphAddMemcpyNode(void **node, void *g, const void *deps, size_t ndeps, const struct fg_copy3d *c, void *ctx) {
+    (void)deps; (void)ndeps; (void)ctx;
+    struct fg_graph *x = g;
+    if (!x || x->magic != FG_MAGIC || !c || x->n >= 64 || g_fg_ncopies >= 64) return CUDA_ERROR_INVALID_VALUE;
+    struct fg_node *nd = &x->node[x->n];
+    memset(nd, 0, sizeof *nd);
+    nd->kind = 2; nd->np = g_fg_ncopies;                     /* index into the copy-parameter store */
+    g_fg_copies[g_fg_ncopies++] = *c;
+    if (node) *node = nd;
+    x->n++;
+    return CUDA_SUCCESS;
+}
+/* CUgraphNodeParams: { int type; int reserved0[3]; union { ... } at offset 16; long long reserved2 }. Types: KERNEL 0, MEMCPY 1, MEMSET 2 */
+struct fg_generic { int type, r0[3]; union { long long pad[29]; struct fg_kparams kernel; struct { int flags, reserved; void *copyCtx; struct fg_copy3d copyParams; } memcpy;
+                                             struct { CUdeviceptr dst; size_t pitch; unsigned value, elementSize; size_t width, height; void *ctx; } memset; } u; long long r2; };
+EXPORT CUresult cuGraphAddKernelNode_v2(void **node, void *g, const void *deps, size_t ndeps, const struct fg_kparams *p);
+EXPORT CUresult cuGraphAddMemsetNode(void **node, void *g, const void *deps, size_t ndeps, const struct fg_msparams *m, void *ctx);
+EXPORT CUresult cuGraphAddNode(void **node, void *g, const void *deps, size_t ndeps, struct fg_generic *np) {
+    if (!np) return CUDA_ERROR_INVALID_VALUE;
+    if (np->type == 0) return cuGraphAddKernelNode_v2(node, g, deps, ndeps, &np->u.kernel);
+    if (np->type == 1) return cuGraphAddMemcpyNode(node, g, deps, ndeps, &np->u.memcpy.copyParams, np->u.memcpy.copyCtx);
+    if (np->type == 2) { struct fg_msparams m = {np->u.memset.dst, np->u.memset.pitch, np->u.memset.value, np->u.memset.elementSize, np->u.memset.width, np->u.memset.height};
+                         return cuGraphAddMemsetNode(node, g, deps, ndeps, &m, np->u.memset.ctx); }
+    return CUDA_ERROR_INVALID_VALUE;
+}
 EXPORT CUresult cuGraphInstantiateWithFlags(void **ge, void *g, unsigned long long flags) {
     (void)flags;
     struct fg_graph *x = g;
     if (!x || x->magic != FG_MAGIC) return CUDA_ERROR_INVALID_VALUE;
     struct fg_graph *c = malloc(sizeof *c);
     memcpy(c, x, sizeof *c);
-    for (int i = 0; i < c->n; i++) for (int k = 0; k < c->node[i].np; k++) c->node[i].pv[k] = c->node[i].val[k];
+    for (int i = 0; i < c->n; i++) if (c->node[i].kind == 0) for (int k = 0; k < c->node[i].np; k++) c->node[i].pv[k] = c->node[i].val[k];
     *ge = c;
     fg_reg(c, 1);
     return CUDA_SUCCESS;
@@ -453,6 +495,7 @@ EXPORT CUresult cuGraphLaunch(void *g, CUstream st) {
     for (int i = 0; i < x->n; i++) {
         struct fg_node *nd = &x->node[i];
         if (nd->kind == 0) { CUresult r = fx_launch(nd->f, nd->pv); if (r != CUDA_SUCCESS) return r; }
+        else if (nd->kind == 2) { CUresult r = fg_copy_now(&g_fg_copies[nd->np]); if (r != CUDA_SUCCESS) return r; }
         else if (nd->esize == 1) memset((void *)(uintptr_t)nd->dst, (int)nd->value, nd->width);
         else if (nd->esize == 2) for (size_t k = 0; k < nd->width; k++) ((unsigned short *)(uintptr_t)nd->dst)[k] = (unsigned short)nd->value;
         else for (size_t k = 0; k < nd->width; k++) ((unsigned *)(uintptr_t)nd->dst)[k] = nd->value;

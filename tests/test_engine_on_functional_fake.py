@@ -806,6 +806,18 @@ for i, p in enumerate(dst):
     launch(f_verify, p, nbytes // 8, 100 + i, 0, cnt.value)
 ck(cu.cuCtxSynchronize(), "sync")
 bad = C.c_uint64(); ck(cu.cuMemcpyDtoH_v2(C.byref(bad), cnt, 8), "read")
+# the 3-D copy family with linear device operands: both ends paged out by now, both admitted by the hook
+class C3(C.Structure):                                        # CUDA_MEMCPY3D
+    _fields_ = [("srcXInBytes", C.c_size_t), ("srcY", C.c_size_t), ("srcZ", C.c_size_t), ("srcLOD", C.c_size_t), ("srcMemoryType", C.c_uint), ("srcHost", C.c_void_p),
+                ("srcDevice", C.c_uint64), ("srcArray", C.c_void_p), ("reserved0", C.c_void_p), ("srcPitch", C.c_size_t), ("srcHeight", C.c_size_t),
+                ("dstXInBytes", C.c_size_t), ("dstY", C.c_size_t), ("dstZ", C.c_size_t), ("dstLOD", C.c_size_t), ("dstMemoryType", C.c_uint), ("dstHost", C.c_void_p),
+                ("dstDevice", C.c_uint64), ("dstArray", C.c_void_p), ("reserved1", C.c_void_p), ("dstPitch", C.c_size_t), ("dstHeight", C.c_size_t),
+                ("WidthInBytes", C.c_size_t), ("Height", C.c_size_t), ("Depth", C.c_size_t)]
+extra = alloc()
+c3 = C3(); c3.srcMemoryType = 2; c3.srcDevice = src[2]; c3.dstMemoryType = 2; c3.dstDevice = extra; c3.WidthInBytes, c3.Height, c3.Depth = nbytes, 1, 1
+ck(cu.cuMemcpy3DAsync_v2(C.byref(c3), None), "3d copy")
+ck(cu.cuMemsetD8_v2(cnt, 0, 8), "cnt0"); launch(f_verify, extra, nbytes // 8, 102, 0, cnt.value); ck(cu.cuCtxSynchronize(), "sync")
+bad3 = C.c_uint64(); ck(cu.cuMemcpyDtoH_v2(C.byref(bad3), cnt, 8), "read")
 # cuMemGetAddressRange answers for every swappable buffer, resident or paged out (most of these 33 are out), with the base
 # and the size the application asked for (not the 2 MiB-rounded mapping)
 odd = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(odd), C.c_size_t(5 * M + 4096)), "odd")
@@ -816,7 +828,7 @@ for p, sz in [(q, nbytes) for q in src + dst] + [(odd.value, 5 * M + 4096)]:
     ranges_ok += int(b.value == p and z.value == sz)
 b, z = C.c_uint64(), C.c_size_t()
 past_end = cu.cuMemGetAddressRange_v2(C.byref(b), C.byref(z), C.c_uint64(odd.value + 5 * M + 4096 + 8))   # inside the granule, outside the buffer
-print(json.dumps({"bad": bad.value, "after_small": after_small, "after_big": after_big, "ranges_ok": ranges_ok, "past_end_rc": past_end}))
+print(json.dumps({"bad": bad.value + bad3.value, "after_small": after_small, "after_big": after_big, "ranges_ok": ranges_ok, "past_end_rc": past_end}))
 """
     env = _env(tmp_path, LD_PRELOAD=HOOK_SO, CUDA_OVERSUBSCRIBE="true", CUDA_DEVICE_MEMORY_LIMIT_0="96m", CUBIN=CUBIN, VGPU_SWAP_CHUNK_MB="2", VGPU_SWAP_RING="2")
     r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
@@ -844,7 +856,7 @@ f_fill, f_touch, f_verify = C.c_void_p(), C.c_void_p(), C.c_void_p()
 for f, nm in ((f_fill, b"vgpu_wl_fill"), (f_touch, b"vgpu_wl_touch"), (f_verify, b"vgpu_wl_verify")):
     ck(cu.cuModuleGetFunction(C.byref(f), mod, nm), nm)
 M = 1 << 20
-n, nbytes = 14, 16 * M                                        # 224 MiB live under a 96 MiB quota
+n, nbytes = 14, 16 * M                                        # 224 MiB live under a 128 MiB quota (16 MiB of it the context, 8 MiB staging)
 bufs = []
 for i in range(n):
     p = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(p), C.c_size_t(nbytes)), "alloc"); bufs.append(p.value)
@@ -864,18 +876,36 @@ class MS(C.Structure):
 g, ge, node = C.c_void_p(), C.c_void_p(), C.c_void_p()
 ck(cu.cuGraphCreate(C.byref(g), 0), "graph")
 scratch = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(scratch), C.c_size_t(4 * M)), "scratch")     # swappable too (> 2 MiB)
-in_graph = [0, 5]                                             # buffers 0 and 5 are touched by the graph: evicted by now (LRU), paged back in to be pinned
-for i in in_graph:
+in_graph = [0, 11]                                            # touched by the graph (11 through cuGraphAddNode below): 0 is evicted by now (LRU), paged back in to be pinned
+no_touch = [9]                                                # read by the graph's memcpy node, never written
+for i in in_graph[:1]:
     keep, arr = params(bufs[i], nbytes // 8)
     kp = KP(f_touch.value, (64, 1, 1), (256, 1, 1), 0, C.cast(arr, C.c_void_p), None, None, None)
     ck(cu.cuGraphAddKernelNode_v2(C.byref(node), g, None, C.c_size_t(0), C.byref(kp)), "kernel node")
 ms = MS(scratch.value, 0, 0xAB, 1, 4 * M, 1)
 ck(cu.cuGraphAddMemsetNode(C.byref(node), g, None, C.c_size_t(0), C.byref(ms), ctx), "memset node")
+class C3(C.Structure):                                        # CUDA_MEMCPY3D
+    _fields_ = [("srcXInBytes", C.c_size_t), ("srcY", C.c_size_t), ("srcZ", C.c_size_t), ("srcLOD", C.c_size_t), ("srcMemoryType", C.c_uint), ("srcHost", C.c_void_p),
+                ("srcDevice", C.c_uint64), ("srcArray", C.c_void_p), ("reserved0", C.c_void_p), ("srcPitch", C.c_size_t), ("srcHeight", C.c_size_t),
+                ("dstXInBytes", C.c_size_t), ("dstY", C.c_size_t), ("dstZ", C.c_size_t), ("dstLOD", C.c_size_t), ("dstMemoryType", C.c_uint), ("dstHost", C.c_void_p),
+                ("dstDevice", C.c_uint64), ("dstArray", C.c_void_p), ("reserved1", C.c_void_p), ("dstPitch", C.c_size_t), ("dstHeight", C.c_size_t),
+                ("WidthInBytes", C.c_size_t), ("Height", C.c_size_t), ("Depth", C.c_size_t)]
+assert C.sizeof(C3) == 200
+copy_dst = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(copy_dst), C.c_size_t(nbytes)), "copy dst")           # swappable, written only by the graph
+c3 = C3(); c3.srcMemoryType = 2; c3.srcDevice = bufs[9]; c3.dstMemoryType = 2; c3.dstDevice = copy_dst.value
+c3.WidthInBytes, c3.Height, c3.Depth = nbytes, 1, 1                                                         # every replay: copy_dst := buffer 9
+ck(cu.cuGraphAddMemcpyNode(C.byref(node), g, None, C.c_size_t(0), C.byref(c3), ctx), "memcpy node")
+class GN(C.Structure):                                        # CUgraphNodeParams with its kernel member
+    _fields_ = [("type", C.c_int), ("reserved0", C.c_int * 3), ("kernel", KP), ("pad", C.c_longlong * (29 - C.sizeof(KP) // 8)), ("reserved2", C.c_longlong)]
+assert C.sizeof(GN) == 16 + 29 * 8 + 8
+keep_g, arr_g = params(bufs[11], nbytes // 8)
+gn = GN(); gn.type = 0; gn.kernel = KP(f_touch.value, (64, 1, 1), (256, 1, 1), 0, C.cast(arr_g, C.c_void_p), None, None, None)
+ck(cu.cuGraphAddNode(C.byref(node), g, None, C.c_size_t(0), C.byref(gn)), "generic kernel node")
 ck(cu.cuGraphInstantiateWithFlags(C.byref(ge), g, C.c_ulonglong(0)), "instantiate")
 touches = [0] * n
 for rep in range(3):
     for i, p in enumerate(bufs):                              # everything else cycles through the quota between replays
-        if i not in in_graph:
+        if i not in in_graph and i not in no_touch:
             launch(f_touch, p, nbytes // 8); touches[i] += 1
     ck(cu.cuGraphLaunch(ge, None), "replay")
     for i in in_graph:
@@ -887,13 +917,15 @@ for i, p in enumerate(bufs):
 ck(cu.cuCtxSynchronize(), "sync")
 bad = C.c_uint64(); ck(cu.cuMemcpyDtoH_v2(C.byref(bad), cnt, 8), "read")
 word = C.c_uint64(); ck(cu.cuMemcpyDtoH_v2(C.byref(word), C.c_uint64(scratch.value + 4 * M - 8), 8), "scratch")
-print(json.dumps({"bad": bad.value, "scratch": hex(word.value)}))
+ck(cu.cuMemsetD8_v2(cnt, 0, 8), "cnt0"); launch(f_verify, copy_dst.value, nbytes // 8, 9, 0, cnt.value); ck(cu.cuCtxSynchronize(), "sync")
+bad_copy = C.c_uint64(); ck(cu.cuMemcpyDtoH_v2(C.byref(bad_copy), cnt, 8), "read")
+print(json.dumps({"bad": bad.value, "scratch": hex(word.value), "bad_copy": bad_copy.value}))
 """
-    env = _env(tmp_path, LD_PRELOAD=HOOK_SO, CUDA_OVERSUBSCRIBE="true", CUDA_DEVICE_MEMORY_LIMIT_0="96m", CUBIN=CUBIN, VGPU_SWAP_CHUNK_MB="2", VGPU_SWAP_RING="2")
+    env = _env(tmp_path, LD_PRELOAD=HOOK_SO, CUDA_OVERSUBSCRIBE="true", CUDA_DEVICE_MEMORY_LIMIT_0="128m", CUBIN=CUBIN, VGPU_SWAP_CHUNK_MB="2", VGPU_SWAP_RING="2")
     r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
-    assert out == {"bad": 0, "scratch": "0xabababababababab"}, out
+    assert out == {"bad": 0, "scratch": "0xabababababababab", "bad_copy": 0}, out
 
 
 def test_host_backed_mode_runs_a_launch_whose_operands_exceed_the_quota(tmp_path):
