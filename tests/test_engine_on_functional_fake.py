@@ -538,8 +538,9 @@ def test_a_killed_sibling_gives_its_share_back(tmp_path):
         out, err = procs[0].communicate(timeout=30)
         assert procs[0].returncode == 0, err[-2000:]
         assert json.loads(out.strip().splitlines()[-1])["mismatches"] == 0
-        # two engines: each at most (256 - 2 x 8 MiB of staging rings) / 2 = 120 MiB; alone again: far above that
-        assert peak_alone > 200 * M, peak_alone
+        # two engines: each at most (256 - 2 x 16 MiB of context - 2 x 8 MiB of staging rings) / 2 = 104 MiB; alone again the
+        # survivor holds its cap minus the headroom its pager keeps free ahead of the page-in queue (a quarter of the cap)
+        assert peak_alone > 140 * M, peak_alone
     finally:
         for p in procs:
             if p.poll() is None:
