@@ -764,11 +764,7 @@ print(json.dumps({"bad": bad.value, "page_out": s.v[0], "page_in": s.v[1], "evic
     assert out["page_out"] < 0.7 * out["page_in"], out
 
 
-def test_batched_copies_admit_all_their_operands(tmp_path):
-    """cuMemcpyBatchAsync (CUDA 12.8) through the hook on the functional fake (an access to a paged-out range is a
-    SIGSEGV there): a batch whose operands fit the quota is admitted as a whole and reaches the driver as ONE batch; a batch
-    that names more than the quota can hold at once is issued copy by copy, each with its own admission. Every word arrives."""
-    code = r"""
+BATCH_COPY_SCRIPT = r"""
 import ctypes as C, json, os
 cu = C.CDLL("libcuda.so.1")
 def ck(rc, what):
@@ -781,7 +777,7 @@ f_fill, f_verify = C.c_void_p(), C.c_void_p()
 for f, nm in ((f_fill, b"vgpu_wl_fill"), (f_verify, b"vgpu_wl_verify")):
     ck(cu.cuModuleGetFunction(C.byref(f), mod, nm), nm)
 M = 1 << 20
-n, nbytes = 16, 8 * M                                        # 16 sources + 16 destinations = 256 MiB live under a 96 MiB quota
+n, nbytes = 16, int(os.environ.get("BUF_MIB", "8")) * M          # 16 sources + 16 destinations (CPU suite: 256 MiB live under a 96 MiB quota)
 def alloc():
     p = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(p), C.c_size_t(nbytes)), "alloc"); return p.value
 src, dst = [alloc() for _ in range(n)], [alloc() for _ in range(n)]
@@ -792,12 +788,19 @@ def launch(f, *vals):
 for i, p in enumerate(src):
     launch(f_fill, p, nbytes // 8, 100 + i)
 cnt = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(cnt), 8), "cnt"); ck(cu.cuMemsetD8_v2(cnt, 0, 8), "cnt0")
+class Attr(C.Structure):                                      # CUmemcpyAttributes: stream-ordered source access, no location hints
+    _fields_ = [("srcAccessOrder", C.c_int), ("srcLoc", C.c_int * 2), ("dstLoc", C.c_int * 2), ("flags", C.c_uint)]
+stream = C.c_void_p(); ck(cu.cuStreamCreate(C.byref(stream), 1), "stream")       # a batch may not go to the legacy stream
 def batch(idx):
     k = len(idx)
     d = (C.c_uint64 * k)(*[dst[i] for i in idx]); s = (C.c_uint64 * k)(*[src[i] for i in idx]); z = (C.c_size_t * k)(*[nbytes] * k)
     fail = C.c_size_t(~0 & 0xffffffffffffffff)
-    ck(cu.cuMemcpyBatchAsync(d, s, z, C.c_size_t(k), None, None, C.c_size_t(0), C.byref(fail), None), "batch")
-calls = cu.fake_batch_calls
+    attr = Attr(); attr.srcAccessOrder = 1                    # CU_MEMCPY_SRC_ACCESS_ORDER_STREAM
+    first = (C.c_size_t * 1)(0)
+    ck(cu.cuCtxSynchronize(), "sync")                         # the fills ran on the legacy stream; `stream` is non-blocking
+    ck(cu.cuMemcpyBatchAsync(d, s, z, C.c_size_t(k), C.byref(attr), first, C.c_size_t(1), C.byref(fail), stream), "batch")
+    ck(cu.cuStreamSynchronize(stream), "stream sync")
+calls = getattr(cu, "fake_batch_calls", None) or (lambda: -1)   # only the fake driver counts the batches it was handed
 batch([0, 1, 2, 3])                                           # 8 operands x 8 MiB = 64 MiB: fits, one driver batch
 after_small = calls()
 batch(list(range(4, n)))                                      # 24 operands = 192 MiB: cannot be resident at once -> single copies
@@ -822,6 +825,11 @@ bad3 = C.c_uint64(); ck(cu.cuMemcpyDtoH_v2(C.byref(bad3), cnt, 8), "read")
 # cuMemGetAddressRange answers for every swappable buffer, resident or paged out (most of these 33 are out), with the base
 # and the size the application asked for (not the 2 MiB-rounded mapping)
 odd = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(odd), C.c_size_t(5 * M + 4096)), "odd")
+class St(C.Structure):
+    _fields_ = [("v", C.c_uint64 * 17), ("pack_ms", C.c_double), ("unpack_ms", C.c_double), ("rest", C.c_uint64 * 64)]
+hook = C.CDLL(None)
+hook.vgpu_runtime_swap_stats.argtypes = [C.c_int, C.POINTER(St)]
+st = St(); ck(hook.vgpu_runtime_swap_stats(0, C.byref(st)), "stats")
 ranges_ok = 0
 for p, sz in [(q, nbytes) for q in src + dst] + [(odd.value, 5 * M + 4096)]:
     b, z = C.c_uint64(), C.c_size_t()
@@ -829,22 +837,25 @@ for p, sz in [(q, nbytes) for q in src + dst] + [(odd.value, 5 * M + 4096)]:
     ranges_ok += int(b.value == p and z.value == sz)
 b, z = C.c_uint64(), C.c_size_t()
 past_end = cu.cuMemGetAddressRange_v2(C.byref(b), C.byref(z), C.c_uint64(odd.value + 5 * M + 4096 + 8))   # inside the granule, outside the buffer
-print(json.dumps({"bad": bad.value + bad3.value, "after_small": after_small, "after_big": after_big, "ranges_ok": ranges_ok, "past_end_rc": past_end}))
+print(json.dumps({"bad": bad.value + bad3.value, "after_small": after_small, "after_big": after_big, "ranges_ok": ranges_ok, "past_end_rc": past_end,
+                  "faults": st.v[3], "evictions": st.v[2]}))
 """
+
+
+def test_batched_copies_admit_all_their_operands(tmp_path):
+    """cuMemcpyBatchAsync (CUDA 12.8) through the hook on the functional fake (an access to a paged-out range is a
+    SIGSEGV there): a batch whose operands fit the quota is admitted as a whole and reaches the driver as ONE batch; a batch
+    that names more than the quota can hold at once is issued copy by copy, each with its own admission. Every word arrives."""
+    code = BATCH_COPY_SCRIPT
     env = _env(tmp_path, LD_PRELOAD=HOOK_SO, CUDA_OVERSUBSCRIBE="true", CUDA_DEVICE_MEMORY_LIMIT_0="96m", CUBIN=CUBIN, VGPU_SWAP_CHUNK_MB="2", VGPU_SWAP_RING="2")
     r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["bad"] == 0 and out["after_small"] == 1 and out["after_big"] == 1, out
-    assert out["ranges_ok"] == 33 and out["past_end_rc"] != 0, out
+    assert out["ranges_ok"] == 33 and out["past_end_rc"] != 0 and out["faults"] > 30, out
 
 
-def test_explicitly_built_graph_keeps_its_operands_resident(tmp_path):
-    """A graph built node by node (cuGraphAddKernelNode / cuGraphAddMemsetNode — no stream capture, so no launch ever passes
-    the hook): the buffers its nodes name are pinned resident when the nodes are defined, everything else keeps cycling
-    through the quota, and replays (which touch the operands with no call into the hook; a paged-out range is a SIGSEGV on
-    the functional fake) find them in place."""
-    code = r"""
+EXPLICIT_GRAPH_SCRIPT = r"""
 import ctypes as C, json, os
 cu = C.CDLL("libcuda.so.1")
 def ck(rc, what):
@@ -857,7 +868,7 @@ f_fill, f_touch, f_verify = C.c_void_p(), C.c_void_p(), C.c_void_p()
 for f, nm in ((f_fill, b"vgpu_wl_fill"), (f_touch, b"vgpu_wl_touch"), (f_verify, b"vgpu_wl_verify")):
     ck(cu.cuModuleGetFunction(C.byref(f), mod, nm), nm)
 M = 1 << 20
-n, nbytes = 14, 16 * M                                        # 224 MiB live under a 128 MiB quota (16 MiB of it the context, 8 MiB staging)
+n, nbytes = 14, int(os.environ.get("BUF_MIB", "16")) * M         # CPU suite: 224 MiB live under a 128 MiB quota (16 MiB of it the context, 8 MiB staging)
 bufs = []
 for i in range(n):
     p = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(p), C.c_size_t(nbytes)), "alloc"); bufs.append(p.value)
@@ -922,6 +933,14 @@ ck(cu.cuMemsetD8_v2(cnt, 0, 8), "cnt0"); launch(f_verify, copy_dst.value, nbytes
 bad_copy = C.c_uint64(); ck(cu.cuMemcpyDtoH_v2(C.byref(bad_copy), cnt, 8), "read")
 print(json.dumps({"bad": bad.value, "scratch": hex(word.value), "bad_copy": bad_copy.value}))
 """
+
+
+def test_explicitly_built_graph_keeps_its_operands_resident(tmp_path):
+    """A graph built node by node (cuGraphAddKernelNode / cuGraphAddMemsetNode — no stream capture, so no launch ever passes
+    the hook): the buffers its nodes name are pinned resident when the nodes are defined, everything else keeps cycling
+    through the quota, and replays (which touch the operands with no call into the hook; a paged-out range is a SIGSEGV on
+    the functional fake) find them in place."""
+    code = EXPLICIT_GRAPH_SCRIPT
     env = _env(tmp_path, LD_PRELOAD=HOOK_SO, CUDA_OVERSUBSCRIBE="true", CUDA_DEVICE_MEMORY_LIMIT_0="128m", CUBIN=CUBIN, VGPU_SWAP_CHUNK_MB="2", VGPU_SWAP_RING="2")
     r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -929,12 +948,7 @@ print(json.dumps({"bad": bad.value, "scratch": hex(word.value), "bad_copy": bad_
     assert out == {"bad": 0, "scratch": "0xabababababababab", "bad_copy": 0}, out
 
 
-def test_host_backed_mode_runs_a_launch_whose_operands_exceed_the_quota(tmp_path):
-    """Under the reference (UVM) a kernel whose operands together exceed the quota thrashes but runs. The default engine
-    refuses such a launch (every operand must be resident while the kernel runs); in host-backed mode the operands that fit
-    are paged in and the others are used where they are — their own range maps the host backing — and only move again once
-    that use is over. Random operand sets of 1-5 buffers x 20 MiB under a 48 MiB cap, every word checked at the end."""
-    code = r"""
+OVERSIZED_LAUNCH_SCRIPT = r"""
 import ctypes as C, json, os, random, sys
 sys.path.insert(0, os.environ["VGPU_ROOT"])
 import k8s_device_plugin_b200 as v
@@ -982,6 +996,14 @@ sw.drain()
 print(json.dumps({"bad": bad.value, "refused": refused, "oversized": oversized, "inplace_uses": st["inplace_uses"], "faults": st["faults"],
                   "touches": sum(touches), "live_after": sw.stats()["live_bytes"]}))
 """
+
+
+def test_host_backed_mode_runs_a_launch_whose_operands_exceed_the_quota(tmp_path):
+    """Under the reference (UVM) a kernel whose operands together exceed the quota thrashes but runs. The default engine
+    refuses such a launch (every operand must be resident while the kernel runs); in host-backed mode the operands that fit
+    are paged in and the others are used where they are — their own range maps the host backing — and only move again once
+    that use is over. Random operand sets of 1-5 buffers x 20 MiB under a 48 MiB cap, every word checked at the end."""
+    code = OVERSIZED_LAUNCH_SCRIPT
     env = _env(tmp_path, VGPU_ROOT=ROOT, VGPU_SWAP_HOST_BACKED=1)
     r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -994,14 +1016,7 @@ print(json.dumps({"bad": bad.value, "refused": refused, "oversized": oversized, 
     assert dflt["bad"] == 0 and dflt["refused"] == out["oversized"] and dflt["inplace_uses"] == 0, dflt
 
 
-@pytest.mark.parametrize("mode", ["host_backed", "default"])
-def test_multi_operand_launches_from_several_threads(tmp_path, mode):
-    """Three application threads share one engine (64 MiB cap, 260 MiB live): each admits random sets of operands — its own
-    buffers (touched) plus buffers all threads read. Host-backed mode, 1-4 operands (4 x 20 MiB exceeds the cap): one thread
-    uses a row in place while another demands the same row resident; the pager must not move a row under a use in place.
-    Default mode, 1-3 operands: at times everything resident is pinned by the other threads' admissions — the demand then
-    waits for their release instead of failing. Every word is checked."""
-    code = r"""
+THREADED_OPERANDS_SCRIPT = r"""
 import ctypes as C, json, os, random, sys, threading
 sys.path.insert(0, os.environ["VGPU_ROOT"])
 import k8s_device_plugin_b200 as v
@@ -1051,6 +1066,16 @@ ths = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
 st = sw.stats()
 print(json.dumps({"errors": errors, "bad": sum(b.value for b in bad), "inplace_uses": st["inplace_uses"], "faults": st["faults"]}))
 """
+
+
+@pytest.mark.parametrize("mode", ["host_backed", "default"])
+def test_multi_operand_launches_from_several_threads(tmp_path, mode):
+    """Three application threads share one engine (64 MiB cap, 260 MiB live): each admits random sets of operands — its own
+    buffers (touched) plus buffers all threads read. Host-backed mode, 1-4 operands (4 x 20 MiB exceeds the cap): one thread
+    uses a row in place while another demands the same row resident; the pager must not move a row under a use in place.
+    Default mode, 1-3 operands: at times everything resident is pinned by the other threads' admissions — the demand then
+    waits for their release instead of failing. Every word is checked."""
+    code = THREADED_OPERANDS_SCRIPT
     env = _env(tmp_path, VGPU_ROOT=ROOT, VGPU_SWAP_HOST_BACKED=int(mode == "host_backed"))
     r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
