@@ -156,6 +156,9 @@ int vgpu_swap_release(vgpu_swap_t *s, const uint64_t *ptrs, int n, void *stream)
 int vgpu_swap_release_ro(vgpu_swap_t *s, const uint64_t *ptrs, int n, void *stream);
 /* cuMemAdvise(SET/UNSET_READ_MOSTLY) for a swappable buffer: kernel launches no longer mark it dirty */
 int vgpu_swap_advise_read_mostly(vgpu_swap_t *s, uint64_t ptr, int on);
+/* cuMemPrefetchAsync for a swappable buffer: to_device != 0 queues a page-in with the pager; 0 ("to the host") makes the
+ * buffer the first victim when room is needed */
+int vgpu_swap_prefetch(vgpu_swap_t *s, uint64_t ptr, int to_device);
 /* keep a buffer resident for good (operands the argument scan cannot see: device-side pointer tables) */
 int vgpu_swap_pin(vgpu_swap_t *s, uint64_t ptr, int on);
 int vgpu_swap_stats(vgpu_swap_t *s, vgpu_swap_stats_t *out);

@@ -121,6 +121,7 @@ ABI = {
     "vgpu_swap_release_ro": (_INT, [_P, C.POINTER(_U64), _INT, _P]),
     "vgpu_swap_advise_read_mostly": (_INT, [_P, _U64, _INT]),
     "vgpu_swap_pin": (_INT, [_P, _U64, _INT]),
+    "vgpu_swap_prefetch": (_INT, [_P, _U64, _INT]),
     "vgpu_swap_stats": (_INT, [_P, C.POINTER(SwapStats)]),
     "vgpu_swap_drain": (_INT, [_P]),
     "vgpu_swap_set_profile": (_INT, [_P, _INT]),
@@ -294,6 +295,10 @@ class Swap:
 
     def advise_read_mostly(self, ptr, on=True):
         _check("vgpu_swap_advise_read_mostly", lib().vgpu_swap_advise_read_mostly(self._h, ptr, int(on)))
+
+    def prefetch(self, ptr, to_device=True):
+        """cuMemPrefetchAsync's twin: queue a page-in (to_device) or make the buffer the first victim (to the host)."""
+        _check("vgpu_swap_prefetch", lib().vgpu_swap_prefetch(self._h, ptr, int(to_device)))
 
     def pin(self, ptr, on=True):
         _check("vgpu_swap_pin", lib().vgpu_swap_pin(self._h, ptr, int(on)))

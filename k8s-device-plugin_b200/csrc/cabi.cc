@@ -324,6 +324,14 @@ VGPU_API int vgpu_swap_advise_read_mostly(vgpu_swap_t *s, uint64_t ptr, int on) 
     s->e->advise_read_mostly(row, on != 0);
     return CUDA_SUCCESS;
 }
+VGPU_API int vgpu_swap_prefetch(vgpu_swap_t *s, uint64_t ptr, int to_device) {
+    if (!s) return CUDA_ERROR_INVALID_VALUE;
+    int row = s->e->lookup(ptr);
+    if (row < 0) return CUDA_ERROR_INVALID_VALUE;
+    if (to_device) s->e->hint_prefetch(row);
+    else s->e->hint_evict(row);
+    return CUDA_SUCCESS;
+}
 VGPU_API int vgpu_swap_pin(vgpu_swap_t *s, uint64_t ptr, int on) {
     if (!s) return CUDA_ERROR_INVALID_VALUE;
     int row = s->e->lookup(ptr);

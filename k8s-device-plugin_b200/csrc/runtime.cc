@@ -1104,6 +1104,7 @@ bool Runtime::swap_prefetch(CUdeviceptr p, bool to_device) {
     int row = e->lookup(p);
     if (row < 0) return false;
     if (to_device) e->hint_prefetch(row);
+    else e->hint_evict(row);                     // "to the host": the application is done with it on the device for now
     return true;
 }
 

@@ -844,6 +844,13 @@ void SwapEngine::hint_prefetch(int row) {
     queued_prefetch_bytes_ += s.mapped;
     kick_pager_locked();
 }
+void SwapEngine::hint_evict(int row) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (!row_live(row) || rows_[row].state != VGPU_ST_RESIDENT || side_[row].phase != PH_IDLE) return;   // pinned, paged out or on its way: nothing to say
+    rows_[row].last_touch = 0;                   // oldest on the LRU clock: the next scan takes it first
+    if (side_[row].prefetched) { side_[row].prefetched = false; prefetched_bytes_ -= side_[row].mapped; st_.prefetch_wasted++; }
+    mark_dirty(row);
+}
 void SwapEngine::schedule_prefetch() {
     if (!cfg_.prefetch_bytes || last_row_ < 0 || resident_mapped_ >= live_mapped_ || !predictor_confident()) return;
     uint64_t window = std::min<uint64_t>(cfg_.prefetch_bytes, cfg_.resident_cap / 4);

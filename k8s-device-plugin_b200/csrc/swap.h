@@ -128,6 +128,7 @@ class SwapEngine {
     void advise_read_mostly(int row, bool on);
     // cuMemPrefetchAsync(range, device): queue a page-in with the pager, do not wait
     void hint_prefetch(int row);
+    void hint_evict(int row);                   // cuMemPrefetchAsync(range, CU_DEVICE_CPU): first in line when room is needed
     // never evict this row (operands the argument scan cannot see: device-side pointer tables)
     CUresult pin_resident(int row, bool on);
 

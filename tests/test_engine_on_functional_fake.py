@@ -1082,3 +1082,52 @@ def test_multi_operand_launches_from_several_threads(tmp_path, mode):
     out = json.loads(r.stdout.strip().splitlines()[-1])
     assert out["errors"] == [] and out["bad"] == 0, out
     assert out["inplace_uses"] > 10 if mode == "host_backed" else out["inplace_uses"] == 0, out
+
+
+def test_prefetch_to_the_host_makes_a_buffer_the_first_victim(tmp_path):
+    """cuMemPrefetchAsync(range, CU_DEVICE_CPU) — here through its C-ABI twin — says "done with it on the device": the
+    buffer stays resident and usable, but the next eviction takes it before the least recently used one. The other
+    direction queues a page-in that completes without any touch."""
+    code = r"""
+import ctypes as C, json, os, sys, time
+sys.path.insert(0, os.environ["VGPU_ROOT"])
+import k8s_device_plugin_b200 as v
+L = v.lib()
+drv = C.CDLL("libcuda.so.1")
+assert drv.cuInit(0) == 0
+dev, ctx = C.c_int(), C.c_void_p()
+assert drv.cuDeviceGet(C.byref(dev), 0) == 0 and drv.cuDevicePrimaryCtxRetain(C.byref(ctx), dev) == 0 and drv.cuCtxSetCurrent(ctx) == 0
+M = 1 << 20
+sw = v.Swap(resident_cap=64 * M, chunk_bytes=4 * M, ring_slots=2, prefetch_bytes=None)
+n, nbytes = 6, 16 * M
+bufs = [sw.alloc(nbytes) for _ in range(n)]
+for i, p in enumerate(bufs):
+    sw.acquire([p], 0); assert L.vgpu_wl_fill(p, nbytes // 8, i, None) == 0; sw.release([p], 0)
+sw.drain()
+def resident():
+    return sorted(bufs.index(e.base) for e in sw.table() if e.state & 1)
+before = resident()                                # the four most recently filled: 2, 3, 4, 5
+sw.prefetch(bufs[5], to_device=False)              # the MOST recently used one is given up
+sw.acquire([bufs[0]], 0); assert L.vgpu_wl_touch(bufs[0], nbytes // 8, None) == 0; sw.release([bufs[0]], 0)
+sw.drain()
+after_evict_hint = resident()
+sw.prefetch(bufs[5], to_device=True)               # and asked back: paged in by the pager, nobody touches it
+for _ in range(400):
+    if 5 in resident(): break
+    time.sleep(0.005)
+after_prefetch = resident()
+cnt = C.c_uint64()
+assert drv.cuMemAlloc_v2(C.byref(cnt), 8) == 0 and drv.cuMemsetD8_v2(cnt, 0, 8) == 0
+for i, p in enumerate(bufs):
+    sw.acquire([p], 0); assert L.vgpu_wl_verify(p, nbytes // 8, i, 1 if i == 0 else 0, cnt.value, None) == 0; sw.release([p], 0)
+assert drv.cuCtxSynchronize() == 0
+bad = C.c_uint64(); assert drv.cuMemcpyDtoH_v2(C.byref(bad), cnt, 8) == 0
+print(json.dumps({"bad": bad.value, "before": before, "after_evict_hint": after_evict_hint, "after_prefetch": after_prefetch}))
+"""
+    env = _env(tmp_path, VGPU_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["bad"] == 0 and out["before"] == [2, 3, 4, 5], out
+    assert out["after_evict_hint"] == [0, 2, 3, 4], out          # 5 went, not the least recently used 2
+    assert 5 in out["after_prefetch"] and 0 in out["after_prefetch"], out
