@@ -1036,6 +1036,10 @@ bool Runtime::touch_batch(const CUdeviceptr *written, size_t nw, const CUdevicep
     if (t_touch_w.empty() && t_touch_r.empty()) return true;
     std::vector<int> all(t_touch_w);
     all.insert(all.end(), t_touch_r.begin(), t_touch_r.end());
+    if (!e->fits_together(all.data(), (int)all.size())) {       // the caller issues the copies one by one: nothing to report
+        t_touch_w.clear(); t_touch_r.clear();
+        return false;
+    }
     bool capturing = stream_is_capturing(st);
     CUresult r = e->ensure_resident(all.data(), (int)all.size(), capturing ? SwapEngine::kHostWait : st);
     if (r != CUDA_SUCCESS || capturing) {          // captured: the operands stay pinned, nothing is recorded into the capture

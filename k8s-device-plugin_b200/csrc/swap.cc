@@ -491,6 +491,14 @@ bool SwapEngine::range_of(CUdeviceptr p, CUdeviceptr *base, size_t *size) const 
     return true;
 }
 
+bool SwapEngine::fits_together(const int *rows, int n) const {
+    std::lock_guard<std::mutex> g(mu_);
+    if (cfg_.host_backed) return true;           // what does not fit is used in place
+    uint64_t sum = 0;
+    for (int i = 0; i < n; i++) if (row_live(rows[i])) sum += side_[rows[i]].mapped;
+    return sum <= (budget_fn_ && sibling_engines_ > 1 ? std::max(cfg_.resident_cap, fair_share_) : cfg_.resident_cap);
+}
+
 void SwapEngine::collect_rows(const void *param, size_t bytes, std::vector<int> *rows) const {
     if (bytes < 8) return;
     const unsigned char *b = static_cast<const unsigned char *>(param);

@@ -110,7 +110,9 @@ class SwapEngine {
     CUresult free(CUdeviceptr dptr);            // CUDA_ERROR_INVALID_VALUE when not one of ours
     bool owns(CUdeviceptr p) const { return p >= arena_ && p < arena_ + cfg_.arena_bytes; }
     int lookup(CUdeviceptr p) const;            // row index of the allocation containing p, or -1
-    bool range_of(CUdeviceptr p, CUdeviceptr *base, size_t *size) const;   // the allocation containing p as the application made it
+    bool range_of(CUdeviceptr p, CUdeviceptr *base, size_t *size) const;
+    // can these rows be resident at the same time (ensure_resident would not refuse them for their size)? no side effects
+    bool fits_together(const int *rows, int n) const;   // the allocation containing p as the application made it
 
     // Makes every listed row resident and orders `stream` after the page-ins. Rows stay pinned (not evictable)
     // until note_use() is called with the same list after the real launch has been enqueued.
