@@ -1663,7 +1663,9 @@ bool SwapEngine::step_demand(Lock &lk) {
                 return false;
             }
         }
-        LOG_ERROR("resident quota %lu MiB cannot hold the working set of this launch (need %lu MiB more, evictable %lu MiB; %d admissions in flight, waited %lu ms)",
+        if (cfg_.host_backed) LOG_INFO("no room for row %d (need %lu MiB more, evictable %lu MiB): it is used where it is (host-mapped)", row,
+                                       (unsigned long)(shortage >> 20), (unsigned long)(evictable >> 20));
+        else LOG_ERROR("resident quota %lu MiB cannot hold the working set of this launch (need %lu MiB more, evictable %lu MiB; %d admissions in flight, waited %lu ms)",
                   (unsigned long)(cfg_.resident_cap >> 20), (unsigned long)(shortage >> 20), (unsigned long)(evictable >> 20), open_admissions_,
                   (unsigned long)(demand_row_ == row ? (mono_ns() - demand_since_ns_) / 1000000 : 0));
         if (std::getenv("VGPU_SWAP_DEBUG_DUMP"))
@@ -1983,24 +1985,23 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
             }
         }
         uint64_t need = 0, pinned = 0;
-        for (int r : missing) need += side_[r].mapped;
         for (int i = 0; i < n; i++) if (rows_[rows[i]].state & VGPU_ST_RESIDENT) pinned += side_[rows[i]].mapped;
         // with sibling engines the cap moves (they give room up as they see our demand): judge against the fair share then
         const uint64_t room = budget_fn_ && sibling_engines_ > 1 ? std::max(cfg_.resident_cap, fair_share_) : cfg_.resident_cap;
         std::vector<int> inplace;
-        if (need + pinned > room && cfg_.host_backed) {
+        if (cfg_.host_backed) {
             // Host-backed mode: a launch whose operands do not fit the quota together still runs (under UVM, the reference's
             // swap, it would thrash but work): as many operands as fit are paged in, in argument order; the others are used
             // WHERE THEY ARE — a paged-out row's own range maps its host backing — at PCIe speed. The pager leaves such a row
-            // alone until this use has been recorded and has completed (Side::inplace, load_direct).
+            // alone until this use has been recorded and has completed (Side::inplace, load_direct). A row that somebody is
+            // using in place right now (or for good: a captured graph's operand) cannot move: it is used in place here too.
             uint64_t take = pinned;
             std::vector<int> fit;
             for (int r : missing) {
-                if (take + side_[r].mapped <= room) { take += side_[r].mapped; fit.push_back(r); }
+                if (side_[r].inplace == 0 && take + side_[r].mapped <= room) { take += side_[r].mapped; fit.push_back(r); }
                 else inplace.push_back(r);
             }
             missing.swap(fit);
-            need = take - pinned;
             for (int r : inplace) {
                 Side &s = side_[r];
                 s.inplace++;
@@ -2009,6 +2010,7 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
             st_.inplace_uses += inplace.size();
             st_.faults -= inplace.size();
         }
+        for (int r : missing) need += side_[r].mapped;
         if (need + pinned > room) {
             LOG_ERROR("resident quota %lu MiB cannot hold the working set of this launch (%lu MiB)", (unsigned long)(cfg_.resident_cap >> 20),
                       (unsigned long)((need + pinned) >> 20));
@@ -2034,8 +2036,17 @@ CUresult SwapEngine::ensure_resident(const int *rows, int n, CUstream stream) {
                 });
             }
             for (int r : missing) {
+                Side &s = side_[r];
                 if (rows_[r].state & VGPU_ST_RESIDENT) rows_[r].state = VGPU_ST_RESIDENT | VGPU_ST_PINNED;
-                else if (rc == CUDA_SUCCESS) rc = side_[r].fail != CUDA_SUCCESS ? side_[r].fail : CUDA_ERROR_OUT_OF_MEMORY;
+                else if (cfg_.host_backed && s.fail == CUDA_ERROR_OUT_OF_MEMORY && s.hosted && s.phase == PH_IDLE) {
+                    // no room could be made for it (what is resident is pinned — other launches in flight, captured graphs'
+                    // operands): host-backed mode uses it where it is instead of failing
+                    s.inplace++;
+                    st_.inplace_uses++;
+                    st_.faults--;
+                    inplace.push_back(r);
+                }
+                else if (rc == CUDA_SUCCESS) rc = s.fail != CUDA_SUCCESS ? s.fail : CUDA_ERROR_OUT_OF_MEMORY;
                 mark_dirty(r);
             }
             if (!inplace.empty()) {

@@ -297,7 +297,9 @@ EXPORT CUresult cuStreamDestroy_v2(CUstream s) { (void)s; return CUDA_SUCCESS; }
 EXPORT CUresult cuStreamSynchronize(CUstream s) { (void)s; return CUDA_SUCCESS; }
 EXPORT CUresult cuStreamQuery(CUstream s) { (void)s; return CUDA_SUCCESS; }
 EXPORT CUresult cuStreamWaitEvent(CUstream s, CUevent e, unsigned f) { (void)s; (void)e; (void)f; return CUDA_SUCCESS; }
-EXPORT CUresult cuStreamIsCapturing(CUstream s, int *status) { (void)s; if (status) *status = 0; return CUDA_SUCCESS; }
+static int g_capturing;                                          /* tests switch "a capture is active" on and off; the work still executes */
+EXPORT void fake_set_capturing(int on) { g_capturing = on; }
+EXPORT CUresult cuStreamIsCapturing(CUstream s, int *status) { (void)s; if (status) *status = g_capturing ? 1 : 0; return CUDA_SUCCESS; }
 /* work completes at call time: an event is the clock at record time */
 EXPORT CUresult cuEventCreate(CUevent *e, unsigned f) { (void)f; return fx_event_create(e); }
 EXPORT CUresult cuEventRecord(CUevent e, CUstream s) { (void)s; return fx_event_record(e); }

@@ -1131,3 +1131,55 @@ print(json.dumps({"bad": bad.value, "before": before, "after_evict_hint": after_
     assert out["bad"] == 0 and out["before"] == [2, 3, 4, 5], out
     assert out["after_evict_hint"] == [0, 2, 3, 4], out          # 5 went, not the least recently used 2
     assert 5 in out["after_prefetch"] and 0 in out["after_prefetch"], out
+
+
+def test_an_operand_captured_in_place_stays_usable_in_place(tmp_path):
+    """Host-backed mode, through the hook: a kernel launched into a capturing stream names two buffers that do not fit the
+    quota together. The one that fits is pinned resident, the other is pinned IN PLACE — for good, a replay may come at any
+    time. A later, ordinary launch that names only that buffer must neither wait for it to become resident (it never will)
+    nor move it: it uses it in place as well."""
+    code = r"""
+import ctypes as C, json, os
+cu = C.CDLL("libcuda.so.1")
+def ck(rc, what):
+    assert rc == 0, (what, rc)
+ck(cu.cuInit(0), "init")
+dev, ctx, mod = C.c_int(), C.c_void_p(), C.c_void_p()
+ck(cu.cuDeviceGet(C.byref(dev), 0), "dev"); ck(cu.cuDevicePrimaryCtxRetain(C.byref(ctx), dev), "ctx"); ck(cu.cuCtxSetCurrent(ctx), "cur")
+ck(cu.cuModuleLoad(C.byref(mod), os.environ["CUBIN"].encode()), "mod")
+f = {}
+for nm in (b"vgpu_wl_fill", b"vgpu_wl_touch", b"vgpu_wl_verify", b"vgpu_copy16"):
+    f[nm] = C.c_void_p(); ck(cu.cuModuleGetFunction(C.byref(f[nm]), mod, nm), nm)
+M = 1 << 20
+nbytes = 32 * M                                               # quota 64 MiB = 16 context + 8 staging + 40: ONE such buffer fits
+def alloc():
+    p = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(p), C.c_size_t(nbytes)), "alloc"); return p.value
+a, b, other = alloc(), alloc(), alloc()
+def launch(fn, *vals):
+    holders = [C.c_uint64(v) for v in vals]
+    arr = (C.c_void_p * len(holders))(*[C.cast(C.byref(h), C.c_void_p) for h in holders])
+    ck(cu.cuLaunchKernel(f[fn], 64, 1, 1, 256, 1, 1, 0, None, arr, None), fn)
+launch(b"vgpu_wl_fill", a, nbytes // 8, 1); launch(b"vgpu_wl_fill", b, nbytes // 8, 2); launch(b"vgpu_wl_fill", other, nbytes // 8, 3)
+cu.fake_set_capturing(1)
+launch(b"vgpu_copy16", a, b, nbytes // 16)                   # "captured": a := b; a is pinned resident, b in place
+cu.fake_set_capturing(0)
+launch(b"vgpu_wl_touch", b, nbytes // 8)                      # b alone: would fit — but it may not move any more
+launch(b"vgpu_wl_touch", other, nbytes // 8)                  # everything else still pages through what is left
+launch(b"vgpu_wl_touch", b, nbytes // 8)
+cnt = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(cnt), 8), "cnt"); ck(cu.cuMemsetD8_v2(cnt, 0, 8), "cnt0")
+launch(b"vgpu_wl_verify", a, nbytes // 8, 2, 0, cnt.value)    # the copy of b as it was
+launch(b"vgpu_wl_verify", b, nbytes // 8, 2, 2, cnt.value)
+launch(b"vgpu_wl_verify", other, nbytes // 8, 3, 1, cnt.value)
+ck(cu.cuCtxSynchronize(), "sync")
+bad = C.c_uint64(); ck(cu.cuMemcpyDtoH_v2(C.byref(bad), cnt, 8), "read")
+class St(C.Structure):
+    _fields_ = [("v", C.c_uint64 * 17), ("pack_ms", C.c_double), ("unpack_ms", C.c_double), ("rest", C.c_uint64 * 64)]
+hook = C.CDLL(None); hook.vgpu_runtime_swap_stats.argtypes = [C.c_int, C.POINTER(St)]
+st = St(); ck(hook.vgpu_runtime_swap_stats(0, C.byref(st)), "stats")
+print(json.dumps({"bad": bad.value}))
+"""
+    env = _env(tmp_path, LD_PRELOAD=HOOK_SO, CUDA_OVERSUBSCRIBE="true", CUDA_DEVICE_MEMORY_LIMIT_0="64m", CUBIN=CUBIN, VGPU_SWAP_CHUNK_MB="2", VGPU_SWAP_RING="2",
+               VGPU_SWAP_HOST_BACKED="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert json.loads(r.stdout.strip().splitlines()[-1]) == {"bad": 0}
