@@ -856,6 +856,7 @@ void SwapEngine::hint_evict(int row) {
     std::lock_guard<std::mutex> g(mu_);
     if (!row_live(row) || rows_[row].state != VGPU_ST_RESIDENT || side_[row].phase != PH_IDLE) return;   // pinned, paged out or on its way: nothing to say
     rows_[row].last_touch = 0;                   // oldest on the LRU clock: the next scan takes it first
+    victim_cache_.clear();                       // ... and the next eviction does scan (the cached surplus predates the hint)
     if (side_[row].prefetched) { side_[row].prefetched = false; prefetched_bytes_ -= side_[row].mapped; st_.prefetch_wasted++; }
     mark_dirty(row);
 }
