@@ -157,9 +157,9 @@ void Runtime::on_exit() {
                 std::fprintf(stderr, "[vgpu-b200 stats] swap dev %d pager vmm ms: unmap=%.1f setaccess=%.1f map=%.1f create=%.1f | issue=%.1f | steps zombies=%.1f reap=%.1f demand=%.1f prefetch=%.1f evict=%.1f\n", d, s.pager_unmap_ns / 1e6,
                              s.pager_setaccess_ns / 1e6, s.pager_map_ns / 1e6, s.pager_create_ns / 1e6, s.pager_issue_ns / 1e6, s.pager_step_ns[0] / 1e6, s.pager_step_ns[1] / 1e6,
                              s.pager_step_ns[2] / 1e6, s.pager_step_ns[3] / 1e6, s.pager_step_ns[4] / 1e6);
-                std::fprintf(stderr, "[vgpu-b200 stats] swap dev %d: prefetch issued=%lu hits=%lu wasted=%lu demand_waits=%lu clean_evictions=%lu direct in=%lu out=%lu\n", d,
+                std::fprintf(stderr, "[vgpu-b200 stats] swap dev %d: prefetch issued=%lu hits=%lu wasted=%lu demand_waits=%lu clean_evictions=%lu inplace_uses=%lu direct in=%lu out=%lu\n", d,
                              (unsigned long)s.prefetch_issued, (unsigned long)s.prefetch_hits, (unsigned long)s.prefetch_wasted, (unsigned long)s.demand_waits,
-                             (unsigned long)s.clean_evictions, (unsigned long)s.direct_in_bytes, (unsigned long)s.direct_out_bytes);
+                             (unsigned long)s.clean_evictions, (unsigned long)s.inplace_uses, (unsigned long)s.direct_in_bytes, (unsigned long)s.direct_out_bytes);
                 std::fprintf(stderr, "[vgpu-b200 stats] swap dev %d: in=%lu out=%lu faults=%lu evictions=%lu scans=%lu cache_hits=%lu creates=%lu reuses=%lu\n", d,
                              (unsigned long)s.page_in_bytes, (unsigned long)s.page_out_bytes, (unsigned long)s.faults, (unsigned long)s.evictions,
                              (unsigned long)s.scans, (unsigned long)s.scan_cache_hits, (unsigned long)s.phys_creates, (unsigned long)s.phys_reuses);
