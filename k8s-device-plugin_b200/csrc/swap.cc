@@ -1640,7 +1640,12 @@ bool SwapEngine::step_demand(Lock &lk) {
     if (r != CUDA_SUCCESS) return fail(r);
     // the lock was released during the scan: the world may have moved on
     if (demand_q_.empty() || demand_q_.front().row != row || side_[row].phase != PH_QUEUED) return true;
-    if (evictable < shortage && release_epoch_ != epoch_before) return true;   // pins were released while the scan ran: it saw them, look again
+    if (evictable < shortage) {
+        if (demand_row_ != row) { demand_row_ = row; demand_since_ns_ = mono_ns(); }
+        // pins were released while the scan ran: it saw them, look again (bounded like the waits below: another thread that
+        // launches on resident buffers in a tight loop releases pins all the time without ever making room)
+        if (release_epoch_ != epoch_before && mono_ns() - demand_since_ns_ < 2000000000ull) return true;
+    }
     if (evictable < shortage) {
         bool in_flight = evicting_mapped_ > 0 || !zombies_.empty();
         if (in_flight) return false;
