@@ -9,7 +9,7 @@ import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.join(_PKG_DIR, "lib")
-CORE_SO = os.path.join(LIB_DIR, "libvgpu_core.so")
+CORE_SO = os.environ.get("VGPU_CORE_SO") or os.path.join(LIB_DIR, "libvgpu_core.so")   # (override: sanitizer builds, tests/tools/asan_check.sh)
 HOOK_SO = os.path.join(LIB_DIR, "libvgpu.so")
 
 MAX_DEVICES = 16

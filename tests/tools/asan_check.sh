@@ -54,5 +54,17 @@ run $SW CUDA_DEVICE_MEMORY_LIMIT_0=256m VGPU_SWAP_PREFETCH_MB=0 -- $SB --buffers
 run $SW CUDA_DEVICE_MEMORY_LIMIT_0=256m VGPU_SWAP_HOST_BACKED=1 -- $SB --buffers 24 --steps 72 --order zipf
 run FAKE_GPU_EXEC=1 CUDA_DEVICE_SM_LIMIT=30 GPU_CORE_UTILIZATION_POLICY=force CUDA_DEVICE_MEMORY_LIMIT_0=1g -- $P/lib/launch_loop $P/build/vgpu_kernels.cubin 8 2
 run $SW CUDA_DEVICE_MEMORY_LIMIT_0=128m -- $R/oracle/_ref/hook_stress swap 4 80
+# the C-ABI engine driven from three Python threads with shared operands (host-backed: operands used in place; default: demands
+# that wait for other threads' pins) — same objects linked as libvgpu_core.so, loaded by the package through VGPU_CORE_SO
+g++ -shared -fsanitize=thread -L$TS -Wl,-soname,libvgpu_core.so -o $TS/libvgpu_core.so $TS/{driver,region,kmod,swap,limiter,runtime,cabi,plugin_core,sched_core,hook,passthrough}.o $P/build/kernels_cubin.o -ldl -lpthread || exit 1
+python - > $T/threaded.py <<'PY'
+import sys
+sys.path.insert(0, "tests")
+import test_engine_on_functional_fake as t
+print(t.THREADED_OPERANDS_SCRIPT + "\nsw.close()\n")
+PY
+for hb in 1 0; do n=$((n+1)); env FAKE_GPU_EXEC=1 VGPU_SWAP_CHUNK_MB=4 VGPU_SWAP_ARENA_GB=8 VGPU_SWAP_SLAB_MB=64 VGPU_SWAP_SPARE_MB=16 VGPU_SWAP_HOST_BACKED=$hb VGPU_ROOT=$R \
+  VGPU_CORE_SO=$TS/libvgpu_core.so CUDA_DEVICE_MEMORY_SHARED_CACHE=$T/c$n.cache LD_PRELOAD=$L/libtsan.so.2 python $T/threaded.py > $T/out$n.txt 2>&1
+  echo "  [$n] rc=$? $(tail -c 120 $T/out$n.txt | tr '\n' ' ' | cut -c1-100)"; done
 if ls $T/tsan.* > /dev/null 2>&1; then echo "TSAN REPORTS:"; head -80 $T/tsan.*; exit 1; fi
 echo "no TSan reports"; rm -rf $T
