@@ -1084,11 +1084,7 @@ def test_multi_operand_launches_from_several_threads(tmp_path, mode):
     assert out["inplace_uses"] > 10 if mode == "host_backed" else out["inplace_uses"] == 0, out
 
 
-def test_prefetch_to_the_host_makes_a_buffer_the_first_victim(tmp_path):
-    """cuMemPrefetchAsync(range, CU_DEVICE_CPU) — here through its C-ABI twin — says "done with it on the device": the
-    buffer stays resident and usable, but the next eviction takes it before the least recently used one. The other
-    direction queues a page-in that completes without any touch."""
-    code = r"""
+PREFETCH_HINT_SCRIPT = r"""
 import ctypes as C, json, os, sys, time
 sys.path.insert(0, os.environ["VGPU_ROOT"])
 import k8s_device_plugin_b200 as v
@@ -1124,6 +1120,13 @@ assert drv.cuCtxSynchronize() == 0
 bad = C.c_uint64(); assert drv.cuMemcpyDtoH_v2(C.byref(bad), cnt, 8) == 0
 print(json.dumps({"bad": bad.value, "before": before, "after_evict_hint": after_evict_hint, "after_prefetch": after_prefetch}))
 """
+
+
+def test_prefetch_to_the_host_makes_a_buffer_the_first_victim(tmp_path):
+    """cuMemPrefetchAsync(range, CU_DEVICE_CPU) — here through its C-ABI twin — says "done with it on the device": the
+    buffer stays resident and usable, but the next eviction takes it before the least recently used one. The other
+    direction queues a page-in that completes without any touch."""
+    code = PREFETCH_HINT_SCRIPT
     env = _env(tmp_path, VGPU_ROOT=ROOT)
     r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]

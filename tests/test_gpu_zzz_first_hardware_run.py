@@ -17,7 +17,7 @@ torch = pytest.importorskip("torch")
 import k8s_device_plugin_b200 as v  # noqa: E402
 from conftest import CUBIN, ROOT  # noqa: E402
 from test_engine_on_functional_fake import (BATCH_COPY_SCRIPT, EXPLICIT_GRAPH_SCRIPT, OVERSIZED_LAUNCH_SCRIPT,  # noqa: E402
-                                            THREADED_OPERANDS_SCRIPT)
+                                            PREFETCH_HINT_SCRIPT, THREADED_OPERANDS_SCRIPT)
 
 FIRST_RUN = pytest.mark.xfail(strict=False, reason="developed on the functional fake after the round's GPU budget was spent: first run on hardware")
 
@@ -69,3 +69,12 @@ def test_explicitly_built_graph_replays_with_its_operands_pinned(tmp_path):
     env = v.hook_env(limit_mib=1500, oversubscribe=True, cache_path=str(tmp_path / "graph.cache"), extra={"BUF_MIB": "64"})
     out = _run(EXPLICIT_GRAPH_SCRIPT, env)
     assert out == {"bad": 0, "scratch": "0xabababababababab", "bad_copy": 0}, out
+
+
+@FIRST_RUN
+def test_prefetch_hints_steer_the_pager():
+    """C ABI twin of cuMemPrefetchAsync: "to the host" makes the most recently used buffer the next victim, "to the device"
+    pages it back in without a touch."""
+    out = _run(PREFETCH_HINT_SCRIPT, {"VGPU_SWAP_CHUNK_MB": 4})
+    assert out["bad"] == 0 and out["before"] == [2, 3, 4, 5] and out["after_evict_hint"] == [0, 2, 3, 4], out
+    assert 5 in out["after_prefetch"] and 0 in out["after_prefetch"], out
