@@ -990,7 +990,19 @@ CUresult Runtime::mem_unmap(CUdeviceptr ptr, size_t size) {
     return r;
 }
 
-static thread_local std::vector<int> t_touch_w, t_touch_r;   // rows pinned between touch_range*() and touch_done(): written / only read
+// Rows pinned between touch_range*() / touch_batch() and touch_done(). A copy can touch two engines: a peer copy between
+// two devices of the container, or any copy issued while another device's context is current — every pointer is looked
+// up in the engine whose arena holds it, not in the current device's.
+struct TouchRef { SwapEngine *e; int row; bool writes; };
+static thread_local std::vector<TouchRef> t_touch;
+
+SwapEngine *Runtime::engine_of(CUdeviceptr p) {
+    if (!p) return nullptr;
+    for (int d = 0; d < VGPU_MAX_DEVICES; d++)
+        if (SwapEngine *e = swap_[d].get())
+            if (e->owns(p)) return e;
+    return nullptr;
+}
 
 void Runtime::touch_range(CUdeviceptr p, size_t bytes, CUstream st, bool writes) {
     if (writes) touch_range2(p, bytes, 0, 0, st);
@@ -999,70 +1011,82 @@ void Runtime::touch_range(CUdeviceptr p, size_t bytes, CUstream st, bool writes)
 
 void Runtime::touch_range2(CUdeviceptr dst, size_t dbytes, CUdeviceptr src, size_t sbytes, CUstream st) {
     if (!cfg_.oversubscribe) return;
-    int dev = current_device();
-    SwapEngine *e = swap(dev);
-    if (!e) return;
-    int rows[2]; int n = 0;
     (void)dbytes; (void)sbytes;
-    int rd = dst ? e->lookup(dst) : -1, rs = src ? e->lookup(src) : -1;
-    if (rd >= 0) rows[n++] = rd;
-    if (rs >= 0 && rs != rd) rows[n++] = rs;
-    if (!n) return;
-    if (stream_is_capturing(st)) {   // captured copy node: operands pinned resident, nothing recorded into the capture
-        if (e->ensure_resident(rows, n, SwapEngine::kHostWait) != CUDA_SUCCESS) LOG_ERROR("captured memcpy/memset target could not be made resident");
+    SwapEngine *ed = engine_of(dst), *es = engine_of(src);
+    int rd = ed ? ed->lookup(dst) : -1, rs = es ? es->lookup(src) : -1;
+    if (rd < 0 && rs < 0) return;
+    const bool capturing = stream_is_capturing(st);   // captured copy node: operands pinned resident, nothing recorded into the capture
+    CUstream how = capturing ? SwapEngine::kHostWait : st;
+    t_touch.clear();
+    auto admit = [&](SwapEngine *e, const int *rows, int n) {
+        if (e->ensure_resident(rows, n, how) != CUDA_SUCCESS) { LOG_ERROR("memcpy/memset operand could not be made resident"); return false; }
+        return true;
+    };
+    if (rd >= 0 && rs >= 0 && ed == es) {
+        int rows[2] = {rd, rs};
+        if (!admit(ed, rows, rd == rs ? 1 : 2) || capturing) return;
+        t_touch.push_back(TouchRef{ed, rd, true});
+        if (rs != rd) t_touch.push_back(TouchRef{es, rs, false});
         return;
     }
-    if (e->ensure_resident(rows, n, st) != CUDA_SUCCESS) { LOG_ERROR("memcpy/memset target could not be made resident"); return; }
+    // one operand, or two operands in two engines: one admission per engine
+    if (rd >= 0 && admit(ed, &rd, 1) && !capturing) t_touch.push_back(TouchRef{ed, rd, true});
+    if (rs >= 0 && admit(es, &rs, 1) && !capturing) t_touch.push_back(TouchRef{es, rs, false});
     // the copy itself is enqueued by the caller right after this returns; note_use after it keeps the rows pinned
-    t_touch_w.clear(); t_touch_r.clear();
-    if (rd >= 0) t_touch_w.push_back(rd);
-    if (rs >= 0 && rs != rd) t_touch_r.push_back(rs);
 }
 
 bool Runtime::touch_batch(const CUdeviceptr *written, size_t nw, const CUdeviceptr *read, size_t nr, CUstream st) {
-    t_touch_w.clear(); t_touch_r.clear();
+    t_touch.clear();
     if (!cfg_.oversubscribe) return true;
-    SwapEngine *e = swap(current_device());
-    if (!e) return true;
+    SwapEngine *e = nullptr;
+    bool several = false;
+    std::vector<int> w, r;
     auto add = [&](std::vector<int> &v, CUdeviceptr p) {
-        if (!p || !e->owns(p)) return;
-        int r = e->lookup(p);
-        if (r < 0) return;
-        if (std::find(t_touch_w.begin(), t_touch_w.end(), r) != t_touch_w.end()) return;     // written wins over read
-        if (std::find(v.begin(), v.end(), r) == v.end()) v.push_back(r);
+        SwapEngine *pe = engine_of(p);
+        if (!pe) return;
+        if (e && pe != e) { several = true; return; }
+        e = pe;
+        int row = e->lookup(p);
+        if (row < 0) return;
+        if (std::find(w.begin(), w.end(), row) != w.end()) return;     // written wins over read
+        if (std::find(v.begin(), v.end(), row) == v.end()) v.push_back(row);
     };
-    for (size_t i = 0; i < nw; i++) add(t_touch_w, written[i]);
-    for (size_t i = 0; i < nr; i++) add(t_touch_r, read[i]);
-    if (t_touch_w.empty() && t_touch_r.empty()) return true;
-    std::vector<int> all(t_touch_w);
-    all.insert(all.end(), t_touch_r.begin(), t_touch_r.end());
-    if (!e->fits_together(all.data(), (int)all.size())) {       // the caller issues the copies one by one: nothing to report
-        t_touch_w.clear(); t_touch_r.clear();
-        return false;
-    }
+    for (size_t i = 0; i < nw; i++) add(w, written[i]);
+    for (size_t i = 0; i < nr; i++) add(r, read[i]);
+    if (several) return false;                     // operands in two engines: the caller issues the copies one by one
+    if (w.empty() && r.empty()) return true;
+    std::vector<int> all(w);
+    all.insert(all.end(), r.begin(), r.end());
+    if (!e->fits_together(all.data(), (int)all.size())) return false;       // likewise: nothing to report
     bool capturing = stream_is_capturing(st);
-    CUresult r = e->ensure_resident(all.data(), (int)all.size(), capturing ? SwapEngine::kHostWait : st);
-    if (r != CUDA_SUCCESS || capturing) {          // captured: the operands stay pinned, nothing is recorded into the capture
-        t_touch_w.clear(); t_touch_r.clear();
-        return r == CUDA_SUCCESS;
-    }
+    CUresult rc = e->ensure_resident(all.data(), (int)all.size(), capturing ? SwapEngine::kHostWait : st);
+    if (rc != CUDA_SUCCESS) return false;
+    if (capturing) return true;                    // captured: the operands stay pinned, nothing is recorded into the capture
+    for (int row : w) t_touch.push_back(TouchRef{e, row, true});
+    for (int row : r) t_touch.push_back(TouchRef{e, row, false});
     return true;                                   // touch_done() after the real call unpins and records the use
 }
 
 void Runtime::touch_done(CUstream st) {
-    if (t_touch_w.empty() && t_touch_r.empty()) return;
-    int dev = current_device();
-    if (SwapEngine *e = swap(dev)) {
-        if (!t_touch_w.empty()) e->note_use(t_touch_w.data(), (int)t_touch_w.size(), st, true);
-        if (!t_touch_r.empty()) e->note_use(t_touch_r.data(), (int)t_touch_r.size(), st, false, /*closes_admission=*/t_touch_w.empty());
+    if (t_touch.empty()) return;
+    // per engine: its written rows, then its read-only rows (one admission each: the second call does not close another)
+    while (!t_touch.empty()) {
+        SwapEngine *e = t_touch.front().e;
+        std::vector<int> w, r;
+        for (auto it = t_touch.begin(); it != t_touch.end();) {
+            if (it->e != e) { ++it; continue; }
+            (it->writes ? w : r).push_back(it->row);
+            it = t_touch.erase(it);
+        }
+        if (!w.empty()) e->note_use(w.data(), (int)w.size(), st, true);
+        if (!r.empty()) e->note_use(r.data(), (int)r.size(), st, false, /*closes_admission=*/w.empty());
     }
-    t_touch_w.clear(); t_touch_r.clear();
 }
 
 bool Runtime::swap_advise(CUdeviceptr p, CUmem_advise advice) {
     if (!cfg_.oversubscribe) return false;
-    SwapEngine *e = swap(current_device());
-    if (!e || !e->owns(p)) return false;
+    SwapEngine *e = engine_of(p);
+    if (!e) return false;
     int row = e->lookup(p);
     if (row < 0) return false;
     // the only advice with a meaning for explicit paging: a read-mostly range is not dirtied by kernel launches, so
@@ -1084,27 +1108,27 @@ CUresult Runtime::pin_graph_kernel(CUfunction f, void **params, void **extra) {
 
 CUresult Runtime::pin_graph_ptrs(const CUdeviceptr *p, size_t n) {
     if (!cfg_.oversubscribe) return CUDA_SUCCESS;
-    SwapEngine *e = swap(current_device());
-    if (!e) return CUDA_SUCCESS;
-    std::vector<int> rows;
-    for (size_t i = 0; i < n; i++) {
-        int r = p[i] ? e->lookup(p[i]) : -1;
-        if (r >= 0 && std::find(rows.begin(), rows.end(), r) == rows.end()) rows.push_back(r);
+    CUresult rc = CUDA_SUCCESS;
+    for (size_t i = 0; i < n; i++) {               // one admission per pointer: the operands of a copy node may live in two engines
+        SwapEngine *e = engine_of(p[i]);
+        int r = e ? e->lookup(p[i]) : -1;
+        if (r < 0 || (i > 0 && p[i] == p[i - 1])) continue;
+        CUresult one = e->ensure_resident(&r, 1, SwapEngine::kHostWait);
+        if (one != CUDA_SUCCESS) rc = one;
     }
-    if (rows.empty()) return CUDA_SUCCESS;
-    return e->ensure_resident(rows.data(), (int)rows.size(), SwapEngine::kHostWait);
+    return rc;
 }
 
 bool Runtime::swap_address_range(CUdeviceptr p, CUdeviceptr *base, size_t *size) {
     if (!cfg_.oversubscribe) return false;
-    SwapEngine *e = swap(current_device());
+    SwapEngine *e = engine_of(p);
     return e && e->range_of(p, base, size);
 }
 
 bool Runtime::swap_prefetch(CUdeviceptr p, bool to_device) {
     if (!cfg_.oversubscribe) return false;
-    SwapEngine *e = swap(current_device());
-    if (!e || !e->owns(p)) return false;
+    SwapEngine *e = engine_of(p);
+    if (!e) return false;
     int row = e->lookup(p);
     if (row < 0) return false;
     if (to_device) e->hint_prefetch(row);

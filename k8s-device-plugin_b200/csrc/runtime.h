@@ -103,6 +103,7 @@ class Runtime {
     // operands named by a node are made resident when the node is defined and stay pinned (same rule as stream capture).
     CUresult pin_graph_kernel(CUfunction f, void **params, void **extra);
     CUresult pin_graph_ptrs(const CUdeviceptr *p, size_t n);
+    SwapEngine *engine_of(CUdeviceptr p);         // the engine (of whichever device) whose arena holds p, or null
     bool swap_address_range(CUdeviceptr p, CUdeviceptr *base, size_t *size);   // true: p is a swappable buffer, answered from the table
     void touch_done(CUstream st);   // after the real copy has been enqueued: unpins + records the use
     // Batched copies (cuMemcpyBatchAsync / cuMemcpy3DBatchAsync, CUDA 12.8): every swappable operand of the batch is admitted

@@ -326,6 +326,8 @@ EXPORT CUresult cuMemcpyBatchAsync(CUdeviceptr *d, CUdeviceptr *s, size_t *n, si
     if (fake_exec_on()) for (size_t i = 0; i < count; i++) memmove((void *)(uintptr_t)d[i], (const void *)(uintptr_t)s[i], n[i]);
     return CUDA_SUCCESS;
 }
+EXPORT CUresult cuMemcpyPeer(CUdeviceptr d, CUcontext dc, CUdeviceptr s, CUcontext sc, size_t n) { (void)dc; (void)sc; FX_ONLY(memmove((void *)(uintptr_t)d, (const void *)(uintptr_t)s, n)); }
+EXPORT CUresult cuMemcpyPeerAsync(CUdeviceptr d, CUcontext dc, CUdeviceptr s, CUcontext sc, size_t n, CUstream st) { (void)dc; (void)sc; (void)st; FX_ONLY(memmove((void *)(uintptr_t)d, (const void *)(uintptr_t)s, n)); }
 EXPORT CUresult cuMemsetD8_v2(CUdeviceptr d, unsigned char v, size_t n) { FX_ONLY(memset((void *)(uintptr_t)d, v, n)); }
 EXPORT CUresult cuMemsetD8Async(CUdeviceptr d, unsigned char v, size_t n, CUstream st) { (void)st; FX_ONLY(memset((void *)(uintptr_t)d, v, n)); }
 EXPORT CUresult cuMemsetD16_v2(CUdeviceptr d, unsigned short v, size_t n) { FX_ONLY(for (size_t i = 0; i < n; i++) ((unsigned short *)(uintptr_t)d)[i] = v); }

@@ -1186,3 +1186,59 @@ print(json.dumps({"bad": bad.value}))
     r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
     assert r.returncode == 0, r.stderr[-3000:]
     assert json.loads(r.stdout.strip().splitlines()[-1]) == {"bad": 0}
+
+
+def test_copies_between_two_gpus_admit_each_operand_in_its_own_engine(tmp_path):
+    """One process, two GPUs, each with its own quota and engine (a multi-GPU container has one limit lane per
+    device). A device-to-device copy whose destination lives on GPU 1 and whose source lives on GPU 0 — both paged out at
+    the time, issued while GPU 0's context is current — must page each operand in through the engine that owns it; so must
+    a pointer query and a prefetch hint for a GPU-1 buffer given from GPU 0's context."""
+    code = r"""
+import ctypes as C, json, os
+cu = C.CDLL("libcuda.so.1")
+def ck(rc, what):
+    assert rc == 0, (what, rc)
+ck(cu.cuInit(0), "init")
+ctx, mod, f = [C.c_void_p(), C.c_void_p()], [C.c_void_p(), C.c_void_p()], [{}, {}]
+for d in (0, 1):
+    dev = C.c_int(); ck(cu.cuDeviceGet(C.byref(dev), d), "dev"); ck(cu.cuDevicePrimaryCtxRetain(C.byref(ctx[d]), dev), "ctx"); ck(cu.cuCtxSetCurrent(ctx[d]), "cur")
+    ck(cu.cuModuleLoad(C.byref(mod[d]), os.environ["CUBIN"].encode()), "mod")
+    for nm in (b"vgpu_wl_fill", b"vgpu_wl_touch", b"vgpu_wl_verify"):
+        f[d][nm] = C.c_void_p(); ck(cu.cuModuleGetFunction(C.byref(f[d][nm]), mod[d], nm), nm)
+M = 1 << 20
+n, nbytes = 8, 16 * M                                         # per GPU: 128 MiB live under a 64 MiB quota
+def launch(d, fn, *vals):
+    holders = [C.c_uint64(v) for v in vals]
+    arr = (C.c_void_p * len(holders))(*[C.cast(C.byref(h), C.c_void_p) for h in holders])
+    ck(cu.cuLaunchKernel(f[d][fn], 64, 1, 1, 256, 1, 1, 0, None, arr, None), fn)
+bufs = [[], []]
+for d in (0, 1):
+    ck(cu.cuCtxSetCurrent(ctx[d]), "cur")
+    for i in range(n):
+        p = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(p), C.c_size_t(nbytes)), "alloc"); bufs[d].append(p.value)
+        launch(d, b"vgpu_wl_fill", p.value, nbytes // 8, 100 * d + i)
+# the first buffers of both GPUs are paged out by now (8 filled through room for ~2)
+ck(cu.cuCtxSetCurrent(ctx[0]), "cur")
+ck(cu.cuMemcpyDtoD_v2(C.c_uint64(bufs[1][0]), C.c_uint64(bufs[0][1]), C.c_size_t(nbytes)), "peer copy, sync")            # GPU1[0] := GPU0[1]
+ck(cu.cuMemcpyPeerAsync(C.c_uint64(bufs[1][1]), ctx[1], C.c_uint64(bufs[0][2]), ctx[0], C.c_size_t(nbytes), None), "peer copy, async")   # GPU1[1] := GPU0[2]
+mt = C.c_uint(); ck(cu.cuPointerGetAttribute(C.byref(mt), 2, C.c_uint64(bufs[1][2])), "query a GPU-1 buffer from GPU 0's context")
+base, size = C.c_uint64(), C.c_size_t()
+ck(cu.cuMemGetAddressRange_v2(C.byref(base), C.byref(size), C.c_uint64(bufs[1][3] + 8)), "range of a GPU-1 buffer")
+dev1 = C.c_int(1)
+ck(cu.cuMemPrefetchAsync(C.c_uint64(bufs[1][4]), C.c_size_t(nbytes), dev1, None), "prefetch a GPU-1 buffer")
+ck(cu.cuCtxSynchronize(), "sync")
+cnt = C.c_uint64(); ck(cu.cuMemAlloc_v2(C.byref(cnt), 8), "cnt"); ck(cu.cuMemsetD8_v2(cnt, 0, 8), "cnt0")
+expect = {(1, 0): 1, (1, 1): 2}                               # (gpu, index) -> fill id of the GPU-0 buffer it was overwritten with
+for d in (0, 1):
+    ck(cu.cuCtxSetCurrent(ctx[d]), "cur")
+    for i, p in enumerate(bufs[d]):
+        launch(d, b"vgpu_wl_verify", p, nbytes // 8, expect.get((d, i), 100 * d + i), 0, cnt.value)
+    ck(cu.cuCtxSynchronize(), "sync")
+bad = C.c_uint64(); ck(cu.cuMemcpyDtoH_v2(C.byref(bad), cnt, 8), "read")
+print(json.dumps({"bad": bad.value, "memory_type": mt.value, "range_ok": base.value == bufs[1][3] and size.value == nbytes}))
+"""
+    env = _env(tmp_path, LD_PRELOAD=HOOK_SO, CUDA_OVERSUBSCRIBE="true", CUDA_DEVICE_MEMORY_LIMIT_0="64m", CUDA_DEVICE_MEMORY_LIMIT_1="64m", FAKE_GPU_COUNT=2,
+               CUBIN=CUBIN, VGPU_SWAP_CHUNK_MB="2", VGPU_SWAP_RING="2")
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert json.loads(r.stdout.strip().splitlines()[-1]) == {"bad": 0, "memory_type": 2, "range_ok": True}
