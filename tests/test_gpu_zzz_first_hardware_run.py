@@ -22,7 +22,7 @@ from test_engine_on_functional_fake import (BATCH_COPY_SCRIPT, EXPLICIT_GRAPH_SC
 FIRST_RUN = pytest.mark.xfail(strict=False, reason="developed on the functional fake after the round's GPU budget was spent: first run on hardware")
 
 
-def _run(code, env_extra, timeout=300):
+def _run(code, env_extra, timeout=120):
     env = dict(os.environ)
     env.pop("LD_PRELOAD", None)
     env.update({"LIBCUDA_LOG_LEVEL": "2", "VGPU_ROOT": ROOT, "CUBIN": CUBIN})
@@ -48,7 +48,7 @@ def test_default_mode_refuses_exactly_the_oversized_launches():
 @FIRST_RUN
 @pytest.mark.parametrize("mode", ["host_backed", "default"])
 def test_multi_operand_launches_from_three_threads(mode):
-    out = _run(THREADED_OPERANDS_SCRIPT, {"VGPU_SWAP_HOST_BACKED": int(mode == "host_backed"), "VGPU_SWAP_CHUNK_MB": 4}, timeout=600)
+    out = _run(THREADED_OPERANDS_SCRIPT, {"VGPU_SWAP_HOST_BACKED": int(mode == "host_backed"), "VGPU_SWAP_CHUNK_MB": 4}, timeout=180)
     assert out["errors"] == [] and out["bad"] == 0, out
     assert out["inplace_uses"] > 10 if mode == "host_backed" else out["inplace_uses"] == 0, out
 
